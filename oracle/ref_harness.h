@@ -1,0 +1,62 @@
+/*
+ * ref_harness.h — C entry points of oracle/_ref/libssba_ref.so  (TEST INFRASTRUCTURE).
+ *
+ * libssba_ref.so is the REFERENCE ITSELF: the vendored g2o core + CSparse solver + CSparse C
+ * sources and ssvio's include/ssvio/g2otypes.hpp, compiled from /root/reference by
+ * oracle/Makefile, plus ref_harness.cpp which replays the graph construction of
+ * src/ssvio/backend.cpp:81-178 over flat arrays (backend.cpp itself needs OpenCV / glog /
+ * Pangolin, which this image does not have).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load it.  The product (libssba.so) never does.
+ */
+#ifndef SSBA_REF_HARNESS_H
+#define SSBA_REF_HARNESS_H
+
+#include <stdint.h>
+#include "ssba.h" /* ssba_report / ssba_iter_record layouts are shared with the product ABI */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* per-phase wall time summed over iterations, from g2o::G2OBatchStatistics
+ * (thirdparty/g2o/g2o/core/batch_stats.h:40-77); only when collect_trace != 0 */
+typedef struct ssba_ref_stats {
+  double t_residuals, t_quadratic_form, t_schur, t_linear_solver, t_linear_solution, t_update;
+  double t_initialize; /* initializeOptimization() wall time */
+  double t_graph_build; /* new Vertex/Edge + addVertex/addEdge wall time */
+  int64_t cholesky_nnz;
+  int32_t n_active_edges, n_index_mapping;
+} ssba_ref_stats;
+
+/*
+ * Build the g2o graph exactly as Backend::OptimizeActiveMap() does and run
+ * initializeOptimization(); optimize(max_iters).  Argument layout = include/ssba.h.
+ *
+ *   jacobian_mode  0 = analytic (corrected closed form, subclass override of linearizeOplus)
+ *                  1 = numeric central differences = the reference AS SHIPPED
+ *   collect_trace  1 = record chi2/lambda/trials per iteration (adds one computeActiveErrors per
+ *                      iteration, so do not use for timing), 0 = timing run
+ *   rounds         number of initializeOptimization()+optimize() rounds of backend.cpp:175-203
+ *                  (<=0 or 1: one round, no inlier-ratio rule); with rounds > 1 the loop stops
+ *                  early when the inlier ratio exceeds 0.7 like the reference
+ * Outputs may be NULL.  report->seconds_total = wall time of the optimize() calls only,
+ * report->seconds_setup = graph construction + initializeOptimization().
+ * Returns 0 on success.
+ */
+int ssba_ref_optimize(const double K[9], int32_t n_cams, const double *ext_qt,
+                      int32_t n_poses, const double *poses_qt, const uint8_t *pose_fixed,
+                      int32_t n_points, const double *points, const uint8_t *point_fixed,
+                      int32_t n_edges, const int32_t *pose_idx, const int32_t *point_idx,
+                      const uint8_t *cam_idx, const double *uv, double huber_delta,
+                      int32_t max_iters, int32_t jacobian_mode, int32_t collect_trace,
+                      int32_t rounds, double outlier_chi2_threshold,
+                      double *poses_out, double *points_out, double *edge_err_out,
+                      ssba_report *report, ssba_ref_stats *stats, int32_t *rounds_done,
+                      int64_t *n_outliers);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
