@@ -1,0 +1,638 @@
+// ssba_api.cu — the C ABI of include/ssba.h: handle life cycle, graph upload, the LM driver that
+// enqueues trial slots on a CUDA stream, result read-back, multi-GPU plumbing (NCCL, loaded with
+// dlopen only when world_size > 1).  No CPU compute path exists here: without a CUDA device
+// ssba_create() fails.
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "ssba.h"
+#include "ssba_device.hpp"
+#include "ssba_structure.hpp"
+
+using namespace ssba;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+using Clock = std::chrono::steady_clock;
+inline double secs(Clock::time_point a, Clock::time_point b) {
+  return std::chrono::duration<double>(b - a).count();
+}
+
+// ---- NCCL, resolved at run time (torch's bundled libnccl.so.2 when it is already in the
+// process, the system one otherwise); only the handful of entry points the path needs.
+struct Nccl {
+  void *lib = nullptr;
+  typedef struct { char internal[128]; } UniqueId;
+  int (*GetUniqueId)(UniqueId *) = nullptr;
+  int (*CommInitRank)(void **, int, UniqueId, int) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool load(std::string &err) {
+    if (lib) return true;
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+    AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) { err = "libnccl lacks required symbols"; return false; }
+    return true;
+  }
+};
+Nccl g_nccl;
+constexpr int kNcclDouble = 8;  // ncclFloat64
+constexpr int kNcclSum = 0, kNcclMax = 2;
+
+inline size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+
+}  // namespace
+
+struct ssba_handle {
+  ssba_options opt{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string error;
+  HostGraph g;
+  Structure s;
+  bool dirty = true;        // graph changed since the last ssba_initialize
+  bool initialized = false;
+  // memory: one device arena (static index data first, then work buffers) + pinned mirror of
+  // the static part so a whole graph goes up in one copy
+  char *d_arena = nullptr; size_t d_arena_bytes = 0;
+  char *h_stage = nullptr; size_t h_stage_bytes = 0;
+  Control *h_ctl = nullptr;   // pinned
+  double *h_small = nullptr;  // pinned scratch (8 doubles)
+  DeviceProblem P{};
+  int cur = 0;
+  double lambda = -1.0, ni = 2.0;
+  size_t device_bytes = 0;
+  void *comm = nullptr;
+  // profiling
+  ssba_profile prof{};
+  std::vector<cudaEvent_t> ev;
+  size_t ev_used = 0;
+  struct Span { size_t a, b; int phase; };
+  std::vector<Span> spans;
+  double setup_seconds = 0.0;
+};
+
+namespace {
+
+#define CUDA_TRY(h, expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      (h)->error = std::string(#expr) + ": " + cudaGetErrorString(_e);                      \
+      return SSBA_ERR_CUDA;                                                                 \
+    }                                                                                       \
+  } while (0)
+
+ssba_status fail(ssba_handle *h, ssba_status st, const std::string &msg) {
+  if (h) h->error = msg; else g_create_error = msg;
+  return st;
+}
+
+ssba_status nccl_allreduce(ssba_handle *h, double *buf, size_t n, int op) {
+  int rc = g_nccl.AllReduce(buf, buf, n, kNcclDouble, op, h->comm, h->stream);
+  if (rc != 0) return fail(h, SSBA_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+  h->prof.kernel_launches += 0;
+  return SSBA_OK;
+}
+
+cudaEvent_t next_event(ssba_handle *h) {
+  if (h->ev_used == h->ev.size()) {
+    cudaEvent_t e; cudaEventCreate(&e); h->ev.push_back(e);
+  }
+  return h->ev[h->ev_used++];
+}
+
+struct PhaseTimer {  // records a CUDA-event span on the launch stream when profiling is on
+  ssba_handle *h; int phase; size_t a = 0;
+  PhaseTimer(ssba_handle *h_, int phase_) : h(h_), phase(phase_) {
+    if (h->opt.profile) { a = h->ev_used; cudaEventRecord(next_event(h), h->stream); }
+  }
+  ~PhaseTimer() {
+    if (h->opt.profile) { size_t b = h->ev_used; cudaEventRecord(next_event(h), h->stream); h->spans.push_back({a, b, phase}); }
+  }
+};
+
+void collect_profile(ssba_handle *h) {
+  if (!h->opt.profile) return;
+  for (auto &sp : h->spans) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[sp.a], h->ev[sp.b]);
+    switch (sp.phase) {
+      case 0: h->prof.ms_linearize += ms; h->prof.n_linearize++; break;
+      case 1: h->prof.ms_schur += ms; h->prof.n_schur++; break;
+      case 2: h->prof.ms_reduced_solve += ms; h->prof.n_reduced_solve++; break;
+      case 3: h->prof.ms_update_chi2 += ms; h->prof.n_update_chi2++; break;
+      case 4: h->prof.ms_allreduce += ms; h->prof.n_allreduce++; break;
+    }
+  }
+  h->spans.clear();
+  h->ev_used = 0;
+}
+
+// one LM trial, stream-ordered; `first` = first slot of an optimize()/step(0) call
+ssba_status enqueue_slot(ssba_handle *h, bool first) {
+  const DeviceProblem &P = h->P;
+  cudaStream_t st = h->stream;
+  const bool multi = h->opt.world_size > 1;
+  ssba_status rc;
+  {
+    PhaseTimer t(h, 0);
+    launch_linearize(P, st);
+    h->prof.kernel_launches += 3;
+  }
+  if (first) {
+    if (multi) { PhaseTimer t(h, 4); if ((rc = nccl_allreduce(h, P.diag_buf, 6 * (size_t)P.n_fp, kNcclSum))) return rc; }
+    launch_maxdiag(P, st);
+    if (multi) { PhaseTimer t(h, 4); if ((rc = nccl_allreduce(h, P.scal + 3, 1, kNcclMax))) return rc; }
+    launch_lambda_init(P, st);
+    h->prof.kernel_launches += 2;
+  }
+  {
+    PhaseTimer t(h, 1);
+    launch_prepare_system(P, st);
+    launch_schur(P, st);
+    h->prof.kernel_launches += 2;
+  }
+  if (multi) { PhaseTimer t(h, 4); if ((rc = nccl_allreduce(h, P.sys, P.sys_doubles, kNcclSum))) return rc; }
+  {
+    PhaseTimer t(h, 2);
+    launch_reduced_solve(P, st);
+    h->prof.kernel_launches += 1;
+  }
+  {
+    PhaseTimer t(h, 3);
+    launch_update(P, st);
+    launch_reduce_partials(P, st);
+    h->prof.kernel_launches += 2;
+  }
+  if (multi) { PhaseTimer t(h, 4); if ((rc = nccl_allreduce(h, P.scal, 3, kNcclSum))) return rc; }
+  launch_control(P, st);
+  h->prof.kernel_launches += 1;
+  return SSBA_OK;
+}
+
+// run outer iterations until Control::done; returns with h->h_ctl holding the final controller
+ssba_status run_lm(ssba_handle *h, int max_iters, bool iteration0) {
+  Control &c = *h->h_ctl;
+  std::memset(&c, 0, sizeof(c));
+  c.tau = h->opt.tau; c.good_lower = h->opt.good_step_lower_scale; c.good_upper = h->opt.good_step_upper_scale;
+  c.user_lambda = h->opt.user_lambda_init; c.max_trials = h->opt.max_trials_after_failure;
+  c.lambda = h->lambda; c.ni = h->ni;
+  c.cur = h->cur; c.need_linearize = 1; c.first_iteration = iteration0 ? 1 : 0;
+  c.max_iters = max_iters; c.last_result = SSBA_SOLVER_OK;
+  c.world = h->opt.world_size; c.rank = h->opt.rank;
+  CUDA_TRY(h, cudaMemcpyAsync(h->P.ctl, &c, sizeof(Control), cudaMemcpyHostToDevice, h->stream));
+  // the copy above must have left the pinned buffer before it is reused for the read-back
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  bool first = true;
+  int guard = 0;
+  const int max_slots = max_iters * (c.max_trials > 0 ? c.max_trials : 1) + 1;
+  while (true) {
+    // optimistic batch: one slot per outstanding outer iteration (every trial accepted)
+    int batch = max_iters - c.outer_iter;
+    if (batch < 1) batch = 1;
+    for (int i = 0; i < batch; ++i) {
+      ssba_status rc = enqueue_slot(h, first);
+      if (rc) return rc;
+      first = false;
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(&c, h->P.ctl, sizeof(Control), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaGetLastError());
+    if (c.done) break;
+    guard += batch;
+    if (guard > max_slots) return fail(h, SSBA_ERR_STATE, "LM driver did not terminate");
+  }
+  h->cur = c.cur; h->lambda = c.lambda; h->ni = c.ni;
+  collect_profile(h);
+  return SSBA_OK;
+}
+
+ssba_status final_chi2(ssba_handle *h, double threshold, double out[4]) {
+  launch_final_chi2(h->P, threshold, h->stream);
+  h->prof.kernel_launches += 2;
+  if (h->opt.world_size > 1) { ssba_status rc = nccl_allreduce(h, h->P.chi_out, 4, kNcclSum); if (rc) return rc; }
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_small, h->P.chi_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < 4; ++i) out[i] = h->h_small[i];
+  return SSBA_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+
+extern "C" {
+
+int32_t ssba_version(void) { return SSBA_VERSION_MAJOR * 100 + SSBA_VERSION_MINOR; }
+
+void ssba_default_options(ssba_options *o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->tau = 1e-5;
+  o->good_step_lower_scale = 1. / 3.;
+  o->good_step_upper_scale = 2. / 3.;
+  o->user_lambda_init = 0.0;
+  o->max_trials_after_failure = 10;
+  o->jacobian_mode = SSBA_JACOBIAN_ANALYTIC;
+  o->device_id = -1;
+  o->world_size = 1;
+}
+
+const char *ssba_last_error(const ssba_handle *h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+ssba_status ssba_nccl_unique_id(uint8_t out[SSBA_NCCL_ID_BYTES]) {
+  std::string err;
+  if (!g_nccl.load(err)) return fail(nullptr, SSBA_ERR_NCCL, err);
+  Nccl::UniqueId id;
+  if (g_nccl.GetUniqueId(&id) != 0) return fail(nullptr, SSBA_ERR_NCCL, "ncclGetUniqueId failed");
+  std::memcpy(out, id.internal, SSBA_NCCL_ID_BYTES);
+  return SSBA_OK;
+}
+
+ssba_status ssba_create(const ssba_options *opt, ssba_handle **out) {
+  if (!out) return fail(nullptr, SSBA_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  ssba_options o;
+  if (opt) o = *opt; else ssba_default_options(&o);
+  if (o.world_size < 1 || o.rank < 0 || o.rank >= o.world_size) return fail(nullptr, SSBA_ERR_INVALID_ARG, "bad rank/world_size");
+  if (o.max_trials_after_failure < 1) return fail(nullptr, SSBA_ERR_INVALID_ARG, "max_trials_after_failure < 1");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, SSBA_ERR_NO_DEVICE, std::string("no CUDA device: libssba has no CPU path (") +
+                                                 (ce != cudaSuccess ? cudaGetErrorString(ce) : "0 devices") + ")");
+  }
+  std::unique_ptr<ssba_handle> h(new ssba_handle);
+  h->opt = o;
+  if (o.device_id >= 0) {
+    if (o.device_id >= ndev) return fail(nullptr, SSBA_ERR_INVALID_ARG, "device_id out of range");
+    h->device = o.device_id;
+  } else if (cudaGetDevice(&h->device) != cudaSuccess) {
+    return fail(nullptr, SSBA_ERR_CUDA, "cudaGetDevice failed");
+  }
+  if (cudaSetDevice(h->device) != cudaSuccess) return fail(nullptr, SSBA_ERR_CUDA, "cudaSetDevice failed");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) return fail(nullptr, SSBA_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major < 10) return fail(nullptr, SSBA_ERR_NO_DEVICE, "libssba is built for sm_100a (Blackwell) only");
+  if (o.stream) { h->stream = (cudaStream_t)o.stream; }
+  else {
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(nullptr, SSBA_ERR_CUDA, "cudaStreamCreate failed");
+    h->own_stream = true;
+  }
+  if (cudaHostAlloc((void **)&h->h_ctl, sizeof(Control), cudaHostAllocDefault) != cudaSuccess ||
+      cudaHostAlloc((void **)&h->h_small, 64 * sizeof(double), cudaHostAllocDefault) != cudaSuccess)
+    return fail(nullptr, SSBA_ERR_ALLOC, "cudaHostAlloc failed");
+  if (o.world_size > 1) {
+    std::string err;
+    if (!g_nccl.load(err)) return fail(nullptr, SSBA_ERR_NCCL, err);
+    Nccl::UniqueId id;
+    std::memcpy(id.internal, o.nccl_id, SSBA_NCCL_ID_BYTES);
+    int rc = g_nccl.CommInitRank(&h->comm, o.world_size, id, o.rank);
+    if (rc != 0) return fail(nullptr, SSBA_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+  }
+  *out = h.release();
+  return SSBA_OK;
+}
+
+void ssba_destroy(ssba_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm) g_nccl.CommDestroy(h->comm);
+  for (auto e : h->ev) cudaEventDestroy(e);
+  if (h->d_arena) cudaFree(h->d_arena);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  if (h->h_small) cudaFreeHost(h->h_small);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+ssba_status ssba_set_cameras(ssba_handle *h, const double K[9], int32_t n_cams, const double *ext_qt) {
+  if (!h) return SSBA_ERR_INVALID_ARG;
+  if (!K || !ext_qt || n_cams < 1 || n_cams > SSBA_MAX_CAMERAS) return fail(h, SSBA_ERR_INVALID_ARG, "set_cameras: bad arguments");
+  std::memcpy(h->g.cams.K, K, 9 * sizeof(double));
+  std::memcpy(h->g.cams.ext, ext_qt, 7 * sizeof(double) * n_cams);
+  h->g.cams.n = n_cams;
+  h->g.have_cams = true;
+  h->dirty = true;
+  return SSBA_OK;
+}
+
+ssba_status ssba_set_poses(ssba_handle *h, int32_t n, const double *qt, const uint8_t *fixed) {
+  if (!h) return SSBA_ERR_INVALID_ARG;
+  if (n < 0 || (n > 0 && !qt)) return fail(h, SSBA_ERR_INVALID_ARG, "set_poses: bad arguments");
+  h->g.n_poses = n;
+  h->g.poses.assign(qt, qt + 7 * (size_t)n);
+  if (fixed) h->g.pose_fixed.assign(fixed, fixed + n); else h->g.pose_fixed.assign(n, 0);
+  h->dirty = true;
+  return SSBA_OK;
+}
+
+ssba_status ssba_set_points(ssba_handle *h, int32_t n, const double *xyz, const uint8_t *fixed) {
+  if (!h) return SSBA_ERR_INVALID_ARG;
+  if (n < 0 || (n > 0 && !xyz)) return fail(h, SSBA_ERR_INVALID_ARG, "set_points: bad arguments");
+  h->g.n_points = n;
+  h->g.points.assign(xyz, xyz + 3 * (size_t)n);
+  if (fixed) h->g.point_fixed.assign(fixed, fixed + n); else h->g.point_fixed.assign(n, 0);
+  h->dirty = true;
+  return SSBA_OK;
+}
+
+ssba_status ssba_set_edges(ssba_handle *h, int32_t n, const int32_t *pose_idx, const int32_t *point_idx,
+                           const uint8_t *cam_idx, const double *uv, const double *info,
+                           const double *huber_delta, double huber_delta_all) {
+  if (!h) return SSBA_ERR_INVALID_ARG;
+  if (n < 0 || (n > 0 && (!pose_idx || !point_idx || !uv))) return fail(h, SSBA_ERR_INVALID_ARG, "set_edges: bad arguments");
+  HostGraph &g = h->g;
+  g.n_edges = n;
+  g.e_pose.assign(pose_idx, pose_idx + n);
+  g.e_point.assign(point_idx, point_idx + n);
+  if (cam_idx) g.e_cam.assign(cam_idx, cam_idx + n); else g.e_cam.assign(n, 0);
+  g.e_uv.assign(uv, uv + 2 * (size_t)n);
+  if (info) g.e_info.assign(info, info + 3 * (size_t)n); else g.e_info.clear();
+  if (huber_delta) g.e_delta.assign(huber_delta, huber_delta + n); else g.e_delta.clear();
+  g.delta_all = huber_delta_all;
+  h->dirty = true;
+  return SSBA_OK;
+}
+
+ssba_status ssba_initialize(ssba_handle *h) {
+  if (!h) return SSBA_ERR_INVALID_ARG;
+  auto t0 = Clock::now();
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  HostGraph &g = h->g;
+  if ((int)g.pose_fixed.size() != g.n_poses || (int)g.point_fixed.size() != g.n_points)
+    return fail(h, SSBA_ERR_STATE, "initialize: vertices not set");
+  if (g.n_edges == 0) {
+    // SparseOptimizer::initializeOptimization: "Attempt to initialize an empty graph"
+    // (sparse_optimizer.cpp:202-205) -> optimize() then returns -1
+    h->initialized = false;
+    return fail(h, SSBA_ERR_EMPTY, "initialize: empty graph (no edges)");
+  }
+  std::string err;
+  Structure &s = h->s;
+  if (!build_structure(g, h->opt.rank, h->opt.world_size, s, err)) return fail(h, SSBA_ERR_INVALID_ARG, err);
+  if (s.n_fp + s.n_fl_global == 0) { h->initialized = false; return fail(h, SSBA_ERR_EMPTY, "initialize: 0 vertices to optimize"); }
+
+  // ---- plan the arena: static (uploaded) part first, then work buffers
+  struct Item { const void *src; size_t bytes; size_t off; void **dst; };
+  std::vector<Item> items;
+  size_t top = 0;
+  DeviceProblem &P = h->P;
+  std::memset(&P, 0, sizeof(P));
+  auto stat = [&](const void *src, size_t bytes, const void **dst) {
+    if (bytes == 0) { *dst = nullptr; return; }
+    Item it{src, bytes, align_up(top), (void **)dst};
+    top = it.off + bytes;
+    items.push_back(it);
+  };
+#define STAT(vec, field) stat((vec).data(), (vec).size() * sizeof((vec)[0]), (const void **)&P.field)
+  STAT(g.poses, pose0); STAT(g.points, point0);
+  STAT(s.slot_vertex, slot_vertex); STAT(s.slot_free, slot_free); STAT(s.slot_pair_ptr, slot_pair_ptr);
+  STAT(s.slot_combo_ptr, slot_combo_ptr); STAT(s.combo_blk, combo_blk);
+  STAT(s.pair_vertex, pair_vertex); STAT(s.pair_q, pair_q); STAT(s.pair_edge_ptr, pair_edge_ptr);
+  STAT(s.e_uv, e_uv); STAT(s.e_info, e_info); STAT(s.e_delta, e_delta); STAT(s.e_cam, e_cam); STAT(s.e_orig, e_orig);
+  STAT(s.chunk_q, chunk_q); STAT(s.chunk_vertex, chunk_vertex); STAT(s.chunk_edge_ptr, chunk_edge_ptr);
+  STAT(s.q_chunk_ptr, q_chunk_ptr); STAT(s.pm_point, pm_point); STAT(s.pm_uv, pm_uv); STAT(s.pm_info, pm_info);
+  STAT(s.pm_delta, pm_delta); STAT(s.pm_cam, pm_cam); STAT(s.pose_of_q, pose_of_q);
+  STAT(s.col_ptr, col_ptr); STAT(s.blk_row, blk_row); STAT(s.blk_col, blk_col); STAT(s.upd_ptr, upd_ptr);
+  STAT(s.upd_dst, upd_dst); STAT(s.upd_a, upd_a); STAT(s.upd_b, upd_b); STAT(s.row_ptr, row_ptr);
+  STAT(s.row_blk, row_blk); STAT(s.row_col, row_col); STAT(s.level_ptr, level_ptr); STAT(s.level_col, level_col);
+#undef STAT
+  const size_t static_bytes = align_up(top);
+  std::vector<Item> work;
+  auto dyn = [&](size_t bytes, void **dst) {
+    Item it{nullptr, bytes, align_up(top), dst};
+    top = it.off + (bytes ? bytes : 8);
+    work.push_back(it);
+  };
+  const int nblk = (s.n_slots + 127) / 128 > 0 ? (s.n_slots + 127) / 128 : 1;
+  P.n_lin_blocks = P.n_upd_blocks = nblk;
+  P.sys_doubles = 36 * (size_t)s.n_blocks + 12 * (size_t)s.n_fp;
+#define DYN(field, count, type) dyn((size_t)(count) * sizeof(type), (void **)&P.field)
+  DYN(pose[0], 7 * g.n_poses, double); DYN(pose[1], 7 * g.n_poses, double);
+  DYN(point[0], 3 * (size_t)g.n_points, double); DYN(point[1], 3 * (size_t)g.n_points, double);
+  DYN(W, 18 * (size_t)s.n_pairs, double); DYN(Hll, 6 * (size_t)s.n_slots, double); DYN(bl, 3 * (size_t)s.n_slots, double);
+  DYN(Dinv, 6 * (size_t)s.n_slots, double); DYN(hpp_part, 27 * (size_t)s.n_chunks, double); DYN(hpp, 27 * (size_t)s.n_fp, double);
+  DYN(sys, P.sys_doubles, double); DYN(xp, 6 * (size_t)s.n_fp, double); DYN(diag_buf, 6 * (size_t)s.n_fp, double);
+  DYN(chi_cur_part, nblk, double); DYN(maxdiag_part, nblk, double); DYN(chi_new_part, nblk, double); DYN(scale_part, nblk, double);
+  DYN(scal, 8, double); DYN(chi_out, 8, double); DYN(err_out, 2 * (size_t)g.n_edges, double);
+  DYN(ctl, 1, Control);
+#undef DYN
+  const size_t total = align_up(top);
+  if (total > h->d_arena_bytes) {
+    if (h->d_arena) cudaFree(h->d_arena);
+    h->d_arena = nullptr; h->d_arena_bytes = 0;
+    const size_t want = total + total / 4;
+    if (cudaMalloc((void **)&h->d_arena, want) != cudaSuccess) { cudaGetLastError(); return fail(h, SSBA_ERR_ALLOC, "cudaMalloc failed"); }
+    h->d_arena_bytes = want;
+  }
+  if (static_bytes > h->h_stage_bytes) {
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    h->h_stage = nullptr; h->h_stage_bytes = 0;
+    const size_t want = static_bytes + static_bytes / 4;
+    if (cudaHostAlloc((void **)&h->h_stage, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return fail(h, SSBA_ERR_ALLOC, "cudaHostAlloc failed"); }
+    h->h_stage_bytes = want;
+  }
+  for (auto &it : items) { std::memcpy(h->h_stage + it.off, it.src, it.bytes); *it.dst = h->d_arena + it.off; }
+  for (auto &it : work) *it.dst = h->d_arena + it.off;
+  h->device_bytes = total;
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_arena, h->h_stage, static_bytes, cudaMemcpyHostToDevice, h->stream));
+
+  P.cams = g.cams;
+  for (int c = 0; c < g.cams.n; ++c) quat_to_matrix(g.cams.ext[c], P.ext_R[c]);
+  P.jacobian_mode = h->opt.jacobian_mode;
+  P.delta_all = g.delta_all;
+  P.n_poses = g.n_poses; P.n_points = g.n_points; P.n_fp = s.n_fp; P.n_slots = s.n_slots; P.n_pairs = s.n_pairs;
+  P.n_edges = s.n_edges; P.n_blocks = s.n_blocks; P.n_chunks = s.n_chunks; P.n_levels = s.n_levels;
+  P.n_edges_total = g.n_edges;
+  h->initialized = true;
+  h->dirty = false;
+  ssba_status rc = ssba_reset_state(h);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // h_stage may be rewritten by the next initialize
+  h->setup_seconds = secs(t0, Clock::now());
+  return SSBA_OK;
+}
+
+ssba_status ssba_reset_state(ssba_handle *h) {
+  if (!h) return SSBA_ERR_INVALID_ARG;
+  if (!h->initialized) return fail(h, SSBA_ERR_STATE, "reset_state: not initialised");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const DeviceProblem &P = h->P;
+  const size_t pb = 7 * sizeof(double) * (size_t)P.n_poses, lb = 3 * sizeof(double) * (size_t)P.n_points;
+  for (int k = 0; k < 2; ++k) {
+    if (pb) CUDA_TRY(h, cudaMemcpyAsync(P.pose[k], P.pose0, pb, cudaMemcpyDeviceToDevice, h->stream));
+    if (lb) CUDA_TRY(h, cudaMemcpyAsync(P.point[k], P.point0, lb, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  h->cur = 0; h->lambda = -1.0; h->ni = 2.0;
+  // the controller must name buffer 0 for the read-out kernels even before the first optimize
+  std::memset(h->h_ctl, 0, sizeof(Control));
+  h->h_ctl->world = h->opt.world_size; h->h_ctl->rank = h->opt.rank;
+  CUDA_TRY(h, cudaMemcpyAsync(P.ctl, h->h_ctl, sizeof(Control), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return SSBA_OK;
+}
+
+static ssba_status ensure_ready(ssba_handle *h) {
+  if (h->dirty || !h->initialized) return ssba_initialize(h);
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return SSBA_OK;
+}
+
+ssba_status ssba_optimize(ssba_handle *h, int32_t max_iters, ssba_report *report) {
+  if (!h) return SSBA_ERR_INVALID_ARG;
+  auto t0 = Clock::now();
+  if (report) std::memset(report, 0, sizeof(*report));
+  if (max_iters > SSBA_MAX_ITER_RECORDS) return fail(h, SSBA_ERR_INVALID_ARG, "optimize: max_iters too large");
+  h->setup_seconds = 0.0;
+  ssba_status rc = ensure_ready(h);
+  if (rc == SSBA_ERR_EMPTY) { if (report) { report->iterations = -1; report->last_result = SSBA_SOLVER_FAIL; } return rc; }
+  if (rc) return rc;
+  if (max_iters <= 0) {  // optimize(0): the loop body never runs (sparse_optimizer.cpp:387)
+    if (report) { report->iterations = 0; report->last_result = SSBA_SOLVER_OK; }
+    return SSBA_OK;
+  }
+  rc = run_lm(h, max_iters, true);
+  if (rc) return rc;
+  if (report) {
+    const Control &c = *h->h_ctl;
+    double f[4];
+    rc = final_chi2(h, 0.0, f);
+    if (rc) return rc;
+    report->iterations = c.outer_iter;
+    report->last_result = c.last_result;
+    report->n_records = c.n_records;
+    report->cholesky_failures = c.cholesky_failures;
+    report->chi2_initial = c.chi2_initial;
+    report->chi2_plain = f[0];
+    report->chi2_robust = f[1];
+    report->lambda = c.lambda;
+    std::memcpy(report->iters, c.records, sizeof(ssba_iter_record) * c.n_records);
+    report->seconds_setup = h->setup_seconds;
+    report->seconds_total = secs(t0, Clock::now());
+  }
+  return SSBA_OK;
+}
+
+ssba_status ssba_step(ssba_handle *h, int32_t iteration, int32_t *solver_result, ssba_iter_record *record) {
+  if (!h) return SSBA_ERR_INVALID_ARG;
+  ssba_status rc = ensure_ready(h);
+  if (rc) return rc;
+  if (iteration > 0 && h->lambda < 0) return fail(h, SSBA_ERR_STATE, "step: iteration > 0 before iteration 0");
+  rc = run_lm(h, 1, iteration == 0);
+  if (rc) return rc;
+  const Control &c = *h->h_ctl;
+  if (solver_result) *solver_result = c.last_result;
+  if (record && c.n_records > 0) *record = c.records[c.n_records - 1];
+  return SSBA_OK;
+}
+
+ssba_status ssba_get_poses(ssba_handle *h, double *out) {
+  if (!h || !out) return SSBA_ERR_INVALID_ARG;
+  if (!h->initialized) {  // nothing ran: the estimates are the ones that were set
+    if ((int)h->g.poses.size() != 7 * h->g.n_poses) return fail(h, SSBA_ERR_STATE, "get_poses: no poses");
+    std::memcpy(out, h->g.poses.data(), h->g.poses.size() * sizeof(double));
+    return SSBA_OK;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  CUDA_TRY(h, cudaMemcpyAsync(out, h->P.pose[h->cur], 7 * sizeof(double) * (size_t)h->P.n_poses, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return SSBA_OK;
+}
+
+ssba_status ssba_get_points(ssba_handle *h, double *out) {
+  if (!h || !out) return SSBA_ERR_INVALID_ARG;
+  if (!h->initialized) {
+    if ((int)h->g.points.size() != 3 * h->g.n_points) return fail(h, SSBA_ERR_STATE, "get_points: no points");
+    std::memcpy(out, h->g.points.data(), h->g.points.size() * sizeof(double));
+    return SSBA_OK;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  if (h->opt.world_size > 1) return fail(h, SSBA_ERR_STATE, "get_points: use ssba_get_points on every rank after gather (not yet supported for world_size > 1)");
+  CUDA_TRY(h, cudaMemcpyAsync(out, h->P.point[h->cur], 3 * sizeof(double) * (size_t)h->P.n_points, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return SSBA_OK;
+}
+
+ssba_status ssba_get_edge_errors(ssba_handle *h, double *out) {
+  if (!h || !out) return SSBA_ERR_INVALID_ARG;
+  ssba_status rc = ensure_ready(h);
+  if (rc) return rc;
+  const size_t bytes = 2 * sizeof(double) * (size_t)h->P.n_edges_total;
+  CUDA_TRY(h, cudaMemsetAsync(h->P.err_out, 0, bytes, h->stream));
+  launch_edge_errors(h->P, h->stream);
+  h->prof.kernel_launches += 1;
+  if (h->opt.world_size > 1) { rc = nccl_allreduce(h, h->P.err_out, 2 * (size_t)h->P.n_edges_total, kNcclSum); if (rc) return rc; }
+  CUDA_TRY(h, cudaMemcpyAsync(out, h->P.err_out, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return SSBA_OK;
+}
+
+ssba_status ssba_chi2(ssba_handle *h, double *plain, double *robust) {
+  if (!h) return SSBA_ERR_INVALID_ARG;
+  ssba_status rc = ensure_ready(h);
+  if (rc) return rc;
+  double f[4];
+  rc = final_chi2(h, 0.0, f);
+  if (rc) return rc;
+  if (plain) *plain = f[0];
+  if (robust) *robust = f[1];
+  return SSBA_OK;
+}
+
+ssba_status ssba_count_outliers(ssba_handle *h, double thr, int64_t *n_out, int64_t *n_in) {
+  if (!h) return SSBA_ERR_INVALID_ARG;
+  ssba_status rc = ensure_ready(h);
+  if (rc) return rc;
+  double f[4];
+  rc = final_chi2(h, thr, f);
+  if (rc) return rc;
+  if (n_out) *n_out = (int64_t)(f[2] + 0.5);
+  if (n_in) *n_in = (int64_t)(f[3] + 0.5);
+  return SSBA_OK;
+}
+
+ssba_status ssba_profile_get(ssba_handle *h, ssba_profile *out) {
+  if (!h || !out) return SSBA_ERR_INVALID_ARG;
+  *out = h->prof;
+  return SSBA_OK;
+}
+
+ssba_status ssba_profile_reset(ssba_handle *h) {
+  if (!h) return SSBA_ERR_INVALID_ARG;
+  std::memset(&h->prof, 0, sizeof(h->prof));
+  return SSBA_OK;
+}
+
+ssba_status ssba_get_problem_info(ssba_handle *h, ssba_problem_info *out) {
+  if (!h || !out) return SSBA_ERR_INVALID_ARG;
+  if (!h->initialized) return fail(h, SSBA_ERR_STATE, "problem_info: not initialised");
+  out->n_free_poses = h->s.n_fp; out->n_free_points = h->s.n_fl_global;
+  out->n_active_edges = h->s.n_active_edges_global; out->n_pairs = h->s.n_pairs;
+  out->n_schur_blocks = h->s.n_schur_blocks; out->n_factor_blocks = h->s.n_blocks;
+  out->device_bytes = (int64_t)h->device_bytes;
+  return SSBA_OK;
+}
+
+}  // extern "C"

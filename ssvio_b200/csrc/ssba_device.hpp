@@ -1,0 +1,101 @@
+// ssba_device.hpp — device-resident problem (HBM layout) and the kernel launch interface.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "ssba.h"
+#include "ssba_geometry.cuh"
+
+namespace ssba {
+
+// LM controller state, lives in device memory; the host only reads it back at sync points.
+// Mirrors the members of g2o::OptimizationAlgorithmLevenberg
+// (g2o/core/optimization_algorithm_levenberg.h:72-81) plus the loop variables of solve()
+// (levenberg.cpp:58-150) and of SparseOptimizer::optimize (sparse_optimizer.cpp:386-426).
+struct Control {
+  // options (levenberg.cpp:44-56)
+  double tau, good_lower, good_upper, user_lambda;
+  int max_trials;
+  // LM state
+  double lambda, ni;
+  double current_chi, temp_chi, rho;
+  double scale_pose;       // sum over poses of x (lambda x + b), written by the reduced solve
+  double maxdiag;          // max |H_jj| for computeLambdaInit
+  double chi2_initial;
+  int cur;                 // which of the two state buffers holds the current estimate
+  int need_linearize;      // next slot starts a new outer iteration (buildSystem)
+  int first_iteration;     // lambda must be initialised (iteration == 0)
+  int done;                // optimize() finished: every kernel returns immediately
+  int outer_iter, max_iters;
+  int qmax;                // _levenbergIterations of the running outer iteration
+  int chol_fail;           // the reduced Cholesky of this trial hit a pivot <= 0
+  int cholesky_failures;
+  int last_result;         // ssba_solver_result of the last finished outer iteration
+  int n_records;
+  int world, rank;
+  ssba_iter_record records[SSBA_MAX_ITER_RECORDS];
+};
+
+struct DeviceProblem {
+  Cameras cams;
+  double ext_R[8][9];  // rotation matrices of the extrinsics
+  int jacobian_mode;
+  double delta_all;
+  // sizes
+  int n_poses, n_points, n_fp, n_slots, n_pairs, n_edges, n_blocks, n_chunks, n_levels;
+  int n_lin_blocks, n_upd_blocks;  // grid sizes = lengths of the partial-sum arrays
+  // estimates: two buffers each (current / trial), selected by Control::cur
+  double *pose[2];    // n_poses x 7
+  double *point[2];   // n_points x 3
+  double *pose0, *point0;  // initial estimates (for ssba_reset_state)
+  // landmark-major shard
+  const int32_t *slot_vertex, *slot_pair_ptr, *slot_combo_ptr, *combo_blk;
+  const uint8_t *slot_free;
+  const int32_t *pair_vertex, *pair_q, *pair_edge_ptr;
+  const double *e_uv, *e_info, *e_delta;   // e_info / e_delta may be null
+  const uint8_t *e_cam;
+  const int32_t *e_orig;
+  // pose-major copy
+  const int32_t *chunk_q, *chunk_vertex, *chunk_edge_ptr, *q_chunk_ptr, *pm_point;
+  const double *pm_uv, *pm_info, *pm_delta;
+  const uint8_t *pm_cam;
+  const int32_t *pose_of_q;
+  // factor structure
+  const int32_t *col_ptr, *blk_row, *blk_col, *upd_ptr, *upd_dst, *upd_a, *upd_b, *row_ptr, *row_blk, *row_col,
+      *level_ptr, *level_col;
+  // system
+  double *W;          // n_pairs x 18, 6x3 row-major  (Hpl blocks)
+  double *Hll;        // n_slots x 6 (xx xy xz yy yz zz)
+  double *bl;         // n_slots x 3
+  double *Dinv;       // n_slots x 6
+  double *hpp_part;   // n_chunks x 27 (b[6], upper-tri H[21])
+  double *hpp;        // n_fp x 27
+  double *sys;        // [ L: n_blocks x 36 | bschur: n_fp x 6 | bp: n_fp x 6 ] — the all-reduced buffer
+  double *xp;         // n_fp x 6
+  double *diag_buf;   // n_fp x 6 Hpp diagonals (lambda init, summed over ranks)
+  double *chi_cur_part, *maxdiag_part;      // n_lin_blocks
+  double *chi_new_part, *scale_part;        // n_upd_blocks
+  double *scal;       // [chi_cur, chi_new, scale_lm, maxdiag] reduced partials (all-reduced)
+  double *err_out;    // n_edges_total x 2 scratch for ssba_get_edge_errors
+  double *chi_out;    // [plain, robust, n_outliers, n_inliers]
+  Control *ctl;
+  size_t sys_doubles;
+  int n_edges_total;
+};
+
+// launches (all asynchronous on `st`)
+void launch_linearize(const DeviceProblem &P, cudaStream_t st);        // K_lin + K_hpp + hpp reduce
+void launch_maxdiag(const DeviceProblem &P, cudaStream_t st);          // -> scal[3]
+void launch_lambda_init(const DeviceProblem &P, cudaStream_t st);
+void launch_prepare_system(const DeviceProblem &P, cudaStream_t st);   // sys <- blockdiag(Hpp)+lambda I, bp
+void launch_schur(const DeviceProblem &P, cudaStream_t st);
+void launch_reduced_solve(const DeviceProblem &P, cudaStream_t st);
+void launch_update(const DeviceProblem &P, cudaStream_t st);
+void launch_reduce_partials(const DeviceProblem &P, cudaStream_t st);  // -> scal[0..2]
+void launch_control(const DeviceProblem &P, cudaStream_t st);
+void launch_final_chi2(const DeviceProblem &P, double threshold, cudaStream_t st);  // -> chi_out
+void launch_edge_errors(const DeviceProblem &P, cudaStream_t st);      // -> err_out
+int kernels_per_linearize();
+
+}  // namespace ssba

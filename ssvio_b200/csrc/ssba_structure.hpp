@@ -1,0 +1,85 @@
+// ssba_structure.hpp — host-side structure of one local-BA problem: what g2o builds in
+// SparseOptimizer::initializeOptimization (g2o/core/sparse_optimizer.cpp:168-272),
+// BlockSolver::buildStructure (g2o/core/block_solver.hpp:102-256) and
+// LinearSolverCSparse::computeSymbolicDecomposition (g2o/solvers/csparse/linear_solver_csparse.h:
+// 246-308), flattened into the index arrays the CUDA kernels walk.
+//
+// Vocabulary
+//   slot   an active landmark of THIS rank's shard (free or fixed), landmark-major order
+//   pair   all edges joining one (pose, landmark) — one Hpl block W (6x3) when both are free
+//   q      permuted index of a free pose = its block row/column in the reduced (Schur) system
+//   block  a 6x6 block of the lower-triangular factor L (CSC over q, diagonal first)
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "ssba_geometry.cuh"
+
+namespace ssba {
+
+struct HostGraph {
+  Cameras cams{};
+  bool have_cams = false;
+  int n_poses = 0, n_points = 0, n_edges = 0;
+  std::vector<double> poses, points;           // 7 / 3 doubles per vertex
+  std::vector<uint8_t> pose_fixed, point_fixed;
+  std::vector<int32_t> e_pose, e_point;
+  std::vector<uint8_t> e_cam;
+  std::vector<double> e_uv;                    // 2 per edge
+  std::vector<double> e_info;                  // 3 per edge or empty (identity)
+  std::vector<double> e_delta;                 // 1 per edge or empty (delta_all)
+  double delta_all = 0.0;
+};
+
+struct Structure {
+  // ---- global (identical on every rank)
+  int n_fp = 0;                       // free active poses
+  int n_fl_global = 0;                // free active landmarks, all ranks
+  int n_active_edges_global = 0;
+  std::vector<int32_t> q_of_pose;     // pose row -> q, -1 fixed / inactive
+  std::vector<int32_t> pose_of_q;     // q -> pose row
+  // ---- this rank's shard, landmark-major
+  int n_slots = 0, n_pairs = 0, n_edges = 0, n_fl = 0;
+  std::vector<int32_t> slot_vertex;   // point row
+  std::vector<uint8_t> slot_free;
+  std::vector<int32_t> slot_pair_ptr; // n_slots + 1
+  std::vector<int32_t> pair_vertex;   // pose row
+  std::vector<int32_t> pair_q;        // -1: pose fixed (pairs with a free pose first, by q)
+  std::vector<int32_t> pair_edge_ptr; // n_pairs + 1
+  std::vector<double> e_uv;           // sorted copies
+  std::vector<uint8_t> e_cam;
+  std::vector<int32_t> e_orig;        // index in the caller's addEdge order
+  std::vector<double> e_info, e_delta;
+  // Schur accumulation targets: per free slot, for W-pairs i <= j (sorted by q): block (q_j, q_i)
+  std::vector<int32_t> slot_combo_ptr; // n_slots + 1
+  std::vector<int32_t> combo_blk;
+  // ---- pose-major copy of the edges with a free pose, cut into chunks of one pose each
+  int n_chunks = 0, n_pm_edges = 0;
+  std::vector<int32_t> chunk_q, chunk_vertex, chunk_edge_ptr; // n_chunks (+1)
+  std::vector<int32_t> q_chunk_ptr;   // n_fp + 1
+  std::vector<double> pm_uv;
+  std::vector<int32_t> pm_point;      // point row
+  std::vector<uint8_t> pm_cam;
+  std::vector<double> pm_info, pm_delta;
+  // ---- reduced system: lower block-CSC factor pattern (with fill) over q
+  int n_blocks = 0, n_schur_blocks = 0;
+  std::vector<int32_t> col_ptr;       // n_fp + 1, diagonal block first in every column
+  std::vector<int32_t> blk_row;       // n_blocks
+  std::vector<int32_t> blk_col;       // n_blocks
+  std::vector<int32_t> upd_ptr;       // n_fp + 1: left-looking updates of column j
+  std::vector<int32_t> upd_dst, upd_a, upd_b; // L[dst] -= L[a] * L[b]^T
+  std::vector<int32_t> row_ptr;       // n_fp + 1: strictly-lower blocks by row (forward solve)
+  std::vector<int32_t> row_blk, row_col;
+  std::vector<int32_t> level_ptr, level_col; // columns grouped by elimination-tree level
+  int n_levels = 0;
+  // original-order map for error read-back
+  int n_edges_total = 0;
+};
+
+// Builds the structure for `rank` of `world`. Returns false and sets err on invalid input.
+// n_fp + n_fl_global == 0 is not an error here (caller maps it to SSBA_ERR_EMPTY).
+bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std::string &err);
+
+}  // namespace ssba

@@ -1,0 +1,188 @@
+// Host-only check of the structure builder (ssvio_b200/csrc/ssba_structure.cpp): runs the
+// block-sparse left-looking Cholesky + level-ordered substitutions exactly as the CUDA kernel
+// walks them (upd lists, row lists, levels), but on the CPU, over a random SPD matrix with the
+// Schur pattern of a synthetic graph, and compares with a dense solve.  Also checks the pair /
+// chunk bookkeeping invariants.  Built and run by tests/test_structure.py (no GPU needed).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+
+#include "ssba_structure.hpp"
+
+using namespace ssba;
+
+static int fails = 0;
+#define CHECK(c, ...) do { if (!(c)) { std::printf("FAIL %s:%d: ", __FILE__, __LINE__); std::printf(__VA_ARGS__); std::printf("\n"); ++fails; } } while (0)
+
+static HostGraph make_graph(int nk, int np, int w, unsigned seed, bool fix0, int n_fixed_pts, bool loop) {
+  HostGraph g;
+  std::mt19937 rng(seed);
+  g.have_cams = true; g.cams.n = 2;
+  g.n_poses = nk; g.n_points = np;
+  g.poses.assign(7 * nk, 0.0); g.points.assign(3 * np, 0.0);
+  g.pose_fixed.assign(nk, 0); g.point_fixed.assign(np, 0);
+  if (fix0) g.pose_fixed[0] = 1;
+  for (int i = 0; i < n_fixed_pts && i < np; ++i) g.point_fixed[(i * 7919) % np] = 1;
+  for (int j = 0; j < np; ++j) {
+    int k0 = rng() % (nk - w + 1);
+    for (int k = 0; k < w; ++k)
+      for (int c = 0; c < 2; ++c) {
+        int pose = k0 + k;
+        if (loop && (j % 17 == 0) && k == w - 1) pose = (k0 + nk / 2) % nk;  // long-range covisibility
+        g.e_pose.push_back(pose); g.e_point.push_back(j); g.e_cam.push_back(c);
+        g.e_uv.push_back(0); g.e_uv.push_back(0);
+      }
+  }
+  g.n_edges = (int)g.e_pose.size();
+  // shuffle edge order to exercise the sort
+  std::vector<int> perm(g.n_edges);
+  for (int i = 0; i < g.n_edges; ++i) perm[i] = i;
+  std::shuffle(perm.begin(), perm.end(), rng);
+  HostGraph h = g;
+  for (int i = 0; i < g.n_edges; ++i) {
+    h.e_pose[i] = g.e_pose[perm[i]]; h.e_point[i] = g.e_point[perm[i]]; h.e_cam[i] = g.e_cam[perm[i]];
+  }
+  return h;
+}
+
+static void check_case(int nk, int np, int w, unsigned seed, bool fix0, int nfix, bool loop, int world) {
+  HostGraph g = make_graph(nk, np, w, seed, fix0, nfix, loop);
+  std::vector<Structure> S(world);
+  std::string err;
+  long long edges_seen = 0, slots_free = 0;
+  for (int r = 0; r < world; ++r) {
+    bool ok = build_structure(g, r, world, S[r], err);
+    CHECK(ok, "build_structure: %s", err.c_str());
+    if (!ok) return;
+    edges_seen += S[r].n_edges;
+    slots_free += S[r].n_fl;
+    // pairs: W-pairs first sorted by q, combos point at existing blocks
+    const Structure &s = S[r];
+    for (int sl = 0; sl < s.n_slots; ++sl) {
+      int prev = -1; bool seen_fixed = false; int k = 0;
+      for (int a = s.slot_pair_ptr[sl]; a < s.slot_pair_ptr[sl + 1]; ++a) {
+        CHECK(s.pair_edge_ptr[a + 1] > s.pair_edge_ptr[a], "empty pair");
+        if (s.pair_q[a] < 0) { seen_fixed = true; continue; }
+        CHECK(!seen_fixed, "free-pose pair after fixed-pose pair");
+        CHECK(s.pair_q[a] > prev, "pairs not sorted by q"); prev = s.pair_q[a]; ++k;
+        CHECK(s.q_of_pose[s.pair_vertex[a]] == s.pair_q[a], "pair_q mismatch");
+      }
+      const int nc = s.slot_combo_ptr[sl + 1] - s.slot_combo_ptr[sl];
+      CHECK(nc == (s.slot_free[sl] ? k * (k + 1) / 2 : 0), "combo count %d vs k=%d", nc, k);
+      int c = s.slot_combo_ptr[sl];
+      if (s.slot_free[sl])
+        for (int i = 0; i < k; ++i)
+          for (int j = i; j < k; ++j, ++c) {
+            const int b = s.combo_blk[c];
+            CHECK(s.blk_col[b] == s.pair_q[s.slot_pair_ptr[sl] + i] && s.blk_row[b] == s.pair_q[s.slot_pair_ptr[sl] + j], "combo block wrong");
+          }
+    }
+    for (int e = 0; e < s.n_edges; ++e) CHECK(s.e_orig[e] >= 0 && s.e_orig[e] < g.n_edges, "e_orig range");
+    int pm = 0;
+    for (int c = 0; c < s.n_chunks; ++c) {
+      CHECK(s.chunk_edge_ptr[c + 1] > s.chunk_edge_ptr[c], "empty chunk");
+      CHECK(s.pose_of_q[s.chunk_q[c]] == s.chunk_vertex[c], "chunk vertex");
+      pm += s.chunk_edge_ptr[c + 1] - s.chunk_edge_ptr[c];
+    }
+    CHECK(pm == s.n_pm_edges, "chunk edges %d vs %d", pm, s.n_pm_edges);
+  }
+  CHECK(edges_seen == S[0].n_active_edges_global, "shards cover %lld of %d active edges", edges_seen, S[0].n_active_edges_global);
+  CHECK(slots_free == S[0].n_fl_global, "free landmarks %lld vs %d", slots_free, S[0].n_fl_global);
+
+  // numeric factorisation through the structure arrays vs dense
+  const Structure &s = S[0];
+  const int n = s.n_fp, N = 6 * n;
+  if (n == 0) return;
+  std::mt19937 rng(seed + 1);
+  std::uniform_real_distribution<double> U(-1, 1);
+  std::vector<double> L(36 * (size_t)s.n_blocks, 0.0), A((size_t)N * N, 0.0), b(N), x(N);
+  for (int j = 0; j < n; ++j)
+    for (int bb = s.col_ptr[j]; bb < s.col_ptr[j + 1]; ++bb) {
+      const int i = s.blk_row[bb];
+      for (int r = 0; r < 6; ++r)
+        for (int c = 0; c < 6; ++c) {
+          double v = (i == j) ? (r == c ? 40.0 + U(rng) : 0.0) : 0.3 * U(rng);
+          if (i == j && r != c) v = 0.0;
+          L[36 * (size_t)bb + 6 * r + c] = v;
+          A[(size_t)(6 * i + r) * N + 6 * j + c] = v;
+          A[(size_t)(6 * j + c) * N + 6 * i + r] = v;
+        }
+    }
+  for (int i = 0; i < N; ++i) b[i] = U(rng);
+  // left-looking by levels
+  for (int lv = 0; lv < s.n_levels; ++lv)
+    for (int t = s.level_ptr[lv]; t < s.level_ptr[lv + 1]; ++t) {
+      const int j = s.level_col[t];
+      for (int u = s.upd_ptr[j]; u < s.upd_ptr[j + 1]; ++u) {
+        const double *Aa = &L[36 * (size_t)s.upd_a[u]], *Bb = &L[36 * (size_t)s.upd_b[u]];
+        double *D = &L[36 * (size_t)s.upd_dst[u]];
+        CHECK(s.blk_col[s.upd_dst[u]] == j, "upd dst column");
+        for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) { double sacc = 0; for (int k = 0; k < 6; ++k) sacc += Aa[6 * r + k] * Bb[6 * c + k]; D[6 * r + c] -= sacc; }
+      }
+      double *Djj = &L[36 * (size_t)s.col_ptr[j]];
+      for (int jj = 0; jj < 6; ++jj) {
+        double d = Djj[7 * jj];
+        for (int k = 0; k < jj; ++k) d -= Djj[6 * jj + k] * Djj[6 * jj + k];
+        CHECK(d > 0, "pivot");
+        Djj[7 * jj] = std::sqrt(d);
+        for (int i = jj + 1; i < 6; ++i) { double sacc = Djj[6 * i + jj]; for (int k = 0; k < jj; ++k) sacc -= Djj[6 * i + k] * Djj[6 * jj + k]; Djj[6 * i + jj] = sacc / Djj[7 * jj]; }
+        for (int c = jj + 1; c < 6; ++c) Djj[6 * jj + c] = 0;
+      }
+      for (int bb = s.col_ptr[j] + 1; bb < s.col_ptr[j + 1]; ++bb)
+        for (int r = 0; r < 6; ++r) {
+          double *row = &L[36 * (size_t)bb + 6 * r], xr[6];
+          for (int c = 0; c < 6; ++c) { double sacc = row[c]; for (int k = 0; k < c; ++k) sacc -= xr[k] * Djj[6 * c + k]; xr[c] = sacc / Djj[7 * c]; }
+          for (int c = 0; c < 6; ++c) row[c] = xr[c];
+        }
+    }
+  for (int lv = 0; lv < s.n_levels; ++lv)
+    for (int t = s.level_ptr[lv]; t < s.level_ptr[lv + 1]; ++t) {
+      const int j = s.level_col[t];
+      double sv[6];
+      for (int r = 0; r < 6; ++r) {
+        sv[r] = b[6 * j + r];
+        for (int rr = s.row_ptr[j]; rr < s.row_ptr[j + 1]; ++rr) {
+          CHECK(s.blk_row[s.row_blk[rr]] == j && s.blk_col[s.row_blk[rr]] == s.row_col[rr], "row list");
+          for (int c = 0; c < 6; ++c) sv[r] -= L[36 * (size_t)s.row_blk[rr] + 6 * r + c] * x[6 * s.row_col[rr] + c];
+        }
+      }
+      const double *Djj = &L[36 * (size_t)s.col_ptr[j]];
+      for (int c = 0; c < 6; ++c) { double v = sv[c]; for (int k = 0; k < c; ++k) v -= Djj[6 * c + k] * x[6 * j + k]; x[6 * j + c] = v / Djj[7 * c]; }
+    }
+  for (int lv = s.n_levels - 1; lv >= 0; --lv)
+    for (int t = s.level_ptr[lv]; t < s.level_ptr[lv + 1]; ++t) {
+      const int j = s.level_col[t];
+      double sv[6];
+      for (int r = 0; r < 6; ++r) {
+        sv[r] = x[6 * j + r];
+        for (int bb = s.col_ptr[j] + 1; bb < s.col_ptr[j + 1]; ++bb)
+          for (int c = 0; c < 6; ++c) sv[r] -= L[36 * (size_t)bb + 6 * c + r] * x[6 * s.blk_row[bb] + c];
+      }
+      const double *Djj = &L[36 * (size_t)s.col_ptr[j]];
+      for (int c = 5; c >= 0; --c) { double v = sv[c]; for (int k = c + 1; k < 6; ++k) v -= Djj[6 * k + c] * x[6 * j + k]; x[6 * j + c] = v / Djj[7 * c]; }
+    }
+  // residual of the dense system
+  double rmax = 0, bmax = 0;
+  for (int i = 0; i < N; ++i) {
+    double r = -b[i];
+    for (int k = 0; k < N; ++k) r += A[(size_t)i * N + k] * x[k];
+    rmax = std::fmax(rmax, std::fabs(r)); bmax = std::fmax(bmax, std::fabs(b[i]));
+  }
+  CHECK(rmax < 1e-10 * (1 + bmax), "residual %.3e (n=%d blocks=%d levels=%d)", rmax, n, s.n_blocks, s.n_levels);
+  std::printf("case nk=%d np=%d w=%d fix0=%d nfix=%d loop=%d world=%d: n_fp=%d blocks=%d schur=%d levels=%d upd=%d resid=%.2e\n",
+              nk, np, w, (int)fix0, nfix, (int)loop, world, n, s.n_blocks, s.n_schur_blocks, s.n_levels, s.upd_ptr[n], rmax);
+}
+
+int main() {
+  check_case(4, 40, 3, 1, false, 0, false, 1);
+  check_case(10, 500, 3, 2, false, 0, false, 1);
+  check_case(30, 800, 5, 3, true, 25, false, 2);
+  check_case(40, 1500, 4, 4, false, 10, true, 3);
+  check_case(64, 3000, 5, 5, true, 0, true, 8);
+  if (fails) { std::printf("%d FAILURES\n", fails); return 1; }
+  std::printf("OK\n");
+  return 0;
+}

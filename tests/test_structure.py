@@ -1,0 +1,18 @@
+"""Host logic of the product: structure build, landmark sharding, symbolic factorisation and the
+level schedule the CUDA solver walks — exercised on the CPU by tests/cpp/test_structure.cpp."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_structure_builder_cpp():
+    exe = "/tmp/ssba_test_structure"
+    cuda_inc = "/usr/local/cuda/include"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + cuda_inc, "-I" + os.path.join(ROOT, "include"),
+                    "-I" + os.path.join(ROOT, "ssvio_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "cpp", "test_structure.cpp"),
+                    os.path.join(ROOT, "ssvio_b200", "csrc", "ssba_structure.cpp"), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.strip().endswith("OK")
