@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — LM iterations/s of ssvio's back-end local bundle adjustment on B200.
+
+Metric (BASELINE.json): LM iterations/sec on the 100 key-frame / 20k landmark / 200k edge
+local BA (KITTI-00 local-window shape, Huber delta 5.891), fp64, synthetic graph from
+ssvio_b200.synth (seed 42).  One "step" = one optimize(10) = 10 outer LM iterations
+(SparseOptimizer::optimize, thirdparty/g2o/g2o/core/sparse_optimizer.cpp:366-431) on that graph.
+
+  value   whole-job LM it/s with the graph resident in HBM (reset of the estimates + 10 iterations)
+  e2e     the same through the C ABI with HOST buffers: set_* (H2D + structure build),
+          optimize(10), get_poses/get_points (D2H) every step
+  --impl reference   the reference's own g2o/CSparse CPU path (oracle/_ref, compiled from the
+          reference tree; falls back to the C restatement when that .so is absent)
+
+N > 1 (torchrun): the landmarks and their edges are sharded over the ranks, the reduced pose
+system is all-reduced over NCCL each LM trial (strong scaling: the same graph).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "LM iterations/sec on 100KF/20k-pt/200k-edge BA"
+UNIT = "LM it/s"
+WORKLOAD = "cfg3"
+WORKLOAD_DESC = "100 KF / 20k landmarks / 200k edges (KITTI-00 local-window shape), Huber 5.891, 10 LM iters"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ssba", choices=["ssba", "reference"])
+    ap.add_argument("--workload", default=WORKLOAD)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(self.index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for k, nme in enumerate(names):
+                    if r[5 + k].strip().lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def iter_algorithmic_bytes(n_edges, n_points, n_poses, nnz_s):
+    """bytes one LM iteration has to move (one linearise + one damped solve +
+    one update + one chi2 pass), compact 28 B edge records."""
+    return 3 * 28 * n_edges + 5 * 24 * n_points + 5 * 56 * n_poses + 2 * 288 * nnz_s + 2 * 8 * 6 * n_poses
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own CPU implementation of the path, timed on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import bindings
+    from ssvio_b200 import synth
+    g = synth.make_config(args.workload)
+    if bindings.RefOracle.available():
+        orc, kind, jac = bindings.RefOracle(), "reference", "numeric"
+        run = lambda it: orc.optimize(g, iters=it, jacobian=jac, trace=False, want_state=False)["report"]
+    else:
+        bindings.build(which=("port",))
+        orc, kind, jac = bindings.PortOracle(), "port", "numeric"
+        run = lambda it: orc.optimize(g, iters=it, jacobian=jac)["report"]
+    # bounded sample: LM iterations per step sized from one probe iteration so the run ends
+    # within ~2 minutes whatever K and W are
+    t0 = time.perf_counter(); run(1); t_probe = time.perf_counter() - t0
+    budget = 120.0
+    its = int(max(1, min(g.iters, budget / max(1e-9, (args.steps + args.warmup) * t_probe))))
+    for _ in range(args.warmup):
+        run(its)
+    t_total, n_its = 0.0, 0
+    for _ in range(args.steps):
+        rep = run(its)
+        t_total += rep.seconds_total  # wall time of optimize() only, as BASELINE.md defines it
+        n_its += rep.iterations
+    value = n_its / t_total
+    sample = (f"{args.workload} full graph, optimize({its}) per step ({its} of {g.iters} LM iterations), "
+              f"Jacobians as shipped (numeric), single thread (G2O_USE_OPENMP OFF as the reference ships)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD_DESC, "n_poses": g.n_poses, "n_points": g.n_points,
+                   "n_edges": g.n_edges, "lm_iters_per_step": its, "host_cores_available": os.cpu_count()},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ssba(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from ssvio_b200 import ba, build, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — libssba has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    multi = world > 1
+    if multi:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        build.build()
+    if multi:
+        dist.barrier()
+    ba.load_library()
+
+    nccl_id = None
+    if multi:
+        idt = torch.zeros(ba.SSBA_NCCL_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt = torch.tensor(list(ba.nccl_unique_id()), dtype=torch.uint8, device=dev)
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().tolist())
+
+    g = synth.make_config(args.workload)
+    iters = g.iters
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier_sync():
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # L2 flush between timed steps: the whole working set (~33 MB) would otherwise sit in the
+    # 126 MB L2 from the previous step
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def flush_l2():
+        flush.add_(1)
+
+    # ---------------- resident: graph uploaded once, timed = reset + optimize(10)
+    opt = ba.BundleAdjuster(device_id=local_rank, stream=stream, rank=rank, world_size=world, nccl_id=nccl_id)
+    opt.set_graph(g)
+    opt.initialize_optimization()
+    info = opt.problem_info()
+    rep = opt.optimize(iters)  # also the numerics record of this run
+    chi2_final, its_done = rep.chi2_robust, rep.iterations
+
+    def step_resident():
+        opt.reset_state()
+        opt.optimize_nowait_report(iters)
+
+    for _ in range(max(args.warmup, 3)):
+        flush_l2(); step_resident()
+    barrier_sync()
+    opt.profile_reset()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier_sync()
+    t_wall0 = time.perf_counter()
+    for a, b in ev:
+        flush_l2()
+        a.record(); step_resident(); b.record()
+    barrier_sync()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    launches = opt.profile().kernel_launches
+    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(ms_steps)
+    if multi:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = iters * args.steps / (total_ms * 1e-3)
+
+    # ---------------- per-phase device time (separate profiled pass: event pairs around phases)
+    popt = ba.BundleAdjuster(device_id=local_rank, stream=stream, rank=rank, world_size=world, nccl_id=None, profile=True) if not multi else None
+    phases = None
+    if popt is not None:
+        popt.set_graph(g); popt.initialize_optimization()
+        for _ in range(3):
+            popt.reset_state(); popt.optimize_nowait_report(iters)
+        popt.profile_reset()
+        for _ in range(args.steps):
+            flush_l2(); popt.reset_state(); popt.optimize_nowait_report(iters)
+        p = popt.profile()
+        phases = {"linearize": (p.ms_linearize, p.n_linearize), "schur": (p.ms_schur, p.n_schur),
+                  "reduced_solve": (p.ms_reduced_solve, p.n_reduced_solve),
+                  "update_chi2": (p.ms_update_chi2, p.n_update_chi2)}
+        popt.close()
+
+    # ---------------- e2e: host buffers in, host buffers out, every step
+    def pin(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    hg = synth.Graph(K=pin(g.K), ext=pin(g.ext), poses=pin(g.poses), pose_fixed=pin(g.pose_fixed),
+                     points=pin(g.points), point_fixed=pin(g.point_fixed), pose_idx=pin(g.pose_idx),
+                     point_idx=pin(g.point_idx), cam_idx=pin(g.cam_idx), uv=pin(g.uv),
+                     huber_delta=g.huber_delta, iters=iters)
+    eopt = ba.BundleAdjuster(device_id=local_rank, stream=stream, rank=rank, world_size=world, nccl_id=nccl_id) if not multi else opt
+    e2e_chi = None
+
+    def step_e2e():
+        nonlocal e2e_chi
+        eopt.set_graph(hg)                   # H2D of every input + structure build
+        r = eopt.optimize(iters)             # incl. final chi2 read-back (the step's result)
+        e2e_chi = r.chi2_robust
+        poses = eopt.poses()                 # D2H
+        points = eopt.points() if not multi else None
+        return poses, points
+
+    e2e = None
+    if not multi:
+        for _ in range(max(args.warmup, 3)):
+            step_e2e()
+        barrier_sync()
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b in ev2:
+            flush_l2()
+            a.record(); step_e2e(); b.record()
+        barrier_sync()
+        e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
+        e2e = {"value": iters * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": hg.input_bytes(), "d2h_bytes_per_step": hg.output_bytes() + 32,
+               "ms_per_step": e2e_ms / args.steps, "chi2_robust": e2e_chi}
+        eopt.close()
+
+    # ---------------- CPU baseline on the box's host cores (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and not multi and not args.no_cpu_baseline:
+        from oracle import bindings
+        if bindings.RefOracle.available():
+            orc, kind = bindings.RefOracle(), "reference"
+            r = orc.optimize(g, iters=iters, jacobian="numeric", trace=False, want_state=False)["report"]
+            cpu_chi = orc.optimize(g, iters=iters, jacobian="numeric", trace=True, want_state=False)["report"].chi2_robust
+        else:
+            bindings.build(which=("port",))
+            orc, kind = bindings.PortOracle(), "port"
+            r = orc.optimize(g, iters=iters, jacobian="numeric")["report"]
+            cpu_chi = r.chi2_robust
+        cpu = {"value": r.iterations / r.seconds_total, "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": f"{args.workload} full graph, one optimize({iters}) ({r.seconds_total:.2f} s), numeric Jacobians as shipped, "
+                         f"single thread (reference ships G2O_USE_OPENMP OFF); host has {os.cpu_count()} cores",
+               "chi2_robust": cpu_chi, "chi2_rel_err_gpu_vs_cpu": abs(chi2_final - cpu_chi) / cpu_chi}
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        nnz_s = info.n_schur_blocks
+        b_iter = iter_algorithmic_bytes(g.n_edges, g.n_points, g.n_poses, nnz_s)
+        roofline = None
+        if phases:
+            # dominant kernel = the phase with the largest share of the step
+            name = max(phases, key=lambda k: phases[k][0])
+            ms, n = phases[name]
+            alg = {  # algorithmic bytes per launch (DESIGN.md "Kernels"), whole graph
+                "linearize": 28 * g.n_edges + 24 * g.n_points + 56 * g.n_poses + 144 * info.n_pairs + 72 * g.n_points,
+                "schur": 144 * info.n_pairs + 72 * g.n_points + 288 * nnz_s + 48 * g.n_poses,
+                "reduced_solve": 2 * 288 * nnz_s + 2 * 48 * g.n_poses,
+                "update_chi2": 28 * g.n_edges + 144 * info.n_pairs + 2 * 24 * g.n_points + 56 * g.n_poses,
+            }[name]
+            dur = ms / max(n, 1) * 1e-3
+            achieved = alg / dur / 1e9
+            roofline = {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": alg, "avg_launch_ms": ms / max(n, 1),
+                        "phase_ms_per_step": {k: v[0] / args.steps for k, v in phases.items()}}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC, "n_poses": g.n_poses, "n_points": g.n_points,
+                       "n_edges": g.n_edges, "lm_iters_per_step": iters, "seed": 42,
+                       "l2": "flushed between timed steps (256 MiB write); working set %.1f MB < 126 MB L2" % (info.device_bytes / 1e6),
+                       "parallelism": "landmark-sharded x%d, NCCL all-reduce of the reduced pose system" % world if multi else "single GPU",
+                       "iter_algorithmic_bytes": b_iter,
+                       "step_hbm_frac": (b_iter * iters / (total_ms / args.steps * 1e-3)) / 1e9 / peak,
+                       "chi2_robust_final": chi2_final, "lm_iterations_done": its_done,
+                       "wall_s_timed_region": t_wall},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    opt.close()
+    if multi:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ssba(args)
+
+
+if __name__ == "__main__":
+    main()
