@@ -37,7 +37,7 @@ WORKLOAD_DESC = "100 KF / 20k landmarks / 200k edges (KITTI-00 local-window shap
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ssba", choices=["ssba", "reference"])
     ap.add_argument("--workload", default=WORKLOAD)
@@ -65,11 +65,21 @@ class ClockSampler:
         self.p = None
 
     def start(self):
+        """Started BEFORE the warm-up (nvidia-smi needs ~1 s to come up); mark() notes where the
+        timed region begins so only samples taken under the timed load are kept."""
+        self.n_before = 0
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-i", str(self.index), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-i", str(self.index), "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+
+    def mark(self):
+        try:
+            self.f.flush()
+            self.n_before = len(open(self.f.name).read().strip().splitlines())
+        except Exception:
+            self.n_before = 0
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
@@ -84,6 +94,11 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
         os.unlink(self.f.name)
+        if len(rows) - self.n_before >= 3:
+            rows = rows[self.n_before:]  # samples of the timed region only
+            out["window"] = "timed region"
+        else:
+            out["window"] = "warm-up + timed region (timed region shorter than the sampling period)"
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
@@ -96,8 +111,8 @@ class ClockSampler:
                 pass
         if sm:
             sm.sort()
-            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                   "samples": len(sm)}
+            out.update({"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                        "samples": len(sm)})
         return out
 
 
@@ -214,13 +229,18 @@ def run_ssba(args):
         opt.reset_state()
         opt.optimize_nowait_report(iters)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        t_s = time.perf_counter()
+        while time.perf_counter() - t_s < 1.5:   # keep the GPU busy while nvidia-smi comes up
+            flush_l2(); step_resident()
     for _ in range(max(args.warmup, 3)):
         flush_l2(); step_resident()
     barrier_sync()
     opt.profile_reset()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.mark()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier_sync()
     t_wall0 = time.perf_counter()

@@ -609,7 +609,9 @@ ssba_status ssba_count_outliers(ssba_handle *h, double thr, int64_t *n_out, int6
   rc = final_chi2(h, thr, f);
   if (rc) return rc;
   if (n_out) *n_out = (int64_t)(f[2] + 0.5);
-  if (n_in) *n_in = (int64_t)(f[3] + 0.5);
+  // edges whose two vertices are fixed are never active (sparse_optimizer.cpp:237): their
+  // _error stays zero in the reference, so backend.cpp:184 counts them as inliers
+  if (n_in) *n_in = (int64_t)(f[3] + 0.5) + (h->g.n_edges - h->s.n_active_edges_global);
   return SSBA_OK;
 }
 
