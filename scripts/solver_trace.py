@@ -1,0 +1,34 @@
+"""Developer aid: per-level clock64 trace of k_reduced_solve (needs a -DSSBA_SOLVER_TRACE build)."""
+import ctypes as C, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+from ssvio_b200 import ba, synth
+name = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
+g = synth.make_config(name)
+with ba.BundleAdjuster() as opt:
+    opt.set_graph(g); opt.initialize_optimization()
+    for _ in range(3):
+        opt.reset_state(); opt.optimize_nowait_report(2)
+    lib = ba.load_library()
+    out = np.zeros(4096, dtype=np.int64)
+    lib.ssba_debug_solver_trace(out.ctypes.data_as(C.POINTER(C.c_longlong)), 4096)
+    info = opt.problem_info()
+t0 = out[0]
+nz = np.nonzero(out[:2900])[0].max()
+rel = out[:nz + 1] - t0
+nseg = (nz - 2) // 4
+print("segments", nseg, "total cycles", rel[nz])
+for sg in range(nseg):
+    a, b, c = rel[1 + 3 * sg], rel[2 + 3 * sg], rel[3 + 3 * sg]
+    print(f"seg {sg:3d}: start {a:8d} items {b - a:7d} wait+barrier {c - b:7d}")
+base = 3 * nseg + 1
+prev = rel[3 * nseg]
+for k in range(1, nseg):
+    v = rel[base + k]
+    print(f"bwd {k:3d}: {v - prev:7d}")
+    prev = v
+print("tail", rel[nz] - prev)
+d = out[3000:3006] - out[3000]
+print("raw", d, "npairs?")
+print("seg 6 warp0 first round: pairs", d[1], "reduce+chol", d[2] - d[1], "inverse", d[3] - d[2], "publish", d[4] - d[3], " (start offset in level:", out[3000] - out[1 + 3 * 6], ")")

@@ -17,7 +17,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libssba.so")
 
 SOURCES = ["ssba_kernels.cu", "ssba_api.cu", "ssba_structure.cpp"]
-HEADERS = ["ssba_geometry.cuh", "ssba_device.hpp", "ssba_structure.hpp"]
+HEADERS = ["ssba_geometry.cuh", "ssba_device.hpp", "ssba_structure.hpp", "ssba_solver_layout.hpp"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -45,7 +45,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+    extra = os.environ.get("SSBA_EXTRA_NVCC_FLAGS", "").split()
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + [
         "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
     ] + [os.path.join(CSRC, f) for f in SOURCES] + ["-o", LIB, "-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -415,9 +415,8 @@ ssba_status ssba_initialize(ssba_handle *h) {
   STAT(s.chunk_q, chunk_q); STAT(s.chunk_vertex, chunk_vertex); STAT(s.chunk_edge_ptr, chunk_edge_ptr);
   STAT(s.q_chunk_ptr, q_chunk_ptr); STAT(s.pm_point, pm_point); STAT(s.pm_uv, pm_uv); STAT(s.pm_info, pm_info);
   STAT(s.pm_delta, pm_delta); STAT(s.pm_cam, pm_cam); STAT(s.pose_of_q, pose_of_q);
-  STAT(s.col_ptr, col_ptr); STAT(s.blk_row, blk_row); STAT(s.blk_col, blk_col); STAT(s.upd_ptr, upd_ptr);
-  STAT(s.upd_dst, upd_dst); STAT(s.upd_a, upd_a); STAT(s.upd_b, upd_b); STAT(s.row_ptr, row_ptr);
-  STAT(s.row_blk, row_blk); STAT(s.row_col, row_col); STAT(s.level_ptr, level_ptr); STAT(s.level_col, level_col);
+  STAT(s.unit_slot, unit_slot); STAT(s.unit_n, unit_n); STAT(s.unit_k, unit_k); STAT(s.unit_c0, unit_c0);
+  STAT(s.blk_row, blk_row); STAT(s.blk_col, blk_col); STAT(s.prog, prog); STAT(s.prog_ptr, prog_ptr);
 #undef STAT
   const size_t static_bytes = align_up(top);
   std::vector<Item> work;
@@ -466,6 +465,9 @@ ssba_status ssba_initialize(ssba_handle *h) {
   P.n_poses = g.n_poses; P.n_points = g.n_points; P.n_fp = s.n_fp; P.n_slots = s.n_slots; P.n_pairs = s.n_pairs;
   P.n_edges = s.n_edges; P.n_blocks = s.n_blocks; P.n_chunks = s.n_chunks; P.n_levels = s.n_levels;
   P.n_edges_total = g.n_edges;
+  P.prog_max_seg = s.prog_max_seg;
+  P.n_segments = s.n_segments;
+  P.n_units = s.n_units;
   h->initialized = true;
   h->dirty = false;
   ssba_status rc = ssba_reset_state(h);

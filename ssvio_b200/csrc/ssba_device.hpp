@@ -61,9 +61,12 @@ struct DeviceProblem {
   const double *pm_uv, *pm_info, *pm_delta;
   const uint8_t *pm_cam;
   const int32_t *pose_of_q;
+  const int32_t *unit_slot, *unit_n, *unit_k, *unit_c0;  // Schur work units
+  int n_units;
   // factor structure
-  const int32_t *col_ptr, *blk_row, *blk_col, *upd_ptr, *upd_dst, *upd_a, *upd_b, *row_ptr, *row_blk, *row_col,
-      *level_ptr, *level_col;
+  const int32_t *blk_row, *blk_col;
+  const int32_t *prog, *prog_ptr;  // per-level solver program (ssba_structure.cpp build_solver_program)
+  int prog_max_seg, n_segments;
   // system
   double *W;          // n_pairs x 18, 6x3 row-major  (Hpl blocks)
   double *Hll;        // n_slots x 6 (xx xy xz yy yz zz)

@@ -11,6 +11,7 @@
 #include <cfloat>
 
 #include "ssba_device.hpp"
+#include "ssba_solver_layout.hpp"
 
 namespace ssba {
 
@@ -18,7 +19,6 @@ namespace {
 
 constexpr int kLinThreads = 128;
 constexpr int kHppThreads = 128;
-constexpr int kSolveThreads = 256;
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -293,211 +293,432 @@ __global__ void k_prepare_system(const DeviceProblem P) {
 // ---------------------------------------------------------------------------------------------
 // k_schur — landmark elimination of BlockSolver::solve (block_solver.hpp:342-400):
 // Dinv = (Hll + lambda I)^-1, bschur -= W Dinv b_l, S(i1,i2) -= W_i1 Dinv W_i2^T.
-// One thread per free landmark; contributions go to the (L2-resident) reduced system with fp64
-// atomic adds.
-__global__ void __launch_bounds__(kLinThreads) k_schur(const DeviceProblem P) {
+//
+// One warp per work unit = a run of <= 32 landmarks that are seen by the same k free poses
+// (the host sorts the landmarks so that such runs exist) x <= 32 of the k(k+1)/2 block pairs.
+// Lane i first inverts the 3x3 block of landmark i of the run into shared memory; then every
+// lane owns ONE 6x6 block pair (a, b) and walks the run, accumulating its block in 36 registers.
+// Only the per-unit totals go to the L2-resident reduced system with fp64 atomic adds
+// (~1/32 of the per-landmark contributions).
+constexpr int kSchurWarps = 4;
+constexpr int kSchurRunPairs = 160;  // W blocks of one run staged in shared memory (= host kSchurRunPairs)
+
+__global__ void __launch_bounds__(32 * kSchurWarps) k_schur(const DeviceProblem P) {
   const Control *ctl = P.ctl;
   if (ctl->done) return;
-  const int sl = blockIdx.x * blockDim.x + threadIdx.x;
-  if (sl >= P.n_slots || !P.slot_free[sl]) return;
+  extern __shared__ double s_w_all[];  // kSchurWarps x kSchurRunPairs x 18
+  __shared__ double s_dinv[kSchurWarps][32][6];
+  __shared__ double s_db[kSchurWarps][32][3];
+  __shared__ int s_pair0[kSchurWarps][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int u = blockIdx.x * kSchurWarps + warp;
+  if (u >= P.n_units) return;  // whole warp; no block-wide barrier below
+  const int s0 = P.unit_slot[u], n = P.unit_n[u], k = P.unit_k[u], c0 = P.unit_c0[u];
+  double *s_w = s_w_all + (size_t)warp * kSchurRunPairs * 18;
+  const bool staged = n * k <= kSchurRunPairs;
+  if (lane < n) s_pair0[warp][lane] = P.slot_pair_ptr[s0 + lane];
+  __syncwarp();
+  if (staged) {
+    // the run's W blocks (k consecutive 6x3 blocks per landmark) -> shared memory, asynchronously
+    const int per_lm = 9 * k;  // 16-byte granules per landmark
+    for (int gi = lane; gi < n * per_lm; gi += 32) {
+      const int i = gi / per_lm, o = gi - i * per_lm;
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(s_w + 18 * (size_t)(i * k) + 2 * o);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa),
+                   "l"(P.W + 18 * (size_t)s_pair0[warp][i] + 2 * o));
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  }
   const double lambda = ctl->lambda;
-  double H[6], Di[6];
+  if (lane < n) {
+    const size_t sl = (size_t)(s0 + lane);
+    double H[6], Di[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) H[i] = P.Hll[6 * (size_t)sl + i];
-  H[0] += lambda; H[3] += lambda; H[5] += lambda;
-  sym3_inverse(H, Di);
+    for (int i = 0; i < 6; ++i) H[i] = P.Hll[6 * sl + i];
+    H[0] += lambda; H[3] += lambda; H[5] += lambda;
+    sym3_inverse(H, Di);
+    const double b0 = P.bl[3 * sl], b1 = P.bl[3 * sl + 1], b2 = P.bl[3 * sl + 2];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) P.Dinv[6 * (size_t)sl + i] = Di[i];
-  const double b0 = P.bl[3 * (size_t)sl], b1 = P.bl[3 * (size_t)sl + 1], b2 = P.bl[3 * (size_t)sl + 2];
-  const double db0 = Di[0] * b0 + Di[1] * b1 + Di[2] * b2;
-  const double db1 = Di[1] * b0 + Di[3] * b1 + Di[4] * b2;
-  const double db2 = Di[2] * b0 + Di[4] * b1 + Di[5] * b2;
-  double *L = P.sys;
-  double *bs = P.sys + 36 * (size_t)P.n_blocks;
-  const int a0 = P.slot_pair_ptr[sl], a1 = P.slot_pair_ptr[sl + 1];
-  int combo = P.slot_combo_ptr[sl];
-  for (int a = a0; a < a1; ++a) {
-    const int qi = P.pair_q[a];
-    if (qi < 0) break;  // fixed-pose pairs come last
-    double Wi[18], BD[18];
-    const double2 *src = reinterpret_cast<const double2 *>(P.W + 18 * (size_t)a);
+    for (int i = 0; i < 6; ++i) s_dinv[warp][lane][i] = Di[i];
+    s_db[warp][lane][0] = Di[0] * b0 + Di[1] * b1 + Di[2] * b2;
+    s_db[warp][lane][1] = Di[1] * b0 + Di[3] * b1 + Di[4] * b2;
+    s_db[warp][lane][2] = Di[2] * b0 + Di[4] * b1 + Di[5] * b2;
+    if (c0 == 0) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { const double2 t = src[i]; Wi[2 * i] = t.x; Wi[2 * i + 1] = t.y; }
+      for (int i = 0; i < 6; ++i) P.Dinv[6 * sl + i] = Di[i];
+    }
+  }
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+  __syncwarp();
+  const int idx = c0 + lane;
+  if (idx >= k * (k + 1) / 2) return;
+  // block pair (a <= b) of this lane, enumerated like combo_blk: a-major
+  int a = 0, rem = idx;
+  while (rem >= k - a) { rem -= k - a; ++a; }
+  const int b = a + rem;
+  const bool diag = a == b;
+  double acc[36], accb[6];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) acc[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) accb[i] = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const double2 *sa, *sb;
+    if (staged) {
+      sa = reinterpret_cast<const double2 *>(s_w + 18 * (size_t)(i * k + a));
+      sb = reinterpret_cast<const double2 *>(s_w + 18 * (size_t)(i * k + b));
+    } else {
+      const int p0 = s_pair0[warp][i];
+      sa = reinterpret_cast<const double2 *>(P.W + 18 * (size_t)(p0 + a));
+      sb = reinterpret_cast<const double2 *>(P.W + 18 * (size_t)(p0 + b));
+    }
+    double Wa[18], Wb[18], BD[18];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) { const double2 x = sa[t]; Wa[2 * t] = x.x; Wa[2 * t + 1] = x.y; }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) { const double2 x = sb[t]; Wb[2 * t] = x.x; Wb[2 * t + 1] = x.y; }
+    const double d0 = s_dinv[warp][i][0], d1 = s_dinv[warp][i][1], d2 = s_dinv[warp][i][2],
+                 d3 = s_dinv[warp][i][3], d4 = s_dinv[warp][i][4], d5 = s_dinv[warp][i][5];
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
-      const double w0 = Wi[3 * r], w1 = Wi[3 * r + 1], w2 = Wi[3 * r + 2];
-      BD[3 * r + 0] = w0 * Di[0] + w1 * Di[1] + w2 * Di[2];
-      BD[3 * r + 1] = w0 * Di[1] + w1 * Di[3] + w2 * Di[4];
-      BD[3 * r + 2] = w0 * Di[2] + w1 * Di[4] + w2 * Di[5];
-      atomicAdd(bs + 6 * (size_t)qi + r, -(w0 * db0 + w1 * db1 + w2 * db2));
+      const double w0 = Wa[3 * r], w1 = Wa[3 * r + 1], w2 = Wa[3 * r + 2];
+      BD[3 * r + 0] = w0 * d0 + w1 * d1 + w2 * d2;
+      BD[3 * r + 1] = w0 * d1 + w1 * d3 + w2 * d4;
+      BD[3 * r + 2] = w0 * d2 + w1 * d4 + w2 * d5;
     }
-    for (int a2 = a; a2 < a1; ++a2) {
-      if (P.pair_q[a2] < 0) break;
-      double Wj[18];
-      const double2 *s2 = reinterpret_cast<const double2 *>(P.W + 18 * (size_t)a2);
+    // block (row q_b, col q_a) += W_b Dinv W_a^T
 #pragma unroll
-      for (int i = 0; i < 9; ++i) { const double2 t = s2[i]; Wj[2 * i] = t.x; Wj[2 * i + 1] = t.y; }
-      double *dst = L + 36 * (size_t)P.combo_blk[combo++];  // block (row q_a2, col q_a)
+    for (int r = 0; r < 6; ++r)
 #pragma unroll
-      for (int r = 0; r < 6; ++r)
+      for (int c = 0; c < 6; ++c)
+        acc[6 * r + c] += Wb[3 * r] * BD[3 * c] + Wb[3 * r + 1] * BD[3 * c + 1] + Wb[3 * r + 2] * BD[3 * c + 2];
+    if (diag) {
+      const double e0 = s_db[warp][i][0], e1 = s_db[warp][i][1], e2 = s_db[warp][i][2];
 #pragma unroll
-        for (int c = 0; c < 6; ++c)
-          atomicAdd(dst + 6 * r + c,
-                    -(Wj[3 * r] * BD[3 * c] + Wj[3 * r + 1] * BD[3 * c + 1] + Wj[3 * r + 2] * BD[3 * c + 2]));
+      for (int r = 0; r < 6; ++r) accb[r] += Wa[3 * r] * e0 + Wa[3 * r + 1] * e1 + Wa[3 * r + 2] * e2;
     }
+  }
+  double *dst = P.sys + 36 * (size_t)P.combo_blk[P.slot_combo_ptr[s0] + idx];
+#pragma unroll
+  for (int i = 0; i < 36; ++i) atomicAdd(dst + i, -acc[i]);
+  if (diag) {
+    double *bs = P.sys + 36 * (size_t)P.n_blocks + 6 * (size_t)P.pair_q[s_pair0[warp][0] + a];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) atomicAdd(bs + r, -accb[r]);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_reduced_solve — the reduced pose system: block-sparse left-looking Cholesky over the
-// elimination-tree levels, forward/backward substitution, then the pose part of
-// SparseOptimizer::update (sparse_optimizer.cpp:433-446) and of computeScale
-// (levenberg.cpp:168-175).  Replaces LinearSolverCSparse::solve
-// (g2o/solvers/csparse/linear_solver_csparse.h:106-142) + cs_chol_workspace
-// (csparse_extension.cpp:67-122), incl. the "pivot <= 0 => fail" rule (:115).
-// Single CTA; a warp per block column inside a level.
-__device__ __forceinline__ bool chol6_inplace(double *A) {  // lower, row-major 6x6, one thread
-  bool ok = true;
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    double d = A[7 * j];
-#pragma unroll
-    for (int k = 0; k < j; ++k) d -= A[6 * j + k] * A[6 * j + k];
-    if (!(d > 0.0)) { ok = false; d = 1.0; }
-    const double l = sqrt(d);
-    A[7 * j] = l;
-    const double il = 1.0 / l;
-#pragma unroll
-    for (int i = j + 1; i < 6; ++i) {
-      double s = A[6 * i + j];
-#pragma unroll
-      for (int k = 0; k < j; ++k) s -= A[6 * i + k] * A[6 * j + k];
-      A[6 * i + j] = s * il;
-    }
-#pragma unroll
-    for (int c = j + 1; c < 6; ++c) A[6 * j + c] = 0.0;
-  }
-  return ok;
+// k_reduced_solve — the reduced pose system S x_p = bschur: block-sparse left-looking Cholesky
+// scheduled over the elimination-tree levels of the host's symbolic factorisation (natural or
+// nested-dissection order), forward substitution fused into the same levels, backward
+// substitution over the levels in reverse, then the pose part of SparseOptimizer::update
+// (sparse_optimizer.cpp:433-446) and of computeScale (levenberg.cpp:168-175).  Replaces
+// LinearSolverCSparse::solve (g2o/solvers/csparse/linear_solver_csparse.h:106-142) +
+// cs_chol_workspace / cs_lsolve / cs_ltsolve (csparse_extension.cpp:35-122), incl. the
+// "pivot <= 0 => the trial is rejected" rule (:115).
+//
+// One CTA.  Every 6x6 block of a column of the running level is one work item handled by one
+// warp: lanes (g, r) = (lane / 6, lane % 6) split the item's update pairs five ways (g) and own
+// one row (r) of the block.  The warp holding a column's diagonal item factors it across lanes
+// 0..5 with shuffles, inverts the 6x6 triangle and publishes the inverse in shared memory; the
+// warps holding the column's other items wait on a shared-memory flag, multiply by that inverse
+// and store the final block.  One __syncthreads per level.
+
+__device__ __forceinline__ double group_reduce(double v, int lane) {
+  // lanes r + 6 g, g = 0..4 (lanes 30, 31 carry zeros): ((g0 + g3) + (g1 + g4)) + g2 -> lanes 0..5
+  double t = __shfl_down_sync(0xffffffffu, v, 18);
+  if (lane < 12) v += t;
+  t = __shfl_down_sync(0xffffffffu, v, 6);
+  const double u = __shfl_down_sync(0xffffffffu, v, 12);
+  if (lane < 6) v = (v + t) + u;
+  return v;
 }
 
-__global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DeviceProblem P) {
+// the index segment of one level, resolved from its header (ssba_structure.cpp build_solver_program)
+struct LevelSeg {
+  int n_cols, n_rounds, n_pairs, n_pf, n_bpf;
+  const int *col_j, *col_b0, *col_bptr, *brow, *round_type, *gt_dst, *gt_slot, *gt_pos, *gt_p0, *gt_p1, *pa,
+      *pb, *pf_blk, *pf_slot, *bpf_blk;
+  __device__ __forceinline__ explicit LevelSeg(const int *seg) {
+    n_cols = seg[0]; n_rounds = seg[1]; n_pairs = seg[2]; n_pf = seg[4]; n_bpf = seg[5];
+    const int n_brows = seg[3];
+    const int *p = seg + 8;
+    col_j = p; p += n_cols;
+    col_b0 = p; p += n_cols;
+    col_bptr = p; p += n_cols + 1;
+    brow = p; p += n_brows;
+    round_type = p; p += n_rounds;
+    gt_dst = p; p += 5 * n_rounds;
+    gt_slot = p; p += 5 * n_rounds;
+    gt_pos = p; p += 5 * n_rounds;
+    gt_p0 = p; p += 5 * n_rounds;
+    gt_p1 = p; p += 5 * n_rounds;
+    pa = p; p += n_pairs;
+    pb = p; p += n_pairs;
+    pf_blk = p; p += n_pf;
+    pf_slot = p; p += n_pf;
+    bpf_blk = p;
+  }
+};
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src));
+}
+// asynchronous global -> shared copy of one level segment (16-byte granules, LDGSTS)
+__device__ __forceinline__ void stage_segment(int *dst, const int *src, int n_ints, int tid) {
+  for (int i = 4 * tid; i < n_ints; i += 4 * kSolveThreads) cp_async16(dst + i, src + i);
+}
+__device__ __forceinline__ void stage_wait() {
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
+}
+
+#ifdef SSBA_SOLVER_TRACE
+__device__ long long g_solver_trace[4096];
+#define TRACE(i) do { if (threadIdx.x == 0 && (i) < 4096) g_solver_trace[(i)] = clock64(); } while (0)
+#define TRACE2(sgv, k) do { if (threadIdx.x == 0 && (sgv) == 6 && rd == warp) g_solver_trace[3000 + (k)] = clock64(); } while (0)
+#else
+#define TRACE(i) do { } while (0)
+#define TRACE2(sgv, k) do { } while (0)
+#endif
+
+__global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DeviceProblem P, const SolverSmemLayout lay) {
   Control *ctl = P.ctl;
   if (ctl->done) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *s_linv = reinterpret_cast<double *>(smem_raw);                          // kSolveMaxCols x 36
+  volatile int *s_flag = reinterpret_cast<volatile int *>(smem_raw + lay.off_flag);  // kSolveMaxCols
+  double *xs = lay.x_in_smem ? reinterpret_cast<double *>(smem_raw + lay.off_x) : P.xp;  // y / x vector
+  int *s_prog = reinterpret_cast<int *>(smem_raw + lay.off_prog);                 // 2 level segments
+  double *s_slots = reinterpret_cast<double *>(smem_raw + lay.off_slots);         // factor cache
+  const int staged = lay.staged;
   __shared__ int s_fail;
   __shared__ double red[kSolveThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = kSolveThreads / 32;
+  const int g = lane / 6, r = lane - 6 * g;  // lanes 30, 31: g == 5, never active
+  const int gl = 6 * g;                      // first lane of this lane's group
   double *L = P.sys;
-  double *bs = P.sys + 36 * (size_t)P.n_blocks;
+  const double *bs = P.sys + 36 * (size_t)P.n_blocks;
   const double *bp = bs + 6 * (size_t)P.n_fp;
-  double *x = P.xp;
+  const int seg_stride = (P.prog_max_seg + 3) & ~3;
+  const int NSEG = P.n_segments;
   if (tid == 0) s_fail = 0;
+  if (tid < kSolveMaxCols) s_flag[tid] = 0;
+  if (staged && NSEG > 0) stage_segment(s_prog, P.prog + P.prog_ptr[0], P.prog_ptr[1] - P.prog_ptr[0], tid);
+  stage_wait();
   __syncthreads();
+  // a block reference r >= 0 is a shared-memory slot, r < 0 is block -1-r in global memory
+  auto deref = [&](int ref) -> const double * {
+    return ref >= 0 ? s_slots + 36 * ref : L + 36 * (size_t)(-1 - ref);
+  };
 
-  // ---- numeric factorisation, level by level
-  for (int lv = 0; lv < P.n_levels; ++lv) {
-    for (int t = P.level_ptr[lv] + warp; t < P.level_ptr[lv + 1]; t += NW) {
-      const int j = P.level_col[t];
-      // 1. gather the updates of column j: L[dst] -= L[a] L[b]^T ; lane owns entries e, e+32
-      for (int u = P.upd_ptr[j]; u < P.upd_ptr[j + 1]; ++u) {
-        const double *A = L + 36 * (size_t)P.upd_a[u];
-        const double *B = L + 36 * (size_t)P.upd_b[u];
-        double *D = L + 36 * (size_t)P.upd_dst[u];
-        for (int e = lane; e < 36; e += 32) {
-          const int r = e / 6, c = e % 6;
-          double s = 0.0;
+  // ---- numeric factorisation + forward substitution, segment by segment (0 = prologue)
+  TRACE(0);
+  for (int sg = 0; sg < NSEG; ++sg) {
+    const int stamp = sg + 1;
+    TRACE(1 + 3 * sg);
+    const LevelSeg S(staged ? s_prog + (sg & 1) * seg_stride : P.prog + P.prog_ptr[sg]);
+    // asynchronously: the next segment's program, and the initial values (Schur complement) of
+    // the next level's blocks into their cache slots
+    if (staged && sg + 1 < NSEG)
+      stage_segment(s_prog + ((sg + 1) & 1) * seg_stride, P.prog + P.prog_ptr[sg + 1],
+                    P.prog_ptr[sg + 2] - P.prog_ptr[sg + 1], tid);
+    for (int i = tid; i < 18 * S.n_pf; i += kSolveThreads) {
+      const int e = i / 18, o = i - 18 * e;
+      const int slot = S.pf_slot[e];
+      if (slot >= 0) cp_async16(s_slots + 36 * slot + 2 * o, L + 36 * (size_t)S.pf_blk[e] + 2 * o);
+    }
+    for (int rd = warp; rd < S.n_rounds; rd += NW) {
+      const int type = S.round_type[rd];
+      const int kind = type & 3;
+      const bool reduce = (type & 4) != 0;
+      const int gt = 5 * rd + (g < 5 ? g : 0);
+      bool active = g < 5 && S.gt_dst[gt] >= 0;
+      const int dst = S.gt_dst[gt], slot = S.gt_slot[gt], pos = S.gt_pos[gt];
+      const int p0 = active ? S.gt_p0[gt] : 0, p1 = active ? S.gt_p1[gt] : 0;
+      double *linv = s_linv + 36 * pos;
+      TRACE2(sg, 0);
+      if (kind != 2) {
+        double *D = L + 36 * (size_t)(active ? dst : 0);
+        double *Ds = slot >= 0 ? s_slots + 36 * slot : D;
+        double v[6];
 #pragma unroll
-          for (int k = 0; k < 6; ++k) s += A[6 * r + k] * B[6 * c + k];
-          D[e] -= s;
+        for (int c = 0; c < 6; ++c) v[c] = 0.0;
+        if (active && (!reduce || g == 0)) {
+          const double2 *d2 = reinterpret_cast<const double2 *>(Ds + 6 * r);
+          const double2 t0 = d2[0], t1 = d2[1], t2 = d2[2];
+          v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y; v[4] = t2.x; v[5] = t2.y;
         }
-      }
-      __syncwarp();
-      // 2. diagonal block
-      double *Djj = L + 36 * (size_t)P.col_ptr[j];
-      if (lane == 0) {
-        double A[36];
+        double acc[6];
 #pragma unroll
-        for (int i = 0; i < 36; ++i) A[i] = Djj[i];
-        if (!chol6_inplace(A)) s_fail = 1;
+        for (int c = 0; c < 6; ++c) acc[c] = 0.0;
+        TRACE2(sg, 5);
+        for (int p = p0; p < p1; ++p) {
+          const double2 *A2 = reinterpret_cast<const double2 *>(deref(S.pa[p]) + 6 * r);
+          const double2 *B2 = reinterpret_cast<const double2 *>(deref(S.pb[p]));
+          const double2 a0 = A2[0], a1 = A2[1], a2 = A2[2];
 #pragma unroll
-        for (int i = 0; i < 36; ++i) Djj[i] = A[i];
-      }
-      __syncwarp();
-      // 3. sub-diagonal blocks: X L_jj^T = B, one lane per (block, row)
-      const int nb = P.col_ptr[j + 1] - P.col_ptr[j] - 1;
-      for (int w = lane; w < 6 * nb; w += 32) {
-        double *row = L + 36 * (size_t)(P.col_ptr[j] + 1 + w / 6) + 6 * (w % 6);
-        double xr[6];
+          for (int c = 0; c < 6; ++c) {
+            const double2 b0 = B2[3 * c], b1 = B2[3 * c + 1], b2 = B2[3 * c + 2];
+            acc[c] += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y;
+          }
+        }
+        TRACE2(sg, 1);
+        if (reduce) {
+#pragma unroll
+          for (int c = 0; c < 6; ++c) acc[c] = group_reduce(acc[c], lane);  // totals on lanes 0..5
+          active = active && g == 0;
+        }
+        if (active) {
+#pragma unroll
+          for (int c = 0; c < 6; ++c) v[c] -= acc[c];
+        }
+        if (kind == 0) {
+          // DIAG: right-looking 6x6 Cholesky inside each group, row r in lane gl + r
+          double invd[6];
+          bool bad = false;
+#pragma unroll
+          for (int p = 0; p < 6; ++p) {
+            double d = __shfl_sync(0xffffffffu, v[p], gl + p);
+            if (!(d > 0.0)) { bad = true; d = 1.0; }
+            const double inv = rsqrt(d);
+            invd[p] = inv;
+            if (r >= p) v[p] *= inv;
+#pragma unroll
+            for (int c = p + 1; c < 6; ++c) {
+              const double lcp = __shfl_sync(0xffffffffu, v[p], gl + c);
+              if (r >= c) v[c] -= v[p] * lcp;
+            }
+          }
+          TRACE2(sg, 2);
+          // X = L^-1, column r in lane gl + r: forward substitution against the identity
+          double X[6];
+#pragma unroll
+          for (int q = 0; q < 6; ++q) X[q] = 0.0;
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int k = 0; k < q; ++k) sacc += __shfl_sync(0xffffffffu, v[k], gl + q) * X[k];
+            X[q] = (q == r) ? invd[q] : -invd[q] * sacc;
+          }
+          if (active) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) { linv[6 * q + r] = X[q]; D[6 * q + r] = X[q]; }
+            if (bad) s_fail = 1;
+          }
+          TRACE2(sg, 3);
+          __threadfence_block();
+          __syncwarp();
+          if (active && r == 0) s_flag[pos] = stamp;
+          TRACE2(sg, 4);
+        } else {
+          // SUB: X = B L_jj^-T once the column's inverse diagonal block is out
+          while (!__all_sync(0xffffffffu, !active || s_flag[pos] == stamp)) { }
+          __threadfence_block();
+          if (active) {
+            double x[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+              double sacc = 0.0;
+#pragma unroll
+              for (int k = 0; k <= c; ++k) sacc += v[k] * linv[6 * c + k];
+              x[c] = sacc;
+            }
+            double2 *d2 = reinterpret_cast<double2 *>(D + 6 * r);
+            d2[0] = make_double2(x[0], x[1]); d2[1] = make_double2(x[2], x[3]); d2[2] = make_double2(x[4], x[5]);
+            if (slot >= 0) {
+              double2 *s2 = reinterpret_cast<double2 *>(Ds + 6 * r);
+              s2[0] = make_double2(x[0], x[1]); s2[1] = make_double2(x[2], x[3]); s2[2] = make_double2(x[4], x[5]);
+            }
+          }
+        }
+      } else {
+        // VEC: forward substitution y_j = L_jj^-1 (bschur_j - sum_k L(j,k) y_k)
+        const int j = active ? S.col_j[pos] : 0;
+        double acc = 0.0;
+        for (int p = p0; p < p1; ++p) {
+          const double2 *B2 = reinterpret_cast<const double2 *>(deref(S.pa[p]) + 6 * r);
+          const double *yk = xs + 6 * S.pb[p];
+          const double2 b0 = B2[0], b1 = B2[1], b2 = B2[2];
+          acc += b0.x * yk[0] + b0.y * yk[1] + b1.x * yk[2] + b1.y * yk[3] + b2.x * yk[4] + b2.y * yk[5];
+        }
+        if (reduce) { acc = group_reduce(acc, lane); active = active && g == 0; }
+        const double sv = active ? bs[6 * j + r] - acc : 0.0;
+        while (!__all_sync(0xffffffffu, !active || s_flag[pos] == stamp)) { }
+        __threadfence_block();
+        double y = 0.0;
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
-          double s = row[c];
-#pragma unroll
-          for (int k = 0; k < c; ++k) s -= xr[k] * Djj[6 * c + k];
-          xr[c] = s / Djj[7 * c];
+          const double sc = __shfl_sync(0xffffffffu, sv, gl + c);
+          if (active && c <= r) y += linv[6 * r + c] * sc;
         }
-#pragma unroll
-        for (int c = 0; c < 6; ++c) row[c] = xr[c];
+        if (active) xs[6 * j + r] = y;
       }
     }
+    TRACE(2 + 3 * sg);
+    stage_wait();
     __syncthreads();
+    TRACE(3 + 3 * sg);
   }
   const bool fail = s_fail != 0;
 
   if (!fail) {
-    // ---- forward: L y = bschur (rows by level)
-    for (int lv = 0; lv < P.n_levels; ++lv) {
-      for (int t = P.level_ptr[lv] + warp; t < P.level_ptr[lv + 1]; t += NW) {
-        const int j = P.level_col[t];
-        // lanes 0..5 own one component each
-        double s = lane < 6 ? bs[6 * j + lane] : 0.0;
-        if (lane < 6) {
-          for (int rr = P.row_ptr[j]; rr < P.row_ptr[j + 1]; ++rr) {
-            const double *B = L + 36 * (size_t)P.row_blk[rr] + 6 * lane;
-            const double *xk = x + 6 * P.row_col[rr];
-#pragma unroll
-            for (int c = 0; c < 6; ++c) s -= B[c] * xk[c];
-          }
+    // ---- backward: x_j = L_jj^-T (y_j - sum_{i > j} L(i,j)^T x_i), segments in reverse.  The
+    // program of the last segment is still in its buffer.  While level sg runs, the blocks of
+    // level sg-1 are copied into one half of the (now free) block cache.
+    const int half = lay.n_slots / 2;
+    for (int sg = NSEG - 1; sg >= 1; --sg) {
+      const LevelSeg S(staged ? s_prog + (sg & 1) * seg_stride : P.prog + P.prog_ptr[sg]);
+      if (staged && sg > 1)
+        stage_segment(s_prog + ((sg - 1) & 1) * seg_stride, P.prog + P.prog_ptr[sg - 1],
+                      P.prog_ptr[sg] - P.prog_ptr[sg - 1], tid);
+      {
+        const int nb = S.n_bpf < half ? S.n_bpf : half;
+        double *dstb = s_slots + 36 * (size_t)(((sg - 1) & 1) * half);
+        for (int i = tid; i < 18 * nb; i += kSolveThreads) {
+          const int e = i / 18, o = i - 18 * e;
+          cp_async16(dstb + 36 * e + 2 * o, L + 36 * (size_t)S.bpf_blk[e] + 2 * o);
         }
-        const double *Djj = L + 36 * (size_t)P.col_ptr[j];
-        // 6-step forward substitution across lanes 0..5
-        double y = 0.0;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          const double yc = __shfl_sync(0xffffffffu, s, c) / Djj[7 * c];
-          if (lane == c) y = yc;
-          if (lane > c && lane < 6) s -= Djj[6 * lane + c] * yc;
-        }
-        if (lane < 6) x[6 * j + lane] = y;
       }
-      __syncthreads();
-    }
-    // ---- backward: L^T x = y (levels in reverse)
-    for (int lv = P.n_levels - 1; lv >= 0; --lv) {
-      for (int t = P.level_ptr[lv] + warp; t < P.level_ptr[lv + 1]; t += NW) {
-        const int j = P.level_col[t];
-        double s = lane < 6 ? x[6 * j + lane] : 0.0;
-        if (lane < 6) {
-          for (int b = P.col_ptr[j] + 1; b < P.col_ptr[j + 1]; ++b) {
-            const double *B = L + 36 * (size_t)b;
-            const double *xi = x + 6 * P.blk_row[b];
+      const bool cached = sg != NSEG - 1;
+      const double *srcb = s_slots + 36 * (size_t)((sg & 1) * half);
+      for (int rd = warp; 5 * rd < S.n_cols; rd += NW) {
+        const int t = 5 * rd + g;
+        const bool active = g < 5 && t < S.n_cols;
+        const int tt = active ? t : 0;
+        const int j = S.col_j[tt];
+        const int b0 = S.col_b0[tt];
+        const int nb = active ? S.col_bptr[tt + 1] - S.col_bptr[tt] : 0;
+        const int *rows = S.brow + S.col_bptr[tt];
+        const int l0 = S.col_bptr[tt] + tt;  // level-local index of the diagonal block
+        double acc = 0.0;
+        for (int k = 0; k < nb; ++k) {
+          const int li = l0 + 1 + k;
+          const double *B = (cached && li < half) ? srcb + 36 * li : L + 36 * (size_t)(b0 + 1 + k);
+          const double *xi = xs + 6 * rows[k];
 #pragma unroll
-            for (int c = 0; c < 6; ++c) s -= B[6 * c + lane] * xi[c];
-          }
+          for (int c = 0; c < 6; ++c) acc += B[6 * c + r] * xi[c];
         }
-        const double *Djj = L + 36 * (size_t)P.col_ptr[j];
+        const double sv = active ? xs[6 * j + r] - acc : 0.0;
+        const double *Li = (cached && l0 < half) ? srcb + 36 * l0 : L + 36 * (size_t)b0;  // inverse diagonal block
         double xv = 0.0;
 #pragma unroll
-        for (int c = 5; c >= 0; --c) {
-          const double xc = __shfl_sync(0xffffffffu, s, c) / Djj[7 * c];
-          if (lane == c) xv = xc;
-          if (lane < c) s -= Djj[6 * c + lane] * xc;
+        for (int c = 0; c < 6; ++c) {
+          const double sc = __shfl_sync(0xffffffffu, sv, gl + c);
+          if (active && c >= r) xv += Li[6 * c + r] * sc;
         }
-        if (lane < 6) x[6 * j + lane] = xv;
+        if (active) xs[6 * j + r] = xv;
       }
+      stage_wait();
       __syncthreads();
+      TRACE(3 * NSEG + 1 + (NSEG - sg));
     }
   } else {
-    for (int i = tid; i < 6 * P.n_fp; i += kSolveThreads) x[i] = 0.0;
+    for (int i = tid; i < 6 * P.n_fp; i += kSolveThreads) xs[i] = 0.0;
     __syncthreads();
   }
 
@@ -505,7 +726,11 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
   const int cur = ctl->cur;
   const double lambda = ctl->lambda;
   double sc = 0.0;
-  for (int i = tid; i < 6 * P.n_fp; i += kSolveThreads) sc += x[i] * (lambda * x[i] + bp[i]);
+  for (int i = tid; i < 6 * P.n_fp; i += kSolveThreads) {
+    const double xi = xs[i];
+    sc += xi * (lambda * xi + bp[i]);
+    if (lay.x_in_smem) P.xp[i] = xi;
+  }
   sc = block_sum<kSolveThreads>(sc, red);
   for (int q = tid; q < P.n_fp; q += kSolveThreads) {
     const int kv = P.pose_of_q[q];
@@ -513,7 +738,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
 #pragma unroll
     for (int i = 0; i < 7; ++i) T[i] = P.pose[cur][7 * kv + i];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) d[i] = x[6 * q + i];
+    for (int i = 0; i < 6; ++i) d[i] = xs[6 * q + i];
     pose_oplus(T, d, out);
 #pragma unroll
     for (int i = 0; i < 7; ++i) P.pose[cur ^ 1][7 * kv + i] = fail ? T[i] : out[i];
@@ -522,6 +747,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
     ctl->scale_pose = sc;
     ctl->chol_fail = fail ? 1 : 0;
   }
+  TRACE(4 * NSEG + 2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -714,6 +940,13 @@ inline int div_up(long long a, int b) { return (int)((a + b - 1) / b); }
 
 int kernels_per_linearize() { return 3; }
 
+#ifdef SSBA_SOLVER_TRACE
+extern "C" int ssba_debug_solver_trace(long long *out, int n) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out, g_solver_trace, sizeof(long long) * (n < 4096 ? n : 4096));
+}
+#endif
+
 void launch_linearize(const DeviceProblem &P, cudaStream_t st) {
   k_linearize<<<P.n_lin_blocks, kLinThreads, 0, st>>>(P);
   if (P.n_chunks > 0) k_hpp<<<P.n_chunks, kHppThreads, 0, st>>>(P);
@@ -730,11 +963,23 @@ void launch_prepare_system(const DeviceProblem &P, cudaStream_t st) {
 }
 
 void launch_schur(const DeviceProblem &P, cudaStream_t st) {
-  k_schur<<<P.n_lin_blocks, kLinThreads, 0, st>>>(P);
+  static bool attr_set = false;
+  constexpr size_t kDyn = (size_t)kSchurWarps * kSchurRunPairs * 18 * sizeof(double);
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDyn);
+    attr_set = true;
+  }
+  if (P.n_units > 0) k_schur<<<div_up(P.n_units, kSchurWarps), 32 * kSchurWarps, kDyn, st>>>(P);
 }
 
 void launch_reduced_solve(const DeviceProblem &P, cudaStream_t st) {
-  k_reduced_solve<<<1, kSolveThreads, 0, st>>>(P);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_reduced_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveMaxDynSmem);
+    attr_set = true;
+  }
+  const SolverSmemLayout lay = solver_smem_layout(P.n_fp, P.prog_max_seg);
+  k_reduced_solve<<<1, kSolveThreads, lay.bytes, st>>>(P, lay);
 }
 
 void launch_update(const DeviceProblem &P, cudaStream_t st) {

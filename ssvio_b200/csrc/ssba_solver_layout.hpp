@@ -1,0 +1,42 @@
+// ssba_solver_layout.hpp — shared-memory budget of k_reduced_solve, shared by the host program
+// builder (slot allocation) and the kernel launch so that both agree on the layout.
+#pragma once
+
+#include <cstddef>
+
+namespace ssba {
+
+constexpr int kSolveThreads = 512;
+constexpr int kSolveMaxCols = 64;             // columns per level
+constexpr size_t kSolveMaxDynSmem = 226 * 1024;  // opt-in dynamic shared memory of the kernel
+
+struct SolverSmemLayout {
+  int x_in_smem;    // y / x vector in shared memory
+  int staged;       // level programs double-buffered in shared memory
+  int n_slots;      // 6x6 block slots of the factor cache
+  size_t off_flag, off_x, off_prog, off_slots, bytes;  // byte offsets into dynamic smem
+};
+
+inline SolverSmemLayout solver_smem_layout(int n_fp, int prog_max_seg_ints) {
+  SolverSmemLayout L{};
+  size_t b = 36 * sizeof(double) * kSolveMaxCols;  // inverse diagonal blocks of the level
+  L.off_flag = b;
+  b += sizeof(int) * kSolveMaxCols;
+  L.off_x = b;
+  const size_t xbytes = 6 * sizeof(double) * (size_t)n_fp;
+  L.x_in_smem = b + xbytes <= kSolveMaxDynSmem / 4 ? 1 : 0;
+  if (L.x_in_smem) b += xbytes;
+  b = (b + 15) & ~size_t(15);
+  L.off_prog = b;
+  const size_t pbytes = 2 * sizeof(int) * (size_t)((prog_max_seg_ints + 3) & ~3);
+  L.staged = b + pbytes <= kSolveMaxDynSmem / 2 ? 1 : 0;
+  if (L.staged) b += pbytes;
+  b = (b + 15) & ~size_t(15);
+  L.off_slots = b;
+  L.n_slots = (int)((kSolveMaxDynSmem - b) / (36 * sizeof(double)));
+  if (L.n_slots < 0) L.n_slots = 0;
+  L.bytes = b + (size_t)L.n_slots * 36 * sizeof(double);
+  return L;
+}
+
+}  // namespace ssba

@@ -1,9 +1,12 @@
 // ssba_structure.cpp — see ssba_structure.hpp.
 #include "ssba_structure.hpp"
+#include "ssba_solver_layout.hpp"
 
 #include <algorithm>
 #include <climits>
+#include <cmath>
 #include <cstring>
+#include <functional>
 #include <numeric>
 
 namespace ssba {
@@ -11,14 +14,388 @@ namespace ssba {
 namespace {
 
 constexpr int kHppChunk = 256;  // edges per pose-major chunk (one CTA each)
+constexpr int kMaxLevelCols = kSolveMaxCols;  // ssba_solver_layout.hpp
+constexpr int kSchurRunPairs = 160; // = kSchurRunPairs of k_schur
 
-// Order of elimination of the free poses in the reduced system.  The reference runs AMD on the
-// block pattern (linear_solver_csparse.h:262); any symmetric permutation gives the same x up to
-// rounding.  Sliding-window graphs are block-banded in key-frame order, where the natural order
-// is already fill-minimal, so that is what is used for now.
-void order_free_poses(int n, const std::vector<std::vector<int>> & /*adj*/, std::vector<int> &perm) {
-  perm.resize(n);
-  std::iota(perm.begin(), perm.end(), 0);
+// Symbolic factorisation of the reduced system under one elimination order, plus the schedule
+// the device solver walks: columns grouped by elimination-tree level, and per level the
+// left-looking update tasks  L(i,j) -= sum_k L(i,k) L(j,k)^T  grouped by destination block.
+struct Factor {
+  int n_blocks = 0, n_levels = 0, n_schur = 0;
+  double est_cycles = 0.0;
+  std::vector<int32_t> col_ptr, blk_row, blk_col, row_ptr, row_blk, row_col, level_ptr, level_col;
+  std::vector<int32_t> ltask_ptr, task_dst, task_pos, task_pair_ptr, pair_a, pair_b;
+};
+
+bool symbolic_factor(int n, const std::vector<std::vector<int>> &adj, const std::vector<int> &perm,
+                     Factor &f, std::string &err) {
+  std::vector<int> iperm(n);
+  for (int q = 0; q < n; ++q) iperm[perm[q]] = q;
+  std::vector<std::vector<int>> Acol(n);  // permuted strictly-lower pattern of S
+  f.n_schur = n;
+  for (int c = 0; c < n; ++c)
+    for (int r : adj[c]) {
+      int qc = iperm[c], qr = iperm[r];
+      if (qr < qc) std::swap(qr, qc);
+      Acol[qc].push_back(qr);
+      ++f.n_schur;
+    }
+  // column structure of L: struct(L_j) = struct(A_j) U (U over children c: struct(L_c) \ {j})
+  std::vector<std::vector<int>> Lcol(n);
+  {
+    std::vector<std::vector<int>> children(n);
+    std::vector<int> mark_v(n, -1), merged;
+    for (int j = 0; j < n; ++j) {
+      merged.clear();
+      mark_v[j] = j;
+      for (int r : Acol[j]) if (mark_v[r] != j) { mark_v[r] = j; merged.push_back(r); }
+      for (int c : children[j])
+        for (int r : Lcol[c]) if (r != j && mark_v[r] != j) { mark_v[r] = j; merged.push_back(r); }
+      std::sort(merged.begin(), merged.end());
+      Lcol[j] = merged;
+      if (!merged.empty()) children[merged[0]].push_back(j);  // etree parent = first sub-diagonal row
+    }
+  }
+  f.col_ptr.assign(n + 1, 0);
+  for (int j = 0; j < n; ++j) f.col_ptr[j + 1] = f.col_ptr[j] + 1 + (int)Lcol[j].size();
+  f.n_blocks = f.col_ptr[n];
+  f.blk_row.resize(f.n_blocks);
+  f.blk_col.resize(f.n_blocks);
+  for (int j = 0; j < n; ++j) {
+    int b = f.col_ptr[j];
+    f.blk_col[b] = j; f.blk_row[b++] = j;
+    for (int r : Lcol[j]) { f.blk_col[b] = j; f.blk_row[b++] = r; }
+  }
+  auto find_block = [&](int row, int col) -> int {
+    const int *b0 = f.blk_row.data() + f.col_ptr[col], *b1 = f.blk_row.data() + f.col_ptr[col + 1];
+    const int *it = std::lower_bound(b0, b1, row);
+    return (it != b1 && *it == row) ? (int)(it - f.blk_row.data()) : -1;
+  };
+  // strictly-lower blocks by row, ordered by column
+  f.row_ptr.assign(n + 1, 0);
+  for (int j = 0; j < n; ++j)
+    for (int r : Lcol[j]) ++f.row_ptr[r + 1];
+  for (int j = 0; j < n; ++j) f.row_ptr[j + 1] += f.row_ptr[j];
+  f.row_blk.resize(f.row_ptr[n]);
+  f.row_col.resize(f.row_ptr[n]);
+  {
+    std::vector<int32_t> fill(f.row_ptr.begin(), f.row_ptr.end() - 1);
+    for (int j = 0; j < n; ++j)
+      for (int b = f.col_ptr[j] + 1; b < f.col_ptr[j + 1]; ++b) {
+        const int r = f.blk_row[b];
+        f.row_blk[fill[r]] = b; f.row_col[fill[r]] = j; ++fill[r];
+      }
+  }
+  // elimination-tree levels: column j can start once every k with L(j,k) != 0 is done; a level
+  // holds at most kMaxLevelCols columns (the device keeps one inverse diagonal block per
+  // column of the running level in shared memory), wider levels are cut into several
+  std::vector<int> level(n, 0);
+  {
+    std::vector<int> dep(n, 0);
+    int nl = 0;
+    for (int j = 0; j < n; ++j) {
+      int lv = 0;
+      for (int t = f.row_ptr[j]; t < f.row_ptr[j + 1]; ++t) lv = std::max(lv, dep[f.row_col[t]] + 1);
+      dep[j] = lv; nl = std::max(nl, lv + 1);
+    }
+    std::vector<std::vector<int>> by_dep(nl);
+    for (int j = 0; j < n; ++j) by_dep[dep[j]].push_back(j);
+    f.level_ptr.assign(1, 0);
+    f.level_col.clear();
+    for (int d = 0; d < nl; ++d)
+      for (size_t o = 0; o < by_dep[d].size(); o += kMaxLevelCols) {
+        const size_t e = std::min(by_dep[d].size(), o + kMaxLevelCols);
+        for (size_t i = o; i < e; ++i) { level[by_dep[d][i]] = (int)f.level_ptr.size() - 1; f.level_col.push_back(by_dep[d][i]); }
+        f.level_ptr.push_back((int32_t)f.level_col.size());
+      }
+    f.n_levels = (int)f.level_ptr.size() - 1;
+  }
+  // Work items of the device solver, level by level.  Every block of a column of the level is
+  // one item:  L(i,j) <- (A(i,j) - sum_k L(i,k) L(j,k)^T) * L(j,j)^-T, the diagonal items of
+  // all columns first (the others wait for the inverse diagonal block they produce), then one
+  // "vector" item per column for the fused forward substitution y_j.  The pairs of an item are
+  // ordered by source column k (deterministic summation order).
+  f.ltask_ptr.assign(f.n_levels + 1, 0);
+  f.task_pair_ptr.assign(1, 0);
+  std::vector<std::vector<std::vector<std::pair<int, int>>>> per_dst;  // [col in level][block][pairs]
+  f.est_cycles = 0.0;
+  for (int lv = 0; lv < f.n_levels; ++lv) {
+    const int c0 = f.level_ptr[lv], nc = f.level_ptr[lv + 1] - c0;
+    per_dst.assign(nc, {});
+    long long level_pairs = 0; int max_rounds = 0, n_items = 0;
+    for (int t = 0; t < nc; ++t) {
+      const int j = f.level_col[c0 + t];
+      per_dst[t].assign(f.col_ptr[j + 1] - f.col_ptr[j], {});
+      for (int rr = f.row_ptr[j]; rr < f.row_ptr[j + 1]; ++rr) {
+        const int bjk = f.row_blk[rr], k = f.row_col[rr];
+        for (int bik = bjk; bik < f.col_ptr[k + 1]; ++bik) {  // rows i >= j of column k
+          const int dst = find_block(f.blk_row[bik], j);
+          if (dst < 0) { err = "internal: symbolic factorisation inconsistent"; return false; }
+          per_dst[t][dst - f.col_ptr[j]].emplace_back(bik, bjk);
+        }
+      }
+    }
+    auto emit = [&](int t, int d) {
+      const int j = f.level_col[c0 + t];
+      f.task_dst.push_back(f.col_ptr[j] + d);
+      f.task_pos.push_back(t);
+      for (auto &ab : per_dst[t][d]) { f.pair_a.push_back(ab.first); f.pair_b.push_back(ab.second); }
+      f.task_pair_ptr.push_back((int32_t)f.pair_a.size());
+      level_pairs += (long long)per_dst[t][d].size();
+      max_rounds = std::max(max_rounds, ((int)per_dst[t][d].size() + 4) / 5);
+      ++n_items;
+    };
+    for (int t = 0; t < nc; ++t) emit(t, 0);                       // diagonal items first
+    for (int t = 0; t < nc; ++t)
+      for (int d = 1; d < (int)per_dst[t].size(); ++d) emit(t, d);   // sub-diagonal items
+    for (int t = 0; t < nc; ++t) {                                  // forward-substitution items
+      f.task_dst.push_back(-1 - f.level_col[c0 + t]);
+      f.task_pos.push_back(t);
+      f.task_pair_ptr.push_back((int32_t)f.pair_a.size());
+      ++n_items;
+    }
+    f.ltask_ptr[lv + 1] = (int32_t)f.task_dst.size();
+    // cost model of one level on one SM (cycles): items round-robin over 32 warps, each paying
+    // an L2 round trip, plus the diagonal factor on the critical path and a barrier
+    const double rounds_per_warp = std::ceil(n_items / 32.0);
+    f.est_cycles += std::max(900.0 * rounds_per_warp + 100.0 * max_rounds, 5.0 * (double)level_pairs) + 1400.0;
+  }
+  f.est_cycles += 1200.0 * f.n_levels;  // backward substitution
+  return true;
+}
+
+// Packs everything the device solver needs to walk one level into one contiguous int32 segment
+// (a level's indices are staged into shared memory with one asynchronous copy).  Segment 0 is a
+// prologue without columns that only prefetches the blocks of level 0; segment 1 + lv is level lv.
+//
+// The work of a level is cut into warp "rounds" of five group tasks (a warp = 5 groups of 6
+// lanes, lane r of a group owns row r of a 6x6 block):
+//   DIAG round  five diagonal blocks: update, 6x6 Cholesky, inverse -> published per column
+//   SUB  round  five sub-diagonal blocks: update, wait for the column's inverse, multiply
+//   VEC  round  five forward substitutions y_j
+// A block with many update pairs gets a round of its own with its pairs split five ways
+// (REDUCE flag: the groups' partial sums are added before group 0 finishes the block).
+//   header[8] = {n_cols, n_rounds, n_pairs, n_brows, n_pf, n_bpf, 0, 0}
+//   col_j[n_cols] col_b0[n_cols] col_bptr[n_cols+1] brow[n_brows]          (backward pass)
+//   round_type[n_rounds]                       bits 0-1: 0 DIAG 1 SUB 2 VEC, bit 2: REDUCE
+//   gt_dst[5 n_rounds] gt_slot[..] gt_pos[..] gt_p0[..] gt_p1[..]           (group tasks)
+//   pa[n_pairs] pb[n_pairs]      block refs; for VEC tasks pb is the column k of y_k
+//   pf_blk[n_pf] pf_slot[n_pf]   blocks of the NEXT level to prefetch into their cache slots
+//   bpf_blk[n_bpf]               blocks of the PREVIOUS level (backward pass prefetch)
+// Factor blocks live in global memory; a shared-memory cache of `n_slots` 6x6 slots is planned
+// here on the host (interval allocation over the levels).  A block reference r >= 0 is slot r,
+// r < 0 is block -1-r in global memory.
+void build_solver_program(Structure &s) {
+  constexpr int kSplitPairs = 10;  // blocks with more update pairs get a REDUCE round
+  const int n = s.n_fp, NL = s.n_levels;
+  std::vector<int> level_of(n, 0);
+  for (int lv = 0; lv < NL; ++lv)
+    for (int t = s.level_ptr[lv]; t < s.level_ptr[lv + 1]; ++t) level_of[s.level_col[t]] = lv;
+  auto level_blocks = [&](int lv) {
+    int nb = 0;
+    for (int t = s.level_ptr[lv]; t < s.level_ptr[lv + 1]; ++t) { const int j = s.level_col[t]; nb += s.col_ptr[j + 1] - s.col_ptr[j]; }
+    return nb;
+  };
+  // ---- rounds of every level (slot-independent part)
+  struct GT { int dst, pos, p0, p1; };             // pairs index the level-local pair arrays
+  struct Round { int type; GT g[5]; };
+  struct LevelPlan { std::vector<Round> rounds; std::vector<std::pair<int, int>> pairs; /* (a block, b block | column) */ };
+  std::vector<LevelPlan> plan(NL);
+  for (int lv = 0; lv < NL; ++lv) {
+    LevelPlan &lp = plan[lv];
+    const int c0 = s.level_ptr[lv], nc = s.level_ptr[lv + 1] - c0;
+    const int t0 = s.ltask_ptr[lv], nt = s.ltask_ptr[lv + 1] - t0;
+    std::vector<GT> diag, sub, vec, big_diag, big_sub, big_vec;
+    for (int t = 0; t < nt; ++t) {
+      const int d = s.task_dst[t0 + t], pos = s.task_pos[t0 + t];
+      GT gt{d, pos, (int)lp.pairs.size(), 0};
+      if (d >= 0) {
+        for (int p = s.task_pair_ptr[t0 + t]; p < s.task_pair_ptr[t0 + t + 1]; ++p) lp.pairs.emplace_back(s.pair_a[p], s.pair_b[p]);
+      } else {
+        const int j = s.level_col[c0 + pos];
+        for (int rr = s.row_ptr[j]; rr < s.row_ptr[j + 1]; ++rr) lp.pairs.emplace_back(s.row_blk[rr], -1 - s.row_col[rr]);
+      }
+      gt.p1 = (int)lp.pairs.size();
+      const bool big = gt.p1 - gt.p0 > kSplitPairs;
+      if (d < 0) (big ? big_vec : vec).push_back(gt);
+      else if (s.blk_row[d] == s.blk_col[d]) (big ? big_diag : diag).push_back(gt);
+      else (big ? big_sub : sub).push_back(gt);
+    }
+    (void)nc;
+    auto pack5 = [&](const std::vector<GT> &v, int type) {
+      for (size_t i = 0; i < v.size(); i += 5) {
+        Round r{type, {}};
+        for (int k = 0; k < 5; ++k) r.g[k] = i + k < v.size() ? v[i + k] : GT{-1, 0, 0, 0};
+        if (type == 2) for (int k = 0; k < 5; ++k) if (i + k < v.size()) r.g[k].dst = 0;  // VEC: dst >= 0 marks "active"
+        lp.rounds.push_back(r);
+      }
+    };
+    auto split5 = [&](const std::vector<GT> &v, int type) {
+      for (const GT &gt : v) {
+        Round r{type | 4, {}};
+        const int np = gt.p1 - gt.p0;
+        for (int k = 0; k < 5; ++k) {
+          r.g[k] = GT{type == 2 ? 0 : gt.dst, gt.pos, gt.p0 + (int)((long long)np * k / 5), gt.p0 + (int)((long long)np * (k + 1) / 5)};
+        }
+        lp.rounds.push_back(r);
+      }
+    };
+    // order matters for the wait-free argument: every DIAG round precedes every SUB / VEC round
+    split5(big_diag, 0); pack5(diag, 0);
+    split5(big_sub, 1); pack5(sub, 1);
+    split5(big_vec, 2); pack5(vec, 2);
+  }
+  // ---- pass 1: segment sizes
+  std::vector<int> seg_size(NL + 1, 0);
+  seg_size[0] = 8 + 1 + 2 * (NL > 0 ? level_blocks(0) : 0);
+  for (int lv = 0; lv < NL; ++lv) {
+    const int c0 = s.level_ptr[lv], nc = s.level_ptr[lv + 1] - c0;
+    int nb = 0;
+    for (int t = 0; t < nc; ++t) { const int j = s.level_col[c0 + t]; nb += s.col_ptr[j + 1] - s.col_ptr[j] - 1; }
+    const int npf = lv + 1 < NL ? level_blocks(lv + 1) : 0;
+    const int nbpf = lv > 0 ? level_blocks(lv - 1) : 0;
+    const int nr = (int)plan[lv].rounds.size();
+    seg_size[lv + 1] = 8 + 2 * nc + (nc + 1) + nb + nr + 25 * nr + 2 * (int)plan[lv].pairs.size() + 2 * npf + nbpf;
+  }
+  s.prog_max_seg = 0;
+  for (int v : seg_size) s.prog_max_seg = std::max(s.prog_max_seg, (v + 3) & ~3);
+  const SolverSmemLayout lay = solver_smem_layout(n, s.prog_max_seg);
+  // ---- slot plan: block (i,k) is resident from the level before its column's (prefetch) until
+  // the level of its row i, where it is read for the last time
+  std::vector<int32_t> slot_of(s.n_blocks, -1);
+  {
+    std::vector<int> free_list;
+    for (int v = lay.n_slots - 1; v >= 0; --v) free_list.push_back(v);
+    std::vector<std::vector<int>> free_after(NL);
+    for (int lv = 0; lv < NL; ++lv) {
+      // blocks of level lv are allocated when level lv-1 starts; slots released after lv-2
+      if (lv >= 2) for (int b : free_after[lv - 2]) free_list.push_back(slot_of[b]);
+      for (int t = s.level_ptr[lv]; t < s.level_ptr[lv + 1]; ++t) {
+        const int j = s.level_col[t];
+        for (int b = s.col_ptr[j + 1] - 1; b >= s.col_ptr[j]; --b) {
+          if (free_list.empty()) break;
+          slot_of[b] = free_list.back(); free_list.pop_back();
+          free_after[level_of[s.blk_row[b]]].push_back(b);
+        }
+      }
+    }
+  }
+  s.solver_slots = lay.n_slots;
+  s.solver_cached_blocks = 0;
+  for (int v : slot_of) if (v >= 0) ++s.solver_cached_blocks;
+  auto ref = [&](int b) { return slot_of[b] >= 0 ? slot_of[b] : -1 - b; };
+  // ---- pass 2: emit
+  std::vector<int32_t> &P = s.prog;
+  P.clear();
+  s.prog_ptr.assign(1, 0);
+  auto emit_level_blocks = [&](int lv, bool with_slots) {
+    if (lv < 0 || lv >= NL) return;
+    for (int t = s.level_ptr[lv]; t < s.level_ptr[lv + 1]; ++t) { const int j = s.level_col[t]; for (int b = s.col_ptr[j]; b < s.col_ptr[j + 1]; ++b) P.push_back(b); }
+    if (with_slots)
+      for (int t = s.level_ptr[lv]; t < s.level_ptr[lv + 1]; ++t) { const int j = s.level_col[t]; for (int b = s.col_ptr[j]; b < s.col_ptr[j + 1]; ++b) P.push_back(slot_of[b]); }
+  };
+  auto close_seg = [&]() { while (P.size() % 4) P.push_back(0); s.prog_ptr.push_back((int32_t)P.size()); };
+  {  // prologue
+    const int npf = NL > 0 ? level_blocks(0) : 0;
+    P.insert(P.end(), {0, 0, 0, 0, npf, 0, 0, 0});
+    P.push_back(0);  // col_bptr[0]
+    emit_level_blocks(0, true);
+    close_seg();
+  }
+  s.solver_rounds = 0;
+  for (int lv = 0; lv < NL; ++lv) {
+    const LevelPlan &lp = plan[lv];
+    const int c0 = s.level_ptr[lv], nc = s.level_ptr[lv + 1] - c0;
+    int nb = 0;
+    for (int t = 0; t < nc; ++t) { const int j = s.level_col[c0 + t]; nb += s.col_ptr[j + 1] - s.col_ptr[j] - 1; }
+    const int npf = lv + 1 < NL ? level_blocks(lv + 1) : 0;
+    const int nbpf = lv > 0 ? level_blocks(lv - 1) : 0;
+    const int nr = (int)lp.rounds.size(), np = (int)lp.pairs.size();
+    s.solver_rounds += nr;
+    P.insert(P.end(), {nc, nr, np, nb, npf, nbpf, 0, 0});
+    for (int t = 0; t < nc; ++t) P.push_back(s.level_col[c0 + t]);
+    for (int t = 0; t < nc; ++t) P.push_back(s.col_ptr[s.level_col[c0 + t]]);
+    int acc = 0;
+    for (int t = 0; t < nc; ++t) { P.push_back(acc); const int j = s.level_col[c0 + t]; acc += s.col_ptr[j + 1] - s.col_ptr[j] - 1; }
+    P.push_back(acc);
+    for (int t = 0; t < nc; ++t) { const int j = s.level_col[c0 + t]; for (int b = s.col_ptr[j] + 1; b < s.col_ptr[j + 1]; ++b) P.push_back(s.blk_row[b]); }
+    for (const Round &r : lp.rounds) P.push_back(r.type);
+    for (const Round &r : lp.rounds) for (int k = 0; k < 5; ++k) P.push_back(r.g[k].dst);
+    for (const Round &r : lp.rounds) for (int k = 0; k < 5; ++k) P.push_back(((r.type & 3) != 2 && r.g[k].dst >= 0) ? slot_of[r.g[k].dst] : -1);
+    for (const Round &r : lp.rounds) for (int k = 0; k < 5; ++k) P.push_back(r.g[k].pos);
+    for (const Round &r : lp.rounds) for (int k = 0; k < 5; ++k) P.push_back(r.g[k].p0);
+    for (const Round &r : lp.rounds) for (int k = 0; k < 5; ++k) P.push_back(r.g[k].p1);
+    for (auto &ab : lp.pairs) P.push_back(ref(ab.first));
+    for (auto &ab : lp.pairs) P.push_back(ab.second >= 0 ? ref(ab.second) : -1 - ab.second);  // VEC: column k
+    emit_level_blocks(lv + 1, true);
+    emit_level_blocks(lv - 1, false);
+    close_seg();
+  }
+  s.n_segments = NL + 1;
+}
+
+// Nested dissection by BFS level structures: the middle level of a breadth-first sweep from a
+// pseudo-peripheral vertex separates the component; sub-graphs are ordered first, separators
+// last.  Turns the chain-shaped elimination tree of a sliding-window (block-banded) reduced
+// system into a tree of height O(bandwidth * log n).  Plays the role of cs_amd at
+// linear_solver_csparse.h:262 (any order gives the same solution up to rounding).
+void nested_dissection_order(int n, const std::vector<std::vector<int>> &adj_lower, std::vector<int> &perm) {
+  constexpr int kLeaf = 8;
+  std::vector<std::vector<int>> nb(n);
+  for (int c = 0; c < n; ++c)
+    for (int r : adj_lower[c]) { nb[c].push_back(r); nb[r].push_back(c); }
+  perm.clear();
+  perm.reserve(n);
+  std::vector<int> tag(n, 0), dist(n, -1), queue;
+  int cur_tag = 0;
+  struct Job { std::vector<int> nodes; };
+  // explicit recursion with post-order emission: (nodes, separator-to-emit-after)
+  std::function<void(std::vector<int> &)> rec = [&](std::vector<int> &nodes) {
+    if ((int)nodes.size() <= kLeaf) { std::sort(nodes.begin(), nodes.end()); for (int v : nodes) perm.push_back(v); return; }
+    const int my = ++cur_tag;
+    for (int v : nodes) tag[v] = my;
+    auto bfs = [&](int src, std::vector<int> &order) {
+      order.clear();
+      for (int v : nodes) dist[v] = -1;
+      dist[src] = 0; order.push_back(src);
+      for (size_t h = 0; h < order.size(); ++h)
+        for (int w : nb[order[h]]) if (tag[w] == my && dist[w] < 0) { dist[w] = dist[order[h]] + 1; order.push_back(w); }
+    };
+    std::vector<int> order;
+    bfs(*std::min_element(nodes.begin(), nodes.end()), order);
+    if (order.size() < nodes.size()) {  // disconnected: order every component on its own
+      std::vector<int> comp(order), rest;
+      for (int v : nodes) if (dist[v] < 0) rest.push_back(v);
+      rec(comp);
+      rec(rest);
+      return;
+    }
+    bfs(order.back(), order);  // second sweep from the far end: pseudo-peripheral start
+    const int depth = dist[order.back()];
+    if (depth < 2) { std::sort(nodes.begin(), nodes.end()); for (int v : nodes) perm.push_back(v); return; }
+    // level whose removal balances the two sides best
+    std::vector<int> cnt(depth + 1, 0);
+    for (int v : nodes) ++cnt[dist[v]];
+    int best = -1; long long best_cost = -1, below = cnt[0];
+    for (int m = 1; m < depth; ++m) {
+      const long long above = (long long)nodes.size() - below - cnt[m];
+      const long long cost = std::max(below, above) + 2LL * cnt[m];
+      if (best < 0 || cost < best_cost) { best = m; best_cost = cost; }
+      below += cnt[m];
+    }
+    std::vector<int> lo, hi, sep;
+    for (int v : nodes) (dist[v] < best ? lo : dist[v] > best ? hi : sep).push_back(v);
+    if (lo.empty() || hi.empty() || sep.size() * 2 >= nodes.size()) {
+      std::sort(nodes.begin(), nodes.end()); for (int v : nodes) perm.push_back(v); return;
+    }
+    rec(lo);
+    rec(hi);
+    std::sort(sep.begin(), sep.end());
+    for (int v : sep) perm.push_back(v);
+  };
+  std::vector<int> all(n);
+  std::iota(all.begin(), all.end(), 0);
+  rec(all);
 }
 
 }  // namespace
@@ -103,118 +480,85 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     for (uint64_t k : keys) { const int c = (int)(k / n), r = (int)(k % n); if (r != c) adj[c].push_back(r); }
   }
 
-  // ---- elimination order and symbolic factorisation over q
-  std::vector<int> perm;   // q -> free pose index
-  order_free_poses(n, adj, perm);
-  std::vector<int> iperm(n);
-  for (int q = 0; q < n; ++q) iperm[perm[q]] = q;
-  s.q_of_pose.assign(NK, -1);
-  s.pose_of_q.resize(n);
-  for (int f = 0; f < n; ++f) { s.q_of_pose[free_pose_rows[f]] = iperm[f]; s.pose_of_q[iperm[f]] = free_pose_rows[f]; }
-
-  std::vector<std::vector<int>> Acol(n);  // permuted strictly-lower pattern of S
-  int n_schur = n;
-  for (int c = 0; c < n; ++c)
-    for (int r : adj[c]) {
-      int qc = iperm[c], qr = iperm[r];
-      if (qr < qc) std::swap(qr, qc);
-      Acol[qc].push_back(qr);
-      ++n_schur;
-    }
-  s.n_schur_blocks = n_schur;
-  // column structure of L: struct(L_j) = struct(A_j) U (U over children c: struct(L_c) \ {j})
-  std::vector<std::vector<int>> Lcol(n);
+  // ---- elimination order and symbolic factorisation over q: natural order vs nested
+  // dissection, whichever the cost model of the level-scheduled device solver prefers
   {
-    std::vector<std::vector<int>> children(n);
-    std::vector<int> mark_v(n, -1), merged;
-    for (int j = 0; j < n; ++j) {
-      merged.clear();
-      mark_v[j] = j;
-      for (int r : Acol[j]) if (mark_v[r] != j) { mark_v[r] = j; merged.push_back(r); }
-      for (int c : children[j])
-        for (int r : Lcol[c]) if (r != j && mark_v[r] != j) { mark_v[r] = j; merged.push_back(r); }
-      std::sort(merged.begin(), merged.end());
-      Lcol[j] = merged;
-      if (!merged.empty()) children[merged[0]].push_back(j);  // etree parent = first sub-diagonal row
+    std::vector<int> perm_nat(n), perm_nd;
+    std::iota(perm_nat.begin(), perm_nat.end(), 0);
+    Factor f_nat, f_nd;
+    if (!symbolic_factor(n, adj, perm_nat, f_nat, err)) return false;
+    Factor *best = &f_nat;
+    std::vector<int> *best_perm = &perm_nat;
+    if (n >= 24) {
+      nested_dissection_order(n, adj, perm_nd);
+      if (perm_nd != perm_nat) {
+        if (!symbolic_factor(n, adj, perm_nd, f_nd, err)) return false;
+        if (f_nd.est_cycles < f_nat.est_cycles) { best = &f_nd; best_perm = &perm_nd; }
+      }
     }
-  }
-  s.col_ptr.assign(n + 1, 0);
-  for (int j = 0; j < n; ++j) s.col_ptr[j + 1] = s.col_ptr[j] + 1 + (int)Lcol[j].size();
-  s.n_blocks = s.col_ptr[n];
-  s.blk_row.resize(s.n_blocks);
-  s.blk_col.resize(s.n_blocks);
-  for (int j = 0; j < n; ++j) {
-    int b = s.col_ptr[j];
-    s.blk_col[b] = j; s.blk_row[b++] = j;
-    for (int r : Lcol[j]) { s.blk_col[b] = j; s.blk_row[b++] = r; }
+    const std::vector<int> &perm = *best_perm;  // q -> free pose index
+    s.q_of_pose.assign(NK, -1);
+    s.pose_of_q.resize(n);
+    for (int q = 0; q < n; ++q) { s.q_of_pose[free_pose_rows[perm[q]]] = q; s.pose_of_q[q] = free_pose_rows[perm[q]]; }
+    s.n_schur_blocks = best->n_schur;
+    s.n_blocks = best->n_blocks; s.n_levels = best->n_levels; s.n_tasks = (int)best->task_dst.size();
+    s.est_solver_cycles = best->est_cycles;
+    s.col_ptr.swap(best->col_ptr); s.blk_row.swap(best->blk_row); s.blk_col.swap(best->blk_col);
+    s.row_ptr.swap(best->row_ptr); s.row_blk.swap(best->row_blk); s.row_col.swap(best->row_col);
+    s.level_ptr.swap(best->level_ptr); s.level_col.swap(best->level_col);
+    s.ltask_ptr.swap(best->ltask_ptr); s.task_dst.swap(best->task_dst); s.task_pos.swap(best->task_pos); s.task_pair_ptr.swap(best->task_pair_ptr);
+    s.pair_a.swap(best->pair_a); s.pair_b.swap(best->pair_b);
+    build_solver_program(s);
   }
   auto find_block = [&](int row, int col) -> int {  // row >= col
     const int *b0 = s.blk_row.data() + s.col_ptr[col], *b1 = s.blk_row.data() + s.col_ptr[col + 1];
     const int *it = std::lower_bound(b0, b1, row);
     return (it != b1 && *it == row) ? (int)(it - s.blk_row.data()) : -1;
   };
-  // strictly-lower blocks by row, ordered by column
-  s.row_ptr.assign(n + 1, 0);
-  for (int j = 0; j < n; ++j)
-    for (int r : Lcol[j]) ++s.row_ptr[r + 1];
-  for (int j = 0; j < n; ++j) s.row_ptr[j + 1] += s.row_ptr[j];
-  s.row_blk.resize(s.row_ptr[n]);
-  s.row_col.resize(s.row_ptr[n]);
-  {
-    std::vector<int32_t> fill(s.row_ptr.begin(), s.row_ptr.end() - 1);
-    for (int j = 0; j < n; ++j)
-      for (int b = s.col_ptr[j] + 1; b < s.col_ptr[j + 1]; ++b) {
-        const int r = s.blk_row[b];
-        s.row_blk[fill[r]] = b; s.row_col[fill[r]] = j; ++fill[r];
-      }
-  }
-  // left-looking update lists: column j gathers L(i,k) L(j,k)^T for every k < j with L(j,k) != 0
-  s.upd_ptr.assign(n + 1, 0);
-  for (int j = 0; j < n; ++j) {
-    int cnt = 0;
-    for (int t = s.row_ptr[j]; t < s.row_ptr[j + 1]; ++t) {
-      const int bjk = s.row_blk[t], k = s.row_col[t];
-      cnt += s.col_ptr[k + 1] - bjk;  // rows i >= j of column k
-    }
-    s.upd_ptr[j + 1] = s.upd_ptr[j] + cnt;
-  }
-  s.upd_dst.resize(s.upd_ptr[n]); s.upd_a.resize(s.upd_ptr[n]); s.upd_b.resize(s.upd_ptr[n]);
-  for (int j = 0; j < n; ++j) {
-    int w = s.upd_ptr[j];
-    for (int t = s.row_ptr[j]; t < s.row_ptr[j + 1]; ++t) {
-      const int bjk = s.row_blk[t], k = s.row_col[t];
-      for (int bik = bjk; bik < s.col_ptr[k + 1]; ++bik) {
-        const int dst = find_block(s.blk_row[bik], j);
-        if (dst < 0) { err = "internal: symbolic factorisation inconsistent"; return false; }
-        s.upd_dst[w] = dst; s.upd_a[w] = bik; s.upd_b[w] = bjk; ++w;
-      }
-    }
-  }
-  // elimination-tree levels: column j can start once every k with L(j,k) != 0 is done
-  {
-    std::vector<int> level(n, 0);
-    int nl = 0;
-    for (int j = 0; j < n; ++j) {
-      int lv = 0;
-      for (int t = s.row_ptr[j]; t < s.row_ptr[j + 1]; ++t) lv = std::max(lv, level[s.row_col[t]] + 1);
-      level[j] = lv; nl = std::max(nl, lv + 1);
-    }
-    s.n_levels = n ? nl : 0;
-    s.level_ptr.assign(s.n_levels + 1, 0);
-    for (int j = 0; j < n; ++j) ++s.level_ptr[level[j] + 1];
-    for (int l = 0; l < s.n_levels; ++l) s.level_ptr[l + 1] += s.level_ptr[l];
-    s.level_col.resize(n);
-    std::vector<int32_t> fill(s.level_ptr.begin(), s.level_ptr.end() - 1);
-    for (int j = 0; j < n; ++j) s.level_col[fill[level[j]]++] = j;
-  }
 
-  // ---- landmark shard of this rank: contiguous runs of active landmarks, balanced by edges
+  // ---- landmark order: landmarks seen by the same set of free poses are made adjacent (sorted
+  // by first pose, then by a hash of the pose list), so that runs of landmarks accumulate into
+  // the same Schur blocks; then the shard of this rank = a contiguous range of that order,
+  // balanced by edge count
   std::vector<int32_t> slots;
   {
-    const long long total = n_active;
-    long long seen = 0;
+    std::vector<int32_t> act;
+    act.reserve(NP);
+    std::vector<uint64_t> key(NP, 0);
+    std::vector<int32_t> bucket_cnt(n + 2, 0);
+    std::vector<int32_t> minq(NP, n);
+    int ql[64];
     for (int j = 0; j < NP; ++j) {
       if (!point_active[j]) continue;
+      act.push_back(j);
+      int m = 0, mn = n;
+      uint64_t h = 1469598103934665603ull;
+      if (!g.point_fixed[j]) {
+        for (int k = pt_ptr[j]; k < pt_ptr[j + 1]; ++k) {
+          const int q = s.q_of_pose[g.e_pose[pt_edges[k]]];
+          if (q < 0) continue;
+          if (q < mn) mn = q;
+          if (m < 64) { int i = m++; while (i > 0 && ql[i - 1] > q) { ql[i] = ql[i - 1]; --i; } ql[i] = q; }
+        }
+        int prev = -1;
+        for (int i = 0; i < m; ++i) if (ql[i] != prev) { prev = ql[i]; h = (h ^ (uint64_t)(prev + 1)) * 1099511628211ull; }
+      }
+      minq[j] = mn;
+      key[j] = h;
+      ++bucket_cnt[mn + 1];
+    }
+    for (int q = 0; q <= n; ++q) bucket_cnt[q + 1] += bucket_cnt[q];
+    std::vector<int32_t> sorted(act.size());
+    {
+      std::vector<int32_t> fill(bucket_cnt.begin(), bucket_cnt.end() - 1);
+      for (int j : act) sorted[fill[minq[j]]++] = j;
+    }
+    for (int q = 0; q <= n; ++q)
+      std::sort(sorted.begin() + bucket_cnt[q], sorted.begin() + bucket_cnt[q + 1],
+                [&](int x, int y) { return key[x] != key[y] ? key[x] < key[y] : x < y; });
+    const long long total = n_active;
+    long long seen = 0;
+    for (int j : sorted) {
       // owner = the rank whose edge-quantile holds the first edge of this landmark
       const int owner = total > 0 ? (int)std::min<long long>(world - 1, seen * world / total) : 0;
       if (owner == rank) slots.push_back(j);
@@ -275,6 +619,36 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   }
   s.n_pairs = (int)s.pair_vertex.size();
   s.n_edges = (int)s.e_orig.size();
+
+  // ---- Schur work units: a run of <= 32 consecutive free landmarks with the same W pose list
+  // x a chunk of <= 32 of its k(k+1)/2 block pairs (one lane per block pair, one warp per unit)
+  {
+    auto wcount = [&](int sl) {
+      int k = 0;
+      for (int a = s.slot_pair_ptr[sl]; a < s.slot_pair_ptr[sl + 1] && s.pair_q[a] >= 0; ++a) ++k;
+      return s.slot_free[sl] ? k : 0;
+    };
+    auto same_list = [&](int x, int y, int k) {
+      for (int i = 0; i < k; ++i)
+        if (s.pair_q[s.slot_pair_ptr[x] + i] != s.pair_q[s.slot_pair_ptr[y] + i]) return false;
+      return true;
+    };
+    int sl = 0;
+    while (sl < s.n_slots) {
+      const int k = wcount(sl);
+      if (k == 0) { ++sl; continue; }
+      int e = sl + 1;
+      // the run's W blocks are staged in shared memory by k_schur: at most kSchurRunPairs of them
+      const int max_run = std::max(1, std::min(32, kSchurRunPairs / k));
+      while (e < s.n_slots && e - sl < max_run && wcount(e) == k && same_list(sl, e, k)) ++e;
+      const int npairs = k * (k + 1) / 2;
+      for (int c0 = 0; c0 < npairs; c0 += 32) {
+        s.unit_slot.push_back(sl); s.unit_n.push_back(e - sl); s.unit_k.push_back(k); s.unit_c0.push_back(c0);
+      }
+      sl = e;
+    }
+    s.n_units = (int)s.unit_slot.size();
+  }
 
   // ---- pose-major copy (edges of this shard whose pose is free), cut into one-pose chunks
   {

@@ -55,6 +55,10 @@ struct Structure {
   // Schur accumulation targets: per free slot, for W-pairs i <= j (sorted by q): block (q_j, q_i)
   std::vector<int32_t> slot_combo_ptr; // n_slots + 1
   std::vector<int32_t> combo_blk;
+  // Schur work units (k_schur): run of landmarks [unit_slot, +unit_n) sharing one W pose list of
+  // unit_k poses, block pairs [unit_c0, +32) of its k(k+1)/2
+  int n_units = 0;
+  std::vector<int32_t> unit_slot, unit_n, unit_k, unit_c0;
   // ---- pose-major copy of the edges with a free pose, cut into chunks of one pose each
   int n_chunks = 0, n_pm_edges = 0;
   std::vector<int32_t> chunk_q, chunk_vertex, chunk_edge_ptr; // n_chunks (+1)
@@ -68,8 +72,22 @@ struct Structure {
   std::vector<int32_t> col_ptr;       // n_fp + 1, diagonal block first in every column
   std::vector<int32_t> blk_row;       // n_blocks
   std::vector<int32_t> blk_col;       // n_blocks
-  std::vector<int32_t> upd_ptr;       // n_fp + 1: left-looking updates of column j
-  std::vector<int32_t> upd_dst, upd_a, upd_b; // L[dst] -= L[a] * L[b]^T
+  // work items of the device solver, grouped by level (diagonal items first):
+  //   task_dst >= 0 : L[dst] <- (A[dst] - sum over its pairs of L[pair_a] L[pair_b]^T) L(j,j)^-T
+  //   task_dst <  0 : forward substitution of column j = -1 - task_dst
+  int n_tasks = 0;
+  std::vector<int32_t> ltask_ptr;     // n_levels + 1 -> tasks
+  std::vector<int32_t> task_dst;      // n_tasks
+  std::vector<int32_t> task_pos;      // n_tasks: position of the item's column inside its level
+  std::vector<int32_t> task_pair_ptr; // n_tasks + 1 -> pairs
+  std::vector<int32_t> pair_a, pair_b;
+  double est_solver_cycles = 0.0;     // cost model that picked the elimination order
+  // the same schedule packed level by level for the device (see build_solver_program)
+  std::vector<int32_t> prog, prog_ptr;
+  int prog_max_seg = 0;               // ints in the largest level segment
+  int n_segments = 0;                 // n_levels + 1 (prologue)
+  int solver_slots = 0, solver_cached_blocks = 0;  // shared-memory factor cache plan
+  int solver_rounds = 0;              // warp rounds of the factorisation
   std::vector<int32_t> row_ptr;       // n_fp + 1: strictly-lower blocks by row (forward solve)
   std::vector<int32_t> row_blk, row_col;
   std::vector<int32_t> level_ptr, level_col; // columns grouped by elimination-tree level

@@ -112,16 +112,22 @@ static void check_case(int nk, int np, int w, unsigned seed, bool fix0, int nfix
         }
     }
   for (int i = 0; i < N; ++i) b[i] = U(rng);
-  // left-looking by levels
-  for (int lv = 0; lv < s.n_levels; ++lv)
-    for (int t = s.level_ptr[lv]; t < s.level_ptr[lv + 1]; ++t) {
-      const int j = s.level_col[t];
-      for (int u = s.upd_ptr[j]; u < s.upd_ptr[j + 1]; ++u) {
-        const double *Aa = &L[36 * (size_t)s.upd_a[u]], *Bb = &L[36 * (size_t)s.upd_b[u]];
-        double *D = &L[36 * (size_t)s.upd_dst[u]];
-        CHECK(s.blk_col[s.upd_dst[u]] == j, "upd dst column");
+  // left-looking by levels: first every update task of the level, then factor its columns
+  for (int lv = 0; lv < s.n_levels; ++lv) {
+    CHECK(s.level_ptr[lv + 1] - s.level_ptr[lv] <= 64, "level too wide");
+    for (int t = s.ltask_ptr[lv]; t < s.ltask_ptr[lv + 1]; ++t) {
+      if (s.task_dst[t] < 0) { CHECK(s.level_col[s.level_ptr[lv] + s.task_pos[t]] == -1 - s.task_dst[t], "vec item pos"); continue; }
+      CHECK(s.level_col[s.level_ptr[lv] + s.task_pos[t]] == s.blk_col[s.task_dst[t]], "item pos");
+      double *D = &L[36 * (size_t)s.task_dst[t]];
+      for (int u = s.task_pair_ptr[t]; u < s.task_pair_ptr[t + 1]; ++u) {
+        const double *Aa = &L[36 * (size_t)s.pair_a[u]], *Bb = &L[36 * (size_t)s.pair_b[u]];
+        CHECK(s.blk_col[s.pair_a[u]] == s.blk_col[s.pair_b[u]], "pair columns differ");
+        CHECK(s.blk_row[s.pair_a[u]] == s.blk_row[s.task_dst[t]] && s.blk_row[s.pair_b[u]] == s.blk_col[s.task_dst[t]], "pair rows");
         for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) { double sacc = 0; for (int k = 0; k < 6; ++k) sacc += Aa[6 * r + k] * Bb[6 * c + k]; D[6 * r + c] -= sacc; }
       }
+    }
+    for (int t = s.level_ptr[lv]; t < s.level_ptr[lv + 1]; ++t) {
+      const int j = s.level_col[t];
       double *Djj = &L[36 * (size_t)s.col_ptr[j]];
       for (int jj = 0; jj < 6; ++jj) {
         double d = Djj[7 * jj];
@@ -138,6 +144,7 @@ static void check_case(int nk, int np, int w, unsigned seed, bool fix0, int nfix
           for (int c = 0; c < 6; ++c) row[c] = xr[c];
         }
     }
+  }
   for (int lv = 0; lv < s.n_levels; ++lv)
     for (int t = s.level_ptr[lv]; t < s.level_ptr[lv + 1]; ++t) {
       const int j = s.level_col[t];
@@ -172,8 +179,8 @@ static void check_case(int nk, int np, int w, unsigned seed, bool fix0, int nfix
     rmax = std::fmax(rmax, std::fabs(r)); bmax = std::fmax(bmax, std::fabs(b[i]));
   }
   CHECK(rmax < 1e-10 * (1 + bmax), "residual %.3e (n=%d blocks=%d levels=%d)", rmax, n, s.n_blocks, s.n_levels);
-  std::printf("case nk=%d np=%d w=%d fix0=%d nfix=%d loop=%d world=%d: n_fp=%d blocks=%d schur=%d levels=%d upd=%d resid=%.2e\n",
-              nk, np, w, (int)fix0, nfix, (int)loop, world, n, s.n_blocks, s.n_schur_blocks, s.n_levels, s.upd_ptr[n], rmax);
+  std::printf("case nk=%d np=%d w=%d fix0=%d nfix=%d loop=%d world=%d: n_fp=%d blocks=%d schur=%d levels=%d tasks=%d pairs=%d est=%.0f slots=%d cached=%d resid=%.2e\n",
+              nk, np, w, (int)fix0, nfix, (int)loop, world, n, s.n_blocks, s.n_schur_blocks, s.n_levels, s.n_tasks, (int)s.pair_a.size(), s.est_solver_cycles, s.solver_slots, s.solver_cached_blocks, rmax);
 }
 
 int main() {
@@ -182,6 +189,9 @@ int main() {
   check_case(30, 800, 5, 3, true, 25, false, 2);
   check_case(40, 1500, 4, 4, false, 10, true, 3);
   check_case(64, 3000, 5, 5, true, 0, true, 8);
+  check_case(100, 4000, 5, 6, false, 0, false, 1);
+  check_case(500, 20000, 5, 7, true, 0, false, 1);
+  check_case(12, 600, 12, 8, false, 0, false, 1);
   if (fails) { std::printf("%d FAILURES\n", fails); return 1; }
   std::printf("OK\n");
   return 0;
