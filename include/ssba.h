@@ -223,6 +223,15 @@ ssba_status ssba_chi2(ssba_handle *h, double *plain, double *robust);
 ssba_status ssba_count_outliers(ssba_handle *h, double chi2_threshold,
                                 int64_t *n_outliers, int64_t *n_inliers);
 
+/* ---- multi-GPU helpers ------------------------------------------------------------- */
+
+/* Host-only (needs no CUDA device): the landmark shard plan used when world_size > 1.
+ * owner_out[point] = rank that owns the landmark and all its edges, -1 if it has no active
+ * edge.  Contiguous runs of the landmark order, balanced by edge count. */
+ssba_status ssba_plan_shards(int32_t n_poses, const uint8_t *pose_fixed, int32_t n_points,
+                             const uint8_t *point_fixed, int32_t n_edges, const int32_t *pose_idx,
+                             const int32_t *point_idx, int32_t world_size, int32_t *owner_out);
+
 /* ---- instrumentation --------------------------------------------------------------- */
 
 ssba_status ssba_profile_get(ssba_handle *h, ssba_profile *out);

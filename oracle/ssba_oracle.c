@@ -277,6 +277,10 @@ typedef struct {
   double *S;    /* (6 n_fp)^2 dense, row-major, lower triangle used by the factorisation */
   int *first;   /* envelope: first non-zero column per row */
   double *bschur, *coeff;
+  /* landmark shard filter (multi-GPU parity tests): point row -> owning rank, NULL = all */
+  const int32_t *owner;
+  int rank;
+  uint8_t *cam0;
 } Prob;
 
 static double now_s(void) {
@@ -316,6 +320,7 @@ static void build_system(Prob *P) {
   memset(P->b, 0, sizeof(double) * (6 * P->n_fp + 3 * P->n_fl));
   for (int k = 0; k < P->n_active; ++k) {
     int e = P->active_edge[k];
+    if (P->owner && P->owner[P->epoint[e]] != P->rank) continue;
     int ip = P->pose_h[P->epose[e]], il = P->point_h[P->epoint[e]];
     double Jx[12], Jp[6], rho[3];
     ssba_oracle_edge_jacobians(P->K, P->ext + 7 * P->ecam[e], P->pose + 7 * P->epose[e],
@@ -392,19 +397,23 @@ static void skyline_solve(const double *L, int n, const int *first, double *x) {
   }
 }
 
-/* BlockSolver::solve with setLambda/restoreDiagonal folded in (block_solver.hpp:314-447,524-565).
- * Returns 0 when the reduced Cholesky fails. */
-static int solve_damped(Prob *P, double lambda) {
+/* The reduced (Schur) system of BlockSolver::solve (block_solver.hpp:334-400): upper block
+ * triangle of S = (Hpp + lambda I) - sum_l W Dinv W^T in P->S, bschur in P->bschur.  With a
+ * shard filter only the owned landmarks contribute and only rank 0 adds lambda, so that the
+ * per-rank systems add up to the full one. */
+static void assemble_reduced_system(Prob *P, double lambda) {
   const int np = P->n_fp, nl = P->n_fl, n = 6 * np;
   double *bl = P->b + n;
+  const double lam_p = (!P->owner || P->rank == 0) ? lambda : 0.0;
   /* Hschur = Hpp + lambda I, pattern of the Schur complement (:334-335, :534-539) */
   memset(P->S, 0, sizeof(double) * (size_t)n * n);
   for (int i = 0; i < np; ++i)
     for (int r = 0; r < 6; ++r)
       for (int c = 0; c < 6; ++c)
-        P->S[(size_t)(6 * i + r) * n + 6 * i + c] = P->Hpp[36 * i + 6 * r + c] + (r == c ? lambda : 0.0);
+        P->S[(size_t)(6 * i + r) * n + 6 * i + c] = P->Hpp[36 * i + 6 * r + c] + (r == c ? lam_p : 0.0);
   memset(P->coeff, 0, sizeof(double) * n);
   for (int l = 0; l < nl; ++l) { /* :342-393 */
+    if (P->owner && P->owner[P->fl_vertex[l]] != P->rank) continue;
     double D[9], *Di = P->Dinv + 9 * l, db[3];
     memcpy(D, P->Hll + 9 * l, sizeof(D));
     D[0] += lambda; D[4] += lambda; D[8] += lambda; /* :541-548 */
@@ -430,6 +439,15 @@ static int solve_damped(Prob *P, double lambda) {
     }
   }
   for (int i = 0; i < n; ++i) P->bschur[i] = P->b[i] - P->coeff[i]; /* :397-400 */
+}
+
+/* BlockSolver::solve with setLambda/restoreDiagonal folded in (block_solver.hpp:314-447,524-565).
+ * Returns 0 when the reduced Cholesky fails. */
+static int solve_damped(Prob *P, double lambda) {
+  const int np = P->n_fp, nl = P->n_fl, n = 6 * np;
+  double *bl = P->b + n;
+  (void)np;
+  assemble_reduced_system(P, lambda);
   /* mirror the upper block triangle into the lower one and take the envelope */
   for (int i = 0; i < n; ++i) {
     int f = i;
@@ -483,24 +501,18 @@ static int cmp_ll(const void *a, const void *b) {
   return (x > y) - (x < y);
 }
 
-int ssba_oracle_optimize(const double K[9], int32_t n_cams, const double *ext_qt,
-                         int32_t n_poses, const double *poses_qt, const uint8_t *pose_fixed,
-                         int32_t n_points, const double *points, const uint8_t *point_fixed,
-                         int32_t n_edges, const int32_t *pose_idx, const int32_t *point_idx,
-                         const uint8_t *cam_idx, const double *uv, double huber_delta,
-                         int32_t max_iters, int32_t jacobian_mode,
-                         double *poses_out, double *points_out, double *edge_err_out,
-                         ssba_report *report) {
-  (void)n_cams;
-  Prob Ps, *P = &Ps;
+/* Graph -> problem: active sets, index mapping, Hpl pattern, work arrays.  Returns 1 when there
+ * is nothing to optimise (optimize() would return -1), 0 otherwise. */
+static int prob_setup(Prob *P, const double K[9], const double *ext_qt, int32_t n_poses,
+                      const double *poses_qt, const uint8_t *pose_fixed, int32_t n_points,
+                      const double *points, const uint8_t *point_fixed, int32_t n_edges,
+                      const int32_t *pose_idx, const int32_t *point_idx, const uint8_t *cam_idx,
+                      const double *uv, double huber_delta, int32_t jacobian_mode) {
   memset(P, 0, sizeof(*P));
-  if (report) memset(report, 0, sizeof(*report));
-  double t_start = now_s();
   P->K = K; P->ext = ext_qt; P->uv = uv; P->epose = pose_idx; P->epoint = point_idx;
   P->n_poses = n_poses; P->n_points = n_points; P->n_edges = n_edges;
   P->huber = huber_delta; P->jac_mode = jacobian_mode;
-  uint8_t *cam0 = NULL;
-  if (!cam_idx) { cam0 = calloc(n_edges > 0 ? n_edges : 1, 1); P->ecam = cam0; } else P->ecam = cam_idx;
+  if (!cam_idx) { P->cam0 = calloc(n_edges > 0 ? n_edges : 1, 1); P->ecam = P->cam0; } else P->ecam = cam_idx;
 
   P->pose = malloc(sizeof(double) * 7 * (n_poses + 1));
   P->point = malloc(sizeof(double) * 3 * (n_points + 1));
@@ -535,11 +547,7 @@ int ssba_oracle_optimize(const double K[9], int32_t n_cams, const double *ext_qt
   free(pa); free(la);
 
   P->err = calloc(2 * (size_t)(n_edges + 1), sizeof(double));
-  int rc = 0, iterations = -1;
-  if (P->n_fp + P->n_fl == 0) { /* optimize(): "0 vertices to optimize" -> -1 (:368-371) */
-    if (report) { report->iterations = -1; report->last_result = SSBA_SOLVER_FAIL; }
-    goto finish;
-  }
+  if (P->n_fp + P->n_fl == 0) return 1; /* optimize(): "0 vertices to optimize" -> -1 (:368-371) */
 
   /* buildStructure (block_solver.hpp:102-256): one Hpl block per (free pose, free landmark)
    * pair, columns (= landmarks) hold their pose rows sorted (fillSparseBlockMatrixCCS). */
@@ -551,7 +559,6 @@ int ssba_oracle_optimize(const double K[9], int32_t n_cams, const double *ext_qt
       int ip = P->pose_h[pose_idx[e]], il = P->point_h[point_idx[e]];
       if (ip >= 0 && il >= 0) keys[nk++] = (long long)il * (P->n_fp + 1) + ip;
     }
-    /* sort + unique */
     qsort(keys, nk, sizeof(long long), cmp_ll);
     int nu = 0;
     for (int i = 0; i < nk; ++i) if (i == 0 || keys[i] != keys[i - 1]) keys[nu++] = keys[i];
@@ -589,6 +596,66 @@ int ssba_oracle_optimize(const double K[9], int32_t n_cams, const double *ext_qt
     P->first = malloc(sizeof(int) * (n + 1));
     P->bschur = malloc(sizeof(double) * (n + 1));
     P->coeff = malloc(sizeof(double) * (n + 1));
+  }
+  return 0;
+}
+
+static void prob_free(Prob *P) {
+  free(P->cam0); free(P->pose); free(P->point); free(P->pose_bak); free(P->point_bak);
+  free(P->pose_h); free(P->point_h); free(P->active_edge); free(P->fp_vertex); free(P->fl_vertex);
+  free(P->edge_pair); free(P->pair_pose); free(P->pair_lm); free(P->lm_pair_ptr);
+  free(P->Hpp); free(P->Hll); free(P->Hpl); free(P->b); free(P->x); free(P->err); free(P->Dinv);
+  free(P->S); free(P->first); free(P->bschur); free(P->coeff);
+}
+
+/* The reduced pose system at the initial estimate for one landmark shard (owner[point] == rank;
+ * owner == NULL: all landmarks): S_out is (6 n_fp)^2 row-major with the upper block triangle
+ * filled (as BlockSolver keeps it), b_out has 6 n_fp entries.  Summing the outputs of all ranks
+ * gives the full system — the identity behind the multi-GPU all-reduce. */
+int ssba_oracle_reduced_system(const double K[9], int32_t n_cams, const double *ext_qt,
+                               int32_t n_poses, const double *poses_qt, const uint8_t *pose_fixed,
+                               int32_t n_points, const double *points, const uint8_t *point_fixed,
+                               int32_t n_edges, const int32_t *pose_idx, const int32_t *point_idx,
+                               const uint8_t *cam_idx, const double *uv, double huber_delta,
+                               double lambda, const int32_t *owner, int32_t rank,
+                               int32_t max_free_poses, double *S_out, double *b_out, int32_t *n_free_poses) {
+  (void)n_cams;
+  Prob Ps, *P = &Ps;
+  int empty = prob_setup(P, K, ext_qt, n_poses, poses_qt, pose_fixed, n_points, points, point_fixed,
+                         n_edges, pose_idx, point_idx, cam_idx, uv, huber_delta, SSBA_JACOBIAN_ANALYTIC);
+  if (n_free_poses) *n_free_poses = P->n_fp;
+  int rc = 0;
+  if (empty || P->n_fp > max_free_poses) { rc = 1; }
+  else {
+    P->owner = owner; P->rank = rank;
+    compute_active_errors(P);
+    build_system(P);
+    assemble_reduced_system(P, lambda);
+    size_t n = 6 * (size_t)P->n_fp;
+    memcpy(S_out, P->S, sizeof(double) * n * n);
+    memcpy(b_out, P->bschur, sizeof(double) * n);
+  }
+  prob_free(P);
+  return rc;
+}
+
+int ssba_oracle_optimize(const double K[9], int32_t n_cams, const double *ext_qt,
+                         int32_t n_poses, const double *poses_qt, const uint8_t *pose_fixed,
+                         int32_t n_points, const double *points, const uint8_t *point_fixed,
+                         int32_t n_edges, const int32_t *pose_idx, const int32_t *point_idx,
+                         const uint8_t *cam_idx, const double *uv, double huber_delta,
+                         int32_t max_iters, int32_t jacobian_mode,
+                         double *poses_out, double *points_out, double *edge_err_out,
+                         ssba_report *report) {
+  (void)n_cams;
+  Prob Ps, *P = &Ps;
+  if (report) memset(report, 0, sizeof(*report));
+  double t_start = now_s();
+  int rc = 0, iterations = -1;
+  if (prob_setup(P, K, ext_qt, n_poses, poses_qt, pose_fixed, n_points, points, point_fixed, n_edges,
+                 pose_idx, point_idx, cam_idx, uv, huber_delta, jacobian_mode)) {
+    if (report) { report->iterations = -1; report->last_result = SSBA_SOLVER_FAIL; }
+    goto finish;
   }
 
   compute_active_errors(P);
@@ -659,10 +726,6 @@ finish:
   if (poses_out) memcpy(poses_out, P->pose, sizeof(double) * 7 * n_poses);
   if (points_out) memcpy(points_out, P->point, sizeof(double) * 3 * n_points);
   if (edge_err_out) memcpy(edge_err_out, P->err, sizeof(double) * 2 * n_edges);
-  free(cam0); free(P->pose); free(P->point); free(P->pose_bak); free(P->point_bak);
-  free(P->pose_h); free(P->point_h); free(P->active_edge); free(P->fp_vertex); free(P->fl_vertex);
-  free(P->edge_pair); free(P->pair_pose); free(P->pair_lm); free(P->lm_pair_ptr);
-  free(P->Hpp); free(P->Hll); free(P->Hpl); free(P->b); free(P->x); free(P->err); free(P->Dinv);
-  free(P->S); free(P->first); free(P->bschur); free(P->coeff);
+  prob_free(P);
   return rc;
 }

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "ssba_nccl_unique_id", "ssba_set_cameras", "ssba_set_poses", "ssba_set_points",
     "ssba_set_edges", "ssba_initialize", "ssba_optimize", "ssba_step", "ssba_reset_state",
     "ssba_get_poses", "ssba_get_points", "ssba_get_edge_errors", "ssba_chi2",
-    "ssba_count_outliers", "ssba_profile_get", "ssba_profile_reset", "ssba_get_problem_info",
+    "ssba_count_outliers", "ssba_plan_shards", "ssba_profile_get", "ssba_profile_reset", "ssba_get_problem_info",
     "ssba_version",
 ]
 
@@ -120,6 +120,7 @@ def load_library():
     lib.ssba_get_edge_errors.argtypes = [H, dp]
     lib.ssba_chi2.argtypes = [H, dp, dp]
     lib.ssba_count_outliers.argtypes = [H, C.c_double, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.ssba_plan_shards.argtypes = [C.c_int32, bp, C.c_int32, bp, C.c_int32, ip, ip, C.c_int32, ip]
     lib.ssba_profile_get.argtypes = [H, C.POINTER(Profile)]
     lib.ssba_profile_reset.argtypes = [H]
     lib.ssba_get_problem_info.argtypes = [H, C.POINTER(ProblemInfo)]
@@ -147,6 +148,19 @@ def nccl_unique_id() -> bytes:
     if st != 0:
         raise SsbaError(st, lib.ssba_last_error(None).decode())
     return bytes(buf)
+
+
+def plan_shards(g, world_size: int) -> np.ndarray:
+    """Host-only: owner rank of every landmark of graph `g` when sharded over `world_size`."""
+    lib = load_library()
+    owner = np.empty(g.n_points, dtype=np.int32)
+    pf, lf = _c(g.pose_fixed, np.uint8), _c(g.point_fixed, np.uint8)
+    pi, li = _c(g.pose_idx, np.int32), _c(g.point_idx, np.int32)
+    st = lib.ssba_plan_shards(g.n_poses, _p(pf, C.c_uint8), g.n_points, _p(lf, C.c_uint8), g.n_edges,
+                              _p(pi, C.c_int32), _p(li, C.c_int32), int(world_size), _p(owner, C.c_int32))
+    if st != 0:
+        raise SsbaError(st, lib.ssba_last_error(None).decode())
+    return owner
 
 
 class BundleAdjuster:

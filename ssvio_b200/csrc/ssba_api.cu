@@ -87,6 +87,7 @@ struct ssba_handle {
   struct Span { size_t a, b; int phase; };
   std::vector<Span> spans;
   double setup_seconds = 0.0;
+  std::vector<uint8_t> owner_mask;
 };
 
 namespace {
@@ -394,6 +395,12 @@ ssba_status ssba_initialize(ssba_handle *h) {
   if (!build_structure(g, h->opt.rank, h->opt.world_size, s, err)) return fail(h, SSBA_ERR_INVALID_ARG, err);
   if (s.n_fp + s.n_fl_global == 0) { h->initialized = false; return fail(h, SSBA_ERR_EMPTY, "initialize: 0 vertices to optimize"); }
 
+  // landmarks whose estimate this rank reports in ssba_get_points (world_size > 1)
+  h->owner_mask.assign(g.n_points, 0);
+  for (int v : s.slot_vertex) h->owner_mask[v] = 1;
+  if (h->opt.rank == 0)
+    for (int v = 0; v < g.n_points; ++v) if (!s.point_active[v]) h->owner_mask[v] = 1;
+
   // ---- plan the arena: static (uploaded) part first, then work buffers
   struct Item { const void *src; size_t bytes; size_t off; void **dst; };
   std::vector<Item> items;
@@ -415,6 +422,7 @@ ssba_status ssba_initialize(ssba_handle *h) {
   STAT(s.chunk_q, chunk_q); STAT(s.chunk_vertex, chunk_vertex); STAT(s.chunk_edge_ptr, chunk_edge_ptr);
   STAT(s.q_chunk_ptr, q_chunk_ptr); STAT(s.pm_point, pm_point); STAT(s.pm_uv, pm_uv); STAT(s.pm_info, pm_info);
   STAT(s.pm_delta, pm_delta); STAT(s.pm_cam, pm_cam); STAT(s.pose_of_q, pose_of_q);
+  STAT(h->owner_mask, owner_mask);
   STAT(s.unit_slot, unit_slot); STAT(s.unit_n, unit_n); STAT(s.unit_k, unit_k); STAT(s.unit_c0, unit_c0);
   STAT(s.blk_row, blk_row); STAT(s.blk_col, blk_col); STAT(s.prog, prog); STAT(s.prog_ptr, prog_ptr);
 #undef STAT
@@ -435,7 +443,8 @@ ssba_status ssba_initialize(ssba_handle *h) {
   DYN(Dinv, 6 * (size_t)s.n_slots, double); DYN(hpp_part, 27 * (size_t)s.n_chunks, double); DYN(hpp, 27 * (size_t)s.n_fp, double);
   DYN(sys, P.sys_doubles, double); DYN(xp, 6 * (size_t)s.n_fp, double); DYN(diag_buf, 6 * (size_t)s.n_fp, double);
   DYN(chi_cur_part, nblk, double); DYN(maxdiag_part, nblk, double); DYN(chi_new_part, nblk, double); DYN(scale_part, nblk, double);
-  DYN(scal, 8, double); DYN(chi_out, 8, double); DYN(err_out, 2 * (size_t)g.n_edges, double);
+  DYN(scal, 8, double); DYN(chi_out, 8, double);
+  DYN(gather, h->opt.world_size > 1 ? 3 * (size_t)g.n_points : 0, double); DYN(err_out, 2 * (size_t)g.n_edges, double);
   DYN(ctl, 1, Control);
 #undef DYN
   const size_t total = align_up(top);
@@ -571,7 +580,17 @@ ssba_status ssba_get_points(ssba_handle *h, double *out) {
     return SSBA_OK;
   }
   CUDA_TRY(h, cudaSetDevice(h->device));
-  if (h->opt.world_size > 1) return fail(h, SSBA_ERR_STATE, "get_points: use ssba_get_points on every rank after gather (not yet supported for world_size > 1)");
+  if (h->opt.world_size > 1) {
+    // every rank owns the estimates of its landmark shard only: zero the rest, sum over ranks
+    // (rank 0 also contributes the landmarks no rank optimises)
+    launch_gather_points(h->P, h->stream);
+    h->prof.kernel_launches += 1;
+    ssba_status rc = nccl_allreduce(h, h->P.gather, 3 * (size_t)h->P.n_points, kNcclSum);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(out, h->P.gather, 3 * sizeof(double) * (size_t)h->P.n_points, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return SSBA_OK;
+  }
   CUDA_TRY(h, cudaMemcpyAsync(out, h->P.point[h->cur], 3 * sizeof(double) * (size_t)h->P.n_points, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return SSBA_OK;
@@ -614,6 +633,27 @@ ssba_status ssba_count_outliers(ssba_handle *h, double thr, int64_t *n_out, int6
   // edges whose two vertices are fixed are never active (sparse_optimizer.cpp:237): their
   // _error stays zero in the reference, so backend.cpp:184 counts them as inliers
   if (n_in) *n_in = (int64_t)(f[3] + 0.5) + (h->g.n_edges - h->s.n_active_edges_global);
+  return SSBA_OK;
+}
+
+ssba_status ssba_plan_shards(int32_t n_poses, const uint8_t *pose_fixed, int32_t n_points,
+                             const uint8_t *point_fixed, int32_t n_edges, const int32_t *pose_idx,
+                             const int32_t *point_idx, int32_t world_size, int32_t *owner_out) {
+  if (n_poses < 0 || n_points < 0 || n_edges < 0 || world_size < 1 || !owner_out ||
+      (n_edges > 0 && (!pose_idx || !point_idx)))
+    return fail(nullptr, SSBA_ERR_INVALID_ARG, "plan_shards: bad arguments");
+  HostGraph g;
+  g.have_cams = true; g.cams.n = 1;
+  g.n_poses = n_poses; g.n_points = n_points; g.n_edges = n_edges;
+  g.poses.assign(7 * (size_t)n_poses, 0.0); g.points.assign(3 * (size_t)n_points, 0.0);
+  if (pose_fixed) g.pose_fixed.assign(pose_fixed, pose_fixed + n_poses); else g.pose_fixed.assign(n_poses, 0);
+  if (point_fixed) g.point_fixed.assign(point_fixed, point_fixed + n_points); else g.point_fixed.assign(n_points, 0);
+  g.e_pose.assign(pose_idx, pose_idx + n_edges); g.e_point.assign(point_idx, point_idx + n_edges);
+  g.e_cam.assign(n_edges, 0); g.e_uv.assign(2 * (size_t)n_edges, 0.0);
+  std::vector<int32_t> owner;
+  std::string err;
+  if (!plan_shards(g, world_size, owner, err)) return fail(nullptr, SSBA_ERR_INVALID_ARG, err);
+  std::memcpy(owner_out, owner.data(), sizeof(int32_t) * (size_t)n_points);
   return SSBA_OK;
 }
 

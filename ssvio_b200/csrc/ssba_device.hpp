@@ -82,6 +82,8 @@ struct DeviceProblem {
   double *scal;       // [chi_cur, chi_new, scale_lm, maxdiag] reduced partials (all-reduced)
   double *err_out;    // n_edges_total x 2 scratch for ssba_get_edge_errors
   double *chi_out;    // [plain, robust, n_outliers, n_inliers]
+  double *gather;     // n_points x 3, multi-GPU read-back of the landmark estimates
+  const uint8_t *owner_mask;  // n_points: this rank reports the landmark
   Control *ctl;
   size_t sys_doubles;
   int n_edges_total;
@@ -99,6 +101,7 @@ void launch_reduce_partials(const DeviceProblem &P, cudaStream_t st);  // -> sca
 void launch_control(const DeviceProblem &P, cudaStream_t st);
 void launch_final_chi2(const DeviceProblem &P, double threshold, cudaStream_t st);  // -> chi_out
 void launch_edge_errors(const DeviceProblem &P, cudaStream_t st);      // -> err_out
+void launch_gather_points(const DeviceProblem &P, cudaStream_t st);    // -> gather
 int kernels_per_linearize();
 
 }  // namespace ssba

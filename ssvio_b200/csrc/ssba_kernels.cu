@@ -932,6 +932,12 @@ __global__ void __launch_bounds__(256) k_final_reduce(const DeviceProblem P) {
   if (threadIdx.x == 0) { P.chi_out[0] = a; P.chi_out[1] = b; P.chi_out[2] = c; P.chi_out[3] = d; }
 }
 
+__global__ void k_gather_points(const DeviceProblem P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * P.n_points) return;
+  P.gather[i] = P.owner_mask[i / 3] ? P.point[P.ctl->cur][i] : 0.0;
+}
+
 inline int div_up(long long a, int b) { return (int)((a + b - 1) / b); }
 
 }  // namespace
@@ -995,6 +1001,10 @@ void launch_control(const DeviceProblem &P, cudaStream_t st) { k_control<<<1, 1,
 void launch_final_chi2(const DeviceProblem &P, double threshold, cudaStream_t st) {
   k_final_chi2<<<P.n_lin_blocks, kLinThreads, 0, st>>>(P, threshold, 0);
   k_final_reduce<<<1, 256, 0, st>>>(P);
+}
+
+void launch_gather_points(const DeviceProblem &P, cudaStream_t st) {
+  if (P.n_points > 0) k_gather_points<<<div_up(3LL * P.n_points, 256), 256, 0, st>>>(P);
 }
 
 void launch_edge_errors(const DeviceProblem &P, cudaStream_t st) {

@@ -422,6 +422,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     ++point_deg[g.e_point[e]];
   }
   s.n_active_edges_global = n_active;
+  s.point_active = point_active;
 
   // ---- index mapping (sparse_optimizer.cpp:168-192): free poses in id order, then landmarks
   std::vector<int32_t> fp_of_pose(NK, -1), free_pose_rows;
@@ -684,6 +685,16 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
       s.q_chunk_ptr[q + 1] = (int32_t)s.chunk_q.size();
     }
     s.n_chunks = (int)s.chunk_q.size();
+  }
+  return true;
+}
+
+bool plan_shards(const HostGraph &g, int world, std::vector<int32_t> &owner, std::string &err) {
+  owner.assign(g.n_points, -1);
+  for (int r = 0; r < world; ++r) {
+    Structure s;
+    if (!build_structure(g, r, world, s, err)) return false;
+    for (int v : s.slot_vertex) owner[v] = r;
   }
   return true;
 }

@@ -40,6 +40,7 @@ struct Structure {
   int n_active_edges_global = 0;
   std::vector<int32_t> q_of_pose;     // pose row -> q, -1 fixed / inactive
   std::vector<int32_t> pose_of_q;     // q -> pose row
+  std::vector<uint8_t> point_active;  // point row has an active edge (on any rank)
   // ---- this rank's shard, landmark-major
   int n_slots = 0, n_pairs = 0, n_edges = 0, n_fl = 0;
   std::vector<int32_t> slot_vertex;   // point row
@@ -99,5 +100,9 @@ struct Structure {
 // Builds the structure for `rank` of `world`. Returns false and sets err on invalid input.
 // n_fp + n_fl_global == 0 is not an error here (caller maps it to SSBA_ERR_EMPTY).
 bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std::string &err);
+
+// Which rank owns which landmark under the sharding rule of build_structure:
+// owner[point row] = rank, or -1 for landmarks without an active edge.
+bool plan_shards(const HostGraph &g, int world, std::vector<int32_t> &owner, std::string &err);
 
 }  // namespace ssba
