@@ -232,9 +232,16 @@ def run_ssba(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        t_s = time.perf_counter()
-        while time.perf_counter() - t_s < 1.5:   # keep the GPU busy while nvidia-smi comes up
-            flush_l2(); step_resident()
+    # keep the GPUs busy ~1.5 s while nvidia-smi comes up; the steps are collective when N > 1,
+    # so rank 0 decides and every rank follows
+    t_s = time.perf_counter()
+    while True:
+        go = torch.tensor([1 if time.perf_counter() - t_s < 1.5 else 0], device=dev)
+        if multi:
+            dist.broadcast(go, 0)
+        if int(go.item()) == 0:
+            break
+        flush_l2(); step_resident()
     for _ in range(max(args.warmup, 3)):
         flush_l2(); step_resident()
     barrier_sync()
@@ -282,7 +289,7 @@ def run_ssba(args):
                      points=pin(g.points), point_fixed=pin(g.point_fixed), pose_idx=pin(g.pose_idx),
                      point_idx=pin(g.point_idx), cam_idx=pin(g.cam_idx), uv=pin(g.uv),
                      huber_delta=g.huber_delta, iters=iters)
-    eopt = ba.BundleAdjuster(device_id=local_rank, stream=stream, rank=rank, world_size=world, nccl_id=nccl_id) if not multi else opt
+    eopt = ba.BundleAdjuster(device_id=local_rank, stream=stream) if not multi else opt
     e2e_chi = None
 
     def step_e2e():
@@ -291,23 +298,26 @@ def run_ssba(args):
         r = eopt.optimize(iters)             # incl. final chi2 read-back (the step's result)
         e2e_chi = r.chi2_robust
         poses = eopt.poses()                 # D2H
-        points = eopt.points() if not multi else None
+        points = eopt.points()               # D2H (all-reduced gather of the shards when N > 1)
         return poses, points
 
-    e2e = None
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
+    barrier_sync()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ev2:
+        flush_l2()
+        a.record(); step_e2e(); b.record()
+    barrier_sync()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
+    if multi:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e = {"value": iters * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+           "h2d_bytes_per_step": hg.input_bytes() * world, "d2h_bytes_per_step": (hg.output_bytes() + 32) * world,
+           "ms_per_step": e2e_ms / args.steps, "chi2_robust": e2e_chi}
     if not multi:
-        for _ in range(max(args.warmup, 3)):
-            step_e2e()
-        barrier_sync()
-        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        for a, b in ev2:
-            flush_l2()
-            a.record(); step_e2e(); b.record()
-        barrier_sync()
-        e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
-        e2e = {"value": iters * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": hg.input_bytes(), "d2h_bytes_per_step": hg.output_bytes() + 32,
-               "ms_per_step": e2e_ms / args.steps, "chi2_robust": e2e_chi}
         eopt.close()
 
     # ---------------- CPU baseline on the box's host cores (rank 0, N = 1 only)
