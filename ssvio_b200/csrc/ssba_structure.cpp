@@ -517,48 +517,69 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     return (it != b1 && *it == row) ? (int)(it - s.blk_row.data()) : -1;
   };
 
-  // ---- landmark order: landmarks seen by the same set of free poses are made adjacent (sorted
-  // by first pose, then by a hash of the pose list), so that runs of landmarks accumulate into
-  // the same Schur blocks; then the shard of this rank = a contiguous range of that order,
-  // balanced by edge count
-  std::vector<int32_t> slots;
+  // ---- per landmark: its edges sorted by pose (free poses first by q, then fixed poses by row;
+  // addEdge order inside a pose), in place in pt_edges; a hash of its free-pose list.  Done once
+  // for every active landmark because the landmark ORDER below is global across ranks.
+  auto pose_key = [&](int e) -> long long {
+    const int q = s.q_of_pose[g.e_pose[e]];
+    return q >= 0 ? q : (long long)n + g.e_pose[e];
+  };
+  std::vector<uint64_t> lm_hash(NP, 0);
+  std::vector<int32_t> lm_minq(NP, n);
   {
-    std::vector<int32_t> act;
-    act.reserve(NP);
-    std::vector<uint64_t> key(NP, 0);
-    std::vector<int32_t> bucket_cnt(n + 2, 0);
-    std::vector<int32_t> minq(NP, n);
-    int ql[64];
+    std::vector<std::pair<long long, int32_t>> big;
     for (int j = 0; j < NP; ++j) {
       if (!point_active[j]) continue;
-      act.push_back(j);
-      int m = 0, mn = n;
-      uint64_t h = 1469598103934665603ull;
-      if (!g.point_fixed[j]) {
-        for (int k = pt_ptr[j]; k < pt_ptr[j + 1]; ++k) {
-          const int q = s.q_of_pose[g.e_pose[pt_edges[k]]];
-          if (q < 0) continue;
-          if (q < mn) mn = q;
-          if (m < 64) { int i = m++; while (i > 0 && ql[i - 1] > q) { ql[i] = ql[i - 1]; --i; } ql[i] = q; }
+      int32_t *seg = pt_edges.data() + pt_ptr[j];
+      const int m = pt_ptr[j + 1] - pt_ptr[j];
+      if (m <= 48) {  // insertion sort, stable
+        long long keys[48];
+        for (int i = 0; i < m; ++i) {
+          const int e = seg[i];
+          const long long k = pose_key(e);
+          int t = i;
+          while (t > 0 && keys[t - 1] > k) { keys[t] = keys[t - 1]; seg[t] = seg[t - 1]; --t; }
+          keys[t] = k; seg[t] = e;
         }
-        int prev = -1;
-        for (int i = 0; i < m; ++i) if (ql[i] != prev) { prev = ql[i]; h = (h ^ (uint64_t)(prev + 1)) * 1099511628211ull; }
+      } else {
+        big.clear();
+        for (int i = 0; i < m; ++i) big.emplace_back(pose_key(seg[i]), seg[i]);
+        std::sort(big.begin(), big.end());
+        for (int i = 0; i < m; ++i) seg[i] = big[i].second;
       }
-      minq[j] = mn;
-      key[j] = h;
-      ++bucket_cnt[mn + 1];
+      if (!g.point_fixed[j]) {
+        uint64_t h = 1469598103934665603ull;
+        int prev = -1;
+        for (int i = 0; i < m; ++i) {
+          const int q = s.q_of_pose[g.e_pose[seg[i]]];
+          if (q < 0) break;
+          if (q != prev) { if (prev < 0) lm_minq[j] = q; prev = q; h = (h ^ (uint64_t)(q + 1)) * 1099511628211ull; }
+        }
+        lm_hash[j] = h;
+      }
     }
+  }
+  // ---- landmark order: landmarks seen by the same set of free poses are made adjacent (bucket
+  // by first pose, then by the hash of the pose list), so that runs of landmarks accumulate into
+  // the same Schur blocks; the shard of this rank = a contiguous range of that order, balanced
+  // by edge count
+  std::vector<int32_t> slots;
+  {
+    std::vector<int32_t> bucket_cnt(n + 2, 0);
+    int n_act_pts = 0;
+    for (int j = 0; j < NP; ++j) if (point_active[j]) { ++bucket_cnt[lm_minq[j] + 1]; ++n_act_pts; }
     for (int q = 0; q <= n; ++q) bucket_cnt[q + 1] += bucket_cnt[q];
-    std::vector<int32_t> sorted(act.size());
+    std::vector<int32_t> sorted(n_act_pts);
     {
       std::vector<int32_t> fill(bucket_cnt.begin(), bucket_cnt.end() - 1);
-      for (int j : act) sorted[fill[minq[j]]++] = j;
+      for (int j = 0; j < NP; ++j) if (point_active[j]) sorted[fill[lm_minq[j]]++] = j;
     }
     for (int q = 0; q <= n; ++q)
       std::sort(sorted.begin() + bucket_cnt[q], sorted.begin() + bucket_cnt[q + 1],
-                [&](int x, int y) { return key[x] != key[y] ? key[x] < key[y] : x < y; });
+                [&](int x, int y) { return lm_hash[x] != lm_hash[y] ? lm_hash[x] < lm_hash[y] : x < y; });
     const long long total = n_active;
     long long seen = 0;
+    slots.reserve(world > 1 ? n_act_pts / world + 64 : n_act_pts);
     for (int j : sorted) {
       // owner = the rank whose edge-quantile holds the first edge of this landmark
       const int owner = total > 0 ? (int)std::min<long long>(world - 1, seen * world / total) : 0;
@@ -572,54 +593,79 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   s.slot_pair_ptr.assign(s.n_slots + 1, 0);
   s.slot_combo_ptr.assign(s.n_slots + 1, 0);
   const bool have_info = !g.e_info.empty(), have_delta = !g.e_delta.empty();
-  std::vector<std::pair<long long, int32_t>> order;  // (pair key, edge)
-  s.pair_edge_ptr.push_back(0);
-  std::vector<int32_t> wq;
-  for (int sl = 0; sl < s.n_slots; ++sl) {
-    const int j = slots[sl];
-    const bool lfree = !g.point_fixed[j];
-    s.slot_free[sl] = lfree;
-    if (lfree) ++s.n_fl;
-    order.clear();
-    for (int k = pt_ptr[j]; k < pt_ptr[j + 1]; ++k) {
-      const int e = pt_edges[k];
-      const int q = s.q_of_pose[g.e_pose[e]];
-      // pairs with a free pose first, by q; fixed-pose pairs after, by pose row
-      const long long key = q >= 0 ? q : (long long)n + g.e_pose[e];
-      order.emplace_back(key, e);
-    }
-    std::sort(order.begin(), order.end());
-    wq.clear();
-    long long last = -1;
-    for (auto &ke : order) {
-      const int e = ke.second;
-      if (ke.first != last) {
-        if (last != -1) s.pair_edge_ptr.push_back((int32_t)s.e_orig.size());
-        last = ke.first;
-        s.pair_vertex.push_back(g.e_pose[e]);
-        const int q = s.q_of_pose[g.e_pose[e]];
-        s.pair_q.push_back(q);
-        if (q >= 0 && lfree) wq.push_back(q);
+  {
+    size_t ne_local = 0;
+    for (int j : slots) ne_local += (size_t)point_deg[j];
+    s.e_orig.resize(ne_local); s.e_uv.resize(2 * ne_local); s.e_cam.resize(ne_local);
+    if (have_info) s.e_info.resize(3 * ne_local);
+    if (have_delta) s.e_delta.resize(ne_local);
+    s.pair_vertex.resize(ne_local); s.pair_q.resize(ne_local); s.pair_edge_ptr.resize(ne_local + 1);
+    s.combo_blk.reserve(ne_local * 2);
+    size_t ne = 0, npair = 0;
+    std::vector<int32_t> wq, wq_prev;
+    size_t prev_combo0 = 0, prev_combo_n = 0;
+    // raw pointers: the byte-typed stores below would otherwise force every vector's data
+    // pointer to be re-read on each iteration
+    const int32_t *__restrict__ ge_pose = g.e_pose.data();
+    const double *__restrict__ ge_uv = g.e_uv.data();
+    const uint8_t *__restrict__ ge_cam = g.e_cam.data();
+    const int32_t *__restrict__ qmap = s.q_of_pose.data();
+    const int32_t *__restrict__ pe = pt_edges.data();
+    int32_t *__restrict__ o_orig = s.e_orig.data();
+    double *__restrict__ o_uv = s.e_uv.data();
+    uint8_t *__restrict__ o_cam = s.e_cam.data();
+    int32_t *__restrict__ o_pv = s.pair_vertex.data(), *__restrict__ o_pq = s.pair_q.data(),
+            *__restrict__ o_pe = s.pair_edge_ptr.data();
+    for (int sl = 0; sl < s.n_slots; ++sl) {
+      const int j = slots[sl];
+      const bool lfree = !g.point_fixed[j];
+      s.slot_free[sl] = lfree;
+      if (lfree) ++s.n_fl;
+      wq.clear();
+      int last_pose = -1;
+      const int k1 = pt_ptr[j + 1];
+      for (int k = pt_ptr[j]; k < k1; ++k) {
+        const int e = pe[k];
+        const int pose = ge_pose[e];
+        if (pose != last_pose) {  // edges are sorted by pose: a new (pose, landmark) pair starts
+          last_pose = pose;
+          const int q = qmap[pose];
+          o_pv[npair] = pose; o_pq[npair] = q; o_pe[npair] = (int32_t)ne; ++npair;
+          if (q >= 0 && lfree) wq.push_back(q);
+        }
+        o_orig[ne] = e;
+        o_uv[2 * ne] = ge_uv[2 * (size_t)e]; o_uv[2 * ne + 1] = ge_uv[2 * (size_t)e + 1];
+        o_cam[ne] = ge_cam[e];
+        if (have_info) for (int t = 0; t < 3; ++t) s.e_info[3 * ne + t] = g.e_info[3 * (size_t)e + t];
+        if (have_delta) s.e_delta[ne] = g.e_delta[e];
+        ++ne;
       }
-      s.e_orig.push_back(e);
-      s.e_uv.push_back(g.e_uv[2 * e]); s.e_uv.push_back(g.e_uv[2 * e + 1]);
-      s.e_cam.push_back(g.e_cam[e]);
-      if (have_info) for (int t = 0; t < 3; ++t) s.e_info.push_back(g.e_info[3 * e + t]);
-      if (have_delta) s.e_delta.push_back(g.e_delta[e]);
-    }
-    if (last != -1) s.pair_edge_ptr.push_back((int32_t)s.e_orig.size());
-    s.slot_pair_ptr[sl + 1] = (int32_t)s.pair_vertex.size();
-    // Schur targets: for W-pairs a <= b (sorted by q): block (row q_b, col q_a)
-    for (size_t a = 0; a < wq.size(); ++a)
-      for (size_t b = a; b < wq.size(); ++b) {
-        const int blk = find_block(wq[b], wq[a]);
-        if (blk < 0) { err = "internal: Schur block missing from the factor pattern"; return false; }
-        s.combo_blk.push_back(blk);
+      s.slot_pair_ptr[sl + 1] = (int32_t)npair;
+      // Schur targets: for W-pairs a <= b (sorted by q): block (row q_b, col q_a); the previous
+      // landmark's list is reused when the pose list is the same (the common case after sorting)
+      if (!wq.empty() && wq == wq_prev) {
+        const size_t c0 = s.combo_blk.size();
+        s.combo_blk.resize(c0 + prev_combo_n);
+        std::copy(s.combo_blk.begin() + prev_combo0, s.combo_blk.begin() + prev_combo0 + prev_combo_n, s.combo_blk.begin() + c0);
+        prev_combo0 = c0;
+      } else {
+        prev_combo0 = s.combo_blk.size();
+        for (size_t a = 0; a < wq.size(); ++a)
+          for (size_t b = a; b < wq.size(); ++b) {
+            const int blk = find_block(wq[b], wq[a]);
+            if (blk < 0) { err = "internal: Schur block missing from the factor pattern"; return false; }
+            s.combo_blk.push_back(blk);
+          }
+        prev_combo_n = s.combo_blk.size() - prev_combo0;
+        wq_prev = wq;
       }
-    s.slot_combo_ptr[sl + 1] = (int32_t)s.combo_blk.size();
+      s.slot_combo_ptr[sl + 1] = (int32_t)s.combo_blk.size();
+    }
+    s.pair_edge_ptr[npair] = (int32_t)ne;
+    s.pair_vertex.resize(npair); s.pair_q.resize(npair); s.pair_edge_ptr.resize(npair + 1);
+    s.n_pairs = (int)npair;
+    s.n_edges = (int)ne;
   }
-  s.n_pairs = (int)s.pair_vertex.size();
-  s.n_edges = (int)s.e_orig.size();
 
   // ---- Schur work units: a run of <= 32 consecutive free landmarks with the same W pose list
   // x a chunk of <= 32 of its k(k+1)/2 block pairs (one lane per block pair, one warp per unit)
