@@ -20,6 +20,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libssba_ref.so")
 PORT_SO = os.path.join(HERE, "_build", "libssba_oracle.so")
+SHIM_SO = os.path.join(HERE, "_ref", "libssba_shim_test.so")
 REFERENCE_ROOT = "/root/reference"
 
 SSBA_MAX_ITER_RECORDS = 128
@@ -159,3 +160,39 @@ class PortOracle(_OracleBase):
         if rc != 0:
             raise RuntimeError(f"ssba_oracle_optimize failed rc={rc}")
         return dict(report=rep, poses=poses, points=points, errors=err)
+
+
+class ShimHarness(_OracleBase):
+    """Drop-in proof (oracle/shim_harness.cpp): the reference's graph construction and g2o
+    SparseOptimizer with include/ssba_g2o_shim.hpp as the optimisation algorithm, i.e. the CUDA
+    path reached exactly the way ssvio's backend.cpp would reach it.  Needs a GPU to run."""
+    so_path = SHIM_SO
+
+    def __init__(self):
+        super().__init__()
+        f = self.lib.ssba_shim_optimize
+        f.restype = C.c_int
+        f.argtypes = [C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_double),
+                      C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_uint8),
+                      C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_uint8),
+                      C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                      C.POINTER(C.c_uint8), C.POINTER(C.c_double), C.c_double, C.c_int32,
+                      C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                      C.POINTER(Report)]
+
+    def optimize(self, g, iters=None):
+        iters = g.iters if iters is None else iters
+        rep = Report()
+        poses = np.empty_like(g.poses)
+        points = np.empty_like(g.points)
+        chi2 = np.empty(g.n_edges)
+        rc = self.lib.ssba_shim_optimize(
+            _p(g.K, C.c_double), g.ext.shape[0], _p(g.ext, C.c_double),
+            g.n_poses, _p(g.poses, C.c_double), _p(g.pose_fixed, C.c_uint8),
+            g.n_points, _p(g.points, C.c_double), _p(g.point_fixed, C.c_uint8),
+            g.n_edges, _p(g.pose_idx, C.c_int32), _p(g.point_idx, C.c_int32),
+            _p(g.cam_idx, C.c_uint8), _p(g.uv, C.c_double), float(g.huber_delta), int(iters),
+            _p(poses, C.c_double), _p(points, C.c_double), _p(chi2, C.c_double), C.byref(rep))
+        if rc != 0:
+            raise RuntimeError(f"ssba_shim_optimize failed rc={rc}")
+        return dict(report=rep, poses=poses, points=points, edge_chi2=chi2)

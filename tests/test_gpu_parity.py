@@ -228,3 +228,26 @@ def test_full_size_properties_cfg3(BA):
     both_fixed = g.pose_fixed[g.pose_idx].astype(bool) & g.point_fixed[g.point_idx].astype(bool)
     assert r["info"].n_active_edges == g.n_edges - int(both_fixed.sum())
     np.testing.assert_array_equal(r["errors"][both_fixed], 0.0)
+
+
+def test_g2o_shim_drop_in(BA):
+    """The boundary: ssvio's graph construction + g2o::SparseOptimizer with
+    ssba::OptimizationAlgorithmLevenbergCuda installed by setAlgorithm() (backend.cpp:83-86) gives
+    the reference's result, read back through the plain g2o API (v->estimate(), e->chi2())."""
+    from oracle import bindings
+    if not bindings.ShimHarness.available():
+        pytest.skip("oracle/_ref/libssba_shim_test.so not built (needs /root/reference at build time)")
+    shim = bindings.ShimHarness()
+    for name in ("small_fixed", "cfg1"):
+        g, z = golden_case(name)
+        gold = golden_scalars()[name]
+        r = shim.optimize(g)
+        rep = r["report"]
+        assert rep.iterations == gold["numeric"]["iterations"]
+        assert rel(rep.chi2_robust, gold["numeric"]["chi2_robust"]) < CHI2_RTOL
+        assert rel(rep.chi2_robust, gold["analytic"]["chi2_robust"]) < CHI2_RTOL_SAME_JACOBIAN
+        np.testing.assert_allclose(r["poses"], z["analytic_poses"], atol=1e-7)
+        np.testing.assert_allclose(r["points"], z["analytic_points"], atol=1e-6)
+        # e->chi2() of every edge, as backend.cpp:184 reads it
+        np.testing.assert_allclose(r["edge_chi2"], (z["analytic_errors"] ** 2).sum(1), rtol=1e-6, atol=1e-6)
+        assert rel(r["edge_chi2"].sum(), rep.chi2_plain) < 1e-12
