@@ -4,6 +4,7 @@
 // ssba_create() fails.
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <memory>
@@ -392,7 +393,10 @@ ssba_status ssba_initialize(ssba_handle *h) {
   }
   std::string err;
   Structure &s = h->s;
+  const bool timing = std::getenv("SSBA_TIMING") != nullptr;
+  auto t_a = Clock::now();
   if (!build_structure(g, h->opt.rank, h->opt.world_size, s, err)) return fail(h, SSBA_ERR_INVALID_ARG, err);
+  auto t_b = Clock::now();
   if (s.n_fp + s.n_fl_global == 0) { h->initialized = false; return fail(h, SSBA_ERR_EMPTY, "initialize: 0 vertices to optimize"); }
 
   // landmarks whose estimate this rank reports in ssba_get_points (world_size > 1)
@@ -420,8 +424,8 @@ ssba_status ssba_initialize(ssba_handle *h) {
   STAT(s.pair_vertex, pair_vertex); STAT(s.pair_q, pair_q); STAT(s.pair_edge_ptr, pair_edge_ptr);
   STAT(s.e_uv, e_uv); STAT(s.e_info, e_info); STAT(s.e_delta, e_delta); STAT(s.e_cam, e_cam); STAT(s.e_orig, e_orig);
   STAT(s.chunk_q, chunk_q); STAT(s.chunk_vertex, chunk_vertex); STAT(s.chunk_edge_ptr, chunk_edge_ptr);
-  STAT(s.q_chunk_ptr, q_chunk_ptr); STAT(s.pm_point, pm_point); STAT(s.pm_uv, pm_uv); STAT(s.pm_info, pm_info);
-  STAT(s.pm_delta, pm_delta); STAT(s.pm_cam, pm_cam); STAT(s.pose_of_q, pose_of_q);
+  STAT(s.q_chunk_ptr, q_chunk_ptr); STAT(s.pm_point, pm_point); STAT(s.pm_src, pm_src);
+  STAT(s.pose_of_q, pose_of_q);
   STAT(h->owner_mask, owner_mask);
   STAT(s.unit_slot, unit_slot); STAT(s.unit_n, unit_n); STAT(s.unit_k, unit_k); STAT(s.unit_c0, unit_c0);
   STAT(s.blk_row, blk_row); STAT(s.blk_col, blk_col); STAT(s.prog, prog); STAT(s.prog_ptr, prog_ptr);
@@ -462,7 +466,9 @@ ssba_status ssba_initialize(ssba_handle *h) {
     if (cudaHostAlloc((void **)&h->h_stage, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return fail(h, SSBA_ERR_ALLOC, "cudaHostAlloc failed"); }
     h->h_stage_bytes = want;
   }
+  auto t_c = Clock::now();
   for (auto &it : items) { std::memcpy(h->h_stage + it.off, it.src, it.bytes); *it.dst = h->d_arena + it.off; }
+  auto t_d = Clock::now();
   for (auto &it : work) *it.dst = h->d_arena + it.off;
   h->device_bytes = total;
   CUDA_TRY(h, cudaMemcpyAsync(h->d_arena, h->h_stage, static_bytes, cudaMemcpyHostToDevice, h->stream));
@@ -483,6 +489,10 @@ ssba_status ssba_initialize(ssba_handle *h) {
   if (rc) return rc;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // h_stage may be rewritten by the next initialize
   h->setup_seconds = secs(t0, Clock::now());
+  if (timing)
+    std::fprintf(stderr, "[ssba] initialize: build_structure %.3f ms, plan+alloc %.3f ms, stage memcpy %.3f ms (%.1f MB), "
+                 "upload+reset+sync %.3f ms, total %.3f ms\n", 1e3 * secs(t_a, t_b), 1e3 * secs(t_b, t_c),
+                 1e3 * secs(t_c, t_d), static_bytes / 1e6, 1e3 * secs(t_d, Clock::now()), 1e3 * h->setup_seconds);
   return SSBA_OK;
 }
 

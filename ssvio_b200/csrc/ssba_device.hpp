@@ -57,9 +57,7 @@ struct DeviceProblem {
   const uint8_t *e_cam;
   const int32_t *e_orig;
   // pose-major copy
-  const int32_t *chunk_q, *chunk_vertex, *chunk_edge_ptr, *q_chunk_ptr, *pm_point;
-  const double *pm_uv, *pm_info, *pm_delta;
-  const uint8_t *pm_cam;
+  const int32_t *chunk_q, *chunk_vertex, *chunk_edge_ptr, *q_chunk_ptr, *pm_point, *pm_src;
   const int32_t *pose_of_q;
   const int32_t *unit_slot, *unit_n, *unit_k, *unit_c0;  // Schur work units
   int n_units;

@@ -189,13 +189,14 @@ __global__ void __launch_bounds__(kHppThreads) k_hpp(const DeviceProblem P) {
 #pragma unroll
   for (int i = 0; i < 27; ++i) acc[i] = 0.0;
   const int e1 = P.chunk_edge_ptr[c + 1];
-  for (int e = P.chunk_edge_ptr[c] + threadIdx.x; e < e1; e += kHppThreads) {
-    const int pv = P.pm_point[e];
+  for (int d = P.chunk_edge_ptr[c] + threadIdx.x; d < e1; d += kHppThreads) {
+    const int pv = P.pm_point[d];
+    const int e = P.pm_src[d];  // the edge in the landmark-major stream
     const double p[3] = {point[3 * pv], point[3 * pv + 1], point[3 * pv + 2]};
     EdgeTerms t;
     double Jx[12], Jp[6];
-    linearize_edge(P, P.pm_cam[e], T, p, P.pm_uv[2 * e], P.pm_uv[2 * e + 1], t, Jx, Jp);
-    load_edge_weighting(P, P.pm_info, P.pm_delta, e, t);
+    linearize_edge(P, P.e_cam[e], T, p, P.e_uv[2 * e], P.e_uv[2 * e + 1], t, Jx, Jp);
+    load_edge_weighting(P, P.e_info, P.e_delta, e, t);
     double A0[6], A1[6];
 #pragma unroll
     for (int r = 0; r < 6; ++r) {

@@ -6,8 +6,12 @@
 #include <climits>
 #include <cmath>
 #include <cstring>
+#include <condition_variable>
+#include <cstdlib>
 #include <functional>
+#include <mutex>
 #include <numeric>
+#include <thread>
 
 namespace ssba {
 
@@ -400,26 +404,95 @@ void nested_dissection_order(int n, const std::vector<std::vector<int>> &adj_low
 
 }  // namespace
 
+// ---- a small persistent fork-join pool for the host passes over the edges (the structure build
+// is on the end-to-end path of every ssba_initialize call)
+namespace {
+class HostPool {
+ public:
+  // leaked on purpose: the detached workers wait on its condition variable until process exit
+  static HostPool &get() { static HostPool *p = new HostPool; return *p; }
+  int size() const { return n_; }
+  // fn(t, T) for t in [0, T); the caller runs t = 0.  Calls are serialised.
+  void run(int T, const std::function<void(int, int)> &fn) {
+    if (T <= 1 || n_ <= 1) { fn(0, 1); return; }
+    if (T > n_) T = n_;
+    std::lock_guard<std::mutex> outer(run_mu_);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn; T_ = T; pending_ = T - 1; ++gen_;
+    }
+    cv_.notify_all();
+    fn(0, T);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [&] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  HostPool() {
+    int n = (int)std::thread::hardware_concurrency();
+    if (const char *e = std::getenv("SSBA_HOST_THREADS")) n = std::atoi(e);
+    n_ = std::max(1, std::min(n, 8));
+    for (int t = 1; t < n_; ++t) std::thread([this, t] { worker(t); }).detach();
+  }
+  void worker(int t) {
+    unsigned long seen = 0;
+    for (;;) {
+      const std::function<void(int, int)> *fn = nullptr;
+      int T = 0;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (t < T_) { fn = fn_; T = T_; }
+      }
+      if (fn) {
+        (*fn)(t, T);
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_cv_.notify_one();
+      }
+    }
+  }
+  int n_ = 1;
+  std::mutex mu_, run_mu_;
+  std::condition_variable cv_, done_cv_;
+  const std::function<void(int, int)> *fn_ = nullptr;
+  int T_ = 0, pending_ = 0;
+  unsigned long gen_ = 0;
+};
+inline void split_range(int t, int T, int N, int &b, int &e) {
+  b = (int)((long long)N * t / T);
+  e = (int)((long long)N * (t + 1) / T);
+}
+}  // namespace
+
 bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std::string &err) {
   s = Structure();
   const int NK = g.n_poses, NP = g.n_points, NE = g.n_edges;
   s.n_edges_total = NE;
   if (!g.have_cams) { err = "ssba_set_cameras was not called"; return false; }
-  for (int e = 0; e < NE; ++e) {
-    if (g.e_pose[e] < 0 || g.e_pose[e] >= NK) { err = "edge pose index out of range"; return false; }
-    if (g.e_point[e] < 0 || g.e_point[e] >= NP) { err = "edge point index out of range"; return false; }
-    if (g.e_cam[e] >= g.cams.n) { err = "edge camera index out of range"; return false; }
-  }
+  HostPool &pool = HostPool::get();
+  const int T = NE >= 20000 ? pool.size() : 1;  // small graphs: threads cost more than they save
+  const int32_t *__restrict__ ge_pose = g.e_pose.data();
+  const int32_t *__restrict__ ge_point = g.e_point.data();
+  const uint8_t *__restrict__ ge_cam = g.e_cam.data();
+  const uint8_t *__restrict__ pfix = g.pose_fixed.data();
+  const uint8_t *__restrict__ lfix = g.point_fixed.data();
 
-  // ---- active sets (sparse_optimizer.cpp:201-272): an edge is active unless both ends are fixed
+  // ---- validation + active sets (sparse_optimizer.cpp:201-272): an edge is active unless both
+  // ends are fixed; a vertex is active when it has an active edge
   std::vector<uint8_t> pose_active(NK, 0), point_active(NP, 0), edge_active(NE, 0);
   std::vector<int32_t> point_deg(NP + 1, 0);
   int n_active = 0;
   for (int e = 0; e < NE; ++e) {
-    if (g.pose_fixed[g.e_pose[e]] && g.point_fixed[g.e_point[e]]) continue;
+    const int ip = ge_pose[e], il = ge_point[e];
+    if ((unsigned)ip >= (unsigned)NK) { err = "edge pose index out of range"; return false; }
+    if ((unsigned)il >= (unsigned)NP) { err = "edge point index out of range"; return false; }
+    if (ge_cam[e] >= g.cams.n) { err = "edge camera index out of range"; return false; }
+    if (pfix[ip] && lfix[il]) continue;
     edge_active[e] = 1; ++n_active;
-    pose_active[g.e_pose[e]] = 1; point_active[g.e_point[e]] = 1;
-    ++point_deg[g.e_point[e]];
+    pose_active[ip] = 1; point_active[il] = 1;
+    ++point_deg[il];
   }
   s.n_active_edges_global = n_active;
   s.point_active = point_active;
@@ -427,11 +500,12 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   // ---- index mapping (sparse_optimizer.cpp:168-192): free poses in id order, then landmarks
   std::vector<int32_t> fp_of_pose(NK, -1), free_pose_rows;
   for (int i = 0; i < NK; ++i)
-    if (pose_active[i] && !g.pose_fixed[i]) { fp_of_pose[i] = (int)free_pose_rows.size(); free_pose_rows.push_back(i); }
+    if (pose_active[i] && !pfix[i]) { fp_of_pose[i] = (int)free_pose_rows.size(); free_pose_rows.push_back(i); }
   s.n_fp = (int)free_pose_rows.size();
   s.n_fl_global = 0;
   for (int j = 0; j < NP; ++j)
-    if (point_active[j] && !g.point_fixed[j]) ++s.n_fl_global;
+    if (point_active[j] && !lfix[j]) ++s.n_fl_global;
+  const int n = s.n_fp;
 
   // ---- edges by landmark (CSR over point rows, stable = addEdge order inside a landmark)
   std::vector<int32_t> pt_ptr(NP + 1, 0);
@@ -440,45 +514,57 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   {
     std::vector<int32_t> fill(pt_ptr.begin(), pt_ptr.end() - 1);
     for (int e = 0; e < NE; ++e)
-      if (edge_active[e]) pt_edges[fill[g.e_point[e]]++] = e;
+      if (edge_active[e]) pt_edges[fill[ge_point[e]]++] = e;
   }
 
   // ---- co-visibility of free poses through free landmarks = pattern of the Schur complement
-  // (block_solver.hpp:224-249), as a bitmap when small enough, else as a key list
-  const int n = s.n_fp;
-  const bool use_bitmap = n <= 8192;
-  std::vector<uint64_t> bitmap;
-  std::vector<uint64_t> keys;
-  if (use_bitmap) bitmap.assign(((size_t)n * n + 63) / 64, 0);
-  std::vector<int32_t> tmp;
-  auto mark = [&](int r, int c) {  // r >= c, unpermuted free-pose indices
-    const size_t bit = (size_t)c * n + r;
-    if (use_bitmap) bitmap[bit >> 6] |= 1ull << (bit & 63); else keys.push_back(bit);
-  };
-  for (int i = 0; i < n; ++i) mark(i, i);
-  for (int j = 0; j < NP; ++j) {
-    if (!point_active[j] || g.point_fixed[j]) continue;
-    tmp.clear();
-    for (int k = pt_ptr[j]; k < pt_ptr[j + 1]; ++k) {
-      const int f = fp_of_pose[g.e_pose[pt_edges[k]]];
-      if (f >= 0) tmp.push_back(f);
+  // (block_solver.hpp:224-249): per-thread bitmaps when small enough, else key lists
+  const bool use_bitmap = n <= 4096;
+  const size_t bm_words = use_bitmap ? ((size_t)n * n + 63) / 64 : 0;
+  std::vector<std::vector<uint64_t>> t_bitmap(T), t_keys(T);
+  pool.run(T, [&](int t, int TT) {
+    int j0, j1; split_range(t, TT, NP, j0, j1);
+    std::vector<uint64_t> &bm = t_bitmap[t], &keys = t_keys[t];
+    if (use_bitmap) bm.assign(bm_words, 0);
+    int ql[64];
+    std::vector<int32_t> big;
+    for (int j = j0; j < j1; ++j) {
+      if (!point_active[j] || lfix[j]) continue;
+      const int m = pt_ptr[j + 1] - pt_ptr[j];
+      int *lst = ql, cnt = 0;
+      if (m > 64) { big.resize(m); lst = big.data(); }
+      for (int k = pt_ptr[j]; k < pt_ptr[j + 1]; ++k) {
+        const int f = fp_of_pose[ge_pose[pt_edges[k]]];
+        if (f < 0) continue;
+        int i = cnt;  // sorted insert, duplicates dropped
+        while (i > 0 && lst[i - 1] > f) --i;
+        if (i > 0 && lst[i - 1] == f) continue;
+        for (int u = cnt; u > i; --u) lst[u] = lst[u - 1];
+        lst[i] = f; ++cnt;
+      }
+      for (int a2 = 0; a2 < cnt; ++a2)
+        for (int b2 = a2 + 1; b2 < cnt; ++b2) {
+          const size_t bit = (size_t)lst[a2] * n + lst[b2];  // column a2 < row b2
+          if (use_bitmap) bm[bit >> 6] |= 1ull << (bit & 63); else keys.push_back(bit);
+        }
     }
-    std::sort(tmp.begin(), tmp.end());
-    tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-    for (size_t a = 0; a < tmp.size(); ++a)
-      for (size_t b = a + 1; b < tmp.size(); ++b) mark(tmp[b], tmp[a]);
-  }
+  });
   std::vector<std::vector<int>> adj(n);  // strictly-lower rows per column, unpermuted
   if (use_bitmap) {
+    std::vector<uint64_t> &bm = t_bitmap[0];
+    for (int t = 1; t < (int)t_bitmap.size(); ++t)
+      if (!t_bitmap[t].empty()) for (size_t w = 0; w < bm_words; ++w) bm[w] |= t_bitmap[t][w];
     for (int c = 0; c < n; ++c)
       for (int r = c + 1; r < n; ++r) {
         const size_t bit = (size_t)c * n + r;
-        if (bitmap[bit >> 6] >> (bit & 63) & 1) adj[c].push_back(r);
+        if (bm[bit >> 6] >> (bit & 63) & 1) adj[c].push_back(r);
       }
   } else {
+    std::vector<uint64_t> keys;
+    for (auto &k : t_keys) keys.insert(keys.end(), k.begin(), k.end());
     std::sort(keys.begin(), keys.end());
     keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
-    for (uint64_t k : keys) { const int c = (int)(k / n), r = (int)(k % n); if (r != c) adj[c].push_back(r); }
+    for (uint64_t k : keys) adj[(int)(k / n)].push_back((int)(k % n));
   }
 
   // ---- elimination order and symbolic factorisation over q: natural order vs nested
@@ -516,30 +602,30 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     const int *it = std::lower_bound(b0, b1, row);
     return (it != b1 && *it == row) ? (int)(it - s.blk_row.data()) : -1;
   };
+  const int32_t *__restrict__ qmap = s.q_of_pose.data();
 
   // ---- per landmark: its edges sorted by pose (free poses first by q, then fixed poses by row;
-  // addEdge order inside a pose), in place in pt_edges; a hash of its free-pose list.  Done once
-  // for every active landmark because the landmark ORDER below is global across ranks.
-  auto pose_key = [&](int e) -> long long {
-    const int q = s.q_of_pose[g.e_pose[e]];
-    return q >= 0 ? q : (long long)n + g.e_pose[e];
-  };
+  // addEdge order inside a pose), in place in pt_edges; a hash of its free-pose list, its first
+  // pose, its number of (pose, landmark) pairs and of W pairs.  For every active landmark,
+  // because the landmark ORDER below is global across ranks.
   std::vector<uint64_t> lm_hash(NP, 0);
-  std::vector<int32_t> lm_minq(NP, n);
-  {
+  std::vector<int32_t> lm_minq(NP, n), lm_npairs(NP, 0), lm_k(NP, 0);
+  pool.run(T, [&](int t, int TT) {
+    int j0, j1; split_range(t, TT, NP, j0, j1);
     std::vector<std::pair<long long, int32_t>> big;
-    for (int j = 0; j < NP; ++j) {
+    for (int j = j0; j < j1; ++j) {
       if (!point_active[j]) continue;
       int32_t *seg = pt_edges.data() + pt_ptr[j];
       const int m = pt_ptr[j + 1] - pt_ptr[j];
+      auto pose_key = [&](int e) -> long long { const int q = qmap[ge_pose[e]]; return q >= 0 ? q : (long long)n + ge_pose[e]; };
       if (m <= 48) {  // insertion sort, stable
         long long keys[48];
         for (int i = 0; i < m; ++i) {
           const int e = seg[i];
           const long long k = pose_key(e);
-          int t = i;
-          while (t > 0 && keys[t - 1] > k) { keys[t] = keys[t - 1]; seg[t] = seg[t - 1]; --t; }
-          keys[t] = k; seg[t] = e;
+          int u = i;
+          while (u > 0 && keys[u - 1] > k) { keys[u] = keys[u - 1]; seg[u] = seg[u - 1]; --u; }
+          keys[u] = k; seg[u] = e;
         }
       } else {
         big.clear();
@@ -547,18 +633,24 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
         std::sort(big.begin(), big.end());
         for (int i = 0; i < m; ++i) seg[i] = big[i].second;
       }
-      if (!g.point_fixed[j]) {
-        uint64_t h = 1469598103934665603ull;
-        int prev = -1;
-        for (int i = 0; i < m; ++i) {
-          const int q = s.q_of_pose[g.e_pose[seg[i]]];
-          if (q < 0) break;
-          if (q != prev) { if (prev < 0) lm_minq[j] = q; prev = q; h = (h ^ (uint64_t)(q + 1)) * 1099511628211ull; }
+      const bool lfree = !lfix[j];
+      uint64_t h = 1469598103934665603ull;
+      int prev_pose = -1, np_ = 0, k_ = 0;
+      for (int i = 0; i < m; ++i) {
+        const int pose = ge_pose[seg[i]];
+        if (pose == prev_pose) continue;
+        prev_pose = pose; ++np_;
+        const int q = qmap[pose];
+        if (q >= 0 && lfree) {
+          if (k_ == 0) lm_minq[j] = q;
+          ++k_;
+          h = (h ^ (uint64_t)(q + 1)) * 1099511628211ull;
         }
-        lm_hash[j] = h;
       }
+      lm_hash[j] = lfree ? h : 0; lm_npairs[j] = np_; lm_k[j] = k_;
     }
-  }
+  });
+
   // ---- landmark order: landmarks seen by the same set of free poses are made adjacent (bucket
   // by first pose, then by the hash of the pose list), so that runs of landmarks accumulate into
   // the same Schur blocks; the shard of this rank = a contiguous range of that order, balanced
@@ -574,9 +666,11 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
       std::vector<int32_t> fill(bucket_cnt.begin(), bucket_cnt.end() - 1);
       for (int j = 0; j < NP; ++j) if (point_active[j]) sorted[fill[lm_minq[j]]++] = j;
     }
-    for (int q = 0; q <= n; ++q)
-      std::sort(sorted.begin() + bucket_cnt[q], sorted.begin() + bucket_cnt[q + 1],
-                [&](int x, int y) { return lm_hash[x] != lm_hash[y] ? lm_hash[x] < lm_hash[y] : x < y; });
+    pool.run(T, [&](int t, int TT) {
+      for (int q = t; q <= n; q += TT)
+        std::sort(sorted.begin() + bucket_cnt[q], sorted.begin() + bucket_cnt[q + 1],
+                  [&](int x, int y) { return lm_hash[x] != lm_hash[y] ? lm_hash[x] < lm_hash[y] : x < y; });
+    });
     const long long total = n_active;
     long long seen = 0;
     slots.reserve(world > 1 ? n_act_pts / world + 64 : n_act_pts);
@@ -593,89 +687,92 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   s.slot_pair_ptr.assign(s.n_slots + 1, 0);
   s.slot_combo_ptr.assign(s.n_slots + 1, 0);
   const bool have_info = !g.e_info.empty(), have_delta = !g.e_delta.empty();
+  // offsets of every slot's edges, pairs and Schur targets (prefix sums), then a parallel fill
+  std::vector<int32_t> slot_edge_ptr(s.n_slots + 1, 0);
+  for (int sl = 0; sl < s.n_slots; ++sl) {
+    const int j = slots[sl];
+    slot_edge_ptr[sl + 1] = slot_edge_ptr[sl] + point_deg[j];
+    s.slot_pair_ptr[sl + 1] = s.slot_pair_ptr[sl] + lm_npairs[j];
+    s.slot_combo_ptr[sl + 1] = s.slot_combo_ptr[sl] + lm_k[j] * (lm_k[j] + 1) / 2;
+    s.slot_free[sl] = !lfix[j];
+    if (!lfix[j]) ++s.n_fl;
+  }
   {
-    size_t ne_local = 0;
-    for (int j : slots) ne_local += (size_t)point_deg[j];
+    const size_t ne_local = (size_t)slot_edge_ptr[s.n_slots], np_local = (size_t)s.slot_pair_ptr[s.n_slots];
+    s.n_edges = (int)ne_local; s.n_pairs = (int)np_local;
     s.e_orig.resize(ne_local); s.e_uv.resize(2 * ne_local); s.e_cam.resize(ne_local);
     if (have_info) s.e_info.resize(3 * ne_local);
     if (have_delta) s.e_delta.resize(ne_local);
-    s.pair_vertex.resize(ne_local); s.pair_q.resize(ne_local); s.pair_edge_ptr.resize(ne_local + 1);
-    s.combo_blk.reserve(ne_local * 2);
-    size_t ne = 0, npair = 0;
-    std::vector<int32_t> wq, wq_prev;
-    size_t prev_combo0 = 0, prev_combo_n = 0;
-    // raw pointers: the byte-typed stores below would otherwise force every vector's data
-    // pointer to be re-read on each iteration
-    const int32_t *__restrict__ ge_pose = g.e_pose.data();
-    const double *__restrict__ ge_uv = g.e_uv.data();
-    const uint8_t *__restrict__ ge_cam = g.e_cam.data();
-    const int32_t *__restrict__ qmap = s.q_of_pose.data();
-    const int32_t *__restrict__ pe = pt_edges.data();
-    int32_t *__restrict__ o_orig = s.e_orig.data();
-    double *__restrict__ o_uv = s.e_uv.data();
-    uint8_t *__restrict__ o_cam = s.e_cam.data();
-    int32_t *__restrict__ o_pv = s.pair_vertex.data(), *__restrict__ o_pq = s.pair_q.data(),
-            *__restrict__ o_pe = s.pair_edge_ptr.data();
-    for (int sl = 0; sl < s.n_slots; ++sl) {
-      const int j = slots[sl];
-      const bool lfree = !g.point_fixed[j];
-      s.slot_free[sl] = lfree;
-      if (lfree) ++s.n_fl;
-      wq.clear();
-      int last_pose = -1;
-      const int k1 = pt_ptr[j + 1];
-      for (int k = pt_ptr[j]; k < k1; ++k) {
-        const int e = pe[k];
-        const int pose = ge_pose[e];
-        if (pose != last_pose) {  // edges are sorted by pose: a new (pose, landmark) pair starts
-          last_pose = pose;
-          const int q = qmap[pose];
-          o_pv[npair] = pose; o_pq[npair] = q; o_pe[npair] = (int32_t)ne; ++npair;
-          if (q >= 0 && lfree) wq.push_back(q);
-        }
-        o_orig[ne] = e;
-        o_uv[2 * ne] = ge_uv[2 * (size_t)e]; o_uv[2 * ne + 1] = ge_uv[2 * (size_t)e + 1];
-        o_cam[ne] = ge_cam[e];
-        if (have_info) for (int t = 0; t < 3; ++t) s.e_info[3 * ne + t] = g.e_info[3 * (size_t)e + t];
-        if (have_delta) s.e_delta[ne] = g.e_delta[e];
-        ++ne;
-      }
-      s.slot_pair_ptr[sl + 1] = (int32_t)npair;
-      // Schur targets: for W-pairs a <= b (sorted by q): block (row q_b, col q_a); the previous
-      // landmark's list is reused when the pose list is the same (the common case after sorting)
-      if (!wq.empty() && wq == wq_prev) {
-        const size_t c0 = s.combo_blk.size();
-        s.combo_blk.resize(c0 + prev_combo_n);
-        std::copy(s.combo_blk.begin() + prev_combo0, s.combo_blk.begin() + prev_combo0 + prev_combo_n, s.combo_blk.begin() + c0);
-        prev_combo0 = c0;
-      } else {
-        prev_combo0 = s.combo_blk.size();
-        for (size_t a = 0; a < wq.size(); ++a)
-          for (size_t b = a; b < wq.size(); ++b) {
-            const int blk = find_block(wq[b], wq[a]);
-            if (blk < 0) { err = "internal: Schur block missing from the factor pattern"; return false; }
-            s.combo_blk.push_back(blk);
+    s.pair_vertex.resize(np_local); s.pair_q.resize(np_local); s.pair_edge_ptr.resize(np_local + 1);
+    s.combo_blk.resize((size_t)s.slot_combo_ptr[s.n_slots]);
+    s.pair_edge_ptr[np_local] = (int32_t)ne_local;
+    std::vector<int> t_err(T, 0);
+    pool.run(T, [&](int t, int TT) {
+      int s0, s1; split_range(t, TT, s.n_slots, s0, s1);
+      const double *__restrict__ ge_uv = g.e_uv.data();
+      const int32_t *__restrict__ pe = pt_edges.data();
+      int32_t *__restrict__ o_orig = s.e_orig.data();
+      double *__restrict__ o_uv = s.e_uv.data();
+      uint8_t *__restrict__ o_cam = s.e_cam.data();
+      int32_t *__restrict__ o_pv = s.pair_vertex.data(), *__restrict__ o_pq = s.pair_q.data(),
+              *__restrict__ o_pe = s.pair_edge_ptr.data(), *__restrict__ o_cb = s.combo_blk.data();
+      int wq[64], wq_prev[64];
+      std::vector<int> wq_big;
+      int k_prev = -1, prev_combo0 = 0;
+      for (int sl = s0; sl < s1; ++sl) {
+        const int j = slots[sl];
+        const bool lfree = !lfix[j];
+        size_t ne = (size_t)slot_edge_ptr[sl], npair = (size_t)s.slot_pair_ptr[sl];
+        const int kk = lm_k[j];
+        int *w = wq;
+        if (kk > 64) { wq_big.resize(kk); w = wq_big.data(); }
+        int nw = 0, last_pose = -1;
+        const int k1 = pt_ptr[j + 1];
+        for (int k = pt_ptr[j]; k < k1; ++k) {
+          const int e = pe[k];
+          const int pose = ge_pose[e];
+          if (pose != last_pose) {  // edges are sorted by pose: a new (pose, landmark) pair starts
+            last_pose = pose;
+            const int q = qmap[pose];
+            o_pv[npair] = pose; o_pq[npair] = q; o_pe[npair] = (int32_t)ne; ++npair;
+            if (q >= 0 && lfree) w[nw++] = q;
           }
-        prev_combo_n = s.combo_blk.size() - prev_combo0;
-        wq_prev = wq;
+          o_orig[ne] = e;
+          o_uv[2 * ne] = ge_uv[2 * (size_t)e]; o_uv[2 * ne + 1] = ge_uv[2 * (size_t)e + 1];
+          o_cam[ne] = ge_cam[e];
+          if (have_info) for (int u = 0; u < 3; ++u) s.e_info[3 * ne + u] = g.e_info[3 * (size_t)e + u];
+          if (have_delta) s.e_delta[ne] = g.e_delta[e];
+          ++ne;
+        }
+        // Schur targets: for W-pairs a <= b (sorted by q): block (row q_b, col q_a); the previous
+        // landmark's list is reused when the pose list is the same (the common case after sorting)
+        const int c0 = s.slot_combo_ptr[sl], nc = nw * (nw + 1) / 2;
+        bool same = nw > 0 && nw == k_prev && nw <= 64;
+        if (same) for (int i = 0; i < nw; ++i) if (w[i] != wq_prev[i]) { same = false; break; }
+        if (same) {
+          for (int i = 0; i < nc; ++i) o_cb[c0 + i] = o_cb[prev_combo0 + i];
+        } else {
+          int c = c0;
+          for (int a2 = 0; a2 < nw; ++a2)
+            for (int b2 = a2; b2 < nw; ++b2) {
+              const int blk = find_block(w[b2], w[a2]);
+              if (blk < 0) t_err[t] = 1;
+              o_cb[c++] = blk;
+            }
+          if (nw <= 64) { for (int i = 0; i < nw; ++i) wq_prev[i] = w[i]; k_prev = nw; } else k_prev = -1;
+        }
+        prev_combo0 = c0;
       }
-      s.slot_combo_ptr[sl + 1] = (int32_t)s.combo_blk.size();
-    }
-    s.pair_edge_ptr[npair] = (int32_t)ne;
-    s.pair_vertex.resize(npair); s.pair_q.resize(npair); s.pair_edge_ptr.resize(npair + 1);
-    s.n_pairs = (int)npair;
-    s.n_edges = (int)ne;
+    });
+    for (int v : t_err) if (v) { err = "internal: Schur block missing from the factor pattern"; return false; }
   }
 
   // ---- Schur work units: a run of <= 32 consecutive free landmarks with the same W pose list
   // x a chunk of <= 32 of its k(k+1)/2 block pairs (one lane per block pair, one warp per unit)
   {
-    auto wcount = [&](int sl) {
-      int k = 0;
-      for (int a = s.slot_pair_ptr[sl]; a < s.slot_pair_ptr[sl + 1] && s.pair_q[a] >= 0; ++a) ++k;
-      return s.slot_free[sl] ? k : 0;
-    };
+    auto wcount = [&](int sl) { return lm_k[slots[sl]]; };
     auto same_list = [&](int x, int y, int k) {
+      if (lm_hash[slots[x]] != lm_hash[slots[y]]) return false;
       for (int i = 0; i < k; ++i)
         if (s.pair_q[s.slot_pair_ptr[x] + i] != s.pair_q[s.slot_pair_ptr[y] + i]) return false;
       return true;
@@ -697,36 +794,45 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     s.n_units = (int)s.unit_slot.size();
   }
 
-  // ---- pose-major copy (edges of this shard whose pose is free), cut into one-pose chunks
+  // ---- pose-major view of the edges with a free pose (for the Hpp pass): an index into the
+  // landmark-major edge stream + the point row, cut into chunks of <= kHppChunk edges of one pose.
+  // Deterministic order (pose, then slot order) whatever the number of threads.
   {
-    std::vector<int32_t> cnt(n + 1, 0);
-    for (int a = 0; a < s.n_pairs; ++a)
-      if (s.pair_q[a] >= 0) cnt[s.pair_q[a] + 1] += s.pair_edge_ptr[a + 1] - s.pair_edge_ptr[a];
-    for (int q = 0; q < n; ++q) cnt[q + 1] += cnt[q];
-    s.n_pm_edges = cnt[n];
-    s.pm_uv.resize(2 * (size_t)s.n_pm_edges); s.pm_point.resize(s.n_pm_edges); s.pm_cam.resize(s.n_pm_edges);
-    if (have_info) s.pm_info.resize(3 * (size_t)s.n_pm_edges);
-    if (have_delta) s.pm_delta.resize(s.n_pm_edges);
-    std::vector<int32_t> fill(cnt.begin(), cnt.end() - 1);
-    for (int sl = 0; sl < s.n_slots; ++sl)
-      for (int a = s.slot_pair_ptr[sl]; a < s.slot_pair_ptr[sl + 1]; ++a) {
-        const int q = s.pair_q[a];
-        if (q < 0) continue;
-        for (int e = s.pair_edge_ptr[a]; e < s.pair_edge_ptr[a + 1]; ++e) {
-          const int d = fill[q]++;
-          s.pm_uv[2 * d] = s.e_uv[2 * e]; s.pm_uv[2 * d + 1] = s.e_uv[2 * e + 1];
-          s.pm_point[d] = s.slot_vertex[sl]; s.pm_cam[d] = s.e_cam[e];
-          if (have_info) for (int t = 0; t < 3; ++t) s.pm_info[3 * d + t] = s.e_info[3 * e + t];
-          if (have_delta) s.pm_delta[d] = s.e_delta[e];
+    std::vector<std::vector<int32_t>> t_cnt(T, std::vector<int32_t>(n + 1, 0));
+    pool.run(T, [&](int t, int TT) {
+      int a0, a1; split_range(t, TT, s.n_slots, a0, a1);
+      std::vector<int32_t> &cnt = t_cnt[t];
+      for (int a = s.slot_pair_ptr[a0]; a < s.slot_pair_ptr[a1]; ++a)
+        if (s.pair_q[a] >= 0) cnt[s.pair_q[a]] += s.pair_edge_ptr[a + 1] - s.pair_edge_ptr[a];
+    });
+    std::vector<int32_t> q_ptr(n + 1, 0);
+    for (int q = 0; q < n; ++q) {
+      int acc = q_ptr[q];
+      for (int t = 0; t < T; ++t) { const int c = t_cnt[t][q]; t_cnt[t][q] = acc; acc += c; }
+      q_ptr[q + 1] = acc;
+    }
+    s.n_pm_edges = q_ptr[n];
+    s.pm_src.resize(s.n_pm_edges); s.pm_point.resize(s.n_pm_edges);
+    pool.run(T, [&](int t, int TT) {
+      int a0, a1; split_range(t, TT, s.n_slots, a0, a1);
+      std::vector<int32_t> &fill = t_cnt[t];
+      for (int sl = a0; sl < a1; ++sl)
+        for (int a = s.slot_pair_ptr[sl]; a < s.slot_pair_ptr[sl + 1]; ++a) {
+          const int q = s.pair_q[a];
+          if (q < 0) continue;
+          for (int e = s.pair_edge_ptr[a]; e < s.pair_edge_ptr[a + 1]; ++e) {
+            const int d = fill[q]++;
+            s.pm_src[d] = e; s.pm_point[d] = s.slot_vertex[sl];
+          }
         }
-      }
+    });
     s.q_chunk_ptr.assign(n + 1, 0);
     s.chunk_edge_ptr.push_back(0);
     for (int q = 0; q < n; ++q) {
-      for (int e0 = cnt[q]; e0 < cnt[q + 1]; e0 += kHppChunk) {
+      for (int e0 = q_ptr[q]; e0 < q_ptr[q + 1]; e0 += kHppChunk) {
         s.chunk_q.push_back(q);
         s.chunk_vertex.push_back(s.pose_of_q[q]);
-        s.chunk_edge_ptr.push_back(std::min(e0 + kHppChunk, cnt[q + 1]));
+        s.chunk_edge_ptr.push_back(std::min(e0 + kHppChunk, q_ptr[q + 1]));
       }
       s.q_chunk_ptr[q + 1] = (int32_t)s.chunk_q.size();
     }

@@ -64,10 +64,8 @@ struct Structure {
   int n_chunks = 0, n_pm_edges = 0;
   std::vector<int32_t> chunk_q, chunk_vertex, chunk_edge_ptr; // n_chunks (+1)
   std::vector<int32_t> q_chunk_ptr;   // n_fp + 1
-  std::vector<double> pm_uv;
+  std::vector<int32_t> pm_src;        // index into the landmark-major edge stream
   std::vector<int32_t> pm_point;      // point row
-  std::vector<uint8_t> pm_cam;
-  std::vector<double> pm_info, pm_delta;
   // ---- reduced system: lower block-CSC factor pattern (with fill) over q
   int n_blocks = 0, n_schur_blocks = 0;
   std::vector<int32_t> col_ptr;       // n_fp + 1, diagonal block first in every column
