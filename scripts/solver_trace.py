@@ -29,6 +29,4 @@ for k in range(1, nseg):
     print(f"bwd {k:3d}: {v - prev:7d}")
     prev = v
 print("tail", rel[nz] - prev)
-d = out[3000:3006] - out[3000]
-print("raw", d, "npairs?")
-print("seg 6 warp0 first round: pairs", d[1], "reduce+chol", d[2] - d[1], "inverse", d[3] - d[2], "publish", d[4] - d[3], " (start offset in level:", out[3000] - out[1 + 3 * 6], ")")
+
