@@ -223,6 +223,16 @@ ssba_status ssba_chi2(ssba_handle *h, double *plain, double *robust);
 ssba_status ssba_count_outliers(ssba_handle *h, double chi2_threshold,
                                 int64_t *n_outliers, int64_t *n_inliers);
 
+/* The optimisation loop of Backend::OptimizeActiveMap (backend.cpp:175-203) with the graph
+ * resident on the device between rounds: up to `max_rounds` (5) rounds of
+ * initializeOptimization(); optimize(iters_per_round) (10), each followed by the outlier count
+ * with `chi2_threshold` (5.891) on the un-robustified chi2; stops as soon as
+ * inliers / (inliers + outliers) > `inlier_ratio` (0.7).  lambda is re-initialised in every round,
+ * as every optimize() call does.  Outputs may be NULL; `last_report` is the report of the last round. */
+ssba_status ssba_optimize_rounds(ssba_handle *h, int32_t max_rounds, int32_t iters_per_round,
+                                 double chi2_threshold, double inlier_ratio, int32_t *rounds_done,
+                                 int64_t *n_outliers, int64_t *n_inliers, ssba_report *last_report);
+
 /* ---- multi-GPU helpers ------------------------------------------------------------- */
 
 /* Host-only (needs no CUDA device): the landmark shard plan used when world_size > 1.

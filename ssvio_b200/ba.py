@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "ssba_nccl_unique_id", "ssba_set_cameras", "ssba_set_poses", "ssba_set_points",
     "ssba_set_edges", "ssba_initialize", "ssba_optimize", "ssba_step", "ssba_reset_state",
     "ssba_get_poses", "ssba_get_points", "ssba_get_edge_errors", "ssba_chi2",
-    "ssba_count_outliers", "ssba_plan_shards", "ssba_profile_get", "ssba_profile_reset", "ssba_get_problem_info",
+    "ssba_count_outliers", "ssba_optimize_rounds", "ssba_plan_shards", "ssba_profile_get", "ssba_profile_reset", "ssba_get_problem_info",
     "ssba_version",
 ]
 
@@ -120,6 +120,8 @@ def load_library():
     lib.ssba_get_edge_errors.argtypes = [H, dp]
     lib.ssba_chi2.argtypes = [H, dp, dp]
     lib.ssba_count_outliers.argtypes = [H, C.c_double, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.ssba_optimize_rounds.argtypes = [H, C.c_int32, C.c_int32, C.c_double, C.c_double, C.POINTER(C.c_int32),
+                                         C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(Report)]
     lib.ssba_plan_shards.argtypes = [C.c_int32, bp, C.c_int32, bp, C.c_int32, ip, ip, C.c_int32, ip]
     lib.ssba_profile_get.argtypes = [H, C.POINTER(Profile)]
     lib.ssba_profile_reset.argtypes = [H]
@@ -267,6 +269,13 @@ class BundleAdjuster:
     def optimize_nowait_report(self, iterations):
         """optimize() without the final chi2 read-out (bench inner loop)."""
         self._check(self.lib.ssba_optimize(self._h, int(iterations), None))
+
+    def optimize_rounds(self, max_rounds=5, iters_per_round=10, chi2_threshold=5.891, inlier_ratio=0.7):
+        """The round loop of backend.cpp:175-203; returns (rounds, n_outliers, n_inliers, report)."""
+        rd, no, ni, rep = C.c_int32(0), C.c_int64(0), C.c_int64(0), Report()
+        self._check(self.lib.ssba_optimize_rounds(self._h, int(max_rounds), int(iters_per_round), float(chi2_threshold),
+                                                  float(inlier_ratio), C.byref(rd), C.byref(no), C.byref(ni), C.byref(rep)))
+        return rd.value, no.value, ni.value, rep
 
     def step(self, iteration):
         res = C.c_int32(0)

@@ -2,6 +2,7 @@
 // enqueues trial slots on a CUDA stream, result read-back, multi-GPU plumbing (NCCL, loaded with
 // dlopen only when world_size > 1).  No CPU compute path exists here: without a CUDA device
 // ssba_create() fails.
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -157,10 +158,15 @@ ssba_status enqueue_slot(ssba_handle *h, bool first) {
   {
     PhaseTimer t(h, 0);
     launch_linearize(P, st);
-    h->prof.kernel_launches += 3;
+    h->prof.kernel_launches += 2;
   }
   if (first) {
-    if (multi) { PhaseTimer t(h, 4); if ((rc = nccl_allreduce(h, P.diag_buf, 6 * (size_t)P.n_fp, kNcclSum))) return rc; }
+    if (multi) {
+      PhaseTimer t(h, 4);
+      launch_hpp_diag(P, st);
+      h->prof.kernel_launches += 1;
+      if ((rc = nccl_allreduce(h, P.diag_buf, 6 * (size_t)P.n_fp, kNcclSum))) return rc;
+    }
     launch_maxdiag(P, st);
     if (multi) { PhaseTimer t(h, 4); if ((rc = nccl_allreduce(h, P.scal + 3, 1, kNcclMax))) return rc; }
     launch_lambda_init(P, st);
@@ -181,11 +187,11 @@ ssba_status enqueue_slot(ssba_handle *h, bool first) {
   {
     PhaseTimer t(h, 3);
     launch_update(P, st);
-    launch_reduce_partials(P, st);
-    h->prof.kernel_launches += 2;
+    h->prof.kernel_launches += 1;
+    if (multi) { launch_reduce_partials(P, st); h->prof.kernel_launches += 1; }
   }
   if (multi) { PhaseTimer t(h, 4); if ((rc = nccl_allreduce(h, P.scal, 3, kNcclSum))) return rc; }
-  launch_control(P, st);
+  launch_control(P, !multi, st);
   h->prof.kernel_launches += 1;
   return SSBA_OK;
 }
@@ -422,6 +428,7 @@ ssba_status ssba_initialize(ssba_handle *h) {
   STAT(s.slot_vertex, slot_vertex); STAT(s.slot_free, slot_free); STAT(s.slot_pair_ptr, slot_pair_ptr);
   STAT(s.slot_combo_ptr, slot_combo_ptr); STAT(s.combo_blk, combo_blk);
   STAT(s.pair_vertex, pair_vertex); STAT(s.pair_q, pair_q); STAT(s.pair_edge_ptr, pair_edge_ptr);
+  STAT(s.pair_slot, pair_slot); STAT(s.lchunk_slot, lchunk_slot);
   STAT(s.e_uv, e_uv); STAT(s.e_info, e_info); STAT(s.e_delta, e_delta); STAT(s.e_cam, e_cam); STAT(s.e_orig, e_orig);
   STAT(s.chunk_q, chunk_q); STAT(s.chunk_vertex, chunk_vertex); STAT(s.chunk_edge_ptr, chunk_edge_ptr);
   STAT(s.q_chunk_ptr, q_chunk_ptr); STAT(s.pm_point, pm_point); STAT(s.pm_src, pm_src);
@@ -437,14 +444,15 @@ ssba_status ssba_initialize(ssba_handle *h) {
     top = it.off + (bytes ? bytes : 8);
     work.push_back(it);
   };
-  const int nblk = (s.n_slots + 127) / 128 > 0 ? (s.n_slots + 127) / 128 : 1;
-  P.n_lin_blocks = P.n_upd_blocks = nblk;
+  P.n_fin_blocks = (s.n_slots + 127) / 128 > 0 ? (s.n_slots + 127) / 128 : 1;
+  P.n_lin_blocks = P.n_upd_blocks = s.n_lchunks;
+  const int nblk = std::max(P.n_fin_blocks, s.n_lchunks);
   P.sys_doubles = 36 * (size_t)s.n_blocks + 12 * (size_t)s.n_fp;
 #define DYN(field, count, type) dyn((size_t)(count) * sizeof(type), (void **)&P.field)
   DYN(pose[0], 7 * g.n_poses, double); DYN(pose[1], 7 * g.n_poses, double);
   DYN(point[0], 3 * (size_t)g.n_points, double); DYN(point[1], 3 * (size_t)g.n_points, double);
   DYN(W, 18 * (size_t)s.n_pairs, double); DYN(Hll, 6 * (size_t)s.n_slots, double); DYN(bl, 3 * (size_t)s.n_slots, double);
-  DYN(Dinv, 6 * (size_t)s.n_slots, double); DYN(hpp_part, 27 * (size_t)s.n_chunks, double); DYN(hpp, 27 * (size_t)s.n_fp, double);
+  DYN(Dinv, 6 * (size_t)s.n_slots, double); DYN(hpp_part, 27 * (size_t)s.n_chunks, double);
   DYN(sys, P.sys_doubles, double); DYN(xp, 6 * (size_t)s.n_fp, double); DYN(diag_buf, 6 * (size_t)s.n_fp, double);
   DYN(chi_cur_part, nblk, double); DYN(maxdiag_part, nblk, double); DYN(chi_new_part, nblk, double); DYN(scale_part, nblk, double);
   DYN(scal, 8, double); DYN(chi_out, 8, double);
@@ -643,6 +651,30 @@ ssba_status ssba_count_outliers(ssba_handle *h, double thr, int64_t *n_out, int6
   // edges whose two vertices are fixed are never active (sparse_optimizer.cpp:237): their
   // _error stays zero in the reference, so backend.cpp:184 counts them as inliers
   if (n_in) *n_in = (int64_t)(f[3] + 0.5) + (h->g.n_edges - h->s.n_active_edges_global);
+  return SSBA_OK;
+}
+
+ssba_status ssba_optimize_rounds(ssba_handle *h, int32_t max_rounds, int32_t iters_per_round,
+                                 double chi2_threshold, double inlier_ratio, int32_t *rounds_done,
+                                 int64_t *n_outliers, int64_t *n_inliers, ssba_report *last_report) {
+  if (!h) return SSBA_ERR_INVALID_ARG;
+  if (max_rounds < 1) return fail(h, SSBA_ERR_INVALID_ARG, "optimize_rounds: max_rounds < 1");
+  int round = 0;
+  int64_t no = 0, ni = 0;
+  ssba_report rep;
+  while (round < max_rounds) {  // backend.cpp:175
+    ssba_status rc = ssba_optimize(h, iters_per_round, &rep);  // :177-178
+    if (rc) { if (last_report) *last_report = rep; return rc; }
+    ++round;
+    rc = ssba_count_outliers(h, chi2_threshold, &no, &ni);  // :179-192
+    if (rc) return rc;
+    const double ratio = (ni + no) > 0 ? ni / double(ni + no) : 1.0;
+    if (ratio > inlier_ratio) break;  // :193-201
+  }
+  if (rounds_done) *rounds_done = round;
+  if (n_outliers) *n_outliers = no;
+  if (n_inliers) *n_inliers = ni;
+  if (last_report) *last_report = rep;
   return SSBA_OK;
 }
 

@@ -44,7 +44,8 @@ struct DeviceProblem {
   double delta_all;
   // sizes
   int n_poses, n_points, n_fp, n_slots, n_pairs, n_edges, n_blocks, n_chunks, n_levels;
-  int n_lin_blocks, n_upd_blocks;  // grid sizes = lengths of the partial-sum arrays
+  int n_lin_blocks, n_upd_blocks;  // grids of k_linearize / k_update = lengths of their partial-sum arrays
+  int n_fin_blocks;                // grid of the thread-per-landmark read-out kernel
   // estimates: two buffers each (current / trial), selected by Control::cur
   double *pose[2];    // n_poses x 7
   double *point[2];   // n_points x 3
@@ -52,7 +53,7 @@ struct DeviceProblem {
   // landmark-major shard
   const int32_t *slot_vertex, *slot_pair_ptr, *slot_combo_ptr, *combo_blk;
   const uint8_t *slot_free;
-  const int32_t *pair_vertex, *pair_q, *pair_edge_ptr;
+  const int32_t *pair_vertex, *pair_q, *pair_edge_ptr, *pair_slot, *lchunk_slot;
   const double *e_uv, *e_info, *e_delta;   // e_info / e_delta may be null
   const uint8_t *e_cam;
   const int32_t *e_orig;
@@ -71,7 +72,6 @@ struct DeviceProblem {
   double *bl;         // n_slots x 3
   double *Dinv;       // n_slots x 6
   double *hpp_part;   // n_chunks x 27 (b[6], upper-tri H[21])
-  double *hpp;        // n_fp x 27
   double *sys;        // [ L: n_blocks x 36 | bschur: n_fp x 6 | bp: n_fp x 6 ] — the all-reduced buffer
   double *xp;         // n_fp x 6
   double *diag_buf;   // n_fp x 6 Hpp diagonals (lambda init, summed over ranks)
@@ -96,7 +96,8 @@ void launch_schur(const DeviceProblem &P, cudaStream_t st);
 void launch_reduced_solve(const DeviceProblem &P, cudaStream_t st);
 void launch_update(const DeviceProblem &P, cudaStream_t st);
 void launch_reduce_partials(const DeviceProblem &P, cudaStream_t st);  // -> scal[0..2]
-void launch_control(const DeviceProblem &P, cudaStream_t st);
+void launch_control(const DeviceProblem &P, bool fused_reduce, cudaStream_t st);
+void launch_hpp_diag(const DeviceProblem &P, cudaStream_t st);       // multi-GPU lambda init
 void launch_final_chi2(const DeviceProblem &P, double threshold, cudaStream_t st);  // -> chi_out
 void launch_edge_errors(const DeviceProblem &P, cudaStream_t st);      // -> err_out
 void launch_gather_points(const DeviceProblem &P, cudaStream_t st);    // -> gather

@@ -78,10 +78,11 @@ __device__ __forceinline__ void load_edge_weighting(const DeviceProblem &P, cons
   huber(t.chi, d, t.rho0, t.w);
 }
 
+template <int kMode>
 __device__ __forceinline__ void linearize_edge(const DeviceProblem &P, int cam, const double *T,
                                                const double *p, double u, double v, EdgeTerms &t,
                                                double *Jx, double *Jp) {
-  if (P.jacobian_mode == SSBA_JACOBIAN_NUMERIC)
+  if (kMode == SSBA_JACOBIAN_NUMERIC)
     edge_linearize_numeric(P.cams.K, P.cams.ext[cam], T, p, u, v, t.e0, t.e1, Jx, Jp);
   else
     edge_linearize_analytic(P.cams.K, P.cams.ext[cam], P.ext_R[cam], T, p, u, v, t.e0, t.e1, Jx, Jp);
@@ -93,86 +94,149 @@ __device__ __forceinline__ void linearize_edge(const DeviceProblem &P, int cam, 
 // the Huber weighting of robust_kernel_impl.cpp:65-78 / base_edge.h:117-123, accumulating
 // Hll, b_l and the Hpl blocks W; also activeRobustChi2 of the current state
 // (sparse_optimizer.cpp:102-116) and the landmark part of computeLambdaInit's max |H_jj|.
-// One thread per landmark slot: Hll/b_l/W stay in registers, no atomics.
+//
+// One thread per (pose, landmark) PAIR (its 1..n_cams edges), one CTA per chunk of whole
+// landmarks with <= 128 pairs: W is produced in registers and stored as consecutive 144-byte
+// records by consecutive threads; the Hll / b_l partials of a landmark's pairs meet in shared
+// memory and are folded in pair order by the landmark's first thread.  No atomics, deterministic.
+struct PairLin {
+  double W[18], H[6], b[3], chi;
+};
+
+template <int kMode>
+__device__ __forceinline__ void linearize_pair(const DeviceProblem &P, int a, bool lfree, const double *pose,
+                                               const double *p, PairLin &o) {
+  const int kv = P.pair_vertex[a];
+  const bool wpair = lfree && P.pair_q[a] >= 0;
+  double T[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) T[i] = pose[7 * kv + i];
+#pragma unroll
+  for (int i = 0; i < 18; ++i) o.W[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) o.H[i] = 0.0;
+  o.b[0] = o.b[1] = o.b[2] = 0.0;
+  o.chi = 0.0;
+  const int e1 = P.pair_edge_ptr[a + 1];
+  for (int e = P.pair_edge_ptr[a]; e < e1; ++e) {
+    EdgeTerms t;
+    double Jx[12], Jp[6];
+    linearize_edge<kMode>(P, P.e_cam[e], T, p, P.e_uv[2 * e], P.e_uv[2 * e + 1], t, Jx, Jp);
+    load_edge_weighting(P, P.e_info, P.e_delta, e, t);
+    o.chi += t.rho0;
+    if (lfree) {
+      // rows of (rho' Omega) J_p
+      double A0[3], A1[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        A0[c] = t.w * (t.o00 * Jp[c] + t.o01 * Jp[3 + c]);
+        A1[c] = t.w * (t.o01 * Jp[c] + t.o11 * Jp[3 + c]);
+      }
+      o.H[0] += Jp[0] * A0[0] + Jp[3] * A1[0];
+      o.H[1] += Jp[0] * A0[1] + Jp[3] * A1[1];
+      o.H[2] += Jp[0] * A0[2] + Jp[3] * A1[2];
+      o.H[3] += Jp[1] * A0[1] + Jp[4] * A1[1];
+      o.H[4] += Jp[1] * A0[2] + Jp[4] * A1[2];
+      o.H[5] += Jp[2] * A0[2] + Jp[5] * A1[2];
+      const double r0 = -t.w * t.we0, r1 = -t.w * t.we1;  // omega_r * rho'
+#pragma unroll
+      for (int c = 0; c < 3; ++c) o.b[c] += Jp[c] * r0 + Jp[3 + c] * r1;
+      if (wpair) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) o.W[3 * r + c] += Jx[r] * A0[c] + Jx[6 + r] * A1[c];
+      }
+    }
+  }
+  if (wpair) {
+    double2 *dst = reinterpret_cast<double2 *>(P.W + 18 * (size_t)a);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) dst[i] = make_double2(o.W[2 * i], o.W[2 * i + 1]);
+  }
+}
+
+template <int kMode>
 __global__ void __launch_bounds__(kLinThreads) k_linearize(const DeviceProblem P) {
   const Control *ctl = P.ctl;
   if (ctl->done || !ctl->need_linearize) return;
   __shared__ double red[kLinThreads / 32];
+  __shared__ double s_part[kLinThreads][9];
   const int cur = ctl->cur;
   const double *__restrict__ pose = P.pose[cur];
   const double *__restrict__ point = P.point[cur];
-  const int sl = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s0 = P.lchunk_slot[blockIdx.x], s1 = P.lchunk_slot[blockIdx.x + 1];
+  const int a0 = P.slot_pair_ptr[s0], a1 = P.slot_pair_ptr[s1];
+  const int tid = threadIdx.x;
   double chi = 0.0, mx = 0.0;
-  if (sl < P.n_slots) {
+  if (a1 - a0 <= kLinThreads) {
+    if (tid < a1 - a0) {
+      const int a = a0 + tid;
+      const int sl = P.pair_slot[a];
+      const int pv = P.slot_vertex[sl];
+      const double p[3] = {point[3 * pv], point[3 * pv + 1], point[3 * pv + 2]};
+      PairLin o;
+      linearize_pair<kMode>(P, a, P.slot_free[sl] != 0, pose, p, o);
+      chi = o.chi;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) s_part[tid][i] = o.H[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) s_part[tid][6 + i] = o.b[i];
+    }
+    __syncthreads();
+    const int sl = s0 + tid;
+    if (sl < s1 && P.slot_free[sl]) {
+      double acc[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) acc[i] = 0.0;
+      for (int a = P.slot_pair_ptr[sl] - a0; a < P.slot_pair_ptr[sl + 1] - a0; ++a) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) acc[i] += s_part[a][i];
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) P.Hll[6 * (size_t)sl + i] = acc[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) P.bl[3 * (size_t)sl + i] = acc[6 + i];
+      mx = fmax(fabs(acc[0]), fmax(fabs(acc[3]), fabs(acc[5])));
+    }
+  } else {
+    // a single landmark seen by more than 128 poses: threads stride over its pairs
+    const int sl = s0;
     const int pv = P.slot_vertex[sl];
     const bool lfree = P.slot_free[sl] != 0;
     const double p[3] = {point[3 * pv], point[3 * pv + 1], point[3 * pv + 2]};
-    double H[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
-    const int a1 = P.slot_pair_ptr[sl + 1];
-    for (int a = P.slot_pair_ptr[sl]; a < a1; ++a) {
-      const int kv = P.pair_vertex[a];
-      const bool wpair = lfree && P.pair_q[a] >= 0;
-      double T[7];
+    double acc[9];
 #pragma unroll
-      for (int i = 0; i < 7; ++i) T[i] = pose[7 * kv + i];
-      double W[18];
+    for (int i = 0; i < 9; ++i) acc[i] = 0.0;
+    for (int a = a0 + tid; a < a1; a += kLinThreads) {
+      PairLin o;
+      linearize_pair<kMode>(P, a, lfree, pose, p, o);
+      chi += o.chi;
 #pragma unroll
-      for (int i = 0; i < 18; ++i) W[i] = 0.0;
-      const int e1 = P.pair_edge_ptr[a + 1];
-      for (int e = P.pair_edge_ptr[a]; e < e1; ++e) {
-        EdgeTerms t;
-        double Jx[12], Jp[6];
-        linearize_edge(P, P.e_cam[e], T, p, P.e_uv[2 * e], P.e_uv[2 * e + 1], t, Jx, Jp);
-        load_edge_weighting(P, P.e_info, P.e_delta, e, t);
-        chi += t.rho0;
-        if (lfree) {
-          // rows of (rho' Omega) J_p
-          double A0[3], A1[3];
+      for (int i = 0; i < 6; ++i) acc[i] += o.H[i];
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            A0[c] = t.w * (t.o00 * Jp[c] + t.o01 * Jp[3 + c]);
-            A1[c] = t.w * (t.o01 * Jp[c] + t.o11 * Jp[3 + c]);
-          }
-          H[0] += Jp[0] * A0[0] + Jp[3] * A1[0];
-          H[1] += Jp[0] * A0[1] + Jp[3] * A1[1];
-          H[2] += Jp[0] * A0[2] + Jp[3] * A1[2];
-          H[3] += Jp[1] * A0[1] + Jp[4] * A1[1];
-          H[4] += Jp[1] * A0[2] + Jp[4] * A1[2];
-          H[5] += Jp[2] * A0[2] + Jp[5] * A1[2];
-          const double r0 = -t.w * t.we0, r1 = -t.w * t.we1;  // omega_r * rho'
-#pragma unroll
-          for (int c = 0; c < 3; ++c) b[c] += Jp[c] * r0 + Jp[3 + c] * r1;
-          if (wpair) {
-#pragma unroll
-            for (int r = 0; r < 6; ++r)
-#pragma unroll
-              for (int c = 0; c < 3; ++c) W[3 * r + c] += Jx[r] * A0[c] + Jx[6 + r] * A1[c];
-          }
-        }
-      }
-      if (wpair) {
-        double2 *dst = reinterpret_cast<double2 *>(P.W + 18 * (size_t)a);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) dst[i] = make_double2(W[2 * i], W[2 * i + 1]);
-      }
+      for (int i = 0; i < 3; ++i) acc[6 + i] += o.b[i];
     }
-    if (lfree) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) P.Hll[6 * (size_t)sl + i] = H[i];
+    for (int i = 0; i < 9; ++i) acc[i] = block_sum<kLinThreads>(acc[i], red);
+    if (tid == 0 && lfree) {
 #pragma unroll
-      for (int i = 0; i < 3; ++i) P.bl[3 * (size_t)sl + i] = b[i];
-      mx = fmax(fabs(H[0]), fmax(fabs(H[3]), fabs(H[5])));
+      for (int i = 0; i < 6; ++i) P.Hll[6 * (size_t)sl + i] = acc[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) P.bl[3 * (size_t)sl + i] = acc[6 + i];
+      mx = fmax(fabs(acc[0]), fmax(fabs(acc[3]), fabs(acc[5])));
     }
   }
-  const double s = block_sum<kLinThreads>(chi, red);
+  const double s_ = block_sum<kLinThreads>(chi, red);
   const double m = block_max<kLinThreads>(mx, red);
-  if (threadIdx.x == 0) { P.chi_cur_part[blockIdx.x] = s; P.maxdiag_part[blockIdx.x] = m; }
+  if (tid == 0) { P.chi_cur_part[blockIdx.x] = s_; P.maxdiag_part[blockIdx.x] = m; }
 }
 
 // ---------------------------------------------------------------------------------------------
 // k_hpp — pose side of buildSystem: Hpp_ii += J_xi^T (rho' Omega) J_xi, b_i += J_xi^T(-rho' Omega e)
 // (base_binary_edge.hpp:104-110).  Pose-major pass, one CTA per chunk of <= 256 edges of ONE pose:
 // 27 register accumulators per thread, deterministic block reduction, no atomics.
+template <int kMode>
 __global__ void __launch_bounds__(kHppThreads) k_hpp(const DeviceProblem P) {
   const Control *ctl = P.ctl;
   if (ctl->done || !ctl->need_linearize) return;
@@ -195,7 +259,7 @@ __global__ void __launch_bounds__(kHppThreads) k_hpp(const DeviceProblem P) {
     const double p[3] = {point[3 * pv], point[3 * pv + 1], point[3 * pv + 2]};
     EdgeTerms t;
     double Jx[12], Jp[6];
-    linearize_edge(P, P.e_cam[e], T, p, P.e_uv[2 * e], P.e_uv[2 * e + 1], t, Jx, Jp);
+    linearize_edge<kMode>(P, P.e_cam[e], T, p, P.e_uv[2 * e], P.e_uv[2 * e + 1], t, Jx, Jp);
     load_edge_weighting(P, P.e_info, P.e_delta, e, t);
     double A0[6], A1[6];
 #pragma unroll
@@ -226,19 +290,23 @@ __global__ void __launch_bounds__(kHppThreads) k_hpp(const DeviceProblem P) {
   }
 }
 
-// fold the chunk partials of every pose in chunk order; keep the diagonal for lambda init
-__global__ void k_hpp_reduce(const DeviceProblem P) {
-  const Control *ctl = P.ctl;
-  if (ctl->done || !ctl->need_linearize) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.n_fp * 27) return;
-  const int q = i / 27, k = i % 27;
+// Hpp / b_p entry k (0..5 = b, 6..26 = upper triangle) of pose q: the chunk partials of the
+// pose folded in chunk order (deterministic)
+__device__ __forceinline__ double hpp_sum(const DeviceProblem &P, int q, int k) {
   double s = 0.0;
   for (int c = P.q_chunk_ptr[q]; c < P.q_chunk_ptr[q + 1]; ++c) s += P.hpp_part[27 * (size_t)c + k];
-  P.hpp[i] = s;
-  // upper-triangle offsets of the diagonal entries: 6, 12, 17, 21, 24, 26
-  const int dsel = k == 6 ? 0 : k == 12 ? 1 : k == 17 ? 2 : k == 21 ? 3 : k == 24 ? 4 : k == 26 ? 5 : -1;
-  if (dsel >= 0) P.diag_buf[6 * q + dsel] = s;
+  return s;
+}
+// upper-triangle offset of diagonal entry d of the 6x6 block: 6, 12, 17, 21, 24, 26
+__device__ __forceinline__ int hpp_diag_index(int d) { return 6 + d * 6 - d * (d - 1) / 2; }
+
+// multi-GPU, first iteration only: this rank's Hpp diagonals -> diag_buf (summed over ranks by
+// the host-enqueued all-reduce before k_maxdiag)
+__global__ void k_hpp_diag(const DeviceProblem P) {
+  const Control *ctl = P.ctl;
+  if (ctl->done || !ctl->first_iteration) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 6 * P.n_fp) P.diag_buf[i] = hpp_sum(P, i / 6, hpp_diag_index(i % 6));
 }
 
 // max |H_jj| over pose and landmark diagonals (levenberg.cpp:152-166) -> scal[3]
@@ -247,7 +315,8 @@ __global__ void __launch_bounds__(256) k_maxdiag(const DeviceProblem P) {
   if (ctl->done || !ctl->first_iteration) return;
   __shared__ double red[8];
   double m = 0.0;
-  for (int i = threadIdx.x; i < 6 * P.n_fp; i += 256) m = fmax(m, fabs(P.diag_buf[i]));
+  for (int i = threadIdx.x; i < 6 * P.n_fp; i += 256)
+    m = fmax(m, fabs(ctl->world > 1 ? P.diag_buf[i] : hpp_sum(P, i / 6, hpp_diag_index(i % 6))));
   for (int i = threadIdx.x; i < P.n_lin_blocks; i += 256) m = fmax(m, P.maxdiag_part[i]);
   m = block_max<256>(m, red);
   if (threadIdx.x == 0) P.scal[3] = m;
@@ -279,13 +348,13 @@ __global__ void k_prepare_system(const DeviceProblem P) {
     if (P.blk_row[b] == col) {
       const int r = e / 6, c = e % 6;
       const int lo = r < c ? r : c, hi = r < c ? c : r;
-      v = P.hpp[27 * (size_t)col + 6 + lo * 6 - lo * (lo - 1) / 2 + (hi - lo)];
+      v = hpp_sum(P, col, 6 + lo * 6 - lo * (lo - 1) / 2 + (hi - lo));
       if (r == c && ctl->rank == 0) v += ctl->lambda;
     }
     P.sys[i] = v;
   } else if (i < nL + 6 * (size_t)P.n_fp) {
     const size_t k = i - nL;
-    const double v = P.hpp[27 * (k / 6) + (k % 6)];
+    const double v = hpp_sum(P, (int)(k / 6), (int)(k % 6));
     P.sys[i] = v;                          // bschur
     P.sys[i + 6 * (size_t)P.n_fp] = v;     // b_p (kept for computeScale)
   }
@@ -754,63 +823,111 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
 // ---------------------------------------------------------------------------------------------
 // k_update — landmark back-substitution x_l = Dinv (b_l - W^T x_p) (block_solver.hpp:420-442),
 // p <- p + x_l (g2otypes.hpp:54-59), the landmark part of computeScale, and the trial
-// computeActiveErrors + activeRobustChi2 (levenberg.cpp:116-117), one thread per landmark slot.
+// computeActiveErrors + activeRobustChi2 (levenberg.cpp:116-117).  Same decomposition as
+// k_linearize: one thread per pair (W^T x_p, then the pair's trial residuals), the landmark's
+// first thread folds the pairs and moves the point.
+__device__ __forceinline__ double pair_trial_chi(const DeviceProblem &P, int a, const double *pose_new, const double *p) {
+  const int kv = P.pair_vertex[a];
+  double T[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) T[i] = pose_new[7 * kv + i];
+  double chi = 0.0;
+  const int e1 = P.pair_edge_ptr[a + 1];
+  for (int e = P.pair_edge_ptr[a]; e < e1; ++e) {
+    EdgeTerms t;
+    edge_error(P.cams.K, P.cams.ext[P.e_cam[e]], T, p, P.e_uv[2 * e], P.e_uv[2 * e + 1], t.e0, t.e1);
+    load_edge_weighting(P, P.e_info, P.e_delta, e, t);
+    chi += t.rho0;
+  }
+  return chi;
+}
+
+__device__ __forceinline__ void pair_wtx(const DeviceProblem &P, int a, double *c3) {
+  c3[0] = c3[1] = c3[2] = 0.0;
+  const int q = P.pair_q[a];
+  if (q < 0) return;
+  const double2 *src = reinterpret_cast<const double2 *>(P.W + 18 * (size_t)a);
+  double Wv[18];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { const double2 t = src[i]; Wv[2 * i] = t.x; Wv[2 * i + 1] = t.y; }
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    const double xr = P.xp[6 * q + r];
+    c3[0] += Wv[3 * r] * xr; c3[1] += Wv[3 * r + 1] * xr; c3[2] += Wv[3 * r + 2] * xr;
+  }
+}
+
 __global__ void __launch_bounds__(kLinThreads) k_update(const DeviceProblem P) {
   const Control *ctl = P.ctl;
   if (ctl->done) return;
   __shared__ double red[kLinThreads / 32];
+  __shared__ double s_part[kLinThreads][3];
+  __shared__ double s_pnew[kLinThreads][3];
   const int cur = ctl->cur;
   const bool fail = ctl->chol_fail != 0;
   const double lambda = ctl->lambda;
   const double *__restrict__ pose_new = P.pose[cur ^ 1];
-  const int sl = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s0 = P.lchunk_slot[blockIdx.x], s1 = P.lchunk_slot[blockIdx.x + 1];
+  const int a0 = P.slot_pair_ptr[s0], a1 = P.slot_pair_ptr[s1];
+  const int tid = threadIdx.x;
+  const bool small = a1 - a0 <= kLinThreads;
   double chi = 0.0, scale = 0.0;
-  if (sl < P.n_slots) {
-    const int pv = P.slot_vertex[sl];
-    double p[3] = {P.point[cur][3 * pv], P.point[cur][3 * pv + 1], P.point[cur][3 * pv + 2]};
-    const int a0 = P.slot_pair_ptr[sl], a1 = P.slot_pair_ptr[sl + 1];
-    if (P.slot_free[sl]) {
-      const double b0 = P.bl[3 * (size_t)sl], b1 = P.bl[3 * (size_t)sl + 1], b2 = P.bl[3 * (size_t)sl + 2];
-      double c0 = b0, c1 = b1, c2 = b2;
-      for (int a = a0; a < a1; ++a) {
-        const int q = P.pair_q[a];
-        if (q < 0) break;
-        const double2 *src = reinterpret_cast<const double2 *>(P.W + 18 * (size_t)a);
-        double Wv[18];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) { const double2 t = src[i]; Wv[2 * i] = t.x; Wv[2 * i + 1] = t.y; }
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {
-          const double xr = P.xp[6 * q + r];
-          c0 -= Wv[3 * r] * xr; c1 -= Wv[3 * r + 1] * xr; c2 -= Wv[3 * r + 2] * xr;
-        }
-      }
-      const double *Di = P.Dinv + 6 * (size_t)sl;
-      double x0 = Di[0] * c0 + Di[1] * c1 + Di[2] * c2;
-      double x1 = Di[1] * c0 + Di[3] * c1 + Di[4] * c2;
-      double x2 = Di[2] * c0 + Di[4] * c1 + Di[5] * c2;
-      if (fail) { x0 = x1 = x2 = 0.0; }
-      scale = x0 * (lambda * x0 + b0) + x1 * (lambda * x1 + b1) + x2 * (lambda * x2 + b2);
-      p[0] += x0; p[1] += x1; p[2] += x2;
-      P.point[cur ^ 1][3 * pv] = p[0]; P.point[cur ^ 1][3 * pv + 1] = p[1]; P.point[cur ^ 1][3 * pv + 2] = p[2];
+  // ---- W^T x_p per pair
+  double c3[3] = {0.0, 0.0, 0.0};
+  if (small) {
+    if (tid < a1 - a0 && P.slot_free[P.pair_slot[a0 + tid]]) pair_wtx(P, a0 + tid, c3);
+    s_part[tid][0] = c3[0]; s_part[tid][1] = c3[1]; s_part[tid][2] = c3[2];
+  } else if (P.slot_free[s0]) {
+    for (int a = a0 + tid; a < a1; a += kLinThreads) {
+      double t3[3];
+      pair_wtx(P, a, t3);
+      c3[0] += t3[0]; c3[1] += t3[1]; c3[2] += t3[2];
     }
-    for (int a = a0; a < a1; ++a) {
-      const int kv = P.pair_vertex[a];
-      double T[7];
 #pragma unroll
-      for (int i = 0; i < 7; ++i) T[i] = pose_new[7 * kv + i];
-      const int e1 = P.pair_edge_ptr[a + 1];
-      for (int e = P.pair_edge_ptr[a]; e < e1; ++e) {
-        EdgeTerms t;
-        edge_error(P.cams.K, P.cams.ext[P.e_cam[e]], T, p, P.e_uv[2 * e], P.e_uv[2 * e + 1], t.e0, t.e1);
-        load_edge_weighting(P, P.e_info, P.e_delta, e, t);
-        chi += t.rho0;
+    for (int i = 0; i < 3; ++i) { const double v = block_sum<kLinThreads>(c3[i], red); if (tid == 0) s_part[0][i] = v; }
+  }
+  __syncthreads();
+  // ---- the landmark's first thread: x_l, scale, new position
+  {
+    const int sl = s0 + tid;
+    if (sl < s1) {
+      const int pv = P.slot_vertex[sl];
+      double p[3] = {P.point[cur][3 * pv], P.point[cur][3 * pv + 1], P.point[cur][3 * pv + 2]};
+      if (P.slot_free[sl]) {
+        const double b0 = P.bl[3 * (size_t)sl], b1 = P.bl[3 * (size_t)sl + 1], b2 = P.bl[3 * (size_t)sl + 2];
+        double c0 = b0, c1 = b1, c2 = b2;
+        if (small) {
+          for (int a = P.slot_pair_ptr[sl] - a0; a < P.slot_pair_ptr[sl + 1] - a0; ++a) {
+            c0 -= s_part[a][0]; c1 -= s_part[a][1]; c2 -= s_part[a][2];
+          }
+        } else {
+          c0 -= s_part[0][0]; c1 -= s_part[0][1]; c2 -= s_part[0][2];
+        }
+        const double *Di = P.Dinv + 6 * (size_t)sl;
+        double x0 = Di[0] * c0 + Di[1] * c1 + Di[2] * c2;
+        double x1 = Di[1] * c0 + Di[3] * c1 + Di[4] * c2;
+        double x2 = Di[2] * c0 + Di[4] * c1 + Di[5] * c2;
+        if (fail) { x0 = x1 = x2 = 0.0; }
+        scale = x0 * (lambda * x0 + b0) + x1 * (lambda * x1 + b1) + x2 * (lambda * x2 + b2);
+        p[0] += x0; p[1] += x1; p[2] += x2;
+        P.point[cur ^ 1][3 * pv] = p[0]; P.point[cur ^ 1][3 * pv + 1] = p[1]; P.point[cur ^ 1][3 * pv + 2] = p[2];
       }
+      s_pnew[tid][0] = p[0]; s_pnew[tid][1] = p[1]; s_pnew[tid][2] = p[2];
     }
   }
-  const double s = block_sum<kLinThreads>(chi, red);
+  __syncthreads();
+  // ---- trial residuals per pair
+  if (small) {
+    if (tid < a1 - a0) {
+      const int a = a0 + tid;
+      chi = pair_trial_chi(P, a, pose_new, s_pnew[P.pair_slot[a] - s0]);
+    }
+  } else {
+    for (int a = a0 + tid; a < a1; a += kLinThreads) chi += pair_trial_chi(P, a, pose_new, s_pnew[0]);
+  }
+  const double s_ = block_sum<kLinThreads>(chi, red);
   const double sc = block_sum<kLinThreads>(scale, red);
-  if (threadIdx.x == 0) { P.chi_new_part[blockIdx.x] = s; P.scale_part[blockIdx.x] = sc; }
+  if (tid == 0) { P.chi_new_part[blockIdx.x] = s_; P.scale_part[blockIdx.x] = sc; }
 }
 
 // partial sums -> scal[0..2] = chi(current), chi(trial), landmark part of computeScale
@@ -831,9 +948,21 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const DeviceProblem P) 
 // k_control — the accept/reject law of OptimizationAlgorithmLevenberg::solve
 // (levenberg.cpp:119-149) and the iteration bookkeeping of SparseOptimizer::optimize
 // (sparse_optimizer.cpp:386-426), on the device so that no host round trip sits between trials.
-__global__ void k_control(const DeviceProblem P) {
+template <bool kFusedReduce>
+__global__ void __launch_bounds__(256) k_control(const DeviceProblem P) {
   Control *c = P.ctl;
   if (c->done) return;
+  if (kFusedReduce) {  // single GPU: fold the partial sums here instead of in k_reduce_partials
+    __shared__ double red[8];
+    double a = 0.0, b = 0.0, cc = 0.0;
+    for (int i = threadIdx.x; i < P.n_lin_blocks; i += 256) a += P.chi_cur_part[i];
+    for (int i = threadIdx.x; i < P.n_upd_blocks; i += 256) { b += P.chi_new_part[i]; cc += P.scale_part[i]; }
+    a = block_sum<256>(a, red);
+    b = block_sum<256>(b, red);
+    cc = block_sum<256>(cc, red);
+    if (threadIdx.x == 0) { P.scal[0] = a; P.scal[1] = b; P.scal[2] = cc; }
+  }
+  if (threadIdx.x != 0) return;
   const double currentChi = P.scal[0];
   double tempChi = P.scal[1];
   if (c->outer_iter == 0 && c->qmax == 0) c->chi2_initial = currentChi;
@@ -925,7 +1054,7 @@ __global__ void __launch_bounds__(kLinThreads) k_final_chi2(const DeviceProblem 
 __global__ void __launch_bounds__(256) k_final_reduce(const DeviceProblem P) {
   __shared__ double red[8];
   double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
-  for (int i = threadIdx.x; i < P.n_lin_blocks; i += 256) {
+  for (int i = threadIdx.x; i < P.n_fin_blocks; i += 256) {
     a += P.chi_cur_part[i]; b += P.maxdiag_part[i]; c += P.chi_new_part[i]; d += P.scale_part[i];
   }
   a = block_sum<256>(a, red); b = block_sum<256>(b, red);
@@ -945,7 +1074,7 @@ inline int div_up(long long a, int b) { return (int)((a + b - 1) / b); }
 
 // ------------------------------------------------------------------------------------------------
 
-int kernels_per_linearize() { return 3; }
+int kernels_per_linearize() { return 2; }
 
 #ifdef SSBA_SOLVER_TRACE
 extern "C" int ssba_debug_solver_trace(long long *out, int n) {
@@ -955,9 +1084,17 @@ extern "C" int ssba_debug_solver_trace(long long *out, int n) {
 #endif
 
 void launch_linearize(const DeviceProblem &P, cudaStream_t st) {
-  k_linearize<<<P.n_lin_blocks, kLinThreads, 0, st>>>(P);
-  if (P.n_chunks > 0) k_hpp<<<P.n_chunks, kHppThreads, 0, st>>>(P);
-  if (P.n_fp > 0) k_hpp_reduce<<<div_up(27LL * P.n_fp, 128), 128, 0, st>>>(P);
+  if (P.jacobian_mode == SSBA_JACOBIAN_NUMERIC) {
+    if (P.n_lin_blocks > 0) k_linearize<SSBA_JACOBIAN_NUMERIC><<<P.n_lin_blocks, kLinThreads, 0, st>>>(P);
+    if (P.n_chunks > 0) k_hpp<SSBA_JACOBIAN_NUMERIC><<<P.n_chunks, kHppThreads, 0, st>>>(P);
+  } else {
+    if (P.n_lin_blocks > 0) k_linearize<SSBA_JACOBIAN_ANALYTIC><<<P.n_lin_blocks, kLinThreads, 0, st>>>(P);
+    if (P.n_chunks > 0) k_hpp<SSBA_JACOBIAN_ANALYTIC><<<P.n_chunks, kHppThreads, 0, st>>>(P);
+  }
+}
+
+void launch_hpp_diag(const DeviceProblem &P, cudaStream_t st) {
+  if (P.n_fp > 0) k_hpp_diag<<<div_up(6LL * P.n_fp, 128), 128, 0, st>>>(P);
 }
 
 void launch_maxdiag(const DeviceProblem &P, cudaStream_t st) { k_maxdiag<<<1, 256, 0, st>>>(P); }
@@ -990,17 +1127,20 @@ void launch_reduced_solve(const DeviceProblem &P, cudaStream_t st) {
 }
 
 void launch_update(const DeviceProblem &P, cudaStream_t st) {
-  k_update<<<P.n_upd_blocks, kLinThreads, 0, st>>>(P);
+  if (P.n_upd_blocks > 0) k_update<<<P.n_upd_blocks, kLinThreads, 0, st>>>(P);
 }
 
 void launch_reduce_partials(const DeviceProblem &P, cudaStream_t st) {
   k_reduce_partials<<<1, 256, 0, st>>>(P);
 }
 
-void launch_control(const DeviceProblem &P, cudaStream_t st) { k_control<<<1, 1, 0, st>>>(P); }
+void launch_control(const DeviceProblem &P, bool fused_reduce, cudaStream_t st) {
+  if (fused_reduce) k_control<true><<<1, 256, 0, st>>>(P);
+  else k_control<false><<<1, 32, 0, st>>>(P);
+}
 
 void launch_final_chi2(const DeviceProblem &P, double threshold, cudaStream_t st) {
-  k_final_chi2<<<P.n_lin_blocks, kLinThreads, 0, st>>>(P, threshold, 0);
+  k_final_chi2<<<P.n_fin_blocks, kLinThreads, 0, st>>>(P, threshold, 0);
   k_final_reduce<<<1, 256, 0, st>>>(P);
 }
 
@@ -1009,7 +1149,7 @@ void launch_gather_points(const DeviceProblem &P, cudaStream_t st) {
 }
 
 void launch_edge_errors(const DeviceProblem &P, cudaStream_t st) {
-  k_final_chi2<<<P.n_lin_blocks, kLinThreads, 0, st>>>(P, 0.0, 1);
+  k_final_chi2<<<P.n_fin_blocks, kLinThreads, 0, st>>>(P, 0.0, 1);
 }
 
 }  // namespace ssba

@@ -20,6 +20,7 @@ namespace {
 constexpr int kHppChunk = 256;  // edges per pose-major chunk (one CTA each)
 constexpr int kMaxLevelCols = kSolveMaxCols;  // ssba_solver_layout.hpp
 constexpr int kSchurRunPairs = 160; // = kSchurRunPairs of k_schur
+constexpr int kLinPairs = 128;      // = kLinThreads of k_linearize / k_update
 
 // Symbolic factorisation of the reduced system under one elimination order, plus the schedule
 // the device solver walks: columns grouped by elimination-tree level, and per level the
@@ -704,6 +705,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     if (have_info) s.e_info.resize(3 * ne_local);
     if (have_delta) s.e_delta.resize(ne_local);
     s.pair_vertex.resize(np_local); s.pair_q.resize(np_local); s.pair_edge_ptr.resize(np_local + 1);
+    s.pair_slot.resize(np_local);
     s.combo_blk.resize((size_t)s.slot_combo_ptr[s.n_slots]);
     s.pair_edge_ptr[np_local] = (int32_t)ne_local;
     std::vector<int> t_err(T, 0);
@@ -715,7 +717,8 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
       double *__restrict__ o_uv = s.e_uv.data();
       uint8_t *__restrict__ o_cam = s.e_cam.data();
       int32_t *__restrict__ o_pv = s.pair_vertex.data(), *__restrict__ o_pq = s.pair_q.data(),
-              *__restrict__ o_pe = s.pair_edge_ptr.data(), *__restrict__ o_cb = s.combo_blk.data();
+              *__restrict__ o_pe = s.pair_edge_ptr.data(), *__restrict__ o_cb = s.combo_blk.data(),
+              *__restrict__ o_ps = s.pair_slot.data();
       int wq[64], wq_prev[64];
       std::vector<int> wq_big;
       int k_prev = -1, prev_combo0 = 0;
@@ -734,7 +737,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
           if (pose != last_pose) {  // edges are sorted by pose: a new (pose, landmark) pair starts
             last_pose = pose;
             const int q = qmap[pose];
-            o_pv[npair] = pose; o_pq[npair] = q; o_pe[npair] = (int32_t)ne; ++npair;
+            o_pv[npair] = pose; o_pq[npair] = q; o_pe[npair] = (int32_t)ne; o_ps[npair] = sl; ++npair;
             if (q >= 0 && lfree) w[nw++] = q;
           }
           o_orig[ne] = e;
@@ -765,6 +768,19 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
       }
     });
     for (int v : t_err) if (v) { err = "internal: Schur block missing from the factor pattern"; return false; }
+  }
+
+  // ---- CTAs of the per-pair kernels: runs of whole landmarks with <= kLinPairs pairs
+  {
+    s.lchunk_slot.assign(1, 0);
+    int acc = 0;
+    for (int sl = 0; sl < s.n_slots; ++sl) {
+      const int np_ = s.slot_pair_ptr[sl + 1] - s.slot_pair_ptr[sl];
+      if (acc > 0 && acc + np_ > kLinPairs) { s.lchunk_slot.push_back(sl); acc = 0; }
+      acc += np_;
+    }
+    if (s.n_slots > 0) s.lchunk_slot.push_back(s.n_slots);
+    s.n_lchunks = (int)s.lchunk_slot.size() - 1;
   }
 
   // ---- Schur work units: a run of <= 32 consecutive free landmarks with the same W pose list

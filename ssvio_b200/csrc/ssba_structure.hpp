@@ -49,6 +49,10 @@ struct Structure {
   std::vector<int32_t> pair_vertex;   // pose row
   std::vector<int32_t> pair_q;        // -1: pose fixed (pairs with a free pose first, by q)
   std::vector<int32_t> pair_edge_ptr; // n_pairs + 1
+  std::vector<int32_t> pair_slot;     // n_pairs: the slot of the pair
+  std::vector<int32_t> lchunk_slot;   // n_lchunks + 1: CTAs of k_linearize / k_update = runs of whole
+                                      // landmarks with <= 128 pairs (a larger landmark is alone)
+  int n_lchunks = 0;
   std::vector<double> e_uv;           // sorted copies
   std::vector<uint8_t> e_cam;
   std::vector<int32_t> e_orig;        // index in the caller's addEdge order

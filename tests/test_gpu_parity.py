@@ -253,3 +253,23 @@ def test_g2o_shim_drop_in(BA):
         act = ~(g.pose_fixed[g.pose_idx].astype(bool) & g.point_fixed[g.point_idx].astype(bool))
         np.testing.assert_allclose(r["edge_chi2"][act], (z["analytic_errors"] ** 2).sum(1)[act], rtol=1e-6, atol=1e-6)
         assert rel(r["edge_chi2"][act].sum(), rep.chi2_plain) < 1e-12
+
+
+def test_outlier_rounds_like_backend(BA, ref_oracle):
+    """The <= 5 rounds of initializeOptimization(); optimize(10) with the inlier-ratio rule
+    (backend.cpp:175-203): many outliers keep the ratio under 0.7 so every round runs; few
+    outliers stop after the first."""
+    for frac, want_rounds in ((0.4, 5), (0.02, 1)):
+        g = synth.make_config("small", outlier_frac=frac, seed=3)
+        a = ref_oracle.optimize(g, iters=10, jacobian="numeric", trace=False, rounds=5, outlier_threshold=5.891)
+        with BA() as opt:
+            opt.set_graph(g)
+            rounds, n_out, n_in, rep = opt.optimize_rounds(5, 10, 5.891, 0.7)
+            poses = opt.poses()
+        assert rounds == a["rounds"] == want_rounds
+        assert n_out + n_in == g.n_edges
+        assert abs(n_out - a["outliers"]) <= max(2, 0.002 * g.n_edges)   # edges sitting on the threshold may flip
+        assert rel(rep.chi2_robust, a["report"].chi2_robust) < 5e-6
+        # no pose is fixed (backend.cpp:93-103): after 50 iterations lambda is tiny and the
+        # estimates may drift along the gauge freedom, so only chi2 is comparable here
+        assert np.isfinite(poses).all()
