@@ -158,7 +158,7 @@ ssba_status enqueue_slot(ssba_handle *h, bool first) {
   {
     PhaseTimer t(h, 0);
     launch_linearize(P, st);
-    h->prof.kernel_launches += 2;
+    h->prof.kernel_launches += 1;
   }
   if (first) {
     if (multi) {
@@ -430,8 +430,8 @@ ssba_status ssba_initialize(ssba_handle *h) {
   STAT(s.pair_vertex, pair_vertex); STAT(s.pair_q, pair_q); STAT(s.pair_edge_ptr, pair_edge_ptr);
   STAT(s.pair_slot, pair_slot); STAT(s.lchunk_slot, lchunk_slot);
   STAT(s.e_uv, e_uv); STAT(s.e_info, e_info); STAT(s.e_delta, e_delta); STAT(s.e_cam, e_cam); STAT(s.e_orig, e_orig);
-  STAT(s.chunk_q, chunk_q); STAT(s.chunk_vertex, chunk_vertex); STAT(s.chunk_edge_ptr, chunk_edge_ptr);
-  STAT(s.q_chunk_ptr, q_chunk_ptr); STAT(s.pm_point, pm_point); STAT(s.pm_src, pm_src);
+  STAT(s.lchunk_lp_ptr, lchunk_lp_ptr); STAT(s.lp_pair_ptr, lp_pair_ptr); STAT(s.lp_pair, lp_pair);
+  STAT(s.q_part_ptr, q_part_ptr); STAT(s.q_part, q_part);
   STAT(s.pose_of_q, pose_of_q);
   STAT(h->owner_mask, owner_mask);
   STAT(s.unit_slot, unit_slot); STAT(s.unit_n, unit_n); STAT(s.unit_k, unit_k); STAT(s.unit_c0, unit_c0);
@@ -452,7 +452,7 @@ ssba_status ssba_initialize(ssba_handle *h) {
   DYN(pose[0], 7 * g.n_poses, double); DYN(pose[1], 7 * g.n_poses, double);
   DYN(point[0], 3 * (size_t)g.n_points, double); DYN(point[1], 3 * (size_t)g.n_points, double);
   DYN(W, 18 * (size_t)s.n_pairs, double); DYN(Hll, 6 * (size_t)s.n_slots, double); DYN(bl, 3 * (size_t)s.n_slots, double);
-  DYN(Dinv, 6 * (size_t)s.n_slots, double); DYN(hpp_part, 27 * (size_t)s.n_chunks, double);
+  DYN(Dinv, 6 * (size_t)s.n_slots, double); DYN(hpp_part, 27 * (size_t)s.n_hpp_parts, double);
   DYN(sys, P.sys_doubles, double); DYN(xp, 6 * (size_t)s.n_fp, double); DYN(diag_buf, 6 * (size_t)s.n_fp, double);
   DYN(chi_cur_part, nblk, double); DYN(maxdiag_part, nblk, double); DYN(chi_new_part, nblk, double); DYN(scale_part, nblk, double);
   DYN(scal, 8, double); DYN(chi_out, 8, double);
@@ -475,7 +475,11 @@ ssba_status ssba_initialize(ssba_handle *h) {
     h->h_stage_bytes = want;
   }
   auto t_c = Clock::now();
-  for (auto &it : items) { std::memcpy(h->h_stage + it.off, it.src, it.bytes); *it.dst = h->d_arena + it.off; }
+  {
+    std::vector<CopyJob> jobs;
+    for (auto &it : items) { jobs.push_back({h->h_stage + it.off, it.src, it.bytes}); *it.dst = h->d_arena + it.off; }
+    parallel_copy(jobs);
+  }
   auto t_d = Clock::now();
   for (auto &it : work) *it.dst = h->d_arena + it.off;
   h->device_bytes = total;
@@ -486,7 +490,7 @@ ssba_status ssba_initialize(ssba_handle *h) {
   P.jacobian_mode = h->opt.jacobian_mode;
   P.delta_all = g.delta_all;
   P.n_poses = g.n_poses; P.n_points = g.n_points; P.n_fp = s.n_fp; P.n_slots = s.n_slots; P.n_pairs = s.n_pairs;
-  P.n_edges = s.n_edges; P.n_blocks = s.n_blocks; P.n_chunks = s.n_chunks; P.n_levels = s.n_levels;
+  P.n_edges = s.n_edges; P.n_blocks = s.n_blocks; P.n_hpp_parts = s.n_hpp_parts; P.n_levels = s.n_levels;
   P.n_edges_total = g.n_edges;
   P.prog_max_seg = s.prog_max_seg;
   P.n_segments = s.n_segments;

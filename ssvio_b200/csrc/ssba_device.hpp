@@ -43,7 +43,7 @@ struct DeviceProblem {
   int jacobian_mode;
   double delta_all;
   // sizes
-  int n_poses, n_points, n_fp, n_slots, n_pairs, n_edges, n_blocks, n_chunks, n_levels;
+  int n_poses, n_points, n_fp, n_slots, n_pairs, n_edges, n_blocks, n_hpp_parts, n_levels;
   int n_lin_blocks, n_upd_blocks;  // grids of k_linearize / k_update = lengths of their partial-sum arrays
   int n_fin_blocks;                // grid of the thread-per-landmark read-out kernel
   // estimates: two buffers each (current / trial), selected by Control::cur
@@ -57,8 +57,9 @@ struct DeviceProblem {
   const double *e_uv, *e_info, *e_delta;   // e_info / e_delta may be null
   const uint8_t *e_cam;
   const int32_t *e_orig;
-  // pose-major copy
-  const int32_t *chunk_q, *chunk_vertex, *chunk_edge_ptr, *q_chunk_ptr, *pm_point, *pm_src;
+  // Hpp partials of the linearize CTAs
+  const int32_t *lchunk_lp_ptr, *lp_pair_ptr, *q_part_ptr, *q_part;
+  const uint8_t *lp_pair;
   const int32_t *pose_of_q;
   const int32_t *unit_slot, *unit_n, *unit_k, *unit_c0;  // Schur work units
   int n_units;
@@ -71,7 +72,7 @@ struct DeviceProblem {
   double *Hll;        // n_slots x 6 (xx xy xz yy yz zz)
   double *bl;         // n_slots x 3
   double *Dinv;       // n_slots x 6
-  double *hpp_part;   // n_chunks x 27 (b[6], upper-tri H[21])
+  double *hpp_part;   // n_hpp_parts x 27 (b[6], upper-tri H[21])
   double *sys;        // [ L: n_blocks x 36 | bschur: n_fp x 6 | bp: n_fp x 6 ] — the all-reduced buffer
   double *xp;         // n_fp x 6
   double *diag_buf;   // n_fp x 6 Hpp diagonals (lambda init, summed over ranks)

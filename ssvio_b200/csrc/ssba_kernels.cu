@@ -18,7 +18,6 @@ namespace ssba {
 namespace {
 
 constexpr int kLinThreads = 128;
-constexpr int kHppThreads = 128;
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -103,14 +102,19 @@ struct PairLin {
   double W[18], H[6], b[3], chi;
 };
 
+// `hp` (27 doubles, the caller's own row of shared memory or a global partial) receives the pose
+// side: b_p[6], then the upper triangle of J_xi^T (rho' Omega) J_xi [21]
 template <int kMode>
 __device__ __forceinline__ void linearize_pair(const DeviceProblem &P, int a, bool lfree, const double *pose,
-                                               const double *p, PairLin &o) {
+                                               const double *p, PairLin &o, double *hp) {
   const int kv = P.pair_vertex[a];
-  const bool wpair = lfree && P.pair_q[a] >= 0;
+  const bool pfree = P.pair_q[a] >= 0;
+  const bool wpair = lfree && pfree;
   double T[7];
 #pragma unroll
   for (int i = 0; i < 7; ++i) T[i] = pose[7 * kv + i];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) hp[i] = 0.0;
 #pragma unroll
   for (int i = 0; i < 18; ++i) o.W[i] = 0.0;
 #pragma unroll
@@ -124,6 +128,23 @@ __device__ __forceinline__ void linearize_pair(const DeviceProblem &P, int a, bo
     linearize_edge<kMode>(P, P.e_cam[e], T, p, P.e_uv[2 * e], P.e_uv[2 * e + 1], t, Jx, Jp);
     load_edge_weighting(P, P.e_info, P.e_delta, e, t);
     o.chi += t.rho0;
+    if (pfree) {
+      // pose side (base_binary_edge.hpp:104-110): b_i += J_xi^T (-rho' Omega e), Hpp_ii += J_xi^T (rho' Omega) J_xi
+      double A0[6], A1[6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        A0[r] = t.w * (t.o00 * Jx[r] + t.o01 * Jx[6 + r]);
+        A1[r] = t.w * (t.o01 * Jx[r] + t.o11 * Jx[6 + r]);
+      }
+      const double r0 = -t.w * t.we0, r1 = -t.w * t.we1;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) hp[r] += Jx[r] * r0 + Jx[6 + r] * r1;
+      int k = 6;
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int cc = r; cc < 6; ++cc) hp[k++] += Jx[r] * A0[cc] + Jx[6 + r] * A1[cc];
+    }
     if (lfree) {
       // rows of (rho' Omega) J_p
       double A0[3], A1[3];
@@ -157,15 +178,17 @@ __device__ __forceinline__ void linearize_pair(const DeviceProblem &P, int a, bo
 }
 
 template <int kMode>
-__global__ void __launch_bounds__(kLinThreads) k_linearize(const DeviceProblem P) {
+__global__ void __launch_bounds__(kLinThreads, 3) k_linearize(const DeviceProblem P) {
   const Control *ctl = P.ctl;
   if (ctl->done || !ctl->need_linearize) return;
   __shared__ double red[kLinThreads / 32];
   __shared__ double s_part[kLinThreads][9];
+  __shared__ double s_hp[kLinThreads][27];
   const int cur = ctl->cur;
   const double *__restrict__ pose = P.pose[cur];
   const double *__restrict__ point = P.point[cur];
   const int s0 = P.lchunk_slot[blockIdx.x], s1 = P.lchunk_slot[blockIdx.x + 1];
+  const int lp0 = P.lchunk_lp_ptr[blockIdx.x], lp1 = P.lchunk_lp_ptr[blockIdx.x + 1];
   const int a0 = P.slot_pair_ptr[s0], a1 = P.slot_pair_ptr[s1];
   const int tid = threadIdx.x;
   double chi = 0.0, mx = 0.0;
@@ -176,7 +199,7 @@ __global__ void __launch_bounds__(kLinThreads) k_linearize(const DeviceProblem P
       const int pv = P.slot_vertex[sl];
       const double p[3] = {point[3 * pv], point[3 * pv + 1], point[3 * pv + 2]};
       PairLin o;
-      linearize_pair<kMode>(P, a, P.slot_free[sl] != 0, pose, p, o);
+      linearize_pair<kMode>(P, a, P.slot_free[sl] != 0, pose, p, o, s_hp[tid]);
       chi = o.chi;
 #pragma unroll
       for (int i = 0; i < 6; ++i) s_part[tid][i] = o.H[i];
@@ -184,6 +207,13 @@ __global__ void __launch_bounds__(kLinThreads) k_linearize(const DeviceProblem P
       for (int i = 0; i < 3; ++i) s_part[tid][6 + i] = o.b[i];
     }
     __syncthreads();
+    // pose side: fold the pairs of every distinct pose of this chunk, in pair order
+    for (int w = tid; w < 27 * (lp1 - lp0); w += kLinThreads) {
+      const int lp = lp0 + w / 27, k = w % 27;
+      double acc = 0.0;
+      for (int i = P.lp_pair_ptr[lp]; i < P.lp_pair_ptr[lp + 1]; ++i) acc += s_hp[P.lp_pair[i]][k];
+      P.hpp_part[27 * (size_t)lp + k] = acc;
+    }
     const int sl = s0 + tid;
     if (sl < s1 && P.slot_free[sl]) {
       double acc[9];
@@ -208,9 +238,13 @@ __global__ void __launch_bounds__(kLinThreads) k_linearize(const DeviceProblem P
     double acc[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) acc[i] = 0.0;
+    // every pair of one landmark is on a different pose: one Hpp partial per free-pose pair, in
+    // pair order (the partial index advances with the free-pose pairs before this one)
     for (int a = a0 + tid; a < a1; a += kLinThreads) {
       PairLin o;
-      linearize_pair<kMode>(P, a, lfree, pose, p, o);
+      // free-pose pairs come first inside a landmark, so the rank of one is simply a - a0
+      linearize_pair<kMode>(P, a, lfree, pose, p, o,
+                            P.pair_q[a] >= 0 ? P.hpp_part + 27 * (size_t)(lp0 + (a - a0)) : s_hp[tid]);
       chi += o.chi;
 #pragma unroll
       for (int i = 0; i < 6; ++i) acc[i] += o.H[i];
@@ -232,69 +266,11 @@ __global__ void __launch_bounds__(kLinThreads) k_linearize(const DeviceProblem P
   if (tid == 0) { P.chi_cur_part[blockIdx.x] = s_; P.maxdiag_part[blockIdx.x] = m; }
 }
 
-// ---------------------------------------------------------------------------------------------
-// k_hpp — pose side of buildSystem: Hpp_ii += J_xi^T (rho' Omega) J_xi, b_i += J_xi^T(-rho' Omega e)
-// (base_binary_edge.hpp:104-110).  Pose-major pass, one CTA per chunk of <= 256 edges of ONE pose:
-// 27 register accumulators per thread, deterministic block reduction, no atomics.
-template <int kMode>
-__global__ void __launch_bounds__(kHppThreads) k_hpp(const DeviceProblem P) {
-  const Control *ctl = P.ctl;
-  if (ctl->done || !ctl->need_linearize) return;
-  __shared__ double red[27][kHppThreads / 32];
-  const int cur = ctl->cur;
-  const double *__restrict__ pose = P.pose[cur];
-  const double *__restrict__ point = P.point[cur];
-  const int c = blockIdx.x;
-  const int kv = P.chunk_vertex[c];
-  double T[7];
-#pragma unroll
-  for (int i = 0; i < 7; ++i) T[i] = pose[7 * kv + i];
-  double acc[27];
-#pragma unroll
-  for (int i = 0; i < 27; ++i) acc[i] = 0.0;
-  const int e1 = P.chunk_edge_ptr[c + 1];
-  for (int d = P.chunk_edge_ptr[c] + threadIdx.x; d < e1; d += kHppThreads) {
-    const int pv = P.pm_point[d];
-    const int e = P.pm_src[d];  // the edge in the landmark-major stream
-    const double p[3] = {point[3 * pv], point[3 * pv + 1], point[3 * pv + 2]};
-    EdgeTerms t;
-    double Jx[12], Jp[6];
-    linearize_edge<kMode>(P, P.e_cam[e], T, p, P.e_uv[2 * e], P.e_uv[2 * e + 1], t, Jx, Jp);
-    load_edge_weighting(P, P.e_info, P.e_delta, e, t);
-    double A0[6], A1[6];
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      A0[r] = t.w * (t.o00 * Jx[r] + t.o01 * Jx[6 + r]);
-      A1[r] = t.w * (t.o01 * Jx[r] + t.o11 * Jx[6 + r]);
-    }
-    const double r0 = -t.w * t.we0, r1 = -t.w * t.we1;
-#pragma unroll
-    for (int r = 0; r < 6; ++r) acc[r] += Jx[r] * r0 + Jx[6 + r] * r1;
-    int k = 6;
-#pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-      for (int cc = r; cc < 6; ++cc) acc[k++] += Jx[r] * A0[cc] + Jx[6 + r] * A1[cc];
-  }
-#pragma unroll
-  for (int i = 0; i < 27; ++i) {
-    const double v = warp_sum(acc[i]);
-    if ((threadIdx.x & 31) == 0) red[i][threadIdx.x >> 5] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < 27) {
-    double s = 0.0;
-#pragma unroll
-    for (int w = 0; w < kHppThreads / 32; ++w) s += red[threadIdx.x][w];
-    P.hpp_part[27 * (size_t)c + threadIdx.x] = s;
-  }
-}
-
-// Hpp / b_p entry k (0..5 = b, 6..26 = upper triangle) of pose q: the chunk partials of the
-// pose folded in chunk order (deterministic)
+// Hpp / b_p entry k (0..5 = b, 6..26 = upper triangle) of pose q: the partials the linearize
+// CTAs wrote for the pose, folded in chunk order (deterministic)
 __device__ __forceinline__ double hpp_sum(const DeviceProblem &P, int q, int k) {
   double s = 0.0;
-  for (int c = P.q_chunk_ptr[q]; c < P.q_chunk_ptr[q + 1]; ++c) s += P.hpp_part[27 * (size_t)c + k];
+  for (int i = P.q_part_ptr[q]; i < P.q_part_ptr[q + 1]; ++i) s += P.hpp_part[27 * (size_t)P.q_part[i] + k];
   return s;
 }
 // upper-triangle offset of diagonal entry d of the 6x6 block: 6, 12, 17, 21, 24, 26
@@ -1074,7 +1050,7 @@ inline int div_up(long long a, int b) { return (int)((a + b - 1) / b); }
 
 // ------------------------------------------------------------------------------------------------
 
-int kernels_per_linearize() { return 2; }
+int kernels_per_linearize() { return 1; }
 
 #ifdef SSBA_SOLVER_TRACE
 extern "C" int ssba_debug_solver_trace(long long *out, int n) {
@@ -1084,13 +1060,9 @@ extern "C" int ssba_debug_solver_trace(long long *out, int n) {
 #endif
 
 void launch_linearize(const DeviceProblem &P, cudaStream_t st) {
-  if (P.jacobian_mode == SSBA_JACOBIAN_NUMERIC) {
-    if (P.n_lin_blocks > 0) k_linearize<SSBA_JACOBIAN_NUMERIC><<<P.n_lin_blocks, kLinThreads, 0, st>>>(P);
-    if (P.n_chunks > 0) k_hpp<SSBA_JACOBIAN_NUMERIC><<<P.n_chunks, kHppThreads, 0, st>>>(P);
-  } else {
-    if (P.n_lin_blocks > 0) k_linearize<SSBA_JACOBIAN_ANALYTIC><<<P.n_lin_blocks, kLinThreads, 0, st>>>(P);
-    if (P.n_chunks > 0) k_hpp<SSBA_JACOBIAN_ANALYTIC><<<P.n_chunks, kHppThreads, 0, st>>>(P);
-  }
+  if (P.n_lin_blocks <= 0) return;
+  if (P.jacobian_mode == SSBA_JACOBIAN_NUMERIC) k_linearize<SSBA_JACOBIAN_NUMERIC><<<P.n_lin_blocks, kLinThreads, 0, st>>>(P);
+  else k_linearize<SSBA_JACOBIAN_ANALYTIC><<<P.n_lin_blocks, kLinThreads, 0, st>>>(P);
 }
 
 void launch_hpp_diag(const DeviceProblem &P, cudaStream_t st) {

@@ -3,8 +3,10 @@
 #include "ssba_solver_layout.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <condition_variable>
 #include <cstdlib>
@@ -17,7 +19,6 @@ namespace ssba {
 
 namespace {
 
-constexpr int kHppChunk = 256;  // edges per pose-major chunk (one CTA each)
 constexpr int kMaxLevelCols = kSolveMaxCols;  // ssba_solver_layout.hpp
 constexpr int kSchurRunPairs = 160; // = kSchurRunPairs of k_schur
 constexpr int kLinPairs = 128;      // = kLinThreads of k_linearize / k_update
@@ -433,7 +434,7 @@ class HostPool {
   HostPool() {
     int n = (int)std::thread::hardware_concurrency();
     if (const char *e = std::getenv("SSBA_HOST_THREADS")) n = std::atoi(e);
-    n_ = std::max(1, std::min(n, 8));
+    n_ = std::max(1, std::min(n, 4));  // measured on the B200 hosts: the passes are memory-bound, 4 threads is the knee
     for (int t = 1; t < n_; ++t) std::thread([this, t] { worker(t); }).detach();
   }
   void worker(int t) {
@@ -467,8 +468,42 @@ inline void split_range(int t, int T, int N, int &b, int &e) {
 }
 }  // namespace
 
+namespace {
+// Clears a Structure for the next build but keeps the capacity of its arrays: ssba_initialize
+// runs once per optimised window and re-allocating megabytes every time costs page faults.
+template <class V> void clr(V &v) { v.clear(); }
+void reset_keep_capacity(Structure &s) {
+  clr(s.q_of_pose); clr(s.pose_of_q); clr(s.point_active);
+  clr(s.slot_vertex); clr(s.slot_free); clr(s.slot_pair_ptr); clr(s.pair_vertex); clr(s.pair_q);
+  clr(s.pair_edge_ptr); clr(s.pair_slot); clr(s.lchunk_slot); clr(s.lchunk_lp_ptr); clr(s.lp_pair_ptr);
+  clr(s.lp_pair); clr(s.q_part_ptr); clr(s.q_part); clr(s.e_uv); clr(s.e_cam); clr(s.e_orig); clr(s.e_info);
+  clr(s.e_delta); clr(s.slot_combo_ptr); clr(s.combo_blk); clr(s.unit_slot); clr(s.unit_n); clr(s.unit_k);
+  clr(s.unit_c0); clr(s.col_ptr); clr(s.blk_row); clr(s.blk_col); clr(s.ltask_ptr); clr(s.task_dst);
+  clr(s.task_pos); clr(s.task_pair_ptr); clr(s.pair_a); clr(s.pair_b); clr(s.prog); clr(s.prog_ptr);
+  clr(s.row_ptr); clr(s.row_blk); clr(s.row_col); clr(s.level_ptr); clr(s.level_col);
+  s.n_fp = s.n_fl_global = s.n_active_edges_global = 0;
+  s.n_slots = s.n_pairs = s.n_edges = s.n_fl = 0;
+  s.n_lchunks = s.n_hpp_parts = s.n_units = 0;
+  s.n_blocks = s.n_schur_blocks = s.n_tasks = s.n_levels = s.n_segments = 0;
+  s.prog_max_seg = s.solver_slots = s.solver_cached_blocks = s.solver_rounds = 0;
+  s.est_solver_cycles = 0.0;
+  s.n_edges_total = 0;
+}
+struct SectionTimer {  // SSBA_TIMING=1: wall time of the sections of build_structure on stderr
+  bool on = std::getenv("SSBA_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void mark(const char *name) {
+    if (!on) return;
+    const auto n = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[ssba]   %-26s %.3f ms\n", name, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+}  // namespace
+
 bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std::string &err) {
-  s = Structure();
+  SectionTimer tm;
+  reset_keep_capacity(s);
   const int NK = g.n_poses, NP = g.n_points, NE = g.n_edges;
   s.n_edges_total = NE;
   if (!g.have_cams) { err = "ssba_set_cameras was not called"; return false; }
@@ -498,6 +533,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   s.n_active_edges_global = n_active;
   s.point_active = point_active;
 
+  tm.mark("validate + active sets");
   // ---- index mapping (sparse_optimizer.cpp:168-192): free poses in id order, then landmarks
   std::vector<int32_t> fp_of_pose(NK, -1), free_pose_rows;
   for (int i = 0; i < NK; ++i)
@@ -518,6 +554,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
       if (edge_active[e]) pt_edges[fill[ge_point[e]]++] = e;
   }
 
+  tm.mark("index map + edges by landmark");
   // ---- co-visibility of free poses through free landmarks = pattern of the Schur complement
   // (block_solver.hpp:224-249): per-thread bitmaps when small enough, else key lists
   const bool use_bitmap = n <= 4096;
@@ -568,6 +605,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     for (uint64_t k : keys) adj[(int)(k / n)].push_back((int)(k % n));
   }
 
+  tm.mark("co-visibility");
   // ---- elimination order and symbolic factorisation over q: natural order vs nested
   // dissection, whichever the cost model of the level-scheduled device solver prefers
   {
@@ -605,6 +643,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   };
   const int32_t *__restrict__ qmap = s.q_of_pose.data();
 
+  tm.mark("order + symbolic + program");
   // ---- per landmark: its edges sorted by pose (free poses first by q, then fixed poses by row;
   // addEdge order inside a pose), in place in pt_edges; a hash of its free-pose list, its first
   // pose, its number of (pose, landmark) pairs and of W pairs.  For every active landmark,
@@ -652,6 +691,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     }
   });
 
+  tm.mark("per-landmark sort + hash");
   // ---- landmark order: landmarks seen by the same set of free poses are made adjacent (bucket
   // by first pose, then by the hash of the pose list), so that runs of landmarks accumulate into
   // the same Schur blocks; the shard of this rank = a contiguous range of that order, balanced
@@ -682,6 +722,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
       seen += point_deg[j];
     }
   }
+  tm.mark("landmark order + shard");
   s.n_slots = (int)slots.size();
   s.slot_vertex.assign(slots.begin(), slots.end());
   s.slot_free.resize(s.n_slots);
@@ -724,6 +765,15 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
       int k_prev = -1, prev_combo0 = 0;
       for (int sl = s0; sl < s1; ++sl) {
         const int j = slots[sl];
+        if (sl + 6 < s1) {  // the class order visits landmarks far apart in the caller's arrays
+          const int e_next = pe[pt_ptr[slots[sl + 6]]];
+          __builtin_prefetch(ge_uv + 2 * (size_t)e_next);
+          __builtin_prefetch(ge_uv + 2 * (size_t)e_next + 8);
+          __builtin_prefetch(ge_uv + 2 * (size_t)e_next + 16);
+          __builtin_prefetch(ge_pose + e_next);
+          __builtin_prefetch(ge_cam + e_next);
+        }
+        if (sl + 12 < s1) __builtin_prefetch(pe + pt_ptr[slots[sl + 12]]);
         const bool lfree = !lfix[j];
         size_t ne = (size_t)slot_edge_ptr[sl], npair = (size_t)s.slot_pair_ptr[sl];
         const int kk = lm_k[j];
@@ -770,6 +820,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     for (int v : t_err) if (v) { err = "internal: Schur block missing from the factor pattern"; return false; }
   }
 
+  tm.mark("slots / pairs / edges fill");
   // ---- CTAs of the per-pair kernels: runs of whole landmarks with <= kLinPairs pairs
   {
     s.lchunk_slot.assign(1, 0);
@@ -810,51 +861,78 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     s.n_units = (int)s.unit_slot.size();
   }
 
-  // ---- pose-major view of the edges with a free pose (for the Hpp pass): an index into the
-  // landmark-major edge stream + the point row, cut into chunks of <= kHppChunk edges of one pose.
-  // Deterministic order (pose, then slot order) whatever the number of threads.
+  tm.mark("chunks + schur units");
+  // ---- Hpp partials of the linearize CTAs: per chunk its distinct free poses ("local poses")
+  // with the list of the chunk's pairs on each, and per pose the list of its partials.
+  // Two parallel passes over the chunks (count, then fill at prefix offsets).
   {
-    std::vector<std::vector<int32_t>> t_cnt(T, std::vector<int32_t>(n + 1, 0));
-    pool.run(T, [&](int t, int TT) {
-      int a0, a1; split_range(t, TT, s.n_slots, a0, a1);
-      std::vector<int32_t> &cnt = t_cnt[t];
-      for (int a = s.slot_pair_ptr[a0]; a < s.slot_pair_ptr[a1]; ++a)
-        if (s.pair_q[a] >= 0) cnt[s.pair_q[a]] += s.pair_edge_ptr[a + 1] - s.pair_edge_ptr[a];
-    });
-    std::vector<int32_t> q_ptr(n + 1, 0);
-    for (int q = 0; q < n; ++q) {
-      int acc = q_ptr[q];
-      for (int t = 0; t < T; ++t) { const int c = t_cnt[t][q]; t_cnt[t][q] = acc; acc += c; }
-      q_ptr[q + 1] = acc;
-    }
-    s.n_pm_edges = q_ptr[n];
-    s.pm_src.resize(s.n_pm_edges); s.pm_point.resize(s.n_pm_edges);
-    pool.run(T, [&](int t, int TT) {
-      int a0, a1; split_range(t, TT, s.n_slots, a0, a1);
-      std::vector<int32_t> &fill = t_cnt[t];
-      for (int sl = a0; sl < a1; ++sl)
-        for (int a = s.slot_pair_ptr[sl]; a < s.slot_pair_ptr[sl + 1]; ++a) {
+    const int NC = s.n_lchunks;
+    std::vector<int32_t> nlp(NC + 1, 0), nlist(NC + 1, 0);
+    auto chunk_pass = [&](int t, int TT, bool fill, std::vector<int32_t> *lp_q) {
+      int c0, c1; split_range(t, TT, NC, c0, c1);
+      std::vector<int32_t> stamp(n, -1), local(n, 0), first_seen;
+      std::vector<std::vector<uint8_t>> lists;
+      for (int c = c0; c < c1; ++c) {
+        const int a0 = s.slot_pair_ptr[s.lchunk_slot[c]], a1 = s.slot_pair_ptr[s.lchunk_slot[c + 1]];
+        const bool small = a1 - a0 <= kLinPairs;
+        first_seen.clear();
+        if (fill) { for (auto &l : lists) l.clear(); }
+        int nl = 0, npairs_free = 0;
+        for (int a = a0; a < a1; ++a) {
           const int q = s.pair_q[a];
           if (q < 0) continue;
-          for (int e = s.pair_edge_ptr[a]; e < s.pair_edge_ptr[a + 1]; ++e) {
-            const int d = fill[q]++;
-            s.pm_src[d] = e; s.pm_point[d] = s.slot_vertex[sl];
+          ++npairs_free;
+          if (!small) { if (fill) (*lp_q)[nlp[c] + nl] = q; ++nl; continue; }  // big landmark: one partial per pair
+          if (stamp[q] != c) {
+            stamp[q] = c; local[q] = nl++;
+            if (fill) { if ((int)lists.size() < nl) lists.emplace_back(); (*lp_q)[nlp[c] + local[q]] = q; }
+          }
+          if (fill) lists[local[q]].push_back((uint8_t)(a - a0));
+        }
+        if (!fill) { nlp[c + 1] = nl; nlist[c + 1] = small ? npairs_free : 0; }
+        else {
+          int off = nlist[c];
+          for (int i = 0; i < nl; ++i) {
+            if (small) { std::copy(lists[i].begin(), lists[i].end(), s.lp_pair.begin() + off); off += (int)lists[i].size(); }
+            s.lp_pair_ptr[nlp[c] + i + 1] = off;
           }
         }
-    });
-    s.q_chunk_ptr.assign(n + 1, 0);
-    s.chunk_edge_ptr.push_back(0);
-    for (int q = 0; q < n; ++q) {
-      for (int e0 = q_ptr[q]; e0 < q_ptr[q + 1]; e0 += kHppChunk) {
-        s.chunk_q.push_back(q);
-        s.chunk_vertex.push_back(s.pose_of_q[q]);
-        s.chunk_edge_ptr.push_back(std::min(e0 + kHppChunk, q_ptr[q + 1]));
+        // stamps are keyed by chunk id, so they need no reset between chunks
       }
-      s.q_chunk_ptr[q + 1] = (int32_t)s.chunk_q.size();
-    }
-    s.n_chunks = (int)s.chunk_q.size();
+    };
+    pool.run(T, [&](int t, int TT) { chunk_pass(t, TT, false, nullptr); });
+    for (int c = 0; c < NC; ++c) { nlp[c + 1] += nlp[c]; nlist[c + 1] += nlist[c]; }
+    s.n_hpp_parts = nlp[NC];
+    s.lchunk_lp_ptr.assign(nlp.begin(), nlp.end());
+    s.lp_pair.resize(nlist[NC]);
+    s.lp_pair_ptr.assign(s.n_hpp_parts + 1, 0);
+    std::vector<int32_t> lp_q(s.n_hpp_parts);
+    pool.run(T, [&](int t, int TT) { chunk_pass(t, TT, true, &lp_q); });
+    s.q_part_ptr.assign(n + 1, 0);
+    for (int q : lp_q) ++s.q_part_ptr[q + 1];
+    for (int q = 0; q < n; ++q) s.q_part_ptr[q + 1] += s.q_part_ptr[q];
+    s.q_part.resize(lp_q.size());
+    std::vector<int32_t> fill(s.q_part_ptr.begin(), s.q_part_ptr.end() - 1);
+    for (size_t i = 0; i < lp_q.size(); ++i) s.q_part[fill[lp_q[i]]++] = (int32_t)i;
   }
+  tm.mark("hpp partial lists");
   return true;
+}
+
+void parallel_copy(const std::vector<CopyJob> &jobs) {
+  size_t total = 0;
+  for (auto &j : jobs) total += j.bytes;
+  HostPool &pool = HostPool::get();
+  const int T = total >= (1u << 20) ? pool.size() : 1;
+  // cut every job into 256 KiB pieces, deal the pieces round-robin
+  struct Piece { char *d; const char *s; size_t n; };
+  std::vector<Piece> pieces;
+  for (auto &j : jobs)
+    for (size_t o = 0; o < j.bytes; o += (256u << 10))
+      pieces.push_back({(char *)j.dst + o, (const char *)j.src + o, std::min<size_t>(256u << 10, j.bytes - o)});
+  pool.run(T, [&](int t, int TT) {
+    for (size_t i = t; i < pieces.size(); i += TT) std::memcpy(pieces[i].d, pieces[i].s, pieces[i].n);
+  });
 }
 
 bool plan_shards(const HostGraph &g, int world, std::vector<int32_t> &owner, std::string &err) {

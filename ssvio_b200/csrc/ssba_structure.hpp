@@ -53,6 +53,14 @@ struct Structure {
   std::vector<int32_t> lchunk_slot;   // n_lchunks + 1: CTAs of k_linearize / k_update = runs of whole
                                       // landmarks with <= 128 pairs (a larger landmark is alone)
   int n_lchunks = 0;
+  // Hpp partials: every linearize CTA folds the pose-side quadratic forms of its pairs per
+  // distinct free pose ("local pose") and writes one 27-vector per (chunk, local pose)
+  int n_hpp_parts = 0;
+  std::vector<int32_t> lchunk_lp_ptr;  // n_lchunks + 1 -> first partial (= local pose) of the chunk
+  std::vector<int32_t> lp_pair_ptr;    // n_hpp_parts + 1 -> lp_pair
+  std::vector<uint8_t> lp_pair;        // pair index inside the chunk (chunks with <= 128 pairs)
+  std::vector<int32_t> q_part_ptr;     // n_fp + 1 -> q_part: the partials of pose q, in chunk order
+  std::vector<int32_t> q_part;
   std::vector<double> e_uv;           // sorted copies
   std::vector<uint8_t> e_cam;
   std::vector<int32_t> e_orig;        // index in the caller's addEdge order
@@ -64,12 +72,6 @@ struct Structure {
   // unit_k poses, block pairs [unit_c0, +32) of its k(k+1)/2
   int n_units = 0;
   std::vector<int32_t> unit_slot, unit_n, unit_k, unit_c0;
-  // ---- pose-major copy of the edges with a free pose, cut into chunks of one pose each
-  int n_chunks = 0, n_pm_edges = 0;
-  std::vector<int32_t> chunk_q, chunk_vertex, chunk_edge_ptr; // n_chunks (+1)
-  std::vector<int32_t> q_chunk_ptr;   // n_fp + 1
-  std::vector<int32_t> pm_src;        // index into the landmark-major edge stream
-  std::vector<int32_t> pm_point;      // point row
   // ---- reduced system: lower block-CSC factor pattern (with fill) over q
   int n_blocks = 0, n_schur_blocks = 0;
   std::vector<int32_t> col_ptr;       // n_fp + 1, diagonal block first in every column
@@ -102,6 +104,10 @@ struct Structure {
 // Builds the structure for `rank` of `world`. Returns false and sets err on invalid input.
 // n_fp + n_fl_global == 0 is not an error here (caller maps it to SSBA_ERR_EMPTY).
 bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std::string &err);
+
+// memcpy of several regions on the host thread pool of the structure builder
+struct CopyJob { void *dst; const void *src; size_t bytes; };
+void parallel_copy(const std::vector<CopyJob> &jobs);
 
 // Which rank owns which landmark under the sharding rule of build_structure:
 // owner[point row] = rank, or -1 for landmarks without an active edge.

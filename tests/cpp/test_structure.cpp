@@ -81,13 +81,32 @@ static void check_case(int nk, int np, int w, unsigned seed, bool fix0, int nfix
           }
     }
     for (int e = 0; e < s.n_edges; ++e) CHECK(s.e_orig[e] >= 0 && s.e_orig[e] < g.n_edges, "e_orig range");
-    int pm = 0;
-    for (int c = 0; c < s.n_chunks; ++c) {
-      CHECK(s.chunk_edge_ptr[c + 1] > s.chunk_edge_ptr[c], "empty chunk");
-      CHECK(s.pose_of_q[s.chunk_q[c]] == s.chunk_vertex[c], "chunk vertex");
-      pm += s.chunk_edge_ptr[c + 1] - s.chunk_edge_ptr[c];
+    // Hpp partial bookkeeping: every free-pose pair is in exactly one partial of its chunk, and the
+    // partial lists of the poses cover all partials
+    {
+      long long covered = 0, free_pairs = 0;
+      for (int a = 0; a < s.n_pairs; ++a) if (s.pair_q[a] >= 0) ++free_pairs;
+      std::vector<int> seen(s.n_hpp_parts, 0);
+      for (int q = 0; q < s.n_fp; ++q)
+        for (int i = s.q_part_ptr[q]; i < s.q_part_ptr[q + 1]; ++i) ++seen[s.q_part[i]];
+      for (int v : seen) CHECK(v == 1, "partial owned by %d poses", v);
+      for (int c = 0; c < s.n_lchunks; ++c) {
+        const int a0 = s.slot_pair_ptr[s.lchunk_slot[c]], a1 = s.slot_pair_ptr[s.lchunk_slot[c + 1]];
+        if (a1 - a0 > 128) { CHECK(s.lchunk_slot[c + 1] - s.lchunk_slot[c] == 1, "big chunk with several landmarks"); for (int a = a0; a < a1; ++a) if (s.pair_q[a] >= 0) ++covered; continue; }
+        for (int lp = s.lchunk_lp_ptr[c]; lp < s.lchunk_lp_ptr[c + 1]; ++lp) {
+          int q = -2;
+          for (int i = s.lp_pair_ptr[lp]; i < s.lp_pair_ptr[lp + 1]; ++i) {
+            const int a = a0 + s.lp_pair[i];
+            CHECK(a < a1 && s.pair_q[a] >= 0, "lp_pair out of chunk");
+            if (q == -2) q = s.pair_q[a];
+            CHECK(s.pair_q[a] == q, "mixed poses in one partial");
+            ++covered;
+          }
+        }
+      }
+      CHECK(covered == free_pairs, "partials cover %lld of %lld free-pose pairs", covered, free_pairs);
     }
-    CHECK(pm == s.n_pm_edges, "chunk edges %d vs %d", pm, s.n_pm_edges);
+
   }
   CHECK(edges_seen == S[0].n_active_edges_global, "shards cover %lld of %d active edges", edges_seen, S[0].n_active_edges_global);
   CHECK(slots_free == S[0].n_fl_global, "free landmarks %lld vs %d", slots_free, S[0].n_fl_global);
