@@ -29,4 +29,12 @@ for k in range(1, nseg):
     print(f"bwd {k:3d}: {v - prev:7d}")
     prev = v
 print("tail", rel[nz] - prev)
+for label, base, sgi in (("seg 6", 3000, 6), ("seg 18", 3512, 18)):
+    start = out[1 + 3 * sgi]
+    print(label, "rounds 0..15 of the level (cycles since level start): begin | pairs done | rows->smem | chol+inv done | published | round end")
+    for rd in range(16):
+        v = out[base + 16 * rd: base + 16 * rd + 7]
+        if v[0] == 0: continue
+        f = lambda x: int(x - start) if x else -1
+        print(f"   rd {rd:2d}: {f(v[0]):6d} | {f(v[1]):6d} | {f(v[2]):6d} | {f(v[3]):6d} | {f(v[4]):6d} | {f(v[6]):6d}")
 

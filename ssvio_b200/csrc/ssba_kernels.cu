@@ -346,6 +346,7 @@ __global__ void k_prepare_system(const DeviceProblem P) {
 // lane owns ONE 6x6 block pair (a, b) and walks the run, accumulating its block in 36 registers.
 // Only the per-unit totals go to the L2-resident reduced system with fp64 atomic adds
 // (~1/32 of the per-landmark contributions).
+constexpr int kStageWarps = 4;  // warps of k_reduced_solve that issue the cp.async prefetches
 constexpr int kSchurWarps = 4;
 constexpr int kSchurRunPairs = 160;  // W blocks of one run staged in shared memory (= host kSchurRunPairs)
 
@@ -524,7 +525,7 @@ __device__ __forceinline__ void stage_wait() {
 #ifdef SSBA_SOLVER_TRACE
 __device__ long long g_solver_trace[4096];
 #define TRACE(i) do { if (threadIdx.x == 0 && (i) < 4096) g_solver_trace[(i)] = clock64(); } while (0)
-#define TRACE2(sgv, k) do { if (threadIdx.x == 0 && (sgv) == 6 && rd == warp) g_solver_trace[3000 + (k)] = clock64(); } while (0)
+#define TRACE2(sgv, k) do { if (lane == 0 && ((sgv) == 6 || (sgv) == 18) && rd < 16) g_solver_trace[3000 + ((sgv) == 18 ? 512 : 0) + 16 * rd + (k)] = clock64(); } while (0)
 #else
 #define TRACE(i) do { } while (0)
 #define TRACE2(sgv, k) do { } while (0)
@@ -569,13 +570,21 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
     const LevelSeg S(staged ? s_prog + (sg & 1) * seg_stride : P.prog + P.prog_ptr[sg]);
     // asynchronously: the next segment's program, and the initial values (Schur complement) of
     // the next level's blocks into their cache slots
-    if (staged && sg + 1 < NSEG)
-      stage_segment(s_prog + ((sg + 1) & 1) * seg_stride, P.prog + P.prog_ptr[sg + 1],
-                    P.prog_ptr[sg + 2] - P.prog_ptr[sg + 1], tid);
-    for (int i = tid; i < 18 * S.n_pf; i += kSolveThreads) {
-      const int e = i / 18, o = i - 18 * e;
-      const int slot = S.pf_slot[e];
-      if (slot >= 0) cp_async16(s_slots + 36 * slot + 2 * o, L + 36 * (size_t)S.pf_blk[e] + 2 * o);
+    // Issued by the last four warps only: the first rounds of a level (the DIAG rounds on its
+    // critical path) go to the first warps, which start at once.
+    if (warp >= NW - kStageWarps) {
+      const int st = tid - 32 * (NW - kStageWarps);
+      if (staged && sg + 1 < NSEG) {
+        const int *src = P.prog + P.prog_ptr[sg + 1];
+        int *dstp = s_prog + ((sg + 1) & 1) * seg_stride;
+        const int n_ints = P.prog_ptr[sg + 2] - P.prog_ptr[sg + 1];
+        for (int i = 4 * st; i < n_ints; i += 4 * 32 * kStageWarps) cp_async16(dstp + i, src + i);
+      }
+      for (int i = st; i < 18 * S.n_pf; i += 32 * kStageWarps) {
+        const int e = i / 18, o = i - 18 * e;
+        const int slot = S.pf_slot[e];
+        if (slot >= 0) cp_async16(s_slots + 36 * slot + 2 * o, L + 36 * (size_t)S.pf_blk[e] + 2 * o);
+      }
     }
     for (int rd = warp; rd < S.n_rounds; rd += NW) {
       const int type = S.round_type[rd];
@@ -623,37 +632,54 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
           for (int c = 0; c < 6; ++c) v[c] -= acc[c];
         }
         if (kind == 0) {
-          // DIAG: right-looking 6x6 Cholesky inside each group, row r in lane gl + r
-          double invd[6];
-          bool bad = false;
-#pragma unroll
-          for (int p = 0; p < 6; ++p) {
-            double d = __shfl_sync(0xffffffffu, v[p], gl + p);
-            if (!(d > 0.0)) { bad = true; d = 1.0; }
-            const double inv = rsqrt(d);
-            invd[p] = inv;
-            if (r >= p) v[p] *= inv;
-#pragma unroll
-            for (int c = p + 1; c < 6; ++c) {
-              const double lcp = __shfl_sync(0xffffffffu, v[p], gl + c);
-              if (r >= c) v[c] -= v[p] * lcp;
-            }
-          }
-          TRACE2(sg, 2);
-          // X = L^-1, column r in lane gl + r: forward substitution against the identity
-          double X[6];
-#pragma unroll
-          for (int q = 0; q < 6; ++q) X[q] = 0.0;
-#pragma unroll
-          for (int q = 0; q < 6; ++q) {
-            double sacc = 0.0;
-#pragma unroll
-            for (int k = 0; k < q; ++k) sacc += __shfl_sync(0xffffffffu, v[k], gl + q) * X[k];
-            X[q] = (q == r) ? invd[q] : -invd[q] * sacc;
-          }
+          // DIAG: the group's rows meet in shared memory, then the group's first lane factors the
+          // 6x6 block and inverts the triangle serially in registers (measured on B200: ~2.5x
+          // shorter than the same recurrences spread over six lanes with shuffles, whose
+          // latency sits on the critical path of every level)
           if (active) {
 #pragma unroll
-            for (int q = 0; q < 6; ++q) { linv[6 * q + r] = X[q]; D[6 * q + r] = X[q]; }
+            for (int c = 0; c < 6; ++c) linv[6 * r + c] = v[c];
+          }
+          __syncwarp();
+          TRACE2(sg, 2);
+          if (active && r == 0) {
+            double a[36], invd[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+              for (int k = 0; k <= i; ++k) a[6 * i + k] = linv[6 * i + k];
+            bool bad = false;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              double dj = a[7 * j];
+              if (!(dj > 0.0)) { bad = true; dj = 1.0; }
+              const double inv = rsqrt(dj);
+              invd[j] = inv;
+#pragma unroll
+              for (int i = j + 1; i < 6; ++i) a[6 * i + j] *= inv;
+#pragma unroll
+              for (int i = j + 1; i < 6; ++i)
+#pragma unroll
+                for (int k = j + 1; k <= i; ++k) a[6 * i + k] -= a[6 * i + j] * a[6 * k + j];
+            }
+            // X = L^-1 (lower triangular), column by column
+            double X[36];
+#pragma unroll
+            for (int i = 0; i < 36; ++i) X[i] = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+              X[7 * c] = invd[c];
+#pragma unroll
+              for (int i = c + 1; i < 6; ++i) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int k = c; k < i; ++k) sacc += a[6 * i + k] * X[6 * k + c];
+                X[6 * i + c] = -invd[i] * sacc;
+              }
+            }
+            double2 *l2 = reinterpret_cast<double2 *>(linv), *d2 = reinterpret_cast<double2 *>(D);
+#pragma unroll
+            for (int i = 0; i < 18; ++i) { const double2 t = make_double2(X[2 * i], X[2 * i + 1]); l2[i] = t; d2[i] = t; }
             if (bad) s_fail = 1;
           }
           TRACE2(sg, 3);
@@ -704,6 +730,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
         }
         if (active) xs[6 * j + r] = y;
       }
+      TRACE2(sg, 6);
     }
     TRACE(2 + 3 * sg);
     stage_wait();
@@ -719,45 +746,50 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
     const int half = lay.n_slots / 2;
     for (int sg = NSEG - 1; sg >= 1; --sg) {
       const LevelSeg S(staged ? s_prog + (sg & 1) * seg_stride : P.prog + P.prog_ptr[sg]);
-      if (staged && sg > 1)
-        stage_segment(s_prog + ((sg - 1) & 1) * seg_stride, P.prog + P.prog_ptr[sg - 1],
-                      P.prog_ptr[sg] - P.prog_ptr[sg - 1], tid);
-      {
+      if (warp >= NW - kStageWarps) {
+        const int st = tid - 32 * (NW - kStageWarps);
+        if (staged && sg > 1) {
+          const int *src = P.prog + P.prog_ptr[sg - 1];
+          int *dstp = s_prog + ((sg - 1) & 1) * seg_stride;
+          const int n_ints = P.prog_ptr[sg] - P.prog_ptr[sg - 1];
+          for (int i = 4 * st; i < n_ints; i += 4 * 32 * kStageWarps) cp_async16(dstp + i, src + i);
+        }
         const int nb = S.n_bpf < half ? S.n_bpf : half;
         double *dstb = s_slots + 36 * (size_t)(((sg - 1) & 1) * half);
-        for (int i = tid; i < 18 * nb; i += kSolveThreads) {
+        for (int i = st; i < 18 * nb; i += 32 * kStageWarps) {
           const int e = i / 18, o = i - 18 * e;
           cp_async16(dstb + 36 * e + 2 * o, L + 36 * (size_t)S.bpf_blk[e] + 2 * o);
         }
       }
       const bool cached = sg != NSEG - 1;
       const double *srcb = s_slots + 36 * (size_t)((sg & 1) * half);
-      for (int rd = warp; 5 * rd < S.n_cols; rd += NW) {
-        const int t = 5 * rd + g;
-        const bool active = g < 5 && t < S.n_cols;
-        const int tt = active ? t : 0;
-        const int j = S.col_j[tt];
-        const int b0 = S.col_b0[tt];
-        const int nb = active ? S.col_bptr[tt + 1] - S.col_bptr[tt] : 0;
-        const int *rows = S.brow + S.col_bptr[tt];
-        const int l0 = S.col_bptr[tt] + tt;  // level-local index of the diagonal block
+      // one warp per column: its sub-diagonal blocks are split over the five lane groups
+      for (int t = warp; t < S.n_cols; t += NW) {
+        const int j = S.col_j[t];
+        const int b0 = S.col_b0[t];
+        const int nb = S.col_bptr[t + 1] - S.col_bptr[t];
+        const int *rows = S.brow + S.col_bptr[t];
+        const int l0 = S.col_bptr[t] + t;  // level-local index of the diagonal block
         double acc = 0.0;
-        for (int k = 0; k < nb; ++k) {
-          const int li = l0 + 1 + k;
-          const double *B = (cached && li < half) ? srcb + 36 * li : L + 36 * (size_t)(b0 + 1 + k);
-          const double *xi = xs + 6 * rows[k];
+        if (g < 5) {
+          for (int k = g; k < nb; k += 5) {
+            const int li = l0 + 1 + k;
+            const double *B = (cached && li < half) ? srcb + 36 * li : L + 36 * (size_t)(b0 + 1 + k);
+            const double *xi = xs + 6 * rows[k];
 #pragma unroll
-          for (int c = 0; c < 6; ++c) acc += B[6 * c + r] * xi[c];
+            for (int c = 0; c < 6; ++c) acc += B[6 * c + r] * xi[c];
+          }
         }
-        const double sv = active ? xs[6 * j + r] - acc : 0.0;
+        acc = group_reduce(acc, lane);  // totals on lanes 0..5
+        const double sv = lane < 6 ? xs[6 * j + r] - acc : 0.0;
         const double *Li = (cached && l0 < half) ? srcb + 36 * l0 : L + 36 * (size_t)b0;  // inverse diagonal block
         double xv = 0.0;
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
-          const double sc = __shfl_sync(0xffffffffu, sv, gl + c);
-          if (active && c >= r) xv += Li[6 * c + r] * sc;
+          const double sc = __shfl_sync(0xffffffffu, sv, c);
+          if (lane < 6 && c >= r) xv += Li[6 * c + r] * sc;
         }
-        if (active) xs[6 * j + r] = xv;
+        if (lane < 6) xs[6 * j + r] = xv;
       }
       stage_wait();
       __syncthreads();
