@@ -9,4 +9,4 @@ for line in sys.stdin:
             mm = re.match(r"(.*?) ([0-9.]+) ms", part)
             if mm: d["init:" + mm.group(1)].append(float(mm.group(2)))
 for k, v in d.items():
-    print(f"{k:34s} median {statistics.median(v[3:]):.3f} ms  (n={len(v)})")
+    print(f"{k:34s} median {statistics.median(v[3:] or v):.3f} ms  (n={len(v)})")

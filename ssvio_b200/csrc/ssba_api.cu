@@ -435,7 +435,7 @@ ssba_status ssba_initialize(ssba_handle *h) {
   STAT(s.pose_of_q, pose_of_q);
   STAT(h->owner_mask, owner_mask);
   STAT(s.unit_slot, unit_slot); STAT(s.unit_n, unit_n); STAT(s.unit_k, unit_k); STAT(s.unit_c0, unit_c0);
-  STAT(s.blk_row, blk_row); STAT(s.blk_col, blk_col); STAT(s.prog, prog); STAT(s.prog_ptr, prog_ptr);
+  STAT(s.blk_row, blk_row); STAT(s.blk_col, blk_col); STAT(s.col_ptr, col_diag); STAT(s.prog, prog); STAT(s.prog_ptr, prog_ptr);
 #undef STAT
   const size_t static_bytes = align_up(top);
   std::vector<Item> work;
@@ -452,7 +452,7 @@ ssba_status ssba_initialize(ssba_handle *h) {
   DYN(pose[0], 7 * g.n_poses, double); DYN(pose[1], 7 * g.n_poses, double);
   DYN(point[0], 3 * (size_t)g.n_points, double); DYN(point[1], 3 * (size_t)g.n_points, double);
   DYN(W, 18 * (size_t)s.n_pairs, double); DYN(Hll, 6 * (size_t)s.n_slots, double); DYN(bl, 3 * (size_t)s.n_slots, double);
-  DYN(Dinv, 6 * (size_t)s.n_slots, double); DYN(hpp_part, 27 * (size_t)s.n_hpp_parts, double);
+  DYN(Dinv, 6 * (size_t)s.n_slots, double); DYN(hpp_part, 27 * (size_t)s.n_hpp_parts, double); DYN(hpp_fold, 27 * (size_t)s.n_fp, double);
   DYN(sys, P.sys_doubles, double); DYN(xp, 6 * (size_t)s.n_fp, double); DYN(diag_buf, 6 * (size_t)s.n_fp, double);
   DYN(chi_cur_part, nblk, double); DYN(maxdiag_part, nblk, double); DYN(chi_new_part, nblk, double); DYN(scale_part, nblk, double);
   DYN(scal, 8, double); DYN(chi_out, 8, double);

@@ -65,6 +65,7 @@ struct DeviceProblem {
   int n_units;
   // factor structure
   const int32_t *blk_row, *blk_col;
+  const int32_t *col_diag;         // n_fp: the diagonal block of every column
   const int32_t *prog, *prog_ptr;  // per-level solver program (ssba_structure.cpp build_solver_program)
   int prog_max_seg, n_segments;
   // system
@@ -73,6 +74,7 @@ struct DeviceProblem {
   double *bl;         // n_slots x 3
   double *Dinv;       // n_slots x 6
   double *hpp_part;   // n_hpp_parts x 27 (b[6], upper-tri H[21])
+  double *hpp_fold;   // n_fp x 27: the partials of each pose folded (k_prepare_system)
   double *sys;        // [ L: n_blocks x 36 | bschur: n_fp x 6 | bp: n_fp x 6 ] — the all-reduced buffer
   double *xp;         // n_fp x 6
   double *diag_buf;   // n_fp x 6 Hpp diagonals (lambda init, summed over ranks)

@@ -266,35 +266,56 @@ __global__ void __launch_bounds__(kLinThreads, 3) k_linearize(const DeviceProble
   if (tid == 0) { P.chi_cur_part[blockIdx.x] = s_; P.maxdiag_part[blockIdx.x] = m; }
 }
 
-// Hpp / b_p entry k (0..5 = b, 6..26 = upper triangle) of pose q: the partials the linearize
-// CTAs wrote for the pose, folded in chunk order (deterministic)
-__device__ __forceinline__ double hpp_sum(const DeviceProblem &P, int q, int k) {
+// Hpp / b_p of pose q (entry k: 0..5 = b, 6..26 = upper triangle): the partials the linearize CTAs
+// wrote for the pose, folded in chunk order (deterministic).  One warp per pose, lane k < 27 owns
+// entry k; the loads of four partials are in flight together, the adds stay in list order.
+__device__ __forceinline__ double warp_fold_pose(const DeviceProblem &P, int q, int lane) {
   double s = 0.0;
-  for (int i = P.q_part_ptr[q]; i < P.q_part_ptr[q + 1]; ++i) s += P.hpp_part[27 * (size_t)P.q_part[i] + k];
+  if (lane < 27) {
+    const int i1 = P.q_part_ptr[q + 1];
+    int i = P.q_part_ptr[q];
+    for (; i + 4 <= i1; i += 4) {
+      const double v0 = P.hpp_part[27 * (size_t)P.q_part[i] + lane], v1 = P.hpp_part[27 * (size_t)P.q_part[i + 1] + lane];
+      const double v2 = P.hpp_part[27 * (size_t)P.q_part[i + 2] + lane], v3 = P.hpp_part[27 * (size_t)P.q_part[i + 3] + lane];
+      s += v0; s += v1; s += v2; s += v3;
+    }
+    for (; i < i1; ++i) s += P.hpp_part[27 * (size_t)P.q_part[i] + lane];
+  }
   return s;
 }
 // upper-triangle offset of diagonal entry d of the 6x6 block: 6, 12, 17, 21, 24, 26
 __device__ __forceinline__ int hpp_diag_index(int d) { return 6 + d * 6 - d * (d - 1) / 2; }
+__device__ __forceinline__ bool is_hpp_diag(int k) { return k == 6 || k == 12 || k == 17 || k == 21 || k == 24 || k == 26; }
 
 // multi-GPU, first iteration only: this rank's Hpp diagonals -> diag_buf (summed over ranks by
 // the host-enqueued all-reduce before k_maxdiag)
-__global__ void k_hpp_diag(const DeviceProblem P) {
+__global__ void __launch_bounds__(128) k_hpp_diag(const DeviceProblem P) {
   const Control *ctl = P.ctl;
   if (ctl->done || !ctl->first_iteration) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 6 * P.n_fp) P.diag_buf[i] = hpp_sum(P, i / 6, hpp_diag_index(i % 6));
+  const int q = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (q >= P.n_fp) return;
+  const double s = warp_fold_pose(P, q, lane);
+#pragma unroll
+  for (int d = 0; d < 6; ++d) if (lane == hpp_diag_index(d)) P.diag_buf[6 * q + d] = s;
 }
 
 // max |H_jj| over pose and landmark diagonals (levenberg.cpp:152-166) -> scal[3]
-__global__ void __launch_bounds__(256) k_maxdiag(const DeviceProblem P) {
+__global__ void __launch_bounds__(1024) k_maxdiag(const DeviceProblem P) {
   const Control *ctl = P.ctl;
   if (ctl->done || !ctl->first_iteration) return;
-  __shared__ double red[8];
+  __shared__ double red[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double m = 0.0;
-  for (int i = threadIdx.x; i < 6 * P.n_fp; i += 256)
-    m = fmax(m, fabs(ctl->world > 1 ? P.diag_buf[i] : hpp_sum(P, i / 6, hpp_diag_index(i % 6))));
-  for (int i = threadIdx.x; i < P.n_lin_blocks; i += 256) m = fmax(m, P.maxdiag_part[i]);
-  m = block_max<256>(m, red);
+  if (ctl->world > 1) {
+    for (int i = threadIdx.x; i < 6 * P.n_fp; i += 1024) m = fmax(m, fabs(P.diag_buf[i]));
+  } else {
+    for (int q = warp; q < P.n_fp; q += 32) {
+      const double s = warp_fold_pose(P, q, lane);
+      if (is_hpp_diag(lane)) m = fmax(m, fabs(s));
+    }
+  }
+  for (int i = threadIdx.x; i < P.n_lin_blocks; i += 1024) m = fmax(m, P.maxdiag_part[i]);
+  m = block_max<1024>(m, red);
   if (threadIdx.x == 0) P.scal[3] = m;
 }
 
@@ -310,29 +331,45 @@ __global__ void k_lambda_init(const DeviceProblem P) {
 // ---------------------------------------------------------------------------------------------
 // k_prepare_system — "Hschur = Hpp" with the lambda of setLambda on the diagonal
 // (block_solver.hpp:334-335,524-539), fill blocks zeroed, bschur = b_p (:397).  Written straight
-// into the factor storage.  With several ranks each rank contributes its own Hpp part and only
-// rank 0 adds lambda; the all-reduce completes the sum.
-__global__ void k_prepare_system(const DeviceProblem P) {
+// into the factor storage.  The first CTAs zero the off-diagonal blocks; then one warp per pose
+// folds the pose's Hpp partials (once per linearisation; a re-trial with a new lambda reads the
+// folded copy) and writes its diagonal block, bschur and b_p.  With several ranks each rank
+// contributes its own Hpp part and only rank 0 adds lambda; the all-reduce completes the sum.
+constexpr int kPrepThreads = 256;
+__global__ void __launch_bounds__(kPrepThreads) k_prepare_system(const DeviceProblem P, int n_zero_ctas) {
   const Control *ctl = P.ctl;
   if (ctl->done) return;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t nL = 36 * (size_t)P.n_blocks;
-  if (i < nL) {
-    const int b = (int)(i / 36), e = (int)(i % 36);
-    const int col = P.blk_col[b];
-    double v = 0.0;
-    if (P.blk_row[b] == col) {
-      const int r = e / 6, c = e % 6;
-      const int lo = r < c ? r : c, hi = r < c ? c : r;
-      v = hpp_sum(P, col, 6 + lo * 6 - lo * (lo - 1) / 2 + (hi - lo));
-      if (r == c && ctl->rank == 0) v += ctl->lambda;
+  if ((int)blockIdx.x < n_zero_ctas) {
+    const size_t i = (size_t)blockIdx.x * kPrepThreads + threadIdx.x;
+    if (i < 36 * (size_t)P.n_blocks) {
+      const int b = (int)(i / 36);
+      if (P.blk_row[b] != P.blk_col[b]) P.sys[i] = 0.0;
     }
-    P.sys[i] = v;
-  } else if (i < nL + 6 * (size_t)P.n_fp) {
-    const size_t k = i - nL;
-    const double v = hpp_sum(P, (int)(k / 6), (int)(k % 6));
-    P.sys[i] = v;                          // bschur
-    P.sys[i + 6 * (size_t)P.n_fp] = v;     // b_p (kept for computeScale)
+    return;
+  }
+  const int q = ((int)blockIdx.x - n_zero_ctas) * (kPrepThreads / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (q >= P.n_fp) return;
+  double s;
+  if (ctl->need_linearize) {
+    s = warp_fold_pose(P, q, lane);
+    if (lane < 27) P.hpp_fold[27 * q + lane] = s;
+  } else {
+    s = lane < 27 ? P.hpp_fold[27 * q + lane] : 0.0;
+  }
+  const double lambda = ctl->rank == 0 ? ctl->lambda : 0.0;
+  double *D = P.sys + 36 * (size_t)P.col_diag[q];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int e = lane + 32 * h, ee = e < 36 ? e : 0;
+    const int r = ee / 6, c = ee - 6 * r;
+    const int lo = r < c ? r : c, hi = r < c ? c : r;
+    const double v = __shfl_sync(0xffffffffu, s, 6 + lo * 6 - lo * (lo - 1) / 2 + (hi - lo));
+    if (e < 36) D[e] = r == c ? v + lambda : v;
+  }
+  if (lane < 6) {
+    double *bsch = P.sys + 36 * (size_t)P.n_blocks + 6 * (size_t)q;
+    bsch[lane] = s;                          // bschur
+    bsch[6 * (size_t)P.n_fp + lane] = s;     // b_p (kept for computeScale)
   }
 }
 
@@ -1098,16 +1135,16 @@ void launch_linearize(const DeviceProblem &P, cudaStream_t st) {
 }
 
 void launch_hpp_diag(const DeviceProblem &P, cudaStream_t st) {
-  if (P.n_fp > 0) k_hpp_diag<<<div_up(6LL * P.n_fp, 128), 128, 0, st>>>(P);
+  if (P.n_fp > 0) k_hpp_diag<<<div_up(P.n_fp, 4), 128, 0, st>>>(P);
 }
 
-void launch_maxdiag(const DeviceProblem &P, cudaStream_t st) { k_maxdiag<<<1, 256, 0, st>>>(P); }
+void launch_maxdiag(const DeviceProblem &P, cudaStream_t st) { k_maxdiag<<<1, 1024, 0, st>>>(P); }
 
 void launch_lambda_init(const DeviceProblem &P, cudaStream_t st) { k_lambda_init<<<1, 1, 0, st>>>(P); }
 
 void launch_prepare_system(const DeviceProblem &P, cudaStream_t st) {
-  const long long n = 36LL * P.n_blocks + 6LL * P.n_fp;
-  if (n > 0) k_prepare_system<<<div_up(n, 256), 256, 0, st>>>(P);
+  const int n_zero = (int)div_up(36LL * P.n_blocks, kPrepThreads), n_pose = (int)div_up(P.n_fp, kPrepThreads / 32);
+  if (n_zero + n_pose > 0) k_prepare_system<<<n_zero + n_pose, kPrepThreads, 0, st>>>(P, n_zero);
 }
 
 void launch_schur(const DeviceProblem &P, cudaStream_t st) {

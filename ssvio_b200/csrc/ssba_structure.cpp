@@ -517,18 +517,38 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
 
   // ---- validation + active sets (sparse_optimizer.cpp:201-272): an edge is active unless both
   // ends are fixed; a vertex is active when it has an active edge
-  std::vector<uint8_t> pose_active(NK, 0), point_active(NP, 0), edge_active(NE, 0);
+  std::vector<uint8_t> pose_active(NK, 0), point_active(NP, 0);
+  uvec<uint8_t> edge_active(NE);
   std::vector<int32_t> point_deg(NP + 1, 0);
   int n_active = 0;
-  for (int e = 0; e < NE; ++e) {
-    const int ip = ge_pose[e], il = ge_point[e];
-    if ((unsigned)ip >= (unsigned)NK) { err = "edge pose index out of range"; return false; }
-    if ((unsigned)il >= (unsigned)NP) { err = "edge point index out of range"; return false; }
-    if (ge_cam[e] >= g.cams.n) { err = "edge camera index out of range"; return false; }
-    if (pfix[ip] && lfix[il]) continue;
-    edge_active[e] = 1; ++n_active;
-    pose_active[ip] = 1; point_active[il] = 1;
-    ++point_deg[il];
+  bool edges_by_landmark = true;  // caller's edges already grouped by non-decreasing landmark row
+  {
+    std::vector<int> t_active(T, 0), t_bad(T, 0), t_sorted(T, 1);
+    uint8_t *pa = pose_active.data(), *la = point_active.data(), *ea = edge_active.data();
+    int32_t *deg = point_deg.data();
+    const int n_cams = g.cams.n;
+    pool.run(T, [&](int t, int TT) {
+      int e0, e1; split_range(t, TT, NE, e0, e1);
+      int na = 0, prev = e0 > 0 ? ge_point[e0 - 1] : -1;
+      bool sorted = true;
+      for (int e = e0; e < e1; ++e) {
+        const int ip = ge_pose[e], il = ge_point[e];
+        if ((unsigned)ip >= (unsigned)NK) { t_bad[t] = 1; return; }
+        if ((unsigned)il >= (unsigned)NP) { t_bad[t] = 2; return; }
+        if (ge_cam[e] >= n_cams) { t_bad[t] = 3; return; }
+        sorted &= il >= prev; prev = il;
+        if (pfix[ip] && lfix[il]) { ea[e] = 0; continue; }
+        ea[e] = 1; ++na;
+        // several threads may flag the same vertex / count edges of the same landmark
+        __atomic_store_n(pa + ip, (uint8_t)1, __ATOMIC_RELAXED);
+        __atomic_store_n(la + il, (uint8_t)1, __ATOMIC_RELAXED);
+        __atomic_fetch_add(deg + il, 1, __ATOMIC_RELAXED);
+      }
+      t_active[t] = na; t_sorted[t] = sorted;
+    });
+    static const char *const kBad[] = {"", "edge pose index out of range", "edge point index out of range", "edge camera index out of range"};
+    for (int t = 0; t < T; ++t) if (t_bad[t]) { err = kBad[t_bad[t]]; return false; }
+    for (int t = 0; t < T; ++t) { n_active += t_active[t]; edges_by_landmark = edges_by_landmark && t_sorted[t]; }
   }
   s.n_active_edges_global = n_active;
   s.point_active = point_active;
@@ -547,8 +567,13 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   // ---- edges by landmark (CSR over point rows, stable = addEdge order inside a landmark)
   std::vector<int32_t> pt_ptr(NP + 1, 0);
   for (int j = 0; j < NP; ++j) pt_ptr[j + 1] = pt_ptr[j] + point_deg[j];
-  std::vector<int32_t> pt_edges(n_active);
-  {
+  uvec<int32_t> pt_edges(n_active);
+  if (edges_by_landmark && n_active == NE) {  // the order ssvio's back-end adds them in: nothing to sort
+    pool.run(T, [&](int t, int TT) {
+      int e0, e1; split_range(t, TT, NE, e0, e1);
+      for (int e = e0; e < e1; ++e) pt_edges[e] = e;
+    });
+  } else {
     std::vector<int32_t> fill(pt_ptr.begin(), pt_ptr.end() - 1);
     for (int e = 0; e < NE; ++e)
       if (edge_active[e]) pt_edges[fill[ge_point[e]]++] = e;

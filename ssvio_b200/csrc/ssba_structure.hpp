@@ -12,12 +12,26 @@
 #pragma once
 
 #include <cstdint>
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "ssba_geometry.cuh"
 
 namespace ssba {
+
+// std::vector whose resize() leaves new elements uninitialised: the big per-edge / per-pair arrays
+// are filled completely (in parallel) right after they are sized, a zero-fill first would be a
+// second pass over several megabytes on the end-to-end path
+template <class T>
+struct DefaultInitAllocator : std::allocator<T> {
+  template <class U> struct rebind { using other = DefaultInitAllocator<U>; };
+  using std::allocator<T>::allocator;
+  template <class U> void construct(U *p) noexcept { ::new (static_cast<void *>(p)) U; }
+  template <class U, class... A> void construct(U *p, A &&...a) { ::new (static_cast<void *>(p)) U(std::forward<A>(a)...); }
+};
+template <class T> using uvec = std::vector<T, DefaultInitAllocator<T>>;
 
 struct HostGraph {
   Cameras cams{};
@@ -46,10 +60,10 @@ struct Structure {
   std::vector<int32_t> slot_vertex;   // point row
   std::vector<uint8_t> slot_free;
   std::vector<int32_t> slot_pair_ptr; // n_slots + 1
-  std::vector<int32_t> pair_vertex;   // pose row
-  std::vector<int32_t> pair_q;        // -1: pose fixed (pairs with a free pose first, by q)
-  std::vector<int32_t> pair_edge_ptr; // n_pairs + 1
-  std::vector<int32_t> pair_slot;     // n_pairs: the slot of the pair
+  uvec<int32_t> pair_vertex;   // pose row
+  uvec<int32_t> pair_q;        // -1: pose fixed (pairs with a free pose first, by q)
+  uvec<int32_t> pair_edge_ptr; // n_pairs + 1
+  uvec<int32_t> pair_slot;     // n_pairs: the slot of the pair
   std::vector<int32_t> lchunk_slot;   // n_lchunks + 1: CTAs of k_linearize / k_update = runs of whole
                                       // landmarks with <= 128 pairs (a larger landmark is alone)
   int n_lchunks = 0;
@@ -61,13 +75,13 @@ struct Structure {
   std::vector<uint8_t> lp_pair;        // pair index inside the chunk (chunks with <= 128 pairs)
   std::vector<int32_t> q_part_ptr;     // n_fp + 1 -> q_part: the partials of pose q, in chunk order
   std::vector<int32_t> q_part;
-  std::vector<double> e_uv;           // sorted copies
-  std::vector<uint8_t> e_cam;
-  std::vector<int32_t> e_orig;        // index in the caller's addEdge order
-  std::vector<double> e_info, e_delta;
+  uvec<double> e_uv;                  // sorted copies
+  uvec<uint8_t> e_cam;
+  uvec<int32_t> e_orig;               // index in the caller's addEdge order
+  uvec<double> e_info, e_delta;
   // Schur accumulation targets: per free slot, for W-pairs i <= j (sorted by q): block (q_j, q_i)
   std::vector<int32_t> slot_combo_ptr; // n_slots + 1
-  std::vector<int32_t> combo_blk;
+  uvec<int32_t> combo_blk;
   // Schur work units (k_schur): run of landmarks [unit_slot, +unit_n) sharing one W pose list of
   // unit_k poses, block pairs [unit_c0, +32) of its k(k+1)/2
   int n_units = 0;
