@@ -16,7 +16,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libssba.so")
+# SSBA_LIB: developer override (e.g. a -DSSBA_SOLVER_TRACE build); the product path is the in-tree library
+LIB_PATH = os.environ.get("SSBA_LIB") or os.path.join(HERE, "lib", "libssba.so")
 
 SSBA_MAX_ITER_RECORDS = 128
 SSBA_NCCL_ID_BYTES = 128

@@ -432,9 +432,9 @@ class HostPool {
 
  private:
   HostPool() {
-    int n = (int)std::thread::hardware_concurrency();
+    int n = std::min((int)std::thread::hardware_concurrency(), 4);  // measured on the B200 hosts: 4 threads is the knee
     if (const char *e = std::getenv("SSBA_HOST_THREADS")) n = std::atoi(e);
-    n_ = std::max(1, std::min(n, 4));  // measured on the B200 hosts: the passes are memory-bound, 4 threads is the knee
+    n_ = std::max(1, std::min(n, 64));
     for (int t = 1; t < n_; ++t) std::thread([this, t] { worker(t); }).detach();
   }
   void worker(int t) {
@@ -531,6 +531,10 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
       int e0, e1; split_range(t, TT, NE, e0, e1);
       int na = 0, prev = e0 > 0 ? ge_point[e0 - 1] : -1;
       bool sorted = true;
+      // The flag arrays are shared by all threads: a flag is only written while it is still 0 (a
+      // store per edge would bounce the few cache lines of pose_active between the cores), and
+      // the degree of a landmark is added once per run of consecutive edges of that landmark.
+      int run_l = -1, run_n = 0;
       for (int e = e0; e < e1; ++e) {
         const int ip = ge_pose[e], il = ge_point[e];
         if ((unsigned)ip >= (unsigned)NK) { t_bad[t] = 1; return; }
@@ -539,11 +543,15 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
         sorted &= il >= prev; prev = il;
         if (pfix[ip] && lfix[il]) { ea[e] = 0; continue; }
         ea[e] = 1; ++na;
-        // several threads may flag the same vertex / count edges of the same landmark
-        __atomic_store_n(pa + ip, (uint8_t)1, __ATOMIC_RELAXED);
-        __atomic_store_n(la + il, (uint8_t)1, __ATOMIC_RELAXED);
-        __atomic_fetch_add(deg + il, 1, __ATOMIC_RELAXED);
+        if (!__atomic_load_n(pa + ip, __ATOMIC_RELAXED)) __atomic_store_n(pa + ip, (uint8_t)1, __ATOMIC_RELAXED);
+        if (il != run_l) {
+          if (run_n) __atomic_fetch_add(deg + run_l, run_n, __ATOMIC_RELAXED);
+          run_l = il; run_n = 0;
+          if (!__atomic_load_n(la + il, __ATOMIC_RELAXED)) __atomic_store_n(la + il, (uint8_t)1, __ATOMIC_RELAXED);
+        }
+        ++run_n;
       }
+      if (run_n) __atomic_fetch_add(deg + run_l, run_n, __ATOMIC_RELAXED);
       t_active[t] = na; t_sorted[t] = sorted;
     });
     static const char *const kBad[] = {"", "edge pose index out of range", "edge point index out of range", "edge camera index out of range"};
