@@ -161,12 +161,12 @@ ssba_status enqueue_slot(ssba_handle *h, bool first) {
     h->prof.kernel_launches += 1;
   }
   if (first) {
-    if (multi) {
-      PhaseTimer t(h, 4);
-      launch_hpp_diag(P, st);
+    {
+      PhaseTimer t(h, 0);
+      launch_fold(P, st);
       h->prof.kernel_launches += 1;
-      if ((rc = nccl_allreduce(h, P.diag_buf, 6 * (size_t)P.n_fp, kNcclSum))) return rc;
     }
+    if (multi) { PhaseTimer t(h, 4); if ((rc = nccl_allreduce(h, P.diag_buf, 6 * (size_t)P.n_fp, kNcclSum))) return rc; }
     launch_maxdiag(P, st);
     if (multi) { PhaseTimer t(h, 4); if ((rc = nccl_allreduce(h, P.scal + 3, 1, kNcclMax))) return rc; }
     launch_lambda_init(P, st);
@@ -174,9 +174,8 @@ ssba_status enqueue_slot(ssba_handle *h, bool first) {
   }
   {
     PhaseTimer t(h, 1);
-    launch_prepare_system(P, st);
-    launch_schur(P, st);
-    h->prof.kernel_launches += 2;
+    launch_schur(P, first, st);
+    h->prof.kernel_launches += 1;
   }
   if (multi) { PhaseTimer t(h, 4); if ((rc = nccl_allreduce(h, P.sys, P.sys_doubles, kNcclSum))) return rc; }
   {
@@ -186,13 +185,15 @@ ssba_status enqueue_slot(ssba_handle *h, bool first) {
   }
   {
     PhaseTimer t(h, 3);
-    launch_update(P, st);
+    launch_update(P, !multi, st);
     h->prof.kernel_launches += 1;
     if (multi) { launch_reduce_partials(P, st); h->prof.kernel_launches += 1; }
   }
-  if (multi) { PhaseTimer t(h, 4); if ((rc = nccl_allreduce(h, P.scal, 3, kNcclSum))) return rc; }
-  launch_control(P, !multi, st);
-  h->prof.kernel_launches += 1;
+  if (multi) {
+    { PhaseTimer t(h, 4); if ((rc = nccl_allreduce(h, P.scal, 3, kNcclSum))) return rc; }
+    launch_control(P, st);
+    h->prof.kernel_launches += 1;
+  }
   return SSBA_OK;
 }
 
@@ -518,6 +519,8 @@ ssba_status ssba_reset_state(ssba_handle *h) {
     if (pb) CUDA_TRY(h, cudaMemcpyAsync(P.pose[k], P.pose0, pb, cudaMemcpyDeviceToDevice, h->stream));
     if (lb) CUDA_TRY(h, cudaMemcpyAsync(P.point[k], P.point0, lb, cudaMemcpyDeviceToDevice, h->stream));
   }
+  // k_schur accumulates into a zeroed reduced system; after the first trial k_update keeps it so
+  CUDA_TRY(h, cudaMemsetAsync(P.sys, 0, sizeof(double) * P.sys_doubles, h->stream));
   h->cur = 0; h->lambda = -1.0; h->ni = 2.0;
   // the controller must name buffer 0 for the read-out kernels even before the first optimize
   std::memset(h->h_ctl, 0, sizeof(Control));

@@ -34,6 +34,7 @@ struct Control {
   int last_result;         // ssba_solver_result of the last finished outer iteration
   int n_records;
   int world, rank;
+  unsigned int ticket;     // CTAs of k_update that have finished (the last one runs control_step)
   ssba_iter_record records[SSBA_MAX_ITER_RECORDS];
 };
 
@@ -94,13 +95,13 @@ struct DeviceProblem {
 void launch_linearize(const DeviceProblem &P, cudaStream_t st);        // K_lin + K_hpp + hpp reduce
 void launch_maxdiag(const DeviceProblem &P, cudaStream_t st);          // -> scal[3]
 void launch_lambda_init(const DeviceProblem &P, cudaStream_t st);
-void launch_prepare_system(const DeviceProblem &P, cudaStream_t st);   // sys <- blockdiag(Hpp)+lambda I, bp
-void launch_schur(const DeviceProblem &P, cudaStream_t st);
+// sys += blockdiag(Hpp) + lambda I - W Hll^-1 W^T, bschur, b_p (sys zeroed by the previous k_update)
+void launch_schur(const DeviceProblem &P, bool prefolded, cudaStream_t st);
 void launch_reduced_solve(const DeviceProblem &P, cudaStream_t st);
-void launch_update(const DeviceProblem &P, cudaStream_t st);
+void launch_update(const DeviceProblem &P, bool fused_control, cudaStream_t st);  // + accept/reject when fused
 void launch_reduce_partials(const DeviceProblem &P, cudaStream_t st);  // -> scal[0..2]
-void launch_control(const DeviceProblem &P, bool fused_reduce, cudaStream_t st);
-void launch_hpp_diag(const DeviceProblem &P, cudaStream_t st);       // multi-GPU lambda init
+void launch_control(const DeviceProblem &P, cudaStream_t st);          // several GPUs only
+void launch_fold(const DeviceProblem &P, cudaStream_t st);           // first slot: hpp_fold + Hpp diagonals
 void launch_final_chi2(const DeviceProblem &P, double threshold, cudaStream_t st);  // -> chi_out
 void launch_edge_errors(const DeviceProblem &P, cudaStream_t st);      // -> err_out
 void launch_gather_points(const DeviceProblem &P, cudaStream_t st);    // -> gather

@@ -287,14 +287,16 @@ __device__ __forceinline__ double warp_fold_pose(const DeviceProblem &P, int q, 
 __device__ __forceinline__ int hpp_diag_index(int d) { return 6 + d * 6 - d * (d - 1) / 2; }
 __device__ __forceinline__ bool is_hpp_diag(int k) { return k == 6 || k == 12 || k == 17 || k == 21 || k == 24 || k == 26; }
 
-// multi-GPU, first iteration only: this rank's Hpp diagonals -> diag_buf (summed over ranks by
-// the host-enqueued all-reduce before k_maxdiag)
-__global__ void __launch_bounds__(128) k_hpp_diag(const DeviceProblem P) {
+// first slot of an optimize()/step() call: every pose's Hpp partials folded once -> hpp_fold, and
+// the Hpp diagonals -> diag_buf for computeLambdaInit (summed over ranks by the host-enqueued
+// all-reduce before k_maxdiag when there are several).  One warp per pose.
+__global__ void __launch_bounds__(128) k_fold(const DeviceProblem P) {
   const Control *ctl = P.ctl;
-  if (ctl->done || !ctl->first_iteration) return;
+  if (ctl->done || !ctl->need_linearize) return;
   const int q = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (q >= P.n_fp) return;
   const double s = warp_fold_pose(P, q, lane);
+  if (lane < 27) P.hpp_fold[27 * q + lane] = s;
 #pragma unroll
   for (int d = 0; d < 6; ++d) if (lane == hpp_diag_index(d)) P.diag_buf[6 * q + d] = s;
 }
@@ -304,16 +306,8 @@ __global__ void __launch_bounds__(1024) k_maxdiag(const DeviceProblem P) {
   const Control *ctl = P.ctl;
   if (ctl->done || !ctl->first_iteration) return;
   __shared__ double red[32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double m = 0.0;
-  if (ctl->world > 1) {
-    for (int i = threadIdx.x; i < 6 * P.n_fp; i += 1024) m = fmax(m, fabs(P.diag_buf[i]));
-  } else {
-    for (int q = warp; q < P.n_fp; q += 32) {
-      const double s = warp_fold_pose(P, q, lane);
-      if (is_hpp_diag(lane)) m = fmax(m, fabs(s));
-    }
-  }
+  for (int i = threadIdx.x; i < 6 * P.n_fp; i += 1024) m = fmax(m, fabs(P.diag_buf[i]));
   for (int i = threadIdx.x; i < P.n_lin_blocks; i += 1024) m = fmax(m, P.maxdiag_part[i]);
   m = block_max<1024>(m, red);
   if (threadIdx.x == 0) P.scal[3] = m;
@@ -329,28 +323,30 @@ __global__ void k_lambda_init(const DeviceProblem P) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_prepare_system — "Hschur = Hpp" with the lambda of setLambda on the diagonal
-// (block_solver.hpp:334-335,524-539), fill blocks zeroed, bschur = b_p (:397).  Written straight
-// into the factor storage.  The first CTAs zero the off-diagonal blocks; then one warp per pose
-// folds the pose's Hpp partials (once per linearisation; a re-trial with a new lambda reads the
-// folded copy) and writes its diagonal block, bschur and b_p.  With several ranks each rank
-// contributes its own Hpp part and only rank 0 adds lambda; the all-reduce completes the sum.
-constexpr int kPrepThreads = 256;
-__global__ void __launch_bounds__(kPrepThreads) k_prepare_system(const DeviceProblem P, int n_zero_ctas) {
-  const Control *ctl = P.ctl;
-  if (ctl->done) return;
-  if ((int)blockIdx.x < n_zero_ctas) {
-    const size_t i = (size_t)blockIdx.x * kPrepThreads + threadIdx.x;
-    if (i < 36 * (size_t)P.n_blocks) {
-      const int b = (int)(i / 36);
-      if (P.blk_row[b] != P.blk_col[b]) P.sys[i] = 0.0;
-    }
-    return;
-  }
-  const int q = ((int)blockIdx.x - n_zero_ctas) * (kPrepThreads / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (q >= P.n_fp) return;
+// k_schur — the reduced system of BlockSolver::solve (block_solver.hpp:334-400), accumulated with
+// fp64 atomic adds into the factor storage `sys`, which the previous trial's k_update left zeroed:
+//   "Hschur = Hpp" with the lambda of setLambda on the diagonal (:334-335,524-539), bschur = b_p (:397)
+//       — the first CTAs, one warp per pose: fold the pose's Hpp partials (once per linearisation;
+//       a re-trial with a new lambda reads the folded copy) and add the diagonal block, bschur,
+//       and store b_p.  With several ranks each rank contributes its own Hpp part and only rank
+//       0 adds lambda; the all-reduce completes the sum.
+//   landmark elimination (:342-400): Dinv = (Hll + lambda I)^-1, bschur -= W Dinv b_l,
+//       S(i1,i2) -= W_i1 Dinv W_i2^T — the other CTAs, one warp per work unit = a run of <= 16
+//       landmarks seen by the same k free poses (the host sorts the landmarks so that such runs
+//       exist) x <= 32 of the k(k+1)/2 block pairs.  Lane i first inverts the 3x3 block of
+//       landmark i of the run into shared memory; then a lane owns ONE 6x6 block pair (a, b) and
+//       walks every G-th landmark of the run (G = 32 / block pairs lane groups share the run),
+//       accumulating its block in 36 registers; the G partial blocks meet through shuffles and
+//       only the per-unit totals go to the L2-resident reduced system.
+constexpr int kStageWarps = 4;  // warps of k_reduced_solve that issue the cp.async prefetches
+constexpr int kSchurWarps = 4;
+constexpr int kSchurRunPairs = 80;  // W blocks of one run staged in shared memory (= host kSchurRunPairs)
+constexpr int kSchurRun = 16;       // landmarks per run (= host kSchurRun)
+
+__device__ __forceinline__ void schur_pose_warp(const DeviceProblem &P, const Control *ctl, int q, int lane,
+                                                bool prefolded) {
   double s;
-  if (ctl->need_linearize) {
+  if (ctl->need_linearize && !prefolded) {
     s = warp_fold_pose(P, q, lane);
     if (lane < 27) P.hpp_fold[27 * q + lane] = s;
   } else {
@@ -364,38 +360,29 @@ __global__ void __launch_bounds__(kPrepThreads) k_prepare_system(const DevicePro
     const int r = ee / 6, c = ee - 6 * r;
     const int lo = r < c ? r : c, hi = r < c ? c : r;
     const double v = __shfl_sync(0xffffffffu, s, 6 + lo * 6 - lo * (lo - 1) / 2 + (hi - lo));
-    if (e < 36) D[e] = r == c ? v + lambda : v;
+    if (e < 36) atomicAdd(D + e, r == c ? v + lambda : v);
   }
   if (lane < 6) {
     double *bsch = P.sys + 36 * (size_t)P.n_blocks + 6 * (size_t)q;
-    bsch[lane] = s;                          // bschur
+    atomicAdd(bsch + lane, s);               // bschur
     bsch[6 * (size_t)P.n_fp + lane] = s;     // b_p (kept for computeScale)
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// k_schur — landmark elimination of BlockSolver::solve (block_solver.hpp:342-400):
-// Dinv = (Hll + lambda I)^-1, bschur -= W Dinv b_l, S(i1,i2) -= W_i1 Dinv W_i2^T.
-//
-// One warp per work unit = a run of <= 32 landmarks that are seen by the same k free poses
-// (the host sorts the landmarks so that such runs exist) x <= 32 of the k(k+1)/2 block pairs.
-// Lane i first inverts the 3x3 block of landmark i of the run into shared memory; then every
-// lane owns ONE 6x6 block pair (a, b) and walks the run, accumulating its block in 36 registers.
-// Only the per-unit totals go to the L2-resident reduced system with fp64 atomic adds
-// (~1/32 of the per-landmark contributions).
-constexpr int kStageWarps = 4;  // warps of k_reduced_solve that issue the cp.async prefetches
-constexpr int kSchurWarps = 4;
-constexpr int kSchurRunPairs = 160;  // W blocks of one run staged in shared memory (= host kSchurRunPairs)
-
-__global__ void __launch_bounds__(32 * kSchurWarps) k_schur(const DeviceProblem P) {
+__global__ void __launch_bounds__(32 * kSchurWarps) k_schur(const DeviceProblem P, int n_pose_ctas, int prefolded) {
   const Control *ctl = P.ctl;
   if (ctl->done) return;
   extern __shared__ double s_w_all[];  // kSchurWarps x kSchurRunPairs x 18
-  __shared__ double s_dinv[kSchurWarps][32][6];
-  __shared__ double s_db[kSchurWarps][32][3];
-  __shared__ int s_pair0[kSchurWarps][32];
+  __shared__ double s_dinv[kSchurWarps][kSchurRun][6];
+  __shared__ double s_db[kSchurWarps][kSchurRun][3];
+  __shared__ int s_pair0[kSchurWarps][kSchurRun];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int u = blockIdx.x * kSchurWarps + warp;
+  if ((int)blockIdx.x < n_pose_ctas) {
+    const int q = blockIdx.x * kSchurWarps + warp;
+    if (q < P.n_fp) schur_pose_warp(P, ctl, q, lane, prefolded != 0);
+    return;
+  }
+  const int u = ((int)blockIdx.x - n_pose_ctas) * kSchurWarps + warp;
   if (u >= P.n_units) return;  // whole warp; no block-wide barrier below
   const int s0 = P.unit_slot[u], n = P.unit_n[u], k = P.unit_k[u], c0 = P.unit_c0[u];
   double *s_w = s_w_all + (size_t)warp * kSchurRunPairs * 18;
@@ -434,8 +421,14 @@ __global__ void __launch_bounds__(32 * kSchurWarps) k_schur(const DeviceProblem 
   }
   asm volatile("cp.async.wait_all;\n" ::: "memory");
   __syncwarp();
-  const int idx = c0 + lane;
-  if (idx >= k * (k + 1) / 2) return;
+  // cw block pairs of this unit, shared by G lane groups that split the run's landmarks
+  const int ncomb = k * (k + 1) / 2;
+  const int cw = ncomb - c0 < 32 ? ncomb - c0 : 32;
+  int G = 32 / cw;
+  G = G > 4 ? 4 : G;
+  const int sub = lane / cw, ci = lane - sub * cw;
+  const bool active = sub < G;
+  const int idx = c0 + ci;
   // block pair (a <= b) of this lane, enumerated like combo_blk: a-major
   int a = 0, rem = idx;
   while (rem >= k - a) { rem -= k - a; ++a; }
@@ -446,42 +439,58 @@ __global__ void __launch_bounds__(32 * kSchurWarps) k_schur(const DeviceProblem 
   for (int i = 0; i < 36; ++i) acc[i] = 0.0;
 #pragma unroll
   for (int i = 0; i < 6; ++i) accb[i] = 0.0;
-  for (int i = 0; i < n; ++i) {
-    const double2 *sa, *sb;
-    if (staged) {
-      sa = reinterpret_cast<const double2 *>(s_w + 18 * (size_t)(i * k + a));
-      sb = reinterpret_cast<const double2 *>(s_w + 18 * (size_t)(i * k + b));
-    } else {
-      const int p0 = s_pair0[warp][i];
-      sa = reinterpret_cast<const double2 *>(P.W + 18 * (size_t)(p0 + a));
-      sb = reinterpret_cast<const double2 *>(P.W + 18 * (size_t)(p0 + b));
-    }
-    double Wa[18], Wb[18], BD[18];
+  if (active) {
+    for (int i = sub; i < n; i += G) {
+      const double2 *sa, *sb;
+      if (staged) {
+        sa = reinterpret_cast<const double2 *>(s_w + 18 * (size_t)(i * k + a));
+        sb = reinterpret_cast<const double2 *>(s_w + 18 * (size_t)(i * k + b));
+      } else {
+        const int p0 = s_pair0[warp][i];
+        sa = reinterpret_cast<const double2 *>(P.W + 18 * (size_t)(p0 + a));
+        sb = reinterpret_cast<const double2 *>(P.W + 18 * (size_t)(p0 + b));
+      }
+      double Wa[18], Wb[18], BD[18];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) { const double2 x = sa[t]; Wa[2 * t] = x.x; Wa[2 * t + 1] = x.y; }
+      for (int t = 0; t < 9; ++t) { const double2 x = sa[t]; Wa[2 * t] = x.x; Wa[2 * t + 1] = x.y; }
 #pragma unroll
-    for (int t = 0; t < 9; ++t) { const double2 x = sb[t]; Wb[2 * t] = x.x; Wb[2 * t + 1] = x.y; }
-    const double d0 = s_dinv[warp][i][0], d1 = s_dinv[warp][i][1], d2 = s_dinv[warp][i][2],
-                 d3 = s_dinv[warp][i][3], d4 = s_dinv[warp][i][4], d5 = s_dinv[warp][i][5];
+      for (int t = 0; t < 9; ++t) { const double2 x = sb[t]; Wb[2 * t] = x.x; Wb[2 * t + 1] = x.y; }
+      const double d0 = s_dinv[warp][i][0], d1 = s_dinv[warp][i][1], d2 = s_dinv[warp][i][2],
+                   d3 = s_dinv[warp][i][3], d4 = s_dinv[warp][i][4], d5 = s_dinv[warp][i][5];
 #pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      const double w0 = Wa[3 * r], w1 = Wa[3 * r + 1], w2 = Wa[3 * r + 2];
-      BD[3 * r + 0] = w0 * d0 + w1 * d1 + w2 * d2;
-      BD[3 * r + 1] = w0 * d1 + w1 * d3 + w2 * d4;
-      BD[3 * r + 2] = w0 * d2 + w1 * d4 + w2 * d5;
-    }
-    // block (row q_b, col q_a) += W_b Dinv W_a^T
+      for (int r = 0; r < 6; ++r) {
+        const double w0 = Wa[3 * r], w1 = Wa[3 * r + 1], w2 = Wa[3 * r + 2];
+        BD[3 * r + 0] = w0 * d0 + w1 * d1 + w2 * d2;
+        BD[3 * r + 1] = w0 * d1 + w1 * d3 + w2 * d4;
+        BD[3 * r + 2] = w0 * d2 + w1 * d4 + w2 * d5;
+      }
+      // block (row q_b, col q_a) += W_b Dinv W_a^T
 #pragma unroll
-    for (int r = 0; r < 6; ++r)
+      for (int r = 0; r < 6; ++r)
 #pragma unroll
-      for (int c = 0; c < 6; ++c)
-        acc[6 * r + c] += Wb[3 * r] * BD[3 * c] + Wb[3 * r + 1] * BD[3 * c + 1] + Wb[3 * r + 2] * BD[3 * c + 2];
-    if (diag) {
-      const double e0 = s_db[warp][i][0], e1 = s_db[warp][i][1], e2 = s_db[warp][i][2];
+        for (int c = 0; c < 6; ++c)
+          acc[6 * r + c] += Wb[3 * r] * BD[3 * c] + Wb[3 * r + 1] * BD[3 * c + 1] + Wb[3 * r + 2] * BD[3 * c + 2];
+      if (diag) {
+        const double e0 = s_db[warp][i][0], e1 = s_db[warp][i][1], e2 = s_db[warp][i][2];
 #pragma unroll
-      for (int r = 0; r < 6; ++r) accb[r] += Wa[3 * r] * e0 + Wa[3 * r + 1] * e1 + Wa[3 * r + 2] * e2;
+        for (int r = 0; r < 6; ++r) accb[r] += Wa[3 * r] * e0 + Wa[3 * r + 1] * e1 + Wa[3 * r + 2] * e2;
+      }
     }
   }
+  // the G partial blocks -> lane group 0 (fixed order, so the unit total is deterministic)
+  for (int g = 1; g < G; ++g) {
+#pragma unroll
+    for (int i = 0; i < 36; ++i) {
+      const double t = __shfl_down_sync(0xffffffffu, acc[i], g * cw);
+      if (sub == 0) acc[i] += t;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const double t = __shfl_down_sync(0xffffffffu, accb[i], g * cw);
+      if (sub == 0) accb[i] += t;
+    }
+  }
+  if (sub != 0) return;
   double *dst = P.sys + 36 * (size_t)P.combo_blk[P.slot_combo_ptr[s0] + idx];
 #pragma unroll
   for (int i = 0; i < 36; ++i) atomicAdd(dst + i, -acc[i]);
@@ -866,6 +875,83 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
 }
 
 // ---------------------------------------------------------------------------------------------
+// control_step — the accept/reject law of OptimizationAlgorithmLevenberg::solve
+// (levenberg.cpp:119-149) and the iteration bookkeeping of SparseOptimizer::optimize
+// (sparse_optimizer.cpp:386-426), on the device so that no host round trip sits between trials.
+// Runs on one thread once scal[0..2] = chi(current), chi(trial), landmark part of computeScale.
+__device__ void control_step(const DeviceProblem &P) {
+  Control *c = P.ctl;
+  const double currentChi = P.scal[0];
+  double tempChi = P.scal[1];
+  if (c->outer_iter == 0 && c->qmax == 0) c->chi2_initial = currentChi;
+  const bool fail = c->chol_fail != 0;
+  if (fail) { tempChi = DBL_MAX; c->cholesky_failures++; }
+  double scale = P.scal[2] + c->scale_pose;
+  scale += 1e-3;
+  double rho = (currentChi - tempChi) / scale;
+  if (fail) rho = -1.0;  // a failed factorisation always rejects the step (levenberg.cpp:120-121)
+  bool broke = false, accepted = false;
+  if (rho > 0 && isfinite(tempChi)) {
+    const double t = 2 * rho - 1;
+    double alpha = 1. - t * t * t;
+    alpha = fmin(alpha, c->good_upper);
+    const double scaleFactor = fmax(c->good_lower, alpha);
+    c->lambda *= scaleFactor;
+    c->ni = 2;
+    c->cur ^= 1;  // discardTop(): the trial buffer becomes the estimate
+    accepted = true;
+  } else {
+    c->lambda *= c->ni;
+    c->ni *= 2;  // pop(): the estimate buffer is simply kept
+    if (!isfinite(c->lambda)) broke = true;
+  }
+  if (!broke) c->qmax++;
+  c->rho = rho;
+  c->temp_chi = tempChi;
+  c->current_chi = accepted ? tempChi : currentChi;
+  const bool again = !broke && rho < 0 && c->qmax < c->max_trials;
+  if (again) {
+    c->need_linearize = 0;
+    return;
+  }
+  const int result = (c->qmax == c->max_trials || rho == 0 || !isfinite(c->lambda))
+                         ? SSBA_SOLVER_TERMINATE : SSBA_SOLVER_OK;
+  if (c->n_records < SSBA_MAX_ITER_RECORDS) {
+    ssba_iter_record &r = c->records[c->n_records++];
+    r.chi2 = c->current_chi; r.lambda = c->lambda; r.trials = c->qmax; r.result = result;
+  }
+  c->last_result = result;
+  c->outer_iter++;
+  c->qmax = 0;
+  c->need_linearize = 1;
+  if (result != SSBA_SOLVER_OK || c->outer_iter >= c->max_iters) c->done = 1;
+}
+
+// partial sums of the linearize / update CTAs -> scal[0..2], folded in a fixed order by one CTA
+template <int NT>
+__device__ __forceinline__ void fold_partials(const DeviceProblem &P, double *red) {
+  // eight loads in flight per thread, added in index order
+  auto strided_sum = [](const double *__restrict__ part, int n) {
+    double acc = 0.0;
+    for (int base = threadIdx.x; base < n; base += 8 * NT) {
+      double v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = base + j * NT < n ? part[base + j * NT] : 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += v[j];
+    }
+    return acc;
+  };
+  double a = strided_sum(P.chi_cur_part, P.n_lin_blocks);
+  double b = strided_sum(P.chi_new_part, P.n_upd_blocks);
+  double c = strided_sum(P.scale_part, P.n_upd_blocks);
+  a = block_sum<NT>(a, red);
+  b = block_sum<NT>(b, red);
+  c = block_sum<NT>(c, red);
+  if (threadIdx.x == 0) { P.scal[0] = a; P.scal[1] = b; P.scal[2] = c; }
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_update — landmark back-substitution x_l = Dinv (b_l - W^T x_p) (block_solver.hpp:420-442),
 // p <- p + x_l (g2otypes.hpp:54-59), the landmark part of computeScale, and the trial
 // computeActiveErrors + activeRobustChi2 (levenberg.cpp:116-117).  Same decomposition as
@@ -902,10 +988,21 @@ __device__ __forceinline__ void pair_wtx(const DeviceProblem &P, int a, double *
   }
 }
 
+//
+// The reduced system is dead once k_reduced_solve has run: every CTA zeroes a slice of it for the
+// atomic accumulation of the next trial's k_schur.  kFusedControl (single GPU): the CTA that
+// finishes last folds the partial sums and takes the accept/reject decision (control_step), so
+// no separate launch sits between two trials.
+template <bool kFusedControl>
 __global__ void __launch_bounds__(kLinThreads) k_update(const DeviceProblem P) {
-  const Control *ctl = P.ctl;
+  Control *ctl = P.ctl;
   if (ctl->done) return;
   __shared__ double red[kLinThreads / 32];
+  __shared__ int s_last;
+  {
+    const size_t nz = 36 * (size_t)P.n_blocks + 6 * (size_t)P.n_fp;  // blocks and bschur; b_p is overwritten
+    for (size_t i = (size_t)blockIdx.x * kLinThreads + threadIdx.x; i < nz; i += (size_t)gridDim.x * kLinThreads) P.sys[i] = 0.0;
+  }
   __shared__ double s_part[kLinThreads][3];
   __shared__ double s_pnew[kLinThreads][3];
   const int cur = ctl->cur;
@@ -973,84 +1070,29 @@ __global__ void __launch_bounds__(kLinThreads) k_update(const DeviceProblem P) {
   const double s_ = block_sum<kLinThreads>(chi, red);
   const double sc = block_sum<kLinThreads>(scale, red);
   if (tid == 0) { P.chi_new_part[blockIdx.x] = s_; P.scale_part[blockIdx.x] = sc; }
+  if (kFusedControl) {
+    if (tid == 0) {
+      __threadfence();
+      s_last = atomicAdd(&ctl->ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;  // block-uniform
+    __threadfence();
+    fold_partials<kLinThreads>(P, red);
+    if (tid == 0) { ctl->ticket = 0; control_step(P); }
+  }
 }
 
-// partial sums -> scal[0..2] = chi(current), chi(trial), landmark part of computeScale
+// several GPUs: partial sums -> scal[0..2] (then all-reduced), and the decision in k_control
 __global__ void __launch_bounds__(256) k_reduce_partials(const DeviceProblem P) {
-  const Control *ctl = P.ctl;
-  if (ctl->done) return;
+  if (P.ctl->done) return;
   __shared__ double red[8];
-  double a = 0.0, b = 0.0, c = 0.0;
-  for (int i = threadIdx.x; i < P.n_lin_blocks; i += 256) a += P.chi_cur_part[i];
-  for (int i = threadIdx.x; i < P.n_upd_blocks; i += 256) { b += P.chi_new_part[i]; c += P.scale_part[i]; }
-  a = block_sum<256>(a, red);
-  b = block_sum<256>(b, red);
-  c = block_sum<256>(c, red);
-  if (threadIdx.x == 0) { P.scal[0] = a; P.scal[1] = b; P.scal[2] = c; }
+  fold_partials<256>(P, red);
 }
 
-// ---------------------------------------------------------------------------------------------
-// k_control — the accept/reject law of OptimizationAlgorithmLevenberg::solve
-// (levenberg.cpp:119-149) and the iteration bookkeeping of SparseOptimizer::optimize
-// (sparse_optimizer.cpp:386-426), on the device so that no host round trip sits between trials.
-template <bool kFusedReduce>
-__global__ void __launch_bounds__(256) k_control(const DeviceProblem P) {
-  Control *c = P.ctl;
-  if (c->done) return;
-  if (kFusedReduce) {  // single GPU: fold the partial sums here instead of in k_reduce_partials
-    __shared__ double red[8];
-    double a = 0.0, b = 0.0, cc = 0.0;
-    for (int i = threadIdx.x; i < P.n_lin_blocks; i += 256) a += P.chi_cur_part[i];
-    for (int i = threadIdx.x; i < P.n_upd_blocks; i += 256) { b += P.chi_new_part[i]; cc += P.scale_part[i]; }
-    a = block_sum<256>(a, red);
-    b = block_sum<256>(b, red);
-    cc = block_sum<256>(cc, red);
-    if (threadIdx.x == 0) { P.scal[0] = a; P.scal[1] = b; P.scal[2] = cc; }
-  }
-  if (threadIdx.x != 0) return;
-  const double currentChi = P.scal[0];
-  double tempChi = P.scal[1];
-  if (c->outer_iter == 0 && c->qmax == 0) c->chi2_initial = currentChi;
-  const bool fail = c->chol_fail != 0;
-  if (fail) { tempChi = DBL_MAX; c->cholesky_failures++; }
-  double scale = P.scal[2] + c->scale_pose;
-  scale += 1e-3;
-  double rho = (currentChi - tempChi) / scale;
-  if (fail) rho = -1.0;  // a failed factorisation always rejects the step (levenberg.cpp:120-121)
-  bool broke = false, accepted = false;
-  if (rho > 0 && isfinite(tempChi)) {
-    double alpha = 1. - pow((2 * rho - 1), 3);
-    alpha = fmin(alpha, c->good_upper);
-    const double scaleFactor = fmax(c->good_lower, alpha);
-    c->lambda *= scaleFactor;
-    c->ni = 2;
-    c->cur ^= 1;  // discardTop(): the trial buffer becomes the estimate
-    accepted = true;
-  } else {
-    c->lambda *= c->ni;
-    c->ni *= 2;  // pop(): the estimate buffer is simply kept
-    if (!isfinite(c->lambda)) broke = true;
-  }
-  if (!broke) c->qmax++;
-  c->rho = rho;
-  c->temp_chi = tempChi;
-  c->current_chi = accepted ? tempChi : currentChi;
-  const bool again = !broke && rho < 0 && c->qmax < c->max_trials;
-  if (again) {
-    c->need_linearize = 0;
-    return;
-  }
-  const int result = (c->qmax == c->max_trials || rho == 0 || !isfinite(c->lambda))
-                         ? SSBA_SOLVER_TERMINATE : SSBA_SOLVER_OK;
-  if (c->n_records < SSBA_MAX_ITER_RECORDS) {
-    ssba_iter_record &r = c->records[c->n_records++];
-    r.chi2 = c->current_chi; r.lambda = c->lambda; r.trials = c->qmax; r.result = result;
-  }
-  c->last_result = result;
-  c->outer_iter++;
-  c->qmax = 0;
-  c->need_linearize = 1;
-  if (result != SSBA_SOLVER_OK || c->outer_iter >= c->max_iters) c->done = 1;
+__global__ void k_control(const DeviceProblem P) {
+  if (P.ctl->done) return;
+  control_step(P);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1134,27 +1176,23 @@ void launch_linearize(const DeviceProblem &P, cudaStream_t st) {
   else k_linearize<SSBA_JACOBIAN_ANALYTIC><<<P.n_lin_blocks, kLinThreads, 0, st>>>(P);
 }
 
-void launch_hpp_diag(const DeviceProblem &P, cudaStream_t st) {
-  if (P.n_fp > 0) k_hpp_diag<<<div_up(P.n_fp, 4), 128, 0, st>>>(P);
+void launch_fold(const DeviceProblem &P, cudaStream_t st) {
+  if (P.n_fp > 0) k_fold<<<div_up(P.n_fp, 4), 128, 0, st>>>(P);
 }
 
 void launch_maxdiag(const DeviceProblem &P, cudaStream_t st) { k_maxdiag<<<1, 1024, 0, st>>>(P); }
 
 void launch_lambda_init(const DeviceProblem &P, cudaStream_t st) { k_lambda_init<<<1, 1, 0, st>>>(P); }
 
-void launch_prepare_system(const DeviceProblem &P, cudaStream_t st) {
-  const int n_zero = (int)div_up(36LL * P.n_blocks, kPrepThreads), n_pose = (int)div_up(P.n_fp, kPrepThreads / 32);
-  if (n_zero + n_pose > 0) k_prepare_system<<<n_zero + n_pose, kPrepThreads, 0, st>>>(P, n_zero);
-}
-
-void launch_schur(const DeviceProblem &P, cudaStream_t st) {
+void launch_schur(const DeviceProblem &P, bool prefolded, cudaStream_t st) {
   static bool attr_set = false;
   constexpr size_t kDyn = (size_t)kSchurWarps * kSchurRunPairs * 18 * sizeof(double);
   if (!attr_set) {
     cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDyn);
     attr_set = true;
   }
-  if (P.n_units > 0) k_schur<<<div_up(P.n_units, kSchurWarps), 32 * kSchurWarps, kDyn, st>>>(P);
+  const int n_pose = div_up(P.n_fp, kSchurWarps), n_unit = div_up(P.n_units, kSchurWarps);
+  if (n_pose + n_unit > 0) k_schur<<<n_pose + n_unit, 32 * kSchurWarps, kDyn, st>>>(P, n_pose, prefolded ? 1 : 0);
 }
 
 void launch_reduced_solve(const DeviceProblem &P, cudaStream_t st) {
@@ -1167,18 +1205,17 @@ void launch_reduced_solve(const DeviceProblem &P, cudaStream_t st) {
   k_reduced_solve<<<1, kSolveThreads, lay.bytes, st>>>(P, lay);
 }
 
-void launch_update(const DeviceProblem &P, cudaStream_t st) {
-  if (P.n_upd_blocks > 0) k_update<<<P.n_upd_blocks, kLinThreads, 0, st>>>(P);
+void launch_update(const DeviceProblem &P, bool fused_control, cudaStream_t st) {
+  if (P.n_upd_blocks <= 0) return;
+  if (fused_control) k_update<true><<<P.n_upd_blocks, kLinThreads, 0, st>>>(P);
+  else k_update<false><<<P.n_upd_blocks, kLinThreads, 0, st>>>(P);
 }
 
 void launch_reduce_partials(const DeviceProblem &P, cudaStream_t st) {
   k_reduce_partials<<<1, 256, 0, st>>>(P);
 }
 
-void launch_control(const DeviceProblem &P, bool fused_reduce, cudaStream_t st) {
-  if (fused_reduce) k_control<true><<<1, 256, 0, st>>>(P);
-  else k_control<false><<<1, 32, 0, st>>>(P);
-}
+void launch_control(const DeviceProblem &P, cudaStream_t st) { k_control<<<1, 1, 0, st>>>(P); }
 
 void launch_final_chi2(const DeviceProblem &P, double threshold, cudaStream_t st) {
   k_final_chi2<<<P.n_fin_blocks, kLinThreads, 0, st>>>(P, threshold, 0);

@@ -20,7 +20,8 @@ namespace ssba {
 namespace {
 
 constexpr int kMaxLevelCols = kSolveMaxCols;  // ssba_solver_layout.hpp
-constexpr int kSchurRunPairs = 160; // = kSchurRunPairs of k_schur
+constexpr int kSchurRunPairs = 80;  // = kSchurRunPairs of k_schur
+constexpr int kSchurRun = 16;       // = kSchurRun of k_schur
 constexpr int kLinPairs = 128;      // = kLinThreads of k_linearize / k_update
 
 // Symbolic factorisation of the reduced system under one elimination order, plus the schedule
@@ -867,7 +868,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     s.n_lchunks = (int)s.lchunk_slot.size() - 1;
   }
 
-  // ---- Schur work units: a run of <= 32 consecutive free landmarks with the same W pose list
+  // ---- Schur work units: a run of <= kSchurRun consecutive free landmarks with the same W pose list
   // x a chunk of <= 32 of its k(k+1)/2 block pairs (one lane per block pair, one warp per unit)
   {
     auto wcount = [&](int sl) { return lm_k[slots[sl]]; };
@@ -883,7 +884,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
       if (k == 0) { ++sl; continue; }
       int e = sl + 1;
       // the run's W blocks are staged in shared memory by k_schur: at most kSchurRunPairs of them
-      const int max_run = std::max(1, std::min(32, kSchurRunPairs / k));
+      const int max_run = std::max(1, std::min(kSchurRun, kSchurRunPairs / k));
       while (e < s.n_slots && e - sl < max_run && wcount(e) == k && same_list(sl, e, k)) ++e;
       const int npairs = k * (k + 1) / 2;
       for (int c0 = 0; c0 < npairs; c0 += 32) {
