@@ -495,6 +495,7 @@ ssba_status ssba_initialize(ssba_handle *h) {
   P.n_edges_total = g.n_edges;
   P.prog_max_seg = s.prog_max_seg;
   P.n_segments = s.n_segments;
+  P.solve_cluster = s.solve_cluster;
   P.n_units = s.n_units;
   h->initialized = true;
   h->dirty = false;

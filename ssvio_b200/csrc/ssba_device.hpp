@@ -69,6 +69,7 @@ struct DeviceProblem {
   const int32_t *col_diag;         // n_fp: the diagonal block of every column
   const int32_t *prog, *prog_ptr;  // per-level solver program (ssba_structure.cpp build_solver_program)
   int prog_max_seg, n_segments;
+  int solve_cluster;               // CTAs the solver program was dealt over (1, 2, 4, 8)
   // system
   double *W;          // n_pairs x 18, 6x3 row-major  (Hpl blocks)
   double *Hll;        // n_slots x 6 (xx xy xz yy yz zz)

@@ -9,6 +9,7 @@
 //
 // Reference semantics per kernel are cited at each kernel; g2o/ = thirdparty/g2o/g2o/.
 #include <cfloat>
+#include <cstdlib>
 
 #include "ssba_device.hpp"
 #include "ssba_solver_layout.hpp"
@@ -285,7 +286,6 @@ __device__ __forceinline__ double warp_fold_pose(const DeviceProblem &P, int q, 
 }
 // upper-triangle offset of diagonal entry d of the 6x6 block: 6, 12, 17, 21, 24, 26
 __device__ __forceinline__ int hpp_diag_index(int d) { return 6 + d * 6 - d * (d - 1) / 2; }
-__device__ __forceinline__ bool is_hpp_diag(int k) { return k == 6 || k == 12 || k == 17 || k == 21 || k == 24 || k == 26; }
 
 // first slot of an optimize()/step() call: every pose's Hpp partials folded once -> hpp_fold, and
 // the Hpp diagonals -> diag_buf for computeLambdaInit (summed over ranks by the host-enqueued
@@ -338,7 +338,6 @@ __global__ void k_lambda_init(const DeviceProblem P) {
 //       walks every G-th landmark of the run (G = 32 / block pairs lane groups share the run),
 //       accumulating its block in 36 registers; the G partial blocks meet through shuffles and
 //       only the per-unit totals go to the L2-resident reduced system.
-constexpr int kStageWarps = 4;  // warps of k_reduced_solve that issue the cp.async prefetches
 constexpr int kSchurWarps = 4;
 constexpr int kSchurRunPairs = 80;  // W blocks of one run staged in shared memory (= host kSchurRunPairs)
 constexpr int kSchurRun = 16;       // landmarks per run (= host kSchurRun)
@@ -531,12 +530,14 @@ __device__ __forceinline__ double group_reduce(double v, int lane) {
 // the index segment of one level, resolved from its header (ssba_structure.cpp build_solver_program)
 struct LevelSeg {
   int n_cols, n_rounds, n_pairs, n_pf, n_bpf;
+  const int *cta_rptr;  // kSolveMaxCluster + 1: the rounds of CTA c are [cta_rptr[c], cta_rptr[c + 1])
   const int *col_j, *col_b0, *col_bptr, *brow, *round_type, *gt_dst, *gt_slot, *gt_pos, *gt_p0, *gt_p1, *pa,
       *pb, *pf_blk, *pf_slot, *bpf_blk;
   __device__ __forceinline__ explicit LevelSeg(const int *seg) {
     n_cols = seg[0]; n_rounds = seg[1]; n_pairs = seg[2]; n_pf = seg[4]; n_bpf = seg[5];
     const int n_brows = seg[3];
     const int *p = seg + 8;
+    cta_rptr = p; p += kSolveMaxCluster + 1;
     col_j = p; p += n_cols;
     col_b0 = p; p += n_cols;
     col_bptr = p; p += n_cols + 1;
@@ -563,23 +564,73 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 __device__ __forceinline__ void stage_segment(int *dst, const int *src, int n_ints, int tid) {
   for (int i = 4 * tid; i < n_ints; i += 4 * kSolveThreads) cp_async16(dst + i, src + i);
 }
+// ---- bulk asynchronous copy (TMA, cp.async.bulk) completing on an mbarrier: one instruction for a
+// whole level program.  (Measured: it does NOT pay for the 288-byte factor blocks, ~70 cycles per
+// copy through the one TMA unit; those use 16-byte LDGSTS granules or plain loads.)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void stage_wait() {
   asm volatile("cp.async.commit_group;\n" ::);
   asm volatile("cp.async.wait_all;\n" ::: "memory");
 }
 
+// ---- thread-block cluster plumbing of k_reduced_solve: the columns of a level are dealt over the
+// CTAs of the cluster (every SM brings its own shared-memory pipe, which is what bounds the
+// update products).  All rounds of a column run in one CTA, so the inverse diagonal block and
+// its flag stay local (measured: publishing it through DSMEM costs ~2.7 k cycles on the critical
+// path of every level); the finished blocks and y are written into the block cache of EVERY CTA
+// through distributed shared memory, off the critical path, so that all reads stay local.
+__device__ __forceinline__ unsigned cluster_cta_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned dsmem_addr(const void *local_smem, unsigned cta) {
+  unsigned ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"((unsigned)__cvta_generic_to_shared(local_smem)), "r"(cta));
+  return ra;
+}
+__device__ __forceinline__ void dsmem_st2(unsigned ra, double a, double b) {
+  asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(ra), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void dsmem_st1(unsigned ra, double a) {
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(a) : "memory");
+}
+__device__ __forceinline__ void dsmem_st_int(unsigned ra, int v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(ra), "r"(v) : "memory");
+}
 #ifdef SSBA_SOLVER_TRACE
 __device__ long long g_solver_trace[4096];
-#define TRACE(i) do { if (threadIdx.x == 0 && (i) < 4096) g_solver_trace[(i)] = clock64(); } while (0)
+#define TRACE(i) do { if (threadIdx.x == 0 && blockIdx.x == 0 && (i) < 4096) g_solver_trace[(i)] = clock64(); } while (0)
 #define TRACE2(sgv, k) do { if (lane == 0 && ((sgv) == 6 || (sgv) == 18) && rd < 16) g_solver_trace[3000 + ((sgv) == 18 ? 512 : 0) + 16 * rd + (k)] = clock64(); } while (0)
 #else
 #define TRACE(i) do { } while (0)
 #define TRACE2(sgv, k) do { } while (0)
 #endif
 
+template <int kCluster>
 __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DeviceProblem P, const SolverSmemLayout lay) {
   Control *ctl = P.ctl;
-  if (ctl->done) return;
+  if (ctl->done) return;  // uniform over the cluster
+  const int cta = kCluster > 1 ? (int)cluster_cta_rank() : 0;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *s_linv = reinterpret_cast<double *>(smem_raw);                          // kSolveMaxCols x 36
   volatile int *s_flag = reinterpret_cast<volatile int *>(smem_raw + lay.off_flag);  // kSolveMaxCols
@@ -589,6 +640,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
   const int staged = lay.staged;
   __shared__ int s_fail;
   __shared__ double red[kSolveThreads / 32];
+  __shared__ __align__(8) unsigned long long s_bar[2];  // prefetch use u completes on s_bar[u & 1], parity (u >> 1) & 1
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = kSolveThreads / 32;
   const int g = lane / 6, r = lane - 6 * g;  // lanes 30, 31: g == 5, never active
@@ -598,11 +650,16 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
   const double *bp = bs + 6 * (size_t)P.n_fp;
   const int seg_stride = (P.prog_max_seg + 3) & ~3;
   const int NSEG = P.n_segments;
-  if (tid == 0) s_fail = 0;
+  if (tid == 0) {
+    s_fail = 0;
+    mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   if (tid < kSolveMaxCols) s_flag[tid] = 0;
   if (staged && NSEG > 0) stage_segment(s_prog, P.prog + P.prog_ptr[0], P.prog_ptr[1] - P.prog_ptr[0], tid);
   stage_wait();
   __syncthreads();
+  if (kCluster > 1) cluster_barrier();  // flags / s_fail of every CTA initialised before anyone publishes
   // a block reference r >= 0 is a shared-memory slot, r < 0 is block -1-r in global memory
   auto deref = [&](int ref) -> const double * {
     return ref >= 0 ? s_slots + 36 * ref : L + 36 * (size_t)(-1 - ref);
@@ -616,23 +673,17 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
     const LevelSeg S(staged ? s_prog + (sg & 1) * seg_stride : P.prog + P.prog_ptr[sg]);
     // asynchronously: the next segment's program, and the initial values (Schur complement) of
     // the next level's blocks into their cache slots
-    // Issued by the last four warps only: the first rounds of a level (the DIAG rounds on its
-    // critical path) go to the first warps, which start at once.
-    if (warp >= NW - kStageWarps) {
-      const int st = tid - 32 * (NW - kStageWarps);
-      if (staged && sg + 1 < NSEG) {
-        const int *src = P.prog + P.prog_ptr[sg + 1];
-        int *dstp = s_prog + ((sg + 1) & 1) * seg_stride;
-        const int n_ints = P.prog_ptr[sg + 2] - P.prog_ptr[sg + 1];
-        for (int i = 4 * st; i < n_ints; i += 4 * 32 * kStageWarps) cp_async16(dstp + i, src + i);
-      }
-      for (int i = st; i < 18 * S.n_pf; i += 32 * kStageWarps) {
-        const int e = i / 18, o = i - 18 * e;
-        const int slot = S.pf_slot[e];
-        if (slot >= 0) cp_async16(s_slots + 36 * slot + 2 * o, L + 36 * (size_t)S.pf_blk[e] + 2 * o);
-      }
+    // Only the program is staged ahead: the initial value of a block (its Schur complement
+    // entry) is read from global memory when its round starts and is not needed before the
+    // round's update products are done, so that latency hides by itself.
+    if (tid == kSolveThreads - 1) {
+      const bool more = staged && sg + 1 < NSEG;
+      const unsigned bytes = more ? 4u * (unsigned)(P.prog_ptr[sg + 2] - P.prog_ptr[sg + 1]) : 0u;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the buffer's last generic reads are two levels old
+      mbar_arrive_expect_tx(&s_bar[sg & 1], bytes);
+      if (more) bulk_g2s(s_prog + ((sg + 1) & 1) * seg_stride, P.prog + P.prog_ptr[sg + 1], bytes, &s_bar[sg & 1]);
     }
-    for (int rd = warp; rd < S.n_rounds; rd += NW) {
+    for (int rd = S.cta_rptr[cta] + warp, rd1 = S.cta_rptr[cta + 1]; rd < rd1; rd += NW) {
       const int type = S.round_type[rd];
       const int kind = type & 3;
       const bool reduce = (type & 4) != 0;
@@ -649,7 +700,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
 #pragma unroll
         for (int c = 0; c < 6; ++c) v[c] = 0.0;
         if (active && (!reduce || g == 0)) {
-          const double2 *d2 = reinterpret_cast<const double2 *>(Ds + 6 * r);
+          const double2 *d2 = reinterpret_cast<const double2 *>(D + 6 * r);
           const double2 t0 = d2[0], t1 = d2[1], t2 = d2[2];
           v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y; v[4] = t2.x; v[5] = t2.y;
         }
@@ -658,13 +709,27 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
         for (int c = 0; c < 6; ++c) acc[c] = 0.0;
         TRACE2(sg, 5);
         for (int p = p0; p < p1; ++p) {
-          const double2 *A2 = reinterpret_cast<const double2 *>(deref(S.pa[p]) + 6 * r);
-          const double2 *B2 = reinterpret_cast<const double2 *>(deref(S.pb[p]));
-          const double2 a0 = A2[0], a1 = A2[1], a2 = A2[2];
+          const int ra = S.pa[p], rb = S.pb[p];
+          if (ra >= 0 && rb >= 0) {
+            // both blocks in the shared-memory cache (the usual case): explicit LDS instead of
+            // generic loads
+            const double2 *A2 = reinterpret_cast<const double2 *>(s_slots + 36 * ra + 6 * r);
+            const double2 *B2 = reinterpret_cast<const double2 *>(s_slots + 36 * rb);
+            const double2 a0 = A2[0], a1 = A2[1], a2 = A2[2];
 #pragma unroll
-          for (int c = 0; c < 6; ++c) {
-            const double2 b0 = B2[3 * c], b1 = B2[3 * c + 1], b2 = B2[3 * c + 2];
-            acc[c] += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y;
+            for (int c = 0; c < 6; ++c) {
+              const double2 b0 = B2[3 * c], b1 = B2[3 * c + 1], b2 = B2[3 * c + 2];
+              acc[c] += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y;
+            }
+          } else {
+            const double2 *A2 = reinterpret_cast<const double2 *>(deref(ra) + 6 * r);
+            const double2 *B2 = reinterpret_cast<const double2 *>(deref(rb));
+            const double2 a0 = A2[0], a1 = A2[1], a2 = A2[2];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+              const double2 b0 = B2[3 * c], b1 = B2[3 * c + 1], b2 = B2[3 * c + 2];
+              acc[c] += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y;
+            }
           }
         }
         TRACE2(sg, 1);
@@ -726,9 +791,13 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
             double2 *l2 = reinterpret_cast<double2 *>(linv), *d2 = reinterpret_cast<double2 *>(D);
 #pragma unroll
             for (int i = 0; i < 18; ++i) { const double2 t = make_double2(X[2 * i], X[2 * i + 1]); l2[i] = t; d2[i] = t; }
-            if (bad) s_fail = 1;
+            if (bad) {
+              if (kCluster == 1) s_fail = 1;
+              else for (int cc = 0; cc < kCluster; ++cc) dsmem_st_int(dsmem_addr(&s_fail, (unsigned)cc), 1);
+            }
           }
           TRACE2(sg, 3);
+          // every round of a column runs in the CTA of its DIAG round: the inverse stays local
           __threadfence_block();
           __syncwarp();
           if (active && r == 0) s_flag[pos] = stamp;
@@ -749,8 +818,16 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
             double2 *d2 = reinterpret_cast<double2 *>(D + 6 * r);
             d2[0] = make_double2(x[0], x[1]); d2[1] = make_double2(x[2], x[3]); d2[2] = make_double2(x[4], x[5]);
             if (slot >= 0) {
-              double2 *s2 = reinterpret_cast<double2 *>(Ds + 6 * r);
-              s2[0] = make_double2(x[0], x[1]); s2[1] = make_double2(x[2], x[3]); s2[2] = make_double2(x[4], x[5]);
+              if (kCluster == 1) {
+                double2 *s2 = reinterpret_cast<double2 *>(Ds + 6 * r);
+                s2[0] = make_double2(x[0], x[1]); s2[1] = make_double2(x[2], x[3]); s2[2] = make_double2(x[4], x[5]);
+              } else {
+#pragma unroll
+                for (int cc = 0; cc < kCluster; ++cc) {
+                  const unsigned ra = dsmem_addr(Ds + 6 * r, (unsigned)cc);
+                  dsmem_st2(ra, x[0], x[1]); dsmem_st2(ra + 16, x[2], x[3]); dsmem_st2(ra + 32, x[4], x[5]);
+                }
+              }
             }
           }
         }
@@ -774,15 +851,24 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
           const double sc = __shfl_sync(0xffffffffu, sv, gl + c);
           if (active && c <= r) y += linv[6 * r + c] * sc;
         }
-        if (active) xs[6 * j + r] = y;
+        if (active) {
+          if (kCluster == 1 || !lay.x_in_smem) xs[6 * j + r] = y;
+          else {
+#pragma unroll
+            for (int cc = 0; cc < kCluster; ++cc) dsmem_st1(dsmem_addr(xs + 6 * j + r, (unsigned)cc), y);
+          }
+        }
       }
       TRACE2(sg, 6);
     }
     TRACE(2 + 3 * sg);
-    stage_wait();
-    __syncthreads();
+    mbar_wait(&s_bar[sg & 1], (unsigned)(sg >> 1) & 1u);
+    if (kCluster == 1) __syncthreads(); else cluster_barrier();
     TRACE(3 + 3 * sg);
   }
+  // the backward pass and the pose update are latency-bound chains: CTA 0 runs them alone (the
+  // factor is complete in global memory, and nobody touches another CTA's memory from here on)
+  if (cta != 0) return;
   const bool fail = s_fail != 0;
 
   if (!fail) {
@@ -792,17 +878,19 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
     const int half = lay.n_slots / 2;
     for (int sg = NSEG - 1; sg >= 1; --sg) {
       const LevelSeg S(staged ? s_prog + (sg & 1) * seg_stride : P.prog + P.prog_ptr[sg]);
-      if (warp >= NW - kStageWarps) {
-        const int st = tid - 32 * (NW - kStageWarps);
-        if (staged && sg > 1) {
-          const int *src = P.prog + P.prog_ptr[sg - 1];
-          int *dstp = s_prog + ((sg - 1) & 1) * seg_stride;
-          const int n_ints = P.prog_ptr[sg] - P.prog_ptr[sg - 1];
-          for (int i = 4 * st; i < n_ints; i += 4 * 32 * kStageWarps) cp_async16(dstp + i, src + i);
-        }
+      const int use = NSEG + (NSEG - 1 - sg);  // prefetch uses continue the numbering of the forward pass
+      if (tid == kSolveThreads - 1) {
+        const bool more = staged && sg > 1;
+        const unsigned bytes = more ? 4u * (unsigned)(P.prog_ptr[sg] - P.prog_ptr[sg - 1]) : 0u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive_expect_tx(&s_bar[use & 1], bytes);
+        if (more) bulk_g2s(s_prog + ((sg - 1) & 1) * seg_stride, P.prog + P.prog_ptr[sg - 1], bytes, &s_bar[use & 1]);
+      }
+      if (warp >= NW / 2) {  // the columns of a level keep the first warps busy
+        const int st = tid - 32 * (NW / 2);
         const int nb = S.n_bpf < half ? S.n_bpf : half;
         double *dstb = s_slots + 36 * (size_t)(((sg - 1) & 1) * half);
-        for (int i = st; i < 18 * nb; i += 32 * kStageWarps) {
+        for (int i = st; i < 18 * nb; i += 32 * (NW / 2)) {
           const int e = i / 18, o = i - 18 * e;
           cp_async16(dstb + 36 * e + 2 * o, L + 36 * (size_t)S.bpf_blk[e] + 2 * o);
         }
@@ -838,6 +926,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
         if (lane < 6) xs[6 * j + r] = xv;
       }
       stage_wait();
+      mbar_wait(&s_bar[use & 1], (unsigned)(use >> 1) & 1u);
       __syncthreads();
       TRACE(3 * NSEG + 1 + (NSEG - sg));
     }
@@ -936,7 +1025,7 @@ __device__ __forceinline__ void fold_partials(const DeviceProblem &P, double *re
     for (int base = threadIdx.x; base < n; base += 8 * NT) {
       double v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = base + j * NT < n ? part[base + j * NT] : 0.0;
+      for (int j = 0; j < 8; ++j) v[j] = base + j * NT < n ? __ldcg(part + base + j * NT) : 0.0;  // written by other CTAs of this launch
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc += v[j];
     }
@@ -1198,11 +1287,24 @@ void launch_schur(const DeviceProblem &P, bool prefolded, cudaStream_t st) {
 void launch_reduced_solve(const DeviceProblem &P, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_reduced_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveMaxDynSmem);
+    cudaFuncSetAttribute(k_reduced_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveMaxDynSmem);
+    cudaFuncSetAttribute(k_reduced_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveMaxDynSmem);
+    cudaFuncSetAttribute(k_reduced_solve<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveMaxDynSmem);
+    cudaFuncSetAttribute(k_reduced_solve<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveMaxDynSmem);
     attr_set = true;
   }
   const SolverSmemLayout lay = solver_smem_layout(P.n_fp, P.prog_max_seg);
-  k_reduced_solve<<<1, kSolveThreads, lay.bytes, st>>>(P, lay);
+  const int c = P.solve_cluster;  // the program was built for this many CTAs
+  if (c == 1) { k_reduced_solve<1><<<1, kSolveThreads, lay.bytes, st>>>(P, lay); return; }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(c); cfg.blockDim = dim3(kSolveThreads); cfg.dynamicSmemBytes = lay.bytes; cfg.stream = st;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = c; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  if (c == 2) cudaLaunchKernelEx(&cfg, k_reduced_solve<2>, P, lay);
+  else if (c == 4) cudaLaunchKernelEx(&cfg, k_reduced_solve<4>, P, lay);
+  else cudaLaunchKernelEx(&cfg, k_reduced_solve<8>, P, lay);
 }
 
 void launch_update(const DeviceProblem &P, bool fused_control, cudaStream_t st) {

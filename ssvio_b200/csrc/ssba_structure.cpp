@@ -17,6 +17,15 @@
 
 namespace ssba {
 
+int solver_cluster_size(int n_fp) {
+  static const int configured = [] {
+    const char *e = std::getenv("SSBA_SOLVE_CLUSTER");
+    const int c = e ? std::atoi(e) : 4;
+    return (c == 1 || c == 2 || c == 4 || c == 8) ? c : 4;
+  }();
+  return n_fp >= 32 ? configured : 1;
+}
+
 namespace {
 
 constexpr int kMaxLevelCols = kSolveMaxCols;  // ssba_solver_layout.hpp
@@ -183,6 +192,7 @@ bool symbolic_factor(int n, const std::vector<std::vector<int>> &adj, const std:
 // A block with many update pairs gets a round of its own with its pairs split five ways
 // (REDUCE flag: the groups' partial sums are added before group 0 finishes the block).
 //   header[8] = {n_cols, n_rounds, n_pairs, n_brows, n_pf, n_bpf, 0, 0}
+//   cta_rptr[kSolveMaxCluster + 1]             rounds [cta_rptr[c], cta_rptr[c+1]) belong to CTA c of the cluster
 //   col_j[n_cols] col_b0[n_cols] col_bptr[n_cols+1] brow[n_brows]          (backward pass)
 //   round_type[n_rounds]                       bits 0-1: 0 DIAG 1 SUB 2 VEC, bit 2: REDUCE
 //   gt_dst[5 n_rounds] gt_slot[..] gt_pos[..] gt_p0[..] gt_p1[..]           (group tasks)
@@ -194,6 +204,7 @@ bool symbolic_factor(int n, const std::vector<std::vector<int>> &adj, const std:
 // r < 0 is block -1-r in global memory.
 void build_solver_program(Structure &s) {
   constexpr int kSplitPairs = 10;  // blocks with more update pairs get a REDUCE round
+  constexpr int kSplitDiag = 1;    // ... diagonal blocks already with two
   const int n = s.n_fp, NL = s.n_levels;
   std::vector<int> level_of(n, 0);
   for (int lv = 0; lv < NL; ++lv)
@@ -206,13 +217,30 @@ void build_solver_program(Structure &s) {
   // ---- rounds of every level (slot-independent part)
   struct GT { int dst, pos, p0, p1; };             // pairs index the level-local pair arrays
   struct Round { int type; GT g[5]; };
-  struct LevelPlan { std::vector<Round> rounds; std::vector<std::pair<int, int>> pairs; /* (a block, b block | column) */ };
+  struct LevelPlan { std::vector<Round> rounds; std::vector<std::pair<int, int>> pairs; /* (a block, b block | column) */ int cta_rptr[kSolveMaxCluster + 1]; };
   std::vector<LevelPlan> plan(NL);
+  const int C = solver_cluster_size(n);
+  s.solve_cluster = C;
   for (int lv = 0; lv < NL; ++lv) {
     LevelPlan &lp = plan[lv];
     const int c0 = s.level_ptr[lv], nc = s.level_ptr[lv + 1] - c0;
     const int t0 = s.ltask_ptr[lv], nt = s.ltask_ptr[lv + 1] - t0;
-    std::vector<GT> diag, sub, vec, big_diag, big_sub, big_vec;
+    // the columns of the level are dealt over the CTAs of the cluster, heaviest first onto the
+    // least loaded CTA; every task of a column runs in the column's CTA (the inverse diagonal
+    // block it waits for never leaves that CTA)
+    std::vector<int> cta_of_pos(nc, 0);
+    if (C > 1) {
+      std::vector<long long> w(nc, 0), load(C, 0);
+      for (int t = 0; t < nt; ++t) w[s.task_pos[t0 + t]] += 2 + (s.task_pair_ptr[t0 + t + 1] - s.task_pair_ptr[t0 + t]);
+      std::vector<int> order(nc);
+      std::iota(order.begin(), order.end(), 0);
+      std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return w[x] > w[y]; });
+      for (int pos : order) {
+        const int c = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        cta_of_pos[pos] = c; load[c] += w[pos];
+      }
+    }
+    std::vector<std::vector<GT>> diag(C), sub(C), vec(C), big_diag(C), big_sub(C), big_vec(C);
     for (int t = 0; t < nt; ++t) {
       const int d = s.task_dst[t0 + t], pos = s.task_pos[t0 + t];
       GT gt{d, pos, (int)lp.pairs.size(), 0};
@@ -223,12 +251,25 @@ void build_solver_program(Structure &s) {
         for (int rr = s.row_ptr[j]; rr < s.row_ptr[j + 1]; ++rr) lp.pairs.emplace_back(s.row_blk[rr], -1 - s.row_col[rr]);
       }
       gt.p1 = (int)lp.pairs.size();
-      const bool big = gt.p1 - gt.p0 > kSplitPairs;
-      if (d < 0) (big ? big_vec : vec).push_back(gt);
-      else if (s.blk_row[d] == s.blk_col[d]) (big ? big_diag : diag).push_back(gt);
-      else (big ? big_sub : sub).push_back(gt);
+      const bool is_diag = d >= 0 && s.blk_row[d] == s.blk_col[d];
+      const int c = cta_of_pos[pos];
+      if (d < 0) vec[c].push_back(gt);
+      else if (is_diag) (gt.p1 - gt.p0 > kSplitDiag ? big_diag : diag)[c].push_back(gt);
+      else sub[c].push_back(gt);
     }
-    (void)nc;
+    // SUB / VEC tasks with more than kSplitPairs pairs get a round of their own (pairs split five
+    // ways).  Measured on B200: splitting more of them to fill idle warps makes the level SLOWER
+    // (the update products are bound by the SM's shared-memory pipe, and a split round wastes lanes).
+    auto npairs = [](const GT &g) { return g.p1 - g.p0; };
+    auto by_size = [&](std::vector<GT> &v) { std::stable_sort(v.begin(), v.end(), [&](const GT &x, const GT &y) { return npairs(x) > npairs(y); }); };
+    for (int c = 0; c < C; ++c) {
+      by_size(diag[c]); by_size(sub[c]); by_size(vec[c]);
+      int ns = 0, nv = 0;
+      while (ns < (int)sub[c].size() && npairs(sub[c][ns]) > kSplitPairs) ++ns;
+      while (nv < (int)vec[c].size() && npairs(vec[c][nv]) > kSplitPairs) ++nv;
+      big_sub[c].assign(sub[c].begin(), sub[c].begin() + ns); sub[c].erase(sub[c].begin(), sub[c].begin() + ns);
+      big_vec[c].assign(vec[c].begin(), vec[c].begin() + nv); vec[c].erase(vec[c].begin(), vec[c].begin() + nv);
+    }
     auto pack5 = [&](const std::vector<GT> &v, int type) {
       for (size_t i = 0; i < v.size(); i += 5) {
         Round r{type, {}};
@@ -247,27 +288,44 @@ void build_solver_program(Structure &s) {
         lp.rounds.push_back(r);
       }
     };
-    // order matters for the wait-free argument: every DIAG round precedes every SUB / VEC round
-    split5(big_diag, 0); pack5(diag, 0);
-    split5(big_sub, 1); pack5(sub, 1);
-    split5(big_vec, 2); pack5(vec, 2);
+    // The DIAG rounds sit on the critical path of the level (every other round of a column waits
+    // for the inverse they publish): a diagonal block with more than kSplitDiag pairs gets its
+    // pairs split five ways.  SUB / VEC tasks are packed five of similar size per round (a
+    // round lasts as long as its longest group), and the rounds are dealt to the warps
+    // heaviest first.  Order matters for the wait-free argument: inside a CTA every DIAG round
+    // precedes every SUB / VEC round.
+    auto cost = [&](const Round &r) {
+      int m = 0;
+      for (int k = 0; k < 5; ++k) if (r.g[k].dst >= 0) m = std::max(m, r.g[k].p1 - r.g[k].p0);
+      return ((r.type & 3) == 2 ? 1 : 3) * m + ((r.type & 4) ? 2 : 0);
+    };
+    for (int c = 0; c <= kSolveMaxCluster; ++c) lp.cta_rptr[c] = 0;
+    for (int c = 0; c < C; ++c) {
+      lp.cta_rptr[c] = (int)lp.rounds.size();
+      split5(big_diag[c], 0); pack5(diag[c], 0);
+      const size_t n_diag_rounds = lp.rounds.size();
+      split5(big_sub[c], 1); pack5(sub[c], 1);
+      split5(big_vec[c], 2); pack5(vec[c], 2);
+      std::stable_sort(lp.rounds.begin() + n_diag_rounds, lp.rounds.end(), [&](const Round &x, const Round &y) { return cost(x) > cost(y); });
+    }
+    for (int c = C; c <= kSolveMaxCluster; ++c) lp.cta_rptr[c] = (int)lp.rounds.size();
   }
   // ---- pass 1: segment sizes
   std::vector<int> seg_size(NL + 1, 0);
-  seg_size[0] = 8 + 1 + 2 * (NL > 0 ? level_blocks(0) : 0);
+  seg_size[0] = 8 + (kSolveMaxCluster + 1) + 1;
   for (int lv = 0; lv < NL; ++lv) {
     const int c0 = s.level_ptr[lv], nc = s.level_ptr[lv + 1] - c0;
     int nb = 0;
     for (int t = 0; t < nc; ++t) { const int j = s.level_col[c0 + t]; nb += s.col_ptr[j + 1] - s.col_ptr[j] - 1; }
-    const int npf = lv + 1 < NL ? level_blocks(lv + 1) : 0;
+    const int npf = 0;  // initial values are read from global memory by the rounds themselves
     const int nbpf = lv > 0 ? level_blocks(lv - 1) : 0;
     const int nr = (int)plan[lv].rounds.size();
-    seg_size[lv + 1] = 8 + 2 * nc + (nc + 1) + nb + nr + 25 * nr + 2 * (int)plan[lv].pairs.size() + 2 * npf + nbpf;
+    seg_size[lv + 1] = 8 + (kSolveMaxCluster + 1) + 2 * nc + (nc + 1) + nb + nr + 25 * nr + 2 * (int)plan[lv].pairs.size() + 2 * npf + nbpf;
   }
   s.prog_max_seg = 0;
   for (int v : seg_size) s.prog_max_seg = std::max(s.prog_max_seg, (v + 3) & ~3);
   const SolverSmemLayout lay = solver_smem_layout(n, s.prog_max_seg);
-  // ---- slot plan: block (i,k) is resident from the level before its column's (prefetch) until
+  // ---- slot plan: block (i,k) is resident from its column's level (where it is written) until
   // the level of its row i, where it is read for the last time
   std::vector<int32_t> slot_of(s.n_blocks, -1);
   {
@@ -275,11 +333,10 @@ void build_solver_program(Structure &s) {
     for (int v = lay.n_slots - 1; v >= 0; --v) free_list.push_back(v);
     std::vector<std::vector<int>> free_after(NL);
     for (int lv = 0; lv < NL; ++lv) {
-      // blocks of level lv are allocated when level lv-1 starts; slots released after lv-2
-      if (lv >= 2) for (int b : free_after[lv - 2]) free_list.push_back(slot_of[b]);
+      if (lv >= 1) for (int b : free_after[lv - 1]) free_list.push_back(slot_of[b]);
       for (int t = s.level_ptr[lv]; t < s.level_ptr[lv + 1]; ++t) {
         const int j = s.level_col[t];
-        for (int b = s.col_ptr[j + 1] - 1; b >= s.col_ptr[j]; --b) {
+        for (int b = s.col_ptr[j + 1] - 1; b > s.col_ptr[j]; --b) {  // the diagonal block is never a source
           if (free_list.empty()) break;
           slot_of[b] = free_list.back(); free_list.pop_back();
           free_after[level_of[s.blk_row[b]]].push_back(b);
@@ -303,10 +360,9 @@ void build_solver_program(Structure &s) {
   };
   auto close_seg = [&]() { while (P.size() % 4) P.push_back(0); s.prog_ptr.push_back((int32_t)P.size()); };
   {  // prologue
-    const int npf = NL > 0 ? level_blocks(0) : 0;
-    P.insert(P.end(), {0, 0, 0, 0, npf, 0, 0, 0});
+    P.insert(P.end(), {0, 0, 0, 0, 0, 0, 0, 0});
+    for (int c = 0; c <= kSolveMaxCluster; ++c) P.push_back(0);  // cta_rptr
     P.push_back(0);  // col_bptr[0]
-    emit_level_blocks(0, true);
     close_seg();
   }
   s.solver_rounds = 0;
@@ -315,11 +371,12 @@ void build_solver_program(Structure &s) {
     const int c0 = s.level_ptr[lv], nc = s.level_ptr[lv + 1] - c0;
     int nb = 0;
     for (int t = 0; t < nc; ++t) { const int j = s.level_col[c0 + t]; nb += s.col_ptr[j + 1] - s.col_ptr[j] - 1; }
-    const int npf = lv + 1 < NL ? level_blocks(lv + 1) : 0;
+    const int npf = 0;
     const int nbpf = lv > 0 ? level_blocks(lv - 1) : 0;
     const int nr = (int)lp.rounds.size(), np = (int)lp.pairs.size();
     s.solver_rounds += nr;
     P.insert(P.end(), {nc, nr, np, nb, npf, nbpf, 0, 0});
+    for (int c = 0; c <= kSolveMaxCluster; ++c) P.push_back(lp.cta_rptr[c]);
     for (int t = 0; t < nc; ++t) P.push_back(s.level_col[c0 + t]);
     for (int t = 0; t < nc; ++t) P.push_back(s.col_ptr[s.level_col[c0 + t]]);
     int acc = 0;
@@ -334,7 +391,6 @@ void build_solver_program(Structure &s) {
     for (const Round &r : lp.rounds) for (int k = 0; k < 5; ++k) P.push_back(r.g[k].p1);
     for (auto &ab : lp.pairs) P.push_back(ref(ab.first));
     for (auto &ab : lp.pairs) P.push_back(ab.second >= 0 ? ref(ab.second) : -1 - ab.second);  // VEC: column k
-    emit_level_blocks(lv + 1, true);
     emit_level_blocks(lv - 1, false);
     close_seg();
   }

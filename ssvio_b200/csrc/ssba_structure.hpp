@@ -105,6 +105,7 @@ struct Structure {
   std::vector<int32_t> prog, prog_ptr;
   int prog_max_seg = 0;               // ints in the largest level segment
   int n_segments = 0;                 // n_levels + 1 (prologue)
+  int solve_cluster = 1;              // CTAs the rounds of every level are dealt over
   int solver_slots = 0, solver_cached_blocks = 0;  // shared-memory factor cache plan
   int solver_rounds = 0;              // warp rounds of the factorisation
   std::vector<int32_t> row_ptr;       // n_fp + 1: strictly-lower blocks by row (forward solve)
