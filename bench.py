@@ -266,21 +266,23 @@ def run_ssba(args):
         total_ms = float(t.item())
     value = iters * args.steps / (total_ms * 1e-3)
 
-    # ---------------- per-phase device time (separate profiled pass: event pairs around phases)
-    popt = ba.BundleAdjuster(device_id=local_rank, stream=stream, rank=rank, world_size=world, nccl_id=None, profile=True) if not multi else None
-    phases = None
-    if popt is not None:
-        popt.set_graph(g); popt.initialize_optimization()
-        for _ in range(3):
-            popt.reset_state(); popt.optimize_nowait_report(iters)
-        popt.profile_reset()
-        for _ in range(args.steps):
-            flush_l2(); popt.reset_state(); popt.optimize_nowait_report(iters)
-        p = popt.profile()
-        phases = {"linearize": (p.ms_linearize, p.n_linearize), "schur": (p.ms_schur, p.n_schur),
-                  "reduced_solve": (p.ms_reduced_solve, p.n_reduced_solve),
-                  "update_chi2": (p.ms_update_chi2, p.n_update_chi2)}
-        popt.close()
+    # ---------------- per-phase device time (separate profiled pass: event pairs around phases,
+    # recorded by the library on its launch stream; same handle, so the same NCCL communicator)
+    opt.set_profiling(True)
+    for _ in range(3):
+        flush_l2(); step_resident()
+    barrier_sync()
+    opt.profile_reset()
+    for _ in range(args.steps):
+        flush_l2(); step_resident()
+    barrier_sync()
+    p = opt.profile()
+    opt.set_profiling(False)
+    phases = {"linearize": (p.ms_linearize, p.n_linearize), "schur": (p.ms_schur, p.n_schur),
+              "reduced_solve": (p.ms_reduced_solve, p.n_reduced_solve),
+              "update_chi2": (p.ms_update_chi2, p.n_update_chi2)}
+    if multi:
+        phases["allreduce"] = (p.ms_allreduce, p.n_allreduce)
 
     # ---------------- e2e: host buffers in, host buffers out, every step
     def pin(a):
@@ -347,6 +349,9 @@ def run_ssba(args):
             # dominant kernel = the phase with the largest share of the step
             name = max(phases, key=lambda k: phases[k][0])
             ms, n = phases[name]
+            if name == "allreduce":  # several GPUs: report the dominant KERNEL, the exchange is in phase_ms_per_step
+                name = max((k for k in phases if k != "allreduce"), key=lambda k: phases[k][0])
+            ms, n = phases[name]
             alg = {  # algorithmic bytes per launch (DESIGN.md "Kernels"), whole graph
                 "linearize": 28 * g.n_edges + 24 * g.n_points + 56 * g.n_poses + 144 * info.n_pairs + 72 * g.n_points,
                 "schur": 144 * info.n_pairs + 72 * g.n_points + 288 * nnz_s + 48 * g.n_poses,
@@ -356,7 +361,8 @@ def run_ssba(args):
             dur = ms / max(n, 1) * 1e-3
             achieved = alg / dur / 1e9
             roofline = {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                        "frac": achieved / peak, "traffic": ncu_traffic(name) if args.workload == WORKLOAD and not multi else None,
+                        "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": alg, "avg_launch_ms": ms / max(n, 1),
                         "phase_ms_per_step": {k: v[0] / args.steps for k, v in phases.items()}}
         line = {
@@ -379,6 +385,16 @@ def run_ssba(args):
     if multi:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
+    ncu --set full capture of this workload (profiles/r1_ncu_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")) as f:
+            return json.load(f)["bytes_per_launch"].get(kernel.replace("_chi2", ""))
+    except (OSError, ValueError, KeyError):
+        return None
 
 
 def main():

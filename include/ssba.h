@@ -244,6 +244,10 @@ ssba_status ssba_plan_shards(int32_t n_poses, const uint8_t *pose_fixed, int32_t
 
 /* ---- instrumentation --------------------------------------------------------------- */
 
+/* Turn the per-phase CUDA-event timers on or off after creation (ssba_options::profile sets
+ * the initial state).  The timers add event records to the stream, so benchmarks time with
+ * them off and profile in a separate pass. */
+ssba_status ssba_set_profiling(ssba_handle *h, int32_t on);
 ssba_status ssba_profile_get(ssba_handle *h, ssba_profile *out);
 ssba_status ssba_profile_reset(ssba_handle *h);
 

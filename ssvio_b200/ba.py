@@ -33,7 +33,8 @@ ABI_SYMBOLS = [
     "ssba_nccl_unique_id", "ssba_set_cameras", "ssba_set_poses", "ssba_set_points",
     "ssba_set_edges", "ssba_initialize", "ssba_optimize", "ssba_step", "ssba_reset_state",
     "ssba_get_poses", "ssba_get_points", "ssba_get_edge_errors", "ssba_chi2",
-    "ssba_count_outliers", "ssba_optimize_rounds", "ssba_plan_shards", "ssba_profile_get", "ssba_profile_reset", "ssba_get_problem_info",
+    "ssba_count_outliers", "ssba_optimize_rounds", "ssba_plan_shards", "ssba_set_profiling", "ssba_profile_get",
+    "ssba_profile_reset", "ssba_get_problem_info",
     "ssba_version",
 ]
 
@@ -124,6 +125,7 @@ def load_library():
     lib.ssba_optimize_rounds.argtypes = [H, C.c_int32, C.c_int32, C.c_double, C.c_double, C.POINTER(C.c_int32),
                                          C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(Report)]
     lib.ssba_plan_shards.argtypes = [C.c_int32, bp, C.c_int32, bp, C.c_int32, ip, ip, C.c_int32, ip]
+    lib.ssba_set_profiling.argtypes = [H, C.c_int32]
     lib.ssba_profile_get.argtypes = [H, C.POINTER(Profile)]
     lib.ssba_profile_reset.argtypes = [H]
     lib.ssba_get_problem_info.argtypes = [H, C.POINTER(ProblemInfo)]
@@ -320,6 +322,9 @@ class BundleAdjuster:
 
     def profile_reset(self):
         self._check(self.lib.ssba_profile_reset(self._h))
+
+    def set_profiling(self, on: bool):
+        self._check(self.lib.ssba_set_profiling(self._h, 1 if on else 0))
 
     def problem_info(self) -> ProblemInfo:
         p = ProblemInfo()

@@ -374,12 +374,17 @@ ssba_status ssba_set_edges(ssba_handle *h, int32_t n, const int32_t *pose_idx, c
   if (n < 0 || (n > 0 && (!pose_idx || !point_idx || !uv))) return fail(h, SSBA_ERR_INVALID_ARG, "set_edges: bad arguments");
   HostGraph &g = h->g;
   g.n_edges = n;
-  g.e_pose.assign(pose_idx, pose_idx + n);
-  g.e_point.assign(point_idx, point_idx + n);
-  if (cam_idx) g.e_cam.assign(cam_idx, cam_idx + n); else g.e_cam.assign(n, 0);
-  g.e_uv.assign(uv, uv + 2 * (size_t)n);
-  if (info) g.e_info.assign(info, info + 3 * (size_t)n); else g.e_info.clear();
-  if (huber_delta) g.e_delta.assign(huber_delta, huber_delta + n); else g.e_delta.clear();
+  // the caller keeps its arrays: copy them (on the host thread pool, several megabytes per window)
+  g.e_pose.resize(n); g.e_point.resize(n); g.e_cam.resize(n); g.e_uv.resize(2 * (size_t)n);
+  if (info) g.e_info.resize(3 * (size_t)n); else g.e_info.clear();
+  if (huber_delta) g.e_delta.resize(n); else g.e_delta.clear();
+  std::vector<CopyJob> jobs = {{g.e_pose.data(), pose_idx, sizeof(int32_t) * (size_t)n},
+                               {g.e_point.data(), point_idx, sizeof(int32_t) * (size_t)n},
+                               {g.e_uv.data(), uv, 2 * sizeof(double) * (size_t)n}};
+  if (cam_idx) jobs.push_back({g.e_cam.data(), cam_idx, (size_t)n}); else std::fill(g.e_cam.begin(), g.e_cam.end(), (uint8_t)0);
+  if (info) jobs.push_back({g.e_info.data(), info, 3 * sizeof(double) * (size_t)n});
+  if (huber_delta) jobs.push_back({g.e_delta.data(), huber_delta, sizeof(double) * (size_t)n});
+  parallel_copy(jobs);
   g.delta_all = huber_delta_all;
   h->dirty = true;
   return SSBA_OK;
@@ -704,6 +709,15 @@ ssba_status ssba_plan_shards(int32_t n_poses, const uint8_t *pose_fixed, int32_t
   std::string err;
   if (!plan_shards(g, world_size, owner, err)) return fail(nullptr, SSBA_ERR_INVALID_ARG, err);
   std::memcpy(owner_out, owner.data(), sizeof(int32_t) * (size_t)n_points);
+  return SSBA_OK;
+}
+
+ssba_status ssba_set_profiling(ssba_handle *h, int32_t on) {
+  if (!h) return SSBA_ERR_INVALID_ARG;
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  h->opt.profile = on ? 1 : 0;
+  h->spans.clear();
+  h->ev_used = 0;
   return SSBA_OK;
 }
 

@@ -194,6 +194,13 @@ __global__ void __launch_bounds__(kLinThreads, 3) k_linearize(const DeviceProble
   const int tid = threadIdx.x;
   double chi = 0.0, mx = 0.0;
   if (a1 - a0 <= kLinThreads) {
+    // the chunk's local-pose lists, fetched now and used after the barrier (their latency hides
+    // behind the linearisation)
+    __shared__ int s_lp_ptr[kLinThreads + 1];
+    __shared__ uint8_t s_lp_pair[kLinThreads];
+    const int lpp0 = P.lp_pair_ptr[lp0];
+    if (tid <= lp1 - lp0) s_lp_ptr[tid] = P.lp_pair_ptr[lp0 + tid] - lpp0;
+    if (tid < P.lp_pair_ptr[lp1] - lpp0) s_lp_pair[tid] = P.lp_pair[lpp0 + tid];
     if (tid < a1 - a0) {
       const int a = a0 + tid;
       const int sl = P.pair_slot[a];
@@ -212,7 +219,7 @@ __global__ void __launch_bounds__(kLinThreads, 3) k_linearize(const DeviceProble
     for (int w = tid; w < 27 * (lp1 - lp0); w += kLinThreads) {
       const int lp = lp0 + w / 27, k = w % 27;
       double acc = 0.0;
-      for (int i = P.lp_pair_ptr[lp]; i < P.lp_pair_ptr[lp + 1]; ++i) acc += s_hp[P.lp_pair[i]][k];
+      for (int i = s_lp_ptr[lp - lp0]; i < s_lp_ptr[lp - lp0 + 1]; ++i) acc += s_hp[s_lp_pair[i]][k];
       P.hpp_part[27 * (size_t)lp + k] = acc;
     }
     const int sl = s0 + tid;
@@ -269,18 +276,23 @@ __global__ void __launch_bounds__(kLinThreads, 3) k_linearize(const DeviceProble
 
 // Hpp / b_p of pose q (entry k: 0..5 = b, 6..26 = upper triangle): the partials the linearize CTAs
 // wrote for the pose, folded in chunk order (deterministic).  One warp per pose, lane k < 27 owns
-// entry k; the loads of four partials are in flight together, the adds stay in list order.
+// entry k; the loads of sixteen partials are in flight together, the adds stay in list order.
 __device__ __forceinline__ double warp_fold_pose(const DeviceProblem &P, int q, int lane) {
   double s = 0.0;
-  if (lane < 27) {
-    const int i1 = P.q_part_ptr[q + 1];
-    int i = P.q_part_ptr[q];
-    for (; i + 4 <= i1; i += 4) {
-      const double v0 = P.hpp_part[27 * (size_t)P.q_part[i] + lane], v1 = P.hpp_part[27 * (size_t)P.q_part[i + 1] + lane];
-      const double v2 = P.hpp_part[27 * (size_t)P.q_part[i + 2] + lane], v3 = P.hpp_part[27 * (size_t)P.q_part[i + 3] + lane];
-      s += v0; s += v1; s += v2; s += v3;
+  const int i0 = P.q_part_ptr[q], i1 = P.q_part_ptr[q + 1];
+  for (int base = i0; base < i1; base += 32) {
+    const int cnt = i1 - base < 32 ? i1 - base : 32;
+    const int mine = lane < cnt ? P.q_part[base + lane] : 0;  // 32 list entries with one coalesced load
+    for (int j0 = 0; j0 < cnt; j0 += 16) {
+      double v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int part = __shfl_sync(0xffffffffu, mine, (j0 + j) & 31);
+        v[j] = (j0 + j < cnt && lane < 27) ? P.hpp_part[27 * (size_t)part + lane] : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) s += v[j];  // list order; the padding adds exact zeros
     }
-    for (; i < i1; ++i) s += P.hpp_part[27 * (size_t)P.q_part[i] + lane];
   }
   return s;
 }
@@ -368,7 +380,7 @@ __device__ __forceinline__ void schur_pose_warp(const DeviceProblem &P, const Co
   }
 }
 
-__global__ void __launch_bounds__(32 * kSchurWarps) k_schur(const DeviceProblem P, int n_pose_ctas, int prefolded) {
+__global__ void __launch_bounds__(32 * kSchurWarps, 3) k_schur(const DeviceProblem P, int n_pose_ctas, int prefolded) {
   const Control *ctl = P.ctl;
   if (ctl->done) return;
   extern __shared__ double s_w_all[];  // kSchurWarps x kSchurRunPairs x 18
@@ -449,30 +461,39 @@ __global__ void __launch_bounds__(32 * kSchurWarps) k_schur(const DeviceProblem 
         sa = reinterpret_cast<const double2 *>(P.W + 18 * (size_t)(p0 + a));
         sb = reinterpret_cast<const double2 *>(P.W + 18 * (size_t)(p0 + b));
       }
-      double Wa[18], Wb[18], BD[18];
-#pragma unroll
-      for (int t = 0; t < 9; ++t) { const double2 x = sa[t]; Wa[2 * t] = x.x; Wa[2 * t + 1] = x.y; }
-#pragma unroll
-      for (int t = 0; t < 9; ++t) { const double2 x = sb[t]; Wb[2 * t] = x.x; Wb[2 * t + 1] = x.y; }
+      // BD = W_a Dinv, two rows of W_a per step (three 16-byte loads); kept short-lived on purpose:
+      // with all of W_a, W_b and BD live the kernel needs 222 registers, i.e. two CTAs per SM and
+      // a second wave of CTAs; this way it fits three
       const double d0 = s_dinv[warp][i][0], d1 = s_dinv[warp][i][1], d2 = s_dinv[warp][i][2],
                    d3 = s_dinv[warp][i][3], d4 = s_dinv[warp][i][4], d5 = s_dinv[warp][i][5];
+      const double e0 = s_db[warp][i][0], e1 = s_db[warp][i][1], e2 = s_db[warp][i][2];
+      double BD[18];
 #pragma unroll
-      for (int r = 0; r < 6; ++r) {
-        const double w0 = Wa[3 * r], w1 = Wa[3 * r + 1], w2 = Wa[3 * r + 2];
-        BD[3 * r + 0] = w0 * d0 + w1 * d1 + w2 * d2;
-        BD[3 * r + 1] = w0 * d1 + w1 * d3 + w2 * d4;
-        BD[3 * r + 2] = w0 * d2 + w1 * d4 + w2 * d5;
+      for (int t = 0; t < 3; ++t) {
+        const double2 x0 = sa[3 * t], x1 = sa[3 * t + 1], x2 = sa[3 * t + 2];
+        const double w[6] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = 2 * t + h;
+          const double w0 = w[3 * h], w1 = w[3 * h + 1], w2 = w[3 * h + 2];
+          BD[3 * r + 0] = w0 * d0 + w1 * d1 + w2 * d2;
+          BD[3 * r + 1] = w0 * d1 + w1 * d3 + w2 * d4;
+          BD[3 * r + 2] = w0 * d2 + w1 * d4 + w2 * d5;
+          if (diag) accb[r] += w0 * e0 + w1 * e1 + w2 * e2;
+        }
       }
-      // block (row q_b, col q_a) += W_b Dinv W_a^T
+      // block (row q_b, col q_a) += W_b Dinv W_a^T, two rows of W_b per step
 #pragma unroll
-      for (int r = 0; r < 6; ++r)
+      for (int t = 0; t < 3; ++t) {
+        const double2 x0 = sb[3 * t], x1 = sb[3 * t + 1], x2 = sb[3 * t + 2];
+        const double w[6] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y};
 #pragma unroll
-        for (int c = 0; c < 6; ++c)
-          acc[6 * r + c] += Wb[3 * r] * BD[3 * c] + Wb[3 * r + 1] * BD[3 * c + 1] + Wb[3 * r + 2] * BD[3 * c + 2];
-      if (diag) {
-        const double e0 = s_db[warp][i][0], e1 = s_db[warp][i][1], e2 = s_db[warp][i][2];
+        for (int h = 0; h < 2; ++h) {
+          const int r = 2 * t + h;
 #pragma unroll
-        for (int r = 0; r < 6; ++r) accb[r] += Wa[3 * r] * e0 + Wa[3 * r + 1] * e1 + Wa[3 * r + 2] * e2;
+          for (int c = 0; c < 6; ++c)
+            acc[6 * r + c] += w[3 * h] * BD[3 * c] + w[3 * h + 1] * BD[3 * c + 1] + w[3 * h + 2] * BD[3 * c + 2];
+        }
       }
     }
   }

@@ -39,11 +39,11 @@ struct HostGraph {
   int n_poses = 0, n_points = 0, n_edges = 0;
   std::vector<double> poses, points;           // 7 / 3 doubles per vertex
   std::vector<uint8_t> pose_fixed, point_fixed;
-  std::vector<int32_t> e_pose, e_point;
-  std::vector<uint8_t> e_cam;
-  std::vector<double> e_uv;                    // 2 per edge
-  std::vector<double> e_info;                  // 3 per edge or empty (identity)
-  std::vector<double> e_delta;                 // 1 per edge or empty (delta_all)
+  uvec<int32_t> e_pose, e_point;
+  uvec<uint8_t> e_cam;
+  uvec<double> e_uv;                           // 2 per edge
+  uvec<double> e_info;                         // 3 per edge or empty (identity)
+  uvec<double> e_delta;                        // 1 per edge or empty (delta_all)
   double delta_all = 0.0;
 };
 
