@@ -552,7 +552,7 @@ __device__ __forceinline__ double group_reduce(double v, int lane) {
 struct LevelSeg {
   int n_cols, n_rounds, n_pairs, n_pf, n_bpf;
   const int *cta_rptr;  // kSolveMaxCluster + 1: the rounds of CTA c are [cta_rptr[c], cta_rptr[c + 1])
-  const int *col_j, *col_b0, *col_bptr, *brow, *round_type, *gt_dst, *gt_slot, *gt_pos, *gt_p0, *gt_p1, *pa,
+  const int *col_j, *col_b0, *col_bptr, *brow, *round_type, *gt_dst, *gt_slot, *gt_pos, *gt_p0, *gt_p1, *gt_mask, *pa,
       *pb, *pf_blk, *pf_slot, *bpf_blk;
   __device__ __forceinline__ explicit LevelSeg(const int *seg) {
     n_cols = seg[0]; n_rounds = seg[1]; n_pairs = seg[2]; n_pf = seg[4]; n_bpf = seg[5];
@@ -569,6 +569,7 @@ struct LevelSeg {
     gt_pos = p; p += 5 * n_rounds;
     gt_p0 = p; p += 5 * n_rounds;
     gt_p1 = p; p += 5 * n_rounds;
+    gt_mask = p; p += 5 * n_rounds;
     pa = p; p += n_pairs;
     pb = p; p += n_pairs;
     pf_blk = p; p += n_pf;
@@ -721,8 +722,9 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
 #pragma unroll
         for (int c = 0; c < 6; ++c) v[c] = 0.0;
         if (active && (!reduce || g == 0)) {
+          // from L2: another CTA's look-ahead round may have updated the block one level ago
           const double2 *d2 = reinterpret_cast<const double2 *>(D + 6 * r);
-          const double2 t0 = d2[0], t1 = d2[1], t2 = d2[2];
+          const double2 t0 = __ldcg(d2), t1 = __ldcg(d2 + 1), t2 = __ldcg(d2 + 2);
           v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y; v[4] = t2.x; v[5] = t2.y;
         }
         double acc[6];
@@ -763,7 +765,15 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
 #pragma unroll
           for (int c = 0; c < 6; ++c) v[c] -= acc[c];
         }
-        if (kind == 0) {
+        if (kind == 3) {
+          // ACC (look-ahead): the products of columns that finished two or more levels ago are
+          // subtracted from the block of a column of the NEXT level ahead of time, in global
+          // memory, where that block's own round will pick its value up
+          if (active) {
+            double2 *d2 = reinterpret_cast<double2 *>(D + 6 * r);
+            d2[0] = make_double2(v[0], v[1]); d2[1] = make_double2(v[2], v[3]); d2[2] = make_double2(v[4], v[5]);
+          }
+        } else if (kind == 0) {
           // DIAG: the group's rows meet in shared memory, then the group's first lane factors the
           // 6x6 block and inverts the triangle serially in registers (measured on B200: ~2.5x
           // shorter than the same recurrences spread over six lanes with shuffles, whose
@@ -843,8 +853,10 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
                 double2 *s2 = reinterpret_cast<double2 *>(Ds + 6 * r);
                 s2[0] = make_double2(x[0], x[1]); s2[1] = make_double2(x[2], x[3]); s2[2] = make_double2(x[4], x[5]);
               } else {
+                const int mask = S.gt_mask[gt];  // the CTAs that read this block at a later level
 #pragma unroll
                 for (int cc = 0; cc < kCluster; ++cc) {
+                  if (!((mask >> cc) & 1)) continue;
                   const unsigned ra = dsmem_addr(Ds + 6 * r, (unsigned)cc);
                   dsmem_st2(ra, x[0], x[1]); dsmem_st2(ra + 16, x[2], x[3]); dsmem_st2(ra + 32, x[4], x[5]);
                 }

@@ -194,8 +194,8 @@ bool symbolic_factor(int n, const std::vector<std::vector<int>> &adj, const std:
 //   header[8] = {n_cols, n_rounds, n_pairs, n_brows, n_pf, n_bpf, 0, 0}
 //   cta_rptr[kSolveMaxCluster + 1]             rounds [cta_rptr[c], cta_rptr[c+1]) belong to CTA c of the cluster
 //   col_j[n_cols] col_b0[n_cols] col_bptr[n_cols+1] brow[n_brows]          (backward pass)
-//   round_type[n_rounds]                       bits 0-1: 0 DIAG 1 SUB 2 VEC, bit 2: REDUCE
-//   gt_dst[5 n_rounds] gt_slot[..] gt_pos[..] gt_p0[..] gt_p1[..]           (group tasks)
+//   round_type[n_rounds]                       bits 0-1: 0 DIAG 1 SUB 2 VEC 3 ACC (look-ahead), bit 2: REDUCE
+//   gt_dst[5 n_rounds] gt_slot[..] gt_pos[..] gt_p0[..] gt_p1[..] gt_mask[..]   (group tasks; mask = CTAs that read the SUB block later)
 //   pa[n_pairs] pb[n_pairs]      block refs; for VEC tasks pb is the column k of y_k
 //   pf_blk[n_pf] pf_slot[n_pf]   blocks of the NEXT level to prefetch into their cache slots
 //   bpf_blk[n_bpf]               blocks of the PREVIOUS level (backward pass prefetch)
@@ -205,6 +205,8 @@ bool symbolic_factor(int n, const std::vector<std::vector<int>> &adj, const std:
 void build_solver_program(Structure &s) {
   constexpr int kSplitPairs = 10;  // blocks with more update pairs get a REDUCE round
   constexpr int kSplitDiag = 1;    // ... diagonal blocks already with two
+  constexpr int kSplitAcc = 5;     // ... look-ahead tasks with more than five (they must not outlast the level's chain)
+  constexpr int kAccMinPairs = 3;  // tasks with more update pairs hand the early ones to the level before
   const int n = s.n_fp, NL = s.n_levels;
   std::vector<int> level_of(n, 0);
   for (int lv = 0; lv < NL; ++lv)
@@ -221,17 +223,79 @@ void build_solver_program(Structure &s) {
   std::vector<LevelPlan> plan(NL);
   const int C = solver_cluster_size(n);
   s.solve_cluster = C;
+  // ---- look-ahead: a task of level lv with more than kAccMinPairs update products hands the ones
+  // whose source column finished at a level sl <= lv - 2 to ACC tasks of earlier levels in
+  // [sl + 1, lv - 1] (which pre-subtract them from the block's value in global memory on otherwise
+  // idle warps / CTAs); at its own level only the products of the columns of level lv - 1 are left
+  // on the critical path.  Measured on B200 (cfg3): everything at lv - 1 overloads the levels below
+  // the top separators, everything at sl + 1 the leaf levels; hence the load-levelled placement.
+  struct Task { int dst, pos; std::vector<std::pair<int, int>> pairs; };  // VEC: dst = -1 - column, pairs (block, -1 - col)
+  std::vector<std::vector<Task>> own(NL), early(NL);
+  {
+    // pass 1: the late products stay with their task; count the work every level has anyway
+    std::vector<long long> load(NL, 0);
+    long long total_pairs = 0;
+    struct Group { int lv, dst, sl; std::vector<std::pair<int, int>> pairs; };
+    std::vector<Group> groups;  // early products of one block from the columns of one level
+    std::vector<int> grp_of(NL, -1), touched;
+    for (int lv = 0; lv < NL; ++lv) {
+      const int c0 = s.level_ptr[lv];
+      const int t0 = s.ltask_ptr[lv], nt = s.ltask_ptr[lv + 1] - t0;
+      for (int t = 0; t < nt; ++t) {
+        Task tk{s.task_dst[t0 + t], s.task_pos[t0 + t], {}};
+        for (int l : touched) grp_of[l] = -1;
+        touched.clear();
+        if (tk.dst >= 0) {
+          const int p0 = s.task_pair_ptr[t0 + t], p1 = s.task_pair_ptr[t0 + t + 1];
+          const bool look = lv >= 2 && p1 - p0 > kAccMinPairs;
+          for (int p = p0; p < p1; ++p) {
+            const int sl = level_of[s.blk_col[s.pair_a[p]]];  // the level that finishes both source blocks
+            if (look && sl <= lv - 2) {
+              if (grp_of[sl] < 0) { grp_of[sl] = (int)groups.size(); groups.push_back(Group{lv, tk.dst, sl, {}}); touched.push_back(sl); }
+              groups[grp_of[sl]].pairs.emplace_back(s.pair_a[p], s.pair_b[p]);
+            } else {
+              tk.pairs.emplace_back(s.pair_a[p], s.pair_b[p]);
+            }
+          }
+          total_pairs += p1 - p0;
+        } else {
+          const int j = s.level_col[c0 + tk.pos];
+          for (int rr = s.row_ptr[j]; rr < s.row_ptr[j + 1]; ++rr) tk.pairs.emplace_back(s.row_blk[rr], -1 - s.row_col[rr]);
+        }
+        load[lv] += 1 + (long long)tk.pairs.size();
+        own[lv].push_back(std::move(tk));
+      }
+    }
+    // pass 2: every group goes to the latest level of its window [sl + 1, lv - 1] that still has
+    // room (an even share of all products, with some slack), else to the emptiest one; the groups
+    // of one block that land on the same level are one ACC task
+    const long long cap = std::max<long long>(64, (total_pairs * 3 / 2) / std::max(1, NL));
+    std::vector<int> acc_at(NL, -1);
+    int cur_dst = -1;
+    touched.clear();
+    for (const Group &g : groups) {
+      if (g.dst != cur_dst) { for (int l : touched) acc_at[l] = -1; touched.clear(); cur_dst = g.dst; }
+      int best = -1;
+      for (int l = g.lv - 1; l > g.sl; --l)
+        if (load[l] + (long long)g.pairs.size() <= cap) { best = l; break; }
+      if (best < 0) { best = g.sl + 1; for (int l = g.sl + 1; l < g.lv; ++l) if (load[l] < load[best]) best = l; }
+      load[best] += (long long)g.pairs.size();
+      if (acc_at[best] < 0) { acc_at[best] = (int)early[best].size(); early[best].push_back(Task{g.dst, 0, {}}); touched.push_back(best); }
+      Task &a = early[best][acc_at[best]];
+      a.pairs.insert(a.pairs.end(), g.pairs.begin(), g.pairs.end());
+    }
+  }
   for (int lv = 0; lv < NL; ++lv) {
     LevelPlan &lp = plan[lv];
-    const int c0 = s.level_ptr[lv], nc = s.level_ptr[lv + 1] - c0;
-    const int t0 = s.ltask_ptr[lv], nt = s.ltask_ptr[lv + 1] - t0;
+    const int nc = s.level_ptr[lv + 1] - s.level_ptr[lv];
     // the columns of the level are dealt over the CTAs of the cluster, heaviest first onto the
     // least loaded CTA; every task of a column runs in the column's CTA (the inverse diagonal
-    // block it waits for never leaves that CTA)
+    // block it waits for never leaves that CTA); the ACC tasks then fill up the lightest CTAs
     std::vector<int> cta_of_pos(nc, 0);
+    std::vector<long long> load(C, 0);
     if (C > 1) {
-      std::vector<long long> w(nc, 0), load(C, 0);
-      for (int t = 0; t < nt; ++t) w[s.task_pos[t0 + t]] += 2 + (s.task_pair_ptr[t0 + t + 1] - s.task_pair_ptr[t0 + t]);
+      std::vector<long long> w(nc, 0);
+      for (const Task &tk : own[lv]) w[tk.pos] += 2 + (long long)tk.pairs.size();
       std::vector<int> order(nc);
       std::iota(order.begin(), order.end(), 0);
       std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return w[x] > w[y]; });
@@ -240,36 +304,43 @@ void build_solver_program(Structure &s) {
         cta_of_pos[pos] = c; load[c] += w[pos];
       }
     }
-    std::vector<std::vector<GT>> diag(C), sub(C), vec(C), big_diag(C), big_sub(C), big_vec(C);
-    for (int t = 0; t < nt; ++t) {
-      const int d = s.task_dst[t0 + t], pos = s.task_pos[t0 + t];
-      GT gt{d, pos, (int)lp.pairs.size(), 0};
-      if (d >= 0) {
-        for (int p = s.task_pair_ptr[t0 + t]; p < s.task_pair_ptr[t0 + t + 1]; ++p) lp.pairs.emplace_back(s.pair_a[p], s.pair_b[p]);
-      } else {
-        const int j = s.level_col[c0 + pos];
-        for (int rr = s.row_ptr[j]; rr < s.row_ptr[j + 1]; ++rr) lp.pairs.emplace_back(s.row_blk[rr], -1 - s.row_col[rr]);
-      }
+    std::vector<std::vector<GT>> diag(C), sub(C), vec(C), acc(C), big_diag(C), big_sub(C), big_vec(C), big_acc(C);
+    auto add_pairs = [&](const Task &tk) {
+      GT gt{tk.dst, tk.pos, (int)lp.pairs.size(), 0};
+      lp.pairs.insert(lp.pairs.end(), tk.pairs.begin(), tk.pairs.end());
       gt.p1 = (int)lp.pairs.size();
-      const bool is_diag = d >= 0 && s.blk_row[d] == s.blk_col[d];
-      const int c = cta_of_pos[pos];
-      if (d < 0) vec[c].push_back(gt);
+      return gt;
+    };
+    for (const Task &tk : own[lv]) {
+      const GT gt = add_pairs(tk);
+      const bool is_diag = tk.dst >= 0 && s.blk_row[tk.dst] == s.blk_col[tk.dst];
+      const int c = cta_of_pos[tk.pos];
+      if (tk.dst < 0) vec[c].push_back(gt);
       else if (is_diag) (gt.p1 - gt.p0 > kSplitDiag ? big_diag : diag)[c].push_back(gt);
       else sub[c].push_back(gt);
     }
-    // SUB / VEC tasks with more than kSplitPairs pairs get a round of their own (pairs split five
-    // ways).  Measured on B200: splitting more of them to fill idle warps makes the level SLOWER
+    {
+      std::vector<const Task *> by_w;
+      for (const Task &tk : early[lv]) by_w.push_back(&tk);
+      std::stable_sort(by_w.begin(), by_w.end(), [](const Task *x, const Task *y) { return x->pairs.size() > y->pairs.size(); });
+      for (const Task *tk : by_w) {
+        const int c = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        load[c] += 2 + (long long)tk->pairs.size();
+        acc[c].push_back(add_pairs(*tk));
+      }
+    }
+    // SUB / VEC / ACC tasks with more than kSplitPairs pairs get a round of their own (pairs split
+    // five ways).  Measured on B200: splitting more of them to fill idle warps makes the level SLOWER
     // (the update products are bound by the SM's shared-memory pipe, and a split round wastes lanes).
     auto npairs = [](const GT &g) { return g.p1 - g.p0; };
     auto by_size = [&](std::vector<GT> &v) { std::stable_sort(v.begin(), v.end(), [&](const GT &x, const GT &y) { return npairs(x) > npairs(y); }); };
-    for (int c = 0; c < C; ++c) {
-      by_size(diag[c]); by_size(sub[c]); by_size(vec[c]);
-      int ns = 0, nv = 0;
-      while (ns < (int)sub[c].size() && npairs(sub[c][ns]) > kSplitPairs) ++ns;
-      while (nv < (int)vec[c].size() && npairs(vec[c][nv]) > kSplitPairs) ++nv;
-      big_sub[c].assign(sub[c].begin(), sub[c].begin() + ns); sub[c].erase(sub[c].begin(), sub[c].begin() + ns);
-      big_vec[c].assign(vec[c].begin(), vec[c].begin() + nv); vec[c].erase(vec[c].begin(), vec[c].begin() + nv);
-    }
+    auto take_big = [&](std::vector<GT> &v, std::vector<GT> &big, int limit) {
+      by_size(v);
+      int nb = 0;
+      while (nb < (int)v.size() && npairs(v[nb]) > limit) ++nb;
+      big.assign(v.begin(), v.begin() + nb); v.erase(v.begin(), v.begin() + nb);
+    };
+    for (int c = 0; c < C; ++c) { by_size(diag[c]); take_big(sub[c], big_sub[c], kSplitPairs); take_big(vec[c], big_vec[c], kSplitPairs); take_big(acc[c], big_acc[c], kSplitAcc); }
     auto pack5 = [&](const std::vector<GT> &v, int type) {
       for (size_t i = 0; i < v.size(); i += 5) {
         Round r{type, {}};
@@ -290,10 +361,10 @@ void build_solver_program(Structure &s) {
     };
     // The DIAG rounds sit on the critical path of the level (every other round of a column waits
     // for the inverse they publish): a diagonal block with more than kSplitDiag pairs gets its
-    // pairs split five ways.  SUB / VEC tasks are packed five of similar size per round (a
+    // pairs split five ways.  SUB / VEC / ACC tasks are packed five of similar size per round (a
     // round lasts as long as its longest group), and the rounds are dealt to the warps
     // heaviest first.  Order matters for the wait-free argument: inside a CTA every DIAG round
-    // precedes every SUB / VEC round.
+    // precedes every SUB / VEC round (ACC rounds never wait).
     auto cost = [&](const Round &r) {
       int m = 0;
       for (int k = 0; k < 5; ++k) if (r.g[k].dst >= 0) m = std::max(m, r.g[k].p1 - r.g[k].p0);
@@ -306,9 +377,27 @@ void build_solver_program(Structure &s) {
       const size_t n_diag_rounds = lp.rounds.size();
       split5(big_sub[c], 1); pack5(sub[c], 1);
       split5(big_vec[c], 2); pack5(vec[c], 2);
+      split5(big_acc[c], 3); pack5(acc[c], 3);
       std::stable_sort(lp.rounds.begin() + n_diag_rounds, lp.rounds.end(), [&](const Round &x, const Round &y) { return cost(x) > cost(y); });
     }
     for (int c = C; c <= kSolveMaxCluster; ++c) lp.cta_rptr[c] = (int)lp.rounds.size();
+  }
+  // ---- which CTAs read a block later on (as a source of an update product or of a forward
+  // substitution): the CTA that finishes the block writes it into the block cache of exactly those
+  std::vector<uint8_t> blk_mask(s.n_blocks, 0);
+  for (int lv = 0; lv < NL; ++lv) {
+    const LevelPlan &lp = plan[lv];
+    for (int c = 0; c < C; ++c)
+      for (int rd = lp.cta_rptr[c]; rd < lp.cta_rptr[c + 1]; ++rd) {
+        const Round &r = lp.rounds[rd];
+        for (int k = 0; k < 5; ++k) {
+          if (r.g[k].dst < 0) continue;
+          for (int p = r.g[k].p0; p < r.g[k].p1; ++p) {
+            blk_mask[lp.pairs[p].first] |= (uint8_t)(1u << c);
+            if ((r.type & 3) != 2) blk_mask[lp.pairs[p].second] |= (uint8_t)(1u << c);
+          }
+        }
+      }
   }
   // ---- pass 1: segment sizes
   std::vector<int> seg_size(NL + 1, 0);
@@ -320,7 +409,7 @@ void build_solver_program(Structure &s) {
     const int npf = 0;  // initial values are read from global memory by the rounds themselves
     const int nbpf = lv > 0 ? level_blocks(lv - 1) : 0;
     const int nr = (int)plan[lv].rounds.size();
-    seg_size[lv + 1] = 8 + (kSolveMaxCluster + 1) + 2 * nc + (nc + 1) + nb + nr + 25 * nr + 2 * (int)plan[lv].pairs.size() + 2 * npf + nbpf;
+    seg_size[lv + 1] = 8 + (kSolveMaxCluster + 1) + 2 * nc + (nc + 1) + nb + nr + 30 * nr + 2 * (int)plan[lv].pairs.size() + 2 * npf + nbpf;
   }
   s.prog_max_seg = 0;
   for (int v : seg_size) s.prog_max_seg = std::max(s.prog_max_seg, (v + 3) & ~3);
@@ -389,6 +478,7 @@ void build_solver_program(Structure &s) {
     for (const Round &r : lp.rounds) for (int k = 0; k < 5; ++k) P.push_back(r.g[k].pos);
     for (const Round &r : lp.rounds) for (int k = 0; k < 5; ++k) P.push_back(r.g[k].p0);
     for (const Round &r : lp.rounds) for (int k = 0; k < 5; ++k) P.push_back(r.g[k].p1);
+    for (const Round &r : lp.rounds) for (int k = 0; k < 5; ++k) P.push_back(((r.type & 3) == 1 && r.g[k].dst >= 0) ? blk_mask[r.g[k].dst] : 0);
     for (auto &ab : lp.pairs) P.push_back(ref(ab.first));
     for (auto &ab : lp.pairs) P.push_back(ab.second >= 0 ? ref(ab.second) : -1 - ab.second);  // VEC: column k
     emit_level_blocks(lv - 1, false);
