@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <functional>
 #include <memory>
 #include <string>
 #include <vector>
@@ -74,7 +75,8 @@ struct ssba_handle {
   // memory: one device arena (static index data first, then work buffers) + pinned mirror of
   // the static part so a whole graph goes up in one copy
   char *d_arena = nullptr; size_t d_arena_bytes = 0;
-  char *h_stage = nullptr; size_t h_stage_bytes = 0;
+  char *h_stage = nullptr; size_t h_stage_bytes = 0;      // pinned mirror of region A (big per-edge / per-pair arrays)
+  char *h_stage_b = nullptr; size_t h_stage_b_bytes = 0;  // ... of region B (solver program, small index lists)
   Control *h_ctl = nullptr;   // pinned
   double *h_small = nullptr;  // pinned scratch (8 doubles)
   DeviceProblem P{};
@@ -330,6 +332,7 @@ void ssba_destroy(ssba_handle *h) {
   for (auto e : h->ev) cudaEventDestroy(e);
   if (h->d_arena) cudaFree(h->d_arena);
   if (h->h_stage) cudaFreeHost(h->h_stage);
+  if (h->h_stage_b) cudaFreeHost(h->h_stage_b);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->h_small) cudaFreeHost(h->h_small);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -406,9 +409,82 @@ ssba_status ssba_initialize(ssba_handle *h) {
   std::string err;
   Structure &s = h->s;
   const bool timing = std::getenv("SSBA_TIMING") != nullptr;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // nothing of a previous upload may still read the staging buffers
+
+  // ---- the arena is planned and filled in two steps so that the upload of the big per-edge /
+  // per-pair arrays (region A, several megabytes over PCIe) runs while the host still builds the
+  // solver program and the small index lists (region B):
+  //   [ A: static big | work buffers sized by edges / pairs / landmarks | B: static small | late work ]
+  struct Item { const void *src; size_t bytes; size_t off; void **dst; };
+  std::vector<Item> items_a, items_b, work;
+  size_t top = 0, bytes_a = 0;
+  DeviceProblem &P = h->P;
+  std::memset(&P, 0, sizeof(P));
+  auto stat = [&](std::vector<Item> &items, const void *src, size_t bytes, const void **dst) {
+    if (bytes == 0) { *dst = nullptr; return; }
+    Item it{src, bytes, align_up(top), (void **)dst};
+    top = it.off + bytes;
+    items.push_back(it);
+  };
+  auto dyn = [&](size_t bytes, void **dst) {
+    Item it{nullptr, bytes, align_up(top), dst};
+    top = it.off + (bytes ? bytes : 8);
+    work.push_back(it);
+  };
+  auto grow_arena = [&](size_t want) -> bool {
+    if (want <= h->d_arena_bytes) return true;
+    if (h->d_arena) cudaFree(h->d_arena);
+    h->d_arena = nullptr; h->d_arena_bytes = 0;
+    if (cudaMalloc((void **)&h->d_arena, want) != cudaSuccess) { cudaGetLastError(); return false; }
+    h->d_arena_bytes = want;
+    return true;
+  };
+  auto grow_stage = [&](char *&buf, size_t &cap, size_t want) -> bool {
+    if (want <= cap) return true;
+    if (buf) cudaFreeHost(buf);
+    buf = nullptr; cap = 0;
+    const size_t sz = want + want / 4;
+    if (cudaHostAlloc((void **)&buf, sz, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return false; }
+    cap = sz;
+    return true;
+  };
+#define STAT(items, vec, field) stat(items, (vec).data(), (vec).size() * sizeof((vec)[0]), (const void **)&P.field)
+#define DYN(field, count, type) dyn((size_t)(count) * sizeof(type), (void **)&P.field)
+  ssba_status cb_rc = SSBA_OK;
+  double t_stage_a = 0.0;
+  const std::function<void()> on_edges_ready = [&]() {
+    auto t_s = Clock::now();
+    STAT(items_a, g.poses, pose0); STAT(items_a, g.points, point0);
+    STAT(items_a, s.slot_vertex, slot_vertex); STAT(items_a, s.slot_free, slot_free); STAT(items_a, s.slot_pair_ptr, slot_pair_ptr);
+    STAT(items_a, s.pair_vertex, pair_vertex); STAT(items_a, s.pair_q, pair_q); STAT(items_a, s.pair_edge_ptr, pair_edge_ptr);
+    STAT(items_a, s.pair_slot, pair_slot);
+    STAT(items_a, s.e_uv, e_uv); STAT(items_a, s.e_info, e_info); STAT(items_a, s.e_delta, e_delta); STAT(items_a, s.e_cam, e_cam);
+    STAT(items_a, s.e_orig, e_orig);
+    bytes_a = align_up(top);
+    DYN(pose[0], 7 * g.n_poses, double); DYN(pose[1], 7 * g.n_poses, double);
+    DYN(point[0], 3 * (size_t)g.n_points, double); DYN(point[1], 3 * (size_t)g.n_points, double);
+    DYN(W, 18 * (size_t)s.n_pairs, double); DYN(Hll, 6 * (size_t)s.n_slots, double); DYN(bl, 3 * (size_t)s.n_slots, double);
+    DYN(Dinv, 6 * (size_t)s.n_slots, double);
+    DYN(gather, h->opt.world_size > 1 ? 3 * (size_t)g.n_points : 0, double); DYN(err_out, 2 * (size_t)g.n_edges, double);
+    const size_t known = align_up(top);
+    // room for region B and the late work buffers (a few hundred KB for a sliding window); if the
+    // guess is short the arena is re-made below and region A sent again
+    if (!grow_arena(known + known / 8 + (4u << 20))) { cb_rc = fail(h, SSBA_ERR_ALLOC, "cudaMalloc failed"); return; }
+    if (!grow_stage(h->h_stage, h->h_stage_bytes, bytes_a)) { cb_rc = fail(h, SSBA_ERR_ALLOC, "cudaHostAlloc failed"); return; }
+    std::vector<CopyJob> jobs;
+    for (auto &it : items_a) jobs.push_back({h->h_stage + it.off, it.src, it.bytes});
+    parallel_copy(jobs);
+    if (cudaMemcpyAsync(h->d_arena, h->h_stage, bytes_a, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) {
+      cb_rc = fail(h, SSBA_ERR_CUDA, "cudaMemcpyAsync (region A) failed");
+      return;
+    }
+    t_stage_a = secs(t_s, Clock::now());
+  };
   auto t_a = Clock::now();
-  if (!build_structure(g, h->opt.rank, h->opt.world_size, s, err)) return fail(h, SSBA_ERR_INVALID_ARG, err);
+  h->initialized = false;  // the device problem is being rebuilt
+  if (!build_structure(g, h->opt.rank, h->opt.world_size, s, err, &on_edges_ready)) return fail(h, SSBA_ERR_INVALID_ARG, err);
   auto t_b = Clock::now();
+  if (cb_rc) return cb_rc;
   if (s.n_fp + s.n_fl_global == 0) { h->initialized = false; return fail(h, SSBA_ERR_EMPTY, "initialize: 0 vertices to optimize"); }
 
   // landmarks whose estimate this rank reports in ssba_get_points (world_size > 1)
@@ -417,79 +493,47 @@ ssba_status ssba_initialize(ssba_handle *h) {
   if (h->opt.rank == 0)
     for (int v = 0; v < g.n_points; ++v) if (!s.point_active[v]) h->owner_mask[v] = 1;
 
-  // ---- plan the arena: static (uploaded) part first, then work buffers
-  struct Item { const void *src; size_t bytes; size_t off; void **dst; };
-  std::vector<Item> items;
-  size_t top = 0;
-  DeviceProblem &P = h->P;
-  std::memset(&P, 0, sizeof(P));
-  auto stat = [&](const void *src, size_t bytes, const void **dst) {
-    if (bytes == 0) { *dst = nullptr; return; }
-    Item it{src, bytes, align_up(top), (void **)dst};
-    top = it.off + bytes;
-    items.push_back(it);
-  };
-#define STAT(vec, field) stat((vec).data(), (vec).size() * sizeof((vec)[0]), (const void **)&P.field)
-  STAT(g.poses, pose0); STAT(g.points, point0);
-  STAT(s.slot_vertex, slot_vertex); STAT(s.slot_free, slot_free); STAT(s.slot_pair_ptr, slot_pair_ptr);
-  STAT(s.slot_combo_ptr, slot_combo_ptr); STAT(s.combo_blk, combo_blk);
-  STAT(s.pair_vertex, pair_vertex); STAT(s.pair_q, pair_q); STAT(s.pair_edge_ptr, pair_edge_ptr);
-  STAT(s.pair_slot, pair_slot); STAT(s.lchunk_slot, lchunk_slot);
-  STAT(s.e_uv, e_uv); STAT(s.e_info, e_info); STAT(s.e_delta, e_delta); STAT(s.e_cam, e_cam); STAT(s.e_orig, e_orig);
-  STAT(s.lchunk_lp_ptr, lchunk_lp_ptr); STAT(s.lp_pair_ptr, lp_pair_ptr); STAT(s.lp_pair, lp_pair);
-  STAT(s.q_part_ptr, q_part_ptr); STAT(s.q_part, q_part);
-  STAT(s.pose_of_q, pose_of_q);
-  STAT(h->owner_mask, owner_mask);
-  STAT(s.unit_slot, unit_slot); STAT(s.unit_n, unit_n); STAT(s.unit_k, unit_k); STAT(s.unit_c0, unit_c0);
-  STAT(s.blk_row, blk_row); STAT(s.blk_col, blk_col); STAT(s.col_ptr, col_diag); STAT(s.prog, prog); STAT(s.prog_ptr, prog_ptr);
-#undef STAT
-  const size_t static_bytes = align_up(top);
-  std::vector<Item> work;
-  auto dyn = [&](size_t bytes, void **dst) {
-    Item it{nullptr, bytes, align_up(top), dst};
-    top = it.off + (bytes ? bytes : 8);
-    work.push_back(it);
-  };
+  // ---- region B and the late work buffers
+  const size_t off_b = align_up(top);
+  STAT(items_b, s.lchunk_slot, lchunk_slot);
+  STAT(items_b, s.lchunk_lp_ptr, lchunk_lp_ptr); STAT(items_b, s.lp_pair_ptr, lp_pair_ptr); STAT(items_b, s.lp_pair, lp_pair);
+  STAT(items_b, s.q_part_ptr, q_part_ptr); STAT(items_b, s.q_part, q_part);
+  STAT(items_b, s.pose_of_q, pose_of_q);
+  STAT(items_b, h->owner_mask, owner_mask);
+  STAT(items_b, s.unit_slot, unit_slot); STAT(items_b, s.unit_n, unit_n); STAT(items_b, s.unit_k, unit_k); STAT(items_b, s.unit_c0, unit_c0);
+  STAT(items_b, s.unit_combo_ptr, unit_combo_ptr); STAT(items_b, s.combo_blk, combo_blk);
+  STAT(items_b, s.blk_row, blk_row); STAT(items_b, s.blk_col, blk_col); STAT(items_b, s.col_ptr, col_diag);
+  STAT(items_b, s.prog, prog); STAT(items_b, s.prog_ptr, prog_ptr);
+  const size_t bytes_b = align_up(top) - off_b;
   P.n_fin_blocks = (s.n_slots + 127) / 128 > 0 ? (s.n_slots + 127) / 128 : 1;
   P.n_lin_blocks = P.n_upd_blocks = s.n_lchunks;
   const int nblk = std::max(P.n_fin_blocks, s.n_lchunks);
   P.sys_doubles = 36 * (size_t)s.n_blocks + 12 * (size_t)s.n_fp;
-#define DYN(field, count, type) dyn((size_t)(count) * sizeof(type), (void **)&P.field)
-  DYN(pose[0], 7 * g.n_poses, double); DYN(pose[1], 7 * g.n_poses, double);
-  DYN(point[0], 3 * (size_t)g.n_points, double); DYN(point[1], 3 * (size_t)g.n_points, double);
-  DYN(W, 18 * (size_t)s.n_pairs, double); DYN(Hll, 6 * (size_t)s.n_slots, double); DYN(bl, 3 * (size_t)s.n_slots, double);
-  DYN(Dinv, 6 * (size_t)s.n_slots, double); DYN(hpp_part, 27 * (size_t)s.n_hpp_parts, double); DYN(hpp_fold, 27 * (size_t)s.n_fp, double);
+  DYN(hpp_part, 27 * (size_t)s.n_hpp_parts, double); DYN(hpp_fold, 27 * (size_t)s.n_fp, double);
   DYN(sys, P.sys_doubles, double); DYN(xp, 6 * (size_t)s.n_fp, double); DYN(diag_buf, 6 * (size_t)s.n_fp, double);
   DYN(chi_cur_part, nblk, double); DYN(maxdiag_part, nblk, double); DYN(chi_new_part, nblk, double); DYN(scale_part, nblk, double);
   DYN(scal, 8, double); DYN(chi_out, 8, double);
-  DYN(gather, h->opt.world_size > 1 ? 3 * (size_t)g.n_points : 0, double); DYN(err_out, 2 * (size_t)g.n_edges, double);
   DYN(ctl, 1, Control);
+#undef STAT
 #undef DYN
   const size_t total = align_up(top);
-  if (total > h->d_arena_bytes) {
-    if (h->d_arena) cudaFree(h->d_arena);
-    h->d_arena = nullptr; h->d_arena_bytes = 0;
-    const size_t want = total + total / 4;
-    if (cudaMalloc((void **)&h->d_arena, want) != cudaSuccess) { cudaGetLastError(); return fail(h, SSBA_ERR_ALLOC, "cudaMalloc failed"); }
-    h->d_arena_bytes = want;
+  const size_t static_bytes = bytes_a + bytes_b;
+  if (total > h->d_arena_bytes) {  // the guess was short: a larger arena, region A goes up again
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (!grow_arena(total + total / 4)) return fail(h, SSBA_ERR_ALLOC, "cudaMalloc failed");
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_arena, h->h_stage, bytes_a, cudaMemcpyHostToDevice, h->stream));
   }
-  if (static_bytes > h->h_stage_bytes) {
-    if (h->h_stage) cudaFreeHost(h->h_stage);
-    h->h_stage = nullptr; h->h_stage_bytes = 0;
-    const size_t want = static_bytes + static_bytes / 4;
-    if (cudaHostAlloc((void **)&h->h_stage, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return fail(h, SSBA_ERR_ALLOC, "cudaHostAlloc failed"); }
-    h->h_stage_bytes = want;
-  }
+  if (!grow_stage(h->h_stage_b, h->h_stage_b_bytes, bytes_b)) return fail(h, SSBA_ERR_ALLOC, "cudaHostAlloc failed");
   auto t_c = Clock::now();
   {
     std::vector<CopyJob> jobs;
-    for (auto &it : items) { jobs.push_back({h->h_stage + it.off, it.src, it.bytes}); *it.dst = h->d_arena + it.off; }
+    for (auto &it : items_b) jobs.push_back({h->h_stage_b + (it.off - off_b), it.src, it.bytes});
     parallel_copy(jobs);
   }
   auto t_d = Clock::now();
-  for (auto &it : work) *it.dst = h->d_arena + it.off;
+  for (auto *v : {&items_a, &items_b, &work}) for (auto &it : *v) *it.dst = h->d_arena + it.off;
   h->device_bytes = total;
-  CUDA_TRY(h, cudaMemcpyAsync(h->d_arena, h->h_stage, static_bytes, cudaMemcpyHostToDevice, h->stream));
+  if (bytes_b) CUDA_TRY(h, cudaMemcpyAsync(h->d_arena + off_b, h->h_stage_b, bytes_b, cudaMemcpyHostToDevice, h->stream));
 
   P.cams = g.cams;
   for (int c = 0; c < g.cams.n; ++c) quat_to_matrix(g.cams.ext[c], P.ext_R[c]);
@@ -509,9 +553,11 @@ ssba_status ssba_initialize(ssba_handle *h) {
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // h_stage may be rewritten by the next initialize
   h->setup_seconds = secs(t0, Clock::now());
   if (timing)
-    std::fprintf(stderr, "[ssba] initialize: build_structure %.3f ms, plan+alloc %.3f ms, stage memcpy %.3f ms (%.1f MB), "
-                 "upload+reset+sync %.3f ms, total %.3f ms\n", 1e3 * secs(t_a, t_b), 1e3 * secs(t_b, t_c),
-                 1e3 * secs(t_c, t_d), static_bytes / 1e6, 1e3 * secs(t_d, Clock::now()), 1e3 * h->setup_seconds);
+    std::fprintf(stderr, "[ssba] initialize: build_structure %.3f ms (of which staging + upload start of region A %.3f ms, %.1f MB), "
+                 "plan %.3f ms, stage B %.3f ms (%.2f MB), upload wait+reset+sync %.3f ms, total %.3f ms\n", 1e3 * secs(t_a, t_b),
+                 1e3 * t_stage_a, bytes_a / 1e6, 1e3 * secs(t_b, t_c), 1e3 * secs(t_c, t_d), bytes_b / 1e6,
+                 1e3 * secs(t_d, Clock::now()), 1e3 * h->setup_seconds);
+  (void)static_bytes;
   return SSBA_OK;
 }
 

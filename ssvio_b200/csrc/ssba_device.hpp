@@ -52,7 +52,7 @@ struct DeviceProblem {
   double *point[2];   // n_points x 3
   double *pose0, *point0;  // initial estimates (for ssba_reset_state)
   // landmark-major shard
-  const int32_t *slot_vertex, *slot_pair_ptr, *slot_combo_ptr, *combo_blk;
+  const int32_t *slot_vertex, *slot_pair_ptr;
   const uint8_t *slot_free;
   const int32_t *pair_vertex, *pair_q, *pair_edge_ptr, *pair_slot, *lchunk_slot;
   const double *e_uv, *e_info, *e_delta;   // e_info / e_delta may be null
@@ -63,6 +63,7 @@ struct DeviceProblem {
   const uint8_t *lp_pair;
   const int32_t *pose_of_q;
   const int32_t *unit_slot, *unit_n, *unit_k, *unit_c0;  // Schur work units
+  const int32_t *unit_combo_ptr, *combo_blk;             // ... and the factor blocks they accumulate into
   int n_units;
   // factor structure
   const int32_t *blk_row, *blk_col;

@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(32 * kSchurWarps, 3) k_schur(const DeviceProbl
     }
   }
   if (sub != 0) return;
-  double *dst = P.sys + 36 * (size_t)P.combo_blk[P.slot_combo_ptr[s0] + idx];
+  double *dst = P.sys + 36 * (size_t)P.combo_blk[P.unit_combo_ptr[u] + ci];
 #pragma unroll
   for (int i = 0; i < 36; ++i) atomicAdd(dst + i, -acc[i]);
   if (diag) {

@@ -624,7 +624,7 @@ void reset_keep_capacity(Structure &s) {
   clr(s.slot_vertex); clr(s.slot_free); clr(s.slot_pair_ptr); clr(s.pair_vertex); clr(s.pair_q);
   clr(s.pair_edge_ptr); clr(s.pair_slot); clr(s.lchunk_slot); clr(s.lchunk_lp_ptr); clr(s.lp_pair_ptr);
   clr(s.lp_pair); clr(s.q_part_ptr); clr(s.q_part); clr(s.e_uv); clr(s.e_cam); clr(s.e_orig); clr(s.e_info);
-  clr(s.e_delta); clr(s.slot_combo_ptr); clr(s.combo_blk); clr(s.unit_slot); clr(s.unit_n); clr(s.unit_k);
+  clr(s.e_delta); clr(s.unit_combo_ptr); clr(s.combo_blk); clr(s.unit_slot); clr(s.unit_n); clr(s.unit_k);
   clr(s.unit_c0); clr(s.col_ptr); clr(s.blk_row); clr(s.blk_col); clr(s.ltask_ptr); clr(s.task_dst);
   clr(s.task_pos); clr(s.task_pair_ptr); clr(s.pair_a); clr(s.pair_b); clr(s.prog); clr(s.prog_ptr);
   clr(s.row_ptr); clr(s.row_blk); clr(s.row_col); clr(s.level_ptr); clr(s.level_col);
@@ -648,7 +648,8 @@ struct SectionTimer {  // SSBA_TIMING=1: wall time of the sections of build_stru
 };
 }  // namespace
 
-bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std::string &err) {
+bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std::string &err,
+                     const std::function<void()> *on_edges_ready) {
   SectionTimer tm;
   reset_keep_capacity(s);
   const int NK = g.n_poses, NP = g.n_points, NE = g.n_edges;
@@ -792,15 +793,20 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     std::vector<int> perm_nat(n), perm_nd;
     std::iota(perm_nat.begin(), perm_nat.end(), 0);
     Factor f_nat, f_nd;
-    if (!symbolic_factor(n, adj, perm_nat, f_nat, err)) return false;
-    Factor *best = &f_nat;
+    Factor *best = nullptr;
     std::vector<int> *best_perm = &perm_nat;
     if (n >= 24) {
       nested_dissection_order(n, adj, perm_nd);
       if (perm_nd != perm_nat) {
         if (!symbolic_factor(n, adj, perm_nd, f_nd, err)) return false;
-        if (f_nd.est_cycles < f_nat.est_cycles) { best = &f_nd; best_perm = &perm_nd; }
+        best = &f_nd; best_perm = &perm_nd;
       }
+    }
+    // the natural order is only worth a symbolic factorisation of its own when nested dissection
+    // did not flatten the elimination tree (it always does for the block-banded windows)
+    if (!best || 2 * f_nd.n_levels > n) {
+      if (!symbolic_factor(n, adj, perm_nat, f_nat, err)) return false;
+      if (!best || f_nat.est_cycles <= f_nd.est_cycles) { best = &f_nat; best_perm = &perm_nat; }
     }
     const std::vector<int> &perm = *best_perm;  // q -> free pose index
     s.q_of_pose.assign(NK, -1);
@@ -814,7 +820,6 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     s.level_ptr.swap(best->level_ptr); s.level_col.swap(best->level_col);
     s.ltask_ptr.swap(best->ltask_ptr); s.task_dst.swap(best->task_dst); s.task_pos.swap(best->task_pos); s.task_pair_ptr.swap(best->task_pair_ptr);
     s.pair_a.swap(best->pair_a); s.pair_b.swap(best->pair_b);
-    build_solver_program(s);
   }
   auto find_block = [&](int row, int col) -> int {  // row >= col
     const int *b0 = s.blk_row.data() + s.col_ptr[col], *b1 = s.blk_row.data() + s.col_ptr[col + 1];
@@ -823,7 +828,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   };
   const int32_t *__restrict__ qmap = s.q_of_pose.data();
 
-  tm.mark("order + symbolic + program");
+  tm.mark("order + symbolic");
   // ---- per landmark: its edges sorted by pose (free poses first by q, then fixed poses by row;
   // addEdge order inside a pose), in place in pt_edges; a hash of its free-pose list, its first
   // pose, its number of (pose, landmark) pairs and of W pairs.  For every active landmark,
@@ -907,7 +912,6 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   s.slot_vertex.assign(slots.begin(), slots.end());
   s.slot_free.resize(s.n_slots);
   s.slot_pair_ptr.assign(s.n_slots + 1, 0);
-  s.slot_combo_ptr.assign(s.n_slots + 1, 0);
   const bool have_info = !g.e_info.empty(), have_delta = !g.e_delta.empty();
   // offsets of every slot's edges, pairs and Schur targets (prefix sums), then a parallel fill
   std::vector<int32_t> slot_edge_ptr(s.n_slots + 1, 0);
@@ -915,7 +919,6 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     const int j = slots[sl];
     slot_edge_ptr[sl + 1] = slot_edge_ptr[sl] + point_deg[j];
     s.slot_pair_ptr[sl + 1] = s.slot_pair_ptr[sl] + lm_npairs[j];
-    s.slot_combo_ptr[sl + 1] = s.slot_combo_ptr[sl] + lm_k[j] * (lm_k[j] + 1) / 2;
     s.slot_free[sl] = !lfix[j];
     if (!lfix[j]) ++s.n_fl;
   }
@@ -927,9 +930,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     if (have_delta) s.e_delta.resize(ne_local);
     s.pair_vertex.resize(np_local); s.pair_q.resize(np_local); s.pair_edge_ptr.resize(np_local + 1);
     s.pair_slot.resize(np_local);
-    s.combo_blk.resize((size_t)s.slot_combo_ptr[s.n_slots]);
     s.pair_edge_ptr[np_local] = (int32_t)ne_local;
-    std::vector<int> t_err(T, 0);
     pool.run(T, [&](int t, int TT) {
       int s0, s1; split_range(t, TT, s.n_slots, s0, s1);
       const double *__restrict__ ge_uv = g.e_uv.data();
@@ -938,11 +939,8 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
       double *__restrict__ o_uv = s.e_uv.data();
       uint8_t *__restrict__ o_cam = s.e_cam.data();
       int32_t *__restrict__ o_pv = s.pair_vertex.data(), *__restrict__ o_pq = s.pair_q.data(),
-              *__restrict__ o_pe = s.pair_edge_ptr.data(), *__restrict__ o_cb = s.combo_blk.data(),
+              *__restrict__ o_pe = s.pair_edge_ptr.data(),
               *__restrict__ o_ps = s.pair_slot.data();
-      int wq[64], wq_prev[64];
-      std::vector<int> wq_big;
-      int k_prev = -1, prev_combo0 = 0;
       for (int sl = s0; sl < s1; ++sl) {
         const int j = slots[sl];
         if (sl + 6 < s1) {  // the class order visits landmarks far apart in the caller's arrays
@@ -954,12 +952,8 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
           __builtin_prefetch(ge_cam + e_next);
         }
         if (sl + 12 < s1) __builtin_prefetch(pe + pt_ptr[slots[sl + 12]]);
-        const bool lfree = !lfix[j];
         size_t ne = (size_t)slot_edge_ptr[sl], npair = (size_t)s.slot_pair_ptr[sl];
-        const int kk = lm_k[j];
-        int *w = wq;
-        if (kk > 64) { wq_big.resize(kk); w = wq_big.data(); }
-        int nw = 0, last_pose = -1;
+        int last_pose = -1;
         const int k1 = pt_ptr[j + 1];
         for (int k = pt_ptr[j]; k < k1; ++k) {
           const int e = pe[k];
@@ -968,7 +962,6 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
             last_pose = pose;
             const int q = qmap[pose];
             o_pv[npair] = pose; o_pq[npair] = q; o_pe[npair] = (int32_t)ne; o_ps[npair] = sl; ++npair;
-            if (q >= 0 && lfree) w[nw++] = q;
           }
           o_orig[ne] = e;
           o_uv[2 * ne] = ge_uv[2 * (size_t)e]; o_uv[2 * ne + 1] = ge_uv[2 * (size_t)e + 1];
@@ -977,30 +970,18 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
           if (have_delta) s.e_delta[ne] = g.e_delta[e];
           ++ne;
         }
-        // Schur targets: for W-pairs a <= b (sorted by q): block (row q_b, col q_a); the previous
-        // landmark's list is reused when the pose list is the same (the common case after sorting)
-        const int c0 = s.slot_combo_ptr[sl], nc = nw * (nw + 1) / 2;
-        bool same = nw > 0 && nw == k_prev && nw <= 64;
-        if (same) for (int i = 0; i < nw; ++i) if (w[i] != wq_prev[i]) { same = false; break; }
-        if (same) {
-          for (int i = 0; i < nc; ++i) o_cb[c0 + i] = o_cb[prev_combo0 + i];
-        } else {
-          int c = c0;
-          for (int a2 = 0; a2 < nw; ++a2)
-            for (int b2 = a2; b2 < nw; ++b2) {
-              const int blk = find_block(w[b2], w[a2]);
-              if (blk < 0) t_err[t] = 1;
-              o_cb[c++] = blk;
-            }
-          if (nw <= 64) { for (int i = 0; i < nw; ++i) wq_prev[i] = w[i]; k_prev = nw; } else k_prev = -1;
-        }
-        prev_combo0 = c0;
       }
     });
-    for (int v : t_err) if (v) { err = "internal: Schur block missing from the factor pattern"; return false; }
   }
-
   tm.mark("slots / pairs / edges fill");
+  // the per-edge / per-pair arrays are final: the caller may start uploading them while the
+  // solver program and the small index lists are still being built
+  if (on_edges_ready) (*on_edges_ready)();
+  // The solver program (serial, the longest single piece of host work left) is built on a thread
+  // of its own while this one goes on with the chunk / unit / partial lists: it reads the factor
+  // structure only and writes prog / prog_ptr / solver_* only.
+  std::thread program_thread([&s] { build_solver_program(s); });
+  struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{program_thread};
   // ---- CTAs of the per-pair kernels: runs of whole landmarks with <= kLinPairs pairs
   {
     s.lchunk_slot.assign(1, 0);
@@ -1039,6 +1020,26 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
       sl = e;
     }
     s.n_units = (int)s.unit_slot.size();
+    // Schur targets of every unit: for its block pairs a <= b (poses of the run sorted by q):
+    // block (row q_b, col q_a) of the factor pattern
+    s.unit_combo_ptr.assign(s.n_units + 1, 0);
+    for (int u = 0; u < s.n_units; ++u) {
+      const int k = s.unit_k[u];
+      s.unit_combo_ptr[u + 1] = s.unit_combo_ptr[u] + std::min(32, k * (k + 1) / 2 - s.unit_c0[u]);
+    }
+    s.combo_blk.resize((size_t)s.unit_combo_ptr[s.n_units]);
+    for (int u = 0; u < s.n_units; ++u) {
+      const int k = s.unit_k[u], c0 = s.unit_c0[u], c1 = c0 + (s.unit_combo_ptr[u + 1] - s.unit_combo_ptr[u]);
+      const int32_t *qs = s.pair_q.data() + s.slot_pair_ptr[s.unit_slot[u]];
+      int idx = 0, o = s.unit_combo_ptr[u];
+      for (int a2 = 0; a2 < k && idx < c1; ++a2)
+        for (int b2 = a2; b2 < k && idx < c1; ++b2, ++idx) {
+          if (idx < c0) continue;
+          const int blk = find_block(qs[b2], qs[a2]);
+          if (blk < 0) { err = "internal: Schur block missing from the factor pattern"; return false; }
+          s.combo_blk[o++] = blk;
+        }
+    }
   }
 
   tm.mark("chunks + schur units");
@@ -1096,6 +1097,8 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     for (size_t i = 0; i < lp_q.size(); ++i) s.q_part[fill[lp_q[i]]++] = (int32_t)i;
   }
   tm.mark("hpp partial lists");
+  program_thread.join();
+  tm.mark("solver program (rest)");
   return true;
 }
 

@@ -12,6 +12,7 @@
 #pragma once
 
 #include <cstdint>
+#include <functional>
 #include <memory>
 #include <string>
 #include <utility>
@@ -79,13 +80,13 @@ struct Structure {
   uvec<uint8_t> e_cam;
   uvec<int32_t> e_orig;               // index in the caller's addEdge order
   uvec<double> e_info, e_delta;
-  // Schur accumulation targets: per free slot, for W-pairs i <= j (sorted by q): block (q_j, q_i)
-  std::vector<int32_t> slot_combo_ptr; // n_slots + 1
-  uvec<int32_t> combo_blk;
   // Schur work units (k_schur): run of landmarks [unit_slot, +unit_n) sharing one W pose list of
   // unit_k poses, block pairs [unit_c0, +32) of its k(k+1)/2
   int n_units = 0;
   std::vector<int32_t> unit_slot, unit_n, unit_k, unit_c0;
+  // Schur accumulation targets of every unit: for its W-pairs a <= b (sorted by q), block (q_b, q_a)
+  std::vector<int32_t> unit_combo_ptr;  // n_units + 1
+  uvec<int32_t> combo_blk;
   // ---- reduced system: lower block-CSC factor pattern (with fill) over q
   int n_blocks = 0, n_schur_blocks = 0;
   std::vector<int32_t> col_ptr;       // n_fp + 1, diagonal block first in every column
@@ -118,7 +119,10 @@ struct Structure {
 
 // Builds the structure for `rank` of `world`. Returns false and sets err on invalid input.
 // n_fp + n_fl_global == 0 is not an error here (caller maps it to SSBA_ERR_EMPTY).
-bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std::string &err);
+// `on_edges_ready` (optional) is called once the per-edge / per-pair arrays (slot_*, pair_*, e_*)
+// are final, before the solver program and the small index lists are built.
+bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std::string &err,
+                     const std::function<void()> *on_edges_ready = nullptr);
 
 // memcpy of several regions on the host thread pool of the structure builder
 struct CopyJob { void *dst; const void *src; size_t bytes; };

@@ -70,15 +70,34 @@ static void check_case(int nk, int np, int w, unsigned seed, bool fix0, int nfix
         CHECK(s.pair_q[a] > prev, "pairs not sorted by q"); prev = s.pair_q[a]; ++k;
         CHECK(s.q_of_pose[s.pair_vertex[a]] == s.pair_q[a], "pair_q mismatch");
       }
-      const int nc = s.slot_combo_ptr[sl + 1] - s.slot_combo_ptr[sl];
-      CHECK(nc == (s.slot_free[sl] ? k * (k + 1) / 2 : 0), "combo count %d vs k=%d", nc, k);
-      int c = s.slot_combo_ptr[sl];
-      if (s.slot_free[sl])
-        for (int i = 0; i < k; ++i)
-          for (int j = i; j < k; ++j, ++c) {
-            const int b = s.combo_blk[c];
-            CHECK(s.blk_col[b] == s.pair_q[s.slot_pair_ptr[sl] + i] && s.blk_row[b] == s.pair_q[s.slot_pair_ptr[sl] + j], "combo block wrong");
+    }
+    // Schur units: every free landmark is in exactly one run; the units of a run cover its
+    // k(k+1)/2 block pairs once, and their targets are the blocks (row q_b, col q_a)
+    {
+      std::vector<int> covered(s.n_slots, 0);
+      for (int u = 0; u < s.n_units; ++u) {
+        const int s0 = s.unit_slot[u], nrun = s.unit_n[u], k = s.unit_k[u], c0 = s.unit_c0[u];
+        const int nc = s.unit_combo_ptr[u + 1] - s.unit_combo_ptr[u];
+        CHECK(nc == std::min(32, k * (k + 1) / 2 - c0) && nc > 0, "unit %d: %d targets", u, nc);
+        if (c0 == 0) for (int i = 0; i < nrun; ++i) ++covered[s0 + i];
+        for (int i = 0; i < nrun; ++i) {
+          CHECK(s.slot_free[s0 + i], "fixed landmark in a Schur run");
+          for (int a = 0; a < k; ++a)
+            CHECK(s.pair_q[s.slot_pair_ptr[s0 + i] + a] == s.pair_q[s.slot_pair_ptr[s0] + a], "run with different pose lists");
+        }
+        int idx = 0;
+        for (int a = 0; a < k; ++a)
+          for (int b2 = a; b2 < k; ++b2, ++idx) {
+            if (idx < c0 || idx >= c0 + nc) continue;
+            const int b = s.combo_blk[s.unit_combo_ptr[u] + idx - c0];
+            CHECK(s.blk_col[b] == s.pair_q[s.slot_pair_ptr[s0] + a] && s.blk_row[b] == s.pair_q[s.slot_pair_ptr[s0] + b2], "combo block wrong");
           }
+      }
+      for (int sl = 0; sl < s.n_slots; ++sl) {
+        int k = 0;
+        for (int a = s.slot_pair_ptr[sl]; a < s.slot_pair_ptr[sl + 1]; ++a) if (s.pair_q[a] >= 0) ++k;
+        CHECK(covered[sl] == ((s.slot_free[sl] && k > 0) ? 1 : 0), "landmark %d in %d Schur runs", sl, covered[sl]);
+      }
     }
     for (int e = 0; e < s.n_edges; ++e) CHECK(s.e_orig[e] >= 0 && s.e_orig[e] < g.n_edges, "e_orig range");
     // Hpp partial bookkeeping: every free-pose pair is in exactly one partial of its chunk, and the
