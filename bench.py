@@ -158,7 +158,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD_DESC, "n_poses": g.n_poses, "n_points": g.n_points,
+        "config": {"workload": workload_desc(args.workload, g), "n_poses": g.n_poses, "n_points": g.n_points,
                    "n_edges": g.n_edges, "lm_iters_per_step": its, "host_cores_available": os.cpu_count()},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -369,7 +369,7 @@ def run_ssba(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD_DESC, "n_poses": g.n_poses, "n_points": g.n_points,
+            "config": {"workload": workload_desc(args.workload, g), "n_poses": g.n_poses, "n_points": g.n_points,
                        "n_edges": g.n_edges, "lm_iters_per_step": iters, "seed": 42,
                        "l2": "flushed between timed steps (256 MiB write); working set %.1f MB < 126 MB L2" % (info.device_bytes / 1e6),
                        "parallelism": "landmark-sharded x%d, NCCL all-reduce of the reduced pose system" % world if multi else "single GPU",
@@ -385,6 +385,12 @@ def run_ssba(args):
     if multi:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def workload_desc(name, g):
+    if name == WORKLOAD:
+        return WORKLOAD_DESC
+    return f"{name}: {g.n_poses} KF / {g.n_points} landmarks / {g.n_edges} edges, Huber {g.huber_delta}, {g.iters} LM iters (not the headline workload)"
 
 
 def ncu_traffic(kernel):

@@ -179,6 +179,7 @@ __device__ __forceinline__ void linearize_pair(const DeviceProblem &P, int a, bo
 }
 
 template <int kMode>
+// three CTAs per SM = 168 registers; measured on B200: four (128 registers, spills) 29 -> 43 us, two 29 -> 30 us
 __global__ void __launch_bounds__(kLinThreads, 3) k_linearize(const DeviceProblem P) {
   const Control *ctl = P.ctl;
   if (ctl->done || !ctl->need_linearize) return;

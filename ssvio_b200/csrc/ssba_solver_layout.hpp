@@ -12,8 +12,8 @@ constexpr size_t kSolveMaxDynSmem = 226 * 1024;  // opt-in dynamic shared memory
 constexpr int kSolveMaxCluster = 8;           // CTAs of the thread-block cluster the solver may span
 
 // Cluster size of the reduced solve for a system of n_fp pose columns: one SM is enough for a
-// small system (and a __syncthreads is cheaper than a cluster barrier); SSBA_SOLVE_CLUSTER
-// overrides the default of 4 (1, 2, 4 or 8).  Used by the host program builder (which deals the
+// small system (and a __syncthreads is cheaper than a cluster barrier), 4 CTAs below 64 poses, 8
+// above; SSBA_SOLVE_CLUSTER overrides (1, 2, 4 or 8).  Used by the host program builder (which deals the
 // columns of every level over the CTAs) and recorded in the structure for the launch.
 int solver_cluster_size(int n_fp);
 

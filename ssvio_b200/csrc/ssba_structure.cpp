@@ -20,10 +20,12 @@ namespace ssba {
 int solver_cluster_size(int n_fp) {
   static const int configured = [] {
     const char *e = std::getenv("SSBA_SOLVE_CLUSTER");
-    const int c = e ? std::atoi(e) : 4;
-    return (c == 1 || c == 2 || c == 4 || c == 8) ? c : 4;
+    const int c = e ? std::atoi(e) : 0;
+    return (c == 1 || c == 2 || c == 4 || c == 8) ? c : 0;
   }();
-  return n_fp >= 32 ? configured : 1;
+  if (n_fp < 32) return 1;
+  if (configured) return configured;
+  return n_fp < 64 ? 4 : 8;  // measured on B200: cfg3 (100 poses) 4 -> 8 CTAs: -2 %, cfg5 (500 poses): -13 %
 }
 
 namespace {

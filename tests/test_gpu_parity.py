@@ -109,16 +109,33 @@ def test_against_compiled_reference_live(BA, ref_oracle):
 
 
 def test_long_run_rejections_and_terminate(BA):
-    """lambda decays until steps get rejected and LM terminates (levenberg.cpp:137-148)."""
+    """lambda decays until steps get rejected and LM terminates (levenberg.cpp:137-148).
+
+    The graph has no fixed vertex, so once lambda is ~1e-7 the reduced system is singular up to
+    rounding and the accept / reject decisions of the last few iterations are rounding noise
+    (in the reference too).  The trajectory is therefore compared strictly over the converging
+    prefix, and the chaotic tail only through what must hold anyway: it terminates early after
+    rejections, and ends at the reference's minimum within the north-star tolerance."""
     g, _ = golden_case("tiny_long")
     gold = golden_scalars()["tiny_long"]["analytic"]
-    rep = run_gpu(BA, g)["report"]
-    assert rel(rep.chi2_robust, gold["chi2_robust"]) < CHI2_RTOL_SAME_JACOBIAN
-    n = min(converging_prefix(rep.trace()), converging_prefix(gold["trace"]))
+    n = converging_prefix(gold["trace"])
     assert n >= 10
-    for (chi, lam, trials), (gchi, glam, gtrials) in list(zip(rep.trace(), gold["trace"]))[:n]:
-        assert rel(chi, gchi) < 1e-9 and trials == gtrials
-    assert max(t[2] for t in rep.trace()) > 1
+    # strict: the first n iterations, run on their own
+    rep = run_gpu(BA, g, iters=n)["report"]
+    tr = rep.trace()
+    assert rep.iterations == n, tr
+    for i, ((chi, lam, trials), (gchi, glam, gtrials)) in enumerate(zip(tr, gold["trace"][:n])):
+        assert rel(chi, gchi) < 1e-9 and rel(lam, glam) < 1e-6 and trials == gtrials, f"iteration {i}: {tr}"
+    assert rel(rep.chi2_robust, gold["trace"][n - 1][0]) < CHI2_RTOL_SAME_JACOBIAN
+    # the full run: same prefix, then rejections and an early Terminate
+    rep = run_gpu(BA, g)["report"]
+    tr = rep.trace()
+    ctx = f"iterations={rep.iterations} chol_fail={rep.cholesky_failures} chi2={rep.chi2_robust!r} trace={tr}"
+    for i, ((chi, lam, trials), (gchi, glam, gtrials)) in enumerate(list(zip(tr, gold["trace"]))[:n]):
+        assert rel(chi, gchi) < 1e-9 and trials == gtrials, f"iteration {i}: {ctx}"
+    assert rep.iterations < g.iters and rep.last_result == 2, ctx   # SSBA_SOLVER_TERMINATE
+    assert max(t[2] for t in tr) > 1, ctx
+    assert rel(rep.chi2_robust, gold["chi2_robust"]) < CHI2_RTOL, ctx
 
 
 def test_step_api_equals_optimize(BA):
