@@ -143,6 +143,12 @@ class PortOracle(_OracleBase):
                       C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                       C.POINTER(Report)]
 
+    def set_tau(self, tau: float = 1e-5):
+        """_tau of the Levenberg initialisation (levenberg.cpp:44-51); 1e-5 is g2o's default."""
+        self.lib.ssba_oracle_set_tau.argtypes = [C.c_double]
+        self.lib.ssba_oracle_set_tau.restype = None
+        self.lib.ssba_oracle_set_tau(float(tau))
+
     def optimize(self, g, iters=None, jacobian="numeric"):
         iters = g.iters if iters is None else iters
         rep = Report()

@@ -639,6 +639,11 @@ int ssba_oracle_reduced_system(const double K[9], int32_t n_cams, const double *
   return rc;
 }
 
+/* _tau of OptimizationAlgorithmLevenberg (levenberg.cpp:44-51, default 1e-5); a test knob: a tiny
+ * tau starts LM as Gauss-Newton, which makes the first trials overshoot and get rejected. */
+static double g_tau = 1e-5;
+void ssba_oracle_set_tau(double tau) { g_tau = tau; }
+
 int ssba_oracle_optimize(const double K[9], int32_t n_cams, const double *ext_qt,
                          int32_t n_poses, const double *poses_qt, const uint8_t *pose_fixed,
                          int32_t n_points, const double *points, const uint8_t *point_fixed,
@@ -663,7 +668,7 @@ int ssba_oracle_optimize(const double K[9], int32_t n_cams, const double *ext_qt
 
   /* optimize() outer loop (sparse_optimizer.cpp:386-426) around
    * OptimizationAlgorithmLevenberg::solve (levenberg.cpp:58-150) */
-  const double tau = 1e-5, good_upper = 2. / 3., good_lower = 1. / 3.;
+  const double tau = g_tau, good_upper = 2. / 3., good_lower = 1. / 3.;
   const int max_trials = 10;
   double lambda = -1., ni = 2.;
   int result = SSBA_SOLVER_OK;

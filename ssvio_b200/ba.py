@@ -174,7 +174,7 @@ class BundleAdjuster:
 
     def __init__(self, *, jacobian="analytic", device_id=-1, stream=None, profile=False,
                  rank=0, world_size=1, nccl_id: bytes | None = None, user_lambda_init=0.0,
-                 max_trials_after_failure=10):
+                 max_trials_after_failure=10, tau=None):
         self.lib = load_library()
         opt = Options()
         self.lib.ssba_default_options(C.byref(opt))
@@ -185,6 +185,8 @@ class BundleAdjuster:
         opt.rank, opt.world_size = rank, world_size
         opt.user_lambda_init = user_lambda_init
         opt.max_trials_after_failure = max_trials_after_failure
+        if tau is not None:
+            opt.tau = tau  # _tau of the Levenberg initialisation (levenberg.cpp:44-51)
         if nccl_id is not None:
             C.memmove(opt.nccl_id, nccl_id, SSBA_NCCL_ID_BYTES)
         self._h = C.c_void_p()

@@ -207,8 +207,11 @@ bool symbolic_factor(int n, const std::vector<std::vector<int>> &adj, const std:
 void build_solver_program(Structure &s) {
   constexpr int kSplitPairs = 10;  // blocks with more update pairs get a REDUCE round
   constexpr int kSplitDiag = 1;    // ... diagonal blocks already with two
+  // (measured on B200, cfg3: the solve time moves by < 1 % for kSplitAcc 3..10, kAccMinPairs 1..6 and a
+  // level capacity of 100..250 % of the even share)
   constexpr int kSplitAcc = 5;     // ... look-ahead tasks with more than five (they must not outlast the level's chain)
-  constexpr int kAccMinPairs = 3;  // tasks with more update pairs hand the early ones to the level before
+  constexpr int kAccMinPairs = 3;  // tasks with more update pairs hand the early ones to the levels before
+  constexpr int kAccCapPct = 150;  // look-ahead work a level takes, in % of an even share of all products  // tasks with more update pairs hand the early ones to the level before
   const int n = s.n_fp, NL = s.n_levels;
   std::vector<int> level_of(n, 0);
   for (int lv = 0; lv < NL; ++lv)
@@ -231,62 +234,88 @@ void build_solver_program(Structure &s) {
   // idle warps / CTAs); at its own level only the products of the columns of level lv - 1 are left
   // on the critical path.  Measured on B200 (cfg3): everything at lv - 1 overloads the levels below
   // the top separators, everything at sl + 1 the leaf levels; hence the load-levelled placement.
-  struct Task { int dst, pos; std::vector<std::pair<int, int>> pairs; };  // VEC: dst = -1 - column, pairs (block, -1 - col)
+  struct Task { int dst, pos, begin, end; };  // its pairs are tpairs[begin, end); VEC: dst = -1 - column, pairs (block, -1 - col)
+  std::vector<std::pair<int, int>> tpairs;
+  tpairs.reserve(s.pair_a.size() + s.row_blk.size() + 16);
   std::vector<std::vector<Task>> own(NL), early(NL);
   {
     // pass 1: the late products stay with their task; count the work every level has anyway
     std::vector<long long> load(NL, 0);
     long long total_pairs = 0;
-    struct Group { int lv, dst, sl; std::vector<std::pair<int, int>> pairs; };
-    std::vector<Group> groups;  // early products of one block from the columns of one level
-    std::vector<int> grp_of(NL, -1), touched;
+    struct Group { int lv, dst, sl, begin, end; };  // early products of one block from the columns of one level: gpairs[begin, end)
+    std::vector<Group> groups;
+    std::vector<std::pair<int, int>> gpairs;
+    gpairs.reserve(s.pair_a.size());
+    struct Early { int sl, a, b; };
+    std::vector<Early> tmp;
     for (int lv = 0; lv < NL; ++lv) {
       const int c0 = s.level_ptr[lv];
       const int t0 = s.ltask_ptr[lv], nt = s.ltask_ptr[lv + 1] - t0;
+      own[lv].reserve(nt);
       for (int t = 0; t < nt; ++t) {
-        Task tk{s.task_dst[t0 + t], s.task_pos[t0 + t], {}};
-        for (int l : touched) grp_of[l] = -1;
-        touched.clear();
+        Task tk{s.task_dst[t0 + t], s.task_pos[t0 + t], (int)tpairs.size(), 0};
         if (tk.dst >= 0) {
           const int p0 = s.task_pair_ptr[t0 + t], p1 = s.task_pair_ptr[t0 + t + 1];
           const bool look = lv >= 2 && p1 - p0 > kAccMinPairs;
+          tmp.clear();
           for (int p = p0; p < p1; ++p) {
             const int sl = level_of[s.blk_col[s.pair_a[p]]];  // the level that finishes both source blocks
-            if (look && sl <= lv - 2) {
-              if (grp_of[sl] < 0) { grp_of[sl] = (int)groups.size(); groups.push_back(Group{lv, tk.dst, sl, {}}); touched.push_back(sl); }
-              groups[grp_of[sl]].pairs.emplace_back(s.pair_a[p], s.pair_b[p]);
-            } else {
-              tk.pairs.emplace_back(s.pair_a[p], s.pair_b[p]);
-            }
+            if (look && sl <= lv - 2) tmp.push_back(Early{sl, s.pair_a[p], s.pair_b[p]});
+            else tpairs.emplace_back(s.pair_a[p], s.pair_b[p]);
           }
+          if (tmp.size() > 1) std::stable_sort(tmp.begin(), tmp.end(), [](const Early &x, const Early &y) { return x.sl < y.sl; });
+          for (size_t i = 0; i < tmp.size(); ++i) {
+            if (i == 0 || tmp[i].sl != tmp[i - 1].sl) {
+              if (i) groups.back().end = (int)gpairs.size();
+              groups.push_back(Group{lv, tk.dst, tmp[i].sl, (int)gpairs.size(), 0});
+            }
+            gpairs.emplace_back(tmp[i].a, tmp[i].b);
+          }
+          if (!tmp.empty()) groups.back().end = (int)gpairs.size();
           total_pairs += p1 - p0;
         } else {
           const int j = s.level_col[c0 + tk.pos];
-          for (int rr = s.row_ptr[j]; rr < s.row_ptr[j + 1]; ++rr) tk.pairs.emplace_back(s.row_blk[rr], -1 - s.row_col[rr]);
+          for (int rr = s.row_ptr[j]; rr < s.row_ptr[j + 1]; ++rr) tpairs.emplace_back(s.row_blk[rr], -1 - s.row_col[rr]);
         }
-        load[lv] += 1 + (long long)tk.pairs.size();
-        own[lv].push_back(std::move(tk));
+        tk.end = (int)tpairs.size();
+        load[lv] += 1 + (long long)(tk.end - tk.begin);
+        own[lv].push_back(tk);
       }
     }
     // pass 2: every group goes to the latest level of its window [sl + 1, lv - 1] that still has
     // room (an even share of all products, with some slack), else to the emptiest one; the groups
     // of one block that land on the same level are one ACC task
-    const long long cap = std::max<long long>(64, (total_pairs * 3 / 2) / std::max(1, NL));
-    std::vector<int> acc_at(NL, -1);
+    const long long cap = std::max<long long>(64, (total_pairs * kAccCapPct / 100) / std::max(1, NL));
+    std::vector<std::pair<int, int>> placed;  // (level, group) of the block being placed
+    auto flush = [&]() {
+      if (placed.empty()) return;
+      std::stable_sort(placed.begin(), placed.end(), [](const std::pair<int, int> &x, const std::pair<int, int> &y) { return x.first < y.first; });
+      for (size_t i = 0; i < placed.size(); ++i) {
+        const Group &g = groups[placed[i].second];
+        if (i == 0 || placed[i].first != placed[i - 1].first) {
+          if (i) early[placed[i - 1].first].back().end = (int)tpairs.size();
+          early[placed[i].first].push_back(Task{g.dst, 0, (int)tpairs.size(), 0});
+        }
+        tpairs.insert(tpairs.end(), gpairs.begin() + g.begin, gpairs.begin() + g.end);
+      }
+      early[placed.back().first].back().end = (int)tpairs.size();
+      placed.clear();
+    };
     int cur_dst = -1;
-    touched.clear();
-    for (const Group &g : groups) {
-      if (g.dst != cur_dst) { for (int l : touched) acc_at[l] = -1; touched.clear(); cur_dst = g.dst; }
+    for (int gi = 0; gi < (int)groups.size(); ++gi) {
+      const Group &g = groups[gi];
+      if (g.dst != cur_dst) { flush(); cur_dst = g.dst; }
+      const long long np = g.end - g.begin;
       int best = -1;
       for (int l = g.lv - 1; l > g.sl; --l)
-        if (load[l] + (long long)g.pairs.size() <= cap) { best = l; break; }
+        if (load[l] + np <= cap) { best = l; break; }
       if (best < 0) { best = g.sl + 1; for (int l = g.sl + 1; l < g.lv; ++l) if (load[l] < load[best]) best = l; }
-      load[best] += (long long)g.pairs.size();
-      if (acc_at[best] < 0) { acc_at[best] = (int)early[best].size(); early[best].push_back(Task{g.dst, 0, {}}); touched.push_back(best); }
-      Task &a = early[best][acc_at[best]];
-      a.pairs.insert(a.pairs.end(), g.pairs.begin(), g.pairs.end());
+      load[best] += np;
+      placed.emplace_back(best, gi);
     }
+    flush();
   }
+  std::vector<std::vector<GT>> diag(C), sub(C), vec(C), acc(C), big_diag(C), big_sub(C), big_vec(C), big_acc(C);
   for (int lv = 0; lv < NL; ++lv) {
     LevelPlan &lp = plan[lv];
     const int nc = s.level_ptr[lv + 1] - s.level_ptr[lv];
@@ -297,7 +326,7 @@ void build_solver_program(Structure &s) {
     std::vector<long long> load(C, 0);
     if (C > 1) {
       std::vector<long long> w(nc, 0);
-      for (const Task &tk : own[lv]) w[tk.pos] += 2 + (long long)tk.pairs.size();
+      for (const Task &tk : own[lv]) w[tk.pos] += 2 + (long long)(tk.end - tk.begin);
       std::vector<int> order(nc);
       std::iota(order.begin(), order.end(), 0);
       std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return w[x] > w[y]; });
@@ -306,10 +335,10 @@ void build_solver_program(Structure &s) {
         cta_of_pos[pos] = c; load[c] += w[pos];
       }
     }
-    std::vector<std::vector<GT>> diag(C), sub(C), vec(C), acc(C), big_diag(C), big_sub(C), big_vec(C), big_acc(C);
+    for (auto *k : {&diag, &sub, &vec, &acc, &big_diag, &big_sub, &big_vec, &big_acc}) for (auto &v : *k) v.clear();
     auto add_pairs = [&](const Task &tk) {
       GT gt{tk.dst, tk.pos, (int)lp.pairs.size(), 0};
-      lp.pairs.insert(lp.pairs.end(), tk.pairs.begin(), tk.pairs.end());
+      lp.pairs.insert(lp.pairs.end(), tpairs.begin() + tk.begin, tpairs.begin() + tk.end);
       gt.p1 = (int)lp.pairs.size();
       return gt;
     };
@@ -324,10 +353,10 @@ void build_solver_program(Structure &s) {
     {
       std::vector<const Task *> by_w;
       for (const Task &tk : early[lv]) by_w.push_back(&tk);
-      std::stable_sort(by_w.begin(), by_w.end(), [](const Task *x, const Task *y) { return x->pairs.size() > y->pairs.size(); });
+      std::stable_sort(by_w.begin(), by_w.end(), [](const Task *x, const Task *y) { return x->end - x->begin > y->end - y->begin; });
       for (const Task *tk : by_w) {
         const int c = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-        load[c] += 2 + (long long)tk->pairs.size();
+        load[c] += 2 + (long long)(tk->end - tk->begin);
         acc[c].push_back(add_pairs(*tk));
       }
     }
@@ -889,20 +918,47 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     int n_act_pts = 0;
     for (int j = 0; j < NP; ++j) if (point_active[j]) { ++bucket_cnt[lm_minq[j] + 1]; ++n_act_pts; }
     for (int q = 0; q <= n; ++q) bucket_cnt[q + 1] += bucket_cnt[q];
-    std::vector<int32_t> sorted(n_act_pts);
+    // (hash, landmark) keys side by side: the comparisons of the sort stay inside the array
+    std::vector<std::pair<uint64_t, int32_t>> sorted(n_act_pts);
     {
       std::vector<int32_t> fill(bucket_cnt.begin(), bucket_cnt.end() - 1);
-      for (int j = 0; j < NP; ++j) if (point_active[j]) sorted[fill[lm_minq[j]]++] = j;
+      for (int j = 0; j < NP; ++j) if (point_active[j]) sorted[fill[lm_minq[j]]++] = {lm_hash[j], j};
     }
+    // Inside a bucket the landmarks only have to be GROUPED by pose list (they arrive in
+    // landmark order, which every group keeps): a stable counting sort over the few distinct
+    // hashes, in order of first appearance; a comparison sort only if a bucket has many lists.
     pool.run(T, [&](int t, int TT) {
-      for (int q = t; q <= n; q += TT)
-        std::sort(sorted.begin() + bucket_cnt[q], sorted.begin() + bucket_cnt[q + 1],
-                  [&](int x, int y) { return lm_hash[x] != lm_hash[y] ? lm_hash[x] < lm_hash[y] : x < y; });
+      constexpr int kMaxGroups = 32;
+      std::vector<uint64_t> gh;
+      std::vector<int> gid;
+      std::vector<std::pair<uint64_t, int32_t>> tmp;
+      for (int q = t; q <= n; q += TT) {
+        std::pair<uint64_t, int32_t> *b = sorted.data() + bucket_cnt[q];
+        const int m = bucket_cnt[q + 1] - bucket_cnt[q];
+        if (m < 2) continue;
+        gh.clear(); gid.resize(m);
+        int gcnt[kMaxGroups + 1] = {0};
+        bool many = false;
+        for (int i = 0; i < m && !many; ++i) {
+          int gi = 0;
+          while (gi < (int)gh.size() && gh[gi] != b[i].first) ++gi;
+          if (gi == (int)gh.size()) { if (gi == kMaxGroups) { many = true; break; } gh.push_back(b[i].first); }
+          gid[i] = gi; ++gcnt[gi];
+        }
+        if (many) { std::sort(b, b + m); continue; }
+        if (gh.size() == 1) continue;
+        int off[kMaxGroups + 1];
+        off[0] = 0;
+        for (int gi = 0; gi < (int)gh.size(); ++gi) off[gi + 1] = off[gi] + gcnt[gi];
+        tmp.assign(b, b + m);
+        for (int i = 0; i < m; ++i) b[off[gid[i]]++] = tmp[i];
+      }
     });
     const long long total = n_active;
     long long seen = 0;
     slots.reserve(world > 1 ? n_act_pts / world + 64 : n_act_pts);
-    for (int j : sorted) {
+    for (const auto &hj : sorted) {
+      const int j = hj.second;
       // owner = the rank whose edge-quantile holds the first edge of this landmark
       const int owner = total > 0 ? (int)std::min<long long>(world - 1, seen * world / total) : 0;
       if (owner == rank) slots.push_back(j);
