@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "ssvio/g2otypes.hpp"
+#include "g2o/solvers/dense/linear_solver_dense.h"
 
 #include "ref_harness.h"
 
@@ -250,5 +251,74 @@ extern "C" int ssba_ref_optimize(
     }
   }
   if (collect_trace) optimizer.removePostIterationAction(&trace);
+  return 0;
+}
+
+
+// ---- FrontEnd::EstimateCurrentPose (src/ssvio/frontend.cpp:184-260) over flat arrays, one frame
+// at a time exactly like the front-end thread does it: the solver stack of :188-193, the vertex
+// of :196-203, the edges of :206-231 (identity information, default-delta Huber), the round loop
+// of :235-270.  features[i]->is_outlier_ lives in `outlier`.
+extern "C" int ssba_ref_pose_only(const double K9[9], int32_t n_frames, const int32_t *feat_ptr,
+                                  const double *poses_qt, const double *xyz, const double *uv,
+                                  int32_t rounds, int32_t iters, double chi2_threshold,
+                                  double *poses_out, uint8_t *outlier_out, int32_t *n_inliers_out,
+                                  double *chi2_out) {
+  Eigen::Matrix3d K;
+  K << K9[0], K9[1], K9[2], K9[3], K9[4], K9[5], K9[6], K9[7], K9[8];
+  for (int f = 0; f < n_frames; ++f) {
+    typedef g2o::BlockSolver_6_3 BlockSolverType;
+    typedef g2o::LinearSolverDense<BlockSolverType::PoseMatrixType> LinearSolverType;
+    auto solver = new g2o::OptimizationAlgorithmLevenberg(
+        g2o::make_unique<BlockSolverType>(g2o::make_unique<LinearSolverType>()));
+    g2o::SparseOptimizer optimizer;
+    optimizer.setAlgorithm(solver);
+    ssvio::VertexPose *vertex_pose = new ssvio::VertexPose();
+    vertex_pose->setId(0);
+    vertex_pose->setEstimate(se3_from_qt(poses_qt + 7 * f));
+    optimizer.addVertex(vertex_pose);
+    const int e0 = feat_ptr[f], n = feat_ptr[f + 1] - e0;
+    std::vector<ssvio::EdgeProjectionPoseOnly *> edges;
+    std::vector<uint8_t> outlier(n, 0);
+    edges.reserve(n);
+    int index = 1;
+    for (int i = 0; i < n; ++i) {
+      auto *edge = new ssvio::EdgeProjectionPoseOnly(
+          Eigen::Vector3d(xyz[3 * (e0 + i)], xyz[3 * (e0 + i) + 1], xyz[3 * (e0 + i) + 2]), K);
+      edge->setId(index);
+      edge->setVertex(0, vertex_pose);
+      edge->setMeasurement(Eigen::Vector2d(uv[2 * (e0 + i)], uv[2 * (e0 + i) + 1]));
+      edge->setInformation(Eigen::Matrix2d::Identity());
+      edge->setRobustKernel(new g2o::RobustKernelHuber);
+      edges.emplace_back(edge);
+      optimizer.addEdge(edge);
+      index++;
+    }
+    int cnt_outliers = 0;
+    double chi_last = 0.0;
+    for (int iteration = 0; iteration < rounds; iteration++) {
+      optimizer.initializeOptimization();
+      optimizer.optimize(iters);
+      chi_last = optimizer.activeRobustChi2();
+      cnt_outliers = 0;
+      for (int i = 0; i < n; i++) {
+        auto e = edges[i];
+        if (outlier[i]) e->computeError();
+        if (e->chi2() > chi2_threshold) {
+          outlier[i] = 1;
+          e->setLevel(1);
+          cnt_outliers++;
+        } else {
+          outlier[i] = 0;
+          e->setLevel(0);
+        }
+        if (iteration == rounds - 2) e->setRobustKernel(nullptr);
+      }
+    }
+    if (poses_out) qt_from_se3(vertex_pose->estimate(), poses_out + 7 * f);
+    if (outlier_out) std::memcpy(outlier_out + e0, outlier.data(), n);
+    if (n_inliers_out) n_inliers_out[f] = n - cnt_outliers;
+    if (chi2_out) chi2_out[f] = chi_last;
+  }
   return 0;
 }

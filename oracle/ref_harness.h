@@ -56,6 +56,28 @@ int ssba_ref_optimize(const double K[9], int32_t n_cams, const double *ext_qt,
                       ssba_report *report, ssba_ref_stats *stats, int32_t *rounds_done,
                       int64_t *n_outliers);
 
+/*
+ * Pose-only LM of FrontEnd::EstimateCurrentPose() (src/ssvio/frontend.cpp:184-260), frame by
+ * frame: one VertexPose, one EdgeProjectionPoseOnly (include/ssvio/g2otypes.hpp:67-110, analytic
+ * Jacobian as shipped) per feature with identity information and a default RobustKernelHuber
+ * (delta = 1), BlockSolver_6_3 + LinearSolverDense + Levenberg; `rounds` rounds (4 in the
+ * reference) of initializeOptimization(); optimize(iters) (10), after each of which every
+ * feature is re-classified by chi2() > chi2_threshold (5.991; outliers get level 1 and their error
+ * recomputed before the test), and the robust kernel is removed at the end of round rounds - 2.
+ *
+ *   feat_ptr[n_frames + 1]  features of frame f = [feat_ptr[f], feat_ptr[f + 1])
+ *   poses_qt                n_frames x 7 initial T_cw (qx qy qz qw tx ty tz)
+ *   xyz, uv                 per feature: map-point position, measured pixel
+ * Outputs (may be NULL): optimised poses, per-feature outlier flag, per-frame inlier count
+ * (what EstimateCurrentPose returns), per-frame activeRobustChi2 after the last round's optimize.
+ * Returns 0 on success.
+ */
+int ssba_ref_pose_only(const double K[9], int32_t n_frames, const int32_t *feat_ptr,
+                       const double *poses_qt, const double *xyz, const double *uv,
+                       int32_t rounds, int32_t iters, double chi2_threshold,
+                       double *poses_out, uint8_t *outlier_out, int32_t *n_inliers_out,
+                       double *chi2_out);
+
 #ifdef __cplusplus
 }
 #endif

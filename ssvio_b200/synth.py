@@ -218,3 +218,47 @@ def make_config(name: str, seed: int = 42, **overrides) -> Graph:
     kw.update(overrides)
     iters = kw.pop("iters", 10)
     return make_graph(seed=seed, name=name, iters=iters, **kw)
+
+
+# --------------------------------------------------------------------------- pose-only frames
+
+@dataclasses.dataclass
+class PoseOnlyBatch:
+    """A batch of front-end pose estimations (src/ssvio/frontend.cpp:184-260): per frame an initial
+    T_cw and its features = (map-point position, measured pixel in the left camera)."""
+
+    K: np.ndarray         # (9,)
+    feat_ptr: np.ndarray  # (F + 1,) int32
+    poses: np.ndarray     # (F, 7) initial T_cw
+    xyz: np.ndarray       # (N, 3)
+    uv: np.ndarray        # (N, 2)
+
+    @property
+    def n_frames(self) -> int:
+        return int(self.poses.shape[0])
+
+
+def make_pose_only(n_frames: int, n_features: int, *, seed: int = 42, pixel_sigma: float = 0.7,
+                   outlier_frac: float = 0.1, outlier_sigma: float = 25.0, pose_sigma_t: float = 0.08,
+                   pose_sigma_r: float = 0.01) -> PoseOnlyBatch:
+    """Frames along the KITTI-shaped trajectory of make_graph; every frame sees `n_features`
+    (+-25 %) map points 8..48 m ahead; 10 % of the measurements are gross outliers, which the
+    reference's four rounds have to find; the initial pose is the truth perturbed like a
+    constant-velocity prediction would be."""
+    rng = _Rng(seed)
+    K = np.array([FX, 0, CX, 0, FY, CY, 0, 0, 1], dtype=np.float64)
+    counts = np.maximum(8, (n_features * rng.uniform(0.75, 1.25, n_frames)).astype(np.int64))
+    feat_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    n = int(feat_ptr[-1])
+    idx = np.arange(n_frames, dtype=np.float64)
+    gt = se3_exp(np.stack([0.02 * idx, 0.01 * idx, -1.0 * idx, 0.002 * idx, 0.002 * idx, 0.002 * idx], axis=1))
+    frame_of = np.repeat(np.arange(n_frames), counts)
+    pc = np.stack([rng.uniform(-15, 15, n), rng.uniform(-3, 3, n), rng.uniform(8, 48, n)], axis=1)
+    xyz = se3_act(se3_inv(gt)[frame_of], pc)
+    uv = np.stack([FX * pc[:, 0] / pc[:, 2] + CX, FY * pc[:, 1] / pc[:, 2] + CY], axis=1)
+    uv = uv + pixel_sigma * rng.normal((n, 2))
+    bad = rng.uniform(0, 1, n) < outlier_frac
+    uv = uv + bad[:, None] * outlier_sigma * rng.normal((n, 2))
+    d = np.concatenate([pose_sigma_t * rng.normal((n_frames, 3)), pose_sigma_r * rng.normal((n_frames, 3))], axis=1)
+    poses = se3_mul(se3_exp(d), gt)
+    return PoseOnlyBatch(K=K, feat_ptr=feat_ptr, poses=poses, xyz=xyz, uv=uv)
