@@ -244,6 +244,29 @@ ssba_status ssba_plan_shards(int32_t n_poses, const uint8_t *pose_fixed, int32_t
 
 /* ---- instrumentation --------------------------------------------------------------- */
 
+/* ---- pose-only LM, batched: FrontEnd::EstimateCurrentPose()
+ * (src/ssvio/frontend.cpp:184-260) for n_frames frames in one call.  Per frame: one VertexPose, one
+ * EdgeProjectionPoseOnly (include/ssvio/g2otypes.hpp:67-110, analytic Jacobian as shipped) per
+ * feature with identity information and g2o's default Huber kernel (delta 1), Levenberg with the
+ * dense 6x6 solve (BlockSolver_6_3 + LinearSolverDense, frontend.cpp:188-193); `rounds` rounds (the
+ * reference: 4) of initializeOptimization(); optimize(iters) (10), each followed by the
+ * re-classification of every feature by chi2() > chi2_threshold (5.991; outliers leave the next
+ * round, frontend.cpp:243-262), the robust kernel removed after round rounds - 2 (:265-268).
+ *   feat_ptr[n_frames + 1]   features of frame f = [feat_ptr[f], feat_ptr[f + 1])
+ *   poses_in / poses_out     n_frames x 7 T_cw (qx qy qz qw tx ty tz): initial / optimised
+ *   xyz, uv                  per feature: map-point position, measured pixel (K: row-major 3x3)
+ *   outlier_out              per feature: features[i]->is_outlier_ after the last round
+ *   n_inliers_out            per frame: what EstimateCurrentPose returns
+ *   chi2_out                 per frame: activeRobustChi2() after the last optimize (may be NULL)
+ * The LM constants are the handle's ssba_options (tau, step scales, max trials).  All arrays are
+ * host memory; the call is synchronous.  Runs on the handle's device and stream; the handle's
+ * bundle-adjustment problem, if any, is untouched. */
+ssba_status ssba_pose_only_optimize(ssba_handle *h, const double K[9], int32_t n_frames,
+                                    const int32_t *feat_ptr, const double *poses_in, const double *xyz,
+                                    const double *uv, int32_t rounds, int32_t iters, double chi2_threshold,
+                                    double *poses_out, uint8_t *outlier_out, int32_t *n_inliers_out,
+                                    double *chi2_out);
+
 /* Turn the per-phase CUDA-event timers on or off after creation (ssba_options::profile sets
  * the initial state).  The timers add event records to the stream, so benchmarks time with
  * them off and profile in a separate pass. */

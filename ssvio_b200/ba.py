@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "ssba_set_edges", "ssba_initialize", "ssba_optimize", "ssba_step", "ssba_reset_state",
     "ssba_get_poses", "ssba_get_points", "ssba_get_edge_errors", "ssba_chi2",
     "ssba_count_outliers", "ssba_optimize_rounds", "ssba_plan_shards", "ssba_set_profiling", "ssba_profile_get",
-    "ssba_profile_reset", "ssba_get_problem_info",
+    "ssba_profile_reset", "ssba_get_problem_info", "ssba_pose_only_optimize",
     "ssba_version",
 ]
 
@@ -125,6 +125,8 @@ def load_library():
     lib.ssba_optimize_rounds.argtypes = [H, C.c_int32, C.c_int32, C.c_double, C.c_double, C.POINTER(C.c_int32),
                                          C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(Report)]
     lib.ssba_plan_shards.argtypes = [C.c_int32, bp, C.c_int32, bp, C.c_int32, ip, ip, C.c_int32, ip]
+    lib.ssba_pose_only_optimize.argtypes = [H, dp, C.c_int32, ip, dp, dp, dp, C.c_int32, C.c_int32, C.c_double,
+                                            dp, bp, ip, dp]
     lib.ssba_set_profiling.argtypes = [H, C.c_int32]
     lib.ssba_profile_get.argtypes = [H, C.POINTER(Profile)]
     lib.ssba_profile_reset.argtypes = [H]
@@ -324,6 +326,21 @@ class BundleAdjuster:
 
     def profile_reset(self):
         self._check(self.lib.ssba_profile_reset(self._h))
+
+    # -- pose-only LM of the front-end (frontend.cpp:184-260), batched over frames
+    def pose_only_optimize(self, batch, rounds=4, iters=10, chi2_threshold=5.991):
+        """batch: ssvio_b200.synth.PoseOnlyBatch.  Returns (poses, outlier flags, inliers per frame,
+        robust chi2 per frame)."""
+        nf, n = batch.n_frames, int(batch.xyz.shape[0])
+        K, fp = _c(batch.K, np.float64), _c(batch.feat_ptr, np.int32)
+        pin, xyz, uv = _c(batch.poses, np.float64), _c(batch.xyz, np.float64), _c(batch.uv, np.float64)
+        poses, chi = np.empty((nf, 7)), np.zeros(nf)
+        flags, n_in = np.zeros(n, np.uint8), np.zeros(nf, np.int32)
+        self._check(self.lib.ssba_pose_only_optimize(
+            self._h, _p(K, C.c_double), nf, _p(fp, C.c_int32), _p(pin, C.c_double), _p(xyz, C.c_double),
+            _p(uv, C.c_double), int(rounds), int(iters), float(chi2_threshold), _p(poses, C.c_double),
+            _p(flags, C.c_uint8), _p(n_in, C.c_int32), _p(chi, C.c_double)))
+        return poses, flags, n_in, chi
 
     def set_profiling(self, on: bool):
         self._check(self.lib.ssba_set_profiling(self._h, 1 if on else 0))

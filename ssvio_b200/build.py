@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libssba.so")
 
-SOURCES = ["ssba_kernels.cu", "ssba_api.cu", "ssba_structure.cpp"]
+SOURCES = ["ssba_kernels.cu", "ssba_pose_only.cu", "ssba_api.cu", "ssba_structure.cpp"]
 HEADERS = ["ssba_geometry.cuh", "ssba_device.hpp", "ssba_structure.hpp", "ssba_solver_layout.hpp"]
 
 NVCC_FLAGS = [

@@ -92,6 +92,9 @@ struct ssba_handle {
   std::vector<Span> spans;
   double setup_seconds = 0.0;
   std::vector<uint8_t> owner_mask;
+  // pose-only LM: its own grow-only device buffer and pinned staging
+  char *d_po = nullptr; size_t d_po_bytes = 0;
+  char *h_po = nullptr; size_t h_po_bytes = 0;
 };
 
 namespace {
@@ -333,6 +336,8 @@ void ssba_destroy(ssba_handle *h) {
   if (h->d_arena) cudaFree(h->d_arena);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->h_stage_b) cudaFreeHost(h->h_stage_b);
+  if (h->d_po) cudaFree(h->d_po);
+  if (h->h_po) cudaFreeHost(h->h_po);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->h_small) cudaFreeHost(h->h_small);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -755,6 +760,62 @@ ssba_status ssba_plan_shards(int32_t n_poses, const uint8_t *pose_fixed, int32_t
   std::string err;
   if (!plan_shards(g, world_size, owner, err)) return fail(nullptr, SSBA_ERR_INVALID_ARG, err);
   std::memcpy(owner_out, owner.data(), sizeof(int32_t) * (size_t)n_points);
+  return SSBA_OK;
+}
+
+ssba_status ssba_pose_only_optimize(ssba_handle *h, const double K[9], int32_t n_frames, const int32_t *feat_ptr,
+                                    const double *poses_in, const double *xyz, const double *uv, int32_t rounds,
+                                    int32_t iters, double chi2_threshold, double *poses_out, uint8_t *outlier_out,
+                                    int32_t *n_inliers_out, double *chi2_out) {
+  if (!h) return SSBA_ERR_INVALID_ARG;
+  if (!K || n_frames < 0 || rounds < 0 || iters < 0 || (n_frames > 0 && (!feat_ptr || !poses_in || !poses_out)))
+    return fail(h, SSBA_ERR_INVALID_ARG, "pose_only_optimize: bad arguments");
+  if (n_frames == 0) return SSBA_OK;
+  const int64_t n = feat_ptr[n_frames];
+  if (feat_ptr[0] != 0 || n < 0 || (n > 0 && (!xyz || !uv))) return fail(h, SSBA_ERR_INVALID_ARG, "pose_only_optimize: bad feature arrays");
+  for (int f = 0; f < n_frames; ++f)
+    if (feat_ptr[f + 1] < feat_ptr[f]) return fail(h, SSBA_ERR_INVALID_ARG, "pose_only_optimize: feat_ptr not monotone");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  // one device buffer, one pinned mirror: [feat_ptr | poses_in | xyz | uv] up, [poses | chi2 | inliers | flags] down
+  size_t top = 0;
+  auto place = [&](size_t bytes) { const size_t o = align_up(top); top = o + bytes; return o; };
+  const size_t o_fp = place(sizeof(int32_t) * (size_t)(n_frames + 1)), o_pin = place(56 * (size_t)n_frames),
+               o_xyz = place(24 * (size_t)n), o_uv = place(16 * (size_t)n);
+  const size_t up_bytes = align_up(top);
+  const size_t o_pout = place(56 * (size_t)n_frames), o_chi = place(8 * (size_t)n_frames),
+               o_nin = place(4 * (size_t)n_frames), o_flag = place((size_t)n);
+  const size_t down_end = align_up(top);
+  const size_t o_err = place(16 * (size_t)n);
+  const size_t total = align_up(top);
+  if (total > h->d_po_bytes) {
+    if (h->d_po) cudaFree(h->d_po);
+    h->d_po = nullptr; h->d_po_bytes = 0;
+    if (cudaMalloc((void **)&h->d_po, total + total / 4) != cudaSuccess) { cudaGetLastError(); return fail(h, SSBA_ERR_ALLOC, "cudaMalloc failed"); }
+    h->d_po_bytes = total + total / 4;
+  }
+  if (down_end > h->h_po_bytes) {
+    if (h->h_po) cudaFreeHost(h->h_po);
+    h->h_po = nullptr; h->h_po_bytes = 0;
+    if (cudaHostAlloc((void **)&h->h_po, down_end + down_end / 4, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return fail(h, SSBA_ERR_ALLOC, "cudaHostAlloc failed"); }
+    h->h_po_bytes = down_end + down_end / 4;
+  }
+  std::memcpy(h->h_po + o_fp, feat_ptr, sizeof(int32_t) * (size_t)(n_frames + 1));
+  std::memcpy(h->h_po + o_pin, poses_in, 56 * (size_t)n_frames);
+  if (n) { std::memcpy(h->h_po + o_xyz, xyz, 24 * (size_t)n); std::memcpy(h->h_po + o_uv, uv, 16 * (size_t)n); }
+  CUDA_TRY(h, cudaMemcpyAsync(h->d_po, h->h_po, up_bytes, cudaMemcpyHostToDevice, h->stream));
+  char *d = h->d_po;
+  launch_pose_only(K, n_frames, rounds, iters, h->opt.max_trials_after_failure, chi2_threshold, h->opt.tau,
+                   h->opt.good_step_lower_scale, h->opt.good_step_upper_scale, (const int32_t *)(d + o_fp),
+                   (const double *)(d + o_pin), (const double *)(d + o_xyz), (const double *)(d + o_uv), (double *)(d + o_err),
+                   (uint8_t *)(d + o_flag), (double *)(d + o_pout), (double *)(d + o_chi), (int32_t *)(d + o_nin), h->stream);
+  h->prof.kernel_launches += 1;
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_po + o_pout, d + o_pout, down_end - o_pout, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaGetLastError());
+  std::memcpy(poses_out, h->h_po + o_pout, 56 * (size_t)n_frames);
+  if (chi2_out) std::memcpy(chi2_out, h->h_po + o_chi, 8 * (size_t)n_frames);
+  if (n_inliers_out) std::memcpy(n_inliers_out, h->h_po + o_nin, 4 * (size_t)n_frames);
+  if (outlier_out && n) std::memcpy(outlier_out, h->h_po + o_flag, (size_t)n);
   return SSBA_OK;
 }
 

@@ -109,4 +109,10 @@ void launch_edge_errors(const DeviceProblem &P, cudaStream_t st);      // -> err
 void launch_gather_points(const DeviceProblem &P, cudaStream_t st);    // -> gather
 int kernels_per_linearize();
 
+// batched pose-only LM (ssba_pose_only.cu): one warp per frame, everything in one launch
+void launch_pose_only(const double K[9], int n_frames, int rounds, int iters, int max_trials, double chi2_threshold,
+                      double tau, double good_lower, double good_upper, const int32_t *feat_ptr, const double *poses_in,
+                      const double *xyz, const double *uv, double *err, uint8_t *outlier, double *poses_out,
+                      double *chi2_out, int32_t *n_inliers_out, cudaStream_t st);
+
 }  // namespace ssba
