@@ -19,6 +19,9 @@ namespace ssba {
 namespace {
 
 constexpr int kLinThreads = 128;
+#ifndef SSBA_LIN_MINB
+#define SSBA_LIN_MINB 3  // CTAs per SM k_linearize is compiled for (factored path: 134 registers, no spills)
+#endif
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -178,9 +181,135 @@ __device__ __forceinline__ void linearize_pair(const DeviceProblem &P, int a, bo
   }
 }
 
+// Closed-form path (the default).  The quadratic form of a (pose, landmark) pair factors through
+// the body-frame point b = T p: for every camera J_xi = Jc [ I | -[b]x ] and J_p = Jc R with
+// Jc = Jpi R_ext (2x3), so with  M = sum_cam Jc^T (rho' Omega) Jc  (3x3) and
+// g = sum_cam Jc^T (-rho' Omega e)  the pair contributes
+//     Hpp = A^T M A,  b_p = A^T g,  Hll = R^T M R,  b_l = R^T g,  W = A^T M R,   A = [ I | -[b]x ],
+// i.e. the per-edge work is a 3x3 accumulation and the 6x6 / 6x3 / 3x3 blocks are expanded once per
+// pair (about a quarter of the fp64 work of expanding every edge, and nothing is re-read from shared
+// memory).  Same sums as base_binary_edge.hpp:61-134 up to the order of the additions.
+__device__ __forceinline__ void cross3(const double *a, double x, double y, double z, double &ox, double &oy, double &oz) {
+  ox = a[1] * z - a[2] * y; oy = a[2] * x - a[0] * z; oz = a[0] * y - a[1] * x;
+}
+__device__ __forceinline__ void linearize_pair_factored(const DeviceProblem &P, int a, bool lfree, const double *pose,
+                                                        const double *p, PairLin &o, double *hp) {
+  const int kv = P.pair_vertex[a];
+  const bool pfree = P.pair_q[a] >= 0;
+  const bool wpair = lfree && pfree;
+  double T[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) T[i] = pose[7 * kv + i];
+  double b[3];
+  se3_act(T, p[0], p[1], p[2], b[0], b[1], b[2]);
+  double M[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};  // M: xx xy xz yy yz zz
+  o.chi = 0.0;
+  const int e1 = P.pair_edge_ptr[a + 1];
+  for (int e = P.pair_edge_ptr[a]; e < e1; ++e) {
+    const int cam = P.e_cam[e];
+    const double *K = P.cams.K, *Re = P.ext_R[cam];
+    double cx, cy, cz;
+    se3_act(P.cams.ext[cam], b[0], b[1], b[2], cx, cy, cz);
+    const double n0 = K[0] * cx + K[1] * cy + K[2] * cz;
+    const double n1 = K[3] * cx + K[4] * cy + K[5] * cz;
+    const double dn = K[6] * cx + K[7] * cy + K[8] * cz;
+    const double id = 1.0 / dn, id2 = id * id;
+    EdgeTerms t;
+    t.e0 = P.e_uv[2 * e] - n0 / dn;
+    t.e1 = P.e_uv[2 * e + 1] - n1 / dn;
+    load_edge_weighting(P, P.e_info, P.e_delta, e, t);
+    o.chi += t.rho0;
+    double J0[3], J1[3];  // rows of Jc = Jpi R_ext
+    {
+      double q0[3], q1[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        q0[c] = -(K[c] * id - n0 * K[6 + c] * id2);
+        q1[c] = -(K[3 + c] * id - n1 * K[6 + c] * id2);
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        J0[c] = q0[0] * Re[c] + q0[1] * Re[3 + c] + q0[2] * Re[6 + c];
+        J1[c] = q1[0] * Re[c] + q1[1] * Re[3 + c] + q1[2] * Re[6 + c];
+      }
+    }
+    double A0[3], A1[3];  // rows of (rho' Omega) Jc
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      A0[c] = t.w * (t.o00 * J0[c] + t.o01 * J1[c]);
+      A1[c] = t.w * (t.o01 * J0[c] + t.o11 * J1[c]);
+    }
+    M[0] += J0[0] * A0[0] + J1[0] * A1[0]; M[1] += J0[0] * A0[1] + J1[0] * A1[1]; M[2] += J0[0] * A0[2] + J1[0] * A1[2];
+    M[3] += J0[1] * A0[1] + J1[1] * A1[1]; M[4] += J0[1] * A0[2] + J1[1] * A1[2]; M[5] += J0[2] * A0[2] + J1[2] * A1[2];
+    const double r0 = -t.w * t.we0, r1 = -t.w * t.we1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g[c] += J0[c] * r0 + J1[c] * r1;
+  }
+  const double Mr[3][3] = {{M[0], M[1], M[2]}, {M[1], M[3], M[4]}, {M[2], M[4], M[5]}};
+  // pose side: Hpp = [[M, N], [N^T, b x N]], N(r, :) = b x M(r, :);  b_p = [g ; b x g]
+  if (pfree) {
+    double N[3][3], BR[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) cross3(b, Mr[r][0], Mr[r][1], Mr[r][2], N[r][0], N[r][1], N[r][2]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) cross3(b, N[0][c], N[1][c], N[2][c], BR[0][c], BR[1][c], BR[2][c]);
+    hp[0] = g[0]; hp[1] = g[1]; hp[2] = g[2];
+    cross3(b, g[0], g[1], g[2], hp[3], hp[4], hp[5]);
+    int k = 6;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int c = r; c < 3; ++c) hp[k++] = Mr[r][c];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) hp[k++] = N[r][c];
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = r; c < 3; ++c) hp[k++] = BR[r][c];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 27; ++i) hp[i] = 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) o.H[i] = 0.0;
+  o.b[0] = o.b[1] = o.b[2] = 0.0;
+  if (lfree) {
+    double R[9], MR[3][3];
+    quat_to_matrix(T, R);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) MR[r][c] = Mr[r][0] * R[c] + Mr[r][1] * R[3 + c] + Mr[r][2] * R[6 + c];
+    // Hll = R^T (M R), b_l = R^T g
+    o.H[0] = R[0] * MR[0][0] + R[3] * MR[1][0] + R[6] * MR[2][0];
+    o.H[1] = R[0] * MR[0][1] + R[3] * MR[1][1] + R[6] * MR[2][1];
+    o.H[2] = R[0] * MR[0][2] + R[3] * MR[1][2] + R[6] * MR[2][2];
+    o.H[3] = R[1] * MR[0][1] + R[4] * MR[1][1] + R[7] * MR[2][1];
+    o.H[4] = R[1] * MR[0][2] + R[4] * MR[1][2] + R[7] * MR[2][2];
+    o.H[5] = R[2] * MR[0][2] + R[5] * MR[1][2] + R[8] * MR[2][2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o.b[c] = R[c] * g[0] + R[3 + c] * g[1] + R[6 + c] * g[2];
+    if (wpair) {
+      // W = [M R ; b x (M R)]  (6x3, row-major)
+      double Wv[18];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Wv[3 * r + c] = MR[r][c];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) cross3(b, MR[0][c], MR[1][c], MR[2][c], Wv[9 + c], Wv[12 + c], Wv[15 + c]);
+      double2 *dst = reinterpret_cast<double2 *>(P.W + 18 * (size_t)a);
+#pragma unroll
+      for (int i = 0; i < 9; ++i) dst[i] = make_double2(Wv[2 * i], Wv[2 * i + 1]);
+    }
+  }
+}
+
 template <int kMode>
-// three CTAs per SM = 168 registers; measured on B200: four (128 registers, spills) 29 -> 43 us, two 29 -> 30 us
-__global__ void __launch_bounds__(kLinThreads, 3) k_linearize(const DeviceProblem P) {
+// measured on B200 (cfg3): per-edge expansion 29 us (168 registers, spills); factored per pair 23 us at three
+// CTAs per SM, 24 us at four (125 registers) - the kernel is bound by its dependent-load chains, not occupancy
+__global__ void __launch_bounds__(kLinThreads, SSBA_LIN_MINB) k_linearize(const DeviceProblem P) {
   const Control *ctl = P.ctl;
   if (ctl->done || !ctl->need_linearize) return;
   __shared__ double red[kLinThreads / 32];
@@ -208,7 +337,8 @@ __global__ void __launch_bounds__(kLinThreads, 3) k_linearize(const DeviceProble
       const int pv = P.slot_vertex[sl];
       const double p[3] = {point[3 * pv], point[3 * pv + 1], point[3 * pv + 2]};
       PairLin o;
-      linearize_pair<kMode>(P, a, P.slot_free[sl] != 0, pose, p, o, s_hp[tid]);
+      if (kMode == SSBA_JACOBIAN_ANALYTIC) linearize_pair_factored(P, a, P.slot_free[sl] != 0, pose, p, o, s_hp[tid]);
+      else linearize_pair<kMode>(P, a, P.slot_free[sl] != 0, pose, p, o, s_hp[tid]);
       chi = o.chi;
 #pragma unroll
       for (int i = 0; i < 6; ++i) s_part[tid][i] = o.H[i];
@@ -252,8 +382,9 @@ __global__ void __launch_bounds__(kLinThreads, 3) k_linearize(const DeviceProble
     for (int a = a0 + tid; a < a1; a += kLinThreads) {
       PairLin o;
       // free-pose pairs come first inside a landmark, so the rank of one is simply a - a0
-      linearize_pair<kMode>(P, a, lfree, pose, p, o,
-                            P.pair_q[a] >= 0 ? P.hpp_part + 27 * (size_t)(lp0 + (a - a0)) : s_hp[tid]);
+      double *hp_dst = P.pair_q[a] >= 0 ? P.hpp_part + 27 * (size_t)(lp0 + (a - a0)) : s_hp[tid];
+      if (kMode == SSBA_JACOBIAN_ANALYTIC) linearize_pair_factored(P, a, lfree, pose, p, o, hp_dst);
+      else linearize_pair<kMode>(P, a, lfree, pose, p, o, hp_dst);
       chi += o.chi;
 #pragma unroll
       for (int i = 0; i < 6; ++i) acc[i] += o.H[i];
