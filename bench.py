@@ -372,7 +372,7 @@ def run_ssba(args):
             "config": {"workload": workload_desc(args.workload, g), "n_poses": g.n_poses, "n_points": g.n_points,
                        "n_edges": g.n_edges, "lm_iters_per_step": iters, "seed": 42,
                        "l2": "flushed between timed steps (256 MiB write); working set %.1f MB < 126 MB L2" % (info.device_bytes / 1e6),
-                       "parallelism": "landmark-sharded x%d, NCCL all-reduce of the reduced pose system" % world if multi else "single GPU",
+                       "parallelism": ("landmark-sharded x%d, %s of the reduced pose system" % (world, "NVLink peer-memory exchange" if info.peer_exchange else "NCCL all-reduce")) if multi else "single GPU",
                        "iter_algorithmic_bytes": b_iter,
                        "step_hbm_frac": (b_iter * iters / (total_ms / args.steps * 1e-3)) / 1e9 / peak,
                        "chi2_robust_final": chi2_final, "lm_iterations_done": its_done,

@@ -280,6 +280,9 @@ typedef struct ssba_problem_info {
   int32_t n_free_poses, n_free_points, n_active_edges, n_pairs;
   int32_t n_schur_blocks, n_factor_blocks;
   int64_t device_bytes;
+  int32_t solve_cluster;   /* CTAs of the thread-block cluster the reduced solve runs on          */
+  int32_t peer_exchange;   /* several GPUs: 1 = per-trial exchanges through NVLink peer memory,     */
+                           /* 0 = NCCL all-reduce (ranks on different nodes, or CUDA IPC refused)  */
 } ssba_problem_info;
 ssba_status ssba_get_problem_info(ssba_handle *h, ssba_problem_info *out);
 

@@ -39,6 +39,7 @@ struct Nccl {
   int (*CommInitRank)(void **, int, UniqueId, int) = nullptr;
   int (*CommDestroy)(void *) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
   bool load(std::string &err) {
     if (lib) return true;
@@ -49,6 +50,7 @@ struct Nccl {
     CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
     CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
     AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+    AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
     GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
     if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) { err = "libnccl lacks required symbols"; return false; }
     return true;
@@ -92,6 +94,12 @@ struct ssba_handle {
   std::vector<Span> spans;
   double setup_seconds = 0.0;
   std::vector<uint8_t> owner_mask;
+  // several GPUs: this rank's exchange buffer (cudaMalloc, shared with the peers through CUDA IPC) and the
+  // peers' buffers as mapped here; capacity in doubles per partial reduced system
+  char *xchg = nullptr; size_t xchg_cap_doubles = 0;
+  char *peer[SSBA_MAX_PEERS] = {nullptr};
+  bool use_p2p = false;
+  long long trial_seq = 0;
   // pose-only LM: its own grow-only device buffer and pinned staging
   char *d_po = nullptr; size_t d_po_bytes = 0;
   char *h_po = nullptr; size_t h_po_bytes = 0;
@@ -154,6 +162,69 @@ void collect_profile(ssba_handle *h) {
   h->ev_used = 0;
 }
 
+// ---- peer-memory exchange (several GPUs of one node): every rank allocates an exchange buffer, the CUDA IPC
+// handles travel through one ncclAllGather, every rank maps the others' buffers.  Collective: all ranks call
+// it with the same `sys_doubles` (they build the same structure).  On any failure the handle simply keeps
+// the NCCL path (use_p2p = false) - on every rank, because the outcome is agreed by an all-reduce (min).
+// Collective when a buffer exists: every rank unmaps its peers' buffers, then all ranks meet (a one-element
+// all-reduce) before anyone frees memory that another process may still have mapped.
+void close_peer_exchange(ssba_handle *h) {
+  const bool had = h->xchg != nullptr;
+  for (int r = 0; r < SSBA_MAX_PEERS; ++r) {
+    if (h->peer[r] && h->peer[r] != h->xchg) cudaIpcCloseMemHandle(h->peer[r]);
+    h->peer[r] = nullptr;
+  }
+  if (had && h->comm && h->use_p2p) {
+    double *d_one = (double *)(h->xchg + sizeof(PeerHeader));
+    if (g_nccl.AllReduce(d_one, d_one, 1, kNcclDouble, kNcclSum, h->comm, h->stream) == 0) cudaStreamSynchronize(h->stream);
+  }
+  if (h->xchg) cudaFree(h->xchg);
+  h->xchg = nullptr; h->xchg_cap_doubles = 0; h->use_p2p = false;
+}
+
+ssba_status setup_peer_exchange(ssba_handle *h, size_t sys_doubles) {
+  const int world = h->opt.world_size, rank = h->opt.rank;
+  if (world <= 1 || world > SSBA_MAX_PEERS || !g_nccl.AllGather) return SSBA_OK;
+  if (const char *e = std::getenv("SSBA_P2P")) if (std::atoi(e) == 0) return SSBA_OK;
+  if (sys_doubles <= h->xchg_cap_doubles && h->use_p2p) return SSBA_OK;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  close_peer_exchange(h);
+  const size_t cap = sys_doubles + sys_doubles / 2 + 4096;
+  const size_t bytes = sizeof(PeerHeader) + 2 * cap * sizeof(double);
+  int ok = 1;
+  if (cudaMalloc((void **)&h->xchg, bytes) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof(mine));
+  if (ok && cudaMemset(h->xchg, 0, bytes) != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&mine, h->xchg) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+  // handles of all ranks (device staging: NCCL moves device memory)
+  char *d_tmp = nullptr;
+  std::vector<cudaIpcMemHandle_t> all(world);
+  const size_t hb = sizeof(cudaIpcMemHandle_t);
+  CUDA_TRY(h, cudaMalloc((void **)&d_tmp, hb * (world + 1) + 64));
+  CUDA_TRY(h, cudaMemcpyAsync(d_tmp + hb * world, &mine, hb, cudaMemcpyHostToDevice, h->stream));
+  if (g_nccl.AllGather(d_tmp + hb * world, d_tmp, hb, /*ncclChar*/ 0, h->comm, h->stream) != 0) { cudaFree(d_tmp); return fail(h, SSBA_ERR_NCCL, "ncclAllGather failed"); }
+  CUDA_TRY(h, cudaMemcpyAsync(all.data(), d_tmp, hb * world, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < world && ok; ++r) {
+    if (r == rank) { h->peer[r] = h->xchg; continue; }
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+    h->peer[r] = (char *)p;
+  }
+  // agree on the outcome: min over ranks of `ok`
+  double okd = ok ? 1.0 : 0.0, *d_ok = (double *)d_tmp;
+  CUDA_TRY(h, cudaMemcpyAsync(d_ok, &okd, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (g_nccl.AllReduce(d_ok, d_ok, 1, kNcclDouble, /*ncclMin*/ 3, h->comm, h->stream) != 0) { cudaFree(d_tmp); return fail(h, SSBA_ERR_NCCL, "ncclAllReduce failed"); }
+  CUDA_TRY(h, cudaMemcpyAsync(&okd, d_ok, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  cudaFree(d_tmp);
+  if (okd < 0.5) { close_peer_exchange(h); return SSBA_OK; }
+  h->xchg_cap_doubles = cap;
+  h->use_p2p = true;
+  return SSBA_OK;
+}
+
 // one LM trial, stream-ordered; `first` = first slot of an optimize()/step(0) call
 ssba_status enqueue_slot(ssba_handle *h, bool first) {
   const DeviceProblem &P = h->P;
@@ -182,7 +253,11 @@ ssba_status enqueue_slot(ssba_handle *h, bool first) {
     launch_schur(P, first, st);
     h->prof.kernel_launches += 1;
   }
-  if (multi) { PhaseTimer t(h, 4); if ((rc = nccl_allreduce(h, P.sys, P.sys_doubles, kNcclSum))) return rc; }
+  if (multi) {
+    PhaseTimer t(h, 4);
+    if (P.use_p2p) { launch_exchange_sys(P, st); h->prof.kernel_launches += 1; }
+    else if ((rc = nccl_allreduce(h, P.sys, P.sys_doubles, kNcclSum))) return rc;
+  }
   {
     PhaseTimer t(h, 2);
     launch_reduced_solve(P, st);
@@ -192,9 +267,13 @@ ssba_status enqueue_slot(ssba_handle *h, bool first) {
     PhaseTimer t(h, 3);
     launch_update(P, !multi, st);
     h->prof.kernel_launches += 1;
-    if (multi) { launch_reduce_partials(P, st); h->prof.kernel_launches += 1; }
+    if (multi && !P.use_p2p) { launch_reduce_partials(P, st); h->prof.kernel_launches += 1; }
   }
-  if (multi) {
+  if (multi && P.use_p2p) {
+    PhaseTimer t(h, 4);
+    launch_control_p2p(P, st);  // partial sums through peer memory, then the decision
+    h->prof.kernel_launches += 1;
+  } else if (multi) {
     { PhaseTimer t(h, 4); if ((rc = nccl_allreduce(h, P.scal, 3, kNcclSum))) return rc; }
     launch_control(P, st);
     h->prof.kernel_launches += 1;
@@ -212,6 +291,7 @@ ssba_status run_lm(ssba_handle *h, int max_iters, bool iteration0) {
   c.cur = h->cur; c.need_linearize = 1; c.first_iteration = iteration0 ? 1 : 0;
   c.max_iters = max_iters; c.last_result = SSBA_SOLVER_OK;
   c.world = h->opt.world_size; c.rank = h->opt.rank;
+  c.trial_seq = h->trial_seq;
   CUDA_TRY(h, cudaMemcpyAsync(h->P.ctl, &c, sizeof(Control), cudaMemcpyHostToDevice, h->stream));
   // the copy above must have left the pinned buffer before it is reused for the read-back
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -235,7 +315,13 @@ ssba_status run_lm(ssba_handle *h, int max_iters, bool iteration0) {
     if (guard > max_slots) return fail(h, SSBA_ERR_STATE, "LM driver did not terminate");
   }
   h->cur = c.cur; h->lambda = c.lambda; h->ni = c.ni;
+  h->trial_seq = c.trial_seq;
+  if (h->opt.world_size > 1 && std::getenv("SSBA_TIMING"))
+    std::fprintf(stderr, "[ssba] rank %d last trial: exchange_sys wait %.2f us, sum %.2f us | gap to control %.2f us | fold %.2f us, scal exchange %.2f us, decision %.2f us\n",
+                 h->opt.rank, (c.dbg[1] - c.dbg[0]) * 1e-3, (c.dbg[2] - c.dbg[1]) * 1e-3, (c.dbg[3] - c.dbg[2]) * 1e-3, (c.dbg[4] - c.dbg[3]) * 1e-3,
+                 (c.dbg[5] - c.dbg[4]) * 1e-3, (c.dbg[6] - c.dbg[5]) * 1e-3);
   collect_profile(h);
+  if (c.comm_timeout) return fail(h, SSBA_ERR_NCCL, "peer-memory exchange: a rank did not publish its part in time");
   return SSBA_OK;
 }
 
@@ -331,6 +417,7 @@ void ssba_destroy(ssba_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  close_peer_exchange(h);
   if (h->comm) g_nccl.CommDestroy(h->comm);
   for (auto e : h->ev) cudaEventDestroy(e);
   if (h->d_arena) cudaFree(h->d_arena);
@@ -550,6 +637,15 @@ ssba_status ssba_initialize(ssba_handle *h) {
   P.prog_max_seg = s.prog_max_seg;
   P.n_segments = s.n_segments;
   P.solve_cluster = s.solve_cluster;
+  if (h->opt.world_size > 1) {
+    ssba_status prc = setup_peer_exchange(h, P.sys_doubles);
+    if (prc) return prc;
+    P.use_p2p = h->use_p2p ? 1 : 0;
+    for (int r = 0; r < SSBA_MAX_PEERS; ++r) P.peer[r] = h->peer[r];
+    // both partial systems of this graph's layout start out zero (no peer can still be reading: it
+    // published the flags the last k_control of this rank waited for only after it was done)
+    if (h->use_p2p) CUDA_TRY(h, cudaMemsetAsync(h->xchg + sizeof(PeerHeader), 0, 2 * sizeof(double) * P.sys_doubles, h->stream));
+  }
   P.n_units = s.n_units;
   h->initialized = true;
   h->dirty = false;
@@ -847,6 +943,8 @@ ssba_status ssba_get_problem_info(ssba_handle *h, ssba_problem_info *out) {
   out->n_active_edges = h->s.n_active_edges_global; out->n_pairs = h->s.n_pairs;
   out->n_schur_blocks = h->s.n_schur_blocks; out->n_factor_blocks = h->s.n_blocks;
   out->device_bytes = (int64_t)h->device_bytes;
+  out->solve_cluster = h->s.solve_cluster;
+  out->peer_exchange = h->use_p2p ? 1 : 0;
   return SSBA_OK;
 }
 

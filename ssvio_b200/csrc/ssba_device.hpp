@@ -35,7 +35,22 @@ struct Control {
   int n_records;
   int world, rank;
   unsigned int ticket;     // CTAs of k_update that have finished (the last one runs control_step)
+  long long trial_seq;     // trials executed on this handle so far (same on every rank): the sequence number of
+                           // the peer-memory exchanges
+  int comm_timeout;        // a peer did not publish its part in time (peer-memory exchange)
+  long long dbg[8];        // SSBA_TIMING: globaltimer stamps of the last trial's exchange kernels
   ssba_iter_record records[SSBA_MAX_ITER_RECORDS];
+};
+
+constexpr int SSBA_MAX_PEERS = 16;
+// head of a rank's exchange buffer.  Flags and the small partial sums are PUSHED: rank s writes them into
+// the `[s]` entries of every peer's header (remote stores over NVLink), so that a rank only ever polls its
+// own memory; the partial reduced systems (after the header, 2 x sys_doubles, indexed by trial parity) are
+// pulled by the readers.  Flags are trial sequence numbers.
+struct PeerHeader {
+  long long flag_sys_from[SSBA_MAX_PEERS];    // rank s's partial reduced system of that trial is complete
+  long long flag_scal_from[SSBA_MAX_PEERS];   // rank s's partial sums of that trial have arrived
+  double scal_from[SSBA_MAX_PEERS][2][4];     // [s][parity]: chi(current), chi(trial), landmark part of computeScale
 };
 
 struct DeviceProblem {
@@ -89,6 +104,10 @@ struct DeviceProblem {
   double *gather;     // n_points x 3, multi-GPU read-back of the landmark estimates
   const uint8_t *owner_mask;  // n_points: this rank reports the landmark
   Control *ctl;
+  // several GPUs, peer-memory exchange (ssba_api.cu setup_peer_exchange): every rank's exchange buffer as
+  // mapped into this process; layout per rank: PeerHeader, then 2 x sys_doubles partial reduced systems
+  char *peer[SSBA_MAX_PEERS];
+  int use_p2p;
   size_t sys_doubles;
   int n_edges_total;
 };
@@ -103,6 +122,8 @@ void launch_reduced_solve(const DeviceProblem &P, cudaStream_t st);
 void launch_update(const DeviceProblem &P, bool fused_control, cudaStream_t st);  // + accept/reject when fused
 void launch_reduce_partials(const DeviceProblem &P, cudaStream_t st);  // -> scal[0..2]
 void launch_control(const DeviceProblem &P, cudaStream_t st);          // several GPUs only
+void launch_exchange_sys(const DeviceProblem &P, cudaStream_t st);     // peer-memory all-reduce of the reduced system
+void launch_control_p2p(const DeviceProblem &P, cudaStream_t st);      // partial sums exchanged through peer memory + decision
 void launch_fold(const DeviceProblem &P, cudaStream_t st);           // first slot: hpp_fold + Hpp diagonals
 void launch_final_chi2(const DeviceProblem &P, double threshold, cudaStream_t st);  // -> chi_out
 void launch_edge_errors(const DeviceProblem &P, cudaStream_t st);      // -> err_out

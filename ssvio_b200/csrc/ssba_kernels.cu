@@ -8,6 +8,7 @@
 // taken on the device by k_control).
 //
 // Reference semantics per kernel are cited at each kernel; g2o/ = thirdparty/g2o/g2o/.
+#include <algorithm>
 #include <cfloat>
 #include <cstdlib>
 
@@ -486,6 +487,13 @@ constexpr int kSchurWarps = 4;
 constexpr int kSchurRunPairs = 80;  // W blocks of one run staged in shared memory (= host kSchurRunPairs)
 constexpr int kSchurRun = 16;       // landmarks per run (= host kSchurRun)
 
+// where k_schur accumulates: the solver's system, or (peer-memory exchange) this rank's partial of the
+// running trial, which k_exchange_sys then sums over the ranks into the solver's system
+__device__ __forceinline__ double *schur_target(const DeviceProblem &P, const Control *ctl) {
+  if (!P.use_p2p) return P.sys;
+  return reinterpret_cast<double *>(P.peer[ctl->rank] + sizeof(PeerHeader)) + (size_t)((ctl->trial_seq + 1) & 1) * P.sys_doubles;
+}
+
 __device__ __forceinline__ void schur_pose_warp(const DeviceProblem &P, const Control *ctl, int q, int lane,
                                                 bool prefolded) {
   double s;
@@ -496,7 +504,8 @@ __device__ __forceinline__ void schur_pose_warp(const DeviceProblem &P, const Co
     s = lane < 27 ? P.hpp_fold[27 * q + lane] : 0.0;
   }
   const double lambda = ctl->rank == 0 ? ctl->lambda : 0.0;
-  double *D = P.sys + 36 * (size_t)P.col_diag[q];
+  double *sysacc = schur_target(P, ctl);
+  double *D = sysacc + 36 * (size_t)P.col_diag[q];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int e = lane + 32 * h, ee = e < 36 ? e : 0;
@@ -506,7 +515,7 @@ __device__ __forceinline__ void schur_pose_warp(const DeviceProblem &P, const Co
     if (e < 36) atomicAdd(D + e, r == c ? v + lambda : v);
   }
   if (lane < 6) {
-    double *bsch = P.sys + 36 * (size_t)P.n_blocks + 6 * (size_t)q;
+    double *bsch = sysacc + 36 * (size_t)P.n_blocks + 6 * (size_t)q;
     atomicAdd(bsch + lane, s);               // bschur
     bsch[6 * (size_t)P.n_fp + lane] = s;     // b_p (kept for computeScale)
   }
@@ -643,11 +652,12 @@ __global__ void __launch_bounds__(32 * kSchurWarps, 3) k_schur(const DeviceProbl
     }
   }
   if (sub != 0) return;
-  double *dst = P.sys + 36 * (size_t)P.combo_blk[P.unit_combo_ptr[u] + ci];
+  double *sysacc = schur_target(P, ctl);
+  double *dst = sysacc + 36 * (size_t)P.combo_blk[P.unit_combo_ptr[u] + ci];
 #pragma unroll
   for (int i = 0; i < 36; ++i) atomicAdd(dst + i, -acc[i]);
   if (diag) {
-    double *bs = P.sys + 36 * (size_t)P.n_blocks + 6 * (size_t)P.pair_q[s_pair0[warp][0] + a];
+    double *bs = sysacc + 36 * (size_t)P.n_blocks + 6 * (size_t)P.pair_q[s_pair0[warp][0] + a];
 #pragma unroll
     for (int r = 0; r < 6; ++r) atomicAdd(bs + r, -accb[r]);
   }
@@ -1135,6 +1145,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
 // Runs on one thread once scal[0..2] = chi(current), chi(trial), landmark part of computeScale.
 __device__ void control_step(const DeviceProblem &P) {
   Control *c = P.ctl;
+  c->trial_seq++;
   const double currentChi = P.scal[0];
   double tempChi = P.scal[1];
   if (c->outer_iter == 0 && c->qmax == 0) c->chi2_initial = currentChi;
@@ -1255,7 +1266,11 @@ __global__ void __launch_bounds__(kLinThreads) k_update(const DeviceProblem P) {
   __shared__ int s_last;
   {
     const size_t nz = 36 * (size_t)P.n_blocks + 6 * (size_t)P.n_fp;  // blocks and bschur; b_p is overwritten
-    for (size_t i = (size_t)blockIdx.x * kLinThreads + threadIdx.x; i < nz; i += (size_t)gridDim.x * kLinThreads) P.sys[i] = 0.0;
+    // peer-memory exchange: the partial the NEXT trial accumulates into is the one the peers read
+    // one trial ago; their flag_scal of that trial (seen by the last k_control) says they are done
+    double *z = P.use_p2p ? reinterpret_cast<double *>(P.peer[ctl->rank] + sizeof(PeerHeader)) + (size_t)(ctl->trial_seq & 1) * P.sys_doubles
+                          : P.sys;
+    for (size_t i = (size_t)blockIdx.x * kLinThreads + threadIdx.x; i < nz; i += (size_t)gridDim.x * kLinThreads) z[i] = 0.0;
   }
   __shared__ double s_part[kLinThreads][3];
   __shared__ double s_pnew[kLinThreads][3];
@@ -1347,6 +1362,109 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const DeviceProblem P) 
 __global__ void k_control(const DeviceProblem P) {
   if (P.ctl->done) return;
   control_step(P);
+}
+
+// ---- several GPUs: the two exchanges of a trial through NVLink peer memory instead of NCCL calls.
+// Every rank owns an exchange buffer that all ranks have mapped (CUDA IPC).  Flags and the small
+// partial sums are pushed into the peers' headers (remote stores, release at system scope), so a
+// rank polls only its own memory; the partial reduced systems are pulled from the peers once their
+// flag is in.  Every rank adds the parts in rank order, so all ranks hold bitwise the same sums.  Parts are double-buffered by trial
+// parity: a buffer is rewritten two trials later, after flags that can only have been published
+// once every peer was done reading it.  A peer that does not show up within about a minute sets
+// comm_timeout (reported as SSBA_ERR_NCCL) instead of hanging the GPU.
+__device__ __forceinline__ long long ld_acquire_sys(const long long *p) {
+  long long v;
+  asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(long long *p, long long v) {
+  asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ bool wait_peer_flag(const long long *flag, long long seq) {
+  for (long long spin = 0; spin < (1ll << 27); ++spin) {  // about a minute: a peer may still be building its structure
+    if (ld_acquire_sys(flag) >= seq) return true;
+    __nanosleep(40);
+  }
+  return false;
+}
+
+__device__ __forceinline__ void st_f64_sys(double *p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
+constexpr int kXchgThreads = 256;
+__global__ void __launch_bounds__(kXchgThreads) k_exchange_sys(const DeviceProblem P) {
+  Control *ctl = P.ctl;
+  if (ctl->done) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctl->dbg[0] = gtime();
+  const long long seq = ctl->trial_seq + 1;  // the running trial
+  const int world = ctl->world, rank = ctl->rank, par = (int)(seq & 1);
+  __shared__ int s_ok;
+  if (threadIdx.x < 32) {
+    // k_schur of this trial is complete (stream order; its sums sit in this GPU's L2, which is where
+    // the peers read them): lane r of CTA 0 tells rank r (release, system scope); every CTA then
+    // waits for the peers' words in this rank's own header - no CTA waits for another one of this launch.
+    const int r = threadIdx.x;
+    bool ok = true;
+    if (r < world) {
+      if (blockIdx.x == 0) st_release_sys(&reinterpret_cast<PeerHeader *>(P.peer[r])->flag_sys_from[rank], seq);
+      if (r != rank) ok = wait_peer_flag(&reinterpret_cast<const PeerHeader *>(P.peer[rank])->flag_sys_from[r], seq);
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (threadIdx.x == 0) s_ok = ok ? 1 : 0;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctl->dbg[1] = gtime();
+  if (!s_ok) { if (threadIdx.x == 0) ctl->comm_timeout = 1; }
+  const size_t n2 = P.sys_doubles / 2;  // sys_doubles is even: 36 n_blocks + 12 n_fp
+  double2 *out = reinterpret_cast<double2 *>(P.sys);
+  for (size_t i = (size_t)blockIdx.x * kXchgThreads + threadIdx.x; i < n2; i += (size_t)gridDim.x * kXchgThreads) {
+    double2 acc = make_double2(0.0, 0.0);
+    for (int r = 0; r < world; ++r) {  // rank order: every rank gets bitwise the same sum
+      const double2 v = __ldcg(reinterpret_cast<const double2 *>(P.peer[r] + sizeof(PeerHeader)) + (size_t)par * n2 + i);
+      acc.x += v.x; acc.y += v.y;
+    }
+    out[i] = acc;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctl->dbg[2] = gtime();
+}
+
+__global__ void __launch_bounds__(256) k_control_p2p(const DeviceProblem P) {
+  Control *ctl = P.ctl;
+  if (ctl->done) return;
+  if (threadIdx.x == 0) ctl->dbg[3] = gtime();
+  __shared__ double red[8];
+  fold_partials<256>(P, red);  // this rank's sums -> scal[0..2]
+  __syncthreads();
+  if (threadIdx.x == 0) ctl->dbg[4] = gtime();
+  if (threadIdx.x >= 32) return;
+  const long long seq = ctl->trial_seq + 1;
+  const int world = ctl->world, rank = ctl->rank, par = (int)(seq & 1);
+  const int r = threadIdx.x;
+  double a = 0.0, b = 0.0, c = 0.0;
+  bool ok = true;
+  if (r < world) {
+    // push this rank's three sums and the flag into rank r's header, then wait for rank r's in ours
+    PeerHeader *dst = reinterpret_cast<PeerHeader *>(P.peer[r]);
+    for (int i = 0; i < 3; ++i) st_f64_sys(&dst->scal_from[rank][par][i], P.scal[i]);
+    st_release_sys(&dst->flag_scal_from[rank], seq);
+    const PeerHeader *mine = reinterpret_cast<const PeerHeader *>(P.peer[rank]);
+    ok = wait_peer_flag(&mine->flag_scal_from[r], seq);
+    a = __ldcg(&mine->scal_from[r][par][0]); b = __ldcg(&mine->scal_from[r][par][1]); c = __ldcg(&mine->scal_from[r][par][2]);
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  double sa = 0.0, sb = 0.0, sc = 0.0;
+  for (int k = 0; k < world; ++k) {  // rank order
+    sa += __shfl_sync(0xffffffffu, a, k); sb += __shfl_sync(0xffffffffu, b, k); sc += __shfl_sync(0xffffffffu, c, k);
+  }
+  if (threadIdx.x != 0) return;
+  ctl->dbg[5] = gtime();
+  if (!ok) ctl->comm_timeout = 1;
+  P.scal[0] = sa; P.scal[1] = sb; P.scal[2] = sc;
+  control_step(P);
+  ctl->dbg[6] = gtime();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1483,6 +1601,13 @@ void launch_reduce_partials(const DeviceProblem &P, cudaStream_t st) {
 }
 
 void launch_control(const DeviceProblem &P, cudaStream_t st) { k_control<<<1, 1, 0, st>>>(P); }
+
+void launch_exchange_sys(const DeviceProblem &P, cudaStream_t st) {
+  const int n = (int)std::min<size_t>(64, (P.sys_doubles / 2 + kXchgThreads - 1) / kXchgThreads);
+  k_exchange_sys<<<n > 0 ? n : 1, kXchgThreads, 0, st>>>(P);
+}
+
+void launch_control_p2p(const DeviceProblem &P, cudaStream_t st) { k_control_p2p<<<1, 256, 0, st>>>(P); }
 
 void launch_final_chi2(const DeviceProblem &P, double threshold, cudaStream_t st) {
   k_final_chi2<<<P.n_fin_blocks, kLinThreads, 0, st>>>(P, threshold, 0);
