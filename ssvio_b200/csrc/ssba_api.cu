@@ -17,6 +17,7 @@
 
 #include "ssba.h"
 #include "ssba_device.hpp"
+#include "ssba_solver_layout.hpp"
 #include "ssba_structure.hpp"
 
 using namespace ssba;
@@ -393,6 +394,11 @@ ssba_status ssba_create(const ssba_options *opt, ssba_handle **out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) return fail(nullptr, SSBA_ERR_CUDA, "cudaGetDeviceProperties failed");
   if (prop.major < 10) return fail(nullptr, SSBA_ERR_NO_DEVICE, "libssba is built for sm_100a (Blackwell) only");
+  {
+    static int cluster_cap = 0;  // per process: the B200s of a node are alike
+    if (cluster_cap == 0) cluster_cap = max_solver_cluster();
+    set_solver_cluster_cap(cluster_cap);
+  }
   if (o.stream) { h->stream = (cudaStream_t)o.stream; }
   else {
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(nullptr, SSBA_ERR_CUDA, "cudaStreamCreate failed");

@@ -129,6 +129,7 @@ void launch_final_chi2(const DeviceProblem &P, double threshold, cudaStream_t st
 void launch_edge_errors(const DeviceProblem &P, cudaStream_t st);      // -> err_out
 void launch_gather_points(const DeviceProblem &P, cudaStream_t st);    // -> gather
 int kernels_per_linearize();
+int max_solver_cluster();  // largest k_reduced_solve cluster the current device can co-schedule
 
 // batched pose-only LM (ssba_pose_only.cu): one warp per frame, everything in one launch
 void launch_pose_only(const double K[9], int n_frames, int rounds, int iters, int max_trials, double chi2_threshold,

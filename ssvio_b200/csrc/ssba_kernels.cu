@@ -1567,6 +1567,29 @@ void launch_schur(const DeviceProblem &P, bool prefolded, cudaStream_t st) {
   if (n_pose + n_unit > 0) k_schur<<<n_pose + n_unit, 32 * kSchurWarps, kDyn, st>>>(P, n_pose, prefolded ? 1 : 0);
 }
 
+// The largest cluster (8, 4, 2 or 1 CTAs of kSolveThreads threads with the full dynamic shared memory)
+// this device can co-schedule for k_reduced_solve; the host program builder is capped by it.
+int max_solver_cluster() {
+  cudaFuncSetAttribute(k_reduced_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveMaxDynSmem);
+  cudaFuncSetAttribute(k_reduced_solve<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveMaxDynSmem);
+  cudaFuncSetAttribute(k_reduced_solve<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveMaxDynSmem);
+  for (int c = 8; c >= 2; c /= 2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(c); cfg.blockDim = dim3(kSolveThreads); cfg.dynamicSmemBytes = kSolveMaxDynSmem;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = c; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    int n = 0;
+    cudaError_t e = c == 8 ? cudaOccupancyMaxActiveClusters(&n, k_reduced_solve<8>, &cfg)
+                  : c == 4 ? cudaOccupancyMaxActiveClusters(&n, k_reduced_solve<4>, &cfg)
+                           : cudaOccupancyMaxActiveClusters(&n, k_reduced_solve<2>, &cfg);
+    if (e == cudaSuccess && n >= 1) return c;
+    cudaGetLastError();
+  }
+  return 1;
+}
+
 void launch_reduced_solve(const DeviceProblem &P, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {

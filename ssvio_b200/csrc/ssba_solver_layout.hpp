@@ -16,6 +16,8 @@ constexpr int kSolveMaxCluster = 8;           // CTAs of the thread-block cluste
 // above; SSBA_SOLVE_CLUSTER overrides (1, 2, 4 or 8).  Used by the host program builder (which deals the
 // columns of every level over the CTAs) and recorded in the structure for the launch.
 int solver_cluster_size(int n_fp);
+// Upper bound from the device (ssba_create asks it once: cudaOccupancyMaxActiveClusters).
+void set_solver_cluster_cap(int cap);
 
 struct SolverSmemLayout {
   int x_in_smem;    // y / x vector in shared memory

@@ -3,6 +3,7 @@
 #include "ssba_solver_layout.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <climits>
 #include <cmath>
@@ -17,6 +18,9 @@
 
 namespace ssba {
 
+static std::atomic<int> g_cluster_cap{8};
+void set_solver_cluster_cap(int cap) { g_cluster_cap.store(cap >= 8 ? 8 : cap >= 4 ? 4 : cap >= 2 ? 2 : 1); }
+
 int solver_cluster_size(int n_fp) {
   static const int configured = [] {
     const char *e = std::getenv("SSBA_SOLVE_CLUSTER");
@@ -24,8 +28,8 @@ int solver_cluster_size(int n_fp) {
     return (c == 1 || c == 2 || c == 4 || c == 8) ? c : 0;
   }();
   if (n_fp < 32) return 1;
-  if (configured) return configured;
-  return n_fp < 64 ? 4 : 8;  // measured on B200: cfg3 (100 poses) 4 -> 8 CTAs: -2 %, cfg5 (500 poses): -13 %
+  const int want = configured ? configured : (n_fp < 64 ? 4 : 8);
+  return std::min(want, g_cluster_cap.load());  // measured on B200: cfg3 (100 poses) 4 -> 8 CTAs: -2 %, cfg5 (500 poses): -13 %
 }
 
 namespace {
