@@ -48,6 +48,118 @@ static HostGraph make_graph(int nk, int np, int w, unsigned seed, bool fix0, int
   return h;
 }
 
+// ---- CPU interpreter of the PACKED device program (Structure::prog), i.e. of what k_reduced_solve
+// really walks: per level the rounds of every CTA of the cluster (DIAG / SUB / VEC / look-ahead ACC,
+// split REDUCE rounds), block references that are shared-memory slots of the executing CTA or global
+// blocks, the reader masks of the DSMEM broadcast, the slot plan (a slot read before it was written, or
+// after it was handed to another block, gives a wrong or NaN result), and the backward lists.
+// Mirrors LevelSeg in ssba_kernels.cu.  A0 = initial block values (Schur complement), b = right-hand side.
+#include "ssba_solver_layout.hpp"
+#include <limits>
+static std::vector<double> interpret_program(const Structure &s, std::vector<double> L, const std::vector<double> &b) {
+  const int n = s.n_fp, C = s.solve_cluster, NSEG = s.n_segments;
+  const SolverSmemLayout lay = solver_smem_layout(n, s.prog_max_seg);
+  const double nan = std::numeric_limits<double>::quiet_NaN();
+  std::vector<std::vector<double>> slots(C, std::vector<double>(36 * (size_t)std::max(lay.n_slots, 1), nan));
+  std::vector<double> y(6 * (size_t)n, nan);
+  struct Seg { int n_cols, n_rounds, n_pairs, n_brows, n_pf, n_bpf; const int *cta_rptr, *col_j, *col_b0, *col_bptr, *brow, *round_type, *gt_dst, *gt_slot, *gt_pos, *gt_p0, *gt_p1, *gt_mask, *pa, *pb; };
+  auto parse = [&](int sg) {
+    const int *seg = s.prog.data() + s.prog_ptr[sg];
+    Seg S; S.n_cols = seg[0]; S.n_rounds = seg[1]; S.n_pairs = seg[2]; S.n_brows = seg[3]; S.n_pf = seg[4]; S.n_bpf = seg[5];
+    const int *p = seg + 8;
+    S.cta_rptr = p; p += kSolveMaxCluster + 1;
+    S.col_j = p; p += S.n_cols; S.col_b0 = p; p += S.n_cols; S.col_bptr = p; p += S.n_cols + 1; S.brow = p; p += S.n_brows;
+    S.round_type = p; p += S.n_rounds;
+    S.gt_dst = p; p += 5 * S.n_rounds; S.gt_slot = p; p += 5 * S.n_rounds; S.gt_pos = p; p += 5 * S.n_rounds;
+    S.gt_p0 = p; p += 5 * S.n_rounds; S.gt_p1 = p; p += 5 * S.n_rounds; S.gt_mask = p; p += 5 * S.n_rounds;
+    S.pa = p; p += S.n_pairs; S.pb = p; p += S.n_pairs;
+    CHECK(p + 2 * S.n_pf + S.n_bpf <= s.prog.data() + s.prog_ptr[sg + 1], "segment %d overruns", sg);
+    return S;
+  };
+  for (int sg = 1; sg < NSEG; ++sg) {
+    const Seg S = parse(sg);
+    CHECK(S.cta_rptr[0] == 0 && S.cta_rptr[C] == S.n_rounds, "round ranges of level %d", sg - 1);
+    std::vector<std::vector<double>> linv(C, std::vector<double>(36 * (size_t)std::max(S.n_cols, 1), nan));
+    auto blk = [&](int cta, int ref) -> const double * { return ref >= 0 ? &slots[cta][36 * (size_t)ref] : &L[36 * (size_t)(-1 - ref)]; };
+    auto products = [&](int cta, int p0, int p1, double *acc) {  // acc += sum of A B^T
+      for (int p = p0; p < p1; ++p) {
+        const double *A = blk(cta, S.pa[p]), *B = blk(cta, S.pb[p]);
+        for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) { double t = 0; for (int k = 0; k < 6; ++k) t += A[6 * r + k] * B[6 * c + k]; acc[6 * r + c] += t; }
+      }
+    };
+    // the device runs the DIAG rounds of a CTA before its other rounds; the host order has them first
+    for (int pass = 0; pass < 2; ++pass)
+      for (int cta = 0; cta < C; ++cta)
+        for (int rd = S.cta_rptr[cta]; rd < S.cta_rptr[cta + 1]; ++rd) {
+          const int kind = S.round_type[rd] & 3;
+          const bool reduce = (S.round_type[rd] & 4) != 0;
+          if ((kind == 0) != (pass == 0)) continue;
+          for (int g = 0; g < (reduce ? 1 : 5); ++g) {
+            const int gt = 5 * rd + g, dst = S.gt_dst[gt], pos = S.gt_pos[gt];
+            if (dst < 0) continue;
+            if (kind == 2) {  // VEC: y_j = Linv (b_j - sum L(j,k) y_k)
+              const int j = S.col_j[pos];
+              double sv[6];
+              for (int r = 0; r < 6; ++r) sv[r] = b[6 * j + r];
+              for (int gg = 0; gg < (reduce ? 5 : 1); ++gg)
+                for (int p = S.gt_p0[5 * rd + (reduce ? gg : g)]; p < S.gt_p1[5 * rd + (reduce ? gg : g)]; ++p) {
+                  const double *B = blk(cta, S.pa[p]); const double *yk = &y[6 * (size_t)S.pb[p]];
+                  for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) sv[r] -= B[6 * r + c] * yk[c];
+                }
+              const double *Li = &linv[cta][36 * (size_t)pos];
+              for (int r = 0; r < 6; ++r) { double t = 0; for (int c = 0; c <= r; ++c) t += Li[6 * r + c] * sv[c]; y[6 * j + r] = t; }
+              continue;
+            }
+            double acc[36] = {0};
+            for (int gg = 0; gg < (reduce ? 5 : 1); ++gg) products(cta, S.gt_p0[5 * rd + (reduce ? gg : g)], S.gt_p1[5 * rd + (reduce ? gg : g)], acc);
+            double v[36];
+            for (int i = 0; i < 36; ++i) v[i] = L[36 * (size_t)dst + i] - acc[i];
+            if (kind == 3) { for (int i = 0; i < 36; ++i) L[36 * (size_t)dst + i] = v[i]; continue; }  // ACC
+            if (kind == 0) {  // DIAG: Cholesky of the lower triangle, explicit inverse
+              double a[36] = {0}, X[36] = {0};
+              for (int i = 0; i < 6; ++i) for (int k = 0; k <= i; ++k) a[6 * i + k] = v[6 * i + k];
+              for (int j = 0; j < 6; ++j) {
+                CHECK(a[7 * j] > 0, "pivot of block %d", dst);
+                const double d = std::sqrt(a[7 * j]); a[7 * j] = d;
+                for (int i = j + 1; i < 6; ++i) a[6 * i + j] /= d;
+                for (int i = j + 1; i < 6; ++i) for (int k = j + 1; k <= i; ++k) a[6 * i + k] -= a[6 * i + j] * a[6 * k + j];
+              }
+              for (int c = 0; c < 6; ++c) {
+                X[7 * c] = 1.0 / a[7 * c];
+                for (int i = c + 1; i < 6; ++i) { double t = 0; for (int k = c; k < i; ++k) t += a[6 * i + k] * X[6 * k + c]; X[6 * i + c] = -t / a[7 * i]; }
+              }
+              for (int i = 0; i < 36; ++i) { L[36 * (size_t)dst + i] = X[i]; linv[cta][36 * (size_t)pos + i] = X[i]; }
+            } else {  // SUB: X = v Linv^T, stored in global memory and in the caches of the reader CTAs
+              const double *Li = &linv[cta][36 * (size_t)pos];
+              double X[36];
+              for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) { double t = 0; for (int k = 0; k <= c; ++k) t += v[6 * r + k] * Li[6 * c + k]; X[6 * r + c] = t; }
+              for (int i = 0; i < 36; ++i) L[36 * (size_t)dst + i] = X[i];
+              const int slot = S.gt_slot[gt];
+              if (slot >= 0) {
+                CHECK(slot < lay.n_slots, "slot out of range");
+                for (int cc = 0; cc < C; ++cc) if (C == 1 || ((S.gt_mask[gt] >> cc) & 1)) for (int i = 0; i < 36; ++i) slots[cc][36 * (size_t)slot + i] = X[i];
+              }
+            }
+          }
+        }
+  }
+  // backward: x_j = Linv_jj^T (y_j - sum_i L(i,j)^T x_i)
+  std::vector<double> x = y;
+  for (int sg = NSEG - 1; sg >= 1; --sg) {
+    const Seg S = parse(sg);
+    for (int t = 0; t < S.n_cols; ++t) {
+      const int j = S.col_j[t], b0 = S.col_b0[t], nb = S.col_bptr[t + 1] - S.col_bptr[t];
+      const int *rows = S.brow + S.col_bptr[t];
+      double sv[6];
+      for (int r = 0; r < 6; ++r) sv[r] = x[6 * j + r];
+      for (int k = 0; k < nb; ++k) { const double *B = &L[36 * (size_t)(b0 + 1 + k)]; for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) sv[r] -= B[6 * c + r] * x[6 * rows[k] + c]; }
+      const double *Li = &L[36 * (size_t)b0];
+      for (int r = 0; r < 6; ++r) { double t2 = 0; for (int c = r; c < 6; ++c) t2 += Li[6 * c + r] * sv[c]; x[6 * j + r] = t2; }
+    }
+  }
+  return x;
+}
+
 static void check_case(int nk, int np, int w, unsigned seed, bool fix0, int nfix, bool loop, int world) {
   HostGraph g = make_graph(nk, np, w, seed, fix0, nfix, loop);
   std::vector<Structure> S(world);
@@ -150,6 +262,7 @@ static void check_case(int nk, int np, int w, unsigned seed, bool fix0, int nfix
         }
     }
   for (int i = 0; i < N; ++i) b[i] = U(rng);
+  const std::vector<double> L0 = L;
   // left-looking by levels: first every update task of the level, then factor its columns
   for (int lv = 0; lv < s.n_levels; ++lv) {
     CHECK(s.level_ptr[lv + 1] - s.level_ptr[lv] <= 64, "level too wide");
@@ -217,6 +330,15 @@ static void check_case(int nk, int np, int w, unsigned seed, bool fix0, int nfix
     rmax = std::fmax(rmax, std::fabs(r)); bmax = std::fmax(bmax, std::fabs(b[i]));
   }
   CHECK(rmax < 1e-10 * (1 + bmax), "residual %.3e (n=%d blocks=%d levels=%d)", rmax, n, s.n_blocks, s.n_levels);
+  {
+    // the same system through the packed device program
+    const std::vector<double> xp = interpret_program(s, L0, b);
+    double dmax = 0;
+    bool finite = true;
+    for (int i = 0; i < N; ++i) { finite = finite && std::isfinite(xp[i]); dmax = std::fmax(dmax, std::fabs(xp[i] - x[i])); }
+    CHECK(finite, "device program: non-finite solution (a block cache slot was read before it was written?)");
+    CHECK(dmax < 1e-10, "device program: solution differs by %.3e (n=%d, cluster %d)", dmax, n, s.solve_cluster);
+  }
   std::printf("case nk=%d np=%d w=%d fix0=%d nfix=%d loop=%d world=%d: n_fp=%d blocks=%d schur=%d levels=%d tasks=%d pairs=%d est=%.0f slots=%d cached=%d resid=%.2e\n",
               nk, np, w, (int)fix0, nfix, (int)loop, world, n, s.n_blocks, s.n_schur_blocks, s.n_levels, s.n_tasks, (int)s.pair_a.size(), s.est_solver_cycles, s.solver_slots, s.solver_cached_blocks, rmax);
 }

@@ -1,5 +1,6 @@
 """Host logic of the product: structure build, landmark sharding, symbolic factorisation and the
-level schedule the CUDA solver walks — exercised on the CPU by tests/cpp/test_structure.cpp."""
+level schedule the CUDA solver walks — exercised on the CPU by tests/cpp/test_structure.cpp, which also
+interprets the PACKED device program (rounds per CTA, slots, reader masks, look-ahead) against a dense solve."""
 import os
 import subprocess
 
@@ -13,6 +14,12 @@ def test_structure_builder_cpp():
                     "-I" + os.path.join(ROOT, "ssvio_b200", "csrc"),
                     os.path.join(ROOT, "tests", "cpp", "test_structure.cpp"),
                     os.path.join(ROOT, "ssvio_b200", "csrc", "ssba_structure.cpp"), "-o", exe], check=True)
-    r = subprocess.run([exe], capture_output=True, text=True)
-    assert r.returncode == 0, r.stdout + r.stderr
-    assert r.stdout.strip().endswith("OK")
+    # every cluster size the device solver can be built for (the packed program differs: rounds per CTA,
+    # reader masks, look-ahead placement)
+    for cluster in ("", "1", "2", "4", "8"):
+        env = dict(os.environ)
+        if cluster:
+            env["SSBA_SOLVE_CLUSTER"] = cluster
+        r = subprocess.run([exe], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, f"cluster={cluster or 'default'}\n" + r.stdout + r.stderr
+        assert r.stdout.strip().endswith("OK")
