@@ -141,6 +141,19 @@ def ref_pose_only(lib, batch, rounds=4, iters=10, chi2_threshold=5.991):
     return poses, flags, n_in, chi
 
 
+def ref_pose_graph(lib, pg, iters=20):
+    """LoopClosing::PoseGraphOptimization through the compiled reference (ssba_ref_pose_graph)."""
+    rep = Report()
+    out = np.empty_like(pg.poses)
+    rc = lib.ssba_ref_pose_graph(
+        pg.poses.shape[0], _p(np.ascontiguousarray(pg.poses), C.c_double), _p(np.ascontiguousarray(pg.fixed, np.uint8), C.c_uint8),
+        len(pg.v0), _p(np.ascontiguousarray(pg.v0, np.int32), C.c_int32), _p(np.ascontiguousarray(pg.v1, np.int32), C.c_int32),
+        _p(np.ascontiguousarray(pg.meas), C.c_double), int(iters), _p(out, C.c_double), C.byref(rep))
+    if rc != 0:
+        raise RuntimeError(f"ssba_ref_pose_graph failed rc={rc}")
+    return out, rep
+
+
 class PortOracle(_OracleBase):
     """The plain-C restatement (kind = "port")."""
     so_path = PORT_SO

@@ -16,6 +16,7 @@
 
 #include "ssvio/g2otypes.hpp"
 #include "g2o/solvers/dense/linear_solver_dense.h"
+#include "g2o/solvers/eigen/linear_solver_eigen.h"
 
 #include "ref_harness.h"
 
@@ -320,5 +321,58 @@ extern "C" int ssba_ref_pose_only(const double K9[9], int32_t n_frames, const in
     if (n_inliers_out) n_inliers_out[f] = n - cnt_outliers;
     if (chi2_out) chi2_out[f] = chi_last;
   }
+  return 0;
+}
+
+
+// ---- LoopClosing::PoseGraphOptimization (src/ssvio/loopclosing.cpp:458-532) over flat arrays: the solver
+// stack of :460-465, one vertex per key-frame (:471-489), one EdgePoseGraph per relative-pose constraint
+// with identity information (:497-527), initializeOptimization(); optimize(iters) (:531-532).
+extern "C" int ssba_ref_pose_graph(int32_t n_poses, const double *poses_qt, const uint8_t *fixed, int32_t n_edges,
+                                   const int32_t *v0, const int32_t *v1, const double *meas_qt, int32_t iters,
+                                   double *poses_out, ssba_report *report) {
+  typedef g2o::BlockSolver<g2o::BlockSolverTraits<6, 6>> BlockSolverType;
+  typedef g2o::LinearSolverEigen<BlockSolverType::PoseMatrixType> LinearSolverType;
+  auto solver = new g2o::OptimizationAlgorithmLevenberg(
+      g2o::make_unique<BlockSolverType>(g2o::make_unique<LinearSolverType>()));
+  g2o::SparseOptimizer optimizer;
+  optimizer.setAlgorithm(solver);
+  std::vector<ssvio::VertexPose *> vertices(n_poses);
+  for (int i = 0; i < n_poses; ++i) {
+    auto *vertex_pose = new ssvio::VertexPose();
+    vertex_pose->setId(i);
+    vertex_pose->setEstimate(se3_from_qt(poses_qt + 7 * i));
+    vertex_pose->setMarginalized(false);
+    if (fixed && fixed[i]) vertex_pose->setFixed(true);
+    optimizer.addVertex(vertex_pose);
+    vertices[i] = vertex_pose;
+  }
+  for (int e = 0; e < n_edges; ++e) {
+    auto *edge = new ssvio::EdgePoseGraph();
+    edge->setId(e);
+    edge->setVertex(0, vertices[v0[e]]);
+    edge->setVertex(1, vertices[v1[e]]);
+    edge->setMeasurement(se3_from_qt(meas_qt + 7 * e));
+    edge->setInformation(Eigen::Matrix<double, 6, 6>::Identity());
+    optimizer.addEdge(edge);
+  }
+  if (report) std::memset(report, 0, sizeof(*report));
+  TraceAction trace;
+  trace.opt = &optimizer; trace.lm = solver; trace.report = report;
+  if (report) optimizer.addPostIterationAction(&trace);
+  optimizer.initializeOptimization();
+  if (report) { optimizer.computeActiveErrors(); report->chi2_initial = optimizer.activeRobustChi2(); }
+  const auto t0 = Clock::now();
+  const int its = optimizer.optimize(iters);
+  if (report) {
+    report->seconds_total = seconds_since(t0);
+    report->iterations = its;
+    optimizer.computeActiveErrors();
+    report->chi2_robust = optimizer.activeRobustChi2();
+    report->chi2_plain = optimizer.activeChi2();
+    report->lambda = solver->currentLambda();
+  }
+  if (poses_out)
+    for (int i = 0; i < n_poses; ++i) qt_from_se3(vertices[i]->estimate(), poses_out + 7 * i);
   return 0;
 }

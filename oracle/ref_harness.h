@@ -78,6 +78,19 @@ int ssba_ref_pose_only(const double K[9], int32_t n_frames, const int32_t *feat_
                        double *poses_out, uint8_t *outlier_out, int32_t *n_inliers_out,
                        double *chi2_out);
 
+/*
+ * Pose-graph optimisation of LoopClosing::PoseGraphOptimization() (src/ssvio/loopclosing.cpp:458-594):
+ * one VertexPose per key-frame (setMarginalized(false), some fixed), one EdgePoseGraph
+ * (include/ssvio/g2otypes.hpp:164-199: error = log(measurement^-1 * v0 * v1^-1), numeric Jacobians as
+ * shipped) with identity 6x6 information and no robust kernel per (vertex 0, vertex 1, measurement),
+ * BlockSolver<6,6> + LinearSolverEigen + Levenberg, initializeOptimization(); optimize(iters) (20).
+ *   poses_qt n_poses x 7 (T_cw), fixed n_poses, edges: v0[e], v1[e], meas_qt n_edges x 7
+ * Outputs may be NULL.  report as for ssba_ref_optimize (chi2 = activeRobustChi2 = plain chi2 here).
+ */
+int ssba_ref_pose_graph(int32_t n_poses, const double *poses_qt, const uint8_t *fixed, int32_t n_edges,
+                        const int32_t *v0, const int32_t *v1, const double *meas_qt, int32_t iters,
+                        double *poses_out, ssba_report *report);
+
 #ifdef __cplusplus
 }
 #endif

@@ -262,3 +262,43 @@ def make_pose_only(n_frames: int, n_features: int, *, seed: int = 42, pixel_sigm
     d = np.concatenate([pose_sigma_t * rng.normal((n_frames, 3)), pose_sigma_r * rng.normal((n_frames, 3))], axis=1)
     poses = se3_mul(se3_exp(d), gt)
     return PoseOnlyBatch(K=K, feat_ptr=feat_ptr, poses=poses, xyz=xyz, uv=uv)
+
+
+# --------------------------------------------------------------------------- pose graphs
+
+@dataclasses.dataclass
+class PoseGraph:
+    """A loop-closure pose graph (src/ssvio/loopclosing.cpp:458-532): key-frame poses T_cw, fixed flags, and
+    relative-pose edges (v0, v1, measurement) with error log(M^-1 * T_v0 * T_v1^-1)."""
+
+    poses: np.ndarray   # (N, 7) initial T_cw
+    fixed: np.ndarray   # (N,) uint8
+    v0: np.ndarray      # (E,) int32
+    v1: np.ndarray      # (E,) int32
+    meas: np.ndarray    # (E, 7)
+
+
+def make_pose_graph(n_kf: int, *, seed: int = 42, n_loops: int = 3, drift_t: float = 0.03, drift_r: float = 0.004,
+                    meas_sigma_t: float = 0.01, meas_sigma_r: float = 0.001, n_fixed_tail: int = 4) -> PoseGraph:
+    """A trajectory of `n_kf` key-frames whose initial poses have accumulated odometry drift; edges between
+    consecutive key-frames (kf -> last kf) plus `n_loops` loop edges from late to early key-frames, measured
+    from the drift-free truth with small noise.  Key-frame 0, the loop key-frames' targets and the last
+    `n_fixed_tail` (the "active" ones) are fixed, like loopclosing.cpp:480-486."""
+    rng = _Rng(seed)
+    idx = np.arange(n_kf, dtype=np.float64)
+    gt = se3_exp(np.stack([0.4 * np.sin(0.05 * idx), 0.01 * idx, -1.0 * idx, 0.002 * idx, 0.01 * np.sin(0.1 * idx), 0.002 * idx], axis=1))
+    poses = gt.copy()
+    acc = np.zeros(6)
+    for i in range(1, n_kf):   # random-walk drift
+        acc = acc + np.concatenate([drift_t * rng.normal(3), drift_r * rng.normal(3)])
+        poses[i] = se3_mul(se3_exp(acc[None, :]), gt[i:i + 1])[0]
+    noise = lambda m: se3_exp(np.concatenate([meas_sigma_t * rng.normal((m, 3)), meas_sigma_r * rng.normal((m, 3))], axis=1))
+    v0 = np.arange(1, n_kf, dtype=np.int32); v1 = v0 - 1
+    lo = rng.integers(0, max(0, n_kf // 4), n_loops).astype(np.int32)
+    hi = (n_kf - 1 - rng.integers(0, max(0, n_kf // 4), n_loops)).astype(np.int32)
+    v0 = np.concatenate([v0, hi]); v1 = np.concatenate([v1, lo])
+    rel = se3_mul(gt[v0], se3_inv(gt[v1]))        # T_v0 * T_v1^-1
+    meas = se3_mul(noise(len(v0)), rel)
+    fixed = np.zeros(n_kf, np.uint8)
+    fixed[0] = 1; fixed[lo] = 1; fixed[n_kf - n_fixed_tail:] = 1
+    return PoseGraph(poses=poses, fixed=fixed, v0=v0.astype(np.int32), v1=v1.astype(np.int32), meas=meas)
