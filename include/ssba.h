@@ -267,6 +267,21 @@ ssba_status ssba_pose_only_optimize(ssba_handle *h, const double K[9], int32_t n
                                     double *poses_out, uint8_t *outlier_out, int32_t *n_inliers_out,
                                     double *chi2_out);
 
+/* ---- pose-graph optimisation: LoopClosing::PoseGraphOptimization()
+ * (src/ssvio/loopclosing.cpp:458-532).  One VertexPose per key-frame (setMarginalized(false); `fixed`
+ * marks the ones :480-486 fixes), one EdgePoseGraph (include/ssvio/g2otypes.hpp:164-199) per relative-pose
+ * constraint: error = log(measurement^-1 * T_v0 * T_v1^-1), identity 6x6 information, no robust kernel,
+ * Jacobians numeric as the reference ships them; Levenberg over the block-sparse H (BlockSolver<6,6> +
+ * LinearSolverEigen in the reference, here the level-scheduled block solver of the bundle adjustment);
+ * initializeOptimization(); optimize(iters) (the reference: 20).
+ *   poses_in / poses_out   n_poses x 7 T_cw (qx qy qz qw tx ty tz)
+ *   v0, v1, meas           per edge: vertex 0, vertex 1 (pose rows), measurement (7 doubles)
+ * report (may be NULL) as for ssba_optimize; chi2_robust = chi2_plain (no kernel).  Host arrays, synchronous;
+ * the handle's bundle-adjustment problem, if any, is untouched.  SSBA_ERR_EMPTY when nothing is free. */
+ssba_status ssba_pose_graph_optimize(ssba_handle *h, int32_t n_poses, const double *poses_in, const uint8_t *fixed,
+                                     int32_t n_edges, const int32_t *v0, const int32_t *v1, const double *meas,
+                                     int32_t iters, double *poses_out, ssba_report *report);
+
 /* Turn the per-phase CUDA-event timers on or off after creation (ssba_options::profile sets
  * the initial state).  The timers add event records to the stream, so benchmarks time with
  * them off and profile in a separate pass. */

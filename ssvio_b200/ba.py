@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "ssba_set_edges", "ssba_initialize", "ssba_optimize", "ssba_step", "ssba_reset_state",
     "ssba_get_poses", "ssba_get_points", "ssba_get_edge_errors", "ssba_chi2",
     "ssba_count_outliers", "ssba_optimize_rounds", "ssba_plan_shards", "ssba_set_profiling", "ssba_profile_get",
-    "ssba_profile_reset", "ssba_get_problem_info", "ssba_pose_only_optimize",
+    "ssba_profile_reset", "ssba_get_problem_info", "ssba_pose_only_optimize", "ssba_pose_graph_optimize",
     "ssba_version",
 ]
 
@@ -127,6 +127,7 @@ def load_library():
     lib.ssba_plan_shards.argtypes = [C.c_int32, bp, C.c_int32, bp, C.c_int32, ip, ip, C.c_int32, ip]
     lib.ssba_pose_only_optimize.argtypes = [H, dp, C.c_int32, ip, dp, dp, dp, C.c_int32, C.c_int32, C.c_double,
                                             dp, bp, ip, dp]
+    lib.ssba_pose_graph_optimize.argtypes = [H, C.c_int32, dp, bp, C.c_int32, ip, ip, dp, C.c_int32, dp, C.POINTER(Report)]
     lib.ssba_set_profiling.argtypes = [H, C.c_int32]
     lib.ssba_profile_get.argtypes = [H, C.POINTER(Profile)]
     lib.ssba_profile_reset.argtypes = [H]
@@ -341,6 +342,20 @@ class BundleAdjuster:
             _p(uv, C.c_double), int(rounds), int(iters), float(chi2_threshold), _p(poses, C.c_double),
             _p(flags, C.c_uint8), _p(n_in, C.c_int32), _p(chi, C.c_double)))
         return poses, flags, n_in, chi
+
+    # -- pose-graph optimisation of the loop closer (loopclosing.cpp:458-532)
+    def pose_graph_optimize(self, pg, iters=20):
+        """pg: ssvio_b200.synth.PoseGraph.  Returns (poses, Report)."""
+        poses_in, fixed = _c(pg.poses, np.float64), _c(pg.fixed, np.uint8)
+        v0, v1, meas = _c(pg.v0, np.int32), _c(pg.v1, np.int32), _c(pg.meas, np.float64)
+        out, rep = np.empty_like(poses_in), Report()
+        st = self.lib.ssba_pose_graph_optimize(self._h, poses_in.shape[0], _p(poses_in, C.c_double), _p(fixed, C.c_uint8),
+                                               len(v0), _p(v0, C.c_int32), _p(v1, C.c_int32), _p(meas, C.c_double), int(iters),
+                                               _p(out, C.c_double), C.byref(rep))
+        if st == SSBA_ERR_EMPTY:
+            return out, rep
+        self._check(st)
+        return out, rep
 
     def set_profiling(self, on: bool):
         self._check(self.lib.ssba_set_profiling(self._h, 1 if on else 0))

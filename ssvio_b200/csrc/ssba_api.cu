@@ -101,6 +101,9 @@ struct ssba_handle {
   char *peer[SSBA_MAX_PEERS] = {nullptr};
   bool use_p2p = false;
   long long trial_seq = 0;
+  // pose-graph optimisation: its own solver structure and grow-only device buffer
+  Structure pg_s;
+  char *d_pg = nullptr; size_t d_pg_bytes = 0;
   // pose-only LM: its own grow-only device buffer and pinned staging
   char *d_po = nullptr; size_t d_po_bytes = 0;
   char *h_po = nullptr; size_t h_po_bytes = 0;
@@ -430,6 +433,7 @@ void ssba_destroy(ssba_handle *h) {
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->h_stage_b) cudaFreeHost(h->h_stage_b);
   if (h->d_po) cudaFree(h->d_po);
+  if (h->d_pg) cudaFree(h->d_pg);
   if (h->h_po) cudaFreeHost(h->h_po);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->h_small) cudaFreeHost(h->h_small);
@@ -891,6 +895,7 @@ ssba_status ssba_pose_only_optimize(ssba_handle *h, const double K[9], int32_t n
   const size_t total = align_up(top);
   if (total > h->d_po_bytes) {
     if (h->d_po) cudaFree(h->d_po);
+  if (h->d_pg) cudaFree(h->d_pg);
     h->d_po = nullptr; h->d_po_bytes = 0;
     if (cudaMalloc((void **)&h->d_po, total + total / 4) != cudaSuccess) { cudaGetLastError(); return fail(h, SSBA_ERR_ALLOC, "cudaMalloc failed"); }
     h->d_po_bytes = total + total / 4;
@@ -918,6 +923,143 @@ ssba_status ssba_pose_only_optimize(ssba_handle *h, const double K[9], int32_t n
   if (chi2_out) std::memcpy(chi2_out, h->h_po + o_chi, 8 * (size_t)n_frames);
   if (n_inliers_out) std::memcpy(n_inliers_out, h->h_po + o_nin, 4 * (size_t)n_frames);
   if (outlier_out && n) std::memcpy(outlier_out, h->h_po + o_flag, (size_t)n);
+  return SSBA_OK;
+}
+
+ssba_status ssba_pose_graph_optimize(ssba_handle *h, int32_t n_poses, const double *poses_in, const uint8_t *fixed,
+                                     int32_t n_edges, const int32_t *v0, const int32_t *v1, const double *meas,
+                                     int32_t iters, double *poses_out, ssba_report *report) {
+  if (!h) return SSBA_ERR_INVALID_ARG;
+  if (report) std::memset(report, 0, sizeof(*report));
+  if (n_poses < 0 || n_edges < 0 || iters < 0 || iters > SSBA_MAX_ITER_RECORDS || (n_poses > 0 && (!poses_in || !poses_out)) ||
+      (n_edges > 0 && (!v0 || !v1 || !meas)))
+    return fail(h, SSBA_ERR_INVALID_ARG, "pose_graph_optimize: bad arguments");
+  auto t0 = Clock::now();
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  // ---- active edges (not both ends fixed, sparse_optimizer.cpp:237), free key-frames, pattern of H
+  std::vector<int32_t> ev0, ev1, fidx(n_poses, -1), free_rows;
+  std::vector<double> minv;
+  for (int e = 0; e < n_edges; ++e) {
+    if ((unsigned)v0[e] >= (unsigned)n_poses || (unsigned)v1[e] >= (unsigned)n_poses || v0[e] == v1[e])
+      return fail(h, SSBA_ERR_INVALID_ARG, "pose_graph_optimize: bad edge");
+    if (fixed && fixed[v0[e]] && fixed[v1[e]]) continue;
+    ev0.push_back(v0[e]); ev1.push_back(v1[e]);
+    double mi[7];
+    se3_inverse(meas + 7 * (size_t)e, mi);
+    minv.insert(minv.end(), mi, mi + 7);
+  }
+  const int ne = (int)ev0.size();
+  {
+    std::vector<uint8_t> touched(n_poses, 0);
+    for (int e = 0; e < ne; ++e) { touched[ev0[e]] = 1; touched[ev1[e]] = 1; }
+    for (int i = 0; i < n_poses; ++i)
+      if (touched[i] && !(fixed && fixed[i])) { fidx[i] = (int)free_rows.size(); free_rows.push_back(i); }
+  }
+  const int nf = (int)free_rows.size();
+  if (nf == 0) {
+    std::memcpy(poses_out, poses_in, 56 * (size_t)n_poses);
+    if (report) { report->iterations = -1; report->last_result = SSBA_SOLVER_FAIL; }
+    return fail(h, SSBA_ERR_EMPTY, "pose_graph_optimize: 0 vertices to optimize");
+  }
+  std::vector<std::vector<int>> adj(nf);
+  for (int e = 0; e < ne; ++e) {
+    const int a = fidx[ev0[e]], b = fidx[ev1[e]];
+    if (a < 0 || b < 0) continue;
+    adj[std::min(a, b)].push_back(std::max(a, b));
+  }
+  for (auto &c : adj) { std::sort(c.begin(), c.end()); c.erase(std::unique(c.begin(), c.end()), c.end()); }
+  Structure &s = h->pg_s;
+  std::vector<int> perm;
+  std::string err;
+  if (!build_solver_structure(nf, adj, s, perm, err)) return fail(h, SSBA_ERR_INVALID_ARG, err);
+  std::vector<int32_t> q_of_free(nf), pose_of_q(nf), eq0(ne), eq1(ne), eblk(ne, -1);
+  for (int q = 0; q < nf; ++q) { q_of_free[perm[q]] = q; pose_of_q[q] = free_rows[perm[q]]; }
+  for (int e = 0; e < ne; ++e) {
+    eq0[e] = fidx[ev0[e]] >= 0 ? q_of_free[fidx[ev0[e]]] : -1;
+    eq1[e] = fidx[ev1[e]] >= 0 ? q_of_free[fidx[ev1[e]]] : -1;
+    if (eq0[e] >= 0 && eq1[e] >= 0) {
+      const int col = std::min(eq0[e], eq1[e]), row = std::max(eq0[e], eq1[e]);
+      const int32_t *b0 = s.blk_row.data() + s.col_ptr[col], *b1 = s.blk_row.data() + s.col_ptr[col + 1];
+      const int32_t *it = std::lower_bound(b0, b1, row);
+      if (it == b1 || *it != row) return fail(h, SSBA_ERR_STATE, "internal: pose-graph block missing from the factor pattern");
+      eblk[e] = (int32_t)(it - s.blk_row.data());
+    }
+  }
+  // ---- device buffer: static part (uploaded), then work buffers
+  DeviceProblem P;
+  std::memset(&P, 0, sizeof(P));
+  P.n_poses = n_poses; P.n_fp = nf; P.n_blocks = s.n_blocks; P.n_levels = s.n_levels;
+  P.prog_max_seg = s.prog_max_seg; P.n_segments = s.n_segments; P.solve_cluster = s.solve_cluster;
+  P.sys_doubles = 36 * (size_t)s.n_blocks + 12 * (size_t)nf;
+  struct Item { const void *src; size_t bytes; size_t off; };
+  std::vector<Item> items;
+  size_t top = 0;
+  auto place = [&](const void *src, size_t bytes) { const size_t o = align_up(top); top = o + (bytes ? bytes : 8); items.push_back({src, bytes, o}); return o; };
+  const size_t o_pose0 = place(poses_in, 56 * (size_t)n_poses), o_ev0 = place(ev0.data(), 4 * (size_t)ne), o_ev1 = place(ev1.data(), 4 * (size_t)ne),
+               o_eq0 = place(eq0.data(), 4 * (size_t)ne), o_eq1 = place(eq1.data(), 4 * (size_t)ne), o_eblk = place(eblk.data(), 4 * (size_t)ne),
+               o_minv = place(minv.data(), 56 * (size_t)ne), o_poq = place(pose_of_q.data(), 4 * (size_t)nf),
+               o_brow = place(s.blk_row.data(), 4 * s.blk_row.size()), o_bcol = place(s.blk_col.data(), 4 * s.blk_col.size()),
+               o_cdiag = place(s.col_ptr.data(), 4 * s.col_ptr.size()), o_prog = place(s.prog.data(), 4 * s.prog.size()),
+               o_pptr = place(s.prog_ptr.data(), 4 * s.prog_ptr.size());
+  const size_t o_pose1 = place(nullptr, 56 * (size_t)n_poses), o_sysH = place(nullptr, 8 * P.sys_doubles), o_sys = place(nullptr, 8 * P.sys_doubles),
+               o_xp = place(nullptr, 48 * (size_t)nf), o_scal = place(nullptr, 64), o_ctl = place(nullptr, sizeof(Control));
+  const size_t total = align_up(top);
+  if (total > h->d_pg_bytes) {
+    if (h->d_pg) cudaFree(h->d_pg);
+    h->d_pg = nullptr; h->d_pg_bytes = 0;
+    if (cudaMalloc((void **)&h->d_pg, total + total / 4) != cudaSuccess) { cudaGetLastError(); return fail(h, SSBA_ERR_ALLOC, "cudaMalloc failed"); }
+    h->d_pg_bytes = total + total / 4;
+  }
+  char *d = h->d_pg;
+  for (auto &it : items)
+    if (it.src && it.bytes) CUDA_TRY(h, cudaMemcpyAsync(d + it.off, it.src, it.bytes, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(d + o_pose1, d + o_pose0, 56 * (size_t)n_poses, cudaMemcpyDeviceToDevice, h->stream));
+  P.pose[0] = (double *)(d + o_pose0); P.pose[1] = (double *)(d + o_pose1);
+  P.pose_of_q = (const int32_t *)(d + o_poq); P.blk_row = (const int32_t *)(d + o_brow); P.blk_col = (const int32_t *)(d + o_bcol);
+  P.col_diag = (const int32_t *)(d + o_cdiag); P.prog = (const int32_t *)(d + o_prog); P.prog_ptr = (const int32_t *)(d + o_pptr);
+  P.sys = (double *)(d + o_sys); P.xp = (double *)(d + o_xp); P.scal = (double *)(d + o_scal); P.ctl = (Control *)(d + o_ctl);
+  const int32_t *d_ev0 = (const int32_t *)(d + o_ev0), *d_ev1 = (const int32_t *)(d + o_ev1), *d_eq0 = (const int32_t *)(d + o_eq0),
+                *d_eq1 = (const int32_t *)(d + o_eq1), *d_eblk = (const int32_t *)(d + o_eblk);
+  const double *d_minv = (const double *)(d + o_minv);
+  double *d_sysH = (double *)(d + o_sysH);
+  // ---- LM: the same device-side control as run_lm
+  Control &c = *h->h_ctl;
+  std::memset(&c, 0, sizeof(c));
+  c.tau = h->opt.tau; c.good_lower = h->opt.good_step_lower_scale; c.good_upper = h->opt.good_step_upper_scale;
+  c.user_lambda = h->opt.user_lambda_init; c.max_trials = h->opt.max_trials_after_failure;
+  c.lambda = -1.0; c.ni = 2.0; c.cur = 0; c.need_linearize = 1; c.first_iteration = 1;
+  c.max_iters = iters; c.last_result = SSBA_SOLVER_OK; c.world = 1; c.rank = 0;
+  if (iters == 0) c.done = 1;
+  CUDA_TRY(h, cudaMemcpyAsync(P.ctl, &c, sizeof(Control), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  bool first = true;
+  int guard = 0;
+  const int max_slots = iters * (c.max_trials > 0 ? c.max_trials : 1) + 1;
+  while (!c.done) {
+    const int batch = std::max(1, iters - c.outer_iter);
+    for (int i = 0; i < batch; ++i) {
+      launch_pose_graph_slot(P, ne, d_ev0, d_ev1, d_eq0, d_eq1, d_eblk, d_minv, d_sysH, first, h->stream);
+      h->prof.kernel_launches += first ? 6 : 5;
+      first = false;
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(&c, P.ctl, sizeof(Control), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaGetLastError());
+    guard += batch;
+    if (guard > max_slots) return fail(h, SSBA_ERR_STATE, "pose_graph_optimize: LM driver did not terminate");
+  }
+  // ---- results
+  launch_pose_graph_chi(P, ne, d_ev0, d_ev1, d_minv, h->stream);
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_small, P.scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(poses_out, P.pose[c.cur], 56 * (size_t)n_poses, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (report) {
+    report->iterations = c.outer_iter; report->last_result = c.last_result; report->n_records = c.n_records;
+    report->cholesky_failures = c.cholesky_failures; report->chi2_initial = c.chi2_initial;
+    report->chi2_robust = report->chi2_plain = h->h_small[0]; report->lambda = c.lambda;
+    std::memcpy(report->iters, c.records, sizeof(ssba_iter_record) * c.n_records);
+    report->seconds_total = secs(t0, Clock::now());
+  }
   return SSBA_OK;
 }
 

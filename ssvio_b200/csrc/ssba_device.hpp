@@ -129,6 +129,14 @@ void launch_final_chi2(const DeviceProblem &P, double threshold, cudaStream_t st
 void launch_edge_errors(const DeviceProblem &P, cudaStream_t st);      // -> err_out
 void launch_gather_points(const DeviceProblem &P, cudaStream_t st);    // -> gather
 int kernels_per_linearize();
+
+// pose-graph optimisation: one LM trial (zero / linearise when needed, lambda_0 in the first slot, H + lambda I,
+// the level-scheduled solver, chi2 of current and trial poses, accept / reject); chi2 of the current poses
+void launch_pose_graph_slot(const DeviceProblem &P, int n_edges, const int32_t *ev0, const int32_t *ev1, const int32_t *eq0,
+                            const int32_t *eq1, const int32_t *eblk, const double *minv, double *sysH, bool first,
+                            cudaStream_t st);
+void launch_pose_graph_chi(const DeviceProblem &P, int n_edges, const int32_t *ev0, const int32_t *ev1, const double *minv,
+                           cudaStream_t st);
 int max_solver_cluster();  // largest k_reduced_solve cluster the current device can co-schedule
 
 // batched pose-only LM (ssba_pose_only.cu): one warp per frame, everything in one launch

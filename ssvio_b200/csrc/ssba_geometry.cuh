@@ -217,4 +217,65 @@ SSBA_HD void sym3_inverse(const double *m, double *o) {
   o[5] = (a * d - b * b) * id;
 }
 
+// ---- SE(3) group operations of the pose-graph edge (EdgePoseGraph, g2otypes.hpp:169-176)
+
+// SE3 product a * b with the quaternion re-normalised like every Sophus SO3 product
+// (sophus/se3.hpp:309-314, so3.hpp:322-334,498-503)
+SSBA_HD void se3_mul(const double *a, const double *b, double *o) {
+  const double ax = a[0], ay = a[1], az = a[2], aw = a[3];
+  const double bx = b[0], by = b[1], bz = b[2], bw = b[3];
+  const double w = aw * bw - ax * bx - ay * by - az * bz;
+  const double x = aw * bx + ax * bw + ay * bz - az * by;
+  const double y = aw * by + ay * bw + az * bx - ax * bz;
+  const double z = aw * bz + az * bw + ax * by - ay * bx;
+  const double len = sqrt(x * x + y * y + z * z + w * w);
+  double rx, ry, rz;
+  quat_rotate(a, b[4], b[5], b[6], rx, ry, rz);
+  o[0] = x / len; o[1] = y / len; o[2] = z / len; o[3] = w / len;
+  o[4] = a[4] + rx; o[5] = a[5] + ry; o[6] = a[6] + rz;
+}
+
+// SE3 inverse (sophus/se3.hpp:214-217): (q*, -q* t)
+SSBA_HD void se3_inverse(const double *a, double *o) {
+  o[0] = -a[0]; o[1] = -a[1]; o[2] = -a[2]; o[3] = a[3];
+  double rx, ry, rz;
+  quat_rotate(o, a[4], a[5], a[6], rx, ry, rz);
+  o[4] = -rx; o[5] = -ry; o[6] = -rz;
+}
+
+// SE3::log (sophus/se3.hpp:223-256) with SO3::logAndTheta (sophus/so3.hpp:245-286): tangent (upsilon, omega)
+SSBA_HD void se3_log(const double *T, double *d) {
+  const double eps = 1e-10;
+  const double sq = T[0] * T[0] + T[1] * T[1] + T[2] * T[2], w = T[3];
+  double f, theta;
+  if (sq < eps * eps) {
+    f = 2.0 / w - (2.0 / 3.0) * sq / (w * w * w);
+    theta = 2.0 * sq / w;
+  } else {
+    const double n = sqrt(sq);
+    if (fabs(w) < eps) f = (w > 0.0 ? 3.14159265358979323846 : -3.14159265358979323846) / n;
+    else f = 2.0 * atan(n / w) / n;
+    theta = f * n;
+  }
+  const double ox = f * T[0], oy = f * T[1], oz = f * T[2];
+  const double tx = T[4], ty = T[5], tz = T[6];
+  // V^-1 t = t - 0.5 (omega x t) + c (omega x (omega x t))
+  const double ax = oy * tz - oz * ty, ay = oz * tx - ox * tz, az = ox * ty - oy * tx;
+  const double bx = oy * az - oz * ay, by = oz * ax - ox * az, bz = ox * ay - oy * ax;
+  double c;
+  if (fabs(theta) < eps) c = 1.0 / 12.0;
+  else { const double h = 0.5 * theta; c = (1.0 - theta * cos(h) / (2.0 * sin(h))) / (theta * theta); }
+  d[0] = tx - 0.5 * ax + c * bx; d[1] = ty - 0.5 * ay + c * by; d[2] = tz - 0.5 * az + c * bz;
+  d[3] = ox; d[4] = oy; d[5] = oz;
+}
+
+// EdgePoseGraph::computeError (g2otypes.hpp:169-176): e = log(Minv * T0 * T1^-1); Minv = measurement^-1
+SSBA_HD void pose_graph_error(const double *Minv, const double *T0, const double *T1, double *e) {
+  double a[7], b[7], c[7];
+  se3_mul(Minv, T0, a);
+  se3_inverse(T1, b);
+  se3_mul(a, b, c);
+  se3_log(c, e);
+}
+
 }  // namespace ssba

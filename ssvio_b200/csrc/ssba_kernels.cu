@@ -1527,6 +1527,155 @@ __global__ void k_gather_points(const DeviceProblem P) {
   P.gather[i] = P.owner_mask[i / 3] ? P.point[P.ctl->cur][i] : 0.0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pose-graph optimisation (LoopClosing::PoseGraphOptimization, src/ssvio/loopclosing.cpp:458-532):
+// EdgePoseGraph errors e = log(M^-1 T0 T1^-1) (g2otypes.hpp:169-176) with the numeric Jacobians the
+// reference ships (base_binary_edge.hpp:144-212: central differences, delta = 1e-9, through
+// VertexPose::oplusImpl), identity information, no robust kernel; H and b assembled with fp64
+// atomics into the block pattern of the factor; the SAME level-scheduled solver (k_reduced_solve)
+// and the same control law (control_step) as the bundle adjustment.  Graphs are small (one vertex
+// per key-frame), so these kernels are plain: one thread per edge / per scalar.
+struct PoseGraphArgs {
+  int n_edges;
+  const int32_t *ev0, *ev1;   // pose rows
+  const int32_t *eq0, *eq1;   // block columns (q) or -1 for a fixed key-frame
+  const int32_t *eblk;        // off-diagonal block (row max(q0,q1), col min) or -1
+  const double *minv;         // n_edges x 7: measurement^-1
+  double *sysH;               // H and b of the current linearisation, layout of DeviceProblem::sys
+};
+
+__global__ void k_pg_begin(const DeviceProblem P, const PoseGraphArgs A) {
+  const Control *ctl = P.ctl;
+  if (ctl->done || !ctl->need_linearize) return;
+  const size_t n = 36 * (size_t)P.n_blocks + 6 * (size_t)P.n_fp;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) A.sysH[i] = 0.0;
+}
+
+__global__ void __launch_bounds__(64) k_pg_linearize(const DeviceProblem P, const PoseGraphArgs A) {
+  const Control *ctl = P.ctl;
+  if (ctl->done || !ctl->need_linearize) return;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= A.n_edges) return;
+  const double *pose = P.pose[ctl->cur];
+  double T0[7], T1[7], Mi[7], err[6];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) { T0[i] = pose[7 * A.ev0[e] + i]; T1[i] = pose[7 * A.ev1[e] + i]; Mi[i] = A.minv[7 * e + i]; }
+  pose_graph_error(Mi, T0, T1, err);
+  const int q0 = A.eq0[e], q1 = A.eq1[e];
+  const double delta = 1e-9, scalar = 1 / (2 * delta);
+  double J0[36], J1[36];  // row-major 6x6: J[6 * k + d] = d e_k / d delta_d
+#pragma unroll 1
+  for (int d = 0; d < 6; ++d) {
+    double add[6] = {0, 0, 0, 0, 0, 0}, Tp[7], ep[6], em[6];
+    if (q0 >= 0) {
+      add[d] = delta; pose_oplus(T0, add, Tp); pose_graph_error(Mi, Tp, T1, ep);
+      add[d] = -delta; pose_oplus(T0, add, Tp); pose_graph_error(Mi, Tp, T1, em);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) J0[6 * k + d] = scalar * (ep[k] - em[k]);
+    }
+    if (q1 >= 0) {
+      add[d] = delta; pose_oplus(T1, add, Tp); pose_graph_error(Mi, T0, Tp, ep);
+      add[d] = -delta; pose_oplus(T1, add, Tp); pose_graph_error(Mi, T0, Tp, em);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) J1[6 * k + d] = scalar * (ep[k] - em[k]);
+    }
+  }
+  double *bvec = A.sysH + 36 * (size_t)P.n_blocks;
+  // constructQuadraticForm (base_binary_edge.hpp:61-134) with Omega = I and no robust kernel
+  auto add_diag = [&](int q, const double *J) {
+    double *D = A.sysH + 36 * (size_t)P.col_diag[q];
+    for (int r = 0; r < 6; ++r) {
+      double br = 0.0;
+      for (int k = 0; k < 6; ++k) br -= J[6 * k + r] * err[k];
+      atomicAdd(bvec + 6 * q + r, br);
+      for (int c = 0; c < 6; ++c) {
+        double h = 0.0;
+        for (int k = 0; k < 6; ++k) h += J[6 * k + r] * J[6 * k + c];
+        atomicAdd(D + 6 * r + c, h);
+      }
+    }
+  };
+  if (q0 >= 0) add_diag(q0, J0);
+  if (q1 >= 0) add_diag(q1, J1);
+  if (q0 >= 0 && q1 >= 0) {
+    // block (row max(q0, q1), col min): Jrow^T Jcol
+    const double *Jr = q0 > q1 ? J0 : J1, *Jc = q0 > q1 ? J1 : J0;
+    double *B = A.sysH + 36 * (size_t)A.eblk[e];
+    for (int r = 0; r < 6; ++r)
+      for (int c = 0; c < 6; ++c) {
+        double h = 0.0;
+        for (int k = 0; k < 6; ++k) h += Jr[6 * k + r] * Jc[6 * k + c];
+        atomicAdd(B + 6 * r + c, h);
+      }
+  }
+}
+
+// lambda_0 = tau * max |H_jj| (levenberg.cpp:152-166) at the first iteration
+__global__ void __launch_bounds__(256) k_pg_lambda_init(const DeviceProblem P, const PoseGraphArgs A) {
+  Control *ctl = P.ctl;
+  if (ctl->done || !ctl->first_iteration) return;
+  __shared__ double red[8];
+  double m = 0.0;
+  for (int i = threadIdx.x; i < 6 * P.n_fp; i += 256) m = fmax(m, fabs(A.sysH[36 * (size_t)P.col_diag[i / 6] + 7 * (i % 6)]));
+  m = block_max<256>(m, red);
+  if (threadIdx.x == 0) {
+    ctl->maxdiag = m;
+    ctl->lambda = ctl->user_lambda > 0 ? ctl->user_lambda : ctl->tau * m;
+    ctl->ni = 2.0;
+    ctl->first_iteration = 0;
+  }
+}
+
+// the trial's system: H + lambda I (setLambda, block_solver.hpp:524-548), b twice (bschur, b_p)
+__global__ void k_pg_prepare(const DeviceProblem P, const PoseGraphArgs A) {
+  const Control *ctl = P.ctl;
+  if (ctl->done) return;
+  const double lambda = ctl->lambda;
+  const size_t nb = 36 * (size_t)P.n_blocks, nv = 6 * (size_t)P.n_fp;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nb + nv; i += (size_t)gridDim.x * blockDim.x) {
+    double v = A.sysH[i];
+    if (i < nb) {
+      const int b = (int)(i / 36), o = (int)(i - 36 * (size_t)b);
+      if (P.blk_row[b] == P.blk_col[b] && o % 7 == 0) v += lambda;
+      P.sys[i] = v;
+    } else {
+      P.sys[i] = v;
+      P.sys[i + nv] = v;
+    }
+  }
+}
+
+// chi2 of the current and of the trial poses (activeRobustChi2 without a kernel = sum e^T e), then the
+// accept / reject decision
+__global__ void __launch_bounds__(256) k_pg_chi_control(const DeviceProblem P, const PoseGraphArgs A, int control) {
+  Control *ctl = P.ctl;
+  if (control && ctl->done) return;
+  __shared__ double red[8];
+  const int cur = ctl->cur;
+  double a = 0.0, b = 0.0;
+  for (int e = threadIdx.x; e < A.n_edges; e += 256) {
+    double T0[7], T1[7], Mi[7], err[6];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) Mi[i] = A.minv[7 * e + i];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const double *pose = P.pose[cur ^ w];
+#pragma unroll
+      for (int i = 0; i < 7; ++i) { T0[i] = pose[7 * A.ev0[e] + i]; T1[i] = pose[7 * A.ev1[e] + i]; }
+      pose_graph_error(Mi, T0, T1, err);
+      double c2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) c2 += err[k] * err[k];
+      if (w == 0) a += c2; else b += c2;
+    }
+  }
+  a = block_sum<256>(a, red);
+  b = block_sum<256>(b, red);
+  if (threadIdx.x != 0) return;
+  P.scal[0] = a; P.scal[1] = b; P.scal[2] = 0.0;
+  if (control) control_step(P);
+}
+
 inline int div_up(long long a, int b) { return (int)((a + b - 1) / b); }
 
 }  // namespace
@@ -1643,6 +1792,25 @@ void launch_gather_points(const DeviceProblem &P, cudaStream_t st) {
 
 void launch_edge_errors(const DeviceProblem &P, cudaStream_t st) {
   k_final_chi2<<<P.n_fin_blocks, kLinThreads, 0, st>>>(P, 0.0, 1);
+}
+
+void launch_pose_graph_slot(const DeviceProblem &P, int n_edges, const int32_t *ev0, const int32_t *ev1, const int32_t *eq0,
+                            const int32_t *eq1, const int32_t *eblk, const double *minv, double *sysH, bool first,
+                            cudaStream_t st) {
+  PoseGraphArgs A{n_edges, ev0, ev1, eq0, eq1, eblk, minv, sysH};
+  const int nz = div_up((long long)P.sys_doubles, 256);
+  k_pg_begin<<<nz, 256, 0, st>>>(P, A);
+  if (n_edges > 0) k_pg_linearize<<<div_up(n_edges, 64), 64, 0, st>>>(P, A);
+  if (first) k_pg_lambda_init<<<1, 256, 0, st>>>(P, A);
+  k_pg_prepare<<<nz, 256, 0, st>>>(P, A);
+  launch_reduced_solve(P, st);
+  k_pg_chi_control<<<1, 256, 0, st>>>(P, A, 1);
+}
+
+void launch_pose_graph_chi(const DeviceProblem &P, int n_edges, const int32_t *ev0, const int32_t *ev1, const double *minv,
+                           cudaStream_t st) {
+  PoseGraphArgs A{n_edges, ev0, ev1, nullptr, nullptr, nullptr, minv, nullptr};
+  k_pg_chi_control<<<1, 256, 0, st>>>(P, A, 0);
 }
 
 }  // namespace ssba

@@ -1164,6 +1164,43 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   return true;
 }
 
+// The reduced-solver part of a Structure for an arbitrary block-sparse SPD system over `n` 6x6 block
+// columns (pose-graph optimisation: H itself instead of a Schur complement): elimination order,
+// symbolic factorisation, levels, the packed device program.  adj[c] = rows r > c with a block (r, c).
+// perm_out[q] = original column of elimination position q.
+bool build_solver_structure(int n, const std::vector<std::vector<int>> &adj, Structure &s, std::vector<int> &perm_out,
+                            std::string &err) {
+  reset_keep_capacity(s);
+  std::vector<int> perm_nat(n), perm_nd;
+  std::iota(perm_nat.begin(), perm_nat.end(), 0);
+  Factor f_nat, f_nd;
+  Factor *best = nullptr;
+  std::vector<int> *best_perm = &perm_nat;
+  if (n >= 24) {
+    nested_dissection_order(n, adj, perm_nd);
+    if (perm_nd != perm_nat) {
+      if (!symbolic_factor(n, adj, perm_nd, f_nd, err)) return false;
+      best = &f_nd; best_perm = &perm_nd;
+    }
+  }
+  if (!best || 2 * f_nd.n_levels > n) {
+    if (!symbolic_factor(n, adj, perm_nat, f_nat, err)) return false;
+    if (!best || f_nat.est_cycles <= f_nd.est_cycles) { best = &f_nat; best_perm = &perm_nat; }
+  }
+  perm_out = *best_perm;
+  s.n_fp = n;
+  s.n_schur_blocks = best->n_schur;
+  s.n_blocks = best->n_blocks; s.n_levels = best->n_levels; s.n_tasks = (int)best->task_dst.size();
+  s.est_solver_cycles = best->est_cycles;
+  s.col_ptr.swap(best->col_ptr); s.blk_row.swap(best->blk_row); s.blk_col.swap(best->blk_col);
+  s.row_ptr.swap(best->row_ptr); s.row_blk.swap(best->row_blk); s.row_col.swap(best->row_col);
+  s.level_ptr.swap(best->level_ptr); s.level_col.swap(best->level_col);
+  s.ltask_ptr.swap(best->ltask_ptr); s.task_dst.swap(best->task_dst); s.task_pos.swap(best->task_pos); s.task_pair_ptr.swap(best->task_pair_ptr);
+  s.pair_a.swap(best->pair_a); s.pair_b.swap(best->pair_b);
+  build_solver_program(s);
+  return true;
+}
+
 void parallel_copy(const std::vector<CopyJob> &jobs) {
   size_t total = 0;
   for (auto &j : jobs) total += j.bytes;

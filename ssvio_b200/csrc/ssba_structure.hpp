@@ -124,6 +124,10 @@ struct Structure {
 bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std::string &err,
                      const std::function<void()> *on_edges_ready = nullptr);
 
+// Solver-only structure for a block-sparse SPD system over n 6x6 block columns (see ssba_structure.cpp).
+bool build_solver_structure(int n, const std::vector<std::vector<int>> &adj, Structure &s, std::vector<int> &perm_out,
+                            std::string &err);
+
 // memcpy of several regions on the host thread pool of the structure builder
 struct CopyJob { void *dst; const void *src; size_t bytes; };
 void parallel_copy(const std::vector<CopyJob> &jobs);
