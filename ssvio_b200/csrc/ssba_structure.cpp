@@ -597,22 +597,40 @@ class HostPool {
   static HostPool &get() { static HostPool *p = new HostPool; return *p; }
   int size() const { return n_; }
   // fn(t, T) for t in [0, T); the caller runs t = 0.  Calls are serialised.
+  // The passes of one structure build follow each other within microseconds: a worker that has just
+  // finished keeps polling for the next job for a short while before it goes to sleep on the
+  // condition variable (a futex wake-up costs tens of microseconds, eight times per build), and the
+  // caller polls the same way for the workers to finish.
   void run(int T, const std::function<void(int, int)> &fn) {
     if (T <= 1 || n_ <= 1) { fn(0, 1); return; }
     if (T > n_) T = n_;
     std::lock_guard<std::mutex> outer(run_mu_);
     {
       std::lock_guard<std::mutex> lk(mu_);
-      fn_ = &fn; T_ = T; pending_ = T - 1; ++gen_;
+      fn_ = &fn; T_ = T; pending_.store(T - 1, std::memory_order_relaxed);
+      gen_.fetch_add(1, std::memory_order_release);
     }
-    cv_.notify_all();
+    if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_all();
     fn(0, T);
-    std::unique_lock<std::mutex> lk(mu_);
-    done_cv_.wait(lk, [&] { return pending_ == 0; });
+    if (!spin_until([&] { return pending_.load(std::memory_order_acquire) == 0; })) {
+      std::unique_lock<std::mutex> lk(mu_);
+      done_cv_.wait(lk, [&] { return pending_.load(std::memory_order_acquire) == 0; });
+    }
     fn_ = nullptr;
   }
 
  private:
+  static constexpr int kSpinMicros = 200;
+  template <class Pred> static bool spin_until(Pred done) {
+    const auto t_end = std::chrono::steady_clock::now() + std::chrono::microseconds(kSpinMicros);
+    for (int i = 0;; ++i) {
+      if (done()) return true;
+      if ((i & 63) == 63 && std::chrono::steady_clock::now() > t_end) return false;
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#endif
+    }
+  }
   HostPool() {
     int n = std::min((int)std::thread::hardware_concurrency(), 4);  // measured on the B200 hosts: 4 threads is the knee
     if (const char *e = std::getenv("SSBA_HOST_THREADS")) n = std::atoi(e);
@@ -622,18 +640,25 @@ class HostPool {
   void worker(int t) {
     unsigned long seen = 0;
     for (;;) {
+      if (!spin_until([&] { return gen_.load(std::memory_order_acquire) != seen; })) {
+        std::unique_lock<std::mutex> lk(mu_);
+        sleepers_.fetch_add(1, std::memory_order_release);
+        cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen; });
+        sleepers_.fetch_sub(1, std::memory_order_release);
+      }
       const std::function<void(int, int)> *fn = nullptr;
       int T = 0;
       {
-        std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return gen_ != seen; });
-        seen = gen_;
+        std::lock_guard<std::mutex> lk(mu_);
+        seen = gen_.load(std::memory_order_acquire);
         if (t < T_) { fn = fn_; T = T_; }
       }
       if (fn) {
         (*fn)(t, T);
-        std::lock_guard<std::mutex> lk(mu_);
-        if (--pending_ == 0) done_cv_.notify_one();
+        if (pending_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+          std::lock_guard<std::mutex> lk(mu_);  // pairs with the caller's wait (no lost wake-up)
+          done_cv_.notify_one();
+        }
       }
     }
   }
@@ -641,8 +666,9 @@ class HostPool {
   std::mutex mu_, run_mu_;
   std::condition_variable cv_, done_cv_;
   const std::function<void(int, int)> *fn_ = nullptr;
-  int T_ = 0, pending_ = 0;
-  unsigned long gen_ = 0;
+  int T_ = 0;
+  std::atomic<int> pending_{0}, sleepers_{0};
+  std::atomic<unsigned long> gen_{0};
 };
 inline void split_range(int t, int T, int N, int &b, int &e) {
   b = (int)((long long)N * t / T);
