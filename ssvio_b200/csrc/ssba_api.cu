@@ -401,6 +401,7 @@ ssba_status ssba_create(const ssba_options *opt, ssba_handle **out) {
     static int cluster_cap = 0;  // per process: the B200s of a node are alike
     if (cluster_cap == 0) cluster_cap = max_solver_cluster();
     set_solver_cluster_cap(cluster_cap);
+    set_ranks_on_host(o.world_size);  // one process per GPU of one node
   }
   if (o.stream) { h->stream = (cudaStream_t)o.stream; }
   else {

@@ -588,6 +588,9 @@ void nested_dissection_order(int n, const std::vector<std::vector<int>> &adj_low
 
 }  // namespace
 
+static std::atomic<int> g_ranks_on_host{1};
+void set_ranks_on_host(int n) { g_ranks_on_host.store(n > 0 ? n : 1); }
+
 // ---- a small persistent fork-join pool for the host passes over the edges (the structure build
 // is on the end-to-end path of every ssba_initialize call)
 namespace {
@@ -635,6 +638,8 @@ class HostPool {
     // measured on the B200 hosts (16 cores) with the polling pool: initialize 1.84 ms with 4 threads, 1.59 with 6,
     // 1.74 with 8 - the passes are short and memory-bound
     int n = std::min((int)std::thread::hardware_concurrency(), 6);
+    // several ranks on one host (one process per GPU) share its cores: polling workers must not oversubscribe them
+    n = std::max(1, std::min(n, (int)std::thread::hardware_concurrency() / std::max(1, g_ranks_on_host.load())));
     if (const char *e = std::getenv("SSBA_HOST_THREADS")) n = std::atoi(e);
     n_ = std::max(1, std::min(n, 64));
     for (int t = 1; t < n_; ++t) std::thread([this, t] { worker(t); }).detach();

@@ -128,6 +128,9 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
 bool build_solver_structure(int n, const std::vector<std::vector<int>> &adj, Structure &s, std::vector<int> &perm_out,
                             std::string &err);
 
+// How many ranks (processes) share this host: sizes the host thread pool; call before the first build.
+void set_ranks_on_host(int n);
+
 // memcpy of several regions on the host thread pool of the structure builder
 struct CopyJob { void *dst; const void *src; size_t bytes; };
 void parallel_copy(const std::vector<CopyJob> &jobs);
