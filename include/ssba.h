@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define SSBA_VERSION_MAJOR 0
-#define SSBA_VERSION_MINOR 1
+#define SSBA_VERSION_MINOR 2  /* 0.2: + ssba_pose_only_optimize, ssba_pose_graph_optimize, ssba_set_profiling */
 
 #define SSBA_MAX_ITER_RECORDS 128
 #define SSBA_MAX_CAMERAS 8
