@@ -352,6 +352,9 @@ int main() {
   check_case(100, 4000, 5, 6, false, 0, false, 1);
   check_case(500, 20000, 5, 7, true, 0, false, 1);
   check_case(12, 600, 12, 8, false, 0, false, 1);
+  check_case(48, 1500, 6, 9, false, 0, true, 1);    // 32 <= poses < 64: the 4-CTA cluster
+  check_case(33, 400, 33, 10, true, 0, false, 1);   // dense co-visibility: one separator, natural order
+  check_case(150, 3000, 3, 11, false, 40, true, 4); // narrow band with long-range loops
   if (fails) { std::printf("%d FAILURES\n", fails); return 1; }
   std::printf("OK\n");
   return 0;
