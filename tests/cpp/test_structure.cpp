@@ -355,6 +355,7 @@ int main() {
   check_case(48, 1500, 6, 9, false, 0, true, 1);    // 32 <= poses < 64: the 4-CTA cluster
   check_case(33, 400, 33, 10, true, 0, false, 1);   // dense co-visibility: one separator, natural order
   check_case(150, 3000, 3, 11, false, 40, true, 4); // narrow band with long-range loops
+  check_case(140, 6, 140, 12, false, 0, false, 2);  // landmarks seen by more poses than a CTA has threads: the big-chunk path
   if (fails) { std::printf("%d FAILURES\n", fails); return 1; }
   std::printf("OK\n");
   return 0;
