@@ -164,6 +164,47 @@ def test_rejected_trials_match_oracle(BA, port_oracle):
     assert rel(rep.chi2_robust, port.chi2_robust) < 1e-8
 
 
+def dense_graph(n_kf=140, n_points=6, seed=12, iters=4):
+    """Key-frames 5 cm apart that ALL see the same few landmarks in both cameras (a slow approach to a wall)."""
+    rng = np.random.default_rng(seed)
+    idx = np.arange(n_kf, dtype=np.float64)
+    gt = synth.se3_exp(np.stack([0.001 * idx, 0 * idx, -0.05 * idx, 0 * idx, 0.0005 * idx, 0 * idx], axis=1))
+    pts = np.stack([rng.uniform(-6, 6, n_points), rng.uniform(-2, 2, n_points), rng.uniform(14, 24, n_points)], axis=1)
+    K = np.array([synth.FX, 0, synth.CX, 0, synth.FY, synth.CY, 0, 0, 1.0])
+    ext = np.array([[0, 0, 0, 1, 0, 0, 0], [0, 0, 0, 1, -synth.BF / synth.FX, 0, 0]], dtype=np.float64)
+    pose_idx, point_idx, cam_idx, uv = [], [], [], []
+    for j in range(n_points):
+        for i in range(n_kf):
+            pb = synth.se3_act(gt[i], pts[j])
+            for c in range(2):
+                pc = synth.se3_act(ext[c], pb)
+                pose_idx.append(i); point_idx.append(j); cam_idx.append(c)
+                uv.append([synth.FX * pc[0] / pc[2] + synth.CX + 0.5 * rng.standard_normal(),
+                           synth.FY * pc[1] / pc[2] + synth.CY + 0.5 * rng.standard_normal()])
+    d = np.concatenate([0.02 * rng.standard_normal((n_kf, 3)), 0.002 * rng.standard_normal((n_kf, 3))], axis=1)
+    poses = synth.se3_mul(synth.se3_exp(d), gt)
+    return synth.Graph(K=K, ext=ext, poses=poses, pose_fixed=np.zeros(n_kf, np.uint8),
+                       points=pts + 0.1 * rng.standard_normal(pts.shape), point_fixed=np.zeros(n_points, np.uint8),
+                       pose_idx=np.array(pose_idx, np.int32), point_idx=np.array(point_idx, np.int32),
+                       cam_idx=np.array(cam_idx, np.uint8), uv=np.array(uv), name="dense", iters=iters)
+
+
+def test_landmarks_seen_by_more_poses_than_a_cta_has_threads(BA, port_oracle):
+    """140 key-frames that all see the same six landmarks: 140 (pose, landmark) pairs per landmark (the strided
+    big-chunk path of k_linearize / k_update), k = 140 poses per Schur run (unstaged W, 9870 block pairs in
+    chunks of 32), a dense 140-column reduced system (natural order, one column per level)."""
+    g = dense_graph()
+    assert g.n_edges == 140 * 6 * 2
+    port = port_oracle.optimize(g, jacobian="analytic")
+    r = run_gpu(BA, g)
+    rep = r["report"]
+    assert r["info"].n_pairs == 140 * 6 and r["info"].n_schur_blocks == 140 * 141 // 2
+    assert rep.iterations == port["report"].iterations
+    assert rel(rep.chi2_initial, port["report"].chi2_initial) < 1e-12
+    assert rel(rep.chi2_robust, port["report"].chi2_robust) < 1e-8
+    np.testing.assert_allclose(r["errors"], port["errors"], rtol=0, atol=1e-5)
+
+
 def test_step_api_equals_optimize(BA):
     """ssba_step(i) (what the g2o shim's solve(i) calls) walks the same trajectory as optimize(N)."""
     g, _ = golden_case("small")
