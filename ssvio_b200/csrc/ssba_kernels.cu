@@ -9,6 +9,7 @@
 //
 // Reference semantics per kernel are cited at each kernel; g2o/ = thirdparty/g2o/g2o/.
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cstdlib>
 
@@ -1705,13 +1706,18 @@ void launch_maxdiag(const DeviceProblem &P, cudaStream_t st) { k_maxdiag<<<1, 10
 
 void launch_lambda_init(const DeviceProblem &P, cudaStream_t st) { k_lambda_init<<<1, 1, 0, st>>>(P); }
 
+// function attributes are per device: remember which devices of this process have them
+bool first_launch_on_this_device(std::atomic<unsigned long long> &seen) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  return (seen.fetch_or(bit) & bit) == 0;
+}
+
 void launch_schur(const DeviceProblem &P, bool prefolded, cudaStream_t st) {
-  static bool attr_set = false;
+  static std::atomic<unsigned long long> seen{0};
   constexpr size_t kDyn = (size_t)kSchurWarps * kSchurRunPairs * 18 * sizeof(double);
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDyn);
-    attr_set = true;
-  }
+  if (first_launch_on_this_device(seen)) cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDyn);
   const int n_pose = div_up(P.n_fp, kSchurWarps), n_unit = div_up(P.n_units, kSchurWarps);
   if (n_pose + n_unit > 0) k_schur<<<n_pose + n_unit, 32 * kSchurWarps, kDyn, st>>>(P, n_pose, prefolded ? 1 : 0);
 }
@@ -1740,13 +1746,12 @@ int max_solver_cluster() {
 }
 
 void launch_reduced_solve(const DeviceProblem &P, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> seen{0};
+  if (first_launch_on_this_device(seen)) {
     cudaFuncSetAttribute(k_reduced_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveMaxDynSmem);
     cudaFuncSetAttribute(k_reduced_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveMaxDynSmem);
     cudaFuncSetAttribute(k_reduced_solve<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveMaxDynSmem);
     cudaFuncSetAttribute(k_reduced_solve<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveMaxDynSmem);
-    attr_set = true;
   }
   const SolverSmemLayout lay = solver_smem_layout(P.n_fp, P.prog_max_seg);
   const int c = P.solve_cluster;  // the program was built for this many CTAs
