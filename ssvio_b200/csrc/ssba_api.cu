@@ -896,7 +896,6 @@ ssba_status ssba_pose_only_optimize(ssba_handle *h, const double K[9], int32_t n
   const size_t total = align_up(top);
   if (total > h->d_po_bytes) {
     if (h->d_po) cudaFree(h->d_po);
-  if (h->d_pg) cudaFree(h->d_pg);
     h->d_po = nullptr; h->d_po_bytes = 0;
     if (cudaMalloc((void **)&h->d_po, total + total / 4) != cudaSuccess) { cudaGetLastError(); return fail(h, SSBA_ERR_ALLOC, "cudaMalloc failed"); }
     h->d_po_bytes = total + total / 4;

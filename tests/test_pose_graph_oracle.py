@@ -1,6 +1,6 @@
 """Oracle side of the pose-graph optimisation (LoopClosing::PoseGraphOptimization,
 src/ssvio/loopclosing.cpp:458-532): the numpy restatement against fixtures made by the
-compiled reference.  The CUDA path for this row is not built yet, so there is no -m gpu test here.
+compiled reference.  The CUDA path of this row is tested against the same fixtures in tests/test_pose_graph.py.
 
 The reference uses numeric Jacobians (delta = 1e-9) for EdgePoseGraph: the trajectory carries ~1e-7 relative
 noise that no restatement reproduces bit for bit, so chi2 is compared to 1e-6 relative (the north-star
