@@ -298,6 +298,10 @@ typedef struct ssba_problem_info {
   int32_t solve_cluster;   /* CTAs of the thread-block cluster the reduced solve runs on          */
   int32_t peer_exchange;   /* several GPUs: 1 = per-trial exchanges through NVLink peer memory,     */
                            /* 0 = NCCL all-reduce (ranks on different nodes, or CUDA IPC refused)  */
+  int32_t solver_kind;     /* 1 = subtree-per-CTA solver (k_tree_solve), 0 = level-scheduled solver  */
+  int32_t solver_steps;    /* elimination steps on the critical path of the reduced solve            */
+  int32_t solver_top_cols; /* columns of the top part (factored by CTA 0 after the hand-off)          */
+  int32_t solver_smem_bytes;
 } ssba_problem_info;
 ssba_status ssba_get_problem_info(ssba_handle *h, ssba_problem_info *out);
 

@@ -78,7 +78,9 @@ class ProblemInfo(C.Structure):
     _fields_ = [("n_free_poses", C.c_int32), ("n_free_points", C.c_int32),
                 ("n_active_edges", C.c_int32), ("n_pairs", C.c_int32),
                 ("n_schur_blocks", C.c_int32), ("n_factor_blocks", C.c_int32),
-                ("device_bytes", C.c_int64), ("solve_cluster", C.c_int32), ("peer_exchange", C.c_int32)]
+                ("device_bytes", C.c_int64), ("solve_cluster", C.c_int32), ("peer_exchange", C.c_int32),
+                ("solver_kind", C.c_int32), ("solver_steps", C.c_int32), ("solver_top_cols", C.c_int32),
+                ("solver_smem_bytes", C.c_int32)]
 
 
 class SsbaError(RuntimeError):

@@ -16,8 +16,10 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libssba.so")
 
-SOURCES = ["ssba_kernels.cu", "ssba_pose_only.cu", "ssba_api.cu", "ssba_structure.cpp"]
-HEADERS = ["ssba_geometry.cuh", "ssba_device.hpp", "ssba_structure.hpp", "ssba_solver_layout.hpp"]
+SOURCES = ["ssba_kernels.cu", "ssba_tree_solve.cu", "ssba_pose_only.cu", "ssba_api.cu", "ssba_structure.cpp",
+           "ssba_tree_program.cpp"]
+HEADERS = ["ssba_geometry.cuh", "ssba_device.hpp", "ssba_structure.hpp", "ssba_solver_layout.hpp",
+           "ssba_tree_program.hpp"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

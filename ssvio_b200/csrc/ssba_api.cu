@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 #include <functional>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -398,9 +399,12 @@ ssba_status ssba_create(const ssba_options *opt, ssba_handle **out) {
   if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) return fail(nullptr, SSBA_ERR_CUDA, "cudaGetDeviceProperties failed");
   if (prop.major < 10) return fail(nullptr, SSBA_ERR_NO_DEVICE, "libssba is built for sm_100a (Blackwell) only");
   {
-    static int cluster_cap = 0;  // per process: the B200s of a node are alike
-    if (cluster_cap == 0) cluster_cap = max_solver_cluster();
+    // per process: the B200s of a node are alike
+    static std::once_flag caps_once;
+    static int cluster_cap = 1, tree_cap = 1;
+    std::call_once(caps_once, [] { cluster_cap = max_solver_cluster(); tree_cap = max_tree_cluster(); });
     set_solver_cluster_cap(cluster_cap);
+    set_tree_cluster_cap(tree_cap);
     set_ranks_on_host(o.world_size);  // one process per GPU of one node
   }
   if (o.stream) { h->stream = (cudaStream_t)o.stream; }
@@ -607,6 +611,8 @@ ssba_status ssba_initialize(ssba_handle *h) {
   STAT(items_b, s.unit_combo_ptr, unit_combo_ptr); STAT(items_b, s.combo_blk, combo_blk);
   STAT(items_b, s.blk_row, blk_row); STAT(items_b, s.blk_col, blk_col); STAT(items_b, s.col_ptr, col_diag);
   STAT(items_b, s.prog, prog); STAT(items_b, s.prog_ptr, prog_ptr);
+  const int32_t *d_tree_prog = nullptr;
+  stat(items_b, s.tree.words.data(), s.tree.words.size() * sizeof(int32_t), (const void **)&d_tree_prog);
   const size_t bytes_b = align_up(top) - off_b;
   P.n_fin_blocks = (s.n_slots + 127) / 128 > 0 ? (s.n_slots + 127) / 128 : 1;
   P.n_lin_blocks = P.n_upd_blocks = s.n_lchunks;
@@ -617,6 +623,8 @@ ssba_status ssba_initialize(ssba_handle *h) {
   DYN(chi_cur_part, nblk, double); DYN(maxdiag_part, nblk, double); DYN(chi_new_part, nblk, double); DYN(scale_part, nblk, double);
   DYN(scal, 8, double); DYN(chi_out, 8, double);
   DYN(ctl, 1, Control);
+  double *d_tree_xchg = nullptr;
+  dyn(sizeof(double) * (size_t)std::max(s.tree.xchg_doubles, 2), (void **)&d_tree_xchg);
 #undef STAT
 #undef DYN
   const size_t total = align_up(top);
@@ -648,6 +656,7 @@ ssba_status ssba_initialize(ssba_handle *h) {
   P.prog_max_seg = s.prog_max_seg;
   P.n_segments = s.n_segments;
   P.solve_cluster = s.solve_cluster;
+  fill_tree_dev(s.tree, d_tree_prog, d_tree_xchg, P.tree);
   if (h->opt.world_size > 1) {
     ssba_status prc = setup_peer_exchange(h, P.sys_doubles);
     if (prc) return prc;
@@ -1000,9 +1009,10 @@ ssba_status ssba_pose_graph_optimize(ssba_handle *h, int32_t n_poses, const doub
                o_minv = place(minv.data(), 56 * (size_t)ne), o_poq = place(pose_of_q.data(), 4 * (size_t)nf),
                o_brow = place(s.blk_row.data(), 4 * s.blk_row.size()), o_bcol = place(s.blk_col.data(), 4 * s.blk_col.size()),
                o_cdiag = place(s.col_ptr.data(), 4 * s.col_ptr.size()), o_prog = place(s.prog.data(), 4 * s.prog.size()),
-               o_pptr = place(s.prog_ptr.data(), 4 * s.prog_ptr.size());
+               o_pptr = place(s.prog_ptr.data(), 4 * s.prog_ptr.size()), o_tprog = place(s.tree.words.data(), 4 * s.tree.words.size());
   const size_t o_pose1 = place(nullptr, 56 * (size_t)n_poses), o_sysH = place(nullptr, 8 * P.sys_doubles), o_sys = place(nullptr, 8 * P.sys_doubles),
-               o_xp = place(nullptr, 48 * (size_t)nf), o_scal = place(nullptr, 64), o_ctl = place(nullptr, sizeof(Control));
+               o_xp = place(nullptr, 48 * (size_t)nf), o_scal = place(nullptr, 64), o_ctl = place(nullptr, sizeof(Control)),
+               o_txchg = place(nullptr, 8 * (size_t)std::max(s.tree.xchg_doubles, 2));
   const size_t total = align_up(top);
   if (total > h->d_pg_bytes) {
     if (h->d_pg) cudaFree(h->d_pg);
@@ -1018,6 +1028,7 @@ ssba_status ssba_pose_graph_optimize(ssba_handle *h, int32_t n_poses, const doub
   P.pose_of_q = (const int32_t *)(d + o_poq); P.blk_row = (const int32_t *)(d + o_brow); P.blk_col = (const int32_t *)(d + o_bcol);
   P.col_diag = (const int32_t *)(d + o_cdiag); P.prog = (const int32_t *)(d + o_prog); P.prog_ptr = (const int32_t *)(d + o_pptr);
   P.sys = (double *)(d + o_sys); P.xp = (double *)(d + o_xp); P.scal = (double *)(d + o_scal); P.ctl = (Control *)(d + o_ctl);
+  fill_tree_dev(s.tree, (const int32_t *)(d + o_tprog), (double *)(d + o_txchg), P.tree);
   const int32_t *d_ev0 = (const int32_t *)(d + o_ev0), *d_ev1 = (const int32_t *)(d + o_ev1), *d_eq0 = (const int32_t *)(d + o_eq0),
                 *d_eq1 = (const int32_t *)(d + o_eq1), *d_eblk = (const int32_t *)(d + o_eblk);
   const double *d_minv = (const double *)(d + o_minv);
@@ -1093,6 +1104,10 @@ ssba_status ssba_get_problem_info(ssba_handle *h, ssba_problem_info *out) {
   out->device_bytes = (int64_t)h->device_bytes;
   out->solve_cluster = h->s.solve_cluster;
   out->peer_exchange = h->use_p2p ? 1 : 0;
+  out->solver_kind = h->s.tree.ok ? 1 : 0;
+  out->solver_steps = h->s.tree.ok ? h->s.tree.chain_steps : h->s.n_levels;
+  out->solver_top_cols = h->s.tree.ok ? h->s.tree.n_top_cols : 0;
+  out->solver_smem_bytes = h->s.tree.ok ? (int32_t)h->s.tree.smem_bytes : 0;
   return SSBA_OK;
 }
 

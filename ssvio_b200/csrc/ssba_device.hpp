@@ -6,6 +6,7 @@
 
 #include "ssba.h"
 #include "ssba_geometry.cuh"
+#include "ssba_tree_program.hpp"
 
 namespace ssba {
 
@@ -20,7 +21,8 @@ struct Control {
   // LM state
   double lambda, ni;
   double current_chi, temp_chi, rho;
-  double scale_pose;       // sum over poses of x (lambda x + b), written by the reduced solve
+  double scale_pose_part[kTreeMaxCluster];  // sum over poses of x (lambda x + b): one partial per CTA of the reduced
+                           // solve (k_reduced_solve writes [0] only), folded in order by control_step
   double maxdiag;          // max |H_jj| for computeLambdaInit
   double chi2_initial;
   int cur;                 // which of the two state buffers holds the current estimate
@@ -51,6 +53,17 @@ struct PeerHeader {
   long long flag_sys_from[SSBA_MAX_PEERS];    // rank s's partial reduced system of that trial is complete
   long long flag_scal_from[SSBA_MAX_PEERS];   // rank s's partial sums of that trial have arrived
   double scal_from[SSBA_MAX_PEERS][2][4];     // [s][parity]: chi(current), chi(trial), landmark part of computeScale
+};
+
+// the subtree-per-CTA solver program on the device (ssba_tree_program.hpp); C == 0: not in use
+struct TreeDev {
+  int C;
+  unsigned smem_bytes;
+  const int32_t *prog;
+  double *xchg;  // contributions of CTAs 1 .. C-1 to the top part
+  int32_t prog_ptr[kTreeMaxCluster + 1];
+  int32_t pool_doubles[kTreeMaxCluster], b0[kTreeMaxCluster], n_own_blocks[kTreeMaxCluster], q0[kTreeMaxCluster],
+      n_own_cols[kTreeMaxCluster], contrib_off[kTreeMaxCluster], contrib_doubles[kTreeMaxCluster], xchg_off[kTreeMaxCluster];
 };
 
 struct DeviceProblem {
@@ -86,6 +99,7 @@ struct DeviceProblem {
   const int32_t *prog, *prog_ptr;  // per-level solver program (ssba_structure.cpp build_solver_program)
   int prog_max_seg, n_segments;
   int solve_cluster;               // CTAs the solver program was dealt over (1, 2, 4, 8)
+  TreeDev tree;                    // k_tree_solve's program; tree.C == 0: k_reduced_solve and the level program
   // system
   double *W;          // n_pairs x 18, 6x3 row-major  (Hpl blocks)
   double *Hll;        // n_slots x 6 (xx xy xz yy yz zz)
@@ -138,6 +152,10 @@ void launch_pose_graph_slot(const DeviceProblem &P, int n_edges, const int32_t *
 void launch_pose_graph_chi(const DeviceProblem &P, int n_edges, const int32_t *ev0, const int32_t *ev1, const double *minv,
                            cudaStream_t st);
 int max_solver_cluster();  // largest k_reduced_solve cluster the current device can co-schedule
+int max_tree_cluster();    // ... and the largest k_tree_solve cluster (16 when the non-portable size is available)
+void launch_tree_solve(const DeviceProblem &P, cudaStream_t st);  // ssba_tree_solve.cu
+// host: fills TreeDev from a planned program (prog / xchg are device pointers)
+void fill_tree_dev(const TreeProgram &tp, const int32_t *d_prog, double *d_xchg, TreeDev &out);
 
 // batched pose-only LM (ssba_pose_only.cu): one warp per frame, everything in one launch
 void launch_pose_only(const double K[9], int n_frames, int rounds, int iters, int max_trials, double chi2_threshold,

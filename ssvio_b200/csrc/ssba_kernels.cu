@@ -1133,7 +1133,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
     for (int i = 0; i < 7; ++i) P.pose[cur ^ 1][7 * kv + i] = fail ? T[i] : out[i];
   }
   if (tid == 0) {
-    ctl->scale_pose = sc;
+    ctl->scale_pose_part[0] = sc;
     ctl->chol_fail = fail ? 1 : 0;
   }
   TRACE(4 * NSEG + 2);
@@ -1152,7 +1152,10 @@ __device__ void control_step(const DeviceProblem &P) {
   if (c->outer_iter == 0 && c->qmax == 0) c->chi2_initial = currentChi;
   const bool fail = c->chol_fail != 0;
   if (fail) { tempChi = DBL_MAX; c->cholesky_failures++; }
-  double scale = P.scal[2] + c->scale_pose;
+  c->chol_fail = 0;  // k_tree_solve only ever raises it
+  double scale_pose = 0.0;
+  for (int i = 0; i < kTreeMaxCluster; ++i) scale_pose += c->scale_pose_part[i];  // CTA order: deterministic
+  double scale = P.scal[2] + scale_pose;
   scale += 1e-3;
   double rho = (currentChi - tempChi) / scale;
   if (fail) rho = -1.0;  // a failed factorisation always rejects the step (levenberg.cpp:120-121)
@@ -1746,6 +1749,7 @@ int max_solver_cluster() {
 }
 
 void launch_reduced_solve(const DeviceProblem &P, cudaStream_t st) {
+  if (P.tree.C > 0) { launch_tree_solve(P, st); return; }
   static std::atomic<unsigned long long> seen{0};
   if (first_launch_on_this_device(seen)) {
     cudaFuncSetAttribute(k_reduced_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveMaxDynSmem);

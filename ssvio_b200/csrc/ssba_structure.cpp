@@ -50,7 +50,7 @@ struct Factor {
 };
 
 bool symbolic_factor(int n, const std::vector<std::vector<int>> &adj, const std::vector<int> &perm,
-                     Factor &f, std::string &err) {
+                     Factor &f, std::string &err, bool want_tasks = true) {
   std::vector<int> iperm(n);
   for (int q = 0; q < n; ++q) iperm[perm[q]] = q;
   std::vector<std::vector<int>> Acol(n);  // permuted strictly-lower pattern of S
@@ -132,6 +132,7 @@ bool symbolic_factor(int n, const std::vector<std::vector<int>> &adj, const std:
       }
     f.n_levels = (int)f.level_ptr.size() - 1;
   }
+  if (!want_tasks) return true;  // the subtree-per-CTA program (ssba_tree_program.cpp) plans its own work items
   // Work items of the device solver, level by level.  Every block of a column of the level is
   // one item:  L(i,j) <- (A(i,j) - sum_k L(i,k) L(j,k)^T) * L(j,j)^-T, the diagonal items of
   // all columns first (the others wait for the inverse diagonal block they produce), then one
@@ -586,6 +587,76 @@ void nested_dissection_order(int n, const std::vector<std::vector<int>> &adj_low
   rec(all);
 }
 
+// Elimination order, symbolic factorisation and solver program(s) of a block-sparse SPD system over n
+// 6x6 block columns (adj[c] = rows r > c with a block (r, c)), shared by the bundle adjustment (the
+// Schur complement) and the pose graph (H itself): natural order vs nested dissection, then the
+// subtree-per-CTA re-order and program (k_tree_solve).  The level program of k_reduced_solve is only
+// built when the tree program does not fit (or SSBA_SOLVER=level asks for it).
+bool plan_reduced_solver(int n, const std::vector<std::vector<int>> &adj, Structure &s, std::vector<int> &perm_out,
+                         std::string &err) {
+  static const bool force_level = [] { const char *e = std::getenv("SSBA_SOLVER"); return e && std::string(e) == "level"; }();
+  std::vector<int> perm_nat(n), perm_nd, perm_tree;
+  std::iota(perm_nat.begin(), perm_nat.end(), 0);
+  Factor f_nat, f_nd, f_tree;
+  Factor *best = nullptr;
+  std::vector<int> *best_perm = &perm_nat;
+  bool have_tasks = false;
+  if (n >= 24) {
+    nested_dissection_order(n, adj, perm_nd);
+    if (perm_nd != perm_nat) {
+      if (!symbolic_factor(n, adj, perm_nd, f_nd, err, false)) return false;
+      best = &f_nd; best_perm = &perm_nd;
+    }
+  }
+  // the natural order is only worth a symbolic factorisation of its own when nested dissection
+  // did not flatten the elimination tree (it always does for the block-banded windows)
+  if (!best || 2 * f_nd.n_levels > n) {
+    if (!symbolic_factor(n, adj, perm_nat, f_nat, err, true)) return false;
+    if (best && !symbolic_factor(n, adj, perm_nd, f_nd, err, true)) return false;
+    if (!best || f_nat.est_cycles <= f_nd.est_cycles) { best = &f_nat; best_perm = &perm_nat; }
+    have_tasks = true;
+  }
+  // subtree-per-CTA solver: columns of a CTA contiguous (a topological re-order of the same elimination
+  // tree: same fill), then the program
+  s.tree = TreeProgram{};
+  if (!force_level && n > 0) {
+    // candidates: the cluster size the problem asks for; a system whose factor does not fit the shared memory
+    // of 8 SMs gets the 16-CTA cluster (when the device has it), if need be with CTA 0 taking the top part only
+    struct Cand { int C; bool cta0_subtree; };
+    std::vector<Cand> cands = {{std::min(solver_cluster_size(n), tree_cluster_cap()), true}};
+    if (n >= 64 && tree_cluster_cap() >= 16) { cands.push_back({16, true}); cands.push_back({16, false}); }
+    else if (n >= 64) cands.push_back({tree_cluster_cap(), false});
+    for (const Cand &cd : cands) {
+      TreeAssign ta;
+      tree_assign(n, best->col_ptr, best->blk_row, cd.C, cd.cta0_subtree, ta);
+      perm_tree.resize(n);
+      for (int q = 0; q < n; ++q) perm_tree[q] = (*best_perm)[ta.order[q]];
+      f_tree = Factor{};
+      if (!symbolic_factor(n, adj, perm_tree, f_tree, err, false)) return false;
+      if (f_tree.n_blocks != best->n_blocks) { err = "internal: re-ordered factor has different fill"; return false; }
+      build_tree_program(n, f_tree.col_ptr, f_tree.blk_row, f_tree.row_ptr, f_tree.row_blk, f_tree.row_col, ta, s.tree);
+      if (s.tree.ok) break;
+    }
+    if (s.tree.ok) { best = &f_tree; best_perm = &perm_tree; have_tasks = false; }
+  }
+  const bool need_level_program = !s.tree.ok;
+  if (need_level_program && !have_tasks) {
+    const std::vector<int> p = *best_perm;
+    if (!symbolic_factor(n, adj, p, *best, err, true)) return false;
+  }
+  perm_out = *best_perm;
+  s.n_schur_blocks = best->n_schur;
+  s.n_blocks = best->n_blocks; s.n_levels = best->n_levels; s.n_tasks = (int)best->task_dst.size();
+  s.est_solver_cycles = best->est_cycles;
+  s.col_ptr.swap(best->col_ptr); s.blk_row.swap(best->blk_row); s.blk_col.swap(best->blk_col);
+  s.row_ptr.swap(best->row_ptr); s.row_blk.swap(best->row_blk); s.row_col.swap(best->row_col);
+  s.level_ptr.swap(best->level_ptr); s.level_col.swap(best->level_col);
+  s.ltask_ptr.swap(best->ltask_ptr); s.task_dst.swap(best->task_dst); s.task_pos.swap(best->task_pos); s.task_pair_ptr.swap(best->task_pair_ptr);
+  s.pair_a.swap(best->pair_a); s.pair_b.swap(best->pair_b);
+  if (s.tree.ok) s.solve_cluster = s.tree.C;
+  return true;
+}
+
 }  // namespace
 
 static std::atomic<int> g_ranks_on_host{1};
@@ -855,39 +926,13 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   }
 
   tm.mark("co-visibility");
-  // ---- elimination order and symbolic factorisation over q: natural order vs nested
-  // dissection, whichever the cost model of the level-scheduled device solver prefers
+  // ---- elimination order, symbolic factorisation and the solver program over q
   {
-    std::vector<int> perm_nat(n), perm_nd;
-    std::iota(perm_nat.begin(), perm_nat.end(), 0);
-    Factor f_nat, f_nd;
-    Factor *best = nullptr;
-    std::vector<int> *best_perm = &perm_nat;
-    if (n >= 24) {
-      nested_dissection_order(n, adj, perm_nd);
-      if (perm_nd != perm_nat) {
-        if (!symbolic_factor(n, adj, perm_nd, f_nd, err)) return false;
-        best = &f_nd; best_perm = &perm_nd;
-      }
-    }
-    // the natural order is only worth a symbolic factorisation of its own when nested dissection
-    // did not flatten the elimination tree (it always does for the block-banded windows)
-    if (!best || 2 * f_nd.n_levels > n) {
-      if (!symbolic_factor(n, adj, perm_nat, f_nat, err)) return false;
-      if (!best || f_nat.est_cycles <= f_nd.est_cycles) { best = &f_nat; best_perm = &perm_nat; }
-    }
-    const std::vector<int> &perm = *best_perm;  // q -> free pose index
+    std::vector<int> perm;  // q -> free pose index
+    if (!plan_reduced_solver(n, adj, s, perm, err)) return false;
     s.q_of_pose.assign(NK, -1);
     s.pose_of_q.resize(n);
     for (int q = 0; q < n; ++q) { s.q_of_pose[free_pose_rows[perm[q]]] = q; s.pose_of_q[q] = free_pose_rows[perm[q]]; }
-    s.n_schur_blocks = best->n_schur;
-    s.n_blocks = best->n_blocks; s.n_levels = best->n_levels; s.n_tasks = (int)best->task_dst.size();
-    s.est_solver_cycles = best->est_cycles;
-    s.col_ptr.swap(best->col_ptr); s.blk_row.swap(best->blk_row); s.blk_col.swap(best->blk_col);
-    s.row_ptr.swap(best->row_ptr); s.row_blk.swap(best->row_blk); s.row_col.swap(best->row_col);
-    s.level_ptr.swap(best->level_ptr); s.level_col.swap(best->level_col);
-    s.ltask_ptr.swap(best->ltask_ptr); s.task_dst.swap(best->task_dst); s.task_pos.swap(best->task_pos); s.task_pair_ptr.swap(best->task_pair_ptr);
-    s.pair_a.swap(best->pair_a); s.pair_b.swap(best->pair_b);
   }
   auto find_block = [&](int row, int col) -> int {  // row >= col
     const int *b0 = s.blk_row.data() + s.col_ptr[col], *b1 = s.blk_row.data() + s.col_ptr[col + 1];
@@ -1075,7 +1120,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   // The solver program (serial, the longest single piece of host work left) is built on a thread
   // of its own while this one goes on with the chunk / unit / partial lists: it reads the factor
   // structure only and writes prog / prog_ptr / solver_* only.
-  std::thread program_thread([&s] { build_solver_program(s); });
+  std::thread program_thread([&s] { if (!s.tree.ok) build_solver_program(s); });
   struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{program_thread};
   // ---- CTAs of the per-pair kernels: runs of whole landmarks with <= kLinPairs pairs
   {
@@ -1204,33 +1249,9 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
 bool build_solver_structure(int n, const std::vector<std::vector<int>> &adj, Structure &s, std::vector<int> &perm_out,
                             std::string &err) {
   reset_keep_capacity(s);
-  std::vector<int> perm_nat(n), perm_nd;
-  std::iota(perm_nat.begin(), perm_nat.end(), 0);
-  Factor f_nat, f_nd;
-  Factor *best = nullptr;
-  std::vector<int> *best_perm = &perm_nat;
-  if (n >= 24) {
-    nested_dissection_order(n, adj, perm_nd);
-    if (perm_nd != perm_nat) {
-      if (!symbolic_factor(n, adj, perm_nd, f_nd, err)) return false;
-      best = &f_nd; best_perm = &perm_nd;
-    }
-  }
-  if (!best || 2 * f_nd.n_levels > n) {
-    if (!symbolic_factor(n, adj, perm_nat, f_nat, err)) return false;
-    if (!best || f_nat.est_cycles <= f_nd.est_cycles) { best = &f_nat; best_perm = &perm_nat; }
-  }
-  perm_out = *best_perm;
   s.n_fp = n;
-  s.n_schur_blocks = best->n_schur;
-  s.n_blocks = best->n_blocks; s.n_levels = best->n_levels; s.n_tasks = (int)best->task_dst.size();
-  s.est_solver_cycles = best->est_cycles;
-  s.col_ptr.swap(best->col_ptr); s.blk_row.swap(best->blk_row); s.blk_col.swap(best->blk_col);
-  s.row_ptr.swap(best->row_ptr); s.row_blk.swap(best->row_blk); s.row_col.swap(best->row_col);
-  s.level_ptr.swap(best->level_ptr); s.level_col.swap(best->level_col);
-  s.ltask_ptr.swap(best->ltask_ptr); s.task_dst.swap(best->task_dst); s.task_pos.swap(best->task_pos); s.task_pair_ptr.swap(best->task_pair_ptr);
-  s.pair_a.swap(best->pair_a); s.pair_b.swap(best->pair_b);
-  build_solver_program(s);
+  if (!plan_reduced_solver(n, adj, s, perm_out, err)) return false;
+  if (!s.tree.ok) build_solver_program(s);
   return true;
 }
 

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "ssba_geometry.cuh"
+#include "ssba_tree_program.hpp"
 
 namespace ssba {
 
@@ -115,6 +116,8 @@ struct Structure {
   int n_levels = 0;
   // original-order map for error read-back
   int n_edges_total = 0;
+  // the subtree-per-CTA solver program (k_tree_solve); when !tree.ok the level program above is used
+  TreeProgram tree;
 };
 
 // Builds the structure for `rank` of `world`. Returns false and sets err on invalid input.

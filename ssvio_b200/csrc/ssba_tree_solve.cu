@@ -1,0 +1,461 @@
+// ssba_tree_solve.cu — k_tree_solve: the reduced pose system S x_p = bschur on a thread-block cluster,
+// one set of elimination subtrees per CTA, entirely out of shared memory (program: ssba_tree_program.hpp).
+// Replaces LinearSolverCSparse::solve (g2o/solvers/csparse/linear_solver_csparse.h:106-142) +
+// cs_chol_workspace / cs_lsolve / cs_ltsolve (g2o/solvers/csparse/csparse_extension.cpp:35-122), incl.
+// "pivot <= 0 => the trial is rejected" (:115), and applies the pose part of SparseOptimizer::update
+// (g2o/core/sparse_optimizer.cpp:433-446) and of computeScale (optimization_algorithm_levenberg.cpp:168-175).
+//
+// Data movement: the CTA's slice of the reduced system (its factor blocks, right-hand sides, b_p) and its
+// whole program arrive with four bulk asynchronous copies (TMA, cp.async.bulk) on one mbarrier; from then
+// on every operand is a shared-memory load.  Two cluster barriers per solve (contributions up, top solution
+// down); two __syncthreads per elimination step.
+#include <atomic>
+
+#include "ssba_device.hpp"
+
+namespace ssba {
+
+namespace {
+
+__device__ __forceinline__ unsigned ts_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ts_mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ts_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ts_mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ts_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ts_mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(ts_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void ts_bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ts_smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(ts_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ unsigned ts_cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void ts_cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// lanes r + 6 g, g = 0..4 (lanes 30, 31 carry zeros): ((g0 + g3) + (g1 + g4)) + g2 -> lanes 0..5
+__device__ __forceinline__ double ts_group_reduce(double v, int lane) {
+  double t = __shfl_down_sync(0xffffffffu, v, 18);
+  if (lane < 12) v += t;
+  t = __shfl_down_sync(0xffffffffu, v, 6);
+  const double u = __shfl_down_sync(0xffffffffu, v, 12);
+  if (lane < 6) v = (v + t) + u;
+  return v;
+}
+
+// row r of  dest -= sum over the item's pairs of A B^T  (A: the item's rows, 6 doubles each; B: a 6x6 block)
+__device__ __forceinline__ void ts_product_rows(double *pool, const int *prog, int w0, int p0, int r) {
+  const int np = (int)((unsigned)w0 >> 20);
+  double acc[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) acc[c] = 0.0;
+  for (int p = p0; p < p0 + np; ++p) {
+    const unsigned pw = (unsigned)prog[p];
+    const double2 *A2 = reinterpret_cast<const double2 *>(pool + (pw & 0xffffu) + 6 * r);
+    const double2 *B2 = reinterpret_cast<const double2 *>(pool + (pw >> 16));
+    const double2 a0 = A2[0], a1 = A2[1], a2 = A2[2];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const double2 b0 = B2[3 * c], b1 = B2[3 * c + 1], b2 = B2[3 * c + 2];
+      acc[c] += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y;
+    }
+  }
+  if (np > 0) {
+    double2 *D = reinterpret_cast<double2 *>(pool + (w0 & 0xffff) + 6 * r);
+    double2 d0 = D[0], d1 = D[1], d2 = D[2];
+    d0.x -= acc[0]; d0.y -= acc[1]; d1.x -= acc[2]; d1.y -= acc[3]; d2.x -= acc[4]; d2.y -= acc[5];
+    D[0] = d0; D[1] = d1; D[2] = d2;
+  }
+}
+
+// in-place Cholesky of the lower triangle of a 6x6 block by one lane: L below the diagonal, 1 / l_cc ON the
+// diagonal; a pivot <= 0 (or NaN) is reported like csparse_extension.cpp:115 and replaced so that the
+// arithmetic stays finite
+__device__ __forceinline__ bool ts_cholesky6(double *D) {
+  double a[36];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int k = 0; k <= i; ++k) a[6 * i + k] = D[6 * i + k];
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double dj = a[7 * j];
+    if (!(dj > 0.0)) { bad = true; dj = 1.0; }
+    const double inv = rsqrt(dj);
+    a[7 * j] = inv;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) a[6 * i + j] *= inv;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i)
+#pragma unroll
+      for (int k = j + 1; k <= i; ++k) a[6 * i + k] -= a[6 * i + j] * a[6 * k + j];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int k = 0; k <= i; ++k) D[6 * i + k] = a[6 * i + k];
+  return bad;
+}
+
+template <int NT>
+__device__ __forceinline__ double ts_block_sum(double v, double *sm /* NT / 32 */) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) r += sm[w];
+  }
+  __syncthreads();
+  return r;  // valid on thread 0
+}
+
+template <bool kCluster>
+__global__ void __launch_bounds__(kTreeThreads, 1) k_tree_solve(const DeviceProblem P) {
+  Control *ctl = P.ctl;
+  if (ctl->done) return;  // uniform over the cluster
+  const TreeDev &T = P.tree;
+  const int cta = kCluster ? (int)ts_cluster_ctarank() : 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane / 6, r = lane - 6 * g;  // lanes 30, 31: g == 5, never active
+  extern __shared__ __align__(128) unsigned char ts_smem[];
+  const int np = T.pool_doubles[cta];
+  const int nwords = T.prog_ptr[cta + 1] - T.prog_ptr[cta];
+  double *pool = reinterpret_cast<double *>(ts_smem);
+  int *prog = reinterpret_cast<int *>(ts_smem + 8 * (size_t)((np + 1) & ~1));
+  unsigned char *misc = reinterpret_cast<unsigned char *>(prog + nwords);  // nwords is a multiple of 4
+  unsigned long long *bar = reinterpret_cast<unsigned long long *>(misc);
+  int *s_ctr = reinterpret_cast<int *>(misc + 8);
+  int *s_fail = reinterpret_cast<int *>(misc + 12);
+  double *red = reinterpret_cast<double *>(misc + 16);  // kTreeWarps doubles
+  const int nblk = T.n_own_blocks[cta], ncols = T.n_own_cols[cta], q0 = T.q0[cta];
+  const int V0 = 36 * nblk, BP0 = V0 + 6 * ncols;
+  const double *bs = P.sys + 36 * (size_t)P.n_blocks;
+
+  if (tid == 0) {
+    ts_mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    *s_ctr = 0; *s_fail = 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned bytes_blk = 288u * (unsigned)nblk, bytes_vec = 48u * (unsigned)ncols, bytes_prog = 4u * (unsigned)nwords;
+    ts_mbar_arrive_expect_tx(bar, bytes_blk + 2u * bytes_vec + bytes_prog);
+    if (bytes_prog) ts_bulk_g2s(prog, T.prog + T.prog_ptr[cta], bytes_prog, bar);
+    if (bytes_blk) ts_bulk_g2s(pool, P.sys + 36 * (size_t)T.b0[cta], bytes_blk, bar);
+    if (bytes_vec) {
+      ts_bulk_g2s(pool + V0, bs + 6 * (size_t)q0, bytes_vec, bar);                  // bschur
+      ts_bulk_g2s(pool + BP0, bs + 6 * (size_t)(P.n_fp + q0), bytes_vec, bar);      // b_p (computeScale)
+    }
+  }
+  {  // contribution slots start at zero
+    const int coff = T.contrib_off[cta], cn = T.contrib_doubles[cta];
+    for (int i = tid; i < cn; i += kTreeThreads) pool[coff + i] = 0.0;
+  }
+  // this thread's pose for the epilogue (one column per thread; its latency hides behind the solve)
+  const int cur = ctl->cur;
+  const double lambda = ctl->lambda;
+  int kv0 = 0;
+  double T0[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) T0[i] = 0.0;
+  if (tid < ncols) {
+    kv0 = P.pose_of_q[q0 + tid];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) T0[i] = P.pose[cur][7 * kv0 + i];
+  }
+  ts_mbar_wait(bar, 0);
+  __syncthreads();
+
+  const int *steps = prog + prog[kTH_OffSteps];
+  const int nsa = prog[kTH_StepsA], nsb = prog[kTH_StepsB];
+
+  // ---- numeric factorisation + forward substitution of the steps [s0, s1)
+  auto forward = [&](int s0, int s1) {
+    for (int s = s0; s < s1; ++s) {
+      const int *st = steps + kTS_Words * s;
+      const int nc = st[kTS_Cols];
+      // interval 1: the diagonal blocks of this step (the products they still wait for, then the
+      // 6x6 Cholesky in one lane per column) beside the look-ahead products of the previous step's columns
+      if (5 * warp < nc) {
+        const int ci = 5 * warp + g;
+        const bool act = g < 5 && ci < nc;
+        int2 it = make_int2(0, 0);
+        if (act) {
+          it = *reinterpret_cast<const int2 *>(prog + st[kTS_OffDiag] + kTreeItemWords * ci);
+          ts_product_rows(pool, prog, it.x, it.y, r);
+        }
+        __syncwarp();
+        if (act && r == 0) {
+          if (ts_cholesky6(pool + (it.x & 0xffff))) { *s_fail = 1; ctl->chol_fail = 1; }
+        }
+      }
+      const int n_look = st[kTS_NLook];
+      if (n_look > 0) {
+        const int *rounds = prog + st[kTS_OffLook];
+        for (;;) {
+          int rd = 0;
+          if (lane == 0) rd = atomicAdd(s_ctr, 1);
+          rd = __shfl_sync(0xffffffffu, rd, 0);
+          if (rd >= n_look) break;
+          if (g < 5) {
+            const int2 it = *reinterpret_cast<const int2 *>(rounds + kTreeRoundWords * rd + kTreeItemWords * g);
+            if (r < ((it.x >> 16) & 15)) ts_product_rows(pool, prog, it.x, it.y, r);
+          }
+        }
+      }
+      __syncthreads();
+      // interval 2: X = B L_jj^-T row by row for every sub-diagonal block of the step's columns, y_j likewise
+      if (tid == 0) *s_ctr = 0;
+      {
+        const int n_panel = st[kTS_NPanel];
+        const int *rounds = prog + st[kTS_OffPanel];
+        for (int rd = warp; rd < n_panel; rd += kTreeWarps) {
+          if (g >= 5) continue;
+          const int2 it = *reinterpret_cast<const int2 *>(rounds + kTreeRoundWords * rd + kTreeItemWords * g);
+          if (r >= ((it.x >> 16) & 15)) continue;
+          double2 *D = reinterpret_cast<double2 *>(pool + (it.x & 0xffff) + 6 * r);
+          const double2 *L2 = reinterpret_cast<const double2 *>(pool + it.y);
+          const double2 v0 = D[0], v1 = D[1], v2 = D[2];
+          const double v[6] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
+          double x[6];
+#pragma unroll
+          for (int m = 0; m < 6; ++m) {
+            const double2 l0 = L2[3 * m], l1 = L2[3 * m + 1], l2 = L2[3 * m + 2];
+            const double l[6] = {l0.x, l0.y, l1.x, l1.y, l2.x, l2.y};
+            double t = v[m];
+#pragma unroll
+            for (int k = 0; k < m; ++k) t -= x[k] * l[k];
+            x[m] = t * l[m];
+          }
+          D[0] = make_double2(x[0], x[1]); D[1] = make_double2(x[2], x[3]); D[2] = make_double2(x[4], x[5]);
+        }
+      }
+      __syncthreads();
+    }
+  };
+
+  // ---- backward substitution of the steps [s0, s1), last first: one warp per column
+  auto backward = [&](int s0, int s1) {
+    for (int s = s1 - 1; s >= s0; --s) {
+      const int *st = steps + kTS_Words * s;
+      const int nc = st[kTS_Cols];
+      for (int t = warp; t < nc; t += kTreeWarps) {
+        const int4 rec = *reinterpret_cast<const int4 *>(prog + st[kTS_OffBwd] + 4 * t);
+        const int dg = rec.x, vo = rec.y, nb = rec.z;
+        const int *rows = prog + rec.w;
+        double acc = 0.0;
+        if (g < 5) {
+          for (int k = g; k < nb; k += 5) {
+            const double *B = pool + dg + 36 * (1 + k);
+            const double2 *x2 = reinterpret_cast<const double2 *>(pool + rows[k]);
+            const double2 x0 = x2[0], x1 = x2[1], xx2 = x2[2];
+            acc += B[r] * x0.x + B[6 + r] * x0.y + B[12 + r] * x1.x + B[18 + r] * x1.y + B[24 + r] * xx2.x + B[30 + r] * xx2.y;
+          }
+        }
+        acc = ts_group_reduce(acc, lane);  // totals on lanes 0..5
+        const double sv = lane < 6 ? pool[vo + r] - acc : 0.0;
+        double sc[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) sc[c] = __shfl_sync(0xffffffffu, sv, c);
+        if (lane == 0) {
+          const double *L = pool + dg;
+          double x[6];
+#pragma unroll
+          for (int m = 5; m >= 0; --m) {
+            double t2 = sc[m];
+#pragma unroll
+            for (int k = m + 1; k < 6; ++k) t2 -= L[6 * k + m] * x[k];
+            x[m] = t2 * L[7 * m];
+          }
+          double2 *o = reinterpret_cast<double2 *>(pool + vo);
+          o[0] = make_double2(x[0], x[1]); o[1] = make_double2(x[2], x[3]); o[2] = make_double2(x[4], x[5]);
+        }
+      }
+      __syncthreads();
+    }
+  };
+
+  forward(0, nsa);
+  if (kCluster) {
+    // ---- contributions of the subtrees to the top part: up through global memory (L2), added by CTA 0 in
+    // CTA order (round r = every destination's r-th contribution: the destinations of a round are distinct)
+    if (cta != 0) {
+      const double2 *src = reinterpret_cast<const double2 *>(pool + T.contrib_off[cta]);
+      double2 *dst = reinterpret_cast<double2 *>(T.xchg + T.xchg_off[cta]);
+      const int n2 = T.contrib_doubles[cta] / 2;
+      for (int i = tid; i < n2; i += kTreeThreads) dst[i] = src[i];
+    }
+    ts_cluster_barrier();
+    if (cta == 0) {
+      const int n_rounds = prog[kTH_AddRounds];
+      const int *tab = prog + prog[kTH_OffAddRounds];
+      const int grp = tid / 18, sub = tid - 18 * grp;  // 28 groups of 18 lanes: one 16-byte piece of a block each
+      const double2 *x2 = reinterpret_cast<const double2 *>(T.xchg);
+      for (int rd = 0; rd < n_rounds; ++rd) {
+        const int nops = tab[2 * rd];
+        const int *ops = prog + tab[2 * rd + 1];
+        for (int base = 0; base < nops; base += 28 * 4) {
+          double2 v[4];
+          int dst[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int op = base + 28 * u + grp;
+            dst[u] = -1;
+            if (grp < 28 && op < nops) {
+              const unsigned wd = (unsigned)ops[op];
+              if (sub < ((wd >> 31) ? 3 : 18)) {
+                dst[u] = (int)(wd & 0xffffu) + 2 * sub;
+                v[u] = __ldcg(x2 + ((wd >> 16) & 0x7fffu) + sub);
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (dst[u] >= 0) {
+              double2 *d = reinterpret_cast<double2 *>(pool + dst[u]);
+              double2 t = *d;
+              t.x += v[u].x; t.y += v[u].y;
+              *d = t;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+  if (cta == 0 && nsb > 0) {
+    forward(nsa, nsa + nsb);
+    backward(nsa, nsa + nsb);
+  }
+  if (kCluster) {
+    // ---- the top solution goes down through global memory
+    if (cta == 0) {
+      const int t0 = prog[kTH_TopCol0];
+      for (int i = tid + 6 * t0; i < 6 * ncols; i += kTreeThreads) P.xp[6 * (size_t)q0 + i] = pool[V0 + i];
+    }
+    ts_cluster_barrier();
+    if (cta != 0) {
+      const int nx = prog[kTH_NXload];
+      const int *xl = prog + prog[kTH_OffXload];
+      for (int i = tid; i < 6 * nx; i += kTreeThreads) {
+        const unsigned wd = (unsigned)xl[i / 6];
+        const int m = i - 6 * (i / 6);
+        pool[(wd & 0xffffu) + m] = __ldcg(P.xp + 6 * (size_t)(wd >> 16) + m);
+      }
+    }
+    __syncthreads();
+  }
+  backward(0, nsa);
+
+  // ---- epilogue: x_p, the pose part of computeScale and of update(): T <- exp(x) T into the trial buffer
+  bool fail;
+  if (kCluster) fail = __ldcg(reinterpret_cast<const int *>(&ctl->chol_fail)) != 0;  // raised before the barriers above
+  else fail = *s_fail != 0;
+  double sc = 0.0;
+  for (int t = tid; t < ncols; t += kTreeThreads) {
+    int kv = kv0;
+    double Tc[7], d[6], out[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) Tc[i] = T0[i];
+    if (t != tid) {
+      kv = P.pose_of_q[q0 + t];
+#pragma unroll
+      for (int i = 0; i < 7; ++i) Tc[i] = P.pose[cur][7 * kv + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      d[i] = fail ? 0.0 : pool[V0 + 6 * t + i];
+      P.xp[6 * (size_t)(q0 + t) + i] = d[i];
+      sc += d[i] * (lambda * d[i] + pool[BP0 + 6 * t + i]);
+    }
+    pose_oplus(Tc, d, out);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) P.pose[cur ^ 1][7 * kv + i] = fail ? Tc[i] : out[i];
+  }
+  sc = ts_block_sum<kTreeThreads>(sc, red);
+  if (tid == 0) ctl->scale_pose_part[cta] = sc;
+}
+
+}  // namespace
+
+void fill_tree_dev(const TreeProgram &tp, const int32_t *d_prog, double *d_xchg, TreeDev &out) {
+  out = TreeDev{};
+  if (!tp.ok) return;
+  out.C = tp.C;
+  out.smem_bytes = (unsigned)tp.smem_bytes;
+  out.prog = d_prog;
+  out.xchg = d_xchg;
+  for (int c = 0; c <= kTreeMaxCluster; ++c) out.prog_ptr[c] = tp.prog_ptr[c];
+  for (int c = 0; c < kTreeMaxCluster; ++c) {
+    out.pool_doubles[c] = tp.pool_doubles[c]; out.b0[c] = tp.b0[c]; out.n_own_blocks[c] = tp.n_own_blocks[c];
+    out.q0[c] = tp.q0[c]; out.n_own_cols[c] = tp.n_own_cols[c]; out.contrib_off[c] = tp.contrib_off[c];
+    out.contrib_doubles[c] = tp.contrib_doubles[c]; out.xchg_off[c] = tp.xchg_off[c];
+  }
+}
+
+namespace {
+// function attributes are per device; one mutex keeps the set-up and the first launches of other threads apart
+void tree_setup_device() {
+  static std::atomic<unsigned long long> done{0};
+  static std::atomic_flag lock = ATOMIC_FLAG_INIT;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return;
+  while (lock.test_and_set(std::memory_order_acquire)) { }
+  if (!(done.load(std::memory_order_acquire) & bit)) {
+    cudaFuncSetAttribute(k_tree_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTreeMaxSmem);
+    cudaFuncSetAttribute(k_tree_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTreeMaxSmem);
+    cudaFuncSetAttribute(k_tree_solve<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaGetLastError();
+    done.fetch_or(bit, std::memory_order_release);
+  }
+  lock.clear(std::memory_order_release);
+}
+}  // namespace
+
+// The largest cluster (16, 8, 4, 2 or 1 CTAs with the full dynamic shared memory) the device can co-schedule
+int max_tree_cluster() {
+  tree_setup_device();
+  for (int c = kTreeMaxCluster; c >= 2; c /= 2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(c); cfg.blockDim = dim3(kTreeThreads); cfg.dynamicSmemBytes = kTreeMaxSmem;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = c; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k_tree_solve<true>, &cfg) == cudaSuccess && n >= 1) return c;
+    cudaGetLastError();
+  }
+  return 1;
+}
+
+void launch_tree_solve(const DeviceProblem &P, cudaStream_t st) {
+  tree_setup_device();
+  const int c = P.tree.C;
+  if (c == 1) { k_tree_solve<false><<<1, kTreeThreads, P.tree.smem_bytes, st>>>(P); return; }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(c); cfg.blockDim = dim3(kTreeThreads); cfg.dynamicSmemBytes = P.tree.smem_bytes; cfg.stream = st;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = c; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, k_tree_solve<true>, P);
+}
+
+}  // namespace ssba

@@ -160,6 +160,166 @@ static std::vector<double> interpret_program(const Structure &s, std::vector<dou
   return x;
 }
 
+// ---- CPU interpreter of the subtree-per-CTA program (Structure::tree, ssba_tree_program.cpp), i.e. of what
+// k_tree_solve walks: per CTA its shared-memory pool (own factor blocks, vectors, contribution slots), per step
+// the diagonal items (critical products + 6x6 Cholesky), the look-ahead product rounds that run beside them,
+// the panel rounds; the contribution hand-off to CTA 0 (add rounds), the top part, the backward passes and the
+// hand-off of the top solution.  Every pool double remembers who wrote / read it in the running barrier
+// interval: two different work items touching the same double in one interval (one of them writing) is a race
+// on the device and fails here.
+struct TreeCta {
+  std::vector<double> pool;
+  std::vector<int> wr_t, wr_i, rd_t, rd_i;
+  const int32_t *w;
+  int T = 0, item = 0;
+  double rd(int off) {
+    if (wr_t[off] == T && wr_i[off] != item) { CHECK(false, "tree program: read of a double written by another item in the same interval (off %d)", off); }
+    if (rd_t[off] == T && rd_i[off] != item) rd_i[off] = -2; else { rd_t[off] = T; rd_i[off] = item; }
+    return pool[off];
+  }
+  void wrt(int off, double v) {
+    if (rd_t[off] == T && rd_i[off] != item) { CHECK(false, "tree program: write of a double read by another item in the same interval (off %d)", off); }
+    if (wr_t[off] == T && wr_i[off] != item) { CHECK(false, "tree program: two items write the same double in one interval (off %d)", off); }
+    wr_t[off] = T; wr_i[off] = item;
+    pool[off] = v;
+  }
+};
+static void tree_products(TreeCta &c, int dest, int nrows, int p0, int p1) {
+  for (int r = 0; r < nrows; ++r) {
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int p = p0; p < p1; ++p) {
+      const unsigned wd = (unsigned)c.w[p];
+      const int a = (int)(wd & 0xffff) + 6 * r, b = (int)(wd >> 16);
+      for (int m = 0; m < 6; ++m) { double t = 0; for (int k = 0; k < 6; ++k) t += c.rd(a + k) * c.rd(b + 6 * m + k); acc[m] += t; }
+    }
+    if (p1 > p0) for (int m = 0; m < 6; ++m) c.wrt(dest + 6 * r + m, c.rd(dest + 6 * r + m) - acc[m]);
+  }
+}
+static void tree_forward_steps(TreeCta &c, int s0, int s1, bool *fail) {
+  const int32_t *w = c.w;
+  for (int s = s0; s < s1; ++s) {
+    const int32_t *st = w + w[kTH_OffSteps] + kTS_Words * s;
+    ++c.T;  // interval 1: diagonal items and look-ahead rounds
+    for (int t = 0; t < st[kTS_Cols]; ++t) {
+      ++c.item;
+      const int32_t *it = w + st[kTS_OffDiag] + kTreeItemWords * t;
+      const int d = it[0] & 0xffff;
+      CHECK(((it[0] >> 16) & 15) == 6, "diagonal item rows");
+      tree_products(c, d, 6, it[1], it[1] + (int)((unsigned)it[0] >> 20));
+      double a[36];
+      for (int i = 0; i < 6; ++i) for (int k = 0; k <= i; ++k) a[6 * i + k] = c.rd(d + 6 * i + k);
+      for (int j = 0; j < 6; ++j) {
+        if (!(a[7 * j] > 0)) { *fail = true; a[7 * j] = 1.0; }
+        const double inv = 1.0 / std::sqrt(a[7 * j]);
+        a[7 * j] = inv;
+        for (int i = j + 1; i < 6; ++i) a[6 * i + j] *= inv;
+        for (int i = j + 1; i < 6; ++i) for (int k = j + 1; k <= i; ++k) a[6 * i + k] -= a[6 * i + j] * a[6 * k + j];
+      }
+      for (int i = 0; i < 6; ++i) for (int k = 0; k <= i; ++k) c.wrt(d + 6 * i + k, a[6 * i + k]);  // L below, 1 / l_cc on the diagonal
+    }
+    for (int i = 0; i < 5 * st[kTS_NLook]; ++i) {
+      ++c.item;
+      const int32_t *it = w + st[kTS_OffLook] + kTreeItemWords * i;
+      const int nrows = (it[0] >> 16) & 15;
+      if (nrows > 0) tree_products(c, it[0] & 0xffff, nrows, it[1], it[1] + (int)((unsigned)it[0] >> 20));
+    }
+    ++c.T;  // interval 2: panel rounds
+    for (int i = 0; i < 5 * st[kTS_NPanel]; ++i) {
+      ++c.item;
+      const int32_t *it = w + st[kTS_OffPanel] + kTreeItemWords * i;
+      const int dest = it[0] & 0xffff, nrows = (it[0] >> 16) & 15, dg = it[1];
+      for (int r = 0; r < nrows; ++r) {
+        double x[6];
+        for (int m = 0; m < 6; ++m) {
+          double v = c.rd(dest + 6 * r + m);
+          for (int k = 0; k < m; ++k) v -= x[k] * c.rd(dg + 6 * m + k);
+          x[m] = v * c.rd(dg + 7 * m);
+        }
+        for (int m = 0; m < 6; ++m) c.wrt(dest + 6 * r + m, x[m]);
+      }
+    }
+  }
+}
+static void tree_backward_steps(TreeCta &c, int s0, int s1) {
+  const int32_t *w = c.w;
+  for (int s = s1 - 1; s >= s0; --s) {
+    const int32_t *st = w + w[kTH_OffSteps] + kTS_Words * s;
+    ++c.T;
+    for (int t = 0; t < st[kTS_Cols]; ++t) {
+      ++c.item;
+      const int32_t *rec = w + st[kTS_OffBwd] + 4 * t;
+      const int dg = rec[0], v = rec[1], nb = rec[2];
+      const int32_t *rows = w + rec[3];
+      double sv[6], x[6];
+      for (int m = 0; m < 6; ++m) sv[m] = c.rd(v + m);
+      for (int k = 0; k < nb; ++k) { const int B = dg + 36 * (1 + k); for (int m = 0; m < 6; ++m) for (int nn = 0; nn < 6; ++nn) sv[m] -= c.rd(B + 6 * nn + m) * c.rd(rows[k] + nn); }
+      for (int m = 5; m >= 0; --m) { double t2 = sv[m]; for (int k = m + 1; k < 6; ++k) t2 -= c.rd(dg + 6 * k + m) * x[k]; x[m] = t2 * c.rd(dg + 7 * m); }
+      for (int m = 0; m < 6; ++m) c.wrt(v + m, x[m]);
+    }
+  }
+}
+static std::vector<double> interpret_tree_program(const Structure &s, const std::vector<double> &L0, const std::vector<double> &b) {
+  const TreeProgram &tp = s.tree;
+  const int n = s.n_fp, C = tp.C;
+  const double nan = std::numeric_limits<double>::quiet_NaN();
+  std::vector<TreeCta> cta(C);
+  std::vector<double> xchg((size_t)std::max(tp.xchg_doubles, 1), nan), x(6 * (size_t)n, nan);
+  CHECK(tp.smem_bytes <= kTreeMaxSmem, "tree program: %zu bytes of shared memory", tp.smem_bytes);
+  int cols_seen = 0;
+  for (int c = 0; c < C; ++c) {
+    TreeCta &t = cta[c];
+    t.w = tp.words.data() + tp.prog_ptr[c];
+    const int np = tp.pool_doubles[c];
+    CHECK(8 * (size_t)np + 4 * (size_t)(tp.prog_ptr[c + 1] - tp.prog_ptr[c]) + kTreeMiscBytes <= tp.smem_bytes, "tree program: CTA %d exceeds the launch size", c);
+    t.pool.assign(np, nan); t.wr_t.assign(np, -1); t.wr_i.assign(np, -1); t.rd_t.assign(np, -1); t.rd_i.assign(np, -1);
+    for (int i = 0; i < 36 * tp.n_own_blocks[c]; ++i) t.pool[i] = L0[36 * (size_t)tp.b0[c] + i];
+    for (int i = 0; i < 6 * tp.n_own_cols[c]; ++i) t.pool[36 * tp.n_own_blocks[c] + i] = b[6 * (size_t)tp.q0[c] + i];
+    for (int i = 0; i < tp.contrib_doubles[c]; ++i) t.pool[tp.contrib_off[c] + i] = 0.0;
+    cols_seen += tp.n_own_cols[c];
+  }
+  CHECK(cols_seen == n, "tree program: CTAs own %d of %d columns", cols_seen, n);
+  bool fail = false;
+  for (int c = 0; c < C; ++c) tree_forward_steps(cta[c], 0, cta[c].w[kTH_StepsA], &fail);
+  for (int c = 1; c < C; ++c)
+    for (int i = 0; i < tp.contrib_doubles[c]; ++i) xchg[tp.xchg_off[c] + i] = cta[c].pool[tp.contrib_off[c] + i];
+  {
+    TreeCta &t = cta[0];
+    const int32_t *w = t.w;
+    for (int r = 0; r < w[kTH_AddRounds]; ++r) {
+      ++t.T;
+      const int nops = w[w[kTH_OffAddRounds] + 2 * r], off = w[w[kTH_OffAddRounds] + 2 * r + 1];
+      for (int i = 0; i < nops; ++i) {
+        ++t.item;
+        const unsigned op = (unsigned)w[off + i];
+        const int dest = (int)(op & 0xffff), src = 2 * (int)((op >> 16) & 0x7fff), nd = (op >> 31) ? 6 : 36;
+        for (int k = 0; k < nd; ++k) t.wrt(dest + k, t.rd(dest + k) + xchg[src + k]);
+      }
+    }
+    tree_forward_steps(t, w[kTH_StepsA], w[kTH_StepsA] + w[kTH_StepsB], &fail);
+    tree_backward_steps(t, w[kTH_StepsA], w[kTH_StepsA] + w[kTH_StepsB]);
+  }
+  CHECK(!fail, "tree program: pivot <= 0");
+  // the top solution goes down through global memory
+  {
+    const int V0 = 36 * tp.n_own_blocks[0];
+    for (int q = tp.q0[0]; q < n; ++q) for (int m = 0; m < 6; ++m) x[6 * (size_t)q + m] = cta[0].pool[V0 + 6 * (q - tp.q0[0]) + m];
+  }
+  for (int c = 1; c < C; ++c) {
+    TreeCta &t = cta[c];
+    ++t.T; ++t.item;
+    for (int i = 0; i < t.w[kTH_NXload]; ++i) {
+      const unsigned wd = (unsigned)t.w[t.w[kTH_OffXload] + i];
+      for (int m = 0; m < 6; ++m) t.wrt((int)(wd & 0xffff) + m, x[6 * (size_t)(wd >> 16) + m]);
+    }
+  }
+  for (int c = 0; c < C; ++c) {
+    tree_backward_steps(cta[c], 0, cta[c].w[kTH_StepsA]);
+    const int V0 = 36 * tp.n_own_blocks[c];
+    for (int q = tp.q0[c]; q < tp.q0[c] + tp.n_own_cols[c]; ++q) for (int m = 0; m < 6; ++m) x[6 * (size_t)q + m] = cta[c].pool[V0 + 6 * (q - tp.q0[c]) + m];
+  }
+  return x;
+}
+
 static void check_case(int nk, int np, int w, unsigned seed, bool fix0, int nfix, bool loop, int world) {
   HostGraph g = make_graph(nk, np, w, seed, fix0, nfix, loop);
   std::vector<Structure> S(world);
@@ -266,7 +426,24 @@ static void check_case(int nk, int np, int w, unsigned seed, bool fix0, int nfix
   // left-looking by levels: first every update task of the level, then factor its columns
   for (int lv = 0; lv < s.n_levels; ++lv) {
     CHECK(s.level_ptr[lv + 1] - s.level_ptr[lv] <= 64, "level too wide");
-    for (int t = s.ltask_ptr[lv]; t < s.ltask_ptr[lv + 1]; ++t) {
+    if (s.ltask_ptr.empty()) {
+      // no level tasks were planned (the tree program is in use): the same updates straight from the row lists
+      for (int t = s.level_ptr[lv]; t < s.level_ptr[lv + 1]; ++t) {
+        const int j = s.level_col[t];
+        for (int rr = s.row_ptr[j]; rr < s.row_ptr[j + 1]; ++rr) {
+          const int bjk = s.row_blk[rr], k = s.row_col[rr];
+          for (int bik = bjk; bik < s.col_ptr[k + 1]; ++bik) {
+            const int32_t *c0 = s.blk_row.data() + s.col_ptr[j], *c1 = s.blk_row.data() + s.col_ptr[j + 1];
+            const int32_t *it = std::lower_bound(c0, c1, s.blk_row[bik]);
+            CHECK(it != c1 && *it == s.blk_row[bik], "fill block missing");
+            double *D = &L[36 * (size_t)(it - s.blk_row.data())];
+            const double *Aa = &L[36 * (size_t)bik], *Bb = &L[36 * (size_t)bjk];
+            for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) { double sacc = 0; for (int kk = 0; kk < 6; ++kk) sacc += Aa[6 * r + kk] * Bb[6 * c + kk]; D[6 * r + c] -= sacc; }
+          }
+        }
+      }
+    }
+    for (int t = s.ltask_ptr.empty() ? 0 : s.ltask_ptr[lv]; t < (s.ltask_ptr.empty() ? 0 : s.ltask_ptr[lv + 1]); ++t) {
       if (s.task_dst[t] < 0) { CHECK(s.level_col[s.level_ptr[lv] + s.task_pos[t]] == -1 - s.task_dst[t], "vec item pos"); continue; }
       CHECK(s.level_col[s.level_ptr[lv] + s.task_pos[t]] == s.blk_col[s.task_dst[t]], "item pos");
       double *D = &L[36 * (size_t)s.task_dst[t]];
@@ -330,7 +507,17 @@ static void check_case(int nk, int np, int w, unsigned seed, bool fix0, int nfix
     rmax = std::fmax(rmax, std::fabs(r)); bmax = std::fmax(bmax, std::fabs(b[i]));
   }
   CHECK(rmax < 1e-10 * (1 + bmax), "residual %.3e (n=%d blocks=%d levels=%d)", rmax, n, s.n_blocks, s.n_levels);
-  {
+  if (s.tree.ok) {
+    const std::vector<double> xt = interpret_tree_program(s, L0, b);
+    double dmax = 0;
+    bool finite = true;
+    for (int i = 0; i < N; ++i) { finite = finite && std::isfinite(xt[i]); dmax = std::fmax(dmax, std::fabs(xt[i] - x[i])); }
+    CHECK(finite, "tree program: non-finite solution (a pool double was read before it was written?)");
+    CHECK(dmax < 1e-10, "tree program: solution differs by %.3e (n=%d, cluster %d)", dmax, n, s.tree.C);
+    std::printf("  tree program: C=%d top=%d chain=%d steps smem=%zu B words=%zu xchg=%d doubles\n", s.tree.C, s.tree.n_top_cols, s.tree.chain_steps,
+                s.tree.smem_bytes, s.tree.words.size(), s.tree.xchg_doubles);
+  } else {
+    std::printf("  tree program not used: %s\n", s.tree.why_not.c_str());
     // the same system through the packed device program
     const std::vector<double> xp = interpret_program(s, L0, b);
     double dmax = 0;

@@ -1,6 +1,7 @@
 """Host logic of the product: structure build, landmark sharding, symbolic factorisation and the
 level schedule the CUDA solver walks — exercised on the CPU by tests/cpp/test_structure.cpp, which also
-interprets the PACKED device program (rounds per CTA, slots, reader masks, look-ahead) against a dense solve."""
+interprets the PACKED device programs (the subtree-per-CTA program of k_tree_solve with a race check per barrier
+interval; the level program of k_reduced_solve: rounds per CTA, slots, reader masks, look-ahead) against a dense solve."""
 import os
 import subprocess
 
@@ -13,13 +14,20 @@ def test_structure_builder_cpp():
     subprocess.run(["g++", "-O2", "-std=c++17", "-I" + cuda_inc, "-I" + os.path.join(ROOT, "include"),
                     "-I" + os.path.join(ROOT, "ssvio_b200", "csrc"),
                     os.path.join(ROOT, "tests", "cpp", "test_structure.cpp"),
-                    os.path.join(ROOT, "ssvio_b200", "csrc", "ssba_structure.cpp"), "-o", exe], check=True)
+                    os.path.join(ROOT, "ssvio_b200", "csrc", "ssba_structure.cpp"),
+                    os.path.join(ROOT, "ssvio_b200", "csrc", "ssba_tree_program.cpp"), "-o", exe, "-lpthread"], check=True)
     # every cluster size the device solver can be built for (the packed program differs: rounds per CTA,
     # reader masks, look-ahead placement)
-    for cluster in ("", "1", "2", "4", "8"):
-        env = dict(os.environ)
-        if cluster:
-            env["SSBA_SOLVE_CLUSTER"] = cluster
-        r = subprocess.run([exe], capture_output=True, text=True, env=env)
-        assert r.returncode == 0, f"cluster={cluster or 'default'}\n" + r.stdout + r.stderr
-        assert r.stdout.strip().endswith("OK")
+    # ... for both solver programs: the subtree-per-CTA program of k_tree_solve (default; with the 8- and the
+    # 16-CTA cluster cap) and the level program of k_reduced_solve (SSBA_SOLVER=level, also the fallback)
+    for solver, cap in (("", "8"), ("", "16"), ("level", "8")):
+        for cluster in ("", "1", "2", "4", "8"):
+            env = dict(os.environ)
+            env["SSBA_TREE_CLUSTER_CAP"] = cap
+            if solver:
+                env["SSBA_SOLVER"] = solver
+            if cluster:
+                env["SSBA_SOLVE_CLUSTER"] = cluster
+            r = subprocess.run([exe], capture_output=True, text=True, env=env)
+            assert r.returncode == 0, f"solver={solver or 'tree'} cap={cap} cluster={cluster or 'default'}\n" + r.stdout + r.stderr
+            assert r.stdout.strip().endswith("OK")
