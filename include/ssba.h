@@ -202,6 +202,15 @@ ssba_status ssba_step(ssba_handle *h, int32_t iteration, int32_t *solver_result,
  * lets a resident graph be optimised repeatedly (bench). */
 ssba_status ssba_reset_state(ssba_handle *h);
 
+/* Structure reuse.  When the set_* calls since the last ssba_initialize() changed only VALUES (estimates,
+ * measurements, information matrices, Huber widths, camera parameters) and not the topology (vertex counts,
+ * fixed flags, edge indices, cameras per edge), ssba_initialize() keeps the resident structure and only
+ * uploads the values: what rounds 2..5 of backend.cpp:175-203 need, where g2o re-runs buildStructure and the
+ * symbolic factorisation on every optimize() (linear_solver_csparse.h:97-104).  The comparison is exact
+ * (memcmp against the arrays of the resident graph).  ssba_drop_structure() forces the next
+ * ssba_initialize() to rebuild (benchmarks of the cold path). */
+ssba_status ssba_drop_structure(ssba_handle *h);
+
 /* ---- results (backend.cpp:180-244) ------------------------------------------------- */
 
 /* VertexPose::estimate() / VertexXYZ::estimate() (backend.cpp:234,238), same layout
@@ -302,6 +311,8 @@ typedef struct ssba_problem_info {
   int32_t solver_steps;    /* elimination steps on the critical path of the reduced solve            */
   int32_t solver_top_cols; /* columns of the top part (factored by CTA 0 after the hand-off)          */
   int32_t solver_smem_bytes;
+  int64_t n_structure_builds; /* ssba_initialize() calls that built the structure ...               */
+  int64_t n_structure_reuses; /* ... and calls that kept it (same topology, values only)             */
 } ssba_problem_info;
 ssba_status ssba_get_problem_info(ssba_handle *h, ssba_problem_info *out);
 

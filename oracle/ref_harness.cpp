@@ -87,7 +87,33 @@ struct TraceAction : public g2o::HyperGraphAction {
   }
 };
 
+// LinearSolverCSparse that counts its failed factorisations (csparse_extension.cpp:115 -> solve() == false):
+// g2o itself only turns them into a rejected trial (optimization_algorithm_levenberg.cpp:120-121)
+int g_cholesky_failures = 0;
+template <class M>
+class CountingCSparse : public g2o::LinearSolverCSparse<M> {
+ public:
+  bool solve(const g2o::SparseBlockMatrix<M> &A, number_t *x, number_t *b) override {
+    const bool ok = g2o::LinearSolverCSparse<M>::solve(A, x, b);
+    if (!ok) ++g_cholesky_failures;
+    return ok;
+  }
+};
+
+// extras of the NEXT ssba_ref_optimize call (consumed by it): LM options of
+// OptimizationAlgorithmLevenberg (optimization_algorithm_levenberg.cpp:44-56) and per-edge information
+// matrices (EdgeProjection::setInformation, backend.cpp:161 uses the identity)
+double g_user_lambda_init = 0.0;
+int g_max_trials = 0;
+const double *g_edge_info = nullptr;
+
 }  // namespace
+
+extern "C" void ssba_ref_set_extras(double user_lambda_init, int32_t max_trials_after_failure, const double *edge_info_xx_xy_yy) {
+  g_user_lambda_init = user_lambda_init;
+  g_max_trials = max_trials_after_failure;
+  g_edge_info = edge_info_xx_xy_yy;
+}
 
 extern "C" int ssba_ref_optimize(
     const double K[9], int32_t n_cams, const double *ext_qt, int32_t n_poses,
@@ -106,11 +132,17 @@ extern "C" int ssba_ref_optimize(
 
   // backend.cpp:81-86
   typedef g2o::BlockSolver_6_3 BlockSolverType;
-  typedef g2o::LinearSolverCSparse<BlockSolverType::PoseMatrixType> LinearSolverType;
+  typedef CountingCSparse<BlockSolverType::PoseMatrixType> LinearSolverType;  // LinearSolverCSparse + a failure counter
+  g_cholesky_failures = 0;
   auto *solver = new g2o::OptimizationAlgorithmLevenberg(
       g2o::make_unique<BlockSolverType>(g2o::make_unique<LinearSolverType>()));
   g2o::SparseOptimizer optimizer;
   optimizer.setAlgorithm(solver);
+  if (g_user_lambda_init > 0) solver->setUserLambdaInit(g_user_lambda_init);
+  if (g_max_trials > 0) solver->setMaxTrialsAfterFailure(g_max_trials);
+  solver->setWriteDebug(false);  // a failed factorisation must not drop debug.txt into the working directory
+  const double *edge_info = g_edge_info;
+  g_user_lambda_init = 0.0; g_max_trials = 0; g_edge_info = nullptr;
 
   Eigen::Matrix3d cam_K;
   for (int r = 0; r < 3; ++r)
@@ -152,7 +184,13 @@ extern "C" int ssba_ref_optimize(
     edge->setVertex(0, vpose[pose_idx[e]]);
     edge->setVertex(1, vpoint[point_idx[e]]);
     edge->setMeasurement(Eigen::Vector2d(uv[2 * e], uv[2 * e + 1]));
-    edge->setInformation(Eigen::Matrix2d::Identity());
+    if (edge_info) {
+      Eigen::Matrix2d om;
+      om << edge_info[3 * e], edge_info[3 * e + 1], edge_info[3 * e + 1], edge_info[3 * e + 2];
+      edge->setInformation(om);
+    } else {
+      edge->setInformation(Eigen::Matrix2d::Identity());
+    }
     if (huber_delta > 0) {
       auto *rk = new g2o::RobustKernelHuber();
       rk->setDelta(huber_delta);
@@ -226,6 +264,7 @@ extern "C" int ssba_ref_optimize(
     report->chi2_robust = its >= 0 ? optimizer.activeRobustChi2() : 0.0;
     report->chi2_plain = its >= 0 ? optimizer.activeChi2() : 0.0;
     report->lambda = solver->currentLambda();
+    report->cholesky_failures = g_cholesky_failures;
     report->seconds_total = t_opt;
     report->seconds_setup = t_build + t_init;
   }

@@ -56,6 +56,12 @@ int ssba_ref_optimize(const double K[9], int32_t n_cams, const double *ext_qt,
                       ssba_report *report, ssba_ref_stats *stats, int32_t *rounds_done,
                       int64_t *n_outliers);
 
+/* Extras of the NEXT ssba_ref_optimize call (consumed by it): _userLambdaInit and _maxTrialsAfterFailure of
+ * OptimizationAlgorithmLevenberg (thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.cpp:44-56; 0 keeps
+ * the default) and per-edge information matrices (n_edges x 3: xx, xy, yy; NULL = identity as backend.cpp:161).
+ * Used to drive the reference into failed factorisations (csparse_extension.cpp:115). */
+void ssba_ref_set_extras(double user_lambda_init, int32_t max_trials_after_failure, const double *edge_info_xx_xy_yy);
+
 /*
  * Pose-only LM of FrontEnd::EstimateCurrentPose() (src/ssvio/frontend.cpp:184-260), frame by
  * frame: one VertexPose, one EdgeProjectionPoseOnly (include/ssvio/g2otypes.hpp:67-110, analytic

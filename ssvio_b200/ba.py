@@ -31,7 +31,7 @@ SOLVER_OK, SOLVER_TERMINATE, SOLVER_FAIL = 1, 2, -1
 ABI_SYMBOLS = [
     "ssba_default_options", "ssba_create", "ssba_destroy", "ssba_last_error",
     "ssba_nccl_unique_id", "ssba_set_cameras", "ssba_set_poses", "ssba_set_points",
-    "ssba_set_edges", "ssba_initialize", "ssba_optimize", "ssba_step", "ssba_reset_state",
+    "ssba_set_edges", "ssba_initialize", "ssba_optimize", "ssba_step", "ssba_reset_state", "ssba_drop_structure",
     "ssba_get_poses", "ssba_get_points", "ssba_get_edge_errors", "ssba_chi2",
     "ssba_count_outliers", "ssba_optimize_rounds", "ssba_plan_shards", "ssba_set_profiling", "ssba_profile_get",
     "ssba_profile_reset", "ssba_get_problem_info", "ssba_pose_only_optimize", "ssba_pose_graph_optimize",
@@ -80,7 +80,7 @@ class ProblemInfo(C.Structure):
                 ("n_schur_blocks", C.c_int32), ("n_factor_blocks", C.c_int32),
                 ("device_bytes", C.c_int64), ("solve_cluster", C.c_int32), ("peer_exchange", C.c_int32),
                 ("solver_kind", C.c_int32), ("solver_steps", C.c_int32), ("solver_top_cols", C.c_int32),
-                ("solver_smem_bytes", C.c_int32)]
+                ("solver_smem_bytes", C.c_int32), ("n_structure_builds", C.c_int64), ("n_structure_reuses", C.c_int64)]
 
 
 class SsbaError(RuntimeError):
@@ -119,6 +119,7 @@ def load_library():
     lib.ssba_optimize.argtypes = [H, C.c_int32, C.POINTER(Report)]
     lib.ssba_step.argtypes = [H, C.c_int32, C.POINTER(C.c_int32), C.POINTER(IterRecord)]
     lib.ssba_reset_state.argtypes = [H]
+    lib.ssba_drop_structure.argtypes = [H]
     lib.ssba_get_poses.argtypes = [H, dp]
     lib.ssba_get_points.argtypes = [H, dp]
     lib.ssba_get_edge_errors.argtypes = [H, dp]
@@ -295,6 +296,10 @@ class BundleAdjuster:
 
     def reset_state(self):
         self._check(self.lib.ssba_reset_state(self._h))
+
+    def drop_structure(self):
+        """Force the next initialize to rebuild the structure even for an unchanged topology."""
+        self._check(self.lib.ssba_drop_structure(self._h))
 
     # -- results (backend.cpp:180-244)
     def poses(self):

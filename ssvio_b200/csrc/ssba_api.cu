@@ -75,7 +75,13 @@ struct ssba_handle {
   HostGraph g;
   Structure s;
   bool dirty = true;        // graph changed since the last ssba_initialize
+  bool topo_dirty = true;   // ... and not only its VALUES (estimates, measurements, information, Huber widths,
+                            // camera parameters): the structure has to be rebuilt
   bool initialized = false;
+  // where the value arrays of the resident structure sit in region A (arena and pinned mirror alike): a graph
+  // with the same topology is re-uploaded without a structure build (the <= 5 rounds of backend.cpp:175-203)
+  size_t off_pose0 = 0, off_point0 = 0, off_e_uv = 0, off_e_info = 0, off_e_delta = 0;
+  long long n_structure_builds = 0, n_structure_reuses = 0;
   // memory: one device arena (static index data first, then work buffers) + pinned mirror of
   // the static part so a whole graph goes up in one copy
   char *d_arena = nullptr; size_t d_arena_bytes = 0;
@@ -340,6 +346,14 @@ ssba_status final_chi2(ssba_handle *h, double threshold, double out[4]) {
   return SSBA_OK;
 }
 
+// fixed flags unchanged? (NULL = none fixed)
+bool same_flags(const std::vector<uint8_t> &old, int old_n, const uint8_t *now, int n) {
+  if (old_n != n || (int)old.size() != n) return false;
+  if (now) return n == 0 || std::memcmp(old.data(), now, (size_t)n) == 0;
+  for (uint8_t v : old) if (v) return false;
+  return true;
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -449,6 +463,7 @@ void ssba_destroy(ssba_handle *h) {
 ssba_status ssba_set_cameras(ssba_handle *h, const double K[9], int32_t n_cams, const double *ext_qt) {
   if (!h) return SSBA_ERR_INVALID_ARG;
   if (!K || !ext_qt || n_cams < 1 || n_cams > SSBA_MAX_CAMERAS) return fail(h, SSBA_ERR_INVALID_ARG, "set_cameras: bad arguments");
+  if (!h->g.have_cams || h->g.cams.n != n_cams) h->topo_dirty = true;  // edges are validated against the camera count
   std::memcpy(h->g.cams.K, K, 9 * sizeof(double));
   std::memcpy(h->g.cams.ext, ext_qt, 7 * sizeof(double) * n_cams);
   h->g.cams.n = n_cams;
@@ -460,6 +475,7 @@ ssba_status ssba_set_cameras(ssba_handle *h, const double K[9], int32_t n_cams, 
 ssba_status ssba_set_poses(ssba_handle *h, int32_t n, const double *qt, const uint8_t *fixed) {
   if (!h) return SSBA_ERR_INVALID_ARG;
   if (n < 0 || (n > 0 && !qt)) return fail(h, SSBA_ERR_INVALID_ARG, "set_poses: bad arguments");
+  if (!same_flags(h->g.pose_fixed, h->g.n_poses, fixed, n)) h->topo_dirty = true;
   h->g.n_poses = n;
   h->g.poses.assign(qt, qt + 7 * (size_t)n);
   if (fixed) h->g.pose_fixed.assign(fixed, fixed + n); else h->g.pose_fixed.assign(n, 0);
@@ -470,6 +486,7 @@ ssba_status ssba_set_poses(ssba_handle *h, int32_t n, const double *qt, const ui
 ssba_status ssba_set_points(ssba_handle *h, int32_t n, const double *xyz, const uint8_t *fixed) {
   if (!h) return SSBA_ERR_INVALID_ARG;
   if (n < 0 || (n > 0 && !xyz)) return fail(h, SSBA_ERR_INVALID_ARG, "set_points: bad arguments");
+  if (!same_flags(h->g.point_fixed, h->g.n_points, fixed, n)) h->topo_dirty = true;
   h->g.n_points = n;
   h->g.points.assign(xyz, xyz + 3 * (size_t)n);
   if (fixed) h->g.point_fixed.assign(fixed, fixed + n); else h->g.point_fixed.assign(n, 0);
@@ -483,15 +500,28 @@ ssba_status ssba_set_edges(ssba_handle *h, int32_t n, const int32_t *pose_idx, c
   if (!h) return SSBA_ERR_INVALID_ARG;
   if (n < 0 || (n > 0 && (!pose_idx || !point_idx || !uv))) return fail(h, SSBA_ERR_INVALID_ARG, "set_edges: bad arguments");
   HostGraph &g = h->g;
+  // same topology as the resident graph (indices, cameras, which optional arrays exist)?  Then only the
+  // values are taken and ssba_initialize keeps the structure.
+  bool same = !h->topo_dirty && g.n_edges == n && (int)g.e_pose.size() == n && (info != nullptr) == !g.e_info.empty() &&
+              (huber_delta != nullptr) == !g.e_delta.empty();
+  if (same && n > 0) {
+    std::vector<CopyJob> cmp = {{g.e_pose.data(), pose_idx, sizeof(int32_t) * (size_t)n}, {g.e_point.data(), point_idx, sizeof(int32_t) * (size_t)n}};
+    if (cam_idx) cmp.push_back({g.e_cam.data(), cam_idx, (size_t)n});
+    same = parallel_equal(cmp);
+    if (same && !cam_idx) for (uint8_t c : g.e_cam) if (c) { same = false; break; }
+  }
+  if (!same) h->topo_dirty = true;
   g.n_edges = n;
   // the caller keeps its arrays: copy them (on the host thread pool, several megabytes per window)
   g.e_pose.resize(n); g.e_point.resize(n); g.e_cam.resize(n); g.e_uv.resize(2 * (size_t)n);
   if (info) g.e_info.resize(3 * (size_t)n); else g.e_info.clear();
   if (huber_delta) g.e_delta.resize(n); else g.e_delta.clear();
-  std::vector<CopyJob> jobs = {{g.e_pose.data(), pose_idx, sizeof(int32_t) * (size_t)n},
-                               {g.e_point.data(), point_idx, sizeof(int32_t) * (size_t)n},
-                               {g.e_uv.data(), uv, 2 * sizeof(double) * (size_t)n}};
-  if (cam_idx) jobs.push_back({g.e_cam.data(), cam_idx, (size_t)n}); else std::fill(g.e_cam.begin(), g.e_cam.end(), (uint8_t)0);
+  std::vector<CopyJob> jobs = {{g.e_uv.data(), uv, 2 * sizeof(double) * (size_t)n}};
+  if (!same) {
+    jobs.push_back({g.e_pose.data(), pose_idx, sizeof(int32_t) * (size_t)n});
+    jobs.push_back({g.e_point.data(), point_idx, sizeof(int32_t) * (size_t)n});
+    if (cam_idx) jobs.push_back({g.e_cam.data(), cam_idx, (size_t)n}); else std::fill(g.e_cam.begin(), g.e_cam.end(), (uint8_t)0);
+  }
   if (info) jobs.push_back({g.e_info.data(), info, 3 * sizeof(double) * (size_t)n});
   if (huber_delta) jobs.push_back({g.e_delta.data(), huber_delta, sizeof(double) * (size_t)n});
   parallel_copy(jobs);
@@ -517,6 +547,34 @@ ssba_status ssba_initialize(ssba_handle *h) {
   Structure &s = h->s;
   const bool timing = std::getenv("SSBA_TIMING") != nullptr;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // nothing of a previous upload may still read the staging buffers
+
+  if (!h->topo_dirty && h->initialized) {
+    // ---- same topology as the resident structure: only the values go up (estimates, measurements in the
+    // structure's edge order, information / Huber widths, cameras), then the state is reset.  This is what
+    // rounds 2..5 of backend.cpp:175-203 and the g2o shim's repeated init() cost.
+    DeviceProblem &P = h->P;
+    const size_t pb = 56 * (size_t)g.n_poses, lb = 24 * (size_t)g.n_points, ne = (size_t)s.n_edges;
+    if (pb) std::memcpy(h->h_stage + h->off_pose0, g.poses.data(), pb);
+    if (lb) std::memcpy(h->h_stage + h->off_point0, g.points.data(), lb);
+    if (ne) parallel_gather_doubles((double *)(h->h_stage + h->off_e_uv), g.e_uv.data(), s.e_orig.data(), ne, 2);
+    if (ne && !g.e_info.empty()) parallel_gather_doubles((double *)(h->h_stage + h->off_e_info), g.e_info.data(), s.e_orig.data(), ne, 3);
+    if (ne && !g.e_delta.empty()) parallel_gather_doubles((double *)(h->h_stage + h->off_e_delta), g.e_delta.data(), s.e_orig.data(), ne, 1);
+    if (pb) CUDA_TRY(h, cudaMemcpyAsync(h->d_arena + h->off_pose0, h->h_stage + h->off_pose0, pb, cudaMemcpyHostToDevice, h->stream));
+    if (lb) CUDA_TRY(h, cudaMemcpyAsync(h->d_arena + h->off_point0, h->h_stage + h->off_point0, lb, cudaMemcpyHostToDevice, h->stream));
+    if (ne) CUDA_TRY(h, cudaMemcpyAsync(h->d_arena + h->off_e_uv, h->h_stage + h->off_e_uv, 16 * ne, cudaMemcpyHostToDevice, h->stream));
+    if (ne && !g.e_info.empty()) CUDA_TRY(h, cudaMemcpyAsync(h->d_arena + h->off_e_info, h->h_stage + h->off_e_info, 24 * ne, cudaMemcpyHostToDevice, h->stream));
+    if (ne && !g.e_delta.empty()) CUDA_TRY(h, cudaMemcpyAsync(h->d_arena + h->off_e_delta, h->h_stage + h->off_e_delta, 8 * ne, cudaMemcpyHostToDevice, h->stream));
+    P.cams = g.cams;
+    for (int c = 0; c < g.cams.n; ++c) quat_to_matrix(g.cams.ext[c], P.ext_R[c]);
+    P.delta_all = g.delta_all;
+    h->dirty = false;
+    ++h->n_structure_reuses;
+    ssba_status rc = ssba_reset_state(h);  // synchronises the stream: the staging buffer is free again
+    if (rc) return rc;
+    h->setup_seconds = secs(t0, Clock::now());
+    if (timing) std::fprintf(stderr, "[ssba] initialize: same topology, values only: %.3f ms\n", 1e3 * h->setup_seconds);
+    return SSBA_OK;
+  }
 
   // ---- the arena is planned and filled in two steps so that the upload of the big per-edge /
   // per-pair arrays (region A, several megabytes over PCIe) runs while the host still builds the
@@ -589,6 +647,7 @@ ssba_status ssba_initialize(ssba_handle *h) {
   };
   auto t_a = Clock::now();
   h->initialized = false;  // the device problem is being rebuilt
+  h->topo_dirty = true;
   if (!build_structure(g, h->opt.rank, h->opt.world_size, s, err, &on_edges_ready)) return fail(h, SSBA_ERR_INVALID_ARG, err);
   auto t_b = Clock::now();
   if (cb_rc) return cb_rc;
@@ -643,6 +702,13 @@ ssba_status ssba_initialize(ssba_handle *h) {
   }
   auto t_d = Clock::now();
   for (auto *v : {&items_a, &items_b, &work}) for (auto &it : *v) *it.dst = h->d_arena + it.off;
+  for (auto &it : items_a) {
+    if (it.src == (const void *)g.poses.data()) h->off_pose0 = it.off;
+    else if (it.src == (const void *)g.points.data()) h->off_point0 = it.off;
+    else if (it.src == (const void *)s.e_uv.data()) h->off_e_uv = it.off;
+    else if (it.src == (const void *)s.e_info.data()) h->off_e_info = it.off;
+    else if (it.src == (const void *)s.e_delta.data()) h->off_e_delta = it.off;
+  }
   h->device_bytes = total;
   if (bytes_b) CUDA_TRY(h, cudaMemcpyAsync(h->d_arena + off_b, h->h_stage_b, bytes_b, cudaMemcpyHostToDevice, h->stream));
 
@@ -669,6 +735,8 @@ ssba_status ssba_initialize(ssba_handle *h) {
   P.n_units = s.n_units;
   h->initialized = true;
   h->dirty = false;
+  h->topo_dirty = false;
+  ++h->n_structure_builds;
   ssba_status rc = ssba_reset_state(h);
   if (rc) return rc;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // h_stage may be rewritten by the next initialize
@@ -679,6 +747,13 @@ ssba_status ssba_initialize(ssba_handle *h) {
                  1e3 * t_stage_a, bytes_a / 1e6, 1e3 * secs(t_b, t_c), 1e3 * secs(t_c, t_d), bytes_b / 1e6,
                  1e3 * secs(t_d, Clock::now()), 1e3 * h->setup_seconds);
   (void)static_bytes;
+  return SSBA_OK;
+}
+
+ssba_status ssba_drop_structure(ssba_handle *h) {
+  if (!h) return SSBA_ERR_INVALID_ARG;
+  h->topo_dirty = true;
+  h->dirty = true;
   return SSBA_OK;
 }
 
@@ -759,7 +834,7 @@ ssba_status ssba_step(ssba_handle *h, int32_t iteration, int32_t *solver_result,
 
 ssba_status ssba_get_poses(ssba_handle *h, double *out) {
   if (!h || !out) return SSBA_ERR_INVALID_ARG;
-  if (!h->initialized) {  // nothing ran: the estimates are the ones that were set
+  if (!h->initialized || h->dirty) {  // nothing ran on the graph as it is now: the estimates are the ones that were set
     if ((int)h->g.poses.size() != 7 * h->g.n_poses) return fail(h, SSBA_ERR_STATE, "get_poses: no poses");
     std::memcpy(out, h->g.poses.data(), h->g.poses.size() * sizeof(double));
     return SSBA_OK;
@@ -772,7 +847,7 @@ ssba_status ssba_get_poses(ssba_handle *h, double *out) {
 
 ssba_status ssba_get_points(ssba_handle *h, double *out) {
   if (!h || !out) return SSBA_ERR_INVALID_ARG;
-  if (!h->initialized) {
+  if (!h->initialized || h->dirty) {
     if ((int)h->g.points.size() != 3 * h->g.n_points) return fail(h, SSBA_ERR_STATE, "get_points: no points");
     std::memcpy(out, h->g.points.data(), h->g.points.size() * sizeof(double));
     return SSBA_OK;
@@ -1108,6 +1183,7 @@ ssba_status ssba_get_problem_info(ssba_handle *h, ssba_problem_info *out) {
   out->solver_steps = h->s.tree.ok ? h->s.tree.chain_steps : h->s.n_levels;
   out->solver_top_cols = h->s.tree.ok ? h->s.tree.n_top_cols : 0;
   out->solver_smem_bytes = h->s.tree.ok ? (int32_t)h->s.tree.smem_bytes : 0;
+  out->n_structure_builds = h->n_structure_builds; out->n_structure_reuses = h->n_structure_reuses;
   return SSBA_OK;
 }
 

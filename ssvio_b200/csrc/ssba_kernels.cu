@@ -12,6 +12,7 @@
 #include <atomic>
 #include <cfloat>
 #include <cstdlib>
+#include <mutex>
 
 #include "ssba_device.hpp"
 #include "ssba_solver_layout.hpp"
@@ -1709,18 +1710,25 @@ void launch_maxdiag(const DeviceProblem &P, cudaStream_t st) { k_maxdiag<<<1, 10
 
 void launch_lambda_init(const DeviceProblem &P, cudaStream_t st) { k_lambda_init<<<1, 1, 0, st>>>(P); }
 
-// function attributes are per device: remember which devices of this process have them
-bool first_launch_on_this_device(std::atomic<unsigned long long> &seen) {
+// function attributes are per device: `setup` runs once per device of this process, and a second thread
+// cannot launch before the first one has finished setting them (handles are used from several threads)
+template <class F>
+void once_per_device(std::atomic<unsigned long long> &done, F &&setup) {
+  static std::mutex mu;
   int dev = 0;
   cudaGetDevice(&dev);
   const unsigned long long bit = 1ull << (dev & 63);
-  return (seen.fetch_or(bit) & bit) == 0;
+  if (done.load(std::memory_order_acquire) & bit) return;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.load(std::memory_order_acquire) & bit) return;
+  setup();
+  done.fetch_or(bit, std::memory_order_release);
 }
 
 void launch_schur(const DeviceProblem &P, bool prefolded, cudaStream_t st) {
   static std::atomic<unsigned long long> seen{0};
   constexpr size_t kDyn = (size_t)kSchurWarps * kSchurRunPairs * 18 * sizeof(double);
-  if (first_launch_on_this_device(seen)) cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDyn);
+  once_per_device(seen, [] { cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDyn); });
   const int n_pose = div_up(P.n_fp, kSchurWarps), n_unit = div_up(P.n_units, kSchurWarps);
   if (n_pose + n_unit > 0) k_schur<<<n_pose + n_unit, 32 * kSchurWarps, kDyn, st>>>(P, n_pose, prefolded ? 1 : 0);
 }
@@ -1751,12 +1759,12 @@ int max_solver_cluster() {
 void launch_reduced_solve(const DeviceProblem &P, cudaStream_t st) {
   if (P.tree.C > 0) { launch_tree_solve(P, st); return; }
   static std::atomic<unsigned long long> seen{0};
-  if (first_launch_on_this_device(seen)) {
+  once_per_device(seen, [] {
     cudaFuncSetAttribute(k_reduced_solve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveMaxDynSmem);
     cudaFuncSetAttribute(k_reduced_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveMaxDynSmem);
     cudaFuncSetAttribute(k_reduced_solve<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveMaxDynSmem);
     cudaFuncSetAttribute(k_reduced_solve<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSolveMaxDynSmem);
-  }
+  });
   const SolverSmemLayout lay = solver_smem_layout(P.n_fp, P.prog_max_seg);
   const int c = P.solve_cluster;  // the program was built for this many CTAs
   if (c == 1) { k_reduced_solve<1><<<1, kSolveThreads, lay.bytes, st>>>(P, lay); return; }

@@ -587,20 +587,36 @@ void nested_dissection_order(int n, const std::vector<std::vector<int>> &adj_low
   rec(all);
 }
 
+struct SectionTimer {  // SSBA_TIMING=1: wall time of the sections of build_structure on stderr
+  bool on = std::getenv("SSBA_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void mark(const char *name) {
+    if (!on) return;
+    const auto n = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[ssba]   %-26s %.3f ms\n", name, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+
 // Elimination order, symbolic factorisation and solver program(s) of a block-sparse SPD system over n
 // 6x6 block columns (adj[c] = rows r > c with a block (r, c)), shared by the bundle adjustment (the
 // Schur complement) and the pose graph (H itself): natural order vs nested dissection, then the
 // subtree-per-CTA re-order and program (k_tree_solve).  The level program of k_reduced_solve is only
 // built when the tree program does not fit (or SSBA_SOLVER=level asks for it).
-bool plan_reduced_solver(int n, const std::vector<std::vector<int>> &adj, Structure &s, std::vector<int> &perm_out,
-                         std::string &err) {
+struct SolverPlan {  // what is left for finish_solver_program (run off the critical path of the structure build)
+  bool want_tree = false, have_tasks = false;
+  TreeAssign ta;
+  std::vector<int> perm;  // q -> original column
+};
+
+bool plan_reduced_solver(int n, const std::vector<std::vector<int>> &adj, Structure &s, SolverPlan &plan, std::string &err) {
   static const bool force_level = [] { const char *e = std::getenv("SSBA_SOLVER"); return e && std::string(e) == "level"; }();
   std::vector<int> perm_nat(n), perm_nd, perm_tree;
   std::iota(perm_nat.begin(), perm_nat.end(), 0);
   Factor f_nat, f_nd, f_tree;
   Factor *best = nullptr;
   std::vector<int> *best_perm = &perm_nat;
-  bool have_tasks = false;
+  plan = SolverPlan{};
   if (n >= 24) {
     nested_dissection_order(n, adj, perm_nd);
     if (perm_nd != perm_nat) {
@@ -614,37 +630,33 @@ bool plan_reduced_solver(int n, const std::vector<std::vector<int>> &adj, Struct
     if (!symbolic_factor(n, adj, perm_nat, f_nat, err, true)) return false;
     if (best && !symbolic_factor(n, adj, perm_nd, f_nd, err, true)) return false;
     if (!best || f_nat.est_cycles <= f_nd.est_cycles) { best = &f_nat; best_perm = &perm_nat; }
-    have_tasks = true;
+    plan.have_tasks = true;
   }
-  // subtree-per-CTA solver: columns of a CTA contiguous (a topological re-order of the same elimination
-  // tree: same fill), then the program
+  // subtree-per-CTA solver: the columns of a CTA made contiguous (a topological re-order of the same
+  // elimination tree: same fill).  Candidates: the cluster size the problem asks for; a system whose factor
+  // does not fit the shared memory of 8 SMs gets the 16-CTA cluster (when the device has it), if need be
+  // with CTA 0 taking the top part only.  The program itself is built by finish_solver_program.
   s.tree = TreeProgram{};
+  if (force_level) s.tree.why_not = "SSBA_SOLVER=level";
   if (!force_level && n > 0) {
-    // candidates: the cluster size the problem asks for; a system whose factor does not fit the shared memory
-    // of 8 SMs gets the 16-CTA cluster (when the device has it), if need be with CTA 0 taking the top part only
     struct Cand { int C; bool cta0_subtree; };
     std::vector<Cand> cands = {{std::min(solver_cluster_size(n), tree_cluster_cap()), true}};
     if (n >= 64 && tree_cluster_cap() >= 16) { cands.push_back({16, true}); cands.push_back({16, false}); }
     else if (n >= 64) cands.push_back({tree_cluster_cap(), false});
     for (const Cand &cd : cands) {
-      TreeAssign ta;
-      tree_assign(n, best->col_ptr, best->blk_row, cd.C, cd.cta0_subtree, ta);
+      tree_assign(n, best->col_ptr, best->blk_row, cd.C, cd.cta0_subtree, plan.ta);
+      if (tree_smem_estimate(n, best->col_ptr, best->blk_row, plan.ta) <= kTreeMaxSmem) { plan.want_tree = true; break; }
+    }
+    if (!plan.want_tree) s.tree.why_not = "estimated shared memory exceeds the cluster";
+    if (plan.want_tree) {
       perm_tree.resize(n);
-      for (int q = 0; q < n; ++q) perm_tree[q] = (*best_perm)[ta.order[q]];
-      f_tree = Factor{};
+      for (int q = 0; q < n; ++q) perm_tree[q] = (*best_perm)[plan.ta.order[q]];
       if (!symbolic_factor(n, adj, perm_tree, f_tree, err, false)) return false;
       if (f_tree.n_blocks != best->n_blocks) { err = "internal: re-ordered factor has different fill"; return false; }
-      build_tree_program(n, f_tree.col_ptr, f_tree.blk_row, f_tree.row_ptr, f_tree.row_blk, f_tree.row_col, ta, s.tree);
-      if (s.tree.ok) break;
+      best = &f_tree; best_perm = &perm_tree; plan.have_tasks = false;
     }
-    if (s.tree.ok) { best = &f_tree; best_perm = &perm_tree; have_tasks = false; }
   }
-  const bool need_level_program = !s.tree.ok;
-  if (need_level_program && !have_tasks) {
-    const std::vector<int> p = *best_perm;
-    if (!symbolic_factor(n, adj, p, *best, err, true)) return false;
-  }
-  perm_out = *best_perm;
+  plan.perm = *best_perm;
   s.n_schur_blocks = best->n_schur;
   s.n_blocks = best->n_blocks; s.n_levels = best->n_levels; s.n_tasks = (int)best->task_dst.size();
   s.est_solver_cycles = best->est_cycles;
@@ -653,8 +665,26 @@ bool plan_reduced_solver(int n, const std::vector<std::vector<int>> &adj, Struct
   s.level_ptr.swap(best->level_ptr); s.level_col.swap(best->level_col);
   s.ltask_ptr.swap(best->ltask_ptr); s.task_dst.swap(best->task_dst); s.task_pos.swap(best->task_pos); s.task_pair_ptr.swap(best->task_pair_ptr);
   s.pair_a.swap(best->pair_a); s.pair_b.swap(best->pair_b);
-  if (s.tree.ok) s.solve_cluster = s.tree.C;
   return true;
+}
+
+// The solver program: the subtree-per-CTA program of k_tree_solve, else (it does not fit, or SSBA_SOLVER=level)
+// the level program of k_reduced_solve with its task lists.  Reads the factor pattern of `s`, writes only
+// tree / prog / prog_ptr / task lists / solver_* / solve_cluster: build_structure runs it on a thread of its own.
+void finish_solver_program(int n, const std::vector<std::vector<int>> &adj, Structure &s, SolverPlan &plan) {
+  if (plan.want_tree) build_tree_program(n, s.col_ptr, s.blk_row, s.row_ptr, s.row_blk, s.row_col, plan.ta, s.tree);
+  if (s.tree.ok) { s.solve_cluster = s.tree.C; return; }
+  if (!plan.have_tasks) {
+    Factor f;
+    std::string err;
+    if (!symbolic_factor(n, adj, plan.perm, f, err, true)) return;  // cannot fail: the same pattern was factored before
+    s.n_tasks = (int)f.task_dst.size();
+    s.est_solver_cycles = f.est_cycles;
+    s.ltask_ptr.swap(f.ltask_ptr); s.task_dst.swap(f.task_dst); s.task_pos.swap(f.task_pos); s.task_pair_ptr.swap(f.task_pair_ptr);
+    s.pair_a.swap(f.pair_a); s.pair_b.swap(f.pair_b);
+    plan.have_tasks = true;
+  }
+  build_solver_program(s);
 }
 
 }  // namespace
@@ -775,16 +805,6 @@ void reset_keep_capacity(Structure &s) {
   s.est_solver_cycles = 0.0;
   s.n_edges_total = 0;
 }
-struct SectionTimer {  // SSBA_TIMING=1: wall time of the sections of build_structure on stderr
-  bool on = std::getenv("SSBA_TIMING") != nullptr;
-  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
-  void mark(const char *name) {
-    if (!on) return;
-    const auto n = std::chrono::steady_clock::now();
-    std::fprintf(stderr, "[ssba]   %-26s %.3f ms\n", name, std::chrono::duration<double, std::milli>(n - t).count());
-    t = n;
-  }
-};
 }  // namespace
 
 bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std::string &err,
@@ -926,14 +946,20 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   }
 
   tm.mark("co-visibility");
-  // ---- elimination order, symbolic factorisation and the solver program over q
+  // ---- elimination order and symbolic factorisation over q (the solver program follows on its own thread)
+  SolverPlan solver_plan;
   {
-    std::vector<int> perm;  // q -> free pose index
-    if (!plan_reduced_solver(n, adj, s, perm, err)) return false;
+    if (!plan_reduced_solver(n, adj, s, solver_plan, err)) return false;
+    const std::vector<int> &perm = solver_plan.perm;  // q -> free pose index
     s.q_of_pose.assign(NK, -1);
     s.pose_of_q.resize(n);
     for (int q = 0; q < n; ++q) { s.q_of_pose[free_pose_rows[perm[q]]] = q; s.pose_of_q[q] = free_pose_rows[perm[q]]; }
   }
+  // The solver program (serial, the longest single piece of host work left) is built on a thread
+  // of its own while this one goes on with the landmark / pair / chunk / unit lists: it reads the factor
+  // pattern only and writes tree / prog / prog_ptr / task lists / solver_* only.
+  std::thread program_thread([&] { finish_solver_program(n, adj, s, solver_plan); });
+  struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{program_thread};
   auto find_block = [&](int row, int col) -> int {  // row >= col
     const int *b0 = s.blk_row.data() + s.col_ptr[col], *b1 = s.blk_row.data() + s.col_ptr[col + 1];
     const int *it = std::lower_bound(b0, b1, row);
@@ -1117,11 +1143,6 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   // the per-edge / per-pair arrays are final: the caller may start uploading them while the
   // solver program and the small index lists are still being built
   if (on_edges_ready) (*on_edges_ready)();
-  // The solver program (serial, the longest single piece of host work left) is built on a thread
-  // of its own while this one goes on with the chunk / unit / partial lists: it reads the factor
-  // structure only and writes prog / prog_ptr / solver_* only.
-  std::thread program_thread([&s] { if (!s.tree.ok) build_solver_program(s); });
-  struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{program_thread};
   // ---- CTAs of the per-pair kernels: runs of whole landmarks with <= kLinPairs pairs
   {
     s.lchunk_slot.assign(1, 0);
@@ -1250,8 +1271,10 @@ bool build_solver_structure(int n, const std::vector<std::vector<int>> &adj, Str
                             std::string &err) {
   reset_keep_capacity(s);
   s.n_fp = n;
-  if (!plan_reduced_solver(n, adj, s, perm_out, err)) return false;
-  if (!s.tree.ok) build_solver_program(s);
+  SolverPlan plan;
+  if (!plan_reduced_solver(n, adj, s, plan, err)) return false;
+  finish_solver_program(n, adj, s, plan);
+  perm_out = plan.perm;
   return true;
 }
 
@@ -1268,6 +1291,35 @@ void parallel_copy(const std::vector<CopyJob> &jobs) {
       pieces.push_back({(char *)j.dst + o, (const char *)j.src + o, std::min<size_t>(256u << 10, j.bytes - o)});
   pool.run(T, [&](int t, int TT) {
     for (size_t i = t; i < pieces.size(); i += TT) std::memcpy(pieces[i].d, pieces[i].s, pieces[i].n);
+  });
+}
+
+bool parallel_equal(const std::vector<CopyJob> &jobs) {
+  size_t total = 0;
+  for (auto &j : jobs) total += j.bytes;
+  HostPool &pool = HostPool::get();
+  const int T = total >= (1u << 20) ? pool.size() : 1;
+  struct Piece { const char *a, *b; size_t n; };
+  std::vector<Piece> pieces;
+  for (auto &j : jobs)
+    for (size_t o = 0; o < j.bytes; o += (256u << 10))
+      pieces.push_back({(const char *)j.dst + o, (const char *)j.src + o, std::min<size_t>(256u << 10, j.bytes - o)});
+  std::atomic<int> differ{0};
+  pool.run(T, [&](int t, int TT) {
+    for (size_t i = t; i < pieces.size() && !differ.load(std::memory_order_relaxed); i += TT)
+      if (std::memcmp(pieces[i].a, pieces[i].b, pieces[i].n) != 0) differ.store(1, std::memory_order_relaxed);
+  });
+  return differ.load() == 0;
+}
+
+// dst[k * i .. k * i + k) = src[k * idx[i] ..] for i < n (k doubles per element), on the host thread pool
+void parallel_gather_doubles(double *dst, const double *src, const int32_t *idx, size_t n, int k) {
+  HostPool &pool = HostPool::get();
+  const int T = n >= 50000 ? pool.size() : 1;
+  pool.run(T, [&](int t, int TT) {
+    int b, e; split_range(t, TT, (int)n, b, e);
+    if (k == 2) for (int i = b; i < e; ++i) { const size_t o = 2 * (size_t)idx[i]; dst[2 * (size_t)i] = src[o]; dst[2 * (size_t)i + 1] = src[o + 1]; }
+    else for (int i = b; i < e; ++i) for (int u = 0; u < k; ++u) dst[(size_t)k * i + u] = src[(size_t)k * idx[i] + u];
   });
 }
 

@@ -137,6 +137,8 @@ void set_ranks_on_host(int n);
 // memcpy of several regions on the host thread pool of the structure builder
 struct CopyJob { void *dst; const void *src; size_t bytes; };
 void parallel_copy(const std::vector<CopyJob> &jobs);
+bool parallel_equal(const std::vector<CopyJob> &jobs);  // every job: dst[0, bytes) == src[0, bytes)
+void parallel_gather_doubles(double *dst, const double *src, const int32_t *idx, size_t n, int k);
 
 // Which rank owns which landmark under the sharding rule of build_structure:
 // owner[point row] = rank, or -1 for landmarks without an active edge.

@@ -119,6 +119,41 @@ void tree_assign(int n, const std::vector<int32_t> &col_ptr, const std::vector<i
   for (int q = 0; q < n; ++q) { const int j = a.order[q]; a.cta[q] = cta[j]; a.step[q] = step[j]; a.top[q] = top[j]; }
 }
 
+// Upper estimate of the dynamic shared memory build_tree_program will need under an assignment (pattern in
+// the OLD order, `old_of` = a.order): exact for the factor blocks and vectors, bounds for the contribution
+// slots and the program.  Lets the caller pick a cluster shape before the program itself is built (which
+// happens off the critical path of the structure build).
+size_t tree_smem_estimate(int n, const std::vector<int32_t> &col_ptr, const std::vector<int32_t> &blk_row, const TreeAssign &a) {
+  const int C = a.C;
+  std::vector<double> words(C, kTH_Words + 64.0);
+  std::vector<long long> nblk(C, 0), ncols(C, 0), nbound(C, 0);
+  std::vector<int> stamp(n, -1);
+  std::vector<int> new_of(n);
+  for (int q = 0; q < n; ++q) new_of[a.order[q]] = q;
+  for (int q = 0; q < n; ++q) {
+    const int j = a.order[q], c = a.cta[q];
+    const int m = col_ptr[j + 1] - col_ptr[j] - 1;
+    nblk[c] += m + 1; ++ncols[c];
+    words[c] += 3.6 * (0.5 * m * (m + 1) + m) + 2.4 * (m + 1) + 6 + m;
+    if (c)
+      for (int b = col_ptr[j] + 1; b < col_ptr[j + 1]; ++b) {
+        const int i = blk_row[b];
+        if (a.top[new_of[i]] && stamp[i] != c) { stamp[i] = c; ++nbound[c]; }
+      }
+  }
+  size_t worst = 0;
+  for (int c = 0; c < C; ++c) {
+    words[c] += 8.0 * (a.steps_a[c] + (c == 0 ? a.steps_b : 0));
+    if (c) { words[0] += (double)(nbound[c] * (nbound[c] + 1) / 2 + nbound[c]); words[c] += (double)nbound[c]; }
+  }
+  for (int c = 0; c < C; ++c) {
+    const long long contrib = c ? 36 * (nbound[c] * (nbound[c] + 1) / 2) + 6 * nbound[c] : 0;
+    const size_t bytes = 8 * (size_t)(36 * nblk[c] + 12 * ncols[c] + contrib) + 4 * (size_t)words[c] + kTreeMiscBytes + 64;
+    worst = std::max(worst, bytes);
+  }
+  return worst;
+}
+
 namespace {
 
 struct Item { int dest, nrows, p0, p1; };   // product item: dest -= sum over pairs of A B^T (row-wise)

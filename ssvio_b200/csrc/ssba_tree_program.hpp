@@ -81,6 +81,7 @@ void tree_assign(int n, const std::vector<int32_t> &col_ptr, const std::vector<i
 // largest cluster k_tree_solve may use on this device (ssba_create asks the device once; 8 until then)
 void set_tree_cluster_cap(int cap);
 int tree_cluster_cap();
+size_t tree_smem_estimate(int n, const std::vector<int32_t> &col_ptr, const std::vector<int32_t> &blk_row, const TreeAssign &a);
 // col_ptr .. row_col: the symbolic factor under the order of tree_assign (Structure fields of the same names)
 bool build_tree_program(int n, const std::vector<int32_t> &col_ptr, const std::vector<int32_t> &blk_row,
                         const std::vector<int32_t> &row_ptr, const std::vector<int32_t> &row_blk,

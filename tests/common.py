@@ -45,3 +45,28 @@ def converging_prefix(trace, tol=1e-9):
         prev = chi
         n += 1
     return n
+
+
+# ---- failed factorisations (tests/golden/make_golden_nonpd.py, tests/test_gpu_nonpd.py)
+# name -> (synth config, fraction of edges with information neg * I, neg, user lambda init, iterations)
+NONPD_CASES = {
+    "lambda30_small": ("small", 0.0, 0.0, 1e-30, 3),
+    "lambda30_cfg2": ("cfg2", 0.0, 0.0, 1e-30, 3),
+    "indef_cfg1": ("cfg1", 0.01, -1.0, 1e-3, 4),
+    "indef_cfg2": ("cfg2", 0.01, -1.0, 1e-3, 3),
+    "indef_cfg3": ("cfg3", 0.002, -1.0, 1e-3, 2),
+}
+
+
+def nonpd_case_inputs(name):
+    """(graph, per-edge information or None, user lambda init, iterations) of a NONPD_CASES recipe."""
+    cfg, frac, neg, ul, iters = NONPD_CASES[name]
+    g = synth.make_config(cfg, seed=42)
+    g.iters = iters
+    info = None
+    if frac > 0:
+        rng = np.random.default_rng(5)
+        info = np.tile(np.array([1.0, 0.0, 1.0]), (g.n_edges, 1))
+        info[rng.random(g.n_edges) < frac] = np.array([neg, 0.0, neg])
+        info = np.ascontiguousarray(info)
+    return g, info, ul, iters
