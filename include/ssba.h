@@ -34,7 +34,9 @@ extern "C" {
 #endif
 
 #define SSBA_VERSION_MAJOR 0
-#define SSBA_VERSION_MINOR 2  /* 0.2: + ssba_pose_only_optimize, ssba_pose_graph_optimize, ssba_set_profiling */
+#define SSBA_VERSION_MINOR 3  /* 0.2: + ssba_pose_only_optimize, ssba_pose_graph_optimize, ssba_set_profiling;
+                                0.3: + ssba_drop_structure (structure reuse), ssba_pose_only_optimize_loop, solver fields of
+                                ssba_problem_info */
 
 #define SSBA_MAX_ITER_RECORDS 128
 #define SSBA_MAX_CAMERAS 8
@@ -271,6 +273,17 @@ ssba_status ssba_plan_shards(int32_t n_poses, const uint8_t *pose_fixed, int32_t
  * host memory; the call is synchronous.  Runs on the handle's device and stream; the handle's
  * bundle-adjustment problem, if any, is untouched. */
 ssba_status ssba_pose_only_optimize(ssba_handle *h, const double K[9], int32_t n_frames,
+                                    const int32_t *feat_ptr, const double *poses_in, const double *xyz,
+                                    const double *uv, int32_t rounds, int32_t iters, double chi2_threshold,
+                                    double *poses_out, uint8_t *outlier_out, int32_t *n_inliers_out,
+                                    double *chi2_out);
+
+/* The loop closer's caller of the same pose-only LM: LoopClosing::OptimizeCurrentPose()
+ * (src/ssvio/loopclosing.cpp:245-351).  Same vertex, edges, kernel and round loop, preceded by ONE more
+ * initializeOptimization(); optimize(iters) with every feature active and no classification (:302-303).
+ * Arguments as for ssba_pose_only_optimize (a "frame" here is a loop candidate: the current key-frame's
+ * features against the loop key-frame's map points; n_inliers_out = the matches that survive, :337-343). */
+ssba_status ssba_pose_only_optimize_loop(ssba_handle *h, const double K[9], int32_t n_frames,
                                     const int32_t *feat_ptr, const double *poses_in, const double *xyz,
                                     const double *uv, int32_t rounds, int32_t iters, double chi2_threshold,
                                     double *poses_out, uint8_t *outlier_out, int32_t *n_inliers_out,

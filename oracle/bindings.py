@@ -126,15 +126,16 @@ class RefOracle(_OracleBase):
                     rounds=rd.value, outliers=no.value)
 
 
-def ref_pose_only(lib, batch, rounds=4, iters=10, chi2_threshold=5.991):
-    """FrontEnd::EstimateCurrentPose through the compiled reference (ref_harness.cpp ssba_ref_pose_only)."""
+def ref_pose_only(lib, batch, rounds=4, iters=10, chi2_threshold=5.991, pre_rounds=0):
+    """FrontEnd::EstimateCurrentPose (pre_rounds = 0) / LoopClosing::OptimizeCurrentPose (pre_rounds = 1) through the
+    compiled reference (ref_harness.cpp ssba_ref_pose_only_ex)."""
     nf, n = batch.n_frames, batch.xyz.shape[0]
     poses = np.empty((nf, 7)); flags = np.zeros(n, np.uint8); n_in = np.zeros(nf, np.int32); chi = np.zeros(nf)
     fp = np.ascontiguousarray(batch.feat_ptr, np.int32)
-    rc = lib.ssba_ref_pose_only(
+    rc = lib.ssba_ref_pose_only_ex(
         _p(np.ascontiguousarray(batch.K), C.c_double), nf, _p(fp, C.c_int32),
         _p(np.ascontiguousarray(batch.poses), C.c_double), _p(np.ascontiguousarray(batch.xyz), C.c_double),
-        _p(np.ascontiguousarray(batch.uv), C.c_double), int(rounds), int(iters), C.c_double(chi2_threshold),
+        _p(np.ascontiguousarray(batch.uv), C.c_double), int(rounds), int(iters), C.c_double(chi2_threshold), C.c_int32(pre_rounds),
         _p(poses, C.c_double), _p(flags, C.c_uint8), _p(n_in, C.c_int32), _p(chi, C.c_double))
     if rc != 0:
         raise RuntimeError(f"ssba_ref_pose_only failed rc={rc}")

@@ -67,8 +67,11 @@ def _oplus(T, d):
     return synth.se3_mul(synth.se3_exp(d)[0], T)
 
 
-def optimize_frame(K, T0, xyz, uv, rounds=4, iters=10, chi2_threshold=5.991):
-    """Returns (T, outlier flags, n_inliers, robust chi2 after the last optimize)."""
+def optimize_frame(K, T0, xyz, uv, rounds=4, iters=10, chi2_threshold=5.991, pre_rounds=0):
+    """Returns (T, outlier flags, n_inliers, robust chi2 after the last optimize).
+    pre_rounds: initializeOptimization(); optimize(iters) calls BEFORE the classified rounds, with every edge
+    and the kernel on: 0 = FrontEnd::EstimateCurrentPose, 1 = LoopClosing::OptimizeCurrentPose
+    (src/ssvio/loopclosing.cpp:302-303)."""
     K = np.asarray(K, float).reshape(9)
     T = np.array(T0, float)
     n = xyz.shape[0]
@@ -78,7 +81,7 @@ def optimize_frame(K, T0, xyz, uv, rounds=4, iters=10, chi2_threshold=5.991):
     err = np.zeros((n, 2))          # the edges' _error members
     chi_last, cnt_out = 0.0, 0
     tau, good_lo, good_hi, max_trials = 1e-5, 1.0 / 3.0, 2.0 / 3.0, 10
-    for rnd in range(rounds):
+    for rnd in range(-pre_rounds, rounds):
         act = ~level1                                   # initializeOptimization(): level-0 edges
         if act.any():
             lam, ni = 0.0, 2.0
@@ -124,6 +127,8 @@ def optimize_frame(K, T0, xyz, uv, rounds=4, iters=10, chi2_threshold=5.991):
                 if qmax == max_trials or rho == 0 or stop:
                     break                                # Terminate: optimize() leaves its loop
             chi_last = _robust_chi2(err[act], robust)    # of the _error members, like activeRobustChi2()
+        if rnd < 0:
+            continue                                     # loopclosing.cpp:302-303: no classification yet
         # frontend.cpp:243-262
         if outlier.any():
             err[outlier], _ = _errors(K, T, xyz[outlier], uv[outlier])
@@ -136,11 +141,11 @@ def optimize_frame(K, T0, xyz, uv, rounds=4, iters=10, chi2_threshold=5.991):
     return T, outlier.astype(np.uint8), n - cnt_out, chi_last
 
 
-def optimize(K, feat_ptr, poses, xyz, uv, rounds=4, iters=10, chi2_threshold=5.991):
+def optimize(K, feat_ptr, poses, xyz, uv, rounds=4, iters=10, chi2_threshold=5.991, pre_rounds=0):
     nf = len(feat_ptr) - 1
     out_T, out_flag = np.empty((nf, 7)), np.zeros(xyz.shape[0], np.uint8)
     n_in, chi = np.zeros(nf, np.int32), np.zeros(nf)
     for f in range(nf):
         a, b = feat_ptr[f], feat_ptr[f + 1]
-        out_T[f], out_flag[a:b], n_in[f], chi[f] = optimize_frame(K, poses[f], xyz[a:b], uv[a:b], rounds, iters, chi2_threshold)
+        out_T[f], out_flag[a:b], n_in[f], chi[f] = optimize_frame(K, poses[f], xyz[a:b], uv[a:b], rounds, iters, chi2_threshold, pre_rounds)
     return out_T, out_flag, n_in, chi

@@ -299,11 +299,13 @@ extern "C" int ssba_ref_optimize(
 // at a time exactly like the front-end thread does it: the solver stack of :188-193, the vertex
 // of :196-203, the edges of :206-231 (identity information, default-delta Huber), the round loop
 // of :235-270.  features[i]->is_outlier_ lives in `outlier`.
-extern "C" int ssba_ref_pose_only(const double K9[9], int32_t n_frames, const int32_t *feat_ptr,
-                                  const double *poses_qt, const double *xyz, const double *uv,
-                                  int32_t rounds, int32_t iters, double chi2_threshold,
-                                  double *poses_out, uint8_t *outlier_out, int32_t *n_inliers_out,
-                                  double *chi2_out) {
+// pre_rounds = 1: LoopClosing::OptimizeCurrentPose (src/ssvio/loopclosing.cpp:245-351), which differs from the
+// front-end's loop by one unclassified initializeOptimization(); optimize(10) before the rounds (:302-303)
+extern "C" int ssba_ref_pose_only_ex(const double K9[9], int32_t n_frames, const int32_t *feat_ptr,
+                                     const double *poses_qt, const double *xyz, const double *uv,
+                                     int32_t rounds, int32_t iters, double chi2_threshold, int32_t pre_rounds,
+                                     double *poses_out, uint8_t *outlier_out, int32_t *n_inliers_out,
+                                     double *chi2_out) {
   Eigen::Matrix3d K;
   K << K9[0], K9[1], K9[2], K9[3], K9[4], K9[5], K9[6], K9[7], K9[8];
   for (int f = 0; f < n_frames; ++f) {
@@ -336,6 +338,11 @@ extern "C" int ssba_ref_pose_only(const double K9[9], int32_t n_frames, const in
     }
     int cnt_outliers = 0;
     double chi_last = 0.0;
+    for (int pre = 0; pre < pre_rounds; ++pre) {  // loopclosing.cpp:302-303
+      optimizer.initializeOptimization();
+      optimizer.optimize(iters);
+      chi_last = optimizer.activeRobustChi2();
+    }
     for (int iteration = 0; iteration < rounds; iteration++) {
       optimizer.initializeOptimization();
       optimizer.optimize(iters);
@@ -361,6 +368,16 @@ extern "C" int ssba_ref_pose_only(const double K9[9], int32_t n_frames, const in
     if (chi2_out) chi2_out[f] = chi_last;
   }
   return 0;
+}
+
+
+extern "C" int ssba_ref_pose_only(const double K9[9], int32_t n_frames, const int32_t *feat_ptr,
+                                  const double *poses_qt, const double *xyz, const double *uv,
+                                  int32_t rounds, int32_t iters, double chi2_threshold,
+                                  double *poses_out, uint8_t *outlier_out, int32_t *n_inliers_out,
+                                  double *chi2_out) {
+  return ssba_ref_pose_only_ex(K9, n_frames, feat_ptr, poses_qt, xyz, uv, rounds, iters, chi2_threshold, 0, poses_out,
+                               outlier_out, n_inliers_out, chi2_out);
 }
 
 

@@ -84,6 +84,14 @@ int ssba_ref_pose_only(const double K[9], int32_t n_frames, const int32_t *feat_
                        double *poses_out, uint8_t *outlier_out, int32_t *n_inliers_out,
                        double *chi2_out);
 
+/* The same with `pre_rounds` unclassified initializeOptimization(); optimize(iters) calls before the rounds:
+ * pre_rounds = 1 is LoopClosing::OptimizeCurrentPose() (src/ssvio/loopclosing.cpp:245-351, the extra call at :302-303). */
+int ssba_ref_pose_only_ex(const double K[9], int32_t n_frames, const int32_t *feat_ptr,
+                          const double *poses_qt, const double *xyz, const double *uv,
+                          int32_t rounds, int32_t iters, double chi2_threshold, int32_t pre_rounds,
+                          double *poses_out, uint8_t *outlier_out, int32_t *n_inliers_out,
+                          double *chi2_out);
+
 /*
  * Pose-graph optimisation of LoopClosing::PoseGraphOptimization() (src/ssvio/loopclosing.cpp:458-594):
  * one VertexPose per key-frame (setMarginalized(false), some fixed), one EdgePoseGraph

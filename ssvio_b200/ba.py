@@ -34,7 +34,8 @@ ABI_SYMBOLS = [
     "ssba_set_edges", "ssba_initialize", "ssba_optimize", "ssba_step", "ssba_reset_state", "ssba_drop_structure",
     "ssba_get_poses", "ssba_get_points", "ssba_get_edge_errors", "ssba_chi2",
     "ssba_count_outliers", "ssba_optimize_rounds", "ssba_plan_shards", "ssba_set_profiling", "ssba_profile_get",
-    "ssba_profile_reset", "ssba_get_problem_info", "ssba_pose_only_optimize", "ssba_pose_graph_optimize",
+    "ssba_profile_reset", "ssba_get_problem_info", "ssba_pose_only_optimize", "ssba_pose_only_optimize_loop",
+    "ssba_pose_graph_optimize",
     "ssba_version",
 ]
 
@@ -130,6 +131,7 @@ def load_library():
     lib.ssba_plan_shards.argtypes = [C.c_int32, bp, C.c_int32, bp, C.c_int32, ip, ip, C.c_int32, ip]
     lib.ssba_pose_only_optimize.argtypes = [H, dp, C.c_int32, ip, dp, dp, dp, C.c_int32, C.c_int32, C.c_double,
                                             dp, bp, ip, dp]
+    lib.ssba_pose_only_optimize_loop.argtypes = lib.ssba_pose_only_optimize.argtypes
     lib.ssba_pose_graph_optimize.argtypes = [H, C.c_int32, dp, bp, C.c_int32, ip, ip, dp, C.c_int32, dp, C.POINTER(Report)]
     lib.ssba_set_profiling.argtypes = [H, C.c_int32]
     lib.ssba_profile_get.argtypes = [H, C.POINTER(Profile)]
@@ -336,15 +338,17 @@ class BundleAdjuster:
         self._check(self.lib.ssba_profile_reset(self._h))
 
     # -- pose-only LM of the front-end (frontend.cpp:184-260), batched over frames
-    def pose_only_optimize(self, batch, rounds=4, iters=10, chi2_threshold=5.991):
+    def pose_only_optimize(self, batch, rounds=4, iters=10, chi2_threshold=5.991, loop_closing=False):
         """batch: ssvio_b200.synth.PoseOnlyBatch.  Returns (poses, outlier flags, inliers per frame,
-        robust chi2 per frame)."""
+        robust chi2 per frame).  loop_closing: the schedule of LoopClosing::OptimizeCurrentPose
+        (loopclosing.cpp:245-351: one unclassified optimize() before the rounds)."""
         nf, n = batch.n_frames, int(batch.xyz.shape[0])
         K, fp = _c(batch.K, np.float64), _c(batch.feat_ptr, np.int32)
         pin, xyz, uv = _c(batch.poses, np.float64), _c(batch.xyz, np.float64), _c(batch.uv, np.float64)
         poses, chi = np.empty((nf, 7)), np.zeros(nf)
         flags, n_in = np.zeros(n, np.uint8), np.zeros(nf, np.int32)
-        self._check(self.lib.ssba_pose_only_optimize(
+        fn = self.lib.ssba_pose_only_optimize_loop if loop_closing else self.lib.ssba_pose_only_optimize
+        self._check(fn(
             self._h, _p(K, C.c_double), nf, _p(fp, C.c_int32), _p(pin, C.c_double), _p(xyz, C.c_double),
             _p(uv, C.c_double), int(rounds), int(iters), float(chi2_threshold), _p(poses, C.c_double),
             _p(flags, C.c_uint8), _p(n_in, C.c_int32), _p(chi, C.c_double)))

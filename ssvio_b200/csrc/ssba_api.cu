@@ -954,10 +954,10 @@ ssba_status ssba_plan_shards(int32_t n_poses, const uint8_t *pose_fixed, int32_t
   return SSBA_OK;
 }
 
-ssba_status ssba_pose_only_optimize(ssba_handle *h, const double K[9], int32_t n_frames, const int32_t *feat_ptr,
-                                    const double *poses_in, const double *xyz, const double *uv, int32_t rounds,
-                                    int32_t iters, double chi2_threshold, double *poses_out, uint8_t *outlier_out,
-                                    int32_t *n_inliers_out, double *chi2_out) {
+static ssba_status pose_only_impl(ssba_handle *h, const double K[9], int32_t n_frames, const int32_t *feat_ptr,
+                                  const double *poses_in, const double *xyz, const double *uv, int32_t rounds,
+                                  int32_t iters, int32_t pre_rounds, double chi2_threshold, double *poses_out, uint8_t *outlier_out,
+                                  int32_t *n_inliers_out, double *chi2_out) {
   if (!h) return SSBA_ERR_INVALID_ARG;
   if (!K || n_frames < 0 || rounds < 0 || iters < 0 || (n_frames > 0 && (!feat_ptr || !poses_in || !poses_out)))
     return fail(h, SSBA_ERR_INVALID_ARG, "pose_only_optimize: bad arguments");
@@ -995,8 +995,8 @@ ssba_status ssba_pose_only_optimize(ssba_handle *h, const double K[9], int32_t n
   if (n) { std::memcpy(h->h_po + o_xyz, xyz, 24 * (size_t)n); std::memcpy(h->h_po + o_uv, uv, 16 * (size_t)n); }
   CUDA_TRY(h, cudaMemcpyAsync(h->d_po, h->h_po, up_bytes, cudaMemcpyHostToDevice, h->stream));
   char *d = h->d_po;
-  launch_pose_only(K, n_frames, rounds, iters, h->opt.max_trials_after_failure, chi2_threshold, h->opt.tau,
-                   h->opt.good_step_lower_scale, h->opt.good_step_upper_scale, (const int32_t *)(d + o_fp),
+  launch_pose_only(K, n_frames, rounds, iters, pre_rounds, h->opt.max_trials_after_failure, chi2_threshold, h->opt.tau,
+                   h->opt.good_step_lower_scale, h->opt.good_step_upper_scale, h->opt.user_lambda_init, (const int32_t *)(d + o_fp),
                    (const double *)(d + o_pin), (const double *)(d + o_xyz), (const double *)(d + o_uv), (double *)(d + o_err),
                    (uint8_t *)(d + o_flag), (double *)(d + o_pout), (double *)(d + o_chi), (int32_t *)(d + o_nin), h->stream);
   h->prof.kernel_launches += 1;
@@ -1008,6 +1008,22 @@ ssba_status ssba_pose_only_optimize(ssba_handle *h, const double K[9], int32_t n
   if (n_inliers_out) std::memcpy(n_inliers_out, h->h_po + o_nin, 4 * (size_t)n_frames);
   if (outlier_out && n) std::memcpy(outlier_out, h->h_po + o_flag, (size_t)n);
   return SSBA_OK;
+}
+
+ssba_status ssba_pose_only_optimize(ssba_handle *h, const double K[9], int32_t n_frames, const int32_t *feat_ptr,
+                                    const double *poses_in, const double *xyz, const double *uv, int32_t rounds,
+                                    int32_t iters, double chi2_threshold, double *poses_out, uint8_t *outlier_out,
+                                    int32_t *n_inliers_out, double *chi2_out) {
+  return pose_only_impl(h, K, n_frames, feat_ptr, poses_in, xyz, uv, rounds, iters, 0, chi2_threshold, poses_out, outlier_out,
+                        n_inliers_out, chi2_out);
+}
+
+ssba_status ssba_pose_only_optimize_loop(ssba_handle *h, const double K[9], int32_t n_frames, const int32_t *feat_ptr,
+                                         const double *poses_in, const double *xyz, const double *uv, int32_t rounds,
+                                         int32_t iters, double chi2_threshold, double *poses_out, uint8_t *outlier_out,
+                                         int32_t *n_inliers_out, double *chi2_out) {
+  return pose_only_impl(h, K, n_frames, feat_ptr, poses_in, xyz, uv, rounds, iters, 1, chi2_threshold, poses_out, outlier_out,
+                        n_inliers_out, chi2_out);
 }
 
 ssba_status ssba_pose_graph_optimize(ssba_handle *h, int32_t n_poses, const double *poses_in, const uint8_t *fixed,

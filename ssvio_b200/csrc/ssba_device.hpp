@@ -158,8 +158,8 @@ void launch_tree_solve(const DeviceProblem &P, cudaStream_t st);  // ssba_tree_s
 void fill_tree_dev(const TreeProgram &tp, const int32_t *d_prog, double *d_xchg, TreeDev &out);
 
 // batched pose-only LM (ssba_pose_only.cu): one warp per frame, everything in one launch
-void launch_pose_only(const double K[9], int n_frames, int rounds, int iters, int max_trials, double chi2_threshold,
-                      double tau, double good_lower, double good_upper, const int32_t *feat_ptr, const double *poses_in,
+void launch_pose_only(const double K[9], int n_frames, int rounds, int iters, int pre_rounds, int max_trials, double chi2_threshold,
+                      double tau, double good_lower, double good_upper, double user_lambda, const int32_t *feat_ptr, const double *poses_in,
                       const double *xyz, const double *uv, double *err, uint8_t *outlier, double *poses_out,
                       double *chi2_out, int32_t *n_inliers_out, cudaStream_t st);
 

@@ -12,6 +12,8 @@
 //   LinearSolverDense (a failed factorisation rejects)       g2o/solvers/dense/linear_solver_dense.h:56-118
 //   the round loop, chi2() > threshold, setLevel, kernel removal at round rounds - 2
 //                                                            src/ssvio/frontend.cpp:235-270
+//   LoopClosing::OptimizeCurrentPose (src/ssvio/loopclosing.cpp:245-351): the same loop after one more
+//       initializeOptimization(); optimize(10) with every edge and the kernel on (:302-303) = pre_rounds 1
 // The edges' _error members live in `err`: like in g2o they hold the errors of the LAST evaluated
 // trial (a rejected trial does not restore them), and that is what the outlier test reads.
 #include <cfloat>
@@ -83,8 +85,8 @@ __device__ __forceinline__ bool po_solve(const double *Hu, double lambda, const 
 
 struct PoseOnlyArgs {
   double K[9];
-  int n_frames, rounds, iters, max_trials;
-  double chi2_threshold, tau, good_lower, good_upper;
+  int n_frames, rounds, iters, max_trials, pre_rounds;
+  double chi2_threshold, tau, good_lower, good_upper, user_lambda;
   const int32_t *feat_ptr;
   const double *poses_in, *xyz, *uv;
   double *err;        // N x 2 scratch: the edges' _error
@@ -125,12 +127,13 @@ __global__ void __launch_bounds__(32 * kPoWarps) k_pose_only(const PoseOnlyArgs 
     }
     return warp_allsum(s);
   };
-  for (int rnd = 0; rnd < A.rounds; ++rnd) {
+  for (int rnd = -A.pre_rounds; rnd < A.rounds; ++rnd) {
     int n_act = 0;
     for (int i = lane; i < n; i += 32) n_act += outl[i] ? 0 : 1;
     n_act = __reduce_add_sync(0xffffffffu, n_act);
     if (n_act > 0) {
       double lambda = 0.0, ni = 2.0;
+      if (A.iters <= 0) chi_last = eval(T);  // no iteration will evaluate the active edges: the test below reads err
       for (int it = 0; it < A.iters; ++it) {
         const double cur0 = eval(T);
         // buildSystem: H (upper triangle) and b over the active edges
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(32 * kPoWarps) k_pose_only(const PoseOnlyArgs 
           double m = 0.0;
 #pragma unroll
           for (int d = 0; d < 6; ++d) m = fmax(m, fabs(Hu[d * 6 - d * (d - 1) / 2]));
-          lambda = A.tau * m; ni = 2.0;
+          lambda = A.user_lambda > 0 ? A.user_lambda : A.tau * m; ni = 2.0;
         }
         double cur = cur0, rho = 0.0;
         int qmax = 0;
@@ -203,6 +206,7 @@ __global__ void __launch_bounds__(32 * kPoWarps) k_pose_only(const PoseOnlyArgs 
         if (qmax == A.max_trials || rho == 0 || stop) break;  // Terminate
       }
     }
+    if (rnd < 0) continue;  // loopclosing.cpp:302-303: an optimize() without classification
     // re-classification (frontend.cpp:243-262)
     cnt_out = 0;
     for (int i = lane; i < n; i += 32) {
@@ -228,15 +232,15 @@ __global__ void __launch_bounds__(32 * kPoWarps) k_pose_only(const PoseOnlyArgs 
 
 }  // namespace
 
-void launch_pose_only(const double K[9], int n_frames, int rounds, int iters, int max_trials, double chi2_threshold,
-                      double tau, double good_lower, double good_upper, const int32_t *feat_ptr, const double *poses_in,
+void launch_pose_only(const double K[9], int n_frames, int rounds, int iters, int pre_rounds, int max_trials, double chi2_threshold,
+                      double tau, double good_lower, double good_upper, double user_lambda, const int32_t *feat_ptr, const double *poses_in,
                       const double *xyz, const double *uv, double *err, uint8_t *outlier, double *poses_out,
                       double *chi2_out, int32_t *n_inliers_out, cudaStream_t st) {
   if (n_frames <= 0) return;
   PoseOnlyArgs A;
   for (int i = 0; i < 9; ++i) A.K[i] = K[i];
-  A.n_frames = n_frames; A.rounds = rounds; A.iters = iters; A.max_trials = max_trials;
-  A.chi2_threshold = chi2_threshold; A.tau = tau; A.good_lower = good_lower; A.good_upper = good_upper;
+  A.n_frames = n_frames; A.rounds = rounds; A.iters = iters; A.max_trials = max_trials; A.pre_rounds = pre_rounds > 0 ? pre_rounds : 0;
+  A.chi2_threshold = chi2_threshold; A.tau = tau; A.good_lower = good_lower; A.good_upper = good_upper; A.user_lambda = user_lambda;
   A.feat_ptr = feat_ptr; A.poses_in = poses_in; A.xyz = xyz; A.uv = uv; A.err = err; A.outlier = outlier;
   A.poses_out = poses_out; A.chi2_out = chi2_out; A.n_inliers_out = n_inliers_out;
   k_pose_only<<<(n_frames + kPoWarps - 1) / kPoWarps, 32 * kPoWarps, 0, st>>>(A);

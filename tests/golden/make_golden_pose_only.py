@@ -19,6 +19,9 @@ for tag, (nf, nfeat, seed, kw) in {"a": (16, 150, 3, {}), "b": (6, 40, 9, dict(o
                                    "c": (4, 300, 21, dict(pose_sigma_t=0.3, pose_sigma_r=0.03))}.items():
     b = synth.make_pose_only(nf, nfeat, seed=seed, **kw)
     poses, flags, n_in, chi = bindings.ref_pose_only(ref.lib, b)
+    # the loop closer's schedule (LoopClosing::OptimizeCurrentPose, src/ssvio/loopclosing.cpp:245-351)
+    lposes, lflags, ln_in, lchi = bindings.ref_pose_only(ref.lib, b, pre_rounds=1)
+    out.update({f"{tag}_loop_poses": lposes, f"{tag}_loop_outlier": lflags, f"{tag}_loop_inliers": ln_in, f"{tag}_loop_chi2": lchi})
     out.update({f"{tag}_K": b.K, f"{tag}_feat_ptr": b.feat_ptr, f"{tag}_poses": b.poses, f"{tag}_xyz": b.xyz,
                 f"{tag}_uv": b.uv, f"{tag}_ref_poses": poses, f"{tag}_ref_outlier": flags,
                 f"{tag}_ref_inliers": n_in, f"{tag}_ref_chi2": chi})

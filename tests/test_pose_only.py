@@ -22,7 +22,10 @@ def golden_batches():
         b = synth.PoseOnlyBatch(K=z[f"{tag}_K"], feat_ptr=z[f"{tag}_feat_ptr"], poses=z[f"{tag}_poses"],
                                 xyz=z[f"{tag}_xyz"], uv=z[f"{tag}_uv"])
         yield tag, b, dict(poses=z[f"{tag}_ref_poses"], outlier=z[f"{tag}_ref_outlier"],
-                           inliers=z[f"{tag}_ref_inliers"], chi2=z[f"{tag}_ref_chi2"])
+                           inliers=z[f"{tag}_ref_inliers"], chi2=z[f"{tag}_ref_chi2"],
+                           # the loop closer's schedule (LoopClosing::OptimizeCurrentPose, loopclosing.cpp:245-351)
+                           loop=dict(poses=z[f"{tag}_loop_poses"], outlier=z[f"{tag}_loop_outlier"],
+                                     inliers=z[f"{tag}_loop_inliers"], chi2=z[f"{tag}_loop_chi2"]))
 
 
 def check(tag, got, want, pose_atol=1e-7):
@@ -37,6 +40,7 @@ def test_numpy_restatement_matches_reference_fixtures():
     from oracle import pose_only_np
     for tag, b, want in golden_batches():
         check(tag, pose_only_np.optimize(b.K, b.feat_ptr, b.poses, b.xyz, b.uv), want)
+        check(tag + " (loop closing)", pose_only_np.optimize(b.K, b.feat_ptr, b.poses, b.xyz, b.uv, pre_rounds=1), want["loop"])
 
 
 def test_generator_is_reproducible():
@@ -66,6 +70,7 @@ def test_cuda_matches_reference_fixtures(ssba_lib):
     with ba.BundleAdjuster() as opt:
         for tag, b, want in golden_batches():
             check(tag, opt.pose_only_optimize(b), want)
+            check(tag + " (loop closing)", opt.pose_only_optimize(b, loop_closing=True), want["loop"])
 
 
 @pytest.mark.gpu
