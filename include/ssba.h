@@ -130,6 +130,17 @@ typedef struct ssba_profile {
   double ms_allreduce;      /* multi-GPU only                                          */
   int64_t n_linearize, n_schur, n_reduced_solve, n_update_chi2, n_allreduce;
   int64_t kernel_launches;  /* kernels launched by libssba since the reset             */
+  /* the remaining G2OBatchStatistics fields (always filled, profile on or off) */
+  int64_t levenberg_iterations;      /* levenbergIterations summed over the outer iterations since the reset */
+  int64_t outer_iterations;          /* solve() calls (outer iterations) since the reset                      */
+  int64_t cholesky_nnz;              /* choleskyNNZ: scalar non-zeros of the factor of the reduced system     */
+  int32_t hessian_pose_dimension;    /* hessianPoseDimension = 6 x free poses                                 */
+  int32_t hessian_landmark_dimension;/* hessianLandmarkDimension = 3 x free landmarks                         */
+  double ms_symbolic_decomposition;  /* timeSymbolicDecomposition: host, ordering + symbolic factorisation +  */
+                                     /* solver program of the last structure build                             */
+  double ms_numeric_decomposition;   /* timeNumericDecomposition + timeLinearSolution = ms_reduced_solve: the  */
+                                     /* device solver factors and substitutes in one kernel                    */
+  double ms_structure_build;         /* buildStructure equivalent: host wall time of the last structure build  */
 } ssba_profile;
 
 /* ---- life cycle ------------------------------------------------------------------ */
@@ -233,6 +244,21 @@ ssba_status ssba_chi2(ssba_handle *h, double *plain, double *robust);
  * are outliers.  Evaluated on the device at the current estimate. */
 ssba_status ssba_count_outliers(ssba_handle *h, double chi2_threshold,
                                 int64_t *n_outliers, int64_t *n_inliers);
+
+/* The per-edge outlier flags of the culling step (backend.cpp:205-227: `ef.first->chi2() > chi2_th`), evaluated on
+ * the device at the current estimate: mask_out[e] = 1 when the plain chi2 of edge e (caller's addEdge order)
+ * exceeds the threshold, else 0 (edges between two fixed vertices are never active: 0).  n_edges bytes come back
+ * instead of the 16 n_edges of ssba_get_edge_errors.  n_outliers may be NULL. */
+ssba_status ssba_get_outlier_mask(ssba_handle *h, double chi2_threshold, uint8_t *mask_out, int64_t *n_outliers);
+
+/* SparseOptimizer::setForceStopFlag (sparse_optimizer.h:183-187): while the flag is raised, optimize()/step() stop
+ * like the reference does -- the trial loop of OptimizationAlgorithmLevenberg::solve ends after the running trial
+ * (optimization_algorithm_levenberg.cpp:145: `!_optimizer->terminate()`) and optimize() starts no further iteration
+ * (sparse_optimizer.cpp:388); raised before the call, optimize() returns 0 iterations.  ssba_request_stop may be
+ * called from ANOTHER thread while ssba_optimize runs on the handle (it only posts a 4-byte copy on a side
+ * stream); the flag stays up until ssba_clear_stop. */
+ssba_status ssba_request_stop(ssba_handle *h);
+ssba_status ssba_clear_stop(ssba_handle *h);
 
 /* The optimisation loop of Backend::OptimizeActiveMap (backend.cpp:175-203) with the graph
  * resident on the device between rounds: up to `max_rounds` (5) rounds of

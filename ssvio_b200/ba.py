@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "ssba_nccl_unique_id", "ssba_set_cameras", "ssba_set_poses", "ssba_set_points",
     "ssba_set_edges", "ssba_initialize", "ssba_optimize", "ssba_step", "ssba_reset_state", "ssba_drop_structure",
     "ssba_get_poses", "ssba_get_points", "ssba_get_edge_errors", "ssba_chi2",
-    "ssba_count_outliers", "ssba_optimize_rounds", "ssba_plan_shards", "ssba_set_profiling", "ssba_profile_get",
+    "ssba_count_outliers", "ssba_get_outlier_mask", "ssba_request_stop", "ssba_clear_stop", "ssba_optimize_rounds", "ssba_plan_shards", "ssba_set_profiling", "ssba_profile_get",
     "ssba_profile_reset", "ssba_get_problem_info", "ssba_pose_only_optimize", "ssba_pose_only_optimize_loop",
     "ssba_pose_graph_optimize",
     "ssba_version",
@@ -72,7 +72,11 @@ class Profile(C.Structure):
                 ("ms_reduced_solve", C.c_double), ("ms_update_chi2", C.c_double),
                 ("ms_allreduce", C.c_double), ("n_linearize", C.c_int64), ("n_schur", C.c_int64),
                 ("n_reduced_solve", C.c_int64), ("n_update_chi2", C.c_int64),
-                ("n_allreduce", C.c_int64), ("kernel_launches", C.c_int64)]
+                ("n_allreduce", C.c_int64), ("kernel_launches", C.c_int64),
+                ("levenberg_iterations", C.c_int64), ("outer_iterations", C.c_int64), ("cholesky_nnz", C.c_int64),
+                ("hessian_pose_dimension", C.c_int32), ("hessian_landmark_dimension", C.c_int32),
+                ("ms_symbolic_decomposition", C.c_double), ("ms_numeric_decomposition", C.c_double),
+                ("ms_structure_build", C.c_double)]
 
 
 class ProblemInfo(C.Structure):
@@ -126,6 +130,9 @@ def load_library():
     lib.ssba_get_edge_errors.argtypes = [H, dp]
     lib.ssba_chi2.argtypes = [H, dp, dp]
     lib.ssba_count_outliers.argtypes = [H, C.c_double, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.ssba_get_outlier_mask.argtypes = [H, C.c_double, bp, C.POINTER(C.c_int64)]
+    lib.ssba_request_stop.argtypes = [H]
+    lib.ssba_clear_stop.argtypes = [H]
     lib.ssba_optimize_rounds.argtypes = [H, C.c_int32, C.c_int32, C.c_double, C.c_double, C.POINTER(C.c_int32),
                                          C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(Report)]
     lib.ssba_plan_shards.argtypes = [C.c_int32, bp, C.c_int32, bp, C.c_int32, ip, ip, C.c_int32, ip]
@@ -328,6 +335,19 @@ class BundleAdjuster:
         a, b = C.c_int64(0), C.c_int64(0)
         self._check(self.lib.ssba_count_outliers(self._h, float(threshold), C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def outlier_mask(self, threshold=5.891):
+        """uint8 per edge (caller's order): plain chi2 > threshold (backend.cpp:205-227)."""
+        out = np.zeros(self._n_edges, np.uint8)
+        n = C.c_int64(0)
+        self._check(self.lib.ssba_get_outlier_mask(self._h, float(threshold), _p(out, C.c_uint8), C.byref(n)))
+        return out, n.value
+
+    def request_stop(self):
+        self._check(self.lib.ssba_request_stop(self._h))
+
+    def clear_stop(self):
+        self._check(self.lib.ssba_clear_stop(self._h))
 
     def profile(self) -> Profile:
         p = Profile()

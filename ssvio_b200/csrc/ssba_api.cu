@@ -3,6 +3,7 @@
 // dlopen only when world_size > 1).  No CPU compute path exists here: without a CUDA device
 // ssba_create() fails.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -82,6 +83,11 @@ struct ssba_handle {
   // with the same topology is re-uploaded without a structure build (the <= 5 rounds of backend.cpp:175-203)
   size_t off_pose0 = 0, off_point0 = 0, off_e_uv = 0, off_e_info = 0, off_e_delta = 0;
   long long n_structure_builds = 0, n_structure_reuses = 0;
+  double ms_structure_build = 0.0, ms_symbolic = 0.0;
+  // SparseOptimizer::setForceStopFlag: raised from any thread, posted to the device on a stream of its own
+  std::atomic<int> stop_requested{0};
+  cudaStream_t aux_stream = nullptr;
+  int *h_one = nullptr;  // pinned constant 1
   // memory: one device arena (static index data first, then work buffers) + pinned mirror of
   // the static part so a whole graph goes up in one copy
   char *d_arena = nullptr; size_t d_arena_bytes = 0;
@@ -303,13 +309,14 @@ ssba_status run_lm(ssba_handle *h, int max_iters, bool iteration0) {
   c.max_iters = max_iters; c.last_result = SSBA_SOLVER_OK;
   c.world = h->opt.world_size; c.rank = h->opt.rank;
   c.trial_seq = h->trial_seq;
+  if (h->stop_requested.load() && h->opt.world_size == 1) { c.force_stop = 1; c.done = 1; }  // terminate() before the first iteration
   CUDA_TRY(h, cudaMemcpyAsync(h->P.ctl, &c, sizeof(Control), cudaMemcpyHostToDevice, h->stream));
   // the copy above must have left the pinned buffer before it is reused for the read-back
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   bool first = true;
   int guard = 0;
   const int max_slots = max_iters * (c.max_trials > 0 ? c.max_trials : 1) + 1;
-  while (true) {
+  while (!c.done) {
     // optimistic batch: one slot per outstanding outer iteration (every trial accepted)
     int batch = max_iters - c.outer_iter;
     if (batch < 1) batch = 1;
@@ -327,6 +334,8 @@ ssba_status run_lm(ssba_handle *h, int max_iters, bool iteration0) {
   }
   h->cur = c.cur; h->lambda = c.lambda; h->ni = c.ni;
   h->trial_seq = c.trial_seq;
+  h->prof.levenberg_iterations += c.n_trials;
+  h->prof.outer_iterations += c.outer_iter;
   if (h->opt.world_size > 1 && std::getenv("SSBA_TIMING"))
     std::fprintf(stderr, "[ssba] rank %d last trial: exchange_sys wait %.2f us, sum %.2f us | gap to control %.2f us | fold %.2f us, scal exchange %.2f us, decision %.2f us\n",
                  h->opt.rank, (c.dbg[1] - c.dbg[0]) * 1e-3, (c.dbg[2] - c.dbg[1]) * 1e-3, (c.dbg[3] - c.dbg[2]) * 1e-3, (c.dbg[4] - c.dbg[3]) * 1e-3,
@@ -427,8 +436,11 @@ ssba_status ssba_create(const ssba_options *opt, ssba_handle **out) {
     h->own_stream = true;
   }
   if (cudaHostAlloc((void **)&h->h_ctl, sizeof(Control), cudaHostAllocDefault) != cudaSuccess ||
-      cudaHostAlloc((void **)&h->h_small, 64 * sizeof(double), cudaHostAllocDefault) != cudaSuccess)
+      cudaHostAlloc((void **)&h->h_small, 64 * sizeof(double), cudaHostAllocDefault) != cudaSuccess ||
+      cudaHostAlloc((void **)&h->h_one, sizeof(int), cudaHostAllocDefault) != cudaSuccess)
     return fail(nullptr, SSBA_ERR_ALLOC, "cudaHostAlloc failed");
+  *h->h_one = 1;
+  if (cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(nullptr, SSBA_ERR_CUDA, "cudaStreamCreate failed");
   if (o.world_size > 1) {
     std::string err;
     if (!g_nccl.load(err)) return fail(nullptr, SSBA_ERR_NCCL, err);
@@ -456,6 +468,8 @@ void ssba_destroy(ssba_handle *h) {
   if (h->h_po) cudaFreeHost(h->h_po);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->h_small) cudaFreeHost(h->h_small);
+  if (h->h_one) cudaFreeHost(h->h_one);
+  if (h->aux_stream) { cudaStreamSynchronize(h->aux_stream); cudaStreamDestroy(h->aux_stream); }
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -631,6 +645,7 @@ ssba_status ssba_initialize(ssba_handle *h) {
     DYN(W, 18 * (size_t)s.n_pairs, double); DYN(Hll, 6 * (size_t)s.n_slots, double); DYN(bl, 3 * (size_t)s.n_slots, double);
     DYN(Dinv, 6 * (size_t)s.n_slots, double);
     DYN(gather, h->opt.world_size > 1 ? 3 * (size_t)g.n_points : 0, double); DYN(err_out, 2 * (size_t)g.n_edges, double);
+    DYN(mask_out, (size_t)g.n_edges, uint8_t);
     const size_t known = align_up(top);
     // room for region B and the late work buffers (a few hundred KB for a sliding window); if the
     // guess is short the arena is re-made below and region A sent again
@@ -650,6 +665,8 @@ ssba_status ssba_initialize(ssba_handle *h) {
   h->topo_dirty = true;
   if (!build_structure(g, h->opt.rank, h->opt.world_size, s, err, &on_edges_ready)) return fail(h, SSBA_ERR_INVALID_ARG, err);
   auto t_b = Clock::now();
+  h->ms_structure_build = 1e3 * secs(t_a, t_b);
+  h->ms_symbolic = 1e3 * s.seconds_symbolic;
   if (cb_rc) return cb_rc;
   if (s.n_fp + s.n_fl_global == 0) { h->initialized = false; return fail(h, SSBA_ERR_EMPTY, "initialize: 0 vertices to optimize"); }
 
@@ -906,6 +923,45 @@ ssba_status ssba_count_outliers(ssba_handle *h, double thr, int64_t *n_out, int6
   // edges whose two vertices are fixed are never active (sparse_optimizer.cpp:237): their
   // _error stays zero in the reference, so backend.cpp:184 counts them as inliers
   if (n_in) *n_in = (int64_t)(f[3] + 0.5) + (h->g.n_edges - h->s.n_active_edges_global);
+  return SSBA_OK;
+}
+
+ssba_status ssba_get_outlier_mask(ssba_handle *h, double thr, uint8_t *mask_out, int64_t *n_out) {
+  if (!h || !mask_out) return SSBA_ERR_INVALID_ARG;
+  ssba_status rc = ensure_ready(h);
+  if (rc) return rc;
+  const size_t n = (size_t)h->P.n_edges_total;
+  CUDA_TRY(h, cudaMemsetAsync(h->P.mask_out, 0, n, h->stream));  // inactive edges (both ends fixed) are never outliers
+  launch_outlier_mask(h->P, thr, h->stream);
+  h->prof.kernel_launches += 2;
+  if (h->opt.world_size > 1) {  // every edge lives on exactly one rank: the sum is the union
+    if (g_nccl.AllReduce(h->P.mask_out, h->P.mask_out, n, /*ncclUint8*/ 1, kNcclSum, h->comm, h->stream) != 0) return fail(h, SSBA_ERR_NCCL, "ncclAllReduce failed");
+    if ((rc = nccl_allreduce(h, h->P.chi_out, 4, kNcclSum))) return rc;
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(mask_out, h->P.mask_out, n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_small, h->P.chi_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (n_out) *n_out = (int64_t)(h->h_small[2] + 0.5);
+  return SSBA_OK;
+}
+
+ssba_status ssba_request_stop(ssba_handle *h) {
+  if (!h) return SSBA_ERR_INVALID_ARG;
+  if (h->opt.world_size > 1) return fail(h, SSBA_ERR_STATE, "request_stop: not supported on a multi-rank handle (the ranks must agree on every trial)");
+  h->stop_requested.store(1);
+  // a running optimize() sees it at its next trial: 4 bytes into the device-resident controller, on a stream of
+  // its own (the launch stream is busy with the enqueued trials)
+  if (h->initialized && h->P.ctl) {
+    if (cudaSetDevice(h->device) != cudaSuccess) return SSBA_ERR_CUDA;
+    if (cudaMemcpyAsync(&h->P.ctl->force_stop, h->h_one, sizeof(int), cudaMemcpyHostToDevice, h->aux_stream) != cudaSuccess) { cudaGetLastError(); return SSBA_ERR_CUDA; }
+  }
+  return SSBA_OK;
+}
+
+ssba_status ssba_clear_stop(ssba_handle *h) {
+  if (!h) return SSBA_ERR_INVALID_ARG;
+  if (h->aux_stream) cudaStreamSynchronize(h->aux_stream);  // a pending raise must not land after this
+  h->stop_requested.store(0);
   return SSBA_OK;
 }
 
@@ -1176,6 +1232,12 @@ ssba_status ssba_set_profiling(ssba_handle *h, int32_t on) {
 
 ssba_status ssba_profile_get(ssba_handle *h, ssba_profile *out) {
   if (!h || !out) return SSBA_ERR_INVALID_ARG;
+  h->prof.cholesky_nnz = h->initialized ? 36LL * (h->s.n_blocks - h->s.n_fp) + 21LL * h->s.n_fp : 0;
+  h->prof.hessian_pose_dimension = h->initialized ? 6 * h->s.n_fp : 0;
+  h->prof.hessian_landmark_dimension = h->initialized ? 3 * h->s.n_fl_global : 0;
+  h->prof.ms_symbolic_decomposition = h->ms_symbolic;
+  h->prof.ms_structure_build = h->ms_structure_build;
+  h->prof.ms_numeric_decomposition = h->prof.ms_reduced_solve;
   *out = h->prof;
   return SSBA_OK;
 }

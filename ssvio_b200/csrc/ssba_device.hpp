@@ -40,6 +40,8 @@ struct Control {
   long long trial_seq;     // trials executed on this handle so far (same on every rank): the sequence number of
                            // the peer-memory exchanges
   int comm_timeout;        // a peer did not publish its part in time (peer-memory exchange)
+  int force_stop;          // SparseOptimizer::terminate(): raised through ssba_request_stop (a copy on a side stream)
+  long long n_trials;      // levenbergIterations summed over this run
   long long dbg[8];        // SSBA_TIMING: globaltimer stamps of the last trial's exchange kernels
   ssba_iter_record records[SSBA_MAX_ITER_RECORDS];
 };
@@ -114,6 +116,7 @@ struct DeviceProblem {
   double *chi_new_part, *scale_part;        // n_upd_blocks
   double *scal;       // [chi_cur, chi_new, scale_lm, maxdiag] reduced partials (all-reduced)
   double *err_out;    // n_edges_total x 2 scratch for ssba_get_edge_errors
+  uint8_t *mask_out;  // n_edges_total: ssba_get_outlier_mask
   double *chi_out;    // [plain, robust, n_outliers, n_inliers]
   double *gather;     // n_points x 3, multi-GPU read-back of the landmark estimates
   const uint8_t *owner_mask;  // n_points: this rank reports the landmark
@@ -141,6 +144,7 @@ void launch_control_p2p(const DeviceProblem &P, cudaStream_t st);      // partia
 void launch_fold(const DeviceProblem &P, cudaStream_t st);           // first slot: hpp_fold + Hpp diagonals
 void launch_final_chi2(const DeviceProblem &P, double threshold, cudaStream_t st);  // -> chi_out
 void launch_edge_errors(const DeviceProblem &P, cudaStream_t st);      // -> err_out
+void launch_outlier_mask(const DeviceProblem &P, double threshold, cudaStream_t st);  // -> mask_out, chi_out[2] = #outliers
 void launch_gather_points(const DeviceProblem &P, cudaStream_t st);    // -> gather
 int kernels_per_linearize();
 

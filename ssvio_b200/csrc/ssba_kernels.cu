@@ -1176,10 +1176,12 @@ __device__ void control_step(const DeviceProblem &P) {
     if (!isfinite(c->lambda)) broke = true;
   }
   if (!broke) c->qmax++;
+  c->n_trials++;
+  const bool stop = *reinterpret_cast<volatile int *>(&c->force_stop) != 0;  // terminate(), levenberg.cpp:145
   c->rho = rho;
   c->temp_chi = tempChi;
   c->current_chi = accepted ? tempChi : currentChi;
-  const bool again = !broke && rho < 0 && c->qmax < c->max_trials;
+  const bool again = !broke && rho < 0 && c->qmax < c->max_trials && !stop;
   if (again) {
     c->need_linearize = 0;
     return;
@@ -1194,7 +1196,7 @@ __device__ void control_step(const DeviceProblem &P) {
   c->outer_iter++;
   c->qmax = 0;
   c->need_linearize = 1;
-  if (result != SSBA_SOLVER_OK || c->outer_iter >= c->max_iters) c->done = 1;
+  if (result != SSBA_SOLVER_OK || c->outer_iter >= c->max_iters || stop) c->done = 1;  // sparse_optimizer.cpp:388
 }
 
 // partial sums of the linearize / update CTAs -> scal[0..2], folded in a fixed order by one CTA
@@ -1497,9 +1499,11 @@ __global__ void __launch_bounds__(kLinThreads) k_final_chi2(const DeviceProblem 
         load_edge_weighting(P, P.e_info, P.e_delta, e, t);
         plain += t.chi; robust += t.rho0;
         if (t.chi > threshold) nout += 1.0; else nin += 1.0;
-        if (write_errors) {
+        if (write_errors == 1) {
           const int o = P.e_orig[e];
           P.err_out[2 * (size_t)o] = t.e0; P.err_out[2 * (size_t)o + 1] = t.e1;
+        } else if (write_errors == 2) {
+          P.mask_out[P.e_orig[e]] = t.chi > threshold ? 1 : 0;
         }
       }
     }
@@ -1809,6 +1813,11 @@ void launch_gather_points(const DeviceProblem &P, cudaStream_t st) {
 
 void launch_edge_errors(const DeviceProblem &P, cudaStream_t st) {
   k_final_chi2<<<P.n_fin_blocks, kLinThreads, 0, st>>>(P, 0.0, 1);
+}
+
+void launch_outlier_mask(const DeviceProblem &P, double threshold, cudaStream_t st) {
+  k_final_chi2<<<P.n_fin_blocks, kLinThreads, 0, st>>>(P, threshold, 2);
+  k_final_reduce<<<1, 256, 0, st>>>(P);
 }
 
 void launch_pose_graph_slot(const DeviceProblem &P, int n_edges, const int32_t *ev0, const int32_t *ev1, const int32_t *eq0,

@@ -610,6 +610,8 @@ struct SolverPlan {  // what is left for finish_solver_program (run off the crit
 };
 
 bool plan_reduced_solver(int n, const std::vector<std::vector<int>> &adj, Structure &s, SolverPlan &plan, std::string &err) {
+  const auto t_plan0 = std::chrono::steady_clock::now();
+  struct AddTime { Structure &s; std::chrono::steady_clock::time_point t0; ~AddTime() { s.seconds_symbolic = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); } } add_time{s, t_plan0};
   static const bool force_level = [] { const char *e = std::getenv("SSBA_SOLVER"); return e && std::string(e) == "level"; }();
   std::vector<int> perm_nat(n), perm_nd, perm_tree;
   std::iota(perm_nat.begin(), perm_nat.end(), 0);
@@ -672,6 +674,8 @@ bool plan_reduced_solver(int n, const std::vector<std::vector<int>> &adj, Struct
 // the level program of k_reduced_solve with its task lists.  Reads the factor pattern of `s`, writes only
 // tree / prog / prog_ptr / task lists / solver_* / solve_cluster: build_structure runs it on a thread of its own.
 void finish_solver_program(int n, const std::vector<std::vector<int>> &adj, Structure &s, SolverPlan &plan) {
+  const auto t0 = std::chrono::steady_clock::now();
+  struct AddTime { Structure &s; std::chrono::steady_clock::time_point t0; ~AddTime() { s.seconds_symbolic += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); } } add_time{s, t0};
   if (plan.want_tree) build_tree_program(n, s.col_ptr, s.blk_row, s.row_ptr, s.row_blk, s.row_col, plan.ta, s.tree);
   if (s.tree.ok) { s.solve_cluster = s.tree.C; return; }
   if (!plan.have_tasks) {

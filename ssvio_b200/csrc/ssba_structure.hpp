@@ -103,6 +103,7 @@ struct Structure {
   std::vector<int32_t> task_pair_ptr; // n_tasks + 1 -> pairs
   std::vector<int32_t> pair_a, pair_b;
   double est_solver_cycles = 0.0;     // cost model that picked the elimination order
+  double seconds_symbolic = 0.0;      // host time of ordering + symbolic factorisation + solver program
   // the same schedule packed level by level for the device (see build_solver_program)
   std::vector<int32_t> prog, prog_ptr;
   int prog_max_seg = 0;               // ints in the largest level segment
