@@ -13,8 +13,14 @@ if has dmma; then
   (cd scripts/microbench && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o dmma dmma.cu && timeout 120 ./dmma) > gpurun_out/r2_dmma.txt 2>&1
   tail -40 gpurun_out/r2_dmma.txt
 fi
+if has sanitize; then
+  for cfg in ${SAN_CFGS:-small cfg2}; do
+    echo "== compute-sanitizer memcheck $cfg"
+    timeout 600 compute-sanitizer --tool memcheck --print-limit 5 python scripts/run_case.py $cfg 3 2>&1 | grep -v "^=========     at\|^=========         in\|Host Frame" | tail -25 | tee gpurun_out/r2_memcheck_$cfg.log
+  done
+fi
 if has parity; then
-  timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/r2_pytest_gpu.log
+  timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -40 | tee gpurun_out/r2_pytest_gpu.log
 fi
 if has bench; then
   for solver in tree level; do

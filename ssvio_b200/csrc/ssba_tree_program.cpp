@@ -357,6 +357,7 @@ bool build_tree_program(int n, const std::vector<int32_t> &col_ptr, const std::v
         else push_panel_item(w, 0, 0, 0);
       }
       // backward records: x_j = L_jj^-T (y_j - sum_i X_ij^T x_i); rows = where x_i lives in the pool
+      while (w.size() & 3) w.push_back(0);  // the records are read as 16-byte words
       st = step_entry();
       st[kTS_OffBwd] = (int)w.size();
       const size_t rec0 = w.size();

@@ -172,6 +172,7 @@ struct TreeCta {
   std::vector<int> wr_t, wr_i, rd_t, rd_i;
   const int32_t *w;
   int T = 0, item = 0;
+  double rd2(int off) { if (off & 1) CHECK(false, "tree program: odd offset %d under a 16-byte access", off); return 0.0; }
   double rd(int off) {
     if (wr_t[off] == T && wr_i[off] != item) { CHECK(false, "tree program: read of a double written by another item in the same interval (off %d)", off); }
     if (rd_t[off] == T && rd_i[off] != item) rd_i[off] = -2; else { rd_t[off] = T; rd_i[off] = item; }
@@ -190,6 +191,7 @@ static void tree_products(TreeCta &c, int dest, int nrows, int p0, int p1) {
     for (int p = p0; p < p1; ++p) {
       const unsigned wd = (unsigned)c.w[p];
       const int a = (int)(wd & 0xffff) + 6 * r, b = (int)(wd >> 16);
+      c.rd2(a); c.rd2(b); c.rd2(dest);
       for (int m = 0; m < 6; ++m) { double t = 0; for (int k = 0; k < 6; ++k) t += c.rd(a + k) * c.rd(b + 6 * m + k); acc[m] += t; }
     }
     if (p1 > p0) for (int m = 0; m < 6; ++m) c.wrt(dest + 6 * r + m, c.rd(dest + 6 * r + m) - acc[m]);
@@ -199,6 +201,8 @@ static void tree_forward_steps(TreeCta &c, int s0, int s1, bool *fail) {
   const int32_t *w = c.w;
   for (int s = s0; s < s1; ++s) {
     const int32_t *st = w + w[kTH_OffSteps] + kTS_Words * s;
+    // alignment the kernel's vector loads rely on (program base is 16-byte aligned)
+    CHECK(st[kTS_OffDiag] % 2 == 0 && st[kTS_OffLook] % 2 == 0 && st[kTS_OffPanel] % 2 == 0 && st[kTS_OffBwd] % 4 == 0, "tree program: item arrays misaligned");
     ++c.T;  // interval 1: diagonal items and look-ahead rounds
     for (int t = 0; t < st[kTS_Cols]; ++t) {
       ++c.item;
