@@ -19,7 +19,7 @@ LIB = os.path.join(LIB_DIR, "libssba.so")
 SOURCES = ["ssba_kernels.cu", "ssba_tree_solve.cu", "ssba_pose_only.cu", "ssba_api.cu", "ssba_structure.cpp",
            "ssba_tree_program.cpp"]
 HEADERS = ["ssba_geometry.cuh", "ssba_device.hpp", "ssba_structure.hpp", "ssba_solver_layout.hpp",
-           "ssba_tree_program.hpp"]
+           "ssba_tree_program.hpp", "ssba_block_inverse.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

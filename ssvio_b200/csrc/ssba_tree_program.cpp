@@ -126,14 +126,20 @@ void tree_assign(int n, const std::vector<int32_t> &col_ptr, const std::vector<i
 size_t tree_smem_estimate(int n, const std::vector<int32_t> &col_ptr, const std::vector<int32_t> &blk_row, const TreeAssign &a) {
   const int C = a.C;
   std::vector<double> words(C, kTH_Words + 64.0);
-  std::vector<long long> nblk(C, 0), ncols(C, 0), nbound(C, 0);
-  std::vector<int> stamp(n, -1);
+  std::vector<long long> nblk(C, 0), ncols(C, 0), nbound(C, 0), ntemp(C, 0), in_step(C, 0);
+  std::vector<int> stamp(n, -1), cur_step(C, -1);
   std::vector<int> new_of(n);
   for (int q = 0; q < n; ++q) new_of[a.order[q]] = q;
   for (int q = 0; q < n; ++q) {
     const int j = a.order[q], c = a.cta[q];
     const int m = col_ptr[j + 1] - col_ptr[j] - 1;
     nblk[c] += m + 1; ++ncols[c];
+    {  // unscaled copies of the sub-diagonal blocks of one step's columns (columns of a step are adjacent in the order)
+      const int key = a.step[q] + (a.top[q] ? 1 << 20 : 0);
+      if (key != cur_step[c]) { cur_step[c] = key; in_step[c] = 0; }
+      in_step[c] += m;
+      ntemp[c] = std::max(ntemp[c], in_step[c]);
+    }
     words[c] += 3.6 * (0.5 * m * (m + 1) + m) + 2.4 * (m + 1) + 6 + m;
     if (c)
       for (int b = col_ptr[j] + 1; b < col_ptr[j + 1]; ++b) {
@@ -148,7 +154,7 @@ size_t tree_smem_estimate(int n, const std::vector<int32_t> &col_ptr, const std:
   }
   for (int c = 0; c < C; ++c) {
     const long long contrib = c ? 36 * (nbound[c] * (nbound[c] + 1) / 2) + 6 * nbound[c] : 0;
-    const size_t bytes = 8 * (size_t)(36 * nblk[c] + 12 * ncols[c] + contrib) + 4 * (size_t)words[c] + kTreeMiscBytes + 64;
+    const size_t bytes = 8 * (size_t)(36 * nblk[c] + 12 * ncols[c] + contrib + 36 * ntemp[c]) + 4 * (size_t)words[c] + kTreeMiscBytes + 64;
     worst = std::max(worst, bytes);
   }
   return worst;
@@ -157,16 +163,16 @@ size_t tree_smem_estimate(int n, const std::vector<int32_t> &col_ptr, const std:
 namespace {
 
 struct Item { int dest, nrows, p0, p1; };   // product item: dest -= sum over pairs of A B^T (row-wise)
-// product item: { dest | nrows << 16 | n_pairs << 20, first pair word }; panel item: { dest | nrows << 16, diagonal block }
+// product item: { dest | nrows << 16 | n_pairs << 20, first pair word }; panel item: { dest | nrows << 16, diagonal block | unscaled copy << 16 }
 inline bool push_product_item(std::vector<int32_t> &w, int dest, int nrows, int p0, int np) {
   if (np >= 4096) return false;
   w.push_back((int32_t)((unsigned)dest | ((unsigned)nrows << 16) | ((unsigned)np << 20)));
   w.push_back(p0);
   return true;
 }
-inline void push_panel_item(std::vector<int32_t> &w, int dest, int nrows, int diag) {
+inline void push_panel_item(std::vector<int32_t> &w, int dest, int nrows, int diag, int xcopy) {
   w.push_back((int32_t)((unsigned)dest | ((unsigned)nrows << 16)));
-  w.push_back(diag);
+  w.push_back((int32_t)((unsigned)diag | ((unsigned)xcopy << 16)));
 }
 
 }  // namespace
@@ -197,6 +203,19 @@ bool build_tree_program(int n, const std::vector<int32_t> &col_ptr, const std::v
     CB0[c] = BP0[c] + 6 * tp.n_own_cols[c];
   }
   auto own = [&](int c, int q) { return q >= q0[c] && q < q1[c]; };
+  // unscaled copies: the sub-diagonal blocks X_ik of the columns of one step sit side by side in the CTA's
+  // scratch area from the panel of their step until the products of the next step have read them
+  std::vector<int32_t> xcopy_idx(col_ptr[n], -1);
+  std::vector<int> xcopy_blocks(C, 0);
+  for (int c = 0; c < C; ++c) {
+    int key = -1, cnt = 0;
+    for (int q = q0[c]; q < q1[c]; ++q) {
+      const int kq = a.step[q];
+      if (kq != key) { key = kq; cnt = 0; }
+      for (int b = col_ptr[q] + 1; b < col_ptr[q + 1]; ++b) xcopy_idx[b] = cnt++;
+      xcopy_blocks[c] = std::max(xcopy_blocks[c], cnt);
+    }
+  }
   auto find_block = [&](int row, int col) -> int {
     const int32_t *b0 = blk_row.data() + col_ptr[col], *b1 = blk_row.data() + col_ptr[col + 1];
     const int32_t *it = std::lower_bound(b0, b1, row);
@@ -208,7 +227,7 @@ bool build_tree_program(int n, const std::vector<int32_t> &col_ptr, const std::v
   for (int c = 1; c < C; ++c) { cb_slot_of[c].assign(col_ptr[n] - col_ptr[q0[0]], -1); cv_slot_of[c].assign(n - q0[0], -1); }
   // symbolic destinations, resolved to pool offsets once the slot counts are known
   enum { kOwnBlk = 0, kOwnVec, kCtbBlk, kCtbVec };
-  struct Prod { int owner, step, critical, dkind, dkey, a_off, b_off, k, nrows; };
+  struct Prod { int owner, step, critical, dkind, dkey, a_off, b_off, k, nrows; };  // b_off: index of the unscaled copy
   std::vector<Prod> prods;
   prods.reserve(8 * (size_t)col_ptr[n]);
   const int tb0 = col_ptr[q0[0]];
@@ -217,7 +236,7 @@ bool build_tree_program(int n, const std::vector<int32_t> &col_ptr, const std::v
       const int bck = row_blk[rr], k = row_col[rr];
       const int o = a.cta[k];
       if (!own(o, k)) return fail("internal: source column not owned");
-      const int b_off = 36 * (bck - tp.b0[o]);
+      const int b_off = xcopy_idx[bck];
       const bool dest_own = own(o, c);
       if (!dest_own && (o == 0 || !a.top[c])) return fail("internal: destination neither own nor top");
       {  // right-hand side: r_c -= X_ck y_k
@@ -245,12 +264,14 @@ bool build_tree_program(int n, const std::vector<int32_t> &col_ptr, const std::v
       }
     }
   }
-  std::vector<int> CV0(C);
+  std::vector<int> CV0(C), XC0(C);
   for (int c = 0; c < C; ++c) {
     CV0[c] = CB0[c] + 36 * (int)cb_blk[c].size();
     tp.contrib_off[c] = CB0[c];
     tp.contrib_doubles[c] = 36 * (int)cb_blk[c].size() + 6 * (int)cv_col[c].size();
-    tp.pool_doubles[c] = CB0[c] + tp.contrib_doubles[c];
+    XC0[c] = CB0[c] + tp.contrib_doubles[c];
+    tp.xcopy_off[c] = XC0[c];
+    tp.pool_doubles[c] = XC0[c] + 36 * xcopy_blocks[c];
     if (tp.pool_doubles[c] >= 65536) return fail("pool exceeds 16-bit offsets");
   }
   {
@@ -307,7 +328,7 @@ bool build_tree_program(int n, const std::vector<int32_t> &col_ptr, const std::v
         size_t pj = pi;
         while (pj < prods.size() && prods[pj].owner == c && prods[pj].step == s && prods[pj].critical == p0.critical &&
                prods[pj].dkind == p0.dkind && prods[pj].dkey == p0.dkey) {
-          pairs.push_back((int32_t)((unsigned)prods[pj].a_off | ((unsigned)prods[pj].b_off << 16)));
+          pairs.push_back((int32_t)((unsigned)prods[pj].a_off | ((unsigned)(XC0[c] + 36 * prods[pj].b_off) << 16)));
           ++pj;
         }
         if (p0.critical) {
@@ -343,7 +364,7 @@ bool build_tree_program(int n, const std::vector<int32_t> &col_ptr, const std::v
       std::vector<Item> panel;
       for (int t = 0; t < nc; ++t) {
         const int j = cols[t], dblk = 36 * (col_ptr[j] - tp.b0[c]);
-        for (int b = col_ptr[j] + 1; b < col_ptr[j + 1]; ++b) panel.push_back(Item{36 * (b - tp.b0[c]), 6, dblk, 0});
+        for (int b = col_ptr[j] + 1; b < col_ptr[j + 1]; ++b) panel.push_back(Item{36 * (b - tp.b0[c]), 6, dblk, XC0[c] + 36 * xcopy_idx[b]});
       }
       for (int t = 0; t < nc; ++t) {
         const int j = cols[t];
@@ -353,10 +374,10 @@ bool build_tree_program(int n, const std::vector<int32_t> &col_ptr, const std::v
       st[kTS_NPanel] = ((int)panel.size() + 4) / 5;
       st[kTS_OffPanel] = (int)w.size();
       for (size_t i = 0; i < 5 * (size_t)(((int)panel.size() + 4) / 5); ++i) {
-        if (i < panel.size()) push_panel_item(w, panel[i].dest, panel[i].nrows, panel[i].p0);
-        else push_panel_item(w, 0, 0, 0);
+        if (i < panel.size()) push_panel_item(w, panel[i].dest, panel[i].nrows, panel[i].p0, panel[i].p1);
+        else push_panel_item(w, 0, 0, 0, 0);
       }
-      // backward records: x_j = L_jj^-T (y_j - sum_i X_ij^T x_i); rows = where x_i lives in the pool
+      // backward records: x_j = w_j - sum_i Y_ij^T x_i; rows = where x_i lives in the pool
       while (w.size() & 3) w.push_back(0);  // the records are read as 16-byte words
       st = step_entry();
       st[kTS_OffBwd] = (int)w.size();

@@ -11,14 +11,18 @@
 // of its subtrees on its own.  Two cluster barriers per solve instead of one per elimination level.
 //
 // Inside a CTA the columns are processed in STEPS (a step = the columns of one elimination level of
-// that CTA's forest).  Numerics per column j (block Cholesky, 6x6 blocks):
-//   D_j  = A_jj - sum_k X_jk X_jk^T              -> L_jj = chol(D_j)          (one lane)
-//   X_ij = (A_ij - sum_k X_ik X_jk^T) L_jj^-T    (one lane per block row)
-//   y_j  = L_jj^-1 (b_j - sum_k X_jk y_k)        (the right-hand side is one more block row of height 1)
-// and backwards  x_j = L_jj^-T (y_j - sum_{i>j} X_ij^T x_i).
-// The products of a finished column k are applied eagerly (right-looking): the ones a diagonal block of
-// the next step waits for by the warp that factors it, all others by the remaining warps WHILE the
-// diagonal blocks are being factored.  Two __syncthreads per step.
+// that CTA's forest).  Numerics per column j: block LDL^T with 6x6 blocks (the same factorisation as the
+// scalar Cholesky of CSparse, grouped differently; D_j is positive definite iff its six Cholesky pivots are
+// positive, csparse_extension.cpp:115):
+//   D_j  = A_jj - sum_k Y_jk X_jk^T,   M_j = D_j^-1            (closed form, one lane: no chain of six square roots)
+//   X_ij = A_ij - sum_k Y_ik X_jk^T,   Y_ij = X_ij M_j         (one lane per block row; Y replaces X in place, the
+//                                                               unscaled X_ij goes to a scratch copy for one step)
+//   z_j  = b_j - sum_k X_jk w_k,       w_j = M_j z_j           (the right-hand side is one more block row of height 1)
+// and backwards  x_j = w_j - sum_{i>j} Y_ij^T x_i  (no triangular solve on the way back).
+// The products of a finished column k are applied eagerly (right-looking), ALL of them in the step after k's
+// (which is why the unscaled copy only lives for one step): the ones a diagonal block of the next step waits
+// for by the warp that inverts it, all others by the remaining warps WHILE the diagonal blocks are being
+// inverted.  Two __syncthreads per step.
 //
 // Everything the kernel walks is planned here; a CPU interpreter of the same program
 // (tests/cpp/test_structure.cpp) checks it against a dense solve.
@@ -39,8 +43,9 @@ constexpr size_t kTreeMiscBytes = 192;            // mbarrier, round counter, fl
 constexpr int kTreeStepCols = 5 * kTreeWarps;     // diagonal blocks one step can factor (5 lane groups per warp)
 
 // A work item is two words: { dest | nrows << 16 | n_pairs << 20,  first pair word } for product items,
-// { dest | nrows << 16, diagonal block } for panel items (offsets in doubles into the CTA's pool); a pair word
-// is  a | b << 16.  Rounds are five items.
+// { dest | nrows << 16, diagonal block | unscaled copy << 16 } for panel items (offsets in doubles into the CTA's
+// pool); a pair word is  a | b << 16  (a: rows of a scaled block Y or a vector w, b: an unscaled copy X).
+// Rounds are five items.
 constexpr int kTreeItemWords = 2, kTreeRoundWords = 5 * kTreeItemWords;
 // program header words
 enum : int { kTH_StepsA = 0, kTH_StepsB, kTH_OffSteps, kTH_AddRounds, kTH_OffAddRounds, kTH_NXload, kTH_OffXload, kTH_TopCol0, kTH_Words = 16 };
@@ -53,11 +58,12 @@ struct TreeProgram {
   std::vector<int32_t> words;         // the programs of all CTAs, each padded to a multiple of 4 words
   int32_t prog_ptr[kTreeMaxCluster + 1] = {0};
   // shared-memory pool of CTA c (doubles): [own factor blocks | own rhs/solution vectors | b_p copy |
-  // contribution blocks | contribution vectors]
+  // contribution blocks | contribution vectors | unscaled copies of one step]
   int32_t pool_doubles[kTreeMaxCluster] = {0};
   int32_t b0[kTreeMaxCluster] = {0}, n_own_blocks[kTreeMaxCluster] = {0};  // first factor block / count
   int32_t q0[kTreeMaxCluster] = {0}, n_own_cols[kTreeMaxCluster] = {0};    // first column / count (CTA 0: incl. the top part)
   int32_t contrib_off[kTreeMaxCluster] = {0}, contrib_doubles[kTreeMaxCluster] = {0};
+  int32_t xcopy_off[kTreeMaxCluster] = {0};  // scratch: unscaled copies of one step's sub-diagonal blocks
   int32_t xchg_off[kTreeMaxCluster] = {0};  // where CTA c's contributions go in the exchange buffer (doubles)
   int32_t xchg_doubles = 0;
   size_t smem_bytes = 0;              // dynamic shared memory of the launch (max over the CTAs)

@@ -5,6 +5,7 @@
 // "pivot <= 0 => the trial is rejected" (:115), and applies the pose part of SparseOptimizer::update
 // (g2o/core/sparse_optimizer.cpp:433-446) and of computeScale (optimization_algorithm_levenberg.cpp:168-175).
 //
+// Numerics: block LDL^T with closed-form 6x6 inverses (ssba_tree_program.hpp).
 // Data movement: the CTA's slice of the reduced system (its factor blocks, right-hand sides, b_p) and its
 // whole program arrive with four bulk asynchronous copies (TMA, cp.async.bulk) on one mbarrier; from then
 // on every operand is a shared-memory load.  Two cluster barriers per solve (contributions up, top solution
@@ -12,6 +13,7 @@
 #include <atomic>
 
 #include "ssba_device.hpp"
+#include "ssba_block_inverse.cuh"
 
 namespace ssba {
 
@@ -53,16 +55,20 @@ __device__ __forceinline__ double ts_group_reduce(double v, int lane) {
   return v;
 }
 
-// row r of  dest -= sum over the item's pairs of A B^T  (A: the item's rows, 6 doubles each; B: a 6x6 block)
-__device__ __forceinline__ void ts_product_rows(double *pool, const int *prog, int w0, int p0, int r) {
+// row r of  dest -= sum over the item's pairs of A B^T  (A: the item's rows, 6 doubles each, of a scaled block Y
+// or a vector w; B: the unscaled copy of a 6x6 block).  `pw` = the item's first pair word (the caller may have
+// fetched it ahead).  Returns the updated row in `d` as well (the diagonal items go on in registers).
+__device__ __forceinline__ void ts_product_rows(double *pool, const int *prog, int w0, int p0, unsigned pw, int r, double *d) {
   const int np = (int)((unsigned)w0 >> 20);
   double acc[6];
 #pragma unroll
   for (int c = 0; c < 6; ++c) acc[c] = 0.0;
-  for (int p = p0; p < p0 + np; ++p) {
-    const unsigned pw = (unsigned)prog[p];
+  double2 *D = reinterpret_cast<double2 *>(pool + (w0 & 0xffff) + 6 * r);
+  const double2 d0 = D[0], d1 = D[1], d2 = D[2];
+  for (int p = 0; p < np; ++p) {
     const double2 *A2 = reinterpret_cast<const double2 *>(pool + (pw & 0xffffu) + 6 * r);
     const double2 *B2 = reinterpret_cast<const double2 *>(pool + (pw >> 16));
+    if (p + 1 < np) pw = (unsigned)prog[p0 + p + 1];
     const double2 a0 = A2[0], a1 = A2[1], a2 = A2[2];
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
@@ -70,42 +76,8 @@ __device__ __forceinline__ void ts_product_rows(double *pool, const int *prog, i
       acc[c] += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y;
     }
   }
-  if (np > 0) {
-    double2 *D = reinterpret_cast<double2 *>(pool + (w0 & 0xffff) + 6 * r);
-    double2 d0 = D[0], d1 = D[1], d2 = D[2];
-    d0.x -= acc[0]; d0.y -= acc[1]; d1.x -= acc[2]; d1.y -= acc[3]; d2.x -= acc[4]; d2.y -= acc[5];
-    D[0] = d0; D[1] = d1; D[2] = d2;
-  }
-}
-
-// in-place Cholesky of the lower triangle of a 6x6 block by one lane: L below the diagonal, 1 / l_cc ON the
-// diagonal; a pivot <= 0 (or NaN) is reported like csparse_extension.cpp:115 and replaced so that the
-// arithmetic stays finite
-__device__ __forceinline__ bool ts_cholesky6(double *D) {
-  double a[36];
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-#pragma unroll
-    for (int k = 0; k <= i; ++k) a[6 * i + k] = D[6 * i + k];
-  bool bad = false;
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    double dj = a[7 * j];
-    if (!(dj > 0.0)) { bad = true; dj = 1.0; }
-    const double inv = rsqrt(dj);
-    a[7 * j] = inv;
-#pragma unroll
-    for (int i = j + 1; i < 6; ++i) a[6 * i + j] *= inv;
-#pragma unroll
-    for (int i = j + 1; i < 6; ++i)
-#pragma unroll
-      for (int k = j + 1; k <= i; ++k) a[6 * i + k] -= a[6 * i + j] * a[6 * k + j];
-  }
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-#pragma unroll
-    for (int k = 0; k <= i; ++k) D[6 * i + k] = a[6 * i + k];
-  return bad;
+  d[0] = d0.x - acc[0]; d[1] = d0.y - acc[1]; d[2] = d1.x - acc[2]; d[3] = d1.y - acc[3]; d[4] = d2.x - acc[4]; d[5] = d2.y - acc[5];
+  if (np > 0) { D[0] = make_double2(d[0], d[1]); D[1] = make_double2(d[2], d[3]); D[2] = make_double2(d[4], d[5]); }
 }
 
 template <int NT>
@@ -123,6 +95,22 @@ __device__ __forceinline__ double ts_block_sum(double v, double *sm /* NT / 32 *
   return r;  // valid on thread 0
 }
 
+#ifdef SSBA_SOLVER_TRACE
+__device__ long long g_tree_trace[kTreeMaxCluster][256];
+__device__ __forceinline__ long long ts_gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// entries 0..15: phase boundaries (globaltimer, ns); 16..: clock64 after interval 1 / interval 2 of every forward step, then per backward step
+#define TS_TRACE_G(i) do { if (threadIdx.x == 0) g_tree_trace[cta][(i)] = ts_gtime(); } while (0)
+#define TS_TRACE_C(i) do { if (threadIdx.x == 0 && (i) < 256) g_tree_trace[cta][(i)] = clock64(); } while (0)
+// fine trace of warp 0 inside the intervals of every step: 8 stamps per step from entry 128 on (steps 0..15)
+#define TS_TRACE_F(s, k) do { if (threadIdx.x == 0 && ((s) == 4 || (s) == 5)) g_tree_trace[cta][200 + 8 * ((s) - 4) + (k)] = clock64(); } while (0)
+#define TS_TRACE_W(s, k) do { if ((threadIdx.x & 31) == 0 && ((s) == 4 || (s) == 5)) g_tree_trace[cta][128 + 32 * ((s) - 4) + 2 * (threadIdx.x >> 5) + (k)] = clock64(); } while (0)
+#else
+#define TS_TRACE_F(s, k) do { } while (0)
+#define TS_TRACE_W(s, k) do { } while (0)
+#define TS_TRACE_G(i) do { } while (0)
+#define TS_TRACE_C(i) do { } while (0)
+#endif
+
 template <bool kCluster>
 __global__ void __launch_bounds__(kTreeThreads, 1) k_tree_solve(const DeviceProblem P) {
   Control *ctl = P.ctl;
@@ -138,17 +126,17 @@ __global__ void __launch_bounds__(kTreeThreads, 1) k_tree_solve(const DeviceProb
   int *prog = reinterpret_cast<int *>(ts_smem + 8 * (size_t)((np + 1) & ~1));
   unsigned char *misc = reinterpret_cast<unsigned char *>(prog + nwords);  // nwords is a multiple of 4
   unsigned long long *bar = reinterpret_cast<unsigned long long *>(misc);
-  int *s_ctr = reinterpret_cast<int *>(misc + 8);
   int *s_fail = reinterpret_cast<int *>(misc + 12);
   double *red = reinterpret_cast<double *>(misc + 16);  // kTreeWarps doubles
   const int nblk = T.n_own_blocks[cta], ncols = T.n_own_cols[cta], q0 = T.q0[cta];
   const int V0 = 36 * nblk, BP0 = V0 + 6 * ncols;
   const double *bs = P.sys + 36 * (size_t)P.n_blocks;
 
+  TS_TRACE_G(0);
   if (tid == 0) {
     ts_mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    *s_ctr = 0; *s_fail = 0;
+    *s_fail = 0;
   }
   __syncthreads();
   if (tid == 0) {
@@ -179,84 +167,213 @@ __global__ void __launch_bounds__(kTreeThreads, 1) k_tree_solve(const DeviceProb
   }
   ts_mbar_wait(bar, 0);
   __syncthreads();
+  TS_TRACE_G(1);
+#ifdef SSBA_SOLVER_TRACE
+  int trc = 16;
+#endif
 
   const int *steps = prog + prog[kTH_OffSteps];
   const int nsa = prog[kTH_StepsA], nsb = prog[kTH_StepsB];
 
-  // ---- numeric factorisation + forward substitution of the steps [s0, s1)
-  auto forward = [&](int s0, int s1) {
-    for (int s = s0; s < s1; ++s) {
-      const int *st = steps + kTS_Words * s;
-      const int nc = st[kTS_Cols];
-      // interval 1: the diagonal blocks of this step (the products they still wait for, then the
-      // 6x6 Cholesky in one lane per column) beside the look-ahead products of the previous step's columns
-      if (5 * warp < nc) {
-        const int ci = 5 * warp + g;
-        const bool act = g < 5 && ci < nc;
-        int2 it = make_int2(0, 0);
-        if (act) {
-          it = *reinterpret_cast<const int2 *>(prog + st[kTS_OffDiag] + kTreeItemWords * ci);
-          ts_product_rows(pool, prog, it.x, it.y, r);
+  // One instance of the step code for the subtree part and the top part (the kernel is latency bound and one
+  // warp often runs alone: instruction fetch matters, the body has to stay small): steps [0, ns_all), with the
+  // hand-over of the contributions when the subtree steps are done.
+  const int ns_all = nsa + (cta == 0 ? nsb : 0);
+  const int ci = 5 * warp + g;
+
+  // ---- numeric factorisation + forward substitution.  Every descriptor a step needs right after a barrier (its
+  // table entry, this lane group's diagonal item and first pair word, this warp's first panel item) is fetched one
+  // step ahead, so that only loads of numeric operands follow the barriers.
+  {
+    int4 da = *reinterpret_cast<const int4 *>(steps), db = *reinterpret_cast<const int4 *>(steps + 4);
+    int2 dit = make_int2(0, 0);   // this lane group's diagonal item of the running step
+    unsigned dpw = 0;             // ... and its first pair word
+    if (g < 5 && ci < da.x) {
+      dit = *reinterpret_cast<const int2 *>(prog + da.y + kTreeItemWords * ci);
+      if ((unsigned)dit.x >> 20) dpw = (unsigned)prog[dit.y];
+    }
+#pragma unroll 1
+    for (int s = 0;; ++s) {
+      if (s == nsa) {
+        TS_TRACE_G(2);
+        if (kCluster) {
+          // ---- contributions of the subtrees to the top part: up through global memory (L2), added by CTA 0 in
+          // CTA order (round r = every destination's r-th contribution: the destinations of a round are distinct)
+          if (cta != 0) {
+            const double2 *src = reinterpret_cast<const double2 *>(pool + T.contrib_off[cta]);
+            double2 *dst = reinterpret_cast<double2 *>(T.xchg + T.xchg_off[cta]);
+            const int n2 = T.contrib_doubles[cta] / 2;
+            for (int i = tid; i < n2; i += kTreeThreads) dst[i] = src[i];
+          }
+          ts_cluster_barrier();
+          TS_TRACE_G(3);
+          if (cta == 0) {
+            const int n_rounds = prog[kTH_AddRounds];
+            const int *tab = prog + prog[kTH_OffAddRounds];
+            const int grp = tid / 18, sub = tid - 18 * grp;  // 28 groups of 18 lanes: one 16-byte piece of a block each
+            const double2 *x2 = reinterpret_cast<const double2 *>(T.xchg);
+            for (int rd = 0; rd < n_rounds; ++rd) {
+              const int nops = tab[2 * rd];
+              const int *ops = prog + tab[2 * rd + 1];
+              for (int base = 0; base < nops; base += 28 * 4) {
+                double2 v[4];
+                int dst[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int op = base + 28 * u + grp;
+                  dst[u] = -1;
+                  if (grp < 28 && op < nops) {
+                    const unsigned wd = (unsigned)ops[op];
+                    if (sub < ((wd >> 31) ? 3 : 18)) {
+                      dst[u] = (int)(wd & 0xffffu) + 2 * sub;
+                      v[u] = __ldcg(x2 + ((wd >> 16) & 0x7fffu) + sub);
+                    }
+                  }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  if (dst[u] >= 0) {
+                    double2 *d = reinterpret_cast<double2 *>(pool + dst[u]);
+                    double2 t = *d;
+                    t.x += v[u].x; t.y += v[u].y;
+                    *d = t;
+                  }
+                }
+              }
+              __syncthreads();
+            }
+          }
         }
-        __syncwarp();
-        if (act && r == 0) {
-          if (ts_cholesky6(pool + (it.x & 0xffff))) { *s_fail = 1; ctl->chol_fail = 1; }
-        }
+        TS_TRACE_G(4);
       }
-      const int n_look = st[kTS_NLook];
-      if (n_look > 0) {
-        const int *rounds = prog + st[kTS_OffLook];
-        for (;;) {
-          int rd = 0;
-          if (lane == 0) rd = atomicAdd(s_ctr, 1);
-          rd = __shfl_sync(0xffffffffu, rd, 0);
-          if (rd >= n_look) break;
+      if (s >= ns_all) break;
+      const int nc = da.x, n_look = da.z, off_look = da.w, n_panel = db.x, off_panel = db.y;
+      TS_TRACE_F(s, 0);
+      // program data of the next step and of this step's panel (nothing the steps write)
+      int4 na = make_int4(0, 0, 0, 0), nb = na;
+      if (s + 1 < ns_all) { na = *reinterpret_cast<const int4 *>(steps + kTS_Words * (s + 1)); nb = *reinterpret_cast<const int4 *>(steps + kTS_Words * (s + 1) + 4); }
+      int2 pit = make_int2(0, 0);   // this warp's first panel item
+      if (warp < n_panel && g < 5) pit = *reinterpret_cast<const int2 *>(prog + off_panel + kTreeRoundWords * warp + kTreeItemWords * g);
+      int2 nit = make_int2(0, 0);   // the next step's diagonal item and first pair word
+      unsigned npw = 0;
+      if (g < 5 && ci < na.x) {
+        nit = *reinterpret_cast<const int2 *>(prog + na.y + kTreeItemWords * ci);
+        if ((unsigned)nit.x >> 20) npw = (unsigned)prog[nit.y];
+      }
+      // interval 1: the diagonal blocks of this step (the products they still wait for, then the closed-form
+      // inverse in one lane per column) on the first warps, beside the look-ahead products of the previous
+      // step's columns on the others (rounds dealt statically: no shared counter on anybody's path)
+      const int nd = nc >= 5 * kTreeWarps ? kTreeWarps : (nc + 4) / 5;
+      if (warp < nd) {
+        const bool act = g < 5 && ci < nc;
+        double d[6];
+        TS_TRACE_F(s, 1);
+        if (act) ts_product_rows(pool, prog, dit.x, dit.y, dpw, r, d);
+        __syncwarp();
+        TS_TRACE_F(s, 2);
+        if (act && r == 0) {
+          if (block_inverse6(pool + (dit.x & 0xffff))) { *s_fail = 1; ctl->chol_fail = 1; }
+        }
+        TS_TRACE_F(s, 3);
+      }
+      // (measured, not kept: holding the look-ahead loads back until the diagonal warps have their operands; keeping
+      // the warps that share a diagonal warp's scheduler out of the look-ahead; neither shortens the step)
+      if (n_look > 0 && (warp >= nd || nd == kTreeWarps)) {
+        const int *rounds = prog + off_look;
+        const int w0 = nd == kTreeWarps ? warp : warp - nd, nw = nd == kTreeWarps ? kTreeWarps : kTreeWarps - nd;
+#pragma unroll 1
+        for (int rd = w0; rd < n_look; rd += nw) {
           if (g < 5) {
             const int2 it = *reinterpret_cast<const int2 *>(rounds + kTreeRoundWords * rd + kTreeItemWords * g);
-            if (r < ((it.x >> 16) & 15)) ts_product_rows(pool, prog, it.x, it.y, r);
+            if (r < ((it.x >> 16) & 15)) {
+              double d[6];
+              ts_product_rows(pool, prog, it.x, it.y, (unsigned)prog[it.y], r, d);
+            }
           }
         }
       }
+      TS_TRACE_W(s, 0);
       __syncthreads();
-      // interval 2: X = B L_jj^-T row by row for every sub-diagonal block of the step's columns, y_j likewise
-      if (tid == 0) *s_ctr = 0;
+      TS_TRACE_F(s, 4);
+#ifdef SSBA_SOLVER_TRACE
+      TS_TRACE_C(trc); ++trc;
+#endif
+      // interval 2: Y = X M_j row by row for every sub-diagonal block of the step's columns (the unscaled row
+      // goes to the scratch copy the next step's products read), w_j = M_j z_j likewise
       {
-        const int n_panel = st[kTS_NPanel];
-        const int *rounds = prog + st[kTS_OffPanel];
+        const int *rounds = prog + off_panel;
+#pragma unroll 1
         for (int rd = warp; rd < n_panel; rd += kTreeWarps) {
           if (g >= 5) continue;
-          const int2 it = *reinterpret_cast<const int2 *>(rounds + kTreeRoundWords * rd + kTreeItemWords * g);
-          if (r >= ((it.x >> 16) & 15)) continue;
+          const int2 it = rd == warp ? pit : *reinterpret_cast<const int2 *>(rounds + kTreeRoundWords * rd + kTreeItemWords * g);
+          const int nrows = (it.x >> 16) & 15;
+          if (r >= nrows) continue;
           double2 *D = reinterpret_cast<double2 *>(pool + (it.x & 0xffff) + 6 * r);
-          const double2 *L2 = reinterpret_cast<const double2 *>(pool + it.y);
+          const double2 *M2 = reinterpret_cast<const double2 *>(pool + (it.y & 0xffff));
           const double2 v0 = D[0], v1 = D[1], v2 = D[2];
-          const double v[6] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
-          double x[6];
+          double y[6];
 #pragma unroll
-          for (int m = 0; m < 6; ++m) {
-            const double2 l0 = L2[3 * m], l1 = L2[3 * m + 1], l2 = L2[3 * m + 2];
-            const double l[6] = {l0.x, l0.y, l1.x, l1.y, l2.x, l2.y};
-            double t = v[m];
-#pragma unroll
-            for (int k = 0; k < m; ++k) t -= x[k] * l[k];
-            x[m] = t * l[m];
+          for (int c = 0; c < 6; ++c) {
+            const double2 m0 = M2[3 * c], m1 = M2[3 * c + 1], m2 = M2[3 * c + 2];
+            y[c] = v0.x * m0.x + v0.y * m0.y + v1.x * m1.x + v1.y * m1.y + v2.x * m2.x + v2.y * m2.y;
           }
-          D[0] = make_double2(x[0], x[1]); D[1] = make_double2(x[2], x[3]); D[2] = make_double2(x[4], x[5]);
+          D[0] = make_double2(y[0], y[1]); D[1] = make_double2(y[2], y[3]); D[2] = make_double2(y[4], y[5]);
+          if (nrows == 6) {
+            double2 *X = reinterpret_cast<double2 *>(pool + ((unsigned)it.y >> 16) + 6 * r);
+            X[0] = v0; X[1] = v1; X[2] = v2;
+          }
         }
       }
+      da = na; db = nb; dit = nit; dpw = npw;
+      TS_TRACE_W(s, 1);
       __syncthreads();
+      TS_TRACE_F(s, 5);
+#ifdef SSBA_SOLVER_TRACE
+      TS_TRACE_C(trc); ++trc;
+#endif
     }
-  };
+  }
+  TS_TRACE_G(5);
 
-  // ---- backward substitution of the steps [s0, s1), last first: one warp per column
-  auto backward = [&](int s0, int s1) {
-    for (int s = s1 - 1; s >= s0; --s) {
-      const int *st = steps + kTS_Words * s;
-      const int nc = st[kTS_Cols];
+  // ---- backward substitution, last step first: one warp per column, x_j = w_j - sum_i Y_ij^T x_i; the records of
+  // the next step are fetched ahead of the barrier.  The top solution goes down to the other CTAs when the top
+  // steps are done.
+  {
+    int nc = 0, off = 0;
+    if (ns_all > 0) { nc = steps[kTS_Words * (ns_all - 1) + kTS_Cols]; off = steps[kTS_Words * (ns_all - 1) + kTS_OffBwd]; }
+    int4 rec = make_int4(0, 0, 0, 0);
+    if (warp < nc) rec = *reinterpret_cast<const int4 *>(prog + off + 4 * warp);
+#pragma unroll 1
+    for (int s = ns_all - 1;; --s) {
+      if (s == nsa - 1) {
+        TS_TRACE_G(6);
+        if (kCluster) {
+          if (cta == 0) {
+            const int t0 = prog[kTH_TopCol0];
+            for (int i = tid + 6 * t0; i < 6 * ncols; i += kTreeThreads) P.xp[6 * (size_t)q0 + i] = pool[V0 + i];
+          }
+          ts_cluster_barrier();
+          if (cta != 0) {
+            const int nx = prog[kTH_NXload];
+            const int *xl = prog + prog[kTH_OffXload];
+            for (int i = tid; i < 6 * nx; i += kTreeThreads) {
+              const unsigned wd = (unsigned)xl[i / 6];
+              const int m = i - 6 * (i / 6);
+              pool[(wd & 0xffffu) + m] = __ldcg(P.xp + 6 * (size_t)(wd >> 16) + m);
+            }
+          }
+          __syncthreads();
+        }
+        TS_TRACE_G(7);
+      }
+      if (s < 0) break;
+      int nnc = 0, noff = 0;
+      if (s > 0) { nnc = steps[kTS_Words * (s - 1) + kTS_Cols]; noff = steps[kTS_Words * (s - 1) + kTS_OffBwd]; }
+#pragma unroll 1
       for (int t = warp; t < nc; t += kTreeWarps) {
-        const int4 rec = *reinterpret_cast<const int4 *>(prog + st[kTS_OffBwd] + 4 * t);
-        const int dg = rec.x, vo = rec.y, nb = rec.z;
-        const int *rows = prog + rec.w;
+        const int4 rc = t == warp ? rec : *reinterpret_cast<const int4 *>(prog + off + 4 * t);
+        const int dg = rc.x, vo = rc.y, nb = rc.z;
+        const int *rows = prog + rc.w;
         double acc = 0.0;
         if (g < 5) {
           for (int k = g; k < nb; k += 5) {
@@ -267,99 +384,18 @@ __global__ void __launch_bounds__(kTreeThreads, 1) k_tree_solve(const DeviceProb
           }
         }
         acc = ts_group_reduce(acc, lane);  // totals on lanes 0..5
-        const double sv = lane < 6 ? pool[vo + r] - acc : 0.0;
-        double sc[6];
-#pragma unroll
-        for (int c = 0; c < 6; ++c) sc[c] = __shfl_sync(0xffffffffu, sv, c);
-        if (lane == 0) {
-          const double *L = pool + dg;
-          double x[6];
-#pragma unroll
-          for (int m = 5; m >= 0; --m) {
-            double t2 = sc[m];
-#pragma unroll
-            for (int k = m + 1; k < 6; ++k) t2 -= L[6 * k + m] * x[k];
-            x[m] = t2 * L[7 * m];
-          }
-          double2 *o = reinterpret_cast<double2 *>(pool + vo);
-          o[0] = make_double2(x[0], x[1]); o[1] = make_double2(x[2], x[3]); o[2] = make_double2(x[4], x[5]);
-        }
+        if (lane < 6) pool[vo + r] -= acc;
       }
+      int4 nrec = make_int4(0, 0, 0, 0);
+      if (warp < nnc) nrec = *reinterpret_cast<const int4 *>(prog + noff + 4 * warp);
+      nc = nnc; off = noff; rec = nrec;
       __syncthreads();
-    }
-  };
-
-  forward(0, nsa);
-  if (kCluster) {
-    // ---- contributions of the subtrees to the top part: up through global memory (L2), added by CTA 0 in
-    // CTA order (round r = every destination's r-th contribution: the destinations of a round are distinct)
-    if (cta != 0) {
-      const double2 *src = reinterpret_cast<const double2 *>(pool + T.contrib_off[cta]);
-      double2 *dst = reinterpret_cast<double2 *>(T.xchg + T.xchg_off[cta]);
-      const int n2 = T.contrib_doubles[cta] / 2;
-      for (int i = tid; i < n2; i += kTreeThreads) dst[i] = src[i];
-    }
-    ts_cluster_barrier();
-    if (cta == 0) {
-      const int n_rounds = prog[kTH_AddRounds];
-      const int *tab = prog + prog[kTH_OffAddRounds];
-      const int grp = tid / 18, sub = tid - 18 * grp;  // 28 groups of 18 lanes: one 16-byte piece of a block each
-      const double2 *x2 = reinterpret_cast<const double2 *>(T.xchg);
-      for (int rd = 0; rd < n_rounds; ++rd) {
-        const int nops = tab[2 * rd];
-        const int *ops = prog + tab[2 * rd + 1];
-        for (int base = 0; base < nops; base += 28 * 4) {
-          double2 v[4];
-          int dst[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int op = base + 28 * u + grp;
-            dst[u] = -1;
-            if (grp < 28 && op < nops) {
-              const unsigned wd = (unsigned)ops[op];
-              if (sub < ((wd >> 31) ? 3 : 18)) {
-                dst[u] = (int)(wd & 0xffffu) + 2 * sub;
-                v[u] = __ldcg(x2 + ((wd >> 16) & 0x7fffu) + sub);
-              }
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (dst[u] >= 0) {
-              double2 *d = reinterpret_cast<double2 *>(pool + dst[u]);
-              double2 t = *d;
-              t.x += v[u].x; t.y += v[u].y;
-              *d = t;
-            }
-          }
-        }
-        __syncthreads();
-      }
+#ifdef SSBA_SOLVER_TRACE
+      TS_TRACE_C(trc); ++trc;
+#endif
     }
   }
-  if (cta == 0 && nsb > 0) {
-    forward(nsa, nsa + nsb);
-    backward(nsa, nsa + nsb);
-  }
-  if (kCluster) {
-    // ---- the top solution goes down through global memory
-    if (cta == 0) {
-      const int t0 = prog[kTH_TopCol0];
-      for (int i = tid + 6 * t0; i < 6 * ncols; i += kTreeThreads) P.xp[6 * (size_t)q0 + i] = pool[V0 + i];
-    }
-    ts_cluster_barrier();
-    if (cta != 0) {
-      const int nx = prog[kTH_NXload];
-      const int *xl = prog + prog[kTH_OffXload];
-      for (int i = tid; i < 6 * nx; i += kTreeThreads) {
-        const unsigned wd = (unsigned)xl[i / 6];
-        const int m = i - 6 * (i / 6);
-        pool[(wd & 0xffffu) + m] = __ldcg(P.xp + 6 * (size_t)(wd >> 16) + m);
-      }
-    }
-    __syncthreads();
-  }
-  backward(0, nsa);
+  TS_TRACE_G(8);
 
   // ---- epilogue: x_p, the pose part of computeScale and of update(): T <- exp(x) T into the trial buffer
   bool fail;
@@ -388,7 +424,17 @@ __global__ void __launch_bounds__(kTreeThreads, 1) k_tree_solve(const DeviceProb
   }
   sc = ts_block_sum<kTreeThreads>(sc, red);
   if (tid == 0) ctl->scale_pose_part[cta] = sc;
+  TS_TRACE_G(9);
 }
+
+#ifdef SSBA_SOLVER_TRACE
+}  // namespace
+extern "C" int ssba_debug_tree_trace(long long *out) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out, g_tree_trace, sizeof(long long) * kTreeMaxCluster * 256);
+}
+namespace {
+#endif
 
 }  // namespace
 

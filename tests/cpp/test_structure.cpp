@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "ssba_structure.hpp"
+#include "ssba_block_inverse.cuh"
 
 using namespace ssba;
 
@@ -162,8 +163,8 @@ static std::vector<double> interpret_program(const Structure &s, std::vector<dou
 
 // ---- CPU interpreter of the subtree-per-CTA program (Structure::tree, ssba_tree_program.cpp), i.e. of what
 // k_tree_solve walks: per CTA its shared-memory pool (own factor blocks, vectors, contribution slots), per step
-// the diagonal items (critical products + 6x6 Cholesky), the look-ahead product rounds that run beside them,
-// the panel rounds; the contribution hand-off to CTA 0 (add rounds), the top part, the backward passes and the
+// the diagonal items (critical products + inverse of the 6x6 block), the look-ahead product rounds that run beside
+// them, the panel rounds (Y = X M in place, the unscaled X into the one-step scratch copy); the contribution hand-off to CTA 0 (add rounds), the top part, the backward passes and the
 // hand-off of the top solution.  Every pool double remembers who wrote / read it in the running barrier
 // interval: two different work items touching the same double in one interval (one of them writing) is a race
 // on the device and fails here.
@@ -210,16 +211,31 @@ static void tree_forward_steps(TreeCta &c, int s0, int s1, bool *fail) {
       const int d = it[0] & 0xffff;
       CHECK(((it[0] >> 16) & 15) == 6, "diagonal item rows");
       tree_products(c, d, 6, it[1], it[1] + (int)((unsigned)it[0] >> 20));
-      double a[36];
+      // M = D^-1 from the LOWER triangle, written back as the full symmetric block; D must be positive definite
+      double a[36], Ls[36] = {0}, Li[36] = {0}, M[36];
       for (int i = 0; i < 6; ++i) for (int k = 0; k <= i; ++k) a[6 * i + k] = c.rd(d + 6 * i + k);
-      for (int j = 0; j < 6; ++j) {
-        if (!(a[7 * j] > 0)) { *fail = true; a[7 * j] = 1.0; }
-        const double inv = 1.0 / std::sqrt(a[7 * j]);
-        a[7 * j] = inv;
-        for (int i = j + 1; i < 6; ++i) a[6 * i + j] *= inv;
-        for (int i = j + 1; i < 6; ++i) for (int k = j + 1; k <= i; ++k) a[6 * i + k] -= a[6 * i + j] * a[6 * k + j];
+      for (int j = 0; j < 6; ++j) {  // reference route: Cholesky, triangular inverse, M = L^-T L^-1
+        double dj = a[7 * j];
+        for (int k = 0; k < j; ++k) dj -= Ls[6 * j + k] * Ls[6 * j + k];
+        if (!(dj > 0)) { *fail = true; dj = 1.0; }
+        Ls[7 * j] = std::sqrt(dj);
+        for (int i = j + 1; i < 6; ++i) { double v = a[6 * i + j]; for (int k = 0; k < j; ++k) v -= Ls[6 * i + k] * Ls[6 * j + k]; Ls[6 * i + j] = v / Ls[7 * j]; }
       }
-      for (int i = 0; i < 6; ++i) for (int k = 0; k <= i; ++k) c.wrt(d + 6 * i + k, a[6 * i + k]);  // L below, 1 / l_cc on the diagonal
+      for (int j = 0; j < 6; ++j) {
+        Li[7 * j] = 1.0 / Ls[7 * j];
+        for (int i = j + 1; i < 6; ++i) { double v = 0; for (int k = j; k < i; ++k) v -= Ls[6 * i + k] * Li[6 * k + j]; Li[6 * i + j] = v / Ls[7 * i]; }
+      }
+      for (int i = 0; i < 6; ++i) for (int k = 0; k < 6; ++k) { double v = 0; for (int m = 0; m < 6; ++m) v += Li[6 * m + i] * Li[6 * m + k]; M[6 * i + k] = v; }
+      {  // the product's closed-form inverse (ssba_block_inverse.cuh) is what the device runs: use it, and compare
+        double Dm[36];
+        for (int i = 0; i < 6; ++i) for (int k = 0; k < 6; ++k) Dm[6 * i + k] = k <= i ? a[6 * i + k] : std::numeric_limits<double>::quiet_NaN();  // upper triangle must not be read
+        const bool bad = block_inverse6(Dm);
+        if (bad) *fail = true;
+        double scale = 0; for (int i = 0; i < 36; ++i) scale = std::max(scale, std::fabs(M[i]));
+        for (int i = 0; i < 36; ++i) CHECK(std::fabs(Dm[i] - M[i]) <= 1e-11 * scale, "closed-form inverse vs Cholesky route: %g vs %g", Dm[i], M[i]);
+        for (int i = 0; i < 36; ++i) M[i] = Dm[i];
+      }
+      for (int i = 0; i < 36; ++i) c.wrt(d + i, M[i]);
     }
     for (int i = 0; i < 5 * st[kTS_NLook]; ++i) {
       ++c.item;
@@ -231,15 +247,14 @@ static void tree_forward_steps(TreeCta &c, int s0, int s1, bool *fail) {
     for (int i = 0; i < 5 * st[kTS_NPanel]; ++i) {
       ++c.item;
       const int32_t *it = w + st[kTS_OffPanel] + kTreeItemWords * i;
-      const int dest = it[0] & 0xffff, nrows = (it[0] >> 16) & 15, dg = it[1];
+      const int dest = it[0] & 0xffff, nrows = (it[0] >> 16) & 15, dg = it[1] & 0xffff, xc = (int)((unsigned)it[1] >> 16);
+      CHECK(dg % 2 == 0 && xc % 2 == 0 && dest % 2 == 0, "panel item misaligned");
       for (int r = 0; r < nrows; ++r) {
-        double x[6];
-        for (int m = 0; m < 6; ++m) {
-          double v = c.rd(dest + 6 * r + m);
-          for (int k = 0; k < m; ++k) v -= x[k] * c.rd(dg + 6 * m + k);
-          x[m] = v * c.rd(dg + 7 * m);
-        }
-        for (int m = 0; m < 6; ++m) c.wrt(dest + 6 * r + m, x[m]);
+        double x[6], y[6];
+        for (int m = 0; m < 6; ++m) x[m] = c.rd(dest + 6 * r + m);
+        for (int m = 0; m < 6; ++m) { double v = 0; for (int k = 0; k < 6; ++k) v += x[k] * c.rd(dg + 6 * m + k); y[m] = v; }
+        for (int m = 0; m < 6; ++m) c.wrt(dest + 6 * r + m, y[m]);       // Y = X M in place
+        if (nrows == 6) for (int m = 0; m < 6; ++m) c.wrt(xc + 6 * r + m, x[m]);  // the unscaled row for the next step's products
       }
     }
   }
@@ -254,11 +269,10 @@ static void tree_backward_steps(TreeCta &c, int s0, int s1) {
       const int32_t *rec = w + st[kTS_OffBwd] + 4 * t;
       const int dg = rec[0], v = rec[1], nb = rec[2];
       const int32_t *rows = w + rec[3];
-      double sv[6], x[6];
+      double sv[6];
       for (int m = 0; m < 6; ++m) sv[m] = c.rd(v + m);
       for (int k = 0; k < nb; ++k) { const int B = dg + 36 * (1 + k); for (int m = 0; m < 6; ++m) for (int nn = 0; nn < 6; ++nn) sv[m] -= c.rd(B + 6 * nn + m) * c.rd(rows[k] + nn); }
-      for (int m = 5; m >= 0; --m) { double t2 = sv[m]; for (int k = m + 1; k < 6; ++k) t2 -= c.rd(dg + 6 * k + m) * x[k]; x[m] = t2 * c.rd(dg + 7 * m); }
-      for (int m = 0; m < 6; ++m) c.wrt(v + m, x[m]);
+      for (int m = 0; m < 6; ++m) c.wrt(v + m, sv[m]);  // x_j = w_j - sum_i Y_ij^T x_i
     }
   }
 }
@@ -534,7 +548,39 @@ static void check_case(int nk, int np, int w, unsigned seed, bool fix0, int nfix
               nk, np, w, (int)fix0, nfix, (int)loop, world, n, s.n_blocks, s.n_schur_blocks, s.n_levels, s.n_tasks, (int)s.pair_a.size(), s.est_solver_cycles, s.solver_slots, s.solver_cached_blocks, rmax);
 }
 
+static void check_block_inverse() {
+  std::mt19937 rng(7);
+  std::uniform_real_distribution<double> U(-1, 1);
+  for (int trial = 0; trial < 2000; ++trial) {
+    // D = G G^T + eps I with rows of very different scale (rotation / translation blocks of a pose)
+    double G[36], D[36], Dm[36];
+    for (int i = 0; i < 36; ++i) G[i] = U(rng) * ((i / 6) < 3 ? 1e3 : 1.0);
+    for (int i = 0; i < 6; ++i) for (int k = 0; k < 6; ++k) { double v = 0; for (int m = 0; m < 6; ++m) v += G[6 * i + m] * G[6 * k + m]; D[6 * i + k] = v + (i == k ? 1e-3 : 0.0); }
+    const int flip = trial % 4 == 3 ? (int)(rng() % 6) : -1;  // every fourth block is made indefinite
+    if (flip >= 0) D[7 * flip] = -D[7 * flip];
+    for (int i = 0; i < 36; ++i) Dm[i] = D[i];
+    const bool bad = block_inverse6(Dm);
+    // Cholesky verdict
+    double L[36] = {0}; bool chol_bad = false;
+    for (int j = 0; j < 6; ++j) {
+      double dj = D[7 * j]; for (int k = 0; k < j; ++k) dj -= L[6 * j + k] * L[6 * j + k];
+      if (!(dj > 0)) { chol_bad = true; break; }
+      L[7 * j] = std::sqrt(dj);
+      for (int i = j + 1; i < 6; ++i) { double v = D[6 * i + j]; for (int k = 0; k < j; ++k) v -= L[6 * i + k] * L[6 * j + k]; L[6 * i + j] = v / L[7 * j]; }
+    }
+    CHECK(bad == chol_bad, "block_inverse6: positive-definiteness verdict %d vs Cholesky %d (trial %d)", (int)bad, (int)chol_bad, trial);
+    if (bad || chol_bad) continue;
+    // residual D M - I, relative to the conditioning
+    double res = 0, nm = 0, nd = 0;
+    for (int i = 0; i < 36; ++i) { nm = std::max(nm, std::fabs(Dm[i])); nd = std::max(nd, std::fabs(D[i])); }
+    for (int i = 0; i < 6; ++i) for (int k = 0; k < 6; ++k) { double v = 0; for (int m = 0; m < 6; ++m) v += D[6 * i + m] * Dm[6 * m + k]; res = std::max(res, std::fabs(v - (i == k ? 1.0 : 0.0))); }
+    CHECK(res <= 1e-13 * nm * nd * 36, "block_inverse6: residual %g (|D| %g |M| %g)", res, nd, nm);
+    for (int i = 0; i < 6; ++i) for (int k = 0; k < i; ++k) CHECK(Dm[6 * i + k] == Dm[6 * k + i], "block_inverse6: result not symmetric");
+  }
+}
+
 int main() {
+  check_block_inverse();
   check_case(4, 40, 3, 1, false, 0, false, 1);
   check_case(10, 500, 3, 2, false, 0, false, 1);
   check_case(30, 800, 5, 3, true, 25, false, 2);
