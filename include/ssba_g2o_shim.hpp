@@ -26,9 +26,15 @@
 // Needs: g2o core headers, ssvio/g2otypes.hpp, ssba.h; link with -lssba.
 #pragma once
 
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
-#include <unordered_map>
+#include <mutex>
+#include <thread>
+#include <typeinfo>
 #include <vector>
 
 #include <g2o/core/optimization_algorithm.h>
@@ -54,83 +60,132 @@ class OptimizationAlgorithmLevenbergCudaT : public g2o::OptimizationAlgorithm {
   explicit OptimizationAlgorithmLevenbergCudaT(const ssba_options *opt = nullptr) {
     if (opt) opt_ = *opt; else ssba_default_options(&opt_);
   }
-  ~OptimizationAlgorithmLevenbergCudaT() override { ssba_destroy(h_); }
+  // backend.cpp:83 makes a new solver for every window; the handle (device arena, pinned staging, stream,
+  // resident structure) is parked here for the next solver instead of being torn down and re-made each time
+  ~OptimizationAlgorithmLevenbergCudaT() override { park(h_, opt_); }
 
-  // OptimizationAlgorithmWithHessian::init (optimization_algorithm_with_hessian.cpp:48-73)
+  // OptimizationAlgorithmWithHessian::init (optimization_algorithm_with_hessian.cpp:48-73).  g2o calls it from
+  // every optimize() (sparse_optimizer.cpp:379), i.e. once per round of backend.cpp:175-203, so it is written to be
+  // cheap: exact-type checks instead of dynamic_cast on the 2e5 edges, the row of a vertex kept in the vertex
+  // (colInHessian, which only g2o's own BlockSolver uses), flat arrays reused between calls.  When the active
+  // graph is the one of the previous call, libssba keeps its structure and only takes the values.
   bool init(bool /*online*/ = false) override {
     if (!_optimizer) return false;
+    const auto t_init0 = std::chrono::steady_clock::now();
+    if (!h_) h_ = unpark(opt_);
     if (!h_ && ssba_create(&opt_, &h_) != SSBA_OK) {
       std::cerr << "ssba: " << ssba_last_error(nullptr) << std::endl;
       return false;
     }
+    const auto &av = _optimizer->activeVertices();  // sorted by id (sparse_optimizer.cpp:493-498)
+    const auto &ae = _optimizer->activeEdges();     // internalId = addEdge order
     poses_.clear(); points_.clear(); edges_.clear();
-    std::unordered_map<const g2o::HyperGraph::Vertex *, int32_t> row;
-    std::vector<double> pose_qt, xyz;
-    std::vector<uint8_t> pose_fixed, point_fixed;
-    for (auto *v : _optimizer->activeVertices()) {  // sorted by id (sparse_optimizer.cpp:493-498)
-      if (auto *vp = dynamic_cast<VertexPoseT *>(v)) {
-        row[v] = (int32_t)poses_.size();
+    pose_qt_.clear(); xyz_.clear(); pose_fixed_.clear(); point_fixed_.clear();
+    poses_.reserve(av.size()); points_.reserve(av.size());
+    for (auto *v : av) {
+      VertexPoseT *vp = typeid(*v) == typeid(VertexPoseT) ? static_cast<VertexPoseT *>(v) : dynamic_cast<VertexPoseT *>(v);
+      if (vp) {
+        vp->setColInHessian((int)poses_.size());
         poses_.push_back(vp);
         const auto &T = vp->estimate();
         const auto &q = T.unit_quaternion();
         const double qt[7] = {q.x(), q.y(), q.z(), q.w(), T.translation()[0], T.translation()[1], T.translation()[2]};
-        pose_qt.insert(pose_qt.end(), qt, qt + 7);
-        pose_fixed.push_back(vp->fixed());
-      } else if (auto *vl = dynamic_cast<VertexXYZT *>(v)) {
-        row[v] = (int32_t)points_.size();
-        points_.push_back(vl);
-        const auto &p = vl->estimate();
-        xyz.insert(xyz.end(), {p[0], p[1], p[2]});
-        point_fixed.push_back(vl->fixed());
-      } else {
-        std::cerr << "ssba: unsupported vertex type in the active graph" << std::endl;
-        return false;
+        pose_qt_.insert(pose_qt_.end(), qt, qt + 7);
+        pose_fixed_.push_back(vp->fixed());
+        continue;
       }
+      VertexXYZT *vl = typeid(*v) == typeid(VertexXYZT) ? static_cast<VertexXYZT *>(v) : dynamic_cast<VertexXYZT *>(v);
+      if (!vl) { std::cerr << "ssba: unsupported vertex type in the active graph" << std::endl; return false; }
+      vl->setColInHessian((int)points_.size());
+      points_.push_back(vl);
+      const auto &p = vl->estimate();
+      const double x3[3] = {p[0], p[1], p[2]};
+      xyz_.insert(xyz_.end(), x3, x3 + 3);
+      point_fixed_.push_back(vl->fixed());
     }
-    std::vector<int32_t> pidx, lidx;
-    std::vector<uint8_t> cam;
-    std::vector<double> uv, info, delta, ext_qt;
+    const size_t ne = ae.size();
+    if (ne == 0) return false;
+    pidx_.resize(ne); lidx_.resize(ne); cam_.resize(ne); uv_.resize(2 * ne); info_.resize(3 * ne); delta_.resize(ne);
+    edges_.resize(ne);
+    // The edges are 2e5 heap objects: walking them is the bulk of init(), so it is spread over a few threads.
+    // Every thread numbers the distinct camera extrinsics it meets locally; the lists are merged afterwards.
+    const int nt = thread_count(ne);
+    std::vector<std::vector<double>> ext_local(nt);
+    std::vector<int> bad(nt, 0);
     double K[9] = {0};
-    bool have_K = false;
-    for (auto *e : _optimizer->activeEdges()) {  // internalId = addEdge order
-      auto *ep = dynamic_cast<EdgeProjectionT *>(e);
-      if (!ep) { std::cerr << "ssba: unsupported edge type in the active graph" << std::endl; return false; }
-      edges_.push_back(ep);
-      pidx.push_back(row.at(ep->vertex(0)));
-      lidx.push_back(row.at(ep->vertex(1)));
-      const Eigen::Matrix3d &Ke = EdgeAccess::K(ep);
-      if (!have_K) { for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) K[3 * r + c] = Ke(r, c); have_K = true; }
-      const auto &X = EdgeAccess::ext(ep);
-      const auto &q = X.unit_quaternion();
-      const double qt[7] = {q.x(), q.y(), q.z(), q.w(), X.translation()[0], X.translation()[1], X.translation()[2]};
-      int ci = -1;
-      for (size_t c = 0; c < ext_qt.size() / 7; ++c)
-        if (std::memcmp(&ext_qt[7 * c], qt, sizeof(qt)) == 0) { ci = (int)c; break; }
-      if (ci < 0) {
-        if (ext_qt.size() / 7 >= SSBA_MAX_CAMERAS) { std::cerr << "ssba: too many distinct camera extrinsics" << std::endl; return false; }
-        ci = (int)(ext_qt.size() / 7);
-        ext_qt.insert(ext_qt.end(), qt, qt + 7);
-      }
-      cam.push_back((uint8_t)ci);
-      uv.insert(uv.end(), {ep->measurement()[0], ep->measurement()[1]});
-      const auto &I = ep->information();
-      info.insert(info.end(), {I(0, 0), I(0, 1), I(1, 1)});
-      double d = 0.0;
-      if (auto *rk = ep->robustKernel()) {
-        auto *hub = dynamic_cast<g2o::RobustKernelHuber *>(rk);
-        if (!hub) { std::cerr << "ssba: only RobustKernelHuber is supported" << std::endl; return false; }
-        d = hub->delta();
-      }
-      delta.push_back(d);
+    if (auto *e0 = dynamic_cast<const EdgeProjectionT *>(ae[0])) {  // one K for the whole graph (g2otypes.hpp:118-121)
+      const Eigen::Matrix3d &Ke = EdgeAccess::K(e0);
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) K[3 * r + c] = Ke(r, c);
     }
-    if (edges_.empty()) return false;
-    bool ok = ssba_set_cameras(h_, K, (int32_t)(ext_qt.size() / 7), ext_qt.data()) == SSBA_OK &&
-              ssba_set_poses(h_, (int32_t)poses_.size(), pose_qt.data(), pose_fixed.data()) == SSBA_OK &&
-              ssba_set_points(h_, (int32_t)points_.size(), xyz.data(), point_fixed.data()) == SSBA_OK &&
-              ssba_set_edges(h_, (int32_t)edges_.size(), pidx.data(), lidx.data(), cam.data(), uv.data(),
-                             info.data(), delta.data(), 0.0) == SSBA_OK &&
+    parallel_chunks(ne, nt, [&](int t, size_t i0, size_t i1) {
+      std::vector<double> &ext = ext_local[t];
+      for (size_t i = i0; i < i1; ++i) {
+        auto *e = ae[i];
+        EdgeProjectionT *ep = typeid(*e) == typeid(EdgeProjectionT) ? static_cast<EdgeProjectionT *>(e) : dynamic_cast<EdgeProjectionT *>(e);
+        if (!ep) { bad[t] = 1; return; }
+        edges_[i] = ep;
+        pidx_[i] = static_cast<const g2o::OptimizableGraph::Vertex *>(ep->vertex(0))->colInHessian();
+        lidx_[i] = static_cast<const g2o::OptimizableGraph::Vertex *>(ep->vertex(1))->colInHessian();
+        const auto &X = EdgeAccess::ext(ep);
+        const auto &q = X.unit_quaternion();
+        const double qt[7] = {q.x(), q.y(), q.z(), q.w(), X.translation()[0], X.translation()[1], X.translation()[2]};
+        int ci = -1;
+        for (size_t c = 0; c < ext.size() / 7; ++c)
+          if (std::memcmp(&ext[7 * c], qt, sizeof(qt)) == 0) { ci = (int)c; break; }
+        if (ci < 0) {
+          if (ext.size() / 7 >= SSBA_MAX_CAMERAS) { bad[t] = 2; return; }
+          ci = (int)(ext.size() / 7);
+          ext.insert(ext.end(), qt, qt + 7);
+        }
+        cam_[i] = (uint8_t)ci;
+        uv_[2 * i] = ep->measurement()[0]; uv_[2 * i + 1] = ep->measurement()[1];
+        const auto &I = ep->information();
+        info_[3 * i] = I(0, 0); info_[3 * i + 1] = I(0, 1); info_[3 * i + 2] = I(1, 1);
+        double d = 0.0;
+        if (auto *rk = ep->robustKernel()) {
+          auto *hub = typeid(*rk) == typeid(g2o::RobustKernelHuber) ? static_cast<g2o::RobustKernelHuber *>(rk) : dynamic_cast<g2o::RobustKernelHuber *>(rk);
+          if (!hub) { bad[t] = 3; return; }
+          d = hub->delta();
+        }
+        delta_[i] = d;
+      }
+    });
+    for (int t = 0; t < nt; ++t) {
+      if (bad[t] == 1) { std::cerr << "ssba: unsupported edge type in the active graph" << std::endl; return false; }
+      if (bad[t] == 3) { std::cerr << "ssba: only RobustKernelHuber is supported" << std::endl; return false; }
+    }
+    // merge the per-thread extrinsics (in thread order, i.e. in edge order) and renumber
+    ext_qt_.clear();
+    std::vector<std::vector<uint8_t>> remap(nt);
+    for (int t = 0; t < nt; ++t) {
+      for (size_t c = 0; c < ext_local[t].size() / 7; ++c) {
+        int ci = -1;
+        for (size_t k = 0; k < ext_qt_.size() / 7; ++k)
+          if (std::memcmp(&ext_qt_[7 * k], &ext_local[t][7 * c], 7 * sizeof(double)) == 0) { ci = (int)k; break; }
+        if (ci < 0) {
+          if (bad[t] == 2 || ext_qt_.size() / 7 >= SSBA_MAX_CAMERAS) { std::cerr << "ssba: too many distinct camera extrinsics" << std::endl; return false; }
+          ci = (int)(ext_qt_.size() / 7);
+          ext_qt_.insert(ext_qt_.end(), &ext_local[t][7 * c], &ext_local[t][7 * c] + 7);
+        }
+        remap[t].push_back((uint8_t)ci);
+      }
+      if (bad[t] == 2) { std::cerr << "ssba: too many distinct camera extrinsics" << std::endl; return false; }
+    }
+    parallel_chunks(ne, nt, [&](int t, size_t i0, size_t i1) {
+      for (size_t i = i0; i < i1; ++i) cam_[i] = remap[t][cam_[i]];
+    });
+    const auto t_init1 = std::chrono::steady_clock::now();
+    bool ok = ssba_set_cameras(h_, K, (int32_t)(ext_qt_.size() / 7), ext_qt_.data()) == SSBA_OK &&
+              ssba_set_poses(h_, (int32_t)poses_.size(), pose_qt_.data(), pose_fixed_.data()) == SSBA_OK &&
+              ssba_set_points(h_, (int32_t)points_.size(), xyz_.data(), point_fixed_.data()) == SSBA_OK &&
+              ssba_set_edges(h_, (int32_t)ne, pidx_.data(), lidx_.data(), cam_.data(), uv_.data(), info_.data(), delta_.data(), 0.0) == SSBA_OK &&
               ssba_initialize(h_) == SSBA_OK;
     if (!ok) std::cerr << "ssba: " << ssba_last_error(h_) << std::endl;
+    if (timing()) {
+      const auto t_init2 = std::chrono::steady_clock::now();
+      std::fprintf(stderr, "[ssba shim] init: flatten %.3f ms, set_* + initialize %.3f ms\n", std::chrono::duration<double, std::milli>(t_init1 - t_init0).count(),
+                   std::chrono::duration<double, std::milli>(t_init2 - t_init1).count());
+    }
     return ok;
   }
 
@@ -148,7 +203,9 @@ class OptimizationAlgorithmLevenbergCudaT : public g2o::OptimizationAlgorithm {
   // estimates -> g2o vertices, errors -> g2o edges (what push/pop/update and computeActiveErrors
   // leave behind in the reference)
   bool writeBack() {
-    std::vector<double> qt(7 * poses_.size()), xyz(3 * points_.size()), err(2 * edges_.size());
+    const auto t_wb0 = std::chrono::steady_clock::now();
+    std::vector<double> &qt = wb_qt_, &xyz = wb_xyz_, &err = wb_err_;
+    qt.resize(7 * poses_.size()); xyz.resize(3 * points_.size()); err.resize(2 * edges_.size());
     if (ssba_get_poses(h_, qt.data()) != SSBA_OK || ssba_get_points(h_, xyz.data()) != SSBA_OK ||
         ssba_get_edge_errors(h_, err.data()) != SSBA_OK) {
       std::cerr << "ssba: " << ssba_last_error(h_) << std::endl;
@@ -163,10 +220,13 @@ class OptimizationAlgorithmLevenbergCudaT : public g2o::OptimizationAlgorithm {
       if (points_[j]->fixed()) continue;
       points_[j]->setEstimate(Eigen::Vector3d(xyz[3 * j], xyz[3 * j + 1], xyz[3 * j + 2]));
     }
-    for (size_t e = 0; e < edges_.size(); ++e) {
-      edges_[e]->error()[0] = err[2 * e];
-      edges_[e]->error()[1] = err[2 * e + 1];
-    }
+    parallel_chunks(edges_.size(), thread_count(edges_.size()), [&](int, size_t e0, size_t e1) {
+      for (size_t e = e0; e < e1; ++e) {
+        edges_[e]->error()[0] = err[2 * e];
+        edges_[e]->error()[1] = err[2 * e + 1];
+      }
+    });
+    if (timing()) std::fprintf(stderr, "[ssba shim] writeBack %.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_wb0).count());
     return true;
   }
 
@@ -185,6 +245,40 @@ class OptimizationAlgorithmLevenbergCudaT : public g2o::OptimizationAlgorithm {
   ssba_handle *handle() { return h_; }
 
  private:
+  static bool timing() { static const bool on = std::getenv("SSBA_TIMING") != nullptr; return on; }
+  // a few short-lived threads for the passes over the edge objects (SSBA_SHIM_THREADS overrides; 1 = none)
+  static int thread_count(size_t n) {
+    static const int cfg = [] { const char *e = std::getenv("SSBA_SHIM_THREADS"); return e ? std::atoi(e) : 0; }();
+    int nt = cfg > 0 ? cfg : (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    if (n < 20000) nt = 1;
+    return nt;
+  }
+  template <class F> static void parallel_chunks(size_t n, int nt, F &&fn) {
+    if (nt <= 1) { fn(0, (size_t)0, n); return; }
+    std::vector<std::thread> th;
+    th.reserve(nt - 1);
+    for (int t = 1; t < nt; ++t) th.emplace_back([&, t] { fn(t, n * t / nt, n * (t + 1) / nt); });
+    fn(0, (size_t)0, n / nt);
+    for (auto &x : th) x.join();
+  }
+  // one parked handle per process (header-only: function-local statics are shared across translation units)
+  struct Parked { std::mutex mu; ssba_handle *h = nullptr; ssba_options opt{}; ~Parked() { if (h) ssba_destroy(h); } };
+  static Parked &parked() { static Parked p; return p; }
+  static void park(ssba_handle *h, const ssba_options &opt) {
+    if (!h) return;
+    Parked &p = parked();
+    std::lock_guard<std::mutex> lk(p.mu);
+    if (p.h) ssba_destroy(p.h);
+    p.h = h; p.opt = opt;
+  }
+  static ssba_handle *unpark(const ssba_options &opt) {
+    Parked &p = parked();
+    std::lock_guard<std::mutex> lk(p.mu);
+    if (!p.h || std::memcmp(&p.opt, &opt, sizeof(opt)) != 0) return nullptr;
+    ssba_handle *h = p.h;
+    p.h = nullptr;
+    return h;
+  }
   ssba_options opt_{};
   ssba_handle *h_ = nullptr;
   ssba_iter_record last_{};
@@ -192,6 +286,10 @@ class OptimizationAlgorithmLevenbergCudaT : public g2o::OptimizationAlgorithm {
   std::vector<VertexPoseT *> poses_;
   std::vector<VertexXYZT *> points_;
   std::vector<EdgeProjectionT *> edges_;
+  // flat arrays handed to libssba (kept between calls: no allocation per round)
+  std::vector<double> pose_qt_, xyz_, uv_, info_, delta_, ext_qt_, wb_qt_, wb_xyz_, wb_err_;
+  std::vector<uint8_t> pose_fixed_, point_fixed_, cam_;
+  std::vector<int32_t> pidx_, lidx_;
 };
 
 }  // namespace ssba

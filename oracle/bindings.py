@@ -215,6 +215,12 @@ class ShimHarness(_OracleBase):
                       C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                       C.POINTER(Report)]
 
+    def set_write_back_every_iteration(self, on: bool):
+        """False: one writeBack() after optimize() (all backend.cpp needs) instead of three read-backs per iteration."""
+        self.lib.ssba_shim_set_write_back_every_iteration.argtypes = [C.c_int32]
+        self.lib.ssba_shim_set_write_back_every_iteration.restype = None
+        self.lib.ssba_shim_set_write_back_every_iteration(1 if on else 0)
+
     def optimize(self, g, iters=None):
         iters = g.iters if iters is None else iters
         rep = Report()
