@@ -97,6 +97,7 @@ struct ssba_handle {
   double *h_small = nullptr;  // pinned scratch (8 doubles)
   DeviceProblem P{};
   int cur = 0;
+  int lin = 0; bool lin_valid = false; double current_chi = 0.0;  // see Control::lin
   double lambda = -1.0, ni = 2.0;
   size_t device_bytes = 0;
   void *comm = nullptr;
@@ -132,6 +133,13 @@ namespace {
       return SSBA_ERR_CUDA;                                                                 \
     }                                                                                       \
   } while (0)
+
+// programmatic dependent launch between the kernels of a trial: on, unless SSBA_PDL=0 or the per-phase events of
+// the profiling mode sit between them
+bool pdl_enabled(const ssba_handle *h) {
+  static const bool env_on = [] { const char *e = std::getenv("SSBA_PDL"); return !(e && std::atoi(e) == 0); }();
+  return env_on && !h->opt.profile;
+}
 
 ssba_status fail(ssba_handle *h, ssba_status st, const std::string &msg) {
   if (h) h->error = msg; else g_create_error = msg;
@@ -242,13 +250,14 @@ ssba_status setup_peer_exchange(ssba_handle *h, size_t sys_doubles) {
   return SSBA_OK;
 }
 
-// one LM trial, stream-ordered; `first` = first slot of an optimize()/step(0) call
-ssba_status enqueue_slot(ssba_handle *h, bool first) {
+// one LM trial, stream-ordered; `first` = first slot of an optimize()/step(0) call; `linearize`: k_linearize is part
+// of the slot (always, unless k_update linearises the accepted trials itself: then only where the controller asks)
+ssba_status enqueue_slot(ssba_handle *h, bool first, bool linearize) {
   const DeviceProblem &P = h->P;
   cudaStream_t st = h->stream;
   const bool multi = h->opt.world_size > 1;
   ssba_status rc;
-  {
+  if (linearize) {
     PhaseTimer t(h, 0);
     launch_linearize(P, st);
     h->prof.kernel_launches += 1;
@@ -305,7 +314,11 @@ ssba_status run_lm(ssba_handle *h, int max_iters, bool iteration0) {
   c.tau = h->opt.tau; c.good_lower = h->opt.good_step_lower_scale; c.good_upper = h->opt.good_step_upper_scale;
   c.user_lambda = h->opt.user_lambda_init; c.max_trials = h->opt.max_trials_after_failure;
   c.lambda = h->lambda; c.ni = h->ni;
-  c.cur = h->cur; c.need_linearize = 1; c.first_iteration = iteration0 ? 1 : 0;
+  c.cur = h->cur; c.first_iteration = iteration0 ? 1 : 0;
+  // a step that continues an optimisation (ssba_step(i > 0)) starts from the linearisation k_update made of the
+  // accepted trial; a new optimize() linearises (lambda_0 needs max |H_jj| of that very pass)
+  const bool keep_lin = h->lin_valid && !iteration0;
+  c.lin = h->lin; c.need_linearize = keep_lin ? 0 : 1; c.need_fold = keep_lin ? 1 : 0; c.current_chi = keep_lin ? h->current_chi : 0.0;
   c.max_iters = max_iters; c.last_result = SSBA_SOLVER_OK;
   c.world = h->opt.world_size; c.rank = h->opt.rank;
   c.trial_seq = h->trial_seq;
@@ -316,23 +329,31 @@ ssba_status run_lm(ssba_handle *h, int max_iters, bool iteration0) {
   bool first = true;
   int guard = 0;
   const int max_slots = max_iters * (c.max_trials > 0 ? c.max_trials : 1) + 1;
+  const bool fused_lin = update_linearizes(h->P);
+  bool want_lin = c.need_linearize != 0;
   while (!c.done) {
     // optimistic batch: one slot per outstanding outer iteration (every trial accepted)
     int batch = max_iters - c.outer_iter;
     if (batch < 1) batch = 1;
     for (int i = 0; i < batch; ++i) {
-      ssba_status rc = enqueue_slot(h, first);
+      ssba_status rc = enqueue_slot(h, first, !fused_lin || want_lin);
       if (rc) return rc;
-      first = false;
+      first = false; want_lin = false;
     }
     CUDA_TRY(h, cudaMemcpyAsync(&c, h->P.ctl, sizeof(Control), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     CUDA_TRY(h, cudaGetLastError());
+    if (c.done == 2) {  // paused for a linearising slot (see control_step)
+      c.done = 0; want_lin = true;
+      CUDA_TRY(h, cudaMemcpyAsync(&h->P.ctl->done, &c.done, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
     if (c.done) break;
     guard += batch;
     if (guard > max_slots) return fail(h, SSBA_ERR_STATE, "LM driver did not terminate");
   }
   h->cur = c.cur; h->lambda = c.lambda; h->ni = c.ni;
+  h->lin = c.lin; h->lin_valid = c.lin_valid != 0; h->current_chi = c.current_chi;
   h->trial_seq = c.trial_seq;
   h->prof.levenberg_iterations += c.n_trials;
   h->prof.outer_iterations += c.outer_iter;
@@ -642,7 +663,7 @@ ssba_status ssba_initialize(ssba_handle *h) {
     bytes_a = align_up(top);
     DYN(pose[0], 7 * g.n_poses, double); DYN(pose[1], 7 * g.n_poses, double);
     DYN(point[0], 3 * (size_t)g.n_points, double); DYN(point[1], 3 * (size_t)g.n_points, double);
-    DYN(W, 18 * (size_t)s.n_pairs, double); DYN(Hll, 6 * (size_t)s.n_slots, double); DYN(bl, 3 * (size_t)s.n_slots, double);
+    for (int k = 0; k < 2; ++k) { DYN(W[k], 18 * (size_t)s.n_pairs, double); DYN(Hll[k], 6 * (size_t)s.n_slots, double); DYN(bl[k], 3 * (size_t)s.n_slots, double); }
     DYN(Dinv, 6 * (size_t)s.n_slots, double);
     DYN(gather, h->opt.world_size > 1 ? 3 * (size_t)g.n_points : 0, double); DYN(err_out, 2 * (size_t)g.n_edges, double);
     DYN(mask_out, (size_t)g.n_edges, uint8_t);
@@ -694,7 +715,8 @@ ssba_status ssba_initialize(ssba_handle *h) {
   P.n_lin_blocks = P.n_upd_blocks = s.n_lchunks;
   const int nblk = std::max(P.n_fin_blocks, s.n_lchunks);
   P.sys_doubles = 36 * (size_t)s.n_blocks + 12 * (size_t)s.n_fp;
-  DYN(hpp_part, 27 * (size_t)s.n_hpp_parts, double); DYN(hpp_fold, 27 * (size_t)s.n_fp, double);
+  DYN(hpp_part[0], 27 * (size_t)s.n_hpp_parts, double); DYN(hpp_part[1], 27 * (size_t)s.n_hpp_parts, double);
+  DYN(hpp_fold, 27 * (size_t)s.n_fp, double);
   DYN(sys, P.sys_doubles, double); DYN(xp, 6 * (size_t)s.n_fp, double); DYN(diag_buf, 6 * (size_t)s.n_fp, double);
   DYN(chi_cur_part, nblk, double); DYN(maxdiag_part, nblk, double); DYN(chi_new_part, nblk, double); DYN(scale_part, nblk, double);
   DYN(scal, 8, double); DYN(chi_out, 8, double);
@@ -750,6 +772,7 @@ ssba_status ssba_initialize(ssba_handle *h) {
     if (h->use_p2p) CUDA_TRY(h, cudaMemsetAsync(h->xchg + sizeof(PeerHeader), 0, 2 * sizeof(double) * P.sys_doubles, h->stream));
   }
   P.n_units = s.n_units;
+  P.pdl = pdl_enabled(h) ? 1 : 0;
   h->initialized = true;
   h->dirty = false;
   h->topo_dirty = false;
@@ -787,6 +810,7 @@ ssba_status ssba_reset_state(ssba_handle *h) {
   // k_schur accumulates into a zeroed reduced system; after the first trial k_update keeps it so
   CUDA_TRY(h, cudaMemsetAsync(P.sys, 0, sizeof(double) * P.sys_doubles, h->stream));
   h->cur = 0; h->lambda = -1.0; h->ni = 2.0;
+  h->lin = 0; h->lin_valid = false;
   // the controller must name buffer 0 for the read-out kernels even before the first optimize
   std::memset(h->h_ctl, 0, sizeof(Control));
   h->h_ctl->world = h->opt.world_size; h->h_ctl->rank = h->opt.rank;
@@ -1225,6 +1249,7 @@ ssba_status ssba_set_profiling(ssba_handle *h, int32_t on) {
   if (!h) return SSBA_ERR_INVALID_ARG;
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->opt.profile = on ? 1 : 0;
+  h->P.pdl = pdl_enabled(h) ? 1 : 0;
   h->spans.clear();
   h->ev_used = 0;
   return SSBA_OK;

@@ -26,7 +26,10 @@ struct Control {
   double maxdiag;          // max |H_jj| for computeLambdaInit
   double chi2_initial;
   int cur;                 // which of the two state buffers holds the current estimate
-  int need_linearize;      // next slot starts a new outer iteration (buildSystem)
+  int need_linearize;      // next slot starts a new outer iteration (buildSystem) and k_linearize has to run
+  int need_fold;           // the linearisation is new (made by k_update of the accepted trial): fold its Hpp partials
+  int lin;                 // which of the two sets of linearisation buffers (W, Hll, b_l, Hpp partials) is current
+  int lin_valid;           // buffers `lin` hold the linearisation of the current estimate
   int first_iteration;     // lambda must be initialised (iteration == 0)
   int done;                // optimize() finished: every kernel returns immediately
   int outer_iter, max_iters;
@@ -103,11 +106,13 @@ struct DeviceProblem {
   int solve_cluster;               // CTAs the solver program was dealt over (1, 2, 4, 8)
   TreeDev tree;                    // k_tree_solve's program; tree.C == 0: k_reduced_solve and the level program
   // system
-  double *W;          // n_pairs x 18, 6x3 row-major  (Hpl blocks)
-  double *Hll;        // n_slots x 6 (xx xy xz yy yz zz)
-  double *bl;         // n_slots x 3
+  // the linearisation, two sets: Control::lin names the one of the current estimate, k_update writes the trial
+  // state's into the other one
+  double *W[2];          // n_pairs x 18, 6x3 row-major  (Hpl blocks)
+  double *Hll[2];        // n_slots x 6 (xx xy xz yy yz zz)
+  double *bl[2];         // n_slots x 3
+  double *hpp_part[2];   // n_hpp_parts x 27 (b[6], upper-tri H[21])
   double *Dinv;       // n_slots x 6
-  double *hpp_part;   // n_hpp_parts x 27 (b[6], upper-tri H[21])
   double *hpp_fold;   // n_fp x 27: the partials of each pose folded (k_prepare_system)
   double *sys;        // [ L: n_blocks x 36 | bschur: n_fp x 6 | bp: n_fp x 6 ] — the all-reduced buffer
   double *xp;         // n_fp x 6
@@ -125,9 +130,28 @@ struct DeviceProblem {
   // mapped into this process; layout per rank: PeerHeader, then 2 x sys_doubles partial reduced systems
   char *peer[SSBA_MAX_PEERS];
   int use_p2p;
+  int pdl;  // launch k_schur / the reduced solve / k_update with programmatic dependent launch (off while profiling)
   size_t sys_doubles;
   int n_edges_total;
 };
+
+// Programmatic dependent launch (griddepcontrol): a kernel launched with the attribute may start while its
+// predecessor in the stream still runs; everything before griddep_wait() must only touch STATIC data (the index
+// structure), griddep_wait() returns once the predecessor has completed and its writes are visible.
+// griddep_launch() lets the successor's CTAs be scheduled from here on.  Both are no-ops in a plain launch.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+template <class... KArgs, class... Args>
+inline cudaError_t launch_maybe_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 
 // launches (all asynchronous on `st`)
 void launch_linearize(const DeviceProblem &P, cudaStream_t st);        // K_lin + K_hpp + hpp reduce
@@ -137,6 +161,7 @@ void launch_lambda_init(const DeviceProblem &P, cudaStream_t st);
 void launch_schur(const DeviceProblem &P, bool prefolded, cudaStream_t st);
 void launch_reduced_solve(const DeviceProblem &P, cudaStream_t st);
 void launch_update(const DeviceProblem &P, bool fused_control, cudaStream_t st);  // + accept/reject when fused
+bool update_linearizes(const DeviceProblem &P);  // k_update also linearises the trial state (closed-form Jacobians)
 void launch_reduce_partials(const DeviceProblem &P, cudaStream_t st);  // -> scal[0..2]
 void launch_control(const DeviceProblem &P, cudaStream_t st);          // several GPUs only
 void launch_exchange_sys(const DeviceProblem &P, cudaStream_t st);     // peer-memory all-reduce of the reduced system

@@ -112,7 +112,7 @@ struct PairLin {
 // `hp` (27 doubles, the caller's own row of shared memory or a global partial) receives the pose
 // side: b_p[6], then the upper triangle of J_xi^T (rho' Omega) J_xi [21]
 template <int kMode>
-__device__ __forceinline__ void linearize_pair(const DeviceProblem &P, int a, bool lfree, const double *pose,
+__device__ __forceinline__ void linearize_pair(const DeviceProblem &P, double *Wout, int a, bool lfree, const double *pose,
                                                const double *p, PairLin &o, double *hp) {
   const int kv = P.pair_vertex[a];
   const bool pfree = P.pair_q[a] >= 0;
@@ -178,7 +178,7 @@ __device__ __forceinline__ void linearize_pair(const DeviceProblem &P, int a, bo
     }
   }
   if (wpair) {
-    double2 *dst = reinterpret_cast<double2 *>(P.W + 18 * (size_t)a);
+    double2 *dst = reinterpret_cast<double2 *>(Wout + 18 * (size_t)a);
 #pragma unroll
     for (int i = 0; i < 9; ++i) dst[i] = make_double2(o.W[2 * i], o.W[2 * i + 1]);
   }
@@ -195,7 +195,7 @@ __device__ __forceinline__ void linearize_pair(const DeviceProblem &P, int a, bo
 __device__ __forceinline__ void cross3(const double *a, double x, double y, double z, double &ox, double &oy, double &oz) {
   ox = a[1] * z - a[2] * y; oy = a[2] * x - a[0] * z; oz = a[0] * y - a[1] * x;
 }
-__device__ __forceinline__ void linearize_pair_factored(const DeviceProblem &P, int a, bool lfree, const double *pose,
+__device__ __forceinline__ void linearize_pair_factored(const DeviceProblem &P, double *Wout, int a, bool lfree, const double *pose,
                                                         const double *p, PairLin &o, double *hp) {
   const int kv = P.pair_vertex[a];
   const bool pfree = P.pair_q[a] >= 0;
@@ -302,59 +302,61 @@ __device__ __forceinline__ void linearize_pair_factored(const DeviceProblem &P, 
         for (int c = 0; c < 3; ++c) Wv[3 * r + c] = MR[r][c];
 #pragma unroll
       for (int c = 0; c < 3; ++c) cross3(b, MR[0][c], MR[1][c], MR[2][c], Wv[9 + c], Wv[12 + c], Wv[15 + c]);
-      double2 *dst = reinterpret_cast<double2 *>(P.W + 18 * (size_t)a);
+      double2 *dst = reinterpret_cast<double2 *>(Wout + 18 * (size_t)a);
 #pragma unroll
       for (int i = 0; i < 9; ++i) dst[i] = make_double2(Wv[2 * i], Wv[2 * i + 1]);
     }
   }
 }
 
+// shared memory of one chunk's linearisation (k_linearize, and k_update when it linearises the trial state)
+struct LinSmem {
+  double part[kLinThreads][9];
+  double hp[kLinThreads][27];
+  double red[kLinThreads / 32];
+  int lp_ptr[kLinThreads + 1];
+  uint8_t lp_pair[kLinThreads];
+};
+
+// The linearisation of chunk `blockIdx.x` at the state (pose, point) into the buffers `lin`: W, Hll, b_l, the
+// Hpp / b_p partials of the chunk's poses; returns this thread's share of the robust chi2 and of max |Hll_jj|.
 template <int kMode>
-// measured on B200 (cfg3): per-edge expansion 29 us (168 registers, spills); factored per pair 23 us at three
-// CTAs per SM, 24 us at four (125 registers) - the kernel is bound by its dependent-load chains, not occupancy
-__global__ void __launch_bounds__(kLinThreads, SSBA_LIN_MINB) k_linearize(const DeviceProblem P) {
-  const Control *ctl = P.ctl;
-  if (ctl->done || !ctl->need_linearize) return;
-  __shared__ double red[kLinThreads / 32];
-  __shared__ double s_part[kLinThreads][9];
-  __shared__ double s_hp[kLinThreads][27];
-  const int cur = ctl->cur;
-  const double *__restrict__ pose = P.pose[cur];
-  const double *__restrict__ point = P.point[cur];
+// (`point` is NOT restrict / read-only: k_update reads positions its own CTA has just written)
+__device__ __forceinline__ void linearize_chunk(const DeviceProblem &P, int lin, const double *__restrict__ pose,
+                                                const double *point, LinSmem &sm, double &chi, double &mx) {
+  double *Wout = P.W[lin], *Hll = P.Hll[lin], *bl = P.bl[lin], *hpp_part = P.hpp_part[lin];
   const int s0 = P.lchunk_slot[blockIdx.x], s1 = P.lchunk_slot[blockIdx.x + 1];
   const int lp0 = P.lchunk_lp_ptr[blockIdx.x], lp1 = P.lchunk_lp_ptr[blockIdx.x + 1];
   const int a0 = P.slot_pair_ptr[s0], a1 = P.slot_pair_ptr[s1];
   const int tid = threadIdx.x;
-  double chi = 0.0, mx = 0.0;
+  chi = 0.0; mx = 0.0;
   if (a1 - a0 <= kLinThreads) {
     // the chunk's local-pose lists, fetched now and used after the barrier (their latency hides
     // behind the linearisation)
-    __shared__ int s_lp_ptr[kLinThreads + 1];
-    __shared__ uint8_t s_lp_pair[kLinThreads];
     const int lpp0 = P.lp_pair_ptr[lp0];
-    if (tid <= lp1 - lp0) s_lp_ptr[tid] = P.lp_pair_ptr[lp0 + tid] - lpp0;
-    if (tid < P.lp_pair_ptr[lp1] - lpp0) s_lp_pair[tid] = P.lp_pair[lpp0 + tid];
+    if (tid <= lp1 - lp0) sm.lp_ptr[tid] = P.lp_pair_ptr[lp0 + tid] - lpp0;
+    if (tid < P.lp_pair_ptr[lp1] - lpp0) sm.lp_pair[tid] = P.lp_pair[lpp0 + tid];
     if (tid < a1 - a0) {
       const int a = a0 + tid;
       const int sl = P.pair_slot[a];
       const int pv = P.slot_vertex[sl];
       const double p[3] = {point[3 * pv], point[3 * pv + 1], point[3 * pv + 2]};
       PairLin o;
-      if (kMode == SSBA_JACOBIAN_ANALYTIC) linearize_pair_factored(P, a, P.slot_free[sl] != 0, pose, p, o, s_hp[tid]);
-      else linearize_pair<kMode>(P, a, P.slot_free[sl] != 0, pose, p, o, s_hp[tid]);
+      if (kMode == SSBA_JACOBIAN_ANALYTIC) linearize_pair_factored(P, Wout, a, P.slot_free[sl] != 0, pose, p, o, sm.hp[tid]);
+      else linearize_pair<kMode>(P, Wout, a, P.slot_free[sl] != 0, pose, p, o, sm.hp[tid]);
       chi = o.chi;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) s_part[tid][i] = o.H[i];
+      for (int i = 0; i < 6; ++i) sm.part[tid][i] = o.H[i];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) s_part[tid][6 + i] = o.b[i];
+      for (int i = 0; i < 3; ++i) sm.part[tid][6 + i] = o.b[i];
     }
     __syncthreads();
     // pose side: fold the pairs of every distinct pose of this chunk, in pair order
     for (int w = tid; w < 27 * (lp1 - lp0); w += kLinThreads) {
       const int lp = lp0 + w / 27, k = w % 27;
       double acc = 0.0;
-      for (int i = s_lp_ptr[lp - lp0]; i < s_lp_ptr[lp - lp0 + 1]; ++i) acc += s_hp[s_lp_pair[i]][k];
-      P.hpp_part[27 * (size_t)lp + k] = acc;
+      for (int i = sm.lp_ptr[lp - lp0]; i < sm.lp_ptr[lp - lp0 + 1]; ++i) acc += sm.hp[sm.lp_pair[i]][k];
+      hpp_part[27 * (size_t)lp + k] = acc;
     }
     const int sl = s0 + tid;
     if (sl < s1 && P.slot_free[sl]) {
@@ -363,12 +365,12 @@ __global__ void __launch_bounds__(kLinThreads, SSBA_LIN_MINB) k_linearize(const 
       for (int i = 0; i < 9; ++i) acc[i] = 0.0;
       for (int a = P.slot_pair_ptr[sl] - a0; a < P.slot_pair_ptr[sl + 1] - a0; ++a) {
 #pragma unroll
-        for (int i = 0; i < 9; ++i) acc[i] += s_part[a][i];
+        for (int i = 0; i < 9; ++i) acc[i] += sm.part[a][i];
       }
 #pragma unroll
-      for (int i = 0; i < 6; ++i) P.Hll[6 * (size_t)sl + i] = acc[i];
+      for (int i = 0; i < 6; ++i) Hll[6 * (size_t)sl + i] = acc[i];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) P.bl[3 * (size_t)sl + i] = acc[6 + i];
+      for (int i = 0; i < 3; ++i) bl[3 * (size_t)sl + i] = acc[6 + i];
       mx = fmax(fabs(acc[0]), fmax(fabs(acc[3]), fabs(acc[5])));
     }
   } else {
@@ -385,9 +387,9 @@ __global__ void __launch_bounds__(kLinThreads, SSBA_LIN_MINB) k_linearize(const 
     for (int a = a0 + tid; a < a1; a += kLinThreads) {
       PairLin o;
       // free-pose pairs come first inside a landmark, so the rank of one is simply a - a0
-      double *hp_dst = P.pair_q[a] >= 0 ? P.hpp_part + 27 * (size_t)(lp0 + (a - a0)) : s_hp[tid];
-      if (kMode == SSBA_JACOBIAN_ANALYTIC) linearize_pair_factored(P, a, lfree, pose, p, o, hp_dst);
-      else linearize_pair<kMode>(P, a, lfree, pose, p, o, hp_dst);
+      double *hp_dst = P.pair_q[a] >= 0 ? hpp_part + 27 * (size_t)(lp0 + (a - a0)) : sm.hp[tid];
+      if (kMode == SSBA_JACOBIAN_ANALYTIC) linearize_pair_factored(P, Wout, a, lfree, pose, p, o, hp_dst);
+      else linearize_pair<kMode>(P, Wout, a, lfree, pose, p, o, hp_dst);
       chi += o.chi;
 #pragma unroll
       for (int i = 0; i < 6; ++i) acc[i] += o.H[i];
@@ -395,24 +397,36 @@ __global__ void __launch_bounds__(kLinThreads, SSBA_LIN_MINB) k_linearize(const 
       for (int i = 0; i < 3; ++i) acc[6 + i] += o.b[i];
     }
 #pragma unroll
-    for (int i = 0; i < 9; ++i) acc[i] = block_sum<kLinThreads>(acc[i], red);
+    for (int i = 0; i < 9; ++i) acc[i] = block_sum<kLinThreads>(acc[i], sm.red);
     if (tid == 0 && lfree) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) P.Hll[6 * (size_t)sl + i] = acc[i];
+      for (int i = 0; i < 6; ++i) Hll[6 * (size_t)sl + i] = acc[i];
 #pragma unroll
-      for (int i = 0; i < 3; ++i) P.bl[3 * (size_t)sl + i] = acc[6 + i];
+      for (int i = 0; i < 3; ++i) bl[3 * (size_t)sl + i] = acc[6 + i];
       mx = fmax(fabs(acc[0]), fmax(fabs(acc[3]), fabs(acc[5])));
     }
   }
-  const double s_ = block_sum<kLinThreads>(chi, red);
-  const double m = block_max<kLinThreads>(mx, red);
-  if (tid == 0) { P.chi_cur_part[blockIdx.x] = s_; P.maxdiag_part[blockIdx.x] = m; }
+}
+
+template <int kMode>
+// measured on B200 (cfg3): per-edge expansion 29 us (168 registers, spills); factored per pair 23 us at three
+// CTAs per SM, 24 us at four (125 registers) - the kernel is bound by its dependent-load chains, not occupancy
+__global__ void __launch_bounds__(kLinThreads, SSBA_LIN_MINB) k_linearize(const DeviceProblem P) {
+  const Control *ctl = P.ctl;
+  if (ctl->done || !ctl->need_linearize) return;
+  __shared__ LinSmem sm;
+  const int cur = ctl->cur;
+  double chi, mx;
+  linearize_chunk<kMode>(P, ctl->lin, P.pose[cur], P.point[cur], sm, chi, mx);
+  const double s_ = block_sum<kLinThreads>(chi, sm.red);
+  const double m = block_max<kLinThreads>(mx, sm.red);
+  if (threadIdx.x == 0) { P.chi_cur_part[blockIdx.x] = s_; P.maxdiag_part[blockIdx.x] = m; }
 }
 
 // Hpp / b_p of pose q (entry k: 0..5 = b, 6..26 = upper triangle): the partials the linearize CTAs
 // wrote for the pose, folded in chunk order (deterministic).  One warp per pose, lane k < 27 owns
 // entry k; the loads of sixteen partials are in flight together, the adds stay in list order.
-__device__ __forceinline__ double warp_fold_pose(const DeviceProblem &P, int q, int lane) {
+__device__ __forceinline__ double warp_fold_pose(const DeviceProblem &P, const double *__restrict__ hpp_part, int q, int lane) {
   double s = 0.0;
   const int i0 = P.q_part_ptr[q], i1 = P.q_part_ptr[q + 1];
   for (int base = i0; base < i1; base += 32) {
@@ -423,7 +437,7 @@ __device__ __forceinline__ double warp_fold_pose(const DeviceProblem &P, int q, 
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int part = __shfl_sync(0xffffffffu, mine, (j0 + j) & 31);
-        v[j] = (j0 + j < cnt && lane < 27) ? P.hpp_part[27 * (size_t)part + lane] : 0.0;
+        v[j] = (j0 + j < cnt && lane < 27) ? hpp_part[27 * (size_t)part + lane] : 0.0;
       }
 #pragma unroll
       for (int j = 0; j < 16; ++j) s += v[j];  // list order; the padding adds exact zeros
@@ -439,10 +453,10 @@ __device__ __forceinline__ int hpp_diag_index(int d) { return 6 + d * 6 - d * (d
 // all-reduce before k_maxdiag when there are several).  One warp per pose.
 __global__ void __launch_bounds__(128) k_fold(const DeviceProblem P) {
   const Control *ctl = P.ctl;
-  if (ctl->done || !ctl->need_linearize) return;
+  if (ctl->done || !(ctl->need_linearize || ctl->need_fold)) return;
   const int q = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (q >= P.n_fp) return;
-  const double s = warp_fold_pose(P, q, lane);
+  const double s = warp_fold_pose(P, P.hpp_part[ctl->lin], q, lane);
   if (lane < 27) P.hpp_fold[27 * q + lane] = s;
 #pragma unroll
   for (int d = 0; d < 6; ++d) if (lane == hpp_diag_index(d)) P.diag_buf[6 * q + d] = s;
@@ -499,8 +513,8 @@ __device__ __forceinline__ double *schur_target(const DeviceProblem &P, const Co
 __device__ __forceinline__ void schur_pose_warp(const DeviceProblem &P, const Control *ctl, int q, int lane,
                                                 bool prefolded) {
   double s;
-  if (ctl->need_linearize && !prefolded) {
-    s = warp_fold_pose(P, q, lane);
+  if ((ctl->need_linearize || ctl->need_fold) && !prefolded) {
+    s = warp_fold_pose(P, P.hpp_part[ctl->lin], q, lane);
     if (lane < 27) P.hpp_fold[27 * q + lane] = s;
   } else {
     s = lane < 27 ? P.hpp_fold[27 * q + lane] : 0.0;
@@ -525,23 +539,36 @@ __device__ __forceinline__ void schur_pose_warp(const DeviceProblem &P, const Co
 
 __global__ void __launch_bounds__(32 * kSchurWarps, 3) k_schur(const DeviceProblem P, int n_pose_ctas, int prefolded) {
   const Control *ctl = P.ctl;
-  if (ctl->done) return;
   extern __shared__ double s_w_all[];  // kSchurWarps x kSchurRunPairs x 18
   __shared__ double s_dinv[kSchurWarps][kSchurRun][6];
   __shared__ double s_db[kSchurWarps][kSchurRun][3];
   __shared__ int s_pair0[kSchurWarps][kSchurRun];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if ((int)blockIdx.x < n_pose_ctas) {
+  // ---- static part (index structure only): runs while the previous kernel of the stream is still busy
+  const bool pose_cta = (int)blockIdx.x < n_pose_ctas;
+  const int u = ((int)blockIdx.x - n_pose_ctas) * kSchurWarps + warp;
+  int s0 = 0, n = 0, k = 0, c0 = 0;
+  if (pose_cta) {
+    const int q = blockIdx.x * kSchurWarps + warp;
+    if (q < P.n_fp) { prefetch_l1(P.q_part_ptr + q); prefetch_l1(P.col_diag + q); }
+  } else if (u < P.n_units) {
+    s0 = P.unit_slot[u]; n = P.unit_n[u]; k = P.unit_k[u]; c0 = P.unit_c0[u];
+    if (lane < n) s_pair0[warp][lane] = P.slot_pair_ptr[s0 + lane];
+    prefetch_l1(P.combo_blk + P.unit_combo_ptr[u] + lane);
+  }
+  griddep_wait();
+  griddep_launch();
+  if (ctl->done) return;
+  if (pose_cta) {
     const int q = blockIdx.x * kSchurWarps + warp;
     if (q < P.n_fp) schur_pose_warp(P, ctl, q, lane, prefolded != 0);
     return;
   }
-  const int u = ((int)blockIdx.x - n_pose_ctas) * kSchurWarps + warp;
   if (u >= P.n_units) return;  // whole warp; no block-wide barrier below
-  const int s0 = P.unit_slot[u], n = P.unit_n[u], k = P.unit_k[u], c0 = P.unit_c0[u];
+  const int lin = ctl->lin;
+  const double *__restrict__ Wl = P.W[lin], *__restrict__ Hlll = P.Hll[lin], *__restrict__ bll = P.bl[lin];
   double *s_w = s_w_all + (size_t)warp * kSchurRunPairs * 18;
   const bool staged = n * k <= kSchurRunPairs;
-  if (lane < n) s_pair0[warp][lane] = P.slot_pair_ptr[s0 + lane];
   __syncwarp();
   if (staged) {
     // the run's W blocks (k consecutive 6x3 blocks per landmark) -> shared memory, asynchronously
@@ -550,7 +577,7 @@ __global__ void __launch_bounds__(32 * kSchurWarps, 3) k_schur(const DeviceProbl
       const int i = gi / per_lm, o = gi - i * per_lm;
       const unsigned sa = (unsigned)__cvta_generic_to_shared(s_w + 18 * (size_t)(i * k) + 2 * o);
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa),
-                   "l"(P.W + 18 * (size_t)s_pair0[warp][i] + 2 * o));
+                   "l"(Wl + 18 * (size_t)s_pair0[warp][i] + 2 * o));
     }
     asm volatile("cp.async.commit_group;\n" ::);
   }
@@ -559,10 +586,10 @@ __global__ void __launch_bounds__(32 * kSchurWarps, 3) k_schur(const DeviceProbl
     const size_t sl = (size_t)(s0 + lane);
     double H[6], Di[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) H[i] = P.Hll[6 * sl + i];
+    for (int i = 0; i < 6; ++i) H[i] = Hlll[6 * sl + i];
     H[0] += lambda; H[3] += lambda; H[5] += lambda;
     sym3_inverse(H, Di);
-    const double b0 = P.bl[3 * sl], b1 = P.bl[3 * sl + 1], b2 = P.bl[3 * sl + 2];
+    const double b0 = bll[3 * sl], b1 = bll[3 * sl + 1], b2 = bll[3 * sl + 2];
 #pragma unroll
     for (int i = 0; i < 6; ++i) s_dinv[warp][lane][i] = Di[i];
     s_db[warp][lane][0] = Di[0] * b0 + Di[1] * b1 + Di[2] * b2;
@@ -601,8 +628,8 @@ __global__ void __launch_bounds__(32 * kSchurWarps, 3) k_schur(const DeviceProbl
         sb = reinterpret_cast<const double2 *>(s_w + 18 * (size_t)(i * k + b));
       } else {
         const int p0 = s_pair0[warp][i];
-        sa = reinterpret_cast<const double2 *>(P.W + 18 * (size_t)(p0 + a));
-        sb = reinterpret_cast<const double2 *>(P.W + 18 * (size_t)(p0 + b));
+        sa = reinterpret_cast<const double2 *>(Wl + 18 * (size_t)(p0 + a));
+        sb = reinterpret_cast<const double2 *>(Wl + 18 * (size_t)(p0 + b));
       }
       // BD = W_a Dinv, two rows of W_a per step (three 16-byte loads); kept short-lived on purpose:
       // with all of W_a, W_b and BD live the kernel needs 222 registers, i.e. two CTAs per SM and
@@ -1145,7 +1172,7 @@ __global__ void __launch_bounds__(kSolveThreads) k_reduced_solve(const DevicePro
 // (levenberg.cpp:119-149) and the iteration bookkeeping of SparseOptimizer::optimize
 // (sparse_optimizer.cpp:386-426), on the device so that no host round trip sits between trials.
 // Runs on one thread once scal[0..2] = chi(current), chi(trial), landmark part of computeScale.
-__device__ void control_step(const DeviceProblem &P) {
+__device__ void control_step(const DeviceProblem &P, bool trial_linearized) {
   Control *c = P.ctl;
   c->trial_seq++;
   const double currentChi = P.scal[0];
@@ -1169,6 +1196,7 @@ __device__ void control_step(const DeviceProblem &P) {
     c->lambda *= scaleFactor;
     c->ni = 2;
     c->cur ^= 1;  // discardTop(): the trial buffer becomes the estimate
+    if (trial_linearized) c->lin ^= 1;  // ... and k_update's linearisation of it the current one
     accepted = true;
   } else {
     c->lambda *= c->ni;
@@ -1184,6 +1212,7 @@ __device__ void control_step(const DeviceProblem &P) {
   const bool again = !broke && rho < 0 && c->qmax < c->max_trials && !stop;
   if (again) {
     c->need_linearize = 0;
+    c->need_fold = 0;
     return;
   }
   const int result = (c->qmax == c->max_trials || rho == 0 || !isfinite(c->lambda))
@@ -1195,7 +1224,14 @@ __device__ void control_step(const DeviceProblem &P) {
   c->last_result = result;
   c->outer_iter++;
   c->qmax = 0;
-  c->need_linearize = 1;
+  // the next iteration starts from a linearisation: the one k_update made of the accepted trial, or k_linearize's
+  c->need_linearize = (accepted && trial_linearized) ? 0 : 1;
+  c->need_fold = (accepted && trial_linearized) ? 1 : 0;
+  c->lin_valid = (accepted && trial_linearized) ? 1 : 0;
+  // k_update linearises: the host does not enqueue k_linearize with every slot.  An iteration that ends without an
+  // accepted step AND without Terminate (rho is NaN) needs one: pause (every kernel returns on done != 0) until the
+  // host has seen it and enqueues a linearising slot.
+  if (trial_linearized && c->need_linearize) c->done = 2;
   if (result != SSBA_SOLVER_OK || c->outer_iter >= c->max_iters || stop) c->done = 1;  // sparse_optimizer.cpp:388
 }
 
@@ -1214,13 +1250,20 @@ __device__ __forceinline__ void fold_partials(const DeviceProblem &P, double *re
     }
     return acc;
   };
-  double a = strided_sum(P.chi_cur_part, P.n_lin_blocks);
+  // chi2 of the current state: k_linearize's partial sums when it ran in this slot, else the value the last decision
+  // left (the accepted trial's chi2, or the unchanged one of a re-trial); several ranks add their parts up, so only
+  // rank 0 contributes the kept value
+  const Control *ctl = P.ctl;
+  double a = ctl->need_linearize ? strided_sum(P.chi_cur_part, P.n_lin_blocks) : 0.0;
   double b = strided_sum(P.chi_new_part, P.n_upd_blocks);
   double c = strided_sum(P.scale_part, P.n_upd_blocks);
   a = block_sum<NT>(a, red);
   b = block_sum<NT>(b, red);
   c = block_sum<NT>(c, red);
-  if (threadIdx.x == 0) { P.scal[0] = a; P.scal[1] = b; P.scal[2] = c; }
+  if (threadIdx.x == 0) {
+    if (!ctl->need_linearize) a = ctl->rank == 0 ? ctl->current_chi : 0.0;
+    P.scal[0] = a; P.scal[1] = b; P.scal[2] = c;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1245,11 +1288,11 @@ __device__ __forceinline__ double pair_trial_chi(const DeviceProblem &P, int a, 
   return chi;
 }
 
-__device__ __forceinline__ void pair_wtx(const DeviceProblem &P, int a, double *c3) {
+__device__ __forceinline__ void pair_wtx(const DeviceProblem &P, const double *__restrict__ Wl, int a, double *c3) {
   c3[0] = c3[1] = c3[2] = 0.0;
   const int q = P.pair_q[a];
   if (q < 0) return;
-  const double2 *src = reinterpret_cast<const double2 *>(P.W + 18 * (size_t)a);
+  const double2 *src = reinterpret_cast<const double2 *>(Wl + 18 * (size_t)a);
   double Wv[18];
 #pragma unroll
   for (int i = 0; i < 9; ++i) { const double2 t = src[i]; Wv[2 * i] = t.x; Wv[2 * i + 1] = t.y; }
@@ -1265,12 +1308,36 @@ __device__ __forceinline__ void pair_wtx(const DeviceProblem &P, int a, double *
 // atomic accumulation of the next trial's k_schur.  kFusedControl (single GPU): the CTA that
 // finishes last folds the partial sums and takes the accept/reject decision (control_step), so
 // no separate launch sits between two trials.
-template <bool kFusedControl>
-__global__ void __launch_bounds__(kLinThreads) k_update(const DeviceProblem P) {
+// kFusedLin (closed-form Jacobians): the trial residuals are not just summed - the trial state is LINEARISED
+// into the other set of buffers (W, Hll, b_l, Hpp partials), exactly as k_linearize would do at the start of the
+// next iteration if the trial is accepted.  control_step then flips Control::lin together with Control::cur and the
+// next slot's k_linearize has nothing to do (three launches per accepted iteration); a rejected trial keeps the
+// old buffers, like the reference keeps its linearisation across the trials of one iteration.
+template <bool kFusedControl, bool kFusedLin>
+__global__ void __launch_bounds__(kLinThreads, kFusedLin ? SSBA_LIN_MINB : 4) k_update(const DeviceProblem P) {
   Control *ctl = P.ctl;
-  if (ctl->done) return;
-  __shared__ double red[kLinThreads / 32];
+  __shared__ LinSmem sm;
   __shared__ int s_last;
+  double *red = sm.red;
+  // ---- static part (index structure only): runs while the reduced solve is still busy on its few SMs; the index
+  // lines this CTA is going to walk are pulled into L1 now
+  const int s0 = P.lchunk_slot[blockIdx.x], s1 = P.lchunk_slot[blockIdx.x + 1];
+  const int a0 = P.slot_pair_ptr[s0], a1 = P.slot_pair_ptr[s1];
+  const int tid = threadIdx.x;
+  {
+    const int a = a0 + tid;
+    if (a < a1) {
+      prefetch_l1(P.pair_q + a); prefetch_l1(P.pair_vertex + a); prefetch_l1(P.pair_edge_ptr + a);
+      const int sl = P.pair_slot[a], e0 = P.pair_edge_ptr[a];
+      prefetch_l1(P.slot_free + sl); prefetch_l1(P.slot_vertex + sl);
+      prefetch_l1(P.e_uv + 2 * (size_t)e0); prefetch_l1(P.e_cam + e0);
+    }
+    if (s0 + tid < s1) prefetch_l1(P.slot_pair_ptr + s0 + tid);
+    if (tid == 0) { prefetch_l1(P.lchunk_lp_ptr + blockIdx.x); }
+  }
+  griddep_wait();
+  griddep_launch();
+  if (ctl->done) return;
   {
     const size_t nz = 36 * (size_t)P.n_blocks + 6 * (size_t)P.n_fp;  // blocks and bschur; b_p is overwritten
     // peer-memory exchange: the partial the NEXT trial accumulates into is the one the peers read
@@ -1279,26 +1346,24 @@ __global__ void __launch_bounds__(kLinThreads) k_update(const DeviceProblem P) {
                           : P.sys;
     for (size_t i = (size_t)blockIdx.x * kLinThreads + threadIdx.x; i < nz; i += (size_t)gridDim.x * kLinThreads) z[i] = 0.0;
   }
-  __shared__ double s_part[kLinThreads][3];
-  __shared__ double s_pnew[kLinThreads][3];
-  const int cur = ctl->cur;
+  double (*s_part)[9] = sm.part;          // [a][0..2]: W^T x_p of the pair
+  double (*s_pnew)[27] = sm.hp;           // [slot - s0][0..2]: the landmark's trial position (plain path)
+  const int cur = ctl->cur, lin = ctl->lin;
   const bool fail = ctl->chol_fail != 0;
   const double lambda = ctl->lambda;
   const double *__restrict__ pose_new = P.pose[cur ^ 1];
-  const int s0 = P.lchunk_slot[blockIdx.x], s1 = P.lchunk_slot[blockIdx.x + 1];
-  const int a0 = P.slot_pair_ptr[s0], a1 = P.slot_pair_ptr[s1];
-  const int tid = threadIdx.x;
+  const double *__restrict__ Wl = P.W[lin], *__restrict__ bll = P.bl[lin];
   const bool small = a1 - a0 <= kLinThreads;
   double chi = 0.0, scale = 0.0;
   // ---- W^T x_p per pair
   double c3[3] = {0.0, 0.0, 0.0};
   if (small) {
-    if (tid < a1 - a0 && P.slot_free[P.pair_slot[a0 + tid]]) pair_wtx(P, a0 + tid, c3);
+    if (tid < a1 - a0 && P.slot_free[P.pair_slot[a0 + tid]]) pair_wtx(P, Wl, a0 + tid, c3);
     s_part[tid][0] = c3[0]; s_part[tid][1] = c3[1]; s_part[tid][2] = c3[2];
   } else if (P.slot_free[s0]) {
     for (int a = a0 + tid; a < a1; a += kLinThreads) {
       double t3[3];
-      pair_wtx(P, a, t3);
+      pair_wtx(P, Wl, a, t3);
       c3[0] += t3[0]; c3[1] += t3[1]; c3[2] += t3[2];
     }
 #pragma unroll
@@ -1312,7 +1377,7 @@ __global__ void __launch_bounds__(kLinThreads) k_update(const DeviceProblem P) {
       const int pv = P.slot_vertex[sl];
       double p[3] = {P.point[cur][3 * pv], P.point[cur][3 * pv + 1], P.point[cur][3 * pv + 2]};
       if (P.slot_free[sl]) {
-        const double b0 = P.bl[3 * (size_t)sl], b1 = P.bl[3 * (size_t)sl + 1], b2 = P.bl[3 * (size_t)sl + 2];
+        const double b0 = bll[3 * (size_t)sl], b1 = bll[3 * (size_t)sl + 1], b2 = bll[3 * (size_t)sl + 2];
         double c0 = b0, c1 = b1, c2 = b2;
         if (small) {
           for (int a = P.slot_pair_ptr[sl] - a0; a < P.slot_pair_ptr[sl + 1] - a0; ++a) {
@@ -1330,12 +1395,16 @@ __global__ void __launch_bounds__(kLinThreads) k_update(const DeviceProblem P) {
         p[0] += x0; p[1] += x1; p[2] += x2;
         P.point[cur ^ 1][3 * pv] = p[0]; P.point[cur ^ 1][3 * pv + 1] = p[1]; P.point[cur ^ 1][3 * pv + 2] = p[2];
       }
-      s_pnew[tid][0] = p[0]; s_pnew[tid][1] = p[1]; s_pnew[tid][2] = p[2];
+      if (!kFusedLin) { s_pnew[tid][0] = p[0]; s_pnew[tid][1] = p[1]; s_pnew[tid][2] = p[2]; }
     }
   }
-  __syncthreads();
-  // ---- trial residuals per pair
-  if (small) {
+  __syncthreads();  // the trial positions of this chunk's landmarks are in place (global memory, written by this CTA)
+  // ---- trial residuals per pair (and, fused, the whole linearisation of the trial state)
+  if (kFusedLin) {
+    double mx;
+    linearize_chunk<SSBA_JACOBIAN_ANALYTIC>(P, lin ^ 1, pose_new, P.point[cur ^ 1], sm, chi, mx);
+    (void)mx;  // lambda_0 uses the first linearisation only (k_linearize)
+  } else if (small) {
     if (tid < a1 - a0) {
       const int a = a0 + tid;
       chi = pair_trial_chi(P, a, pose_new, s_pnew[P.pair_slot[a] - s0]);
@@ -1355,7 +1424,7 @@ __global__ void __launch_bounds__(kLinThreads) k_update(const DeviceProblem P) {
     if (!s_last) return;  // block-uniform
     __threadfence();
     fold_partials<kLinThreads>(P, red);
-    if (tid == 0) { ctl->ticket = 0; control_step(P); }
+    if (tid == 0) { ctl->ticket = 0; control_step(P, kFusedLin); }
   }
 }
 
@@ -1366,9 +1435,9 @@ __global__ void __launch_bounds__(256) k_reduce_partials(const DeviceProblem P) 
   fold_partials<256>(P, red);
 }
 
-__global__ void k_control(const DeviceProblem P) {
+__global__ void k_control(const DeviceProblem P, int trial_linearized) {
   if (P.ctl->done) return;
-  control_step(P);
+  control_step(P, trial_linearized != 0);
 }
 
 // ---- several GPUs: the two exchanges of a trial through NVLink peer memory instead of NCCL calls.
@@ -1438,7 +1507,7 @@ __global__ void __launch_bounds__(kXchgThreads) k_exchange_sys(const DeviceProbl
   if (blockIdx.x == 0 && threadIdx.x == 0) ctl->dbg[2] = gtime();
 }
 
-__global__ void __launch_bounds__(256) k_control_p2p(const DeviceProblem P) {
+__global__ void __launch_bounds__(256) k_control_p2p(const DeviceProblem P, int trial_linearized) {
   Control *ctl = P.ctl;
   if (ctl->done) return;
   if (threadIdx.x == 0) ctl->dbg[3] = gtime();
@@ -1470,7 +1539,7 @@ __global__ void __launch_bounds__(256) k_control_p2p(const DeviceProblem P) {
   ctl->dbg[5] = gtime();
   if (!ok) ctl->comm_timeout = 1;
   P.scal[0] = sa; P.scal[1] = sb; P.scal[2] = sc;
-  control_step(P);
+  control_step(P, trial_linearized != 0);
   ctl->dbg[6] = gtime();
 }
 
@@ -1682,7 +1751,7 @@ __global__ void __launch_bounds__(256) k_pg_chi_control(const DeviceProblem P, c
   b = block_sum<256>(b, red);
   if (threadIdx.x != 0) return;
   P.scal[0] = a; P.scal[1] = b; P.scal[2] = 0.0;
-  if (control) control_step(P);
+  if (control) control_step(P, false);
 }
 
 inline int div_up(long long a, int b) { return (int)((a + b - 1) / b); }
@@ -1734,7 +1803,7 @@ void launch_schur(const DeviceProblem &P, bool prefolded, cudaStream_t st) {
   constexpr size_t kDyn = (size_t)kSchurWarps * kSchurRunPairs * 18 * sizeof(double);
   once_per_device(seen, [] { cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDyn); });
   const int n_pose = div_up(P.n_fp, kSchurWarps), n_unit = div_up(P.n_units, kSchurWarps);
-  if (n_pose + n_unit > 0) k_schur<<<n_pose + n_unit, 32 * kSchurWarps, kDyn, st>>>(P, n_pose, prefolded ? 1 : 0);
+  if (n_pose + n_unit > 0) launch_maybe_pdl(k_schur, dim3(n_pose + n_unit), dim3(32 * kSchurWarps), kDyn, st, P.pdl != 0, P, n_pose, prefolded ? 1 : 0);
 }
 
 // The largest cluster (8, 4, 2 or 1 CTAs of kSolveThreads threads with the full dynamic shared memory)
@@ -1783,24 +1852,36 @@ void launch_reduced_solve(const DeviceProblem &P, cudaStream_t st) {
   else cudaLaunchKernelEx(&cfg, k_reduced_solve<8>, P, lay);
 }
 
+// k_update linearises the trial state itself (closed-form Jacobians; SSBA_FUSE_LIN=0 keeps the plain kernel)
+bool update_linearizes(const DeviceProblem &P) {
+  static const bool on = [] { const char *e = std::getenv("SSBA_FUSE_LIN"); return !(e && std::atoi(e) == 0); }();
+  return on && P.jacobian_mode == SSBA_JACOBIAN_ANALYTIC;
+}
+
 void launch_update(const DeviceProblem &P, bool fused_control, cudaStream_t st) {
   if (P.n_upd_blocks <= 0) return;
-  if (fused_control) k_update<true><<<P.n_upd_blocks, kLinThreads, 0, st>>>(P);
-  else k_update<false><<<P.n_upd_blocks, kLinThreads, 0, st>>>(P);
+  const bool lin = update_linearizes(P);
+  if (fused_control) {
+    if (lin) launch_maybe_pdl(k_update<true, true>, dim3(P.n_upd_blocks), dim3(kLinThreads), 0, st, P.pdl != 0, P);
+    else launch_maybe_pdl(k_update<true, false>, dim3(P.n_upd_blocks), dim3(kLinThreads), 0, st, P.pdl != 0, P);
+  } else {
+    if (lin) launch_maybe_pdl(k_update<false, true>, dim3(P.n_upd_blocks), dim3(kLinThreads), 0, st, P.pdl != 0, P);
+    else launch_maybe_pdl(k_update<false, false>, dim3(P.n_upd_blocks), dim3(kLinThreads), 0, st, P.pdl != 0, P);
+  }
 }
 
 void launch_reduce_partials(const DeviceProblem &P, cudaStream_t st) {
   k_reduce_partials<<<1, 256, 0, st>>>(P);
 }
 
-void launch_control(const DeviceProblem &P, cudaStream_t st) { k_control<<<1, 1, 0, st>>>(P); }
+void launch_control(const DeviceProblem &P, cudaStream_t st) { k_control<<<1, 1, 0, st>>>(P, update_linearizes(P) ? 1 : 0); }
 
 void launch_exchange_sys(const DeviceProblem &P, cudaStream_t st) {
   const int n = (int)std::min<size_t>(64, (P.sys_doubles / 2 + kXchgThreads - 1) / kXchgThreads);
   k_exchange_sys<<<n > 0 ? n : 1, kXchgThreads, 0, st>>>(P);
 }
 
-void launch_control_p2p(const DeviceProblem &P, cudaStream_t st) { k_control_p2p<<<1, 256, 0, st>>>(P); }
+void launch_control_p2p(const DeviceProblem &P, cudaStream_t st) { k_control_p2p<<<1, 256, 0, st>>>(P, update_linearizes(P) ? 1 : 0); }
 
 void launch_final_chi2(const DeviceProblem &P, double threshold, cudaStream_t st) {
   k_final_chi2<<<P.n_fin_blocks, kLinThreads, 0, st>>>(P, threshold, 0);

@@ -114,7 +114,6 @@ __device__ __forceinline__ long long ts_gtime() { long long t; asm volatile("mov
 template <bool kCluster>
 __global__ void __launch_bounds__(kTreeThreads, 1) k_tree_solve(const DeviceProblem P) {
   Control *ctl = P.ctl;
-  if (ctl->done) return;  // uniform over the cluster
   const TreeDev &T = P.tree;
   const int cta = kCluster ? (int)ts_cluster_ctarank() : 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -139,10 +138,24 @@ __global__ void __launch_bounds__(kTreeThreads, 1) k_tree_solve(const DeviceProb
     *s_fail = 0;
   }
   __syncthreads();
+  // the program is static: its copy starts while the previous kernel (k_schur) may still be running (programmatic
+  // dependent launch); the reduced system itself only after griddep_wait()
+  const unsigned bytes_blk = 288u * (unsigned)nblk, bytes_vec = 48u * (unsigned)ncols, bytes_prog = 4u * (unsigned)nwords;
   if (tid == 0) {
-    const unsigned bytes_blk = 288u * (unsigned)nblk, bytes_vec = 48u * (unsigned)ncols, bytes_prog = 4u * (unsigned)nwords;
     ts_mbar_arrive_expect_tx(bar, bytes_blk + 2u * bytes_vec + bytes_prog);
     if (bytes_prog) ts_bulk_g2s(prog, T.prog + T.prog_ptr[cta], bytes_prog, bar);
+  }
+  griddep_wait();
+  griddep_launch();
+  if (ctl->done) {  // uniform over the cluster; the program copy in flight must land before the CTA may exit
+    if (tid == 0) {
+      if (bytes_blk) ts_bulk_g2s(pool, P.sys + 36 * (size_t)T.b0[cta], bytes_blk, bar);
+      if (bytes_vec) { ts_bulk_g2s(pool + V0, bs + 6 * (size_t)q0, bytes_vec, bar); ts_bulk_g2s(pool + BP0, bs + 6 * (size_t)(P.n_fp + q0), bytes_vec, bar); }
+    }
+    ts_mbar_wait(bar, 0);
+    return;
+  }
+  if (tid == 0) {
     if (bytes_blk) ts_bulk_g2s(pool, P.sys + 36 * (size_t)T.b0[cta], bytes_blk, bar);
     if (bytes_vec) {
       ts_bulk_g2s(pool + V0, bs + 6 * (size_t)q0, bytes_vec, bar);                  // bschur
@@ -494,13 +507,15 @@ int max_tree_cluster() {
 void launch_tree_solve(const DeviceProblem &P, cudaStream_t st) {
   tree_setup_device();
   const int c = P.tree.C;
-  if (c == 1) { k_tree_solve<false><<<1, kTreeThreads, P.tree.smem_bytes, st>>>(P); return; }
+  if (c == 1) { launch_maybe_pdl(k_tree_solve<false>, dim3(1), dim3(kTreeThreads), P.tree.smem_bytes, st, P.pdl != 0, P); return; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(c); cfg.blockDim = dim3(kTreeThreads); cfg.dynamicSmemBytes = P.tree.smem_bytes; cfg.stream = st;
-  cudaLaunchAttribute attr{};
-  attr.id = cudaLaunchAttributeClusterDimension;
-  attr.val.clusterDim.x = c; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-  cfg.attrs = &attr; cfg.numAttrs = 1;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = c; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = P.pdl ? 2 : 1;
   cudaLaunchKernelEx(&cfg, k_tree_solve<true>, P);
 }
 
