@@ -24,6 +24,13 @@ int main(int argc, char **argv) {
   std::string err;
   if (!build_structure(g, 0, 1, s, err)) { std::printf("build failed: %s\n", err.c_str()); return 1; }
   std::printf("n_fp %d blocks %d schur blocks %d levels %d symbolic %.3f ms\n", s.n_fp, s.n_blocks, s.n_schur_blocks, s.n_levels, 1e3 * s.seconds_symbolic);
+  {
+    int mx = 0; long long tot = 0; std::vector<int> hist(12, 0);
+    for (int b = 0; b < s.n_blocks; ++b) { const int n = s.blk_prod_ptr[b + 1] - s.blk_prod_ptr[b]; mx = std::max(mx, n); tot += n; int k = 0; while ((1 << k) < n + 1 && k < 11) ++k; ++hist[k]; }
+    std::printf("schur units %d combos %zu  producers per block: max %d mean %.1f  histogram (<=1,2,4,...):", s.n_units, s.combo_blk.size(), mx, (double)tot / s.n_blocks);
+    for (int k = 0; k < 12; ++k) std::printf(" %d", hist[k]);
+    std::printf("\n");
+  }
   const TreeProgram &tp = s.tree;
   if (!tp.ok) { std::printf("tree program not built: %s\n", tp.why_not.c_str()); return 0; }
   std::printf("tree: C %d smem %zu chain_steps %d top cols %d xchg doubles %d words %zu\n", tp.C, tp.smem_bytes, tp.chain_steps, tp.n_top_cols, tp.xchg_doubles, tp.words.size());

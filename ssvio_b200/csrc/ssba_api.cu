@@ -277,7 +277,7 @@ ssba_status enqueue_slot(ssba_handle *h, bool first, bool linearize) {
   {
     PhaseTimer t(h, 1);
     launch_schur(P, first, st);
-    h->prof.kernel_launches += 1;
+    h->prof.kernel_launches += P.deterministic ? 2 : 1;
   }
   if (multi) {
     PhaseTimer t(h, 4);
@@ -706,6 +706,7 @@ ssba_status ssba_initialize(ssba_handle *h) {
   STAT(items_b, h->owner_mask, owner_mask);
   STAT(items_b, s.unit_slot, unit_slot); STAT(items_b, s.unit_n, unit_n); STAT(items_b, s.unit_k, unit_k); STAT(items_b, s.unit_c0, unit_c0);
   STAT(items_b, s.unit_combo_ptr, unit_combo_ptr); STAT(items_b, s.combo_blk, combo_blk);
+  STAT(items_b, s.blk_prod_ptr, blk_prod_ptr); STAT(items_b, s.combo_pos, combo_pos);
   STAT(items_b, s.blk_row, blk_row); STAT(items_b, s.blk_col, blk_col); STAT(items_b, s.col_ptr, col_diag);
   STAT(items_b, s.prog, prog); STAT(items_b, s.prog_ptr, prog_ptr);
   const int32_t *d_tree_prog = nullptr;
@@ -720,6 +721,7 @@ ssba_status ssba_initialize(ssba_handle *h) {
   DYN(sys, P.sys_doubles, double); DYN(xp, 6 * (size_t)s.n_fp, double); DYN(diag_buf, 6 * (size_t)s.n_fp, double);
   DYN(chi_cur_part, nblk, double); DYN(maxdiag_part, nblk, double); DYN(chi_new_part, nblk, double); DYN(scale_part, nblk, double);
   DYN(scal, 8, double); DYN(chi_out, 8, double);
+  DYN(stage, 36 * s.combo_blk.size(), double); DYN(stage_b, 6 * s.combo_blk.size(), double);
   DYN(ctl, 1, Control);
   double *d_tree_xchg = nullptr;
   dyn(sizeof(double) * (size_t)std::max(s.tree.xchg_doubles, 2), (void **)&d_tree_xchg);
@@ -773,6 +775,10 @@ ssba_status ssba_initialize(ssba_handle *h) {
   }
   P.n_units = s.n_units;
   P.pdl = pdl_enabled(h) ? 1 : 0;
+  {
+    static const bool det = [] { const char *e = std::getenv("SSBA_DETERMINISTIC"); return !(e && std::atoi(e) == 0); }();
+    P.deterministic = det ? 1 : 0;
+  }
   h->initialized = true;
   h->dirty = false;
   h->topo_dirty = false;

@@ -97,6 +97,10 @@ struct DeviceProblem {
   const int32_t *pose_of_q;
   const int32_t *unit_slot, *unit_n, *unit_k, *unit_c0;  // Schur work units
   const int32_t *unit_combo_ptr, *combo_blk;             // ... and the factor blocks they accumulate into
+  const int32_t *blk_prod_ptr, *combo_pos;               // per factor block its producers (combos, in unit order) are the
+                                                         // staging slots [blk_prod_ptr[b], blk_prod_ptr[b + 1]); combo -> slot
+  double *stage, *stage_b;  // deterministic accumulation: per combo its 6x6 total (and, diagonal combos, its 6-vector)
+  int deterministic;        // k_schur stores per-unit totals, k_schur_reduce adds them in a fixed order (no fp64 atomics)
   int n_units;
   // factor structure
   const int32_t *blk_row, *blk_col;
@@ -158,7 +162,7 @@ void launch_linearize(const DeviceProblem &P, cudaStream_t st);        // K_lin 
 void launch_maxdiag(const DeviceProblem &P, cudaStream_t st);          // -> scal[3]
 void launch_lambda_init(const DeviceProblem &P, cudaStream_t st);
 // sys += blockdiag(Hpp) + lambda I - W Hll^-1 W^T, bschur, b_p (sys zeroed by the previous k_update)
-void launch_schur(const DeviceProblem &P, bool prefolded, cudaStream_t st);
+void launch_schur(const DeviceProblem &P, bool prefolded, cudaStream_t st);  // + k_schur_reduce when P.deterministic
 void launch_reduced_solve(const DeviceProblem &P, cudaStream_t st);
 void launch_update(const DeviceProblem &P, bool fused_control, cudaStream_t st);  // + accept/reject when fused
 bool update_linearizes(const DeviceProblem &P);  // k_update also linearises the trial state (closed-form Jacobians)

@@ -519,6 +519,7 @@ __device__ __forceinline__ void schur_pose_warp(const DeviceProblem &P, const Co
   } else {
     s = lane < 27 ? P.hpp_fold[27 * q + lane] : 0.0;
   }
+  if (P.deterministic) return;  // k_schur_reduce puts Hpp + lambda I, bschur and b_p in place
   const double lambda = ctl->rank == 0 ? ctl->lambda : 0.0;
   double *sysacc = schur_target(P, ctl);
   double *D = sysacc + 36 * (size_t)P.col_diag[q];
@@ -554,7 +555,7 @@ __global__ void __launch_bounds__(32 * kSchurWarps, 3) k_schur(const DeviceProbl
   } else if (u < P.n_units) {
     s0 = P.unit_slot[u]; n = P.unit_n[u]; k = P.unit_k[u]; c0 = P.unit_c0[u];
     if (lane < n) s_pair0[warp][lane] = P.slot_pair_ptr[s0 + lane];
-    prefetch_l1(P.combo_blk + P.unit_combo_ptr[u] + lane);
+    prefetch_l1((P.deterministic ? P.combo_pos : P.combo_blk) + P.unit_combo_ptr[u] + lane);
   }
   griddep_wait();
   griddep_launch();
@@ -681,6 +682,19 @@ __global__ void __launch_bounds__(32 * kSchurWarps, 3) k_schur(const DeviceProbl
     }
   }
   if (sub != 0) return;
+  if (P.deterministic) {
+    // the unit's totals go to its own place; k_schur_reduce adds the producers of every block in a fixed order
+    const size_t cidx = (size_t)P.combo_pos[P.unit_combo_ptr[u] + ci];
+    double2 *dst2 = reinterpret_cast<double2 *>(P.stage + 36 * cidx);
+#pragma unroll
+    for (int i = 0; i < 18; ++i) dst2[i] = make_double2(-acc[2 * i], -acc[2 * i + 1]);
+    if (diag) {
+      double2 *db2 = reinterpret_cast<double2 *>(P.stage_b + 6 * cidx);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) db2[i] = make_double2(-accb[2 * i], -accb[2 * i + 1]);
+    }
+    return;
+  }
   double *sysacc = schur_target(P, ctl);
   double *dst = sysacc + 36 * (size_t)P.combo_blk[P.unit_combo_ptr[u] + ci];
 #pragma unroll
@@ -689,6 +703,63 @@ __global__ void __launch_bounds__(32 * kSchurWarps, 3) k_schur(const DeviceProbl
     double *bs = sysacc + 36 * (size_t)P.n_blocks + 6 * (size_t)P.pair_q[s_pair0[warp][0] + a];
 #pragma unroll
     for (int r = 0; r < 6; ++r) atomicAdd(bs + r, -accb[r]);
+  }
+}
+
+// k_schur_reduce - the deterministic accumulation of the reduced system: one CTA per factor block adds the totals
+// the units of k_schur stored for it (contiguous in the staging buffer, in unit order: a list the host made) on top
+// of Hpp + lambda I for a diagonal block (block_solver.hpp:334-335, 524-539); bschur = b_p - sum of the units'
+// vectors (:397); blocks of the fill-in that no landmark touches become zero.  The four warps take a quarter of
+// the producers each (a diagonal block of a window has a hundred of them: every run of landmarks the pose sees)
+// and the four partial sums are combined as (w0 + w1) + (w2 + w3): a fixed order, no fp64 atomics anywhere, so
+// two runs give the same bits.
+__global__ void __launch_bounds__(128) k_schur_reduce(const DeviceProblem P) {
+  const Control *ctl = P.ctl;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x;
+  __shared__ double2 s_part[4][24];  // per warp: 18 pieces of the block, 3 of the vector
+  const int row = P.blk_row[b], col = P.blk_col[b], p0 = P.blk_prod_ptr[b], p1 = P.blk_prod_ptr[b + 1];
+  griddep_wait();
+  griddep_launch();
+  if (ctl->done) return;
+  const bool diag = row == col;
+  // this warp's quarter of the producers; lanes 0..17 own one 16-byte piece of the block, lanes 24..26 of the vector
+  const int per = (p1 - p0 + 3) / 4;
+  const int q0 = min(p1, p0 + warp * per), q1 = min(p1, q0 + per);
+  double2 acc = make_double2(0.0, 0.0);
+  if (lane < 18) {
+    const double2 *src = reinterpret_cast<const double2 *>(P.stage) + 18 * (size_t)q0 + lane;
+    for (int p = q0; p < q1; ++p, src += 18) { const double2 v = __ldcg(src); acc.x += v.x; acc.y += v.y; }
+  } else if (diag && lane >= 24 && lane < 27) {
+    const double2 *src = reinterpret_cast<const double2 *>(P.stage_b) + 3 * (size_t)q0 + (lane - 24);
+    for (int p = q0; p < q1; ++p, src += 3) { const double2 v = __ldcg(src); acc.x += v.x; acc.y += v.y; }
+  }
+  if (lane < 18) s_part[warp][lane] = acc;
+  else if (lane >= 24 && lane < 27) s_part[warp][lane - 6] = acc;
+  __syncthreads();
+  if (warp != 0) return;
+  const double lambda = ctl->rank == 0 ? ctl->lambda : 0.0;
+  double *sysacc = schur_target(P, ctl);
+  if (lane < 18) {
+    double2 base = make_double2(0.0, 0.0);
+    if (diag) {
+      auto tri = [](int e) { const int r = e / 6, c = e - 6 * r; const int lo = r < c ? r : c, hi = r < c ? c : r; return 6 + lo * 6 - lo * (lo - 1) / 2 + (hi - lo); };
+      const int e0 = 2 * lane, e1 = 2 * lane + 1;
+      base.x = P.hpp_fold[27 * col + tri(e0)] + ((e0 / 6 == e0 % 6) ? lambda : 0.0);
+      base.y = P.hpp_fold[27 * col + tri(e1)] + ((e1 / 6 == e1 % 6) ? lambda : 0.0);
+    }
+    const double2 a0 = s_part[0][lane], a1 = s_part[1][lane], a2 = s_part[2][lane], a3 = s_part[3][lane];
+    double2 out;
+    out.x = base.x + ((a0.x + a1.x) + (a2.x + a3.x));
+    out.y = base.y + ((a0.y + a1.y) + (a2.y + a3.y));
+    reinterpret_cast<double2 *>(sysacc + 36 * (size_t)b)[lane] = out;
+  } else if (diag && lane >= 24 && lane < 27) {
+    const int k = lane - 24;
+    const double2 bp = make_double2(P.hpp_fold[27 * col + 2 * k], P.hpp_fold[27 * col + 2 * k + 1]);
+    const double2 a0 = s_part[0][18 + k], a1 = s_part[1][18 + k], a2 = s_part[2][18 + k], a3 = s_part[3][18 + k];
+    double2 *bsch = reinterpret_cast<double2 *>(sysacc + 36 * (size_t)P.n_blocks + 6 * (size_t)col);
+    bsch[k] = make_double2(bp.x + ((a0.x + a1.x) + (a2.x + a3.x)), bp.y + ((a0.y + a1.y) + (a2.y + a3.y)));  // bschur
+    bsch[3 * (size_t)P.n_fp + k] = bp;                                                                         // b_p (kept for computeScale)
   }
 }
 
@@ -1338,7 +1409,7 @@ __global__ void __launch_bounds__(kLinThreads, kFusedLin ? SSBA_LIN_MINB : 4) k_
   griddep_wait();
   griddep_launch();
   if (ctl->done) return;
-  {
+  if (!P.deterministic) {
     const size_t nz = 36 * (size_t)P.n_blocks + 6 * (size_t)P.n_fp;  // blocks and bschur; b_p is overwritten
     // peer-memory exchange: the partial the NEXT trial accumulates into is the one the peers read
     // one trial ago; their flag_scal of that trial (seen by the last k_control) says they are done
@@ -1804,6 +1875,7 @@ void launch_schur(const DeviceProblem &P, bool prefolded, cudaStream_t st) {
   once_per_device(seen, [] { cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDyn); });
   const int n_pose = div_up(P.n_fp, kSchurWarps), n_unit = div_up(P.n_units, kSchurWarps);
   if (n_pose + n_unit > 0) launch_maybe_pdl(k_schur, dim3(n_pose + n_unit), dim3(32 * kSchurWarps), kDyn, st, P.pdl != 0, P, n_pose, prefolded ? 1 : 0);
+  if (P.deterministic && P.n_blocks > 0) launch_maybe_pdl(k_schur_reduce, dim3(P.n_blocks), dim3(128), 0, st, P.pdl != 0, P);
 }
 
 // The largest cluster (8, 4, 2 or 1 CTAs of kSolveThreads threads with the full dynamic shared memory)

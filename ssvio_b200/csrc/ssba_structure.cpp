@@ -797,7 +797,7 @@ void reset_keep_capacity(Structure &s) {
   clr(s.slot_vertex); clr(s.slot_free); clr(s.slot_pair_ptr); clr(s.pair_vertex); clr(s.pair_q);
   clr(s.pair_edge_ptr); clr(s.pair_slot); clr(s.lchunk_slot); clr(s.lchunk_lp_ptr); clr(s.lp_pair_ptr);
   clr(s.lp_pair); clr(s.q_part_ptr); clr(s.q_part); clr(s.e_uv); clr(s.e_cam); clr(s.e_orig); clr(s.e_info);
-  clr(s.e_delta); clr(s.unit_combo_ptr); clr(s.combo_blk); clr(s.unit_slot); clr(s.unit_n); clr(s.unit_k);
+  clr(s.e_delta); clr(s.unit_combo_ptr); clr(s.combo_blk); clr(s.blk_prod_ptr); clr(s.blk_prod); clr(s.combo_pos); clr(s.unit_slot); clr(s.unit_n); clr(s.unit_k);
   clr(s.unit_c0); clr(s.col_ptr); clr(s.blk_row); clr(s.blk_col); clr(s.ltask_ptr); clr(s.task_dst);
   clr(s.task_pos); clr(s.task_pair_ptr); clr(s.pair_a); clr(s.pair_b); clr(s.prog); clr(s.prog_ptr);
   clr(s.row_ptr); clr(s.row_blk); clr(s.row_col); clr(s.level_ptr); clr(s.level_col);
@@ -1205,6 +1205,18 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
           s.combo_blk[o++] = blk;
         }
     }
+    // producers of every factor block: a stable counting sort of the combos by block
+    const int ncomb = (int)s.combo_blk.size();
+    s.blk_prod_ptr.assign(s.n_blocks + 1, 0);
+    for (int c = 0; c < ncomb; ++c) ++s.blk_prod_ptr[s.combo_blk[c] + 1];
+    for (int b = 0; b < s.n_blocks; ++b) s.blk_prod_ptr[b + 1] += s.blk_prod_ptr[b];
+    s.blk_prod.resize(ncomb);
+    {
+      std::vector<int32_t> fill(s.blk_prod_ptr.begin(), s.blk_prod_ptr.end() - 1);
+      for (int c = 0; c < ncomb; ++c) s.blk_prod[fill[s.combo_blk[c]]++] = c;
+    }
+    s.combo_pos.resize(ncomb);
+    for (int p = 0; p < ncomb; ++p) s.combo_pos[s.blk_prod[p]] = p;
   }
 
   tm.mark("chunks + schur units");

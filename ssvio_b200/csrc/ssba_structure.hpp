@@ -88,6 +88,12 @@ struct Structure {
   // Schur accumulation targets of every unit: for its W-pairs a <= b (sorted by q), block (q_b, q_a)
   std::vector<int32_t> unit_combo_ptr;  // n_units + 1
   uvec<int32_t> combo_blk;
+  // ... and per factor block the combos that produce it, in unit order: the fixed summation order of the
+  // deterministic accumulation (k_schur_reduce)
+  std::vector<int32_t> blk_prod_ptr;    // n_blocks + 1
+  std::vector<int32_t> blk_prod;        // combo indices
+  std::vector<int32_t> combo_pos;       // combo -> its position in blk_prod: where the unit stores its total, so that
+                                        // the producers of a block are contiguous in memory
   // ---- reduced system: lower block-CSC factor pattern (with fill) over q
   int n_blocks = 0, n_schur_blocks = 0;
   std::vector<int32_t> col_ptr;       // n_fp + 1, diagonal block first in every column

@@ -383,6 +383,19 @@ static void check_case(int nk, int np, int w, unsigned seed, bool fix0, int nfix
             CHECK(s.blk_col[b] == s.pair_q[s.slot_pair_ptr[s0] + a] && s.blk_row[b] == s.pair_q[s.slot_pair_ptr[s0] + b2], "combo block wrong");
           }
       }
+      // producer lists of the deterministic accumulation: every combo appears once, under its block, in unit order
+      CHECK((int)s.blk_prod_ptr.size() == s.n_blocks + 1 && s.blk_prod.size() == s.combo_blk.size(), "producer lists sized wrong");
+      if ((int)s.blk_prod_ptr.size() == s.n_blocks + 1) {
+        std::vector<int> seen_combo(s.combo_blk.size(), 0);
+        for (int b = 0; b < s.n_blocks; ++b)
+          for (int p = s.blk_prod_ptr[b]; p < s.blk_prod_ptr[b + 1]; ++p) {
+            const int c = s.blk_prod[p];
+            CHECK(s.combo_blk[c] == b, "producer %d listed under block %d but targets %d", c, b, s.combo_blk[c]);
+            CHECK(p == s.blk_prod_ptr[b] || s.blk_prod[p - 1] < c, "producers of block %d out of order", b);
+            ++seen_combo[c];
+          }
+        for (int v : seen_combo) CHECK(v == 1, "combo listed %d times", v);
+      }
       for (int sl = 0; sl < s.n_slots; ++sl) {
         int k = 0;
         for (int a = s.slot_pair_ptr[sl]; a < s.slot_pair_ptr[sl + 1]; ++a) if (s.pair_q[a] >= 0) ++k;
