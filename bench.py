@@ -229,7 +229,13 @@ def run_ssba(args):
         flush.add_(1)
 
     # ---------------- resident: graph uploaded once, timed = reset + optimize(10)
-    opt = ba.BundleAdjuster(device_id=local_rank, stream=stream, rank=rank, world_size=world, nccl_id=nccl_id)
+    # several GPUs: pre-sharded input - every rank is handed (and uploads, and builds the structure of) only the
+    # edges of the landmarks it owns; the partition itself (contiguous ranges of landmark rows with equal edge counts)
+    # is the caller's bookkeeping, made once here
+    opt = ba.BundleAdjuster(device_id=local_rank, stream=stream, rank=rank, world_size=world, nccl_id=nccl_id, presharded=multi)
+    g_full = g
+    if multi:
+        g = g.shard(rank, world)
     opt.set_graph(g)
     opt.initialize_optimization()
     info = opt.problem_info()
@@ -333,12 +339,17 @@ def run_ssba(args):
             ms = float(t.item())
         return ms
 
+    h2d_total = hg.input_bytes()
+    if multi:  # the ranks upload different amounts: the sum over the ranks
+        t = torch.tensor([float(h2d_total)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t)
+        h2d_total = int(t.item())
     e2e_ms = time_e2e(True)
     builds = eopt.problem_info().n_structure_builds
     same_ms = time_e2e(False)
     reuses = eopt.problem_info().n_structure_reuses
     e2e = {"value": iters * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
-           "h2d_bytes_per_step": hg.input_bytes() * world, "d2h_bytes_per_step": (hg.output_bytes() + 32) * world,
+           "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": (hg.output_bytes() + 32) * world,
            "ms_per_step": e2e_ms / args.steps, "chi2_robust": e2e_chi,
            "what": "new window every step: set_* + structure build + upload + optimize(%d) + read-back" % iters,
            "structure_builds_counted": int(builds),
@@ -410,14 +421,16 @@ def run_ssba(args):
     if rank == 0:
         peak, peak_src = measured_peaks()
         nnz_s = info.n_schur_blocks
+        gl = g          # this rank's shard (kernel-level algorithmic bytes: what THIS GPU's launches move)
+        g = g_full      # the workload (config, whole-iteration bytes)
         b_iter = iter_algorithmic_bytes(g.n_edges, g.n_points, g.n_poses, nnz_s)
         roofline, roofline_all = None, []
         if phases:
             alg_all = {  # algorithmic bytes per launch (DESIGN.md "Kernels"), whole graph
-                "linearize": 28 * g.n_edges + 24 * g.n_points + 56 * g.n_poses + 144 * info.n_pairs + 72 * g.n_points,
-                "schur": 144 * info.n_pairs + 72 * g.n_points + 288 * nnz_s + 48 * g.n_poses,
+                "linearize": 28 * gl.n_edges + 24 * g.n_points // world + 56 * g.n_poses + 144 * info.n_pairs + 72 * g.n_points // world,
+                "schur": 144 * info.n_pairs + 72 * g.n_points // world + 288 * nnz_s + 48 * g.n_poses,
                 "reduced_solve": 2 * 288 * nnz_s + 2 * 48 * g.n_poses,
-                "update_chi2": 28 * g.n_edges + 144 * info.n_pairs + 2 * 24 * g.n_points + 56 * g.n_poses,
+                "update_chi2": 28 * gl.n_edges + 144 * info.n_pairs + 2 * 24 * g.n_points // world + 56 * g.n_poses,
             }
             ncu = ncu_record() if args.workload == WORKLOAD and not multi else {}
             for k in alg_all:  # one entry per kernel of the LM trial; durations measured live (CUDA events of this run)
@@ -449,7 +462,7 @@ def run_ssba(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {**workload_config(args.workload, g, iters),
                        "l2": "flushed between timed steps (256 MiB write); working set %.1f MB < 126 MB L2" % (info.device_bytes / 1e6),
-                       "parallelism": ("landmark-sharded x%d, %s of the reduced pose system" % (world, "NVLink peer-memory exchange" if info.peer_exchange else "NCCL all-reduce")) if multi else "single GPU",
+                       "parallelism": ("landmark-sharded x%d (pre-sharded input: every rank is handed its own landmarks' edges), %s of the reduced pose system" % (world, "NVLink peer-memory exchange" if info.peer_exchange else "NCCL all-reduce")) if multi else "single GPU",
                        "iter_algorithmic_bytes": b_iter,
                        "step_hbm_frac": (b_iter * iters / (total_ms / args.steps * 1e-3)) / 1e9 / peak,
                        "chi2_robust_final": chi2_final, "lm_iterations_done": its_done,

@@ -89,7 +89,15 @@ typedef struct ssba_options {
   int32_t rank;                     /* 0..world_size-1                               */
   int32_t world_size;               /* 1 => single GPU                               */
   uint8_t nccl_id[SSBA_NCCL_ID_BYTES]; /* from ssba_nccl_unique_id() on rank 0       */
-  int32_t reserved[8];
+  int32_t presharded;               /* world_size > 1 only.  0: every rank is handed the WHOLE graph and keeps the
+                                     * landmarks ssba_plan_shards assigns to it.  1: every rank is handed only the
+                                     * edges of the landmarks it owns (any partition by landmark; all edges of a
+                                     * landmark on one rank), the same poses / fixed flags / n_points everywhere; point
+                                     * rows of other ranks' landmarks are not read.  The ranks agree on the active
+                                     * poses and on the co-visibility pattern through NCCL inside ssba_initialize
+                                     * (collective: all ranks must call it); per-edge read-outs
+                                     * (ssba_get_edge_errors, ssba_get_outlier_mask) then cover the rank's own edges */
+  int32_t reserved[7];
 } ssba_options;
 
 /* One outer LM iteration = one OptimizationAlgorithmLevenberg::solve() call

@@ -10,6 +10,7 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 rows = []
 with ba.BundleAdjuster() as opt:
     for rep in range(reps):
+        if os.environ.get('E2E_FRESH', '1') != '0': opt.drop_structure()
         t0 = time.perf_counter(); opt.set_graph(g)
         t1 = time.perf_counter(); opt.initialize_optimization()
         t2 = time.perf_counter(); r = opt.optimize(g.iters)

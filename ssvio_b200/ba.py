@@ -46,7 +46,7 @@ class Options(C.Structure):
                 ("max_trials_after_failure", C.c_int32), ("jacobian_mode", C.c_int32),
                 ("device_id", C.c_int32), ("profile", C.c_int32), ("stream", C.c_void_p),
                 ("rank", C.c_int32), ("world_size", C.c_int32),
-                ("nccl_id", C.c_uint8 * SSBA_NCCL_ID_BYTES), ("reserved", C.c_int32 * 8)]
+                ("nccl_id", C.c_uint8 * SSBA_NCCL_ID_BYTES), ("presharded", C.c_int32), ("reserved", C.c_int32 * 7)]
 
 
 class IterRecord(C.Structure):
@@ -189,7 +189,7 @@ class BundleAdjuster:
 
     def __init__(self, *, jacobian="analytic", device_id=-1, stream=None, profile=False,
                  rank=0, world_size=1, nccl_id: bytes | None = None, user_lambda_init=0.0,
-                 max_trials_after_failure=10, tau=None):
+                 max_trials_after_failure=10, tau=None, presharded=False):
         self.lib = load_library()
         opt = Options()
         self.lib.ssba_default_options(C.byref(opt))
@@ -198,6 +198,7 @@ class BundleAdjuster:
         opt.profile = 1 if profile else 0
         opt.stream = stream
         opt.rank, opt.world_size = rank, world_size
+        opt.presharded = 1 if presharded else 0
         opt.user_lambda_init = user_lambda_init
         opt.max_trials_after_failure = max_trials_after_failure
         if tau is not None:

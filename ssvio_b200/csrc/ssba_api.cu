@@ -119,6 +119,7 @@ struct ssba_handle {
   Structure pg_s;
   char *d_pg = nullptr; size_t d_pg_bytes = 0;
   // pose-only LM: its own grow-only device buffer and pinned staging
+  char *d_xr = nullptr; size_t d_xr_bytes = 0;  // device scratch of the pre-sharded structure build's exchanges
   char *d_po = nullptr; size_t d_po_bytes = 0;
   char *h_po = nullptr; size_t h_po_bytes = 0;
 };
@@ -485,6 +486,7 @@ void ssba_destroy(ssba_handle *h) {
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->h_stage_b) cudaFreeHost(h->h_stage_b);
   if (h->d_po) cudaFree(h->d_po);
+  if (h->d_xr) cudaFree(h->d_xr);
   if (h->d_pg) cudaFree(h->d_pg);
   if (h->h_po) cudaFreeHost(h->h_po);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -583,7 +585,19 @@ ssba_status ssba_initialize(ssba_handle *h) {
   const bool timing = std::getenv("SSBA_TIMING") != nullptr;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // nothing of a previous upload may still read the staging buffers
 
-  if (!h->topo_dirty && h->initialized) {
+  bool reuse = !h->topo_dirty && h->initialized;
+  if (h->opt.world_size > 1 && h->opt.presharded) {
+    // pre-sharded input: the structure build is collective, so either every rank keeps its structure or none does
+    if (!h->d_xr) { if (cudaMalloc((void **)&h->d_xr, 4096) != cudaSuccess) { cudaGetLastError(); return fail(h, SSBA_ERR_ALLOC, "cudaMalloc failed"); } h->d_xr_bytes = 4096; }
+    double flag = reuse ? 0.0 : 1.0;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_xr, &flag, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    ssba_status arc = nccl_allreduce(h, (double *)h->d_xr, 1, kNcclMax);
+    if (arc) return arc;
+    CUDA_TRY(h, cudaMemcpyAsync(&flag, h->d_xr, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    reuse = flag < 0.5;
+  }
+  if (reuse) {
     // ---- same topology as the resident structure: only the values go up (estimates, measurements in the
     // structure's edge order, information / Huber widths, cameras), then the state is reset.  This is what
     // rounds 2..5 of backend.cpp:175-203 and the g2o shim's repeated init() cost.
@@ -684,7 +698,32 @@ ssba_status ssba_initialize(ssba_handle *h) {
   auto t_a = Clock::now();
   h->initialized = false;  // the device problem is being rebuilt
   h->topo_dirty = true;
-  if (!build_structure(g, h->opt.rank, h->opt.world_size, s, err, &on_edges_ready)) return fail(h, SSBA_ERR_INVALID_ARG, err);
+  // pre-sharded input (options.presharded, several ranks): what all ranks must agree on travels through NCCL
+  // (element-wise maximum of a byte array, sum of a few counters), staged through the pinned / device scratch
+  const bool presharded = h->opt.world_size > 1 && h->opt.presharded != 0;
+  const AcrossRanks across_ranks = [&](uint8_t *bytes, size_t nb, long long *sums, int ns) -> bool {
+    const size_t need = nb + 64;
+    if (need > h->d_xr_bytes) {
+      if (h->d_xr) cudaFree(h->d_xr);
+      h->d_xr = nullptr; h->d_xr_bytes = 0;
+      if (cudaMalloc((void **)&h->d_xr, need + need / 2) != cudaSuccess) { cudaGetLastError(); return false; }
+      h->d_xr_bytes = need + need / 2;
+    }
+    double *d_s = (double *)h->d_xr;          // up to 8 counters first (8-byte aligned), then the bytes
+    uint8_t *d_b = (uint8_t *)h->d_xr + 64;
+    double hs[8] = {0};
+    for (int i = 0; i < ns && i < 8; ++i) hs[i] = (double)sums[i];
+    if (nb && cudaMemcpyAsync(d_b, bytes, nb, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return false;
+    if (ns && cudaMemcpyAsync(d_s, hs, sizeof(double) * ns, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return false;
+    if (nb && g_nccl.AllReduce(d_b, d_b, nb, /*ncclUint8*/ 1, kNcclMax, h->comm, h->stream) != 0) return false;
+    if (ns && g_nccl.AllReduce(d_s, d_s, (size_t)ns, kNcclDouble, kNcclSum, h->comm, h->stream) != 0) return false;
+    if (nb && cudaMemcpyAsync(bytes, d_b, nb, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return false;
+    if (ns && cudaMemcpyAsync(hs, d_s, sizeof(double) * ns, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return false;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return false;
+    for (int i = 0; i < ns && i < 8; ++i) sums[i] = (long long)(hs[i] + 0.5);
+    return true;
+  };
+  if (!build_structure(g, h->opt.rank, h->opt.world_size, s, err, &on_edges_ready, presharded ? &across_ranks : nullptr)) return fail(h, SSBA_ERR_INVALID_ARG, err);
   auto t_b = Clock::now();
   h->ms_structure_build = 1e3 * secs(t_a, t_b);
   h->ms_symbolic = 1e3 * s.seconds_symbolic;
@@ -924,7 +963,8 @@ ssba_status ssba_get_edge_errors(ssba_handle *h, double *out) {
   CUDA_TRY(h, cudaMemsetAsync(h->P.err_out, 0, bytes, h->stream));
   launch_edge_errors(h->P, h->stream);
   h->prof.kernel_launches += 1;
-  if (h->opt.world_size > 1) { rc = nccl_allreduce(h, h->P.err_out, 2 * (size_t)h->P.n_edges_total, kNcclSum); if (rc) return rc; }
+  // replicated input: every edge lives on exactly one rank, the sum is the union; pre-sharded input: the edges are this rank's own
+  if (h->opt.world_size > 1 && !h->opt.presharded) { rc = nccl_allreduce(h, h->P.err_out, 2 * (size_t)h->P.n_edges_total, kNcclSum); if (rc) return rc; }
   CUDA_TRY(h, cudaMemcpyAsync(out, h->P.err_out, bytes, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   return SSBA_OK;
@@ -952,7 +992,7 @@ ssba_status ssba_count_outliers(ssba_handle *h, double thr, int64_t *n_out, int6
   if (n_out) *n_out = (int64_t)(f[2] + 0.5);
   // edges whose two vertices are fixed are never active (sparse_optimizer.cpp:237): their
   // _error stays zero in the reference, so backend.cpp:184 counts them as inliers
-  if (n_in) *n_in = (int64_t)(f[3] + 0.5) + (h->g.n_edges - h->s.n_active_edges_global);
+  if (n_in) *n_in = (int64_t)(f[3] + 0.5) + h->s.n_inactive_edges_global;
   return SSBA_OK;
 }
 
@@ -965,7 +1005,7 @@ ssba_status ssba_get_outlier_mask(ssba_handle *h, double thr, uint8_t *mask_out,
   launch_outlier_mask(h->P, thr, h->stream);
   h->prof.kernel_launches += 2;
   if (h->opt.world_size > 1) {  // every edge lives on exactly one rank: the sum is the union
-    if (g_nccl.AllReduce(h->P.mask_out, h->P.mask_out, n, /*ncclUint8*/ 1, kNcclSum, h->comm, h->stream) != 0) return fail(h, SSBA_ERR_NCCL, "ncclAllReduce failed");
+    if (!h->opt.presharded && g_nccl.AllReduce(h->P.mask_out, h->P.mask_out, n, /*ncclUint8*/ 1, kNcclSum, h->comm, h->stream) != 0) return fail(h, SSBA_ERR_NCCL, "ncclAllReduce failed");
     if ((rc = nccl_allreduce(h, h->P.chi_out, 4, kNcclSum))) return rc;
   }
   CUDA_TRY(h, cudaMemcpyAsync(mask_out, h->P.mask_out, n, cudaMemcpyDeviceToHost, h->stream));

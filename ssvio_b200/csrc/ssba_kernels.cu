@@ -65,6 +65,33 @@ __device__ __forceinline__ double block_max(double v, double *sm) {
   return r;
 }
 
+// ---- TMA staging of the pose array (cp.async.bulk + mbarrier): the poses of a window are a few KB that every
+// pair of a CTA gathers from; one bulk copy per CTA puts them into shared memory while the CTA does other work.
+__device__ __forceinline__ unsigned ek_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ek_stage_begin(unsigned long long *bar, double *dst, const double *src, unsigned bytes) {
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ek_smem_u32(bar)), "r"(1u) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ek_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ek_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(ek_smem_u32(bar)) : "memory");
+  }
+}
+// every thread that is going to read the staged data waits (after a __syncthreads that follows ek_stage_begin)
+__device__ __forceinline__ void ek_stage_wait(unsigned long long *bar) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(ek_smem_u32(bar)), "r"(0u) : "memory");
+}
+// bytes of the staged pose array, 0 = too large for shared memory beside the linearisation scratch (then the pairs
+// gather from global memory as before)
+constexpr unsigned kPoseStageMaxBytes = 32 * 1024;
+__host__ __device__ inline unsigned pose_stage_bytes(int n_poses) {
+  const unsigned b = (56u * (unsigned)n_poses + 15u) & ~15u;  // the arena pads every array: reading up to 8 bytes on is safe
+  return b <= kPoseStageMaxBytes ? b : 0u;
+}
+
 struct EdgeTerms {
   double e0, e1;      // error
   double we0, we1;    // Omega e
@@ -415,9 +442,19 @@ __global__ void __launch_bounds__(kLinThreads, SSBA_LIN_MINB) k_linearize(const 
   const Control *ctl = P.ctl;
   if (ctl->done || !ctl->need_linearize) return;
   __shared__ LinSmem sm;
+  __shared__ __align__(8) unsigned long long s_bar;
+  extern __shared__ __align__(16) double s_pose[];
   const int cur = ctl->cur;
+  const unsigned pb = pose_stage_bytes(P.n_poses);
+  const double *pose = P.pose[cur];
+  if (pb) {
+    ek_stage_begin(&s_bar, s_pose, pose, pb);
+    __syncthreads();
+    ek_stage_wait(&s_bar);
+    pose = s_pose;
+  }
   double chi, mx;
-  linearize_chunk<kMode>(P, ctl->lin, P.pose[cur], P.point[cur], sm, chi, mx);
+  linearize_chunk<kMode>(P, ctl->lin, pose, P.point[cur], sm, chi, mx);
   const double s_ = block_sum<kLinThreads>(chi, sm.red);
   const double m = block_max<kLinThreads>(mx, sm.red);
   if (threadIdx.x == 0) { P.chi_cur_part[blockIdx.x] = s_; P.maxdiag_part[blockIdx.x] = m; }
@@ -1409,6 +1446,10 @@ __global__ void __launch_bounds__(kLinThreads, kFusedLin ? SSBA_LIN_MINB : 4) k_
   griddep_wait();
   griddep_launch();
   if (ctl->done) return;
+  __shared__ __align__(8) unsigned long long s_bar;
+  extern __shared__ __align__(16) double s_pose[];
+  const unsigned pb = kFusedLin ? pose_stage_bytes(P.n_poses) : 0u;
+  if (pb) ek_stage_begin(&s_bar, s_pose, P.pose[ctl->cur ^ 1], pb);  // the trial poses: needed by the third phase only
   if (!P.deterministic) {
     const size_t nz = 36 * (size_t)P.n_blocks + 6 * (size_t)P.n_fp;  // blocks and bschur; b_p is overwritten
     // peer-memory exchange: the partial the NEXT trial accumulates into is the one the peers read
@@ -1473,7 +1514,8 @@ __global__ void __launch_bounds__(kLinThreads, kFusedLin ? SSBA_LIN_MINB : 4) k_
   // ---- trial residuals per pair (and, fused, the whole linearisation of the trial state)
   if (kFusedLin) {
     double mx;
-    linearize_chunk<SSBA_JACOBIAN_ANALYTIC>(P, lin ^ 1, pose_new, P.point[cur ^ 1], sm, chi, mx);
+    if (pb) ek_stage_wait(&s_bar);  // (two __syncthreads since ek_stage_begin)
+    linearize_chunk<SSBA_JACOBIAN_ANALYTIC>(P, lin ^ 1, pb ? s_pose : pose_new, P.point[cur ^ 1], sm, chi, mx);
     (void)mx;  // lambda_0 uses the first linearisation only (k_linearize)
   } else if (small) {
     if (tid < a1 - a0) {
@@ -1840,20 +1882,6 @@ extern "C" int ssba_debug_solver_trace(long long *out, int n) {
 }
 #endif
 
-void launch_linearize(const DeviceProblem &P, cudaStream_t st) {
-  if (P.n_lin_blocks <= 0) return;
-  if (P.jacobian_mode == SSBA_JACOBIAN_NUMERIC) k_linearize<SSBA_JACOBIAN_NUMERIC><<<P.n_lin_blocks, kLinThreads, 0, st>>>(P);
-  else k_linearize<SSBA_JACOBIAN_ANALYTIC><<<P.n_lin_blocks, kLinThreads, 0, st>>>(P);
-}
-
-void launch_fold(const DeviceProblem &P, cudaStream_t st) {
-  if (P.n_fp > 0) k_fold<<<div_up(P.n_fp, 4), 128, 0, st>>>(P);
-}
-
-void launch_maxdiag(const DeviceProblem &P, cudaStream_t st) { k_maxdiag<<<1, 1024, 0, st>>>(P); }
-
-void launch_lambda_init(const DeviceProblem &P, cudaStream_t st) { k_lambda_init<<<1, 1, 0, st>>>(P); }
-
 // function attributes are per device: `setup` runs once per device of this process, and a second thread
 // cannot launch before the first one has finished setting them (handles are used from several threads)
 template <class F>
@@ -1868,6 +1896,26 @@ void once_per_device(std::atomic<unsigned long long> &done, F &&setup) {
   setup();
   done.fetch_or(bit, std::memory_order_release);
 }
+
+void launch_linearize(const DeviceProblem &P, cudaStream_t st) {
+  if (P.n_lin_blocks <= 0) return;
+  static std::atomic<unsigned long long> seen{0};
+  once_per_device(seen, [] {
+    cudaFuncSetAttribute(k_linearize<SSBA_JACOBIAN_NUMERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoseStageMaxBytes);
+    cudaFuncSetAttribute(k_linearize<SSBA_JACOBIAN_ANALYTIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoseStageMaxBytes);
+  });
+  const size_t dyn = pose_stage_bytes(P.n_poses);
+  if (P.jacobian_mode == SSBA_JACOBIAN_NUMERIC) k_linearize<SSBA_JACOBIAN_NUMERIC><<<P.n_lin_blocks, kLinThreads, dyn, st>>>(P);
+  else k_linearize<SSBA_JACOBIAN_ANALYTIC><<<P.n_lin_blocks, kLinThreads, dyn, st>>>(P);
+}
+
+void launch_fold(const DeviceProblem &P, cudaStream_t st) {
+  if (P.n_fp > 0) k_fold<<<div_up(P.n_fp, 4), 128, 0, st>>>(P);
+}
+
+void launch_maxdiag(const DeviceProblem &P, cudaStream_t st) { k_maxdiag<<<1, 1024, 0, st>>>(P); }
+
+void launch_lambda_init(const DeviceProblem &P, cudaStream_t st) { k_lambda_init<<<1, 1, 0, st>>>(P); }
 
 void launch_schur(const DeviceProblem &P, bool prefolded, cudaStream_t st) {
   static std::atomic<unsigned long long> seen{0};
@@ -1933,11 +1981,17 @@ bool update_linearizes(const DeviceProblem &P) {
 void launch_update(const DeviceProblem &P, bool fused_control, cudaStream_t st) {
   if (P.n_upd_blocks <= 0) return;
   const bool lin = update_linearizes(P);
+  static std::atomic<unsigned long long> seen{0};
+  once_per_device(seen, [] {
+    cudaFuncSetAttribute(k_update<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoseStageMaxBytes);
+    cudaFuncSetAttribute(k_update<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoseStageMaxBytes);
+  });
+  const size_t dyn = lin ? pose_stage_bytes(P.n_poses) : 0;
   if (fused_control) {
-    if (lin) launch_maybe_pdl(k_update<true, true>, dim3(P.n_upd_blocks), dim3(kLinThreads), 0, st, P.pdl != 0, P);
+    if (lin) launch_maybe_pdl(k_update<true, true>, dim3(P.n_upd_blocks), dim3(kLinThreads), dyn, st, P.pdl != 0, P);
     else launch_maybe_pdl(k_update<true, false>, dim3(P.n_upd_blocks), dim3(kLinThreads), 0, st, P.pdl != 0, P);
   } else {
-    if (lin) launch_maybe_pdl(k_update<false, true>, dim3(P.n_upd_blocks), dim3(kLinThreads), 0, st, P.pdl != 0, P);
+    if (lin) launch_maybe_pdl(k_update<false, true>, dim3(P.n_upd_blocks), dim3(kLinThreads), dyn, st, P.pdl != 0, P);
     else launch_maybe_pdl(k_update<false, false>, dim3(P.n_upd_blocks), dim3(kLinThreads), 0, st, P.pdl != 0, P);
   }
 }
@@ -1949,7 +2003,10 @@ void launch_reduce_partials(const DeviceProblem &P, cudaStream_t st) {
 void launch_control(const DeviceProblem &P, cudaStream_t st) { k_control<<<1, 1, 0, st>>>(P, update_linearizes(P) ? 1 : 0); }
 
 void launch_exchange_sys(const DeviceProblem &P, cudaStream_t st) {
-  const int n = (int)std::min<size_t>(64, (P.sys_doubles / 2 + kXchgThreads - 1) / kXchgThreads);
+  // remote loads over NVLink take microseconds: enough CTAs that every thread has one or two 16-byte pieces and the
+  // whole pull is one round of loads in flight (cfg5 on 8 GPUs: 64 CTAs took 5 rounds, 119 us per trial with the
+  // control exchange; two CTAs per SM bring it to a single round)
+  const int n = (int)std::min<size_t>(2 * 148, (P.sys_doubles / 2 + kXchgThreads - 1) / kXchgThreads);
   k_exchange_sys<<<n > 0 ? n : 1, kXchgThreads, 0, st>>>(P);
 }
 

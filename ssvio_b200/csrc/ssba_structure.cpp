@@ -812,7 +812,8 @@ void reset_keep_capacity(Structure &s) {
 }  // namespace
 
 bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std::string &err,
-                     const std::function<void()> *on_edges_ready) {
+                     const std::function<void()> *on_edges_ready, const AcrossRanks *across_ranks) {
+  if (across_ranks) { rank = 0; world = 1; }  // pre-sharded input: every local landmark is a slot of this rank
   SectionTimer tm;
   reset_keep_capacity(s);
   const int NK = g.n_poses, NP = g.n_points, NE = g.n_edges;
@@ -870,7 +871,21 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     for (int t = 0; t < T; ++t) { n_active += t_active[t]; edges_by_landmark = edges_by_landmark && t_sorted[t]; }
   }
   s.n_active_edges_global = n_active;
-  s.point_active = point_active;
+  s.n_inactive_edges_global = NE - n_active;
+  if (across_ranks) {
+    // which poses / landmarks are active anywhere, and the global counts
+    std::vector<uint8_t> flags((size_t)NK + NP);
+    std::copy(pose_active.begin(), pose_active.end(), flags.begin());
+    std::copy(point_active.begin(), point_active.end(), flags.begin() + NK);
+    long long sums[2] = {n_active, NE - n_active};
+    if (!(*across_ranks)(flags.data(), flags.size(), sums, 2)) { err = "pre-sharded input: exchange of the active sets failed"; return false; }
+    std::copy(flags.begin(), flags.begin() + NK, pose_active.begin());
+    s.n_active_edges_global = (int)sums[0];
+    s.n_inactive_edges_global = sums[1];
+    s.point_active.assign(flags.begin() + NK, flags.end());  // global: who reports which landmark (ssba_get_points)
+  } else {
+    s.point_active = point_active;
+  }
 
   tm.mark("validate + active sets");
   // ---- index mapping (sparse_optimizer.cpp:168-192): free poses in id order, then landmarks
@@ -880,7 +895,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   s.n_fp = (int)free_pose_rows.size();
   s.n_fl_global = 0;
   for (int j = 0; j < NP; ++j)
-    if (point_active[j] && !lfix[j]) ++s.n_fl_global;
+    if ((across_ranks ? s.point_active[j] : point_active[j]) && !lfix[j]) ++s.n_fl_global;
   const int n = s.n_fp;
 
   // ---- edges by landmark (CSR over point rows, stable = addEdge order inside a landmark)
@@ -932,10 +947,21 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     }
   });
   std::vector<std::vector<int>> adj(n);  // strictly-lower rows per column, unpermuted
+  if (across_ranks && !use_bitmap) { err = "pre-sharded input: more than 4096 free poses"; return false; }
   if (use_bitmap) {
     std::vector<uint64_t> &bm = t_bitmap[0];
+    if (bm.empty()) bm.assign(bm_words, 0);
     for (int t = 1; t < (int)t_bitmap.size(); ++t)
       if (!t_bitmap[t].empty()) for (size_t w = 0; w < bm_words; ++w) bm[w] |= t_bitmap[t][w];
+    if (across_ranks && bm_words) {
+      // the pattern of the reduced system is the union over the ranks: one byte per possible block (the callback
+      // takes element-wise maxima, which is OR for 0 / 1 bytes but not for packed bits)
+      std::vector<uint8_t> bytes((size_t)n * n);
+      for (size_t bit = 0; bit < bytes.size(); ++bit) bytes[bit] = (uint8_t)(bm[bit >> 6] >> (bit & 63) & 1);
+      if (!(*across_ranks)(bytes.data(), bytes.size(), nullptr, 0)) { err = "pre-sharded input: exchange of the co-visibility pattern failed"; return false; }
+      std::fill(bm.begin(), bm.end(), 0);
+      for (size_t bit = 0; bit < bytes.size(); ++bit) if (bytes[bit]) bm[bit >> 6] |= 1ull << (bit & 63);
+    }
     for (int c = 0; c < n; ++c)
       for (int r = c + 1; r < n; ++r) {
         const size_t bit = (size_t)c * n + r;
@@ -1193,18 +1219,23 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
       s.unit_combo_ptr[u + 1] = s.unit_combo_ptr[u] + std::min(32, k * (k + 1) / 2 - s.unit_c0[u]);
     }
     s.combo_blk.resize((size_t)s.unit_combo_ptr[s.n_units]);
-    for (int u = 0; u < s.n_units; ++u) {
-      const int k = s.unit_k[u], c0 = s.unit_c0[u], c1 = c0 + (s.unit_combo_ptr[u + 1] - s.unit_combo_ptr[u]);
-      const int32_t *qs = s.pair_q.data() + s.slot_pair_ptr[s.unit_slot[u]];
-      int idx = 0, o = s.unit_combo_ptr[u];
-      for (int a2 = 0; a2 < k && idx < c1; ++a2)
-        for (int b2 = a2; b2 < k && idx < c1; ++b2, ++idx) {
-          if (idx < c0) continue;
-          const int blk = find_block(qs[b2], qs[a2]);
-          if (blk < 0) { err = "internal: Schur block missing from the factor pattern"; return false; }
-          s.combo_blk[o++] = blk;
-        }
-    }
+    std::vector<int> t_bad(T, 0);
+    pool.run(T, [&](int t, int TT) {
+      int u0, u1; split_range(t, TT, s.n_units, u0, u1);
+      for (int u = u0; u < u1; ++u) {
+        const int k = s.unit_k[u], c0 = s.unit_c0[u], c1 = c0 + (s.unit_combo_ptr[u + 1] - s.unit_combo_ptr[u]);
+        const int32_t *qs = s.pair_q.data() + s.slot_pair_ptr[s.unit_slot[u]];
+        int idx = 0, o = s.unit_combo_ptr[u];
+        for (int a2 = 0; a2 < k && idx < c1; ++a2)
+          for (int b2 = a2; b2 < k && idx < c1; ++b2, ++idx) {
+            if (idx < c0) continue;
+            const int blk = find_block(qs[b2], qs[a2]);
+            if (blk < 0) { t_bad[t] = 1; return; }
+            s.combo_blk[o++] = blk;
+          }
+      }
+    });
+    for (int t = 0; t < T; ++t) if (t_bad[t]) { err = "internal: Schur block missing from the factor pattern"; return false; }
     // producers of every factor block: a stable counting sort of the combos by block
     const int ncomb = (int)s.combo_blk.size();
     s.blk_prod_ptr.assign(s.n_blocks + 1, 0);

@@ -54,6 +54,7 @@ struct Structure {
   int n_fp = 0;                       // free active poses
   int n_fl_global = 0;                // free active landmarks, all ranks
   int n_active_edges_global = 0;
+  long long n_inactive_edges_global = 0;  // edges whose two ends are fixed (never active), all ranks
   std::vector<int32_t> q_of_pose;     // pose row -> q, -1 fixed / inactive
   std::vector<int32_t> pose_of_q;     // q -> pose row
   std::vector<uint8_t> point_active;  // point row has an active edge (on any rank)
@@ -131,8 +132,17 @@ struct Structure {
 // n_fp + n_fl_global == 0 is not an error here (caller maps it to SSBA_ERR_EMPTY).
 // `on_edges_ready` (optional) is called once the per-edge / per-pair arrays (slot_*, pair_*, e_*)
 // are final, before the solver program and the small index lists are built.
+//
+// `across_ranks` (optional) switches to PRE-SHARDED input: `g` holds only the edges of the landmarks this rank owns
+// (all of them), poses and fixed flags are the same on every rank.  Every landmark with a local edge becomes a
+// slot (rank / world are not used to select), and what has to be the same on every rank - which poses are active,
+// the co-visibility pattern of the reduced system, the global counts - is agreed through the callback:
+// across_ranks(bytes, n_bytes, sums, n_sums) replaces `bytes` by the element-wise maximum and `sums` by the sum
+// over the ranks (returns false on a communication failure).  Ordering, symbolic factorisation and the solver
+// program then come out identical on every rank because they only depend on that pattern.
+using AcrossRanks = std::function<bool(uint8_t *bytes, size_t n_bytes, long long *sums, int n_sums)>;
 bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std::string &err,
-                     const std::function<void()> *on_edges_ready = nullptr);
+                     const std::function<void()> *on_edges_ready = nullptr, const AcrossRanks *across_ranks = nullptr);
 
 // Solver-only structure for a block-sparse SPD system over n 6x6 block columns (see ssba_structure.cpp).
 bool build_solver_structure(int n, const std::vector<std::vector<int>> &adj, Structure &s, std::vector<int> &perm_out,

@@ -60,6 +60,21 @@ class Graph:
     def output_bytes(self) -> int:
         return int(self.poses.nbytes + self.points.nbytes)
 
+    def shard(self, rank: int, world: int) -> "Graph":
+        """The part of the graph rank `rank` of `world` is handed with ssba_options.presharded: all edges of the
+        landmarks it owns (contiguous ranges of point rows holding about 1 / world of the edges each); poses, fixed
+        flags and the point array (indexed globally) are the same on every rank."""
+        deg = np.bincount(self.point_idx, minlength=self.n_points)
+        cum = np.cumsum(deg)
+        bounds = np.searchsorted(cum, [cum[-1] * r / world for r in range(1, world)], side="left") + 1
+        lo = 0 if rank == 0 else int(bounds[rank - 1])
+        hi = self.n_points if rank == world - 1 else int(bounds[rank])
+        sel = np.nonzero((self.point_idx >= lo) & (self.point_idx < hi))[0]
+        return Graph(K=self.K, ext=self.ext, poses=self.poses, pose_fixed=self.pose_fixed, points=self.points,
+                     point_fixed=self.point_fixed, pose_idx=np.ascontiguousarray(self.pose_idx[sel]),
+                     point_idx=np.ascontiguousarray(self.point_idx[sel]), cam_idx=np.ascontiguousarray(self.cam_idx[sel]),
+                     uv=np.ascontiguousarray(self.uv[sel]), huber_delta=self.huber_delta, iters=self.iters)
+
 
 # --------------------------------------------------------------------------- SE(3) helpers
 # Sophus conventions (thirdparty/sophus/sophus/so3.hpp:593-622, se3.hpp:763-784): tangent is

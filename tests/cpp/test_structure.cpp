@@ -561,6 +561,73 @@ static void check_case(int nk, int np, int w, unsigned seed, bool fix0, int nfix
               nk, np, w, (int)fix0, nfix, (int)loop, world, n, s.n_blocks, s.n_schur_blocks, s.n_levels, s.n_tasks, (int)s.pair_a.size(), s.est_solver_cycles, s.solver_slots, s.solver_cached_blocks, rmax);
 }
 
+// ---- pre-sharded input (ssba_options.presharded): every rank builds from the edges of its own landmarks; the ranks
+// agree on the active sets and the co-visibility pattern through the callback.  Emulated with one thread per rank
+// and a shared reducer; the result must give every rank the factor pattern of the single-rank build.
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+struct Reducer {
+  int world, arrived = 0, gen = 0;
+  std::mutex mu; std::condition_variable cv;
+  std::vector<uint8_t> bytes[2]; std::vector<long long> sums[2];  // by round parity: a round's result survives the next round's start
+  bool failed = false;
+  bool operator()(uint8_t *b, size_t nb, long long *s, int ns) {
+    std::unique_lock<std::mutex> lk(mu);
+    const int my = gen, k = my & 1;
+    if (arrived == 0) { bytes[k].assign(nb, 0); sums[k].assign(ns, 0); }
+    if (bytes[k].size() != nb || (int)sums[k].size() != ns) failed = true;  // (still take part: nobody may be left waiting)
+    else {
+      for (size_t i = 0; i < nb; ++i) bytes[k][i] = std::max(bytes[k][i], b[i]);
+      for (int i = 0; i < ns; ++i) sums[k][i] += s[i];
+    }
+    if (++arrived == world) { arrived = 0; ++gen; cv.notify_all(); }
+    else cv.wait(lk, [&] { return gen != my; });
+    if (failed) return false;
+    for (size_t i = 0; i < nb; ++i) b[i] = bytes[k][i];
+    for (int i = 0; i < ns; ++i) s[i] = sums[k][i];
+    return true;
+  }
+};
+static void check_presharded(int nk, int np, int w, unsigned seed, bool fix0, int nfix, bool loop, int world) {
+  HostGraph g = make_graph(nk, np, w, seed, fix0, nfix, loop);
+  Structure full;
+  std::string err;
+  CHECK(build_structure(g, 0, 1, full, err), "full build: %s", err.c_str());
+  std::vector<HostGraph> parts(world, g);
+  for (int r = 0; r < world; ++r) {
+    HostGraph &h = parts[r];
+    h.e_pose.clear(); h.e_point.clear(); h.e_cam.clear(); h.e_uv.clear();
+    for (int e = 0; e < g.n_edges; ++e)
+      if (g.e_point[e] % world == r) { h.e_pose.push_back(g.e_pose[e]); h.e_point.push_back(g.e_point[e]); h.e_cam.push_back(g.e_cam[e]); h.e_uv.push_back(0); h.e_uv.push_back(0); }
+    h.n_edges = (int)h.e_pose.size();
+  }
+  Reducer red; red.world = world;
+  const AcrossRanks ar = [&](uint8_t *b, size_t nb, long long *s, int ns) { return red(b, nb, s, ns); };
+  std::vector<Structure> S(world);
+  std::vector<std::string> errs(world);
+  std::vector<int> ok(world, 0);
+  std::vector<std::thread> th;
+  for (int r = 0; r < world; ++r) th.emplace_back([&, r] { ok[r] = build_structure(parts[r], r, world, S[r], errs[r], nullptr, &ar) ? 1 : 0; });
+  for (auto &t : th) t.join();
+  long long slots = 0, edges = 0;
+  std::vector<int> owner(np, -1);
+  for (int r = 0; r < world; ++r) {
+    CHECK(ok[r], "pre-sharded build of rank %d: %s", r, errs[r].c_str());
+    if (!ok[r]) return;
+    const Structure &s = S[r];
+    CHECK(s.n_fp == full.n_fp && s.n_blocks == full.n_blocks && s.col_ptr == full.col_ptr && s.blk_row == full.blk_row, "rank %d: factor pattern differs from the single-rank build", r);
+    CHECK(s.pose_of_q == full.pose_of_q, "rank %d: elimination order differs", r);
+    CHECK(s.n_active_edges_global == full.n_active_edges_global && s.n_fl_global == full.n_fl_global, "rank %d: global counts %d %d vs %d %d", r, s.n_active_edges_global, s.n_fl_global, full.n_active_edges_global, full.n_fl_global);
+    CHECK(s.point_active == full.point_active, "rank %d: active landmarks differ", r);
+    CHECK(s.tree.ok == full.tree.ok && s.tree.words == full.tree.words, "rank %d: solver program differs", r);
+    for (int v : s.slot_vertex) { CHECK(owner[v] < 0, "landmark %d on two ranks", v); owner[v] = r; CHECK(v % world == r, "landmark %d on the wrong rank", v); }
+    slots += s.n_slots; edges += s.n_edges;
+    for (int c : s.combo_blk) CHECK(c >= 0 && c < s.n_blocks, "combo block out of range");
+  }
+  CHECK(slots == full.n_slots && edges == full.n_edges, "shards hold %lld slots / %lld edges of %d / %d", slots, edges, full.n_slots, full.n_edges);
+}
+
 static void check_block_inverse() {
   std::mt19937 rng(7);
   std::uniform_real_distribution<double> U(-1, 1);
@@ -594,6 +661,9 @@ static void check_block_inverse() {
 
 int main() {
   check_block_inverse();
+  check_presharded(30, 800, 5, 3, true, 25, false, 2);
+  check_presharded(64, 3000, 5, 5, true, 0, true, 4);
+  check_presharded(100, 4000, 5, 6, false, 0, false, 8);
   check_case(4, 40, 3, 1, false, 0, false, 1);
   check_case(10, 500, 3, 2, false, 0, false, 1);
   check_case(30, 800, 5, 3, true, 25, false, 2);

@@ -67,6 +67,45 @@ def main():
                   flush=True)
         dist.barrier()
     opt.close()
+
+    # ---- pre-sharded input (ssba_options.presharded): every rank hands over only the edges of its own landmarks;
+    # the ranks agree on the active sets and the co-visibility pattern inside ssba_initialize
+    idt = torch.zeros(ba.SSBA_NCCL_ID_BYTES, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        idt = torch.tensor(list(ba.nccl_unique_id()), dtype=torch.uint8, device=dev)
+    dist.broadcast(idt, 0)
+    opt = ba.BundleAdjuster(device_id=local, rank=rank, world_size=world, nccl_id=bytes(idt.cpu().tolist()), presharded=True)
+    for name, g in cases:
+        mine = g.shard(rank, world)
+        for attempt in range(2):  # the second pass re-uses the resident structure (same indices): values only
+            opt.set_graph(mine)
+            rep = opt.optimize(g.iters)
+        poses, points, errs = opt.poses(), opt.points(), opt.edge_errors()
+        info = opt.problem_info()
+        assert info.n_structure_reuses >= 1, name
+        assert rep.iterations == gold[name]["numeric"]["iterations"], (name, rep.iterations)
+        assert rel(rep.chi2_robust, gold[name]["numeric"]["chi2_robust"]) < CHI2_RTOL, name
+        assert rel(rep.chi2_robust, gold[name]["analytic"]["chi2_robust"]) < 1e-9, name
+        nout, nin = opt.count_outliers(5.891)
+        assert nout + nin == g.n_edges, (name, nout, nin, g.n_edges)
+        assert errs.shape[0] == mine.n_edges
+        t = torch.from_numpy(np.concatenate([poses.ravel(), points.ravel()])).to(dev)
+        t0 = t.clone()
+        dist.broadcast(t0, 0)
+        assert torch.equal(t, t0), f"{name}: ranks disagree on the estimates (pre-sharded)"
+        with ba.BundleAdjuster(device_id=local) as single:
+            single.set_graph(g)
+            r1 = single.optimize(g.iters)
+            assert rel(rep.chi2_robust, r1.chi2_robust) < 1e-11
+            np.testing.assert_allclose(poses, single.poses(), atol=1e-9)
+            np.testing.assert_allclose(points, single.points(), atol=1e-8)
+            # this rank's edges, in its own order, against the same edges of the single-GPU run
+            sel = np.nonzero(np.isin(g.point_idx, np.unique(mine.point_idx)))[0]
+            np.testing.assert_allclose(errs, single.edge_errors()[sel], atol=1e-8)
+        if rank == 0:
+            print(f"[mgpu x{world}, pre-sharded] {name}: chi2={rep.chi2_robust:.8f} rel_vs_ref={rel(rep.chi2_robust, gold[name]['numeric']['chi2_robust']):.2e} OK", flush=True)
+        dist.barrier()
+    opt.close()
     dist.destroy_process_group()
     if rank == 0:
         print("MGPU_OK", flush=True)
