@@ -436,7 +436,9 @@ def run_ssba(args):
             for k in alg_all:  # one entry per kernel of the LM trial; durations measured live (CUDA events of this run)
                 ms_k, n_k = phases[k]
                 dur_k = ms_k / max(n_k, 1) * 1e-3
-                rec = ncu.get(k.replace("_chi2", ""), {})
+                rec = dict(ncu.get(k.replace("_chi2", ""), {}))
+                if k == "schur" and "schur_reduce" in ncu:  # the phase is two kernels: k_schur and k_schur_reduce
+                    rec["dram_bytes"] = rec.get("dram_bytes", 0) + ncu["schur_reduce"].get("dram_bytes", 0)
                 roofline_all.append({"kernel": k, "bound": "hbm", "achieved": alg_all[k] / dur_k / 1e9, "peak": peak, "unit": "GB/s",
                                      "frac": alg_all[k] / dur_k / 1e9 / peak, "algorithmic_bytes_per_launch": alg_all[k],
                                      "avg_launch_ms": ms_k / max(n_k, 1), "share_of_step": ms_k / max(1e-12, sum(v[0] for v in phases.values())),

@@ -59,7 +59,7 @@ def to_json(path):
     hdr, data = rows[0], rows[2:]
     ki = hdr.index("Kernel Name")
     col = {m: hdr.index(m) for m, _ in WANT if m in hdr}
-    names = {"k_linearize": "linearize", "k_schur": "schur", "k_tree_solve": "reduced_solve", "k_reduced_solve": "reduced_solve", "k_update": "update"}
+    names = {"k_linearize": "linearize", "k_schur": "schur", "k_schur_reduce": "schur_reduce", "k_tree_solve": "reduced_solve", "k_reduced_solve": "reduced_solve", "k_update": "update"}
     acc = {}
     for r in data:
         kn = r[ki].split("(")[0].split("::")[-1].split("<")[0]

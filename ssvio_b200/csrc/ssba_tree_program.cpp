@@ -341,8 +341,15 @@ bool build_tree_program(int n, const std::vector<int32_t> &col_ptr, const std::v
         }
         pi = pj;
       }
-      // look-ahead rounds: five items of similar length per warp round, longest first
-      std::stable_sort(look.begin(), look.end(), [](const Item &x, const Item &y) { return x.p1 - x.p0 > y.p1 - y.p0; });
+      // look-ahead rounds: five items of similar length per warp round, longest first; among items of one length the
+      // ones that multiply by the same unscaled block X_jk (same source column, same j) side by side, so that the five
+      // lane groups of a round load the same B operand (one shared-memory wavefront per load instead of two)
+      std::stable_sort(look.begin(), look.end(), [&](const Item &x, const Item &y) {
+        const int lx = x.p1 - x.p0, ly = y.p1 - y.p0;
+        if (lx != ly) return lx > ly;
+        if (lx == 0) return false;
+        return ((unsigned)pairs[x.p0] >> 16) < ((unsigned)pairs[y.p0] >> 16);
+      });
       int32_t *st = nullptr;
       auto step_entry = [&]() { return w.data() + kTH_Words + kTS_Words * (size_t)s; };
       const int off_pairs = (int)w.size();

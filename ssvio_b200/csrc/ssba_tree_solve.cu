@@ -401,8 +401,10 @@ __global__ void __launch_bounds__(kTreeThreads, 1) k_tree_solve(const DeviceProb
       }
       int4 nrec = make_int4(0, 0, 0, 0);
       if (warp < nnc) nrec = *reinterpret_cast<const int4 *>(prog + noff + 4 * warp);
+      // a chain of single-column steps runs on warp 0 alone: its own stores and loads only need the warp in step
+      const bool chain = nc == 1 && nnc == 1 && s != nsa;
       nc = nnc; off = noff; rec = nrec;
-      __syncthreads();
+      if (chain) __syncwarp(); else __syncthreads();
 #ifdef SSBA_SOLVER_TRACE
       TS_TRACE_C(trc); ++trc;
 #endif
