@@ -81,7 +81,7 @@ struct ssba_handle {
   bool initialized = false;
   // where the value arrays of the resident structure sit in region A (arena and pinned mirror alike): a graph
   // with the same topology is re-uploaded without a structure build (the <= 5 rounds of backend.cpp:175-203)
-  size_t off_pose0 = 0, off_point0 = 0, off_e_uv = 0, off_e_info = 0, off_e_delta = 0;
+  size_t off_pose0 = 0, off_point0 = 0;
   long long n_structure_builds = 0, n_structure_reuses = 0;
   double ms_structure_build = 0.0, ms_symbolic = 0.0;
   // SparseOptimizer::setForceStopFlag: raised from any thread, posted to the device on a stream of its own
@@ -119,6 +119,11 @@ struct ssba_handle {
   Structure pg_s;
   char *d_pg = nullptr; size_t d_pg_bytes = 0;
   // pose-only LM: its own grow-only device buffer and pinned staging
+  // the edges' values (uv | information | Huber widths) in the caller's order: pinned copy of the caller's arrays
+  // (set_edges) and its image on the device; k_gather_edge_values sorts them into the structure's order
+  char *h_raw = nullptr; size_t h_raw_bytes = 0;
+  char *d_raw = nullptr; size_t d_raw_bytes = 0;
+  size_t raw_off_info = 0, raw_off_delta = 0;
   char *d_xr = nullptr; size_t d_xr_bytes = 0;  // device scratch of the pre-sharded structure build's exchanges
   char *d_po = nullptr; size_t d_po_bytes = 0;
   char *h_po = nullptr; size_t h_po_bytes = 0;
@@ -487,6 +492,8 @@ void ssba_destroy(ssba_handle *h) {
   if (h->h_stage_b) cudaFreeHost(h->h_stage_b);
   if (h->d_po) cudaFree(h->d_po);
   if (h->d_xr) cudaFree(h->d_xr);
+  if (h->d_raw) cudaFree(h->d_raw);
+  if (h->h_raw) cudaFreeHost(h->h_raw);
   if (h->d_pg) cudaFree(h->d_pg);
   if (h->h_po) cudaFreeHost(h->h_po);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -539,8 +546,8 @@ ssba_status ssba_set_edges(ssba_handle *h, int32_t n, const int32_t *pose_idx, c
   HostGraph &g = h->g;
   // same topology as the resident graph (indices, cameras, which optional arrays exist)?  Then only the
   // values are taken and ssba_initialize keeps the structure.
-  bool same = !h->topo_dirty && g.n_edges == n && (int)g.e_pose.size() == n && (info != nullptr) == !g.e_info.empty() &&
-              (huber_delta != nullptr) == !g.e_delta.empty();
+  bool same = !h->topo_dirty && g.n_edges == n && (int)g.e_pose.size() == n && (info != nullptr) == g.has_info &&
+              (huber_delta != nullptr) == g.has_delta;
   if (same && n > 0) {
     std::vector<CopyJob> cmp = {{g.e_pose.data(), pose_idx, sizeof(int32_t) * (size_t)n}, {g.e_point.data(), point_idx, sizeof(int32_t) * (size_t)n}};
     if (cam_idx) cmp.push_back({g.e_cam.data(), cam_idx, (size_t)n});
@@ -550,18 +557,37 @@ ssba_status ssba_set_edges(ssba_handle *h, int32_t n, const int32_t *pose_idx, c
   if (!same) h->topo_dirty = true;
   g.n_edges = n;
   // the caller keeps its arrays: copy them (on the host thread pool, several megabytes per window)
-  g.e_pose.resize(n); g.e_point.resize(n); g.e_cam.resize(n); g.e_uv.resize(2 * (size_t)n);
-  if (info) g.e_info.resize(3 * (size_t)n); else g.e_info.clear();
-  if (huber_delta) g.e_delta.resize(n); else g.e_delta.clear();
-  std::vector<CopyJob> jobs = {{g.e_uv.data(), uv, 2 * sizeof(double) * (size_t)n}};
+  g.e_pose.resize(n); g.e_point.resize(n); g.e_cam.resize(n);
+  g.e_uv.clear(); g.e_info.clear(); g.e_delta.clear();
+  g.values_on_device = true; g.has_info = info != nullptr; g.has_delta = huber_delta != nullptr;
+  // the values go: caller -> pinned copy (the caller's arrays are free again when this returns) -> device, the
+  // copy over PCIe running while the host goes on to build the structure
+  const size_t b_uv = 16 * (size_t)n, b_info = info ? 24 * (size_t)n : 0, b_delta = huber_delta ? 8 * (size_t)n : 0;
+  const size_t raw_bytes = align_up(b_uv) + align_up(b_info) + align_up(b_delta) + 256;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  if (raw_bytes > h->h_raw_bytes) {
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->h_raw) cudaFreeHost(h->h_raw);
+    if (h->d_raw) cudaFree(h->d_raw);
+    h->h_raw = nullptr; h->d_raw = nullptr; h->h_raw_bytes = h->d_raw_bytes = 0;
+    const size_t cap = raw_bytes + raw_bytes / 4;
+    if (cudaHostAlloc((void **)&h->h_raw, cap, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return fail(h, SSBA_ERR_ALLOC, "cudaHostAlloc failed"); }
+    if (cudaMalloc((void **)&h->d_raw, cap) != cudaSuccess) { cudaGetLastError(); return fail(h, SSBA_ERR_ALLOC, "cudaMalloc failed"); }
+    h->h_raw_bytes = h->d_raw_bytes = cap;
+  } else {
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));  // an earlier upload may still be reading the pinned copy
+  }
+  h->raw_off_info = align_up(b_uv); h->raw_off_delta = h->raw_off_info + align_up(b_info);
+  std::vector<CopyJob> jobs = {{h->h_raw, uv, b_uv}};
   if (!same) {
     jobs.push_back({g.e_pose.data(), pose_idx, sizeof(int32_t) * (size_t)n});
     jobs.push_back({g.e_point.data(), point_idx, sizeof(int32_t) * (size_t)n});
     if (cam_idx) jobs.push_back({g.e_cam.data(), cam_idx, (size_t)n}); else std::fill(g.e_cam.begin(), g.e_cam.end(), (uint8_t)0);
   }
-  if (info) jobs.push_back({g.e_info.data(), info, 3 * sizeof(double) * (size_t)n});
-  if (huber_delta) jobs.push_back({g.e_delta.data(), huber_delta, sizeof(double) * (size_t)n});
+  if (info) jobs.push_back({h->h_raw + h->raw_off_info, info, b_info});
+  if (huber_delta) jobs.push_back({h->h_raw + h->raw_off_delta, huber_delta, b_delta});
   parallel_copy(jobs);
+  if (n > 0) CUDA_TRY(h, cudaMemcpyAsync(h->d_raw, h->h_raw, h->raw_off_delta + b_delta, cudaMemcpyHostToDevice, h->stream));
   g.delta_all = huber_delta_all;
   h->dirty = true;
   return SSBA_OK;
@@ -605,14 +631,11 @@ ssba_status ssba_initialize(ssba_handle *h) {
     const size_t pb = 56 * (size_t)g.n_poses, lb = 24 * (size_t)g.n_points, ne = (size_t)s.n_edges;
     if (pb) std::memcpy(h->h_stage + h->off_pose0, g.poses.data(), pb);
     if (lb) std::memcpy(h->h_stage + h->off_point0, g.points.data(), lb);
-    if (ne) parallel_gather_doubles((double *)(h->h_stage + h->off_e_uv), g.e_uv.data(), s.e_orig.data(), ne, 2);
-    if (ne && !g.e_info.empty()) parallel_gather_doubles((double *)(h->h_stage + h->off_e_info), g.e_info.data(), s.e_orig.data(), ne, 3);
-    if (ne && !g.e_delta.empty()) parallel_gather_doubles((double *)(h->h_stage + h->off_e_delta), g.e_delta.data(), s.e_orig.data(), ne, 1);
+    (void)ne;
     if (pb) CUDA_TRY(h, cudaMemcpyAsync(h->d_arena + h->off_pose0, h->h_stage + h->off_pose0, pb, cudaMemcpyHostToDevice, h->stream));
     if (lb) CUDA_TRY(h, cudaMemcpyAsync(h->d_arena + h->off_point0, h->h_stage + h->off_point0, lb, cudaMemcpyHostToDevice, h->stream));
-    if (ne) CUDA_TRY(h, cudaMemcpyAsync(h->d_arena + h->off_e_uv, h->h_stage + h->off_e_uv, 16 * ne, cudaMemcpyHostToDevice, h->stream));
-    if (ne && !g.e_info.empty()) CUDA_TRY(h, cudaMemcpyAsync(h->d_arena + h->off_e_info, h->h_stage + h->off_e_info, 24 * ne, cudaMemcpyHostToDevice, h->stream));
-    if (ne && !g.e_delta.empty()) CUDA_TRY(h, cudaMemcpyAsync(h->d_arena + h->off_e_delta, h->h_stage + h->off_e_delta, 8 * ne, cudaMemcpyHostToDevice, h->stream));
+    launch_gather_edge_values(P, (const double *)h->d_raw, g.has_info ? (const double *)(h->d_raw + h->raw_off_info) : nullptr,
+                              g.has_delta ? (const double *)(h->d_raw + h->raw_off_delta) : nullptr, h->stream);
     P.cams = g.cams;
     for (int c = 0; c < g.cams.n; ++c) quat_to_matrix(g.cams.ext[c], P.ext_R[c]);
     P.delta_all = g.delta_all;
@@ -672,13 +695,16 @@ ssba_status ssba_initialize(ssba_handle *h) {
     STAT(items_a, s.slot_vertex, slot_vertex); STAT(items_a, s.slot_free, slot_free); STAT(items_a, s.slot_pair_ptr, slot_pair_ptr);
     STAT(items_a, s.pair_vertex, pair_vertex); STAT(items_a, s.pair_q, pair_q); STAT(items_a, s.pair_edge_ptr, pair_edge_ptr);
     STAT(items_a, s.pair_slot, pair_slot);
-    STAT(items_a, s.e_uv, e_uv); STAT(items_a, s.e_info, e_info); STAT(items_a, s.e_delta, e_delta); STAT(items_a, s.e_cam, e_cam);
+    STAT(items_a, s.e_cam, e_cam);
     STAT(items_a, s.e_orig, e_orig);
     bytes_a = align_up(top);
     DYN(pose[0], 7 * g.n_poses, double); DYN(pose[1], 7 * g.n_poses, double);
     DYN(point[0], 3 * (size_t)g.n_points, double); DYN(point[1], 3 * (size_t)g.n_points, double);
     for (int k = 0; k < 2; ++k) { DYN(W[k], 18 * (size_t)s.n_pairs, double); DYN(Hll[k], 6 * (size_t)s.n_slots, double); DYN(bl[k], 3 * (size_t)s.n_slots, double); }
     DYN(Dinv, 6 * (size_t)s.n_slots, double);
+    DYN(e_uv, 2 * (size_t)s.n_edges, double);  // filled on the device (k_gather_edge_values)
+    if (g.has_info) DYN(e_info, 3 * (size_t)s.n_edges, double);
+    if (g.has_delta) DYN(e_delta, (size_t)s.n_edges, double);
     DYN(gather, h->opt.world_size > 1 ? 3 * (size_t)g.n_points : 0, double); DYN(err_out, 2 * (size_t)g.n_edges, double);
     DYN(mask_out, (size_t)g.n_edges, uint8_t);
     const size_t known = align_up(top);
@@ -785,9 +811,6 @@ ssba_status ssba_initialize(ssba_handle *h) {
   for (auto &it : items_a) {
     if (it.src == (const void *)g.poses.data()) h->off_pose0 = it.off;
     else if (it.src == (const void *)g.points.data()) h->off_point0 = it.off;
-    else if (it.src == (const void *)s.e_uv.data()) h->off_e_uv = it.off;
-    else if (it.src == (const void *)s.e_info.data()) h->off_e_info = it.off;
-    else if (it.src == (const void *)s.e_delta.data()) h->off_e_delta = it.off;
   }
   h->device_bytes = total;
   if (bytes_b) CUDA_TRY(h, cudaMemcpyAsync(h->d_arena + off_b, h->h_stage_b, bytes_b, cudaMemcpyHostToDevice, h->stream));
@@ -813,7 +836,13 @@ ssba_status ssba_initialize(ssba_handle *h) {
     if (h->use_p2p) CUDA_TRY(h, cudaMemsetAsync(h->xchg + sizeof(PeerHeader), 0, 2 * sizeof(double) * P.sys_doubles, h->stream));
   }
   P.n_units = s.n_units;
+  launch_gather_edge_values(P, (const double *)h->d_raw, g.has_info ? (const double *)(h->d_raw + h->raw_off_info) : nullptr,
+                            g.has_delta ? (const double *)(h->d_raw + h->raw_off_delta) : nullptr, h->stream);
   P.pdl = pdl_enabled(h) ? 1 : 0;
+  {
+    static const bool stage = [] { const char *e = std::getenv("SSBA_POSE_STAGE"); return !(e && std::atoi(e) == 0); }();
+    P.pose_stage = stage ? pose_stage_bytes(P.n_poses) : 0u;
+  }
   {
     static const bool det = [] { const char *e = std::getenv("SSBA_DETERMINISTIC"); return !(e && std::atoi(e) == 0); }();
     P.deterministic = det ? 1 : 0;

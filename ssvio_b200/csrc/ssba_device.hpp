@@ -134,6 +134,7 @@ struct DeviceProblem {
   // mapped into this process; layout per rank: PeerHeader, then 2 x sys_doubles partial reduced systems
   char *peer[SSBA_MAX_PEERS];
   int use_p2p;
+  unsigned pose_stage;  // bytes of the pose array the edge kernels stage into shared memory with one bulk copy (0: gather from L2)
   int pdl;  // launch k_schur / the reduced solve / k_update with programmatic dependent launch (off while profiling)
   size_t sys_doubles;
   int n_edges_total;
@@ -165,7 +166,8 @@ void launch_lambda_init(const DeviceProblem &P, cudaStream_t st);
 void launch_schur(const DeviceProblem &P, bool prefolded, cudaStream_t st);  // + k_schur_reduce when P.deterministic
 void launch_reduced_solve(const DeviceProblem &P, cudaStream_t st);
 void launch_update(const DeviceProblem &P, bool fused_control, cudaStream_t st);  // + accept/reject when fused
-bool update_linearizes(const DeviceProblem &P);  // k_update also linearises the trial state (closed-form Jacobians)
+bool update_linearizes(const DeviceProblem &P);
+unsigned pose_stage_bytes(int n_poses);  // what fits beside the linearisation scratch, else 0  // k_update also linearises the trial state (closed-form Jacobians)
 void launch_reduce_partials(const DeviceProblem &P, cudaStream_t st);  // -> scal[0..2]
 void launch_control(const DeviceProblem &P, cudaStream_t st);          // several GPUs only
 void launch_exchange_sys(const DeviceProblem &P, cudaStream_t st);     // peer-memory all-reduce of the reduced system
@@ -175,6 +177,8 @@ void launch_final_chi2(const DeviceProblem &P, double threshold, cudaStream_t st
 void launch_edge_errors(const DeviceProblem &P, cudaStream_t st);      // -> err_out
 void launch_outlier_mask(const DeviceProblem &P, double threshold, cudaStream_t st);  // -> mask_out, chi_out[2] = #outliers
 void launch_gather_points(const DeviceProblem &P, cudaStream_t st);    // -> gather
+// uv / information / Huber widths from the caller's edge order (raw_*) into the structure's order (P.e_*)
+void launch_gather_edge_values(const DeviceProblem &P, const double *raw_uv, const double *raw_info, const double *raw_delta, cudaStream_t st);
 int kernels_per_linearize();
 
 // pose-graph optimisation: one LM trial (zero / linearise when needed, lambda_0 in the first slot, H + lambda I,

@@ -87,10 +87,12 @@ __device__ __forceinline__ void ek_stage_wait(unsigned long long *bar) {
 // bytes of the staged pose array, 0 = too large for shared memory beside the linearisation scratch (then the pairs
 // gather from global memory as before)
 constexpr unsigned kPoseStageMaxBytes = 32 * 1024;
-__host__ __device__ inline unsigned pose_stage_bytes(int n_poses) {
+}  // namespace
+unsigned pose_stage_bytes(int n_poses) {
   const unsigned b = (56u * (unsigned)n_poses + 15u) & ~15u;  // the arena pads every array: reading up to 8 bytes on is safe
   return b <= kPoseStageMaxBytes ? b : 0u;
 }
+namespace {
 
 struct EdgeTerms {
   double e0, e1;      // error
@@ -445,7 +447,7 @@ __global__ void __launch_bounds__(kLinThreads, SSBA_LIN_MINB) k_linearize(const 
   __shared__ __align__(8) unsigned long long s_bar;
   extern __shared__ __align__(16) double s_pose[];
   const int cur = ctl->cur;
-  const unsigned pb = pose_stage_bytes(P.n_poses);
+  const unsigned pb = P.pose_stage;
   const double *pose = P.pose[cur];
   if (pb) {
     ek_stage_begin(&s_bar, s_pose, pose, pb);
@@ -1448,7 +1450,7 @@ __global__ void __launch_bounds__(kLinThreads, kFusedLin ? SSBA_LIN_MINB : 4) k_
   if (ctl->done) return;
   __shared__ __align__(8) unsigned long long s_bar;
   extern __shared__ __align__(16) double s_pose[];
-  const unsigned pb = kFusedLin ? pose_stage_bytes(P.n_poses) : 0u;
+  const unsigned pb = kFusedLin ? P.pose_stage : 0u;
   if (pb) ek_stage_begin(&s_bar, s_pose, P.pose[ctl->cur ^ 1], pb);  // the trial poses: needed by the third phase only
   if (!P.deterministic) {
     const size_t nz = 36 * (size_t)P.n_blocks + 6 * (size_t)P.n_fp;  // blocks and bschur; b_p is overwritten
@@ -1712,6 +1714,19 @@ __global__ void __launch_bounds__(256) k_final_reduce(const DeviceProblem P) {
   if (threadIdx.x == 0) { P.chi_out[0] = a; P.chi_out[1] = b; P.chi_out[2] = c; P.chi_out[3] = d; }
 }
 
+// The measurement values arrive in the caller's edge order (one plain copy of the caller's arrays); this puts them
+// into the structure's landmark-major order - the host structure build never touches them.
+__global__ void __launch_bounds__(256) k_gather_edge_values(const DeviceProblem P, const double *__restrict__ raw_uv,
+                                                            const double *__restrict__ raw_info, const double *__restrict__ raw_delta,
+                                                            double *e_uv, double *e_info, double *e_delta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n_edges) return;
+  const size_t o = (size_t)P.e_orig[i];
+  reinterpret_cast<double2 *>(e_uv)[i] = reinterpret_cast<const double2 *>(raw_uv)[o];
+  if (e_info) { e_info[3 * (size_t)i] = raw_info[3 * o]; e_info[3 * (size_t)i + 1] = raw_info[3 * o + 1]; e_info[3 * (size_t)i + 2] = raw_info[3 * o + 2]; }
+  if (e_delta) e_delta[i] = raw_delta[o];
+}
+
 __global__ void k_gather_points(const DeviceProblem P) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 3 * P.n_points) return;
@@ -1904,7 +1919,7 @@ void launch_linearize(const DeviceProblem &P, cudaStream_t st) {
     cudaFuncSetAttribute(k_linearize<SSBA_JACOBIAN_NUMERIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoseStageMaxBytes);
     cudaFuncSetAttribute(k_linearize<SSBA_JACOBIAN_ANALYTIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoseStageMaxBytes);
   });
-  const size_t dyn = pose_stage_bytes(P.n_poses);
+  const size_t dyn = P.pose_stage;
   if (P.jacobian_mode == SSBA_JACOBIAN_NUMERIC) k_linearize<SSBA_JACOBIAN_NUMERIC><<<P.n_lin_blocks, kLinThreads, dyn, st>>>(P);
   else k_linearize<SSBA_JACOBIAN_ANALYTIC><<<P.n_lin_blocks, kLinThreads, dyn, st>>>(P);
 }
@@ -1986,7 +2001,7 @@ void launch_update(const DeviceProblem &P, bool fused_control, cudaStream_t st) 
     cudaFuncSetAttribute(k_update<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoseStageMaxBytes);
     cudaFuncSetAttribute(k_update<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPoseStageMaxBytes);
   });
-  const size_t dyn = lin ? pose_stage_bytes(P.n_poses) : 0;
+  const size_t dyn = lin ? P.pose_stage : 0;
   if (fused_control) {
     if (lin) launch_maybe_pdl(k_update<true, true>, dim3(P.n_upd_blocks), dim3(kLinThreads), dyn, st, P.pdl != 0, P);
     else launch_maybe_pdl(k_update<true, false>, dim3(P.n_upd_blocks), dim3(kLinThreads), 0, st, P.pdl != 0, P);
@@ -2015,6 +2030,12 @@ void launch_control_p2p(const DeviceProblem &P, cudaStream_t st) { k_control_p2p
 void launch_final_chi2(const DeviceProblem &P, double threshold, cudaStream_t st) {
   k_final_chi2<<<P.n_fin_blocks, kLinThreads, 0, st>>>(P, threshold, 0);
   k_final_reduce<<<1, 256, 0, st>>>(P);
+}
+
+void launch_gather_edge_values(const DeviceProblem &P, const double *raw_uv, const double *raw_info, const double *raw_delta, cudaStream_t st) {
+  if (P.n_edges <= 0) return;
+  k_gather_edge_values<<<div_up(P.n_edges, 256), 256, 0, st>>>(P, raw_uv, raw_info, raw_delta, const_cast<double *>(P.e_uv),
+                                                                 const_cast<double *>(P.e_info), const_cast<double *>(P.e_delta));
 }
 
 void launch_gather_points(const DeviceProblem &P, cudaStream_t st) {

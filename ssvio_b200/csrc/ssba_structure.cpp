@@ -1108,7 +1108,8 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   s.slot_vertex.assign(slots.begin(), slots.end());
   s.slot_free.resize(s.n_slots);
   s.slot_pair_ptr.assign(s.n_slots + 1, 0);
-  const bool have_info = !g.e_info.empty(), have_delta = !g.e_delta.empty();
+  const bool host_values = !g.values_on_device;
+  const bool have_info = host_values && !g.e_info.empty(), have_delta = host_values && !g.e_delta.empty();
   // offsets of every slot's edges, pairs and Schur targets (prefix sums), then a parallel fill
   std::vector<int32_t> slot_edge_ptr(s.n_slots + 1, 0);
   for (int sl = 0; sl < s.n_slots; ++sl) {
@@ -1121,7 +1122,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   {
     const size_t ne_local = (size_t)slot_edge_ptr[s.n_slots], np_local = (size_t)s.slot_pair_ptr[s.n_slots];
     s.n_edges = (int)ne_local; s.n_pairs = (int)np_local;
-    s.e_orig.resize(ne_local); s.e_uv.resize(2 * ne_local); s.e_cam.resize(ne_local);
+    s.e_orig.resize(ne_local); s.e_uv.resize(host_values ? 2 * ne_local : 0); s.e_cam.resize(ne_local);
     if (have_info) s.e_info.resize(3 * ne_local);
     if (have_delta) s.e_delta.resize(ne_local);
     s.pair_vertex.resize(np_local); s.pair_q.resize(np_local); s.pair_edge_ptr.resize(np_local + 1);
@@ -1141,9 +1142,11 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
         const int j = slots[sl];
         if (sl + 6 < s1) {  // the class order visits landmarks far apart in the caller's arrays
           const int e_next = pe[pt_ptr[slots[sl + 6]]];
-          __builtin_prefetch(ge_uv + 2 * (size_t)e_next);
-          __builtin_prefetch(ge_uv + 2 * (size_t)e_next + 8);
-          __builtin_prefetch(ge_uv + 2 * (size_t)e_next + 16);
+          if (host_values) {
+            __builtin_prefetch(ge_uv + 2 * (size_t)e_next);
+            __builtin_prefetch(ge_uv + 2 * (size_t)e_next + 8);
+            __builtin_prefetch(ge_uv + 2 * (size_t)e_next + 16);
+          }
           __builtin_prefetch(ge_pose + e_next);
           __builtin_prefetch(ge_cam + e_next);
         }
@@ -1160,7 +1163,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
             o_pv[npair] = pose; o_pq[npair] = q; o_pe[npair] = (int32_t)ne; o_ps[npair] = sl; ++npair;
           }
           o_orig[ne] = e;
-          o_uv[2 * ne] = ge_uv[2 * (size_t)e]; o_uv[2 * ne + 1] = ge_uv[2 * (size_t)e + 1];
+          if (host_values) { o_uv[2 * ne] = ge_uv[2 * (size_t)e]; o_uv[2 * ne + 1] = ge_uv[2 * (size_t)e + 1]; }
           o_cam[ne] = ge_cam[e];
           if (have_info) for (int u = 0; u < 3; ++u) s.e_info[3 * ne + u] = g.e_info[3 * (size_t)e + u];
           if (have_delta) s.e_delta[ne] = g.e_delta[e];

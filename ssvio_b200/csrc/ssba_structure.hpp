@@ -47,6 +47,10 @@ struct HostGraph {
   uvec<double> e_info;                         // 3 per edge or empty (identity)
   uvec<double> e_delta;                        // 1 per edge or empty (delta_all)
   double delta_all = 0.0;
+  // the measurement values (uv, information, Huber widths) never visit these vectors: the caller's arrays went to
+  // the device in the caller's order and a kernel gathers them into the structure's edge order (ssba_api.cu);
+  // build_structure then fills indices only
+  bool values_on_device = false, has_info = false, has_delta = false;
 };
 
 struct Structure {
