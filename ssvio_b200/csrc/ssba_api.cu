@@ -1240,6 +1240,25 @@ ssba_status ssba_pose_graph_optimize(ssba_handle *h, int32_t n_poses, const doub
       eblk[e] = (int32_t)(it - s.blk_row.data());
     }
   }
+  // producers of every block of H and of every right-hand side, in edge order (the fixed summation order of
+  // k_pg_assemble): offsets into the per-edge staging records of k_pg_linearize
+  std::vector<int32_t> prod_ptr(s.n_blocks + nf + 1, 0), prod;
+  {
+    auto lists_of = [&](int e, int out[5][2]) {  // {list, offset in the record} of what edge e produces; list < 0: nothing
+      const int q0 = eq0[e], q1 = eq1[e];
+      out[0][0] = q0 >= 0 ? s.col_ptr[q0] : -1; out[0][1] = 0;            // diagonal block of q0 (first block of its column)
+      out[1][0] = q1 >= 0 ? s.col_ptr[q1] : -1; out[1][1] = 36;
+      out[2][0] = eblk[e]; out[2][1] = 72;
+      out[3][0] = q0 >= 0 ? s.n_blocks + q0 : -1; out[3][1] = 108;
+      out[4][0] = q1 >= 0 ? s.n_blocks + q1 : -1; out[4][1] = 114;
+    };
+    int tmp[5][2];
+    for (int e = 0; e < ne; ++e) { lists_of(e, tmp); for (auto &t : tmp) if (t[0] >= 0) ++prod_ptr[t[0] + 1]; }
+    for (size_t i = 1; i < prod_ptr.size(); ++i) prod_ptr[i] += prod_ptr[i - 1];
+    prod.resize(prod_ptr.back());
+    std::vector<int32_t> fillp(prod_ptr.begin(), prod_ptr.end() - 1);
+    for (int e = 0; e < ne; ++e) { lists_of(e, tmp); for (auto &t : tmp) if (t[0] >= 0) prod[fillp[t[0]]++] = 120 * e + t[1]; }
+  }
   // ---- device buffer: static part (uploaded), then work buffers
   DeviceProblem P;
   std::memset(&P, 0, sizeof(P));
@@ -1255,10 +1274,11 @@ ssba_status ssba_pose_graph_optimize(ssba_handle *h, int32_t n_poses, const doub
                o_minv = place(minv.data(), 56 * (size_t)ne), o_poq = place(pose_of_q.data(), 4 * (size_t)nf),
                o_brow = place(s.blk_row.data(), 4 * s.blk_row.size()), o_bcol = place(s.blk_col.data(), 4 * s.blk_col.size()),
                o_cdiag = place(s.col_ptr.data(), 4 * s.col_ptr.size()), o_prog = place(s.prog.data(), 4 * s.prog.size()),
-               o_pptr = place(s.prog_ptr.data(), 4 * s.prog_ptr.size()), o_tprog = place(s.tree.words.data(), 4 * s.tree.words.size());
+               o_pptr = place(s.prog_ptr.data(), 4 * s.prog_ptr.size()), o_tprog = place(s.tree.words.data(), 4 * s.tree.words.size()),
+               o_prodp = place(prod_ptr.data(), 4 * prod_ptr.size()), o_prod = place(prod.data(), 4 * prod.size());
   const size_t o_pose1 = place(nullptr, 56 * (size_t)n_poses), o_sysH = place(nullptr, 8 * P.sys_doubles), o_sys = place(nullptr, 8 * P.sys_doubles),
                o_xp = place(nullptr, 48 * (size_t)nf), o_scal = place(nullptr, 64), o_ctl = place(nullptr, sizeof(Control)),
-               o_txchg = place(nullptr, 8 * (size_t)std::max(s.tree.xchg_doubles, 2));
+               o_txchg = place(nullptr, 8 * (size_t)std::max(s.tree.xchg_doubles, 2)), o_stage = place(nullptr, 8 * 120 * (size_t)std::max(ne, 1));
   const size_t total = align_up(top);
   if (total > h->d_pg_bytes) {
     if (h->d_pg) cudaFree(h->d_pg);
@@ -1295,7 +1315,8 @@ ssba_status ssba_pose_graph_optimize(ssba_handle *h, int32_t n_poses, const doub
   while (!c.done) {
     const int batch = std::max(1, iters - c.outer_iter);
     for (int i = 0; i < batch; ++i) {
-      launch_pose_graph_slot(P, ne, d_ev0, d_ev1, d_eq0, d_eq1, d_eblk, d_minv, d_sysH, first, h->stream);
+      launch_pose_graph_slot(P, ne, d_ev0, d_ev1, d_eq0, d_eq1, d_eblk, d_minv, d_sysH, (double *)(d + o_stage),
+                             (const int32_t *)(d + o_prodp), (const int32_t *)(d + o_prod), first, h->stream);
       h->prof.kernel_launches += first ? 6 : 5;
       first = false;
     }

@@ -184,8 +184,8 @@ int kernels_per_linearize();
 // pose-graph optimisation: one LM trial (zero / linearise when needed, lambda_0 in the first slot, H + lambda I,
 // the level-scheduled solver, chi2 of current and trial poses, accept / reject); chi2 of the current poses
 void launch_pose_graph_slot(const DeviceProblem &P, int n_edges, const int32_t *ev0, const int32_t *ev1, const int32_t *eq0,
-                            const int32_t *eq1, const int32_t *eblk, const double *minv, double *sysH, bool first,
-                            cudaStream_t st);
+                            const int32_t *eq1, const int32_t *eblk, const double *minv, double *sysH, double *stage,
+                            const int32_t *prod_ptr, const int32_t *prod, bool first, cudaStream_t st);
 void launch_pose_graph_chi(const DeviceProblem &P, int n_edges, const int32_t *ev0, const int32_t *ev1, const double *minv,
                            cudaStream_t st);
 int max_solver_cluster();  // largest k_reduced_solve cluster the current device can co-schedule

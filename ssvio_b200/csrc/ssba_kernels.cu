@@ -1748,71 +1748,89 @@ struct PoseGraphArgs {
   const int32_t *eblk;        // off-diagonal block (row max(q0,q1), col min) or -1
   const double *minv;         // n_edges x 7: measurement^-1
   double *sysH;               // H and b of the current linearisation, layout of DeviceProblem::sys
+  // deterministic assembly: every edge stores its three 6x6 products and two 6-vectors (120 doubles); every block
+  // / right-hand side of H sums its producers in edge order (lists made by the host): no atomics
+  double *stage;              // n_edges x 120: [J0^T J0 | J1^T J1 | Jrow^T Jcol | -J0^T e | -J1^T e]
+  const int32_t *prod_ptr;    // n_blocks + n_fp + 1: producers of every block, then of every right-hand side
+  const int32_t *prod;        // offsets into `stage` (in doubles)
 };
 
-__global__ void k_pg_begin(const DeviceProblem P, const PoseGraphArgs A) {
+// One WARP per edge: the 24 perturbed evaluations of the central differences (2 vertices x 6 directions x +-delta)
+// run on 24 lanes at once instead of one after the other in one thread (the reference's order of operations inside
+// every evaluation is kept, so the Jacobian entries are the same numbers); the J^T J / J^T e products are then
+// spread over the lanes.  (One thread per edge: 85 us per launch on 400 key-frames, the largest part of the whole
+// pose-graph optimisation.)
+constexpr int kPgWarps = 4;
+__global__ void __launch_bounds__(32 * kPgWarps) k_pg_linearize(const DeviceProblem P, const PoseGraphArgs A) {
   const Control *ctl = P.ctl;
   if (ctl->done || !ctl->need_linearize) return;
-  const size_t n = 36 * (size_t)P.n_blocks + 6 * (size_t)P.n_fp;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) A.sysH[i] = 0.0;
-}
-
-__global__ void __launch_bounds__(64) k_pg_linearize(const DeviceProblem P, const PoseGraphArgs A) {
-  const Control *ctl = P.ctl;
-  if (ctl->done || !ctl->need_linearize) return;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= A.n_edges) return;
+  __shared__ double s_J[kPgWarps][2][36];  // per warp: J0, J1 row-major 6x6: J[6 * k + d] = d e_k / d delta_d
+  __shared__ double s_err[kPgWarps][6];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = blockIdx.x * kPgWarps + warp;
+  if (e >= A.n_edges) return;  // whole warp
   const double *pose = P.pose[ctl->cur];
-  double T0[7], T1[7], Mi[7], err[6];
+  double T0[7], T1[7], Mi[7];
 #pragma unroll
   for (int i = 0; i < 7; ++i) { T0[i] = pose[7 * A.ev0[e] + i]; T1[i] = pose[7 * A.ev1[e] + i]; Mi[i] = A.minv[7 * e + i]; }
-  pose_graph_error(Mi, T0, T1, err);
   const int q0 = A.eq0[e], q1 = A.eq1[e];
   const double delta = 1e-9, scalar = 1 / (2 * delta);
-  double J0[36], J1[36];  // row-major 6x6: J[6 * k + d] = d e_k / d delta_d
-#pragma unroll 1
-  for (int d = 0; d < 6; ++d) {
-    double add[6] = {0, 0, 0, 0, 0, 0}, Tp[7], ep[6], em[6];
-    if (q0 >= 0) {
-      add[d] = delta; pose_oplus(T0, add, Tp); pose_graph_error(Mi, Tp, T1, ep);
-      add[d] = -delta; pose_oplus(T0, add, Tp); pose_graph_error(Mi, Tp, T1, em);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) J0[6 * k + d] = scalar * (ep[k] - em[k]);
-    }
-    if (q1 >= 0) {
-      add[d] = delta; pose_oplus(T1, add, Tp); pose_graph_error(Mi, T0, Tp, ep);
-      add[d] = -delta; pose_oplus(T1, add, Tp); pose_graph_error(Mi, T0, Tp, em);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) J1[6 * k + d] = scalar * (ep[k] - em[k]);
-    }
+  // lane = 12 * side + 2 * d + (0: +delta, 1: -delta); lanes 24..31: the unperturbed error (lane 24 keeps it)
+  const int side = lane / 12, d = (lane % 12) >> 1, minus = lane & 1;
+  double ev[6];
+  if (lane < 24) {
+    double add[6] = {0, 0, 0, 0, 0, 0}, Tp[7];
+    add[d] = minus ? -delta : delta;
+    if (side == 0) { pose_oplus(T0, add, Tp); pose_graph_error(Mi, Tp, T1, ev); }
+    else { pose_oplus(T1, add, Tp); pose_graph_error(Mi, T0, Tp, ev); }
+  } else {
+    pose_graph_error(Mi, T0, T1, ev);
   }
-  double *bvec = A.sysH + 36 * (size_t)P.n_blocks;
-  // constructQuadraticForm (base_binary_edge.hpp:61-134) with Omega = I and no robust kernel
-  auto add_diag = [&](int q, const double *J) {
-    double *D = A.sysH + 36 * (size_t)P.col_diag[q];
-    for (int r = 0; r < 6; ++r) {
-      double br = 0.0;
-      for (int k = 0; k < 6; ++k) br -= J[6 * k + r] * err[k];
-      atomicAdd(bvec + 6 * q + r, br);
-      for (int c = 0; c < 6; ++c) {
-        double h = 0.0;
-        for (int k = 0; k < 6; ++k) h += J[6 * k + r] * J[6 * k + c];
-        atomicAdd(D + 6 * r + c, h);
-      }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double em = __shfl_down_sync(0xffffffffu, ev[k], 1);  // the -delta evaluation sits on the next lane
+    if (lane < 24 && !minus) s_J[warp][side][6 * k + d] = scalar * (ev[k] - em);
+    if (lane == 24) s_err[warp][k] = ev[k];
+  }
+  __syncwarp();
+  // constructQuadraticForm (base_binary_edge.hpp:61-134) with Omega = I and no robust kernel, into this edge's staging
+  // record (k_pg_assemble sums the records of every block in edge order): 120 outputs over 32 lanes
+  double *st = A.stage + 120 * (size_t)e;
+  const double *J0 = s_J[warp][0], *J1 = s_J[warp][1], *err = s_err[warp];
+  for (int o = lane; o < 120; o += 32) {
+    double v = 0.0;
+    if (o < 108) {
+      const int part = o / 36, rc = o - 36 * part, r = rc / 6, c = rc - 6 * r;
+      const double *Ja, *Jb;
+      if (part == 0) { if (q0 < 0) continue; Ja = J0; Jb = J0; }
+      else if (part == 1) { if (q1 < 0) continue; Ja = J1; Jb = J1; }
+      else { if (q0 < 0 || q1 < 0) continue; Ja = q0 > q1 ? J0 : J1; Jb = q0 > q1 ? J1 : J0; }  // block (row max(q0, q1), col min): Jrow^T Jcol
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v += Ja[6 * k + r] * Jb[6 * k + c];
+    } else {
+      const int sd = (o - 108) / 6, r = (o - 108) - 6 * sd;
+      if ((sd == 0 ? q0 : q1) < 0) continue;
+      const double *J = sd == 0 ? J0 : J1;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v -= J[6 * k + r] * err[k];
     }
-  };
-  if (q0 >= 0) add_diag(q0, J0);
-  if (q1 >= 0) add_diag(q1, J1);
-  if (q0 >= 0 && q1 >= 0) {
-    // block (row max(q0, q1), col min): Jrow^T Jcol
-    const double *Jr = q0 > q1 ? J0 : J1, *Jc = q0 > q1 ? J1 : J0;
-    double *B = A.sysH + 36 * (size_t)A.eblk[e];
-    for (int r = 0; r < 6; ++r)
-      for (int c = 0; c < 6; ++c) {
-        double h = 0.0;
-        for (int k = 0; k < 6; ++k) h += Jr[6 * k + r] * Jc[6 * k + c];
-        atomicAdd(B + 6 * r + c, h);
-      }
+    st[o] = v;
+  }
+}
+
+// H and b of the linearisation: every scalar of every block (and right-hand side) = the sum of its producers' staged
+// values, in edge order -> sysH (kept for the re-trials of the iteration)
+__global__ void __launch_bounds__(256) k_pg_assemble(const DeviceProblem P, const PoseGraphArgs A) {
+  const Control *ctl = P.ctl;
+  if (ctl->done || !ctl->need_linearize) return;
+  const size_t nb = 36 * (size_t)P.n_blocks, nv = 6 * (size_t)P.n_fp;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nb + nv; i += (size_t)gridDim.x * blockDim.x) {
+    int list, o;
+    if (i < nb) { list = (int)(i / 36); o = (int)(i - 36 * (size_t)list); }
+    else { const size_t v = i - nb; list = P.n_blocks + (int)(v / 6); o = (int)(v % 6); }
+    double acc = 0.0;
+    for (int p = A.prod_ptr[list]; p < A.prod_ptr[list + 1]; ++p) acc += A.stage[A.prod[p] + o];
+    A.sysH[i] = acc;
   }
 }
 
@@ -2052,12 +2070,12 @@ void launch_outlier_mask(const DeviceProblem &P, double threshold, cudaStream_t 
 }
 
 void launch_pose_graph_slot(const DeviceProblem &P, int n_edges, const int32_t *ev0, const int32_t *ev1, const int32_t *eq0,
-                            const int32_t *eq1, const int32_t *eblk, const double *minv, double *sysH, bool first,
-                            cudaStream_t st) {
-  PoseGraphArgs A{n_edges, ev0, ev1, eq0, eq1, eblk, minv, sysH};
+                            const int32_t *eq1, const int32_t *eblk, const double *minv, double *sysH, double *stage,
+                            const int32_t *prod_ptr, const int32_t *prod, bool first, cudaStream_t st) {
+  PoseGraphArgs A{n_edges, ev0, ev1, eq0, eq1, eblk, minv, sysH, stage, prod_ptr, prod};
   const int nz = div_up((long long)P.sys_doubles, 256);
-  k_pg_begin<<<nz, 256, 0, st>>>(P, A);
-  if (n_edges > 0) k_pg_linearize<<<div_up(n_edges, 64), 64, 0, st>>>(P, A);
+  if (n_edges > 0) k_pg_linearize<<<div_up(n_edges, kPgWarps), 32 * kPgWarps, 0, st>>>(P, A);
+  k_pg_assemble<<<nz, 256, 0, st>>>(P, A);
   if (first) k_pg_lambda_init<<<1, 256, 0, st>>>(P, A);
   k_pg_prepare<<<nz, 256, 0, st>>>(P, A);
   launch_reduced_solve(P, st);
@@ -2066,7 +2084,7 @@ void launch_pose_graph_slot(const DeviceProblem &P, int n_edges, const int32_t *
 
 void launch_pose_graph_chi(const DeviceProblem &P, int n_edges, const int32_t *ev0, const int32_t *ev1, const double *minv,
                            cudaStream_t st) {
-  PoseGraphArgs A{n_edges, ev0, ev1, nullptr, nullptr, nullptr, minv, nullptr};
+  PoseGraphArgs A{n_edges, ev0, ev1, nullptr, nullptr, nullptr, minv, nullptr, nullptr, nullptr, nullptr};
   k_pg_chi_control<<<1, 256, 0, st>>>(P, A, 0);
 }
 

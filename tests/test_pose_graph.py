@@ -78,3 +78,7 @@ def test_cuda_matches_oracle_and_edge_cases(ssba_lib):
         big = synth.make_pose_graph(400, seed=9, n_loops=8)
         poses, rep = opt.pose_graph_optimize(big, iters=10)
         assert rep.iterations == 10 and rep.chi2_robust < 0.01 * rep.chi2_initial and rep.cholesky_failures == 0
+        # H and b are assembled in a fixed order (k_pg_assemble, no atomics): the same bits again
+        poses2, rep2 = opt.pose_graph_optimize(big, iters=10)
+        np.testing.assert_array_equal(poses, poses2)
+        assert rep2.trace() == rep.trace()
