@@ -31,6 +31,22 @@ int main(int argc, char **argv) {
     for (int k = 0; k < 12; ++k) std::printf(" %d", hist[k]);
     std::printf("\n");
   }
+  {
+    // fundamental / relaxed supernode chains in the final order: column j merges into its parent p when p == j + 1 is its
+    // etree parent and struct(j) = struct(p) + {p} (fundamental), or with `extra` explicit zero blocks (relaxed)
+    const int n = s.n_fp;
+    int fund = 0, relax1 = 0, relax2 = 0;
+    std::vector<int> chain(n, 1);
+    for (int j = 0; j + 1 < n; ++j) {
+      const int nbj = s.col_ptr[j + 1] - s.col_ptr[j] - 1;
+      if (nbj == 0 || s.blk_row[s.col_ptr[j] + 1] != j + 1) continue;
+      const int nbp = s.col_ptr[j + 2] - s.col_ptr[j + 1] - 1;
+      const int extra = nbp + 1 - nbj;
+      if (extra == 0) ++fund; else if (extra == 1) ++relax1; else if (extra == 2) ++relax2;
+      std::printf("col %3d -> %3d: blocks %2d parent blocks %2d extra %d\n", j, j + 1, nbj, nbp, extra);
+    }
+    std::printf("parent == j+1 pairs: fundamental %d, one extra block %d, two %d (of %d columns)\n", fund, relax1, relax2, n);
+  }
   const TreeProgram &tp = s.tree;
   if (!tp.ok) { std::printf("tree program not built: %s\n", tp.why_not.c_str()); return 0; }
   std::printf("tree: C %d smem %zu chain_steps %d top cols %d xchg doubles %d words %zu\n", tp.C, tp.smem_bytes, tp.chain_steps, tp.n_top_cols, tp.xchg_doubles, tp.words.size());

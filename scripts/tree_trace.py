@@ -32,9 +32,9 @@ for c in (0, 1):
 
 for c in (0, 1):
     for st in (4, 5):
-        f = out[c, 200 + 8 * (st - 4): 208 + 8 * (st - 4)]
-        if f[0] == 0: continue
-        print(f"CTA {c} step {st}: warp 0 (cycles since step start): descriptors fetched {f[1]-f[0]} | products done {f[2]-f[0]} | inverse done {f[3]-f[0]} | barrier 1 passed {f[4]-f[0]} | barrier 2 passed {f[5]-f[0]}")
-        w = out[c, 128 + 32 * (st - 4): 160 + 32 * (st - 4)].reshape(16, 2)
-        print("    warps arrive at barrier 1: " + " ".join(str(int(x - f[0])) for x in w[:, 0]))
-        print("    warps arrive at barrier 2: " + " ".join(str(int(x - f[0])) for x in w[:, 1]))
+        w = out[c, 128 + 32 * (st - 4): 128 + 32 * (st - 4) + 30].reshape(6, 5)
+        if w[0, 0] == 0: continue
+        t0 = w[:, 0].min()
+        print(f"CTA {c} step {st} (cycles since the first warp entered the step); warp 0 = diagonal: start | own blocks scaled | products done | inverse done | barrier passed;  warps 1..5 = look-ahead: start | panel done | named barrier passed | look-ahead done | barrier passed")
+        for k in range(6):
+            print(f"    warp {k}: " + " | ".join(str(int(x - t0)) if x else "-" for x in w[k]))

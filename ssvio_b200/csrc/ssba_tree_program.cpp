@@ -313,6 +313,7 @@ bool build_tree_program(int n, const std::vector<int32_t> &col_ptr, const std::v
       if (a.step[q] < 0 || a.step[q] >= ns) return fail("internal: step out of range");
       step_cols[a.step[q]].push_back(q);
     }
+    std::vector<std::vector<Item>> pre_of(q1[c] - q0[c]);  // column -> critical panel items feeding it (filled one step earlier)
     for (int s = 0; s < ns; ++s) {
       const std::vector<int> &cols = step_cols[s];
       const int nc = (int)cols.size();
@@ -367,11 +368,31 @@ bool build_tree_program(int n, const std::vector<int32_t> &col_ptr, const std::v
         if (i >= look.size()) push_product_item(w, 0, 0, 0, 0);
         else if (!push_product_item(w, look[i].dest, look[i].nrows, off_pairs + look[i].p0, look[i].p1 - look[i].p0)) return fail("too many products for one block");
       }
-      // panel rounds: every sub-diagonal block row-wise times L_jj^-T, then the right-hand sides
+      // the critical panel items of the previous step, per diagonal item of this one
+      st = step_entry();
+      st[kTS_OffPre] = (int)w.size();
+      {
+        const size_t tab = w.size();
+        w.resize(w.size() + 2 * (size_t)nc, 0);
+        for (int t = 0; t < nc; ++t) {
+          std::vector<Item> &pre = pre_of[cols[t] - q0[c]];
+          w[tab + 2 * t] = (int)pre.size();
+          w[tab + 2 * t + 1] = (int)w.size();
+          for (const Item &it : pre) push_panel_item(w, it.dest, it.nrows, it.p0, it.p1);
+          pre.clear();
+        }
+      }
+      // panel items: every sub-diagonal block row-wise times M_j, then the right-hand sides.  A block whose ROW is a
+      // column of this CTA's next step feeds that column's critical products: it goes to that column's lane group
       std::vector<Item> panel;
       for (int t = 0; t < nc; ++t) {
         const int j = cols[t], dblk = 36 * (col_ptr[j] - tp.b0[c]);
-        for (int b = col_ptr[j] + 1; b < col_ptr[j + 1]; ++b) panel.push_back(Item{36 * (b - tp.b0[c]), 6, dblk, XC0[c] + 36 * xcopy_idx[b]});
+        for (int b = col_ptr[j] + 1; b < col_ptr[j + 1]; ++b) {
+          const int i = blk_row[b];
+          const Item it{36 * (b - tp.b0[c]), 6, dblk, XC0[c] + 36 * xcopy_idx[b]};
+          if (own(c, i) && a.step[i] == s + 1 && s + 1 < ns) pre_of[i - q0[c]].push_back(it);
+          else panel.push_back(it);
+        }
       }
       for (int t = 0; t < nc; ++t) {
         const int j = cols[t];

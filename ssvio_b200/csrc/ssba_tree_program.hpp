@@ -22,7 +22,9 @@
 // The products of a finished column k are applied eagerly (right-looking), ALL of them in the step after k's
 // (which is why the unscaled copy only lives for one step): the ones a diagonal block of the next step waits
 // for by the warp that inverts it, all others by the remaining warps WHILE the diagonal blocks are being
-// inverted.  Two __syncthreads per step.
+// inverted.  ONE __syncthreads per step: the scaling Y = X M of a finished column's blocks happens at the start of
+// the next step - the blocks the next diagonal blocks wait for by their own lane groups, the rest by the
+// look-ahead warps, which meet the diagonal warps' results at a named barrier before their products.
 //
 // Everything the kernel walks is planned here; a CPU interpreter of the same program
 // (tests/cpp/test_structure.cpp) checks it against a dense solve.
@@ -50,7 +52,11 @@ constexpr int kTreeItemWords = 2, kTreeRoundWords = 5 * kTreeItemWords;
 // program header words
 enum : int { kTH_StepsA = 0, kTH_StepsB, kTH_OffSteps, kTH_AddRounds, kTH_OffAddRounds, kTH_NXload, kTH_OffXload, kTH_TopCol0, kTH_Words = 16 };
 // step table entry (8 words)
-enum : int { kTS_Cols = 0, kTS_OffDiag, kTS_NLook, kTS_OffLook, kTS_NPanel, kTS_OffPanel, kTS_OffBwd, kTS_Words = 8 };
+// kTS_OffPre: per diagonal item of the step two words { n, offset } = the panel items of the PREVIOUS step's columns
+// that feed this column's critical products (its own block row): the lane group that inverts the column scales them
+// itself, first thing in the step; kTS_NPanel / kTS_OffPanel: the other panel items of THIS step's columns, run by the
+// look-ahead warps at the start of the next step (or after the last one)
+enum : int { kTS_Cols = 0, kTS_OffDiag, kTS_NLook, kTS_OffLook, kTS_NPanel, kTS_OffPanel, kTS_OffBwd, kTS_OffPre, kTS_Words = 8 };
 
 struct TreeProgram {
   bool ok = false;

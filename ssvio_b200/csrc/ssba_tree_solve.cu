@@ -103,7 +103,9 @@ __device__ __forceinline__ long long ts_gtime() { long long t; asm volatile("mov
 #define TS_TRACE_C(i) do { if (threadIdx.x == 0 && (i) < 256) g_tree_trace[cta][(i)] = clock64(); } while (0)
 // fine trace of warp 0 inside the intervals of every step: 8 stamps per step from entry 128 on (steps 0..15)
 #define TS_TRACE_F(s, k) do { if (threadIdx.x == 0 && ((s) == 4 || (s) == 5)) g_tree_trace[cta][200 + 8 * ((s) - 4) + (k)] = clock64(); } while (0)
-#define TS_TRACE_W(s, k) do { if ((threadIdx.x & 31) == 0 && ((s) == 4 || (s) == 5)) g_tree_trace[cta][128 + 32 * ((s) - 4) + 2 * (threadIdx.x >> 5) + (k)] = clock64(); } while (0)
+// per warp, steps 4 and 5: five stamps (diagonal warp: step start, scaled its blocks, products done, inverse done, barrier
+// passed; look-ahead warp: step start, panel done, named barrier passed, look-ahead done, barrier passed) for warps 0..5
+#define TS_TRACE_W(s, k) do { if ((threadIdx.x & 31) == 0 && ((s) == 4 || (s) == 5) && (threadIdx.x >> 5) < 6) g_tree_trace[cta][128 + 32 * ((s) - 4) + 5 * (threadIdx.x >> 5) + (k)] = clock64(); } while (0)
 #else
 #define TS_TRACE_F(s, k) do { } while (0)
 #define TS_TRACE_W(s, k) do { } while (0)
@@ -200,7 +202,9 @@ __global__ void __launch_bounds__(kTreeThreads, 1) k_tree_solve(const DeviceProb
   {
     int4 da = *reinterpret_cast<const int4 *>(steps), db = *reinterpret_cast<const int4 *>(steps + 4);
     int2 dit = make_int2(0, 0);   // this lane group's diagonal item of the running step
-    unsigned dpw = 0;             // ... and its first pair word
+    unsigned dpw = 0;             // ... its first pair word
+    int2 dpre = make_int2(0, 0);  // ... and the critical panel items of the previous step it scales itself
+    int p_n = 0, p_off = 0;       // the previous step's other panel items (rounds, offset)
     if (g < 5 && ci < da.x) {
       dit = *reinterpret_cast<const int2 *>(prog + da.y + kTreeItemWords * ci);
       if ((unsigned)dit.x >> 20) dpw = (unsigned)prog[dit.y];
@@ -260,65 +264,105 @@ __global__ void __launch_bounds__(kTreeThreads, 1) k_tree_solve(const DeviceProb
         TS_TRACE_G(4);
       }
       if (s >= ns_all) break;
-      const int nc = da.x, n_look = da.z, off_look = da.w, n_panel = db.x, off_panel = db.y;
-      TS_TRACE_F(s, 0);
-      // program data of the next step and of this step's panel (nothing the steps write)
+      const int nc = da.x, n_look = da.z, off_look = da.w;
+      // program data of the next step (nothing the steps write)
       int4 na = make_int4(0, 0, 0, 0), nb = na;
       if (s + 1 < ns_all) { na = *reinterpret_cast<const int4 *>(steps + kTS_Words * (s + 1)); nb = *reinterpret_cast<const int4 *>(steps + kTS_Words * (s + 1) + 4); }
-      int2 pit = make_int2(0, 0);   // this warp's first panel item
-      if (warp < n_panel && g < 5) pit = *reinterpret_cast<const int2 *>(prog + off_panel + kTreeRoundWords * warp + kTreeItemWords * g);
-      int2 nit = make_int2(0, 0);   // the next step's diagonal item and first pair word
+      int2 nit = make_int2(0, 0), npre = make_int2(0, 0);  // the next step's diagonal item, first pair word, critical panel list
       unsigned npw = 0;
       if (g < 5 && ci < na.x) {
         nit = *reinterpret_cast<const int2 *>(prog + na.y + kTreeItemWords * ci);
+        npre = *reinterpret_cast<const int2 *>(prog + nb.w + 2 * ci);
         if ((unsigned)nit.x >> 20) npw = (unsigned)prog[nit.y];
       }
-      // interval 1: the diagonal blocks of this step (the products they still wait for, then the closed-form
-      // inverse in one lane per column) on the first warps, beside the look-ahead products of the previous
-      // step's columns on the others (rounds dealt statically: no shared counter on anybody's path)
+      // Y = X M row by row (the unscaled row goes to the scratch copy the products read), w = z M for a vector item
+      auto panel_item = [&](int2 it) {
+        const int nrows = (it.x >> 16) & 15;
+        if (r >= nrows) return;
+        double2 *D = reinterpret_cast<double2 *>(pool + (it.x & 0xffff) + 6 * r);
+        const double2 *M2 = reinterpret_cast<const double2 *>(pool + (it.y & 0xffff));
+        const double2 v0 = D[0], v1 = D[1], v2 = D[2];
+        double y[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          const double2 m0 = M2[3 * c], m1 = M2[3 * c + 1], m2 = M2[3 * c + 2];
+          y[c] = v0.x * m0.x + v0.y * m0.y + v1.x * m1.x + v1.y * m1.y + v2.x * m2.x + v2.y * m2.y;
+        }
+        D[0] = make_double2(y[0], y[1]); D[1] = make_double2(y[2], y[3]); D[2] = make_double2(y[4], y[5]);
+        if (nrows == 6) {
+          double2 *X = reinterpret_cast<double2 *>(pool + ((unsigned)it.y >> 16) + 6 * r);
+          X[0] = v0; X[1] = v1; X[2] = v2;
+        }
+      };
+      // The step, ONE block barrier: the columns of the previous step get their blocks scaled (Y = X M) first - the
+      // blocks this step's diagonal blocks wait for by the lane groups that own those diagonal blocks, all the others
+      // by the look-ahead warps; then the diagonal groups apply their critical products and invert, while the
+      // look-ahead warps meet everybody's scaled blocks at named barrier 1 and apply the products of the previous
+      // step's columns to everything else.
+      TS_TRACE_W(s, 0);
       const int nd = nc >= 5 * kTreeWarps ? kTreeWarps : (nc + 4) / 5;
+      const bool all_diag = nd == kTreeWarps;
+      const int w0 = all_diag ? warp : warp - nd, nw = all_diag ? kTreeWarps : kTreeWarps - nd;
+      if (warp < nd) {
+        const bool act = g < 5 && ci < nc;
+        if (act) {
+          for (int i = 0; i < dpre.x; ++i) panel_item(*reinterpret_cast<const int2 *>(prog + dpre.y + kTreeItemWords * i));
+        }
+        __syncwarp();
+        TS_TRACE_W(s, 1);
+        // (measured, not kept: arriving only after the critical products, so that the look-ahead warps' loads do not
+        // queue in front of the diagonal blocks' operands: 56.0 -> 59.9 us per solve - the look-ahead is on the path too)
+        if (!all_diag) asm volatile("bar.arrive 1, %0;" ::"n"(kTreeThreads) : "memory");
+      }
+      if (w0 >= 0 && g < 5) {
+        const int *rounds = prog + p_off;
+#pragma unroll 1
+        for (int rd = w0; rd < p_n; rd += nw) panel_item(*reinterpret_cast<const int2 *>(rounds + kTreeRoundWords * rd + kTreeItemWords * g));
+      }
       if (warp < nd) {
         const bool act = g < 5 && ci < nc;
         double d[6];
-        TS_TRACE_F(s, 1);
         if (act) ts_product_rows(pool, prog, dit.x, dit.y, dpw, r, d);
         __syncwarp();
-        TS_TRACE_F(s, 2);
+        TS_TRACE_W(s, 2);
         if (act && r == 0) {
           if (block_inverse6(pool + (dit.x & 0xffff))) { *s_fail = 1; ctl->chol_fail = 1; }
         }
-        TS_TRACE_F(s, 3);
+        TS_TRACE_W(s, 3);
       }
-      // (measured, not kept: holding the look-ahead loads back until the diagonal warps have their operands; keeping
-      // the warps that share a diagonal warp's scheduler out of the look-ahead; neither shortens the step)
-      if (n_look > 0 && (warp >= nd || nd == kTreeWarps)) {
-        const int *rounds = prog + off_look;
-        const int w0 = nd == kTreeWarps ? warp : warp - nd, nw = nd == kTreeWarps ? kTreeWarps : kTreeWarps - nd;
+      if (w0 >= 0) {
+        TS_TRACE_W(s, 1);
+        asm volatile("bar.sync 1, %0;" ::"n"(kTreeThreads) : "memory");
+        TS_TRACE_W(s, 2);
+        if (n_look > 0) {
+          const int *rounds = prog + off_look;
 #pragma unroll 1
-        for (int rd = w0; rd < n_look; rd += nw) {
-          if (g < 5) {
-            const int2 it = *reinterpret_cast<const int2 *>(rounds + kTreeRoundWords * rd + kTreeItemWords * g);
-            if (r < ((it.x >> 16) & 15)) {
-              double d[6];
-              ts_product_rows(pool, prog, it.x, it.y, (unsigned)prog[it.y], r, d);
+          for (int rd = w0; rd < n_look; rd += nw) {
+            if (g < 5) {
+              const int2 it = *reinterpret_cast<const int2 *>(rounds + kTreeRoundWords * rd + kTreeItemWords * g);
+              if (r < ((it.x >> 16) & 15)) {
+                double d[6];
+                ts_product_rows(pool, prog, it.x, it.y, (unsigned)prog[it.y], r, d);
+              }
             }
           }
         }
       }
-      TS_TRACE_W(s, 0);
+      p_n = db.x; p_off = db.y;  // this step's other panel items: the next step's (or the drain's) business
+      da = na; db = nb; dit = nit; dpw = npw; dpre = npre;
+      if (w0 >= 0) TS_TRACE_W(s, 3);
       __syncthreads();
-      TS_TRACE_F(s, 4);
+      TS_TRACE_W(s, 4);
 #ifdef SSBA_SOLVER_TRACE
       TS_TRACE_C(trc); ++trc;
 #endif
-      // interval 2: Y = X M_j row by row for every sub-diagonal block of the step's columns (the unscaled row
-      // goes to the scratch copy the next step's products read), w_j = M_j z_j likewise
-      {
-        const int *rounds = prog + off_panel;
-#pragma unroll 1
-        for (int rd = warp; rd < n_panel; rd += kTreeWarps) {
-          if (g >= 5) continue;
-          const int2 it = rd == warp ? pit : *reinterpret_cast<const int2 *>(rounds + kTreeRoundWords * rd + kTreeItemWords * g);
+    }
+    // the panel items of the last step (right-hand sides of the root columns)
+    if (p_n > 0) {
+      if (g < 5) {
+        const int *rounds = prog + p_off;
+        for (int rd = warp; rd < p_n; rd += kTreeWarps) {
+          const int2 it = *reinterpret_cast<const int2 *>(rounds + kTreeRoundWords * rd + kTreeItemWords * g);
           const int nrows = (it.x >> 16) & 15;
           if (r >= nrows) continue;
           double2 *D = reinterpret_cast<double2 *>(pool + (it.x & 0xffff) + 6 * r);
@@ -331,19 +375,9 @@ __global__ void __launch_bounds__(kTreeThreads, 1) k_tree_solve(const DeviceProb
             y[c] = v0.x * m0.x + v0.y * m0.y + v1.x * m1.x + v1.y * m1.y + v2.x * m2.x + v2.y * m2.y;
           }
           D[0] = make_double2(y[0], y[1]); D[1] = make_double2(y[2], y[3]); D[2] = make_double2(y[4], y[5]);
-          if (nrows == 6) {
-            double2 *X = reinterpret_cast<double2 *>(pool + ((unsigned)it.y >> 16) + 6 * r);
-            X[0] = v0; X[1] = v1; X[2] = v2;
-          }
         }
       }
-      da = na; db = nb; dit = nit; dpw = npw;
-      TS_TRACE_W(s, 1);
       __syncthreads();
-      TS_TRACE_F(s, 5);
-#ifdef SSBA_SOLVER_TRACE
-      TS_TRACE_C(trc); ++trc;
-#endif
     }
   }
   TS_TRACE_G(5);

@@ -171,15 +171,23 @@ static std::vector<double> interpret_program(const Structure &s, std::vector<dou
 struct TreeCta {
   std::vector<double> pool;
   std::vector<int> wr_t, wr_i, rd_t, rd_i;
+  // the diagonal items of a step are still running while the look-ahead items of the same step run: what they
+  // touch (dg_mode 1: record under dg_stamp) must not be touched by a look-ahead item (dg_mode 2: check)
+  std::vector<int> dg_w, dg_r;
+  int dg_mode = 0, dg_stamp = 0;
   const int32_t *w;
   int T = 0, item = 0;
   double rd2(int off) { if (off & 1) CHECK(false, "tree program: odd offset %d under a 16-byte access", off); return 0.0; }
   double rd(int off) {
+    if (dg_mode == 1) dg_r[off] = dg_stamp;
+    if (dg_mode == 2 && dg_w[off] == dg_stamp) CHECK(false, "tree program: a look-ahead item reads a double a diagonal item of the same step writes (off %d)", off);
     if (wr_t[off] == T && wr_i[off] != item) { CHECK(false, "tree program: read of a double written by another item in the same interval (off %d)", off); }
     if (rd_t[off] == T && rd_i[off] != item) rd_i[off] = -2; else { rd_t[off] = T; rd_i[off] = item; }
     return pool[off];
   }
   void wrt(int off, double v) {
+    if (dg_mode == 1) dg_w[off] = dg_stamp;
+    if (dg_mode == 2 && (dg_w[off] == dg_stamp || dg_r[off] == dg_stamp)) CHECK(false, "tree program: a look-ahead item writes a double a diagonal item of the same step touches (off %d)", off);
     if (rd_t[off] == T && rd_i[off] != item) { CHECK(false, "tree program: write of a double read by another item in the same interval (off %d)", off); }
     if (wr_t[off] == T && wr_i[off] != item) { CHECK(false, "tree program: two items write the same double in one interval (off %d)", off); }
     wr_t[off] = T; wr_i[off] = item;
@@ -198,65 +206,85 @@ static void tree_products(TreeCta &c, int dest, int nrows, int p0, int p1) {
     if (p1 > p0) for (int m = 0; m < 6; ++m) c.wrt(dest + 6 * r + m, c.rd(dest + 6 * r + m) - acc[m]);
   }
 }
+static void tree_panel_item(TreeCta &c, const int32_t *it) {
+  const int dest = it[0] & 0xffff, nrows = (it[0] >> 16) & 15, dg = it[1] & 0xffff, xc = (int)((unsigned)it[1] >> 16);
+  CHECK(dg % 2 == 0 && xc % 2 == 0 && dest % 2 == 0, "panel item misaligned");
+  for (int r = 0; r < nrows; ++r) {
+    double x[6], y[6];
+    for (int m = 0; m < 6; ++m) x[m] = c.rd(dest + 6 * r + m);
+    for (int m = 0; m < 6; ++m) { double v = 0; for (int k = 0; k < 6; ++k) v += x[k] * c.rd(dg + 6 * m + k); y[m] = v; }
+    for (int m = 0; m < 6; ++m) c.wrt(dest + 6 * r + m, y[m]);       // Y = X M in place
+    if (nrows == 6) for (int m = 0; m < 6; ++m) c.wrt(xc + 6 * r + m, x[m]);  // the unscaled row for the next step's products
+  }
+}
+// One step = two intervals on the device.  Interval A: every diagonal column as ONE work item (the panel items of
+// the previous step that feed it, its critical products, the inverse - one lane group does all three, in order)
+// beside the other panel items of the previous step (the look-ahead warps).  Named barrier.  Interval B: the
+// look-ahead products - the diagonal groups may still be busy with their item, which is why that item must not
+// touch anything an interval-B item touches (same T for both is too strict only for reads of the inverse, which
+// nobody does before the next step).
 static void tree_forward_steps(TreeCta &c, int s0, int s1, bool *fail) {
   const int32_t *w = c.w;
-  for (int s = s0; s < s1; ++s) {
-    const int32_t *st = w + w[kTH_OffSteps] + kTS_Words * s;
-    // alignment the kernel's vector loads rely on (program base is 16-byte aligned)
-    CHECK(st[kTS_OffDiag] % 2 == 0 && st[kTS_OffLook] % 2 == 0 && st[kTS_OffPanel] % 2 == 0 && st[kTS_OffBwd] % 4 == 0, "tree program: item arrays misaligned");
-    ++c.T;  // interval 1: diagonal items and look-ahead rounds
-    for (int t = 0; t < st[kTS_Cols]; ++t) {
-      ++c.item;
-      const int32_t *it = w + st[kTS_OffDiag] + kTreeItemWords * t;
-      const int d = it[0] & 0xffff;
-      CHECK(((it[0] >> 16) & 15) == 6, "diagonal item rows");
-      tree_products(c, d, 6, it[1], it[1] + (int)((unsigned)it[0] >> 20));
-      // M = D^-1 from the LOWER triangle, written back as the full symmetric block; D must be positive definite
-      double a[36], Ls[36] = {0}, Li[36] = {0}, M[36];
-      for (int i = 0; i < 6; ++i) for (int k = 0; k <= i; ++k) a[6 * i + k] = c.rd(d + 6 * i + k);
-      for (int j = 0; j < 6; ++j) {  // reference route: Cholesky, triangular inverse, M = L^-T L^-1
-        double dj = a[7 * j];
-        for (int k = 0; k < j; ++k) dj -= Ls[6 * j + k] * Ls[6 * j + k];
-        if (!(dj > 0)) { *fail = true; dj = 1.0; }
-        Ls[7 * j] = std::sqrt(dj);
-        for (int i = j + 1; i < 6; ++i) { double v = a[6 * i + j]; for (int k = 0; k < j; ++k) v -= Ls[6 * i + k] * Ls[6 * j + k]; Ls[6 * i + j] = v / Ls[7 * j]; }
+  const int32_t *prev = nullptr;  // the previous step's table entry
+  for (int s = s0; s <= s1; ++s) {
+    const int32_t *st = s < s1 ? w + w[kTH_OffSteps] + kTS_Words * s : nullptr;
+    if (st) CHECK(st[kTS_OffDiag] % 2 == 0 && st[kTS_OffLook] % 2 == 0 && st[kTS_OffPanel] % 2 == 0 && st[kTS_OffBwd] % 4 == 0 && st[kTS_OffPre] % 2 == 0, "tree program: item arrays misaligned");
+    ++c.T;  // interval A (after the last step: the drain of its panel items)
+    ++c.dg_stamp;
+    if (st)
+      for (int t = 0; t < st[kTS_Cols]; ++t) {
+        ++c.item;
+        const int32_t *pre = w + st[kTS_OffPre] + 2 * t;
+        for (int i = 0; i < pre[0]; ++i) tree_panel_item(c, w + pre[1] + kTreeItemWords * i);
+        c.dg_mode = 1;  // from here on (after the group's arrival at the named barrier) it runs beside the look-ahead items
+        const int32_t *it = w + st[kTS_OffDiag] + kTreeItemWords * t;
+        const int d = it[0] & 0xffff;
+        CHECK(((it[0] >> 16) & 15) == 6, "diagonal item rows");
+        tree_products(c, d, 6, it[1], it[1] + (int)((unsigned)it[0] >> 20));
+        // M = D^-1 from the LOWER triangle, written back as the full symmetric block; D must be positive definite
+        double a[36], Ls[36] = {0}, Li[36] = {0}, M[36];
+        for (int i = 0; i < 6; ++i) for (int k = 0; k <= i; ++k) a[6 * i + k] = c.rd(d + 6 * i + k);
+        for (int j = 0; j < 6; ++j) {  // reference route: Cholesky, triangular inverse, M = L^-T L^-1
+          double dj = a[7 * j];
+          for (int k = 0; k < j; ++k) dj -= Ls[6 * j + k] * Ls[6 * j + k];
+          if (!(dj > 0)) { *fail = true; dj = 1.0; }
+          Ls[7 * j] = std::sqrt(dj);
+          for (int i = j + 1; i < 6; ++i) { double v = a[6 * i + j]; for (int k = 0; k < j; ++k) v -= Ls[6 * i + k] * Ls[6 * j + k]; Ls[6 * i + j] = v / Ls[7 * j]; }
+        }
+        for (int j = 0; j < 6; ++j) {
+          Li[7 * j] = 1.0 / Ls[7 * j];
+          for (int i = j + 1; i < 6; ++i) { double v = 0; for (int k = j; k < i; ++k) v -= Ls[6 * i + k] * Li[6 * k + j]; Li[6 * i + j] = v / Ls[7 * i]; }
+        }
+        for (int i = 0; i < 6; ++i) for (int k = 0; k < 6; ++k) { double v = 0; for (int m = 0; m < 6; ++m) v += Li[6 * m + i] * Li[6 * m + k]; M[6 * i + k] = v; }
+        {  // the product's closed-form inverse (ssba_block_inverse.cuh) is what the device runs: use it, and compare
+          double Dm[36];
+          for (int i = 0; i < 6; ++i) for (int k = 0; k < 6; ++k) Dm[6 * i + k] = k <= i ? a[6 * i + k] : std::numeric_limits<double>::quiet_NaN();  // upper triangle must not be read
+          const bool bad = block_inverse6(Dm);
+          if (bad) *fail = true;
+          double scale = 0; for (int i = 0; i < 36; ++i) scale = std::max(scale, std::fabs(M[i]));
+          for (int i = 0; i < 36; ++i) CHECK(std::fabs(Dm[i] - M[i]) <= 1e-11 * scale, "closed-form inverse vs Cholesky route: %g vs %g", Dm[i], M[i]);
+          for (int i = 0; i < 36; ++i) M[i] = Dm[i];
+        }
+        for (int i = 0; i < 36; ++i) c.wrt(d + i, M[i]);
+        c.dg_mode = 0;
       }
-      for (int j = 0; j < 6; ++j) {
-        Li[7 * j] = 1.0 / Ls[7 * j];
-        for (int i = j + 1; i < 6; ++i) { double v = 0; for (int k = j; k < i; ++k) v -= Ls[6 * i + k] * Li[6 * k + j]; Li[6 * i + j] = v / Ls[7 * i]; }
+    if (prev)
+      for (int i = 0; i < 5 * prev[kTS_NPanel]; ++i) {
+        ++c.item;
+        tree_panel_item(c, w + prev[kTS_OffPanel] + kTreeItemWords * i);
       }
-      for (int i = 0; i < 6; ++i) for (int k = 0; k < 6; ++k) { double v = 0; for (int m = 0; m < 6; ++m) v += Li[6 * m + i] * Li[6 * m + k]; M[6 * i + k] = v; }
-      {  // the product's closed-form inverse (ssba_block_inverse.cuh) is what the device runs: use it, and compare
-        double Dm[36];
-        for (int i = 0; i < 6; ++i) for (int k = 0; k < 6; ++k) Dm[6 * i + k] = k <= i ? a[6 * i + k] : std::numeric_limits<double>::quiet_NaN();  // upper triangle must not be read
-        const bool bad = block_inverse6(Dm);
-        if (bad) *fail = true;
-        double scale = 0; for (int i = 0; i < 36; ++i) scale = std::max(scale, std::fabs(M[i]));
-        for (int i = 0; i < 36; ++i) CHECK(std::fabs(Dm[i] - M[i]) <= 1e-11 * scale, "closed-form inverse vs Cholesky route: %g vs %g", Dm[i], M[i]);
-        for (int i = 0; i < 36; ++i) M[i] = Dm[i];
-      }
-      for (int i = 0; i < 36; ++i) c.wrt(d + i, M[i]);
-    }
+    if (!st) break;
+    // interval B (after named barrier 1): look-ahead rounds; the diagonal items of interval A may still be running
+    ++c.T;
+    c.dg_mode = 2;
     for (int i = 0; i < 5 * st[kTS_NLook]; ++i) {
       ++c.item;
       const int32_t *it = w + st[kTS_OffLook] + kTreeItemWords * i;
       const int nrows = (it[0] >> 16) & 15;
       if (nrows > 0) tree_products(c, it[0] & 0xffff, nrows, it[1], it[1] + (int)((unsigned)it[0] >> 20));
     }
-    ++c.T;  // interval 2: panel rounds
-    for (int i = 0; i < 5 * st[kTS_NPanel]; ++i) {
-      ++c.item;
-      const int32_t *it = w + st[kTS_OffPanel] + kTreeItemWords * i;
-      const int dest = it[0] & 0xffff, nrows = (it[0] >> 16) & 15, dg = it[1] & 0xffff, xc = (int)((unsigned)it[1] >> 16);
-      CHECK(dg % 2 == 0 && xc % 2 == 0 && dest % 2 == 0, "panel item misaligned");
-      for (int r = 0; r < nrows; ++r) {
-        double x[6], y[6];
-        for (int m = 0; m < 6; ++m) x[m] = c.rd(dest + 6 * r + m);
-        for (int m = 0; m < 6; ++m) { double v = 0; for (int k = 0; k < 6; ++k) v += x[k] * c.rd(dg + 6 * m + k); y[m] = v; }
-        for (int m = 0; m < 6; ++m) c.wrt(dest + 6 * r + m, y[m]);       // Y = X M in place
-        if (nrows == 6) for (int m = 0; m < 6; ++m) c.wrt(xc + 6 * r + m, x[m]);  // the unscaled row for the next step's products
-      }
-    }
+    c.dg_mode = 0;
+    prev = st;
   }
 }
 static void tree_backward_steps(TreeCta &c, int s0, int s1) {
@@ -290,6 +318,7 @@ static std::vector<double> interpret_tree_program(const Structure &s, const std:
     const int np = tp.pool_doubles[c];
     CHECK(8 * (size_t)np + 4 * (size_t)(tp.prog_ptr[c + 1] - tp.prog_ptr[c]) + kTreeMiscBytes <= tp.smem_bytes, "tree program: CTA %d exceeds the launch size", c);
     t.pool.assign(np, nan); t.wr_t.assign(np, -1); t.wr_i.assign(np, -1); t.rd_t.assign(np, -1); t.rd_i.assign(np, -1);
+    t.dg_w.assign(np, -1); t.dg_r.assign(np, -1);
     for (int i = 0; i < 36 * tp.n_own_blocks[c]; ++i) t.pool[i] = L0[36 * (size_t)tp.b0[c] + i];
     for (int i = 0; i < 6 * tp.n_own_cols[c]; ++i) t.pool[36 * tp.n_own_blocks[c] + i] = b[6 * (size_t)tp.q0[c] + i];
     for (int i = 0; i < tp.contrib_doubles[c]; ++i) t.pool[tp.contrib_off[c] + i] = 0.0;
