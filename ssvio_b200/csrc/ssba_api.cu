@@ -702,6 +702,7 @@ ssba_status ssba_initialize(ssba_handle *h) {
     DYN(point[0], 3 * (size_t)g.n_points, double); DYN(point[1], 3 * (size_t)g.n_points, double);
     for (int k = 0; k < 2; ++k) { DYN(W[k], 18 * (size_t)s.n_pairs, double); DYN(Hll[k], 6 * (size_t)s.n_slots, double); DYN(bl[k], 3 * (size_t)s.n_slots, double); }
     DYN(Dinv, 6 * (size_t)s.n_slots, double);
+    DYN(pair_rec, (size_t)s.n_pairs, PairRec);  // packed on the device (k_pack_pairs)
     DYN(e_uv, 2 * (size_t)s.n_edges, double);  // filled on the device (k_gather_edge_values)
     if (g.has_info) DYN(e_info, 3 * (size_t)s.n_edges, double);
     if (g.has_delta) DYN(e_delta, (size_t)s.n_edges, double);
@@ -836,6 +837,7 @@ ssba_status ssba_initialize(ssba_handle *h) {
     if (h->use_p2p) CUDA_TRY(h, cudaMemsetAsync(h->xchg + sizeof(PeerHeader), 0, 2 * sizeof(double) * P.sys_doubles, h->stream));
   }
   P.n_units = s.n_units;
+  launch_pack_pairs(P, h->stream);
   launch_gather_edge_values(P, (const double *)h->d_raw, g.has_info ? (const double *)(h->d_raw + h->raw_off_info) : nullptr,
                             g.has_delta ? (const double *)(h->d_raw + h->raw_off_delta) : nullptr, h->stream);
   P.pdl = pdl_enabled(h) ? 1 : 0;

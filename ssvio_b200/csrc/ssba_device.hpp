@@ -71,6 +71,14 @@ struct TreeDev {
       n_own_cols[kTreeMaxCluster], contrib_off[kTreeMaxCluster], contrib_doubles[kTreeMaxCluster], xchg_off[kTreeMaxCluster];
 };
 
+// Everything the per-pair kernels need to know about a (pose, landmark) pair in ONE 32-byte record (two 16-byte
+// loads, coalesced over the threads of a chunk) instead of a chain through pair_vertex / pair_q / pair_slot ->
+// slot_vertex, slot_free / pair_edge_ptr.  Packed on the device from those arrays when a structure is uploaded.
+struct __align__(16) PairRec {
+  int32_t pose_row, q, slot, e0;          // q < 0: the pose is fixed; e0: first edge of the pair
+  int32_t n_edges, point_row, lfree, pad;  // lfree: the landmark is free
+};
+
 struct DeviceProblem {
   Cameras cams;
   double ext_R[8][9];  // rotation matrices of the extrinsics
@@ -88,6 +96,7 @@ struct DeviceProblem {
   const int32_t *slot_vertex, *slot_pair_ptr;
   const uint8_t *slot_free;
   const int32_t *pair_vertex, *pair_q, *pair_edge_ptr, *pair_slot, *lchunk_slot;
+  const PairRec *pair_rec;  // n_pairs, see PairRec
   const double *e_uv, *e_info, *e_delta;   // e_info / e_delta may be null
   const uint8_t *e_cam;
   const int32_t *e_orig;
@@ -177,6 +186,7 @@ void launch_final_chi2(const DeviceProblem &P, double threshold, cudaStream_t st
 void launch_edge_errors(const DeviceProblem &P, cudaStream_t st);      // -> err_out
 void launch_outlier_mask(const DeviceProblem &P, double threshold, cudaStream_t st);  // -> mask_out, chi_out[2] = #outliers
 void launch_gather_points(const DeviceProblem &P, cudaStream_t st);    // -> gather
+void launch_pack_pairs(const DeviceProblem &P, cudaStream_t st);       // pair_* / slot_* -> pair_rec
 // uv / information / Huber widths from the caller's edge order (raw_*) into the structure's order (P.e_*)
 void launch_gather_edge_values(const DeviceProblem &P, const double *raw_uv, const double *raw_info, const double *raw_delta, cudaStream_t st);
 int kernels_per_linearize();

@@ -137,14 +137,21 @@ __device__ __forceinline__ void linearize_edge(const DeviceProblem &P, int cam, 
 struct PairLin {
   double W[18], H[6], b[3], chi;
 };
+__device__ __forceinline__ PairRec load_pair_rec(const DeviceProblem &P, int a) {
+  const int4 *src = reinterpret_cast<const int4 *>(P.pair_rec + a);
+  const int4 x = src[0], y = src[1];
+  PairRec r;
+  r.pose_row = x.x; r.q = x.y; r.slot = x.z; r.e0 = x.w; r.n_edges = y.x; r.point_row = y.y; r.lfree = y.z; r.pad = 0;
+  return r;
+}
 
 // `hp` (27 doubles, the caller's own row of shared memory or a global partial) receives the pose
 // side: b_p[6], then the upper triangle of J_xi^T (rho' Omega) J_xi [21]
 template <int kMode>
-__device__ __forceinline__ void linearize_pair(const DeviceProblem &P, double *Wout, int a, bool lfree, const double *pose,
+__device__ __forceinline__ void linearize_pair(const DeviceProblem &P, double *Wout, int a, const PairRec &rec, const double *pose,
                                                const double *p, PairLin &o, double *hp) {
-  const int kv = P.pair_vertex[a];
-  const bool pfree = P.pair_q[a] >= 0;
+  const int kv = rec.pose_row;
+  const bool lfree = rec.lfree != 0, pfree = rec.q >= 0;
   const bool wpair = lfree && pfree;
   double T[7];
 #pragma unroll
@@ -157,8 +164,8 @@ __device__ __forceinline__ void linearize_pair(const DeviceProblem &P, double *W
   for (int i = 0; i < 6; ++i) o.H[i] = 0.0;
   o.b[0] = o.b[1] = o.b[2] = 0.0;
   o.chi = 0.0;
-  const int e1 = P.pair_edge_ptr[a + 1];
-  for (int e = P.pair_edge_ptr[a]; e < e1; ++e) {
+  const int e1 = rec.e0 + rec.n_edges;
+  for (int e = rec.e0; e < e1; ++e) {
     EdgeTerms t;
     double Jx[12], Jp[6];
     linearize_edge<kMode>(P, P.e_cam[e], T, p, P.e_uv[2 * e], P.e_uv[2 * e + 1], t, Jx, Jp);
@@ -224,10 +231,10 @@ __device__ __forceinline__ void linearize_pair(const DeviceProblem &P, double *W
 __device__ __forceinline__ void cross3(const double *a, double x, double y, double z, double &ox, double &oy, double &oz) {
   ox = a[1] * z - a[2] * y; oy = a[2] * x - a[0] * z; oz = a[0] * y - a[1] * x;
 }
-__device__ __forceinline__ void linearize_pair_factored(const DeviceProblem &P, double *Wout, int a, bool lfree, const double *pose,
+__device__ __forceinline__ void linearize_pair_factored(const DeviceProblem &P, double *Wout, int a, const PairRec &rec, const double *pose,
                                                         const double *p, PairLin &o, double *hp) {
-  const int kv = P.pair_vertex[a];
-  const bool pfree = P.pair_q[a] >= 0;
+  const int kv = rec.pose_row;
+  const bool lfree = rec.lfree != 0, pfree = rec.q >= 0;
   const bool wpair = lfree && pfree;
   double T[7];
 #pragma unroll
@@ -236,8 +243,8 @@ __device__ __forceinline__ void linearize_pair_factored(const DeviceProblem &P, 
   se3_act(T, p[0], p[1], p[2], b[0], b[1], b[2]);
   double M[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};  // M: xx xy xz yy yz zz
   o.chi = 0.0;
-  const int e1 = P.pair_edge_ptr[a + 1];
-  for (int e = P.pair_edge_ptr[a]; e < e1; ++e) {
+  const int e1 = rec.e0 + rec.n_edges;
+  for (int e = rec.e0; e < e1; ++e) {
     const int cam = P.e_cam[e];
     const double *K = P.cams.K, *Re = P.ext_R[cam];
     double cx, cy, cz;
@@ -367,12 +374,12 @@ __device__ __forceinline__ void linearize_chunk(const DeviceProblem &P, int lin,
     if (tid < P.lp_pair_ptr[lp1] - lpp0) sm.lp_pair[tid] = P.lp_pair[lpp0 + tid];
     if (tid < a1 - a0) {
       const int a = a0 + tid;
-      const int sl = P.pair_slot[a];
-      const int pv = P.slot_vertex[sl];
+      const PairRec rec = load_pair_rec(P, a);
+      const int pv = rec.point_row;
       const double p[3] = {point[3 * pv], point[3 * pv + 1], point[3 * pv + 2]};
       PairLin o;
-      if (kMode == SSBA_JACOBIAN_ANALYTIC) linearize_pair_factored(P, Wout, a, P.slot_free[sl] != 0, pose, p, o, sm.hp[tid]);
-      else linearize_pair<kMode>(P, Wout, a, P.slot_free[sl] != 0, pose, p, o, sm.hp[tid]);
+      if (kMode == SSBA_JACOBIAN_ANALYTIC) linearize_pair_factored(P, Wout, a, rec, pose, p, o, sm.hp[tid]);
+      else linearize_pair<kMode>(P, Wout, a, rec, pose, p, o, sm.hp[tid]);
       chi = o.chi;
 #pragma unroll
       for (int i = 0; i < 6; ++i) sm.part[tid][i] = o.H[i];
@@ -416,9 +423,10 @@ __device__ __forceinline__ void linearize_chunk(const DeviceProblem &P, int lin,
     for (int a = a0 + tid; a < a1; a += kLinThreads) {
       PairLin o;
       // free-pose pairs come first inside a landmark, so the rank of one is simply a - a0
-      double *hp_dst = P.pair_q[a] >= 0 ? hpp_part + 27 * (size_t)(lp0 + (a - a0)) : sm.hp[tid];
-      if (kMode == SSBA_JACOBIAN_ANALYTIC) linearize_pair_factored(P, Wout, a, lfree, pose, p, o, hp_dst);
-      else linearize_pair<kMode>(P, Wout, a, lfree, pose, p, o, hp_dst);
+      const PairRec rec = load_pair_rec(P, a);
+      double *hp_dst = rec.q >= 0 ? hpp_part + 27 * (size_t)(lp0 + (a - a0)) : sm.hp[tid];
+      if (kMode == SSBA_JACOBIAN_ANALYTIC) linearize_pair_factored(P, Wout, a, rec, pose, p, o, hp_dst);
+      else linearize_pair<kMode>(P, Wout, a, rec, pose, p, o, hp_dst);
       chi += o.chi;
 #pragma unroll
       for (int i = 0; i < 6; ++i) acc[i] += o.H[i];
@@ -1398,9 +1406,8 @@ __device__ __forceinline__ double pair_trial_chi(const DeviceProblem &P, int a, 
   return chi;
 }
 
-__device__ __forceinline__ void pair_wtx(const DeviceProblem &P, const double *__restrict__ Wl, int a, double *c3) {
+__device__ __forceinline__ void pair_wtx(const DeviceProblem &P, const double *__restrict__ Wl, int a, int q, double *c3) {
   c3[0] = c3[1] = c3[2] = 0.0;
-  const int q = P.pair_q[a];
   if (q < 0) return;
   const double2 *src = reinterpret_cast<const double2 *>(Wl + 18 * (size_t)a);
   double Wv[18];
@@ -1434,15 +1441,15 @@ __global__ void __launch_bounds__(kLinThreads, kFusedLin ? SSBA_LIN_MINB : 4) k_
   const int s0 = P.lchunk_slot[blockIdx.x], s1 = P.lchunk_slot[blockIdx.x + 1];
   const int a0 = P.slot_pair_ptr[s0], a1 = P.slot_pair_ptr[s1];
   const int tid = threadIdx.x;
+  PairRec my = {0, -1, 0, 0, 0, 0, 0, 0};  // this thread's pair (chunks of <= 128 pairs), in registers before the wait
   {
     const int a = a0 + tid;
-    if (a < a1) {
-      prefetch_l1(P.pair_q + a); prefetch_l1(P.pair_vertex + a); prefetch_l1(P.pair_edge_ptr + a);
-      const int sl = P.pair_slot[a], e0 = P.pair_edge_ptr[a];
-      prefetch_l1(P.slot_free + sl); prefetch_l1(P.slot_vertex + sl);
-      prefetch_l1(P.e_uv + 2 * (size_t)e0); prefetch_l1(P.e_cam + e0);
+    if (a < a1 && a1 - a0 <= kLinThreads) {
+      my = load_pair_rec(P, a);
+      prefetch_l1(P.e_uv + 2 * (size_t)my.e0); prefetch_l1(P.e_cam + my.e0);
+      prefetch_l1(P.pair_rec + a);  // linearize_chunk loads it again
     }
-    if (s0 + tid < s1) prefetch_l1(P.slot_pair_ptr + s0 + tid);
+    if (s0 + tid < s1) { prefetch_l1(P.slot_pair_ptr + s0 + tid); prefetch_l1(P.slot_vertex + s0 + tid); prefetch_l1(P.slot_free + s0 + tid); }
     if (tid == 0) { prefetch_l1(P.lchunk_lp_ptr + blockIdx.x); }
   }
   griddep_wait();
@@ -1472,12 +1479,12 @@ __global__ void __launch_bounds__(kLinThreads, kFusedLin ? SSBA_LIN_MINB : 4) k_
   // ---- W^T x_p per pair
   double c3[3] = {0.0, 0.0, 0.0};
   if (small) {
-    if (tid < a1 - a0 && P.slot_free[P.pair_slot[a0 + tid]]) pair_wtx(P, Wl, a0 + tid, c3);
+    if (tid < a1 - a0 && my.lfree) pair_wtx(P, Wl, a0 + tid, my.q, c3);
     s_part[tid][0] = c3[0]; s_part[tid][1] = c3[1]; s_part[tid][2] = c3[2];
   } else if (P.slot_free[s0]) {
     for (int a = a0 + tid; a < a1; a += kLinThreads) {
       double t3[3];
-      pair_wtx(P, Wl, a, t3);
+      pair_wtx(P, Wl, a, P.pair_q[a], t3);
       c3[0] += t3[0]; c3[1] += t3[1]; c3[2] += t3[2];
     }
 #pragma unroll
@@ -1725,6 +1732,16 @@ __global__ void __launch_bounds__(256) k_gather_edge_values(const DeviceProblem 
   reinterpret_cast<double2 *>(e_uv)[i] = reinterpret_cast<const double2 *>(raw_uv)[o];
   if (e_info) { e_info[3 * (size_t)i] = raw_info[3 * o]; e_info[3 * (size_t)i + 1] = raw_info[3 * o + 1]; e_info[3 * (size_t)i + 2] = raw_info[3 * o + 2]; }
   if (e_delta) e_delta[i] = raw_delta[o];
+}
+
+__global__ void __launch_bounds__(256) k_pack_pairs(const DeviceProblem P, PairRec *out) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= P.n_pairs) return;
+  const int sl = P.pair_slot[a], e0 = P.pair_edge_ptr[a];
+  PairRec r;
+  r.pose_row = P.pair_vertex[a]; r.q = P.pair_q[a]; r.slot = sl; r.e0 = e0;
+  r.n_edges = P.pair_edge_ptr[a + 1] - e0; r.point_row = P.slot_vertex[sl]; r.lfree = P.slot_free[sl] ? 1 : 0; r.pad = 0;
+  out[a] = r;
 }
 
 __global__ void k_gather_points(const DeviceProblem P) {
@@ -2054,6 +2071,10 @@ void launch_gather_edge_values(const DeviceProblem &P, const double *raw_uv, con
   if (P.n_edges <= 0) return;
   k_gather_edge_values<<<div_up(P.n_edges, 256), 256, 0, st>>>(P, raw_uv, raw_info, raw_delta, const_cast<double *>(P.e_uv),
                                                                  const_cast<double *>(P.e_info), const_cast<double *>(P.e_delta));
+}
+
+void launch_pack_pairs(const DeviceProblem &P, cudaStream_t st) {
+  if (P.n_pairs > 0) k_pack_pairs<<<div_up(P.n_pairs, 256), 256, 0, st>>>(P, const_cast<PairRec *>(P.pair_rec));
 }
 
 void launch_gather_points(const DeviceProblem &P, cudaStream_t st) {
