@@ -94,6 +94,8 @@ unsigned pose_stage_bytes(int n_poses) {
 }
 namespace {
 
+__device__ __forceinline__ long long gtime_early() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
 struct EdgeTerms {
   double e0, e1;      // error
   double we0, we1;    // Omega e
@@ -932,9 +934,12 @@ __device__ __forceinline__ void dsmem_st_int(unsigned ra, int v) {
 __device__ long long g_solver_trace[4096];
 #define TRACE(i) do { if (threadIdx.x == 0 && blockIdx.x == 0 && (i) < 4096) g_solver_trace[(i)] = clock64(); } while (0)
 #define TRACE2(sgv, k) do { if (lane == 0 && ((sgv) == 6 || (sgv) == 18) && rd < 16) g_solver_trace[3000 + ((sgv) == 18 ? 512 : 0) + 16 * rd + (k)] = clock64(); } while (0)
+// k_update: phase stamps (globaltimer, ns) of CTAs 0, 300 and 700 at entries 3800 + 16 * {0, 1, 2}
+#define UTRACE(k) do { if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 300 || blockIdx.x == 700)) g_solver_trace[3800 + 16 * (blockIdx.x == 0 ? 0 : blockIdx.x == 300 ? 1 : 2) + (k)] = gtime_early(); } while (0)
 #else
 #define TRACE(i) do { } while (0)
 #define TRACE2(sgv, k) do { } while (0)
+#define UTRACE(k) do { } while (0)
 #endif
 
 template <int kCluster>
@@ -1441,6 +1446,7 @@ __global__ void __launch_bounds__(kLinThreads, kFusedLin ? SSBA_LIN_MINB : 4) k_
   const int s0 = P.lchunk_slot[blockIdx.x], s1 = P.lchunk_slot[blockIdx.x + 1];
   const int a0 = P.slot_pair_ptr[s0], a1 = P.slot_pair_ptr[s1];
   const int tid = threadIdx.x;
+  UTRACE(0);
   PairRec my = {0, -1, 0, 0, 0, 0, 0, 0};  // this thread's pair (chunks of <= 128 pairs), in registers before the wait
   {
     const int a = a0 + tid;
@@ -1452,8 +1458,10 @@ __global__ void __launch_bounds__(kLinThreads, kFusedLin ? SSBA_LIN_MINB : 4) k_
     if (s0 + tid < s1) { prefetch_l1(P.slot_pair_ptr + s0 + tid); prefetch_l1(P.slot_vertex + s0 + tid); prefetch_l1(P.slot_free + s0 + tid); }
     if (tid == 0) { prefetch_l1(P.lchunk_lp_ptr + blockIdx.x); }
   }
+  UTRACE(1);
   griddep_wait();
   griddep_launch();
+  UTRACE(2);
   if (ctl->done) return;
   __shared__ __align__(8) unsigned long long s_bar;
   extern __shared__ __align__(16) double s_pose[];
@@ -1491,6 +1499,7 @@ __global__ void __launch_bounds__(kLinThreads, kFusedLin ? SSBA_LIN_MINB : 4) k_
     for (int i = 0; i < 3; ++i) { const double v = block_sum<kLinThreads>(c3[i], red); if (tid == 0) s_part[0][i] = v; }
   }
   __syncthreads();
+  UTRACE(3);
   // ---- the landmark's first thread: x_l, scale, new position
   {
     const int sl = s0 + tid;
@@ -1520,6 +1529,7 @@ __global__ void __launch_bounds__(kLinThreads, kFusedLin ? SSBA_LIN_MINB : 4) k_
     }
   }
   __syncthreads();  // the trial positions of this chunk's landmarks are in place (global memory, written by this CTA)
+  UTRACE(4);
   // ---- trial residuals per pair (and, fused, the whole linearisation of the trial state)
   if (kFusedLin) {
     double mx;
@@ -1534,9 +1544,11 @@ __global__ void __launch_bounds__(kLinThreads, kFusedLin ? SSBA_LIN_MINB : 4) k_
   } else {
     for (int a = a0 + tid; a < a1; a += kLinThreads) chi += pair_trial_chi(P, a, pose_new, s_pnew[0]);
   }
+  UTRACE(5);
   const double s_ = block_sum<kLinThreads>(chi, red);
   const double sc = block_sum<kLinThreads>(scale, red);
   if (tid == 0) { P.chi_new_part[blockIdx.x] = s_; P.scale_part[blockIdx.x] = sc; }
+  UTRACE(6);
   if (kFusedControl) {
     if (tid == 0) {
       __threadfence();
