@@ -79,30 +79,65 @@ class OptimizationAlgorithmLevenbergCudaT : public g2o::OptimizationAlgorithm {
     }
     const auto &av = _optimizer->activeVertices();  // sorted by id (sparse_optimizer.cpp:493-498)
     const auto &ae = _optimizer->activeEdges();     // internalId = addEdge order
-    poses_.clear(); points_.clear(); edges_.clear();
-    pose_qt_.clear(); xyz_.clear(); pose_fixed_.clear(); point_fixed_.clear();
-    poses_.reserve(av.size()); points_.reserve(av.size());
-    for (auto *v : av) {
-      VertexPoseT *vp = typeid(*v) == typeid(VertexPoseT) ? static_cast<VertexPoseT *>(v) : dynamic_cast<VertexPoseT *>(v);
-      if (vp) {
-        vp->setColInHessian((int)poses_.size());
-        poses_.push_back(vp);
-        const auto &T = vp->estimate();
-        const auto &q = T.unit_quaternion();
-        const double qt[7] = {q.x(), q.y(), q.z(), q.w(), T.translation()[0], T.translation()[1], T.translation()[2]};
-        pose_qt_.insert(pose_qt_.end(), qt, qt + 7);
-        pose_fixed_.push_back(vp->fixed());
-        continue;
+    edges_.clear();
+    {
+      // The vertices are 2e4 heap objects: two passes over a few threads - (1) the kind of every vertex and the
+      // number of poses / landmarks per chunk, (2) with the chunk offsets known, rows (colInHessian), pointers,
+      // estimates and fixed flags.  Rows follow the order of activeVertices() (by id), like g2o's own index mapping.
+      const size_t nv = av.size();
+      const int ntv = thread_count(4 * nv);
+      kind_.resize(nv);
+      std::vector<size_t> n_pose(ntv + 1, 0), n_point(ntv + 1, 0);
+      std::vector<int> vbad(ntv, 0);
+      parallel_chunks(nv, ntv, [&](int t, size_t i0, size_t i1) {
+        size_t np = 0, nl = 0;
+        for (size_t i = i0; i < i1; ++i) {
+          if (i + 8 < i1) __builtin_prefetch(av[i + 8]);
+          auto *v = av[i];
+          const std::type_info &ti = typeid(*v);  // exact types first: a failing dynamic_cast walks the hierarchy
+          if (ti == typeid(VertexXYZT)) { kind_[i] = 1; ++nl; }
+          else if (ti == typeid(VertexPoseT)) { kind_[i] = 0; ++np; }
+          else if (dynamic_cast<VertexPoseT *>(v)) { kind_[i] = 0; ++np; }
+          else if (dynamic_cast<VertexXYZT *>(v)) { kind_[i] = 1; ++nl; }
+          else { vbad[t] = 1; return; }
+        }
+        n_pose[t + 1] = np; n_point[t + 1] = nl;
+      });
+      for (int t = 0; t < ntv; ++t) {
+        if (vbad[t]) { std::cerr << "ssba: unsupported vertex type in the active graph" << std::endl; return false; }
+        n_pose[t + 1] += n_pose[t]; n_point[t + 1] += n_point[t];
       }
-      VertexXYZT *vl = typeid(*v) == typeid(VertexXYZT) ? static_cast<VertexXYZT *>(v) : dynamic_cast<VertexXYZT *>(v);
-      if (!vl) { std::cerr << "ssba: unsupported vertex type in the active graph" << std::endl; return false; }
-      vl->setColInHessian((int)points_.size());
-      points_.push_back(vl);
-      const auto &p = vl->estimate();
-      const double x3[3] = {p[0], p[1], p[2]};
-      xyz_.insert(xyz_.end(), x3, x3 + 3);
-      point_fixed_.push_back(vl->fixed());
+      const size_t NPose = n_pose[ntv], NPoint = n_point[ntv];
+      poses_.resize(NPose); points_.resize(NPoint);
+      pose_qt_.resize(7 * NPose); xyz_.resize(3 * NPoint); pose_fixed_.resize(NPose); point_fixed_.resize(NPoint);
+      parallel_chunks(nv, ntv, [&](int t, size_t i0, size_t i1) {
+        size_t ip = n_pose[t], il = n_point[t];
+        for (size_t i = i0; i < i1; ++i) {
+          if (i + 8 < i1) { const char *nx = reinterpret_cast<const char *>(av[i + 8]); __builtin_prefetch(nx); __builtin_prefetch(nx + 64); __builtin_prefetch(nx + 128); }
+          if (kind_[i] == 0) {
+            VertexPoseT *vp = static_cast<VertexPoseT *>(av[i]);
+            vp->setColInHessian((int)ip);
+            poses_[ip] = vp;
+            const auto &T = vp->estimate();
+            const auto &q = T.unit_quaternion();
+            double *qt = &pose_qt_[7 * ip];
+            qt[0] = q.x(); qt[1] = q.y(); qt[2] = q.z(); qt[3] = q.w();
+            qt[4] = T.translation()[0]; qt[5] = T.translation()[1]; qt[6] = T.translation()[2];
+            pose_fixed_[ip] = vp->fixed();
+            ++ip;
+          } else {
+            VertexXYZT *vl = static_cast<VertexXYZT *>(av[i]);
+            vl->setColInHessian((int)il);
+            points_[il] = vl;
+            const auto &p = vl->estimate();
+            xyz_[3 * il] = p[0]; xyz_[3 * il + 1] = p[1]; xyz_[3 * il + 2] = p[2];
+            point_fixed_[il] = vl->fixed();
+            ++il;
+          }
+        }
+      });
     }
+    const auto t_init_v = std::chrono::steady_clock::now();
     const size_t ne = ae.size();
     if (ne == 0) return false;
     pidx_.resize(ne); lidx_.resize(ne); cam_.resize(ne); uv_.resize(2 * ne); info_.resize(3 * ne); delta_.resize(ne);
@@ -120,6 +155,14 @@ class OptimizationAlgorithmLevenbergCudaT : public g2o::OptimizationAlgorithm {
     parallel_chunks(ne, nt, [&](int t, size_t i0, size_t i1) {
       std::vector<double> &ext = ext_local[t];
       for (size_t i = i0; i < i1; ++i) {
+        // the walk is bound by cache misses (an edge object spans ~10 lines, its vertex array and robust kernel are
+        // separate allocations): fetch the object 16 edges ahead, and what it points to 8 edges ahead
+        if (i + 16 < i1) prefetch_edge(ae[i + 16]);
+        if (i + 8 < i1) {
+          const g2o::OptimizableGraph::Edge *e8 = ae[i + 8];
+          __builtin_prefetch(e8->vertices().data());
+          if (const auto *rk = e8->robustKernel()) { __builtin_prefetch(rk); __builtin_prefetch(reinterpret_cast<const char *>(rk) + sizeof(g2o::RobustKernelHuber) - 8); }
+        }
         auto *e = ae[i];
         EdgeProjectionT *ep = typeid(*e) == typeid(EdgeProjectionT) ? static_cast<EdgeProjectionT *>(e) : dynamic_cast<EdgeProjectionT *>(e);
         if (!ep) { bad[t] = 1; return; }
@@ -183,8 +226,8 @@ class OptimizationAlgorithmLevenbergCudaT : public g2o::OptimizationAlgorithm {
     if (!ok) std::cerr << "ssba: " << ssba_last_error(h_) << std::endl;
     if (timing()) {
       const auto t_init2 = std::chrono::steady_clock::now();
-      std::fprintf(stderr, "[ssba shim] init: flatten %.3f ms, set_* + initialize %.3f ms\n", std::chrono::duration<double, std::milli>(t_init1 - t_init0).count(),
-                   std::chrono::duration<double, std::milli>(t_init2 - t_init1).count());
+      std::fprintf(stderr, "[ssba shim] init: flatten %.3f ms (vertices %.3f), set_* + initialize %.3f ms\n", std::chrono::duration<double, std::milli>(t_init1 - t_init0).count(),
+                   std::chrono::duration<double, std::milli>(t_init_v - t_init0).count(), std::chrono::duration<double, std::milli>(t_init2 - t_init1).count());
     }
     return ok;
   }
@@ -222,6 +265,7 @@ class OptimizationAlgorithmLevenbergCudaT : public g2o::OptimizationAlgorithm {
     }
     parallel_chunks(edges_.size(), thread_count(edges_.size()), [&](int, size_t e0, size_t e1) {
       for (size_t e = e0; e < e1; ++e) {
+        if (e + 12 < e1) __builtin_prefetch(&edges_[e + 12]->error(), 1);
         edges_[e]->error()[0] = err[2 * e];
         edges_[e]->error()[1] = err[2 * e + 1];
       }
@@ -252,6 +296,15 @@ class OptimizationAlgorithmLevenbergCudaT : public g2o::OptimizationAlgorithm {
     int nt = cfg > 0 ? cfg : (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
     if (n < 20000) nt = 1;
     return nt;
+  }
+  // the lines of an edge object init() reads: vptr / vertex container / robust kernel pointer at the front,
+  // measurement + information behind the OptimizableGraph::Edge part, K / extrinsics at the end (addresses only)
+  static void prefetch_edge(const g2o::OptimizableGraph::Edge *e) {
+    const char *p = reinterpret_cast<const char *>(e);
+    __builtin_prefetch(p); __builtin_prefetch(p + 64); __builtin_prefetch(p + 128); __builtin_prefetch(p + 192);
+    const EdgeProjectionT *ep = static_cast<const EdgeProjectionT *>(e);  // never dereferenced here
+    const char *x = reinterpret_cast<const char *>(&EdgeAccess::ext(ep));
+    __builtin_prefetch(x); __builtin_prefetch(x + 56);
   }
   template <class F> static void parallel_chunks(size_t n, int nt, F &&fn) {
     if (nt <= 1) { fn(0, (size_t)0, n); return; }
@@ -288,7 +341,7 @@ class OptimizationAlgorithmLevenbergCudaT : public g2o::OptimizationAlgorithm {
   std::vector<EdgeProjectionT *> edges_;
   // flat arrays handed to libssba (kept between calls: no allocation per round)
   std::vector<double> pose_qt_, xyz_, uv_, info_, delta_, ext_qt_, wb_qt_, wb_xyz_, wb_err_;
-  std::vector<uint8_t> pose_fixed_, point_fixed_, cam_;
+  std::vector<uint8_t> pose_fixed_, point_fixed_, cam_, kind_;
   std::vector<int32_t> pidx_, lidx_;
 };
 
