@@ -758,27 +758,34 @@ __global__ void __launch_bounds__(32 * kSchurWarps, 3) k_schur(const DeviceProbl
 // k_schur_reduce - the deterministic accumulation of the reduced system: one CTA per factor block adds the totals
 // the units of k_schur stored for it (contiguous in the staging buffer, in unit order: a list the host made) on top
 // of Hpp + lambda I for a diagonal block (block_solver.hpp:334-335, 524-539); bschur = b_p - sum of the units'
-// vectors (:397); blocks of the fill-in that no landmark touches become zero.  The four warps take a quarter of
+// vectors (:397); blocks of the fill-in that no landmark touches become zero.  The eight warps take an eighth of
 // the producers each (a diagonal block of a window has a hundred of them: every run of landmarks the pose sees)
-// and the four partial sums are combined as (w0 + w1) + (w2 + w3): a fixed order, no fp64 atomics anywhere, so
-// two runs give the same bits.
-__global__ void __launch_bounds__(128) k_schur_reduce(const DeviceProblem P) {
+// and the partial sums are combined as ((w0 + w1) + (w2 + w3)) + ((w4 + w5) + (w6 + w7)): a fixed order, no fp64
+// atomics anywhere, so two runs give the same bits.
+constexpr int kRedWarps = 8;
+__global__ void __launch_bounds__(32 * kRedWarps) k_schur_reduce(const DeviceProblem P) {
   const Control *ctl = P.ctl;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x;
-  __shared__ double2 s_part[4][24];  // per warp: 18 pieces of the block, 3 of the vector
+  __shared__ double2 s_part[kRedWarps][24];  // per warp: 18 pieces of the block, 3 of the vector
   const int row = P.blk_row[b], col = P.blk_col[b], p0 = P.blk_prod_ptr[b], p1 = P.blk_prod_ptr[b + 1];
   griddep_wait();
   griddep_launch();
   if (ctl->done) return;
   const bool diag = row == col;
   // this warp's quarter of the producers; lanes 0..17 own one 16-byte piece of the block, lanes 24..26 of the vector
-  const int per = (p1 - p0 + 3) / 4;
+  const int per = (p1 - p0 + kRedWarps - 1) / kRedWarps;
   const int q0 = min(p1, p0 + warp * per), q1 = min(p1, q0 + per);
   double2 acc = make_double2(0.0, 0.0);
   if (lane < 18) {
     const double2 *src = reinterpret_cast<const double2 *>(P.stage) + 18 * (size_t)q0 + lane;
-    for (int p = q0; p < q1; ++p, src += 18) { const double2 v = __ldcg(src); acc.x += v.x; acc.y += v.y; }
+    // four loads in flight, added in producer order (the sum keeps its fixed order)
+    int p = q0;
+    for (; p + 4 <= q1; p += 4, src += 72) {
+      const double2 v0 = __ldcg(src), v1 = __ldcg(src + 18), v2 = __ldcg(src + 36), v3 = __ldcg(src + 54);
+      acc.x += v0.x; acc.y += v0.y; acc.x += v1.x; acc.y += v1.y; acc.x += v2.x; acc.y += v2.y; acc.x += v3.x; acc.y += v3.y;
+    }
+    for (; p < q1; ++p, src += 18) { const double2 v = __ldcg(src); acc.x += v.x; acc.y += v.y; }
   } else if (diag && lane >= 24 && lane < 27) {
     const double2 *src = reinterpret_cast<const double2 *>(P.stage_b) + 3 * (size_t)q0 + (lane - 24);
     for (int p = q0; p < q1; ++p, src += 3) { const double2 v = __ldcg(src); acc.x += v.x; acc.y += v.y; }
@@ -798,16 +805,19 @@ __global__ void __launch_bounds__(128) k_schur_reduce(const DeviceProblem P) {
       base.y = P.hpp_fold[27 * col + tri(e1)] + ((e1 / 6 == e1 % 6) ? lambda : 0.0);
     }
     const double2 a0 = s_part[0][lane], a1 = s_part[1][lane], a2 = s_part[2][lane], a3 = s_part[3][lane];
+    const double2 a4 = s_part[4][lane], a5 = s_part[5][lane], a6 = s_part[6][lane], a7 = s_part[7][lane];
     double2 out;
-    out.x = base.x + ((a0.x + a1.x) + (a2.x + a3.x));
-    out.y = base.y + ((a0.y + a1.y) + (a2.y + a3.y));
+    out.x = base.x + (((a0.x + a1.x) + (a2.x + a3.x)) + ((a4.x + a5.x) + (a6.x + a7.x)));
+    out.y = base.y + (((a0.y + a1.y) + (a2.y + a3.y)) + ((a4.y + a5.y) + (a6.y + a7.y)));
     reinterpret_cast<double2 *>(sysacc + 36 * (size_t)b)[lane] = out;
   } else if (diag && lane >= 24 && lane < 27) {
     const int k = lane - 24;
     const double2 bp = make_double2(P.hpp_fold[27 * col + 2 * k], P.hpp_fold[27 * col + 2 * k + 1]);
     const double2 a0 = s_part[0][18 + k], a1 = s_part[1][18 + k], a2 = s_part[2][18 + k], a3 = s_part[3][18 + k];
+    const double2 a4 = s_part[4][18 + k], a5 = s_part[5][18 + k], a6 = s_part[6][18 + k], a7 = s_part[7][18 + k];
     double2 *bsch = reinterpret_cast<double2 *>(sysacc + 36 * (size_t)P.n_blocks + 6 * (size_t)col);
-    bsch[k] = make_double2(bp.x + ((a0.x + a1.x) + (a2.x + a3.x)), bp.y + ((a0.y + a1.y) + (a2.y + a3.y)));  // bschur
+    bsch[k] = make_double2(bp.x + (((a0.x + a1.x) + (a2.x + a3.x)) + ((a4.x + a5.x) + (a6.x + a7.x))),
+                           bp.y + (((a0.y + a1.y) + (a2.y + a3.y)) + ((a4.y + a5.y) + (a6.y + a7.y))));  // bschur
     bsch[3 * (size_t)P.n_fp + k] = bp;                                                                         // b_p (kept for computeScale)
   }
 }
@@ -1985,7 +1995,7 @@ void launch_schur(const DeviceProblem &P, bool prefolded, cudaStream_t st) {
   once_per_device(seen, [] { cudaFuncSetAttribute(k_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDyn); });
   const int n_pose = div_up(P.n_fp, kSchurWarps), n_unit = div_up(P.n_units, kSchurWarps);
   if (n_pose + n_unit > 0) launch_maybe_pdl(k_schur, dim3(n_pose + n_unit), dim3(32 * kSchurWarps), kDyn, st, P.pdl != 0, P, n_pose, prefolded ? 1 : 0);
-  if (P.deterministic && P.n_blocks > 0) launch_maybe_pdl(k_schur_reduce, dim3(P.n_blocks), dim3(128), 0, st, P.pdl != 0, P);
+  if (P.deterministic && P.n_blocks > 0) launch_maybe_pdl(k_schur_reduce, dim3(P.n_blocks), dim3(32 * kRedWarps), 0, st, P.pdl != 0, P);
 }
 
 // The largest cluster (8, 4, 2 or 1 CTAs of kSolveThreads threads with the full dynamic shared memory)

@@ -1188,6 +1188,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     if (s.n_slots > 0) s.lchunk_slot.push_back(s.n_slots);
     s.n_lchunks = (int)s.lchunk_slot.size() - 1;
   }
+  tm.mark("  chunks");
 
   // ---- Schur work units: a run of <= kSchurRun consecutive free landmarks with the same W pose list
   // x a chunk of <= 32 of its k(k+1)/2 block pairs (one lane per block pair, one warp per unit)
@@ -1214,6 +1215,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
       sl = e;
     }
     s.n_units = (int)s.unit_slot.size();
+    tm.mark("  unit runs");
     // Schur targets of every unit: for its block pairs a <= b (poses of the run sorted by q):
     // block (row q_b, col q_a) of the factor pattern
     s.unit_combo_ptr.assign(s.n_units + 1, 0);
@@ -1239,6 +1241,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
       }
     });
     for (int t = 0; t < T; ++t) if (t_bad[t]) { err = "internal: Schur block missing from the factor pattern"; return false; }
+    tm.mark("  combos");
     // producers of every factor block: a stable counting sort of the combos by block
     const int ncomb = (int)s.combo_blk.size();
     s.blk_prod_ptr.assign(s.n_blocks + 1, 0);
