@@ -450,7 +450,9 @@ def run_ssba(args):
             roofline = {"kernel": name, "bound": "hbm", "achieved": dom["achieved"], "peak": peak, "unit": "GB/s",
                         "frac": dom["frac"], "traffic": dom["traffic"], "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"], "avg_launch_ms": dom["avg_launch_ms"],
-                        "note": "the reduced solve is bound by its chain of dependent 6x6 pivot blocks (latency), not by bytes: see DESIGN.md",
+                        "note": ("the reduced solve is bound by its chain of dependent 6x6 pivot blocks (latency), not by bytes: see DESIGN.md"
+                                 if name == "reduced_solve" else
+                                 "per-pair fp64 chains and L2 round trips at 12 warps per SM (latency), not bytes: see DESIGN.md"),
                         "phase_ms_per_step": {k: v[0] / args.steps for k, v in phases.items()}}
         golden = golden_chi2(args.workload)
         numerics = {"chi2_robust_final": chi2_final, "lm_iterations_done": its_done,

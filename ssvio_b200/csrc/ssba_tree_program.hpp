@@ -37,7 +37,7 @@
 
 namespace ssba {
 
-constexpr int kTreeThreads = 512;
+constexpr int kTreeThreads = 384;
 constexpr int kTreeWarps = kTreeThreads / 32;
 constexpr int kTreeMaxCluster = 16;  // 8 is the portable cluster size, 16 needs cudaFuncAttributeNonPortableClusterSizeAllowed
 constexpr size_t kTreeMaxSmem = 227 * 1024;       // opt-in dynamic shared memory per CTA on sm_100

@@ -227,19 +227,20 @@ __global__ void __launch_bounds__(kTreeThreads, 1) k_tree_solve(const DeviceProb
           if (cta == 0) {
             const int n_rounds = prog[kTH_AddRounds];
             const int *tab = prog + prog[kTH_OffAddRounds];
-            const int grp = tid / 18, sub = tid - 18 * grp;  // 28 groups of 18 lanes: one 16-byte piece of a block each
+            constexpr int kAddGroups = kTreeThreads / 18;  // groups of 18 lanes: one 16-byte piece of a block each
+            const int grp = tid / 18, sub = tid - 18 * grp;
             const double2 *x2 = reinterpret_cast<const double2 *>(T.xchg);
             for (int rd = 0; rd < n_rounds; ++rd) {
               const int nops = tab[2 * rd];
               const int *ops = prog + tab[2 * rd + 1];
-              for (int base = 0; base < nops; base += 28 * 4) {
+              for (int base = 0; base < nops; base += kAddGroups * 4) {
                 double2 v[4];
                 int dst[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                  const int op = base + 28 * u + grp;
+                  const int op = base + kAddGroups * u + grp;
                   dst[u] = -1;
-                  if (grp < 28 && op < nops) {
+                  if (grp < kAddGroups && op < nops) {
                     const unsigned wd = (unsigned)ops[op];
                     if (sub < ((wd >> 31) ? 3 : 18)) {
                       dst[u] = (int)(wd & 0xffffu) + 2 * sub;
@@ -311,7 +312,9 @@ __global__ void __launch_bounds__(kTreeThreads, 1) k_tree_solve(const DeviceProb
         __syncwarp();
         TS_TRACE_W(s, 1);
         // (measured, not kept: arriving only after the critical products, so that the look-ahead warps' loads do not
-        // queue in front of the diagonal blocks' operands: 56.0 -> 59.9 us per solve - the look-ahead is on the path too)
+        // queue in front of the diagonal blocks' operands: 56.0 -> 59.9 us per solve - the look-ahead is on the path too;
+        // requesting the first critical pair's operands (21 x 16 bytes per lane) before the arrive: 68 us - the kernel
+        // sits at its 128-register cap and the 42 extra live doubles spill)
         if (!all_diag) asm volatile("bar.arrive 1, %0;" ::"n"(kTreeThreads) : "memory");
       }
       if (w0 >= 0 && g < 5) {
