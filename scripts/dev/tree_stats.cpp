@@ -59,11 +59,11 @@ int main(int argc, char **argv) {
     for (int st = 0; st < nsa + nsb; ++st) {
       const int32_t *e = steps + kTS_Words * st;
       int maxcrit = 0, sumcrit = 0;
-      for (int t = 0; t < e[kTS_Cols]; ++t) { const int np = (int)((unsigned)w[e[kTS_OffDiag] + 2 * t] >> 20); maxcrit = std::max(maxcrit, np); sumcrit += np; }
+      for (int t = 0; t < (e[kTS_Cols] & 0xffff); ++t) { const int np = (int)((unsigned)w[e[kTS_OffDiag] + 2 * t] >> 20); maxcrit = std::max(maxcrit, np); sumcrit += np; }
       long long lookp = 0; int maxlook = 0;
       for (int i = 0; i < 5 * e[kTS_NLook]; ++i) { const unsigned x = (unsigned)w[e[kTS_OffLook] + 2 * i]; const int np = x >> 20, nr = (x >> 16) & 15; lookp += (long long)np * nr; maxlook = std::max(maxlook, np); }
       tot_look += lookp; tot_crit += sumcrit;
-      if (c == 0 || c == 1) std::printf("   step %2d%s: cols %2d crit pairs max %2d sum %3d | look rounds %3d (row-products %5lld, longest %2d) | panel rounds %3d\n", st, st >= nsa ? "T" : " ", e[kTS_Cols], maxcrit, sumcrit, e[kTS_NLook], lookp, maxlook, e[kTS_NPanel]);
+      if (c == 0 || c == 1) std::printf("   step %2d%s: cols %2d crit pairs max %2d sum %3d | look rounds %3d (row-products %5lld, longest %2d) | panel rounds %3d\n", st, st >= nsa ? "T" : " ", (e[kTS_Cols] & 0xffff), maxcrit, sumcrit, e[kTS_NLook], lookp, maxlook, e[kTS_NPanel]);
     }
     std::printf("   total: critical block products %lld, look-ahead row products %lld (= %lld block products)\n", tot_crit, tot_look, tot_look / 6);
   }

@@ -140,7 +140,7 @@ size_t tree_smem_estimate(int n, const std::vector<int32_t> &col_ptr, const std:
       in_step[c] += m;
       ntemp[c] = std::max(ntemp[c], in_step[c]);
     }
-    words[c] += 3.6 * (0.5 * m * (m + 1) + m) + 2.4 * (m + 1) + 6 + m;
+    words[c] += 3.6 * (0.5 * m * (m + 1) + m) + 2.4 * (m + 1) + 12 + 3 * m;  // (backward: a pair word per block, an item per destination and source step)
     if (c)
       for (int b = col_ptr[j] + 1; b < col_ptr[j + 1]; ++b) {
         const int i = blk_row[b];
@@ -173,6 +173,33 @@ inline bool push_product_item(std::vector<int32_t> &w, int dest, int nrows, int 
 inline void push_panel_item(std::vector<int32_t> &w, int dest, int nrows, int diag, int xcopy) {
   w.push_back((int32_t)((unsigned)dest | ((unsigned)nrows << 16)));
   w.push_back((int32_t)((unsigned)diag | ((unsigned)xcopy << 16)));
+}
+// one term of the backward substitution: w_dest -= Y^T x, `blk` / `x` = pool offsets; `rank` orders the destinations
+struct BwdPair { int dest, rank, src, blk, x; };
+// pair words, then rounds of five items { destination vector | n_pairs << 16, first pair word }; returns the rounds
+inline int emit_bwd_rounds(std::vector<int32_t> &w, std::vector<BwdPair> &bp, int V0, int q0, int &off_items) {
+  std::stable_sort(bp.begin(), bp.end(), [](const BwdPair &x, const BwdPair &y) {
+    if (x.rank != y.rank) return x.rank < y.rank;
+    if (x.dest != y.dest) return x.dest > y.dest;  // later columns become final first
+    return x.src > y.src;
+  });
+  const int off_pairs = (int)w.size();
+  for (const BwdPair &p : bp) w.push_back((int32_t)((unsigned)p.blk | ((unsigned)p.x << 16)));
+  if (w.size() & 1) w.push_back(0);
+  std::vector<int32_t> items;
+  for (size_t i = 0; i < bp.size();) {
+    size_t j = i;
+    while (j < bp.size() && bp[j].dest == bp[i].dest) ++j;
+    if (j - i >= 65536) return -1;
+    items.push_back((int32_t)((unsigned)(V0 + 6 * (bp[i].dest - q0)) | ((unsigned)(j - i) << 16)));
+    items.push_back(off_pairs + (int)i);
+    i = j;
+  }
+  const int n_rounds = ((int)items.size() / 2 + 4) / 5;
+  items.resize((size_t)n_rounds * kTreeRoundWords, 0);
+  off_items = (int)w.size();  // even: the items are read as 8-byte words
+  w.insert(w.end(), items.begin(), items.end());
+  return n_rounds;
 }
 
 }  // namespace
@@ -405,28 +432,43 @@ bool build_tree_program(int n, const std::vector<int32_t> &col_ptr, const std::v
         if (i < panel.size()) push_panel_item(w, panel[i].dest, panel[i].nrows, panel[i].p0, panel[i].p1);
         else push_panel_item(w, 0, 0, 0, 0);
       }
-      // backward records: x_j = w_j - sum_i Y_ij^T x_i; rows = where x_i lives in the pool
-      while (w.size() & 3) w.push_back(0);  // the records are read as 16-byte words
-      st = step_entry();
-      st[kTS_OffBwd] = (int)w.size();
-      const size_t rec0 = w.size();
-      w.resize(w.size() + 4 * (size_t)nc, 0);
-      for (int t = 0; t < nc; ++t) {
-        const int j = cols[t], nb = col_ptr[j + 1] - col_ptr[j] - 1;
-        w[rec0 + 4 * t + 0] = 36 * (col_ptr[j] - tp.b0[c]);
-        w[rec0 + 4 * t + 1] = V0[c] + 6 * (j - q0[c]);
-        w[rec0 + 4 * t + 2] = nb;
-        w[rec0 + 4 * t + 3] = (int)w.size();
-        for (int b = col_ptr[j] + 1; b < col_ptr[j + 1]; ++b) {
-          const int i = blk_row[b];
-          if (own(c, i)) w.push_back(V0[c] + 6 * (i - q0[c]));
-          else {
-            const int sl = (c && a.top[i]) ? cv_slot_of[c][i - q0[0]] : -1;
-            if (sl < 0) return fail("internal: backward row without a slot");
-            w.push_back(CV0[c] + 6 * sl);
+      // backward rounds of this step: its columns i are the sources, w_j -= Y_ij^T x_i for every own column j
+      // with a block (i, j); one item per destination, the destinations of the previous step (the next to become
+      // final on the way back) first
+      {
+        std::vector<BwdPair> bp;
+        for (int t = 0; t < nc; ++t) {
+          const int i = cols[t];
+          for (int rr = row_ptr[i]; rr < row_ptr[i + 1]; ++rr) {
+            const int k = row_col[rr];
+            if (!own(c, k)) continue;  // a top row reaching into another CTA's subtree: that CTA's top rounds
+            bp.push_back(BwdPair{k, a.step[k] == s - 1 ? 0 : 1, i, 36 * (row_blk[rr] - tp.b0[c]), V0[c] + 6 * (i - q0[c])});
           }
         }
+        int off_items = 0;
+        const int n_rounds = emit_bwd_rounds(w, bp, V0[c], q0[c], off_items);
+        if (n_rounds < 0 || n_rounds >= 32768) return fail("too many backward rounds");
+        st = step_entry();
+        st[kTS_OffBwd] = off_items;
+        st[kTS_Cols] = nc | (n_rounds << 16);
       }
+    }
+    if (c) {
+      // the top solution arrives in this CTA's vector slots: its rounds come before the CTA's own backward steps
+      std::vector<BwdPair> bp;
+      for (int j = q0[c]; j < q1[c]; ++j)
+        for (int b = col_ptr[j] + 1; b < col_ptr[j + 1]; ++b) {
+          const int i = blk_row[b];
+          if (own(c, i)) continue;
+          const int sl = a.top[i] ? cv_slot_of[c][i - q0[0]] : -1;
+          if (sl < 0) return fail("internal: backward row without a slot");
+          bp.push_back(BwdPair{j, -a.step[j], i, 36 * (b - tp.b0[c]), CV0[c] + 6 * sl});
+        }
+      int off_items = 0;
+      const int n_rounds = emit_bwd_rounds(w, bp, V0[c], q0[c], off_items);
+      if (n_rounds < 0) return fail("too many backward rounds");
+      w[kTH_OffTopBwd] = off_items;
+      w[kTH_NTopBwd] = n_rounds;
     }
     if (pi < prods.size() && prods[pi].owner == c) return fail("internal: product scheduled after the last step");
     if (c == 0 && C > 1) {

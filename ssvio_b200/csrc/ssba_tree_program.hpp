@@ -18,7 +18,9 @@
 //   X_ij = A_ij - sum_k Y_ik X_jk^T,   Y_ij = X_ij M_j         (one lane per block row; Y replaces X in place, the
 //                                                               unscaled X_ij goes to a scratch copy for one step)
 //   z_j  = b_j - sum_k X_jk w_k,       w_j = M_j z_j           (the right-hand side is one more block row of height 1)
-// and backwards  x_j = w_j - sum_{i>j} Y_ij^T x_i  (no triangular solve on the way back).
+// and backwards  x_j = w_j - sum_{i>j} Y_ij^T x_i  (no triangular solve on the way back), right-looking: as soon as
+// the columns i of a step are final, every w_j they reach is updated (one lane group per destination j), so that the
+// chain from one step to the next is a single 6x6 product - the other terms of a column were subtracted earlier.
 // The products of a finished column k are applied eagerly (right-looking), ALL of them in the step after k's
 // (which is why the unscaled copy only lives for one step): the ones a diagonal block of the next step waits
 // for by the warp that inverts it, all others by the remaining warps WHILE the diagonal blocks are being
@@ -50,12 +52,18 @@ constexpr int kTreeStepCols = 5 * kTreeWarps;     // diagonal blocks one step ca
 // Rounds are five items.
 constexpr int kTreeItemWords = 2, kTreeRoundWords = 5 * kTreeItemWords;
 // program header words
-enum : int { kTH_StepsA = 0, kTH_StepsB, kTH_OffSteps, kTH_AddRounds, kTH_OffAddRounds, kTH_NXload, kTH_OffXload, kTH_TopCol0, kTH_Words = 16 };
+// kTH_NTopBwd / kTH_OffTopBwd (CTAs != 0): backward rounds whose sources are the top columns (their solution arrives
+// from CTA 0), run before the CTA's own backward steps
+enum : int { kTH_StepsA = 0, kTH_StepsB, kTH_OffSteps, kTH_AddRounds, kTH_OffAddRounds, kTH_NXload, kTH_OffXload, kTH_TopCol0, kTH_NTopBwd, kTH_OffTopBwd, kTH_Words = 16 };
 // step table entry (8 words)
 // kTS_OffPre: per diagonal item of the step two words { n, offset } = the panel items of the PREVIOUS step's columns
 // that feed this column's critical products (its own block row): the lane group that inverts the column scales them
 // itself, first thing in the step; kTS_NPanel / kTS_OffPanel: the other panel items of THIS step's columns, run by the
 // look-ahead warps at the start of the next step (or after the last one)
+// kTS_Cols: columns | backward rounds << 16; kTS_OffBwd: the backward rounds of the step = five items
+// { destination vector | n_pairs << 16, first pair word } each, pair word = block Y_ij | x_i << 16: w_j -= Y_ij^T x_i for
+// the columns i of THIS step (final when the rounds run) and every own column j they reach; the destinations in the
+// step before come first
 enum : int { kTS_Cols = 0, kTS_OffDiag, kTS_NLook, kTS_OffLook, kTS_NPanel, kTS_OffPanel, kTS_OffBwd, kTS_OffPre, kTS_Words = 8 };
 
 struct TreeProgram {

@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kTreeThreads, 1) k_tree_solve(const DeviceProb
     unsigned dpw = 0;             // ... its first pair word
     int2 dpre = make_int2(0, 0);  // ... and the critical panel items of the previous step it scales itself
     int p_n = 0, p_off = 0;       // the previous step's other panel items (rounds, offset)
-    if (g < 5 && ci < da.x) {
+    if (g < 5 && ci < (da.x & 0xffff)) {
       dit = *reinterpret_cast<const int2 *>(prog + da.y + kTreeItemWords * ci);
       if ((unsigned)dit.x >> 20) dpw = (unsigned)prog[dit.y];
     }
@@ -265,13 +265,13 @@ __global__ void __launch_bounds__(kTreeThreads, 1) k_tree_solve(const DeviceProb
         TS_TRACE_G(4);
       }
       if (s >= ns_all) break;
-      const int nc = da.x, n_look = da.z, off_look = da.w;
+      const int nc = da.x & 0xffff, n_look = da.z, off_look = da.w;
       // program data of the next step (nothing the steps write)
       int4 na = make_int4(0, 0, 0, 0), nb = na;
       if (s + 1 < ns_all) { na = *reinterpret_cast<const int4 *>(steps + kTS_Words * (s + 1)); nb = *reinterpret_cast<const int4 *>(steps + kTS_Words * (s + 1) + 4); }
       int2 nit = make_int2(0, 0), npre = make_int2(0, 0);  // the next step's diagonal item, first pair word, critical panel list
       unsigned npw = 0;
-      if (g < 5 && ci < na.x) {
+      if (g < 5 && ci < (na.x & 0xffff)) {
         nit = *reinterpret_cast<const int2 *>(prog + na.y + kTreeItemWords * ci);
         npre = *reinterpret_cast<const int2 *>(prog + nb.w + 2 * ci);
         if ((unsigned)nit.x >> 20) npw = (unsigned)prog[nit.y];
@@ -385,14 +385,36 @@ __global__ void __launch_bounds__(kTreeThreads, 1) k_tree_solve(const DeviceProb
   }
   TS_TRACE_G(5);
 
-  // ---- backward substitution, last step first: one warp per column, x_j = w_j - sum_i Y_ij^T x_i; the records of
-  // the next step are fetched ahead of the barrier.  The top solution goes down to the other CTAs when the top
-  // steps are done.
+  // ---- backward substitution, right-looking, last step first: the columns i of a step are final when its rounds
+  // run; every own column j they reach gets w_j -= Y_ij^T x_i from one lane group (an item per destination, the
+  // destinations of the step before first), so that between two steps only one 6x6 product is on the chain.  The
+  // top solution goes down to the other CTAs when the top steps are done; their rounds with the top columns as
+  // sources come first.
   {
-    int nc = 0, off = 0;
-    if (ns_all > 0) { nc = steps[kTS_Words * (ns_all - 1) + kTS_Cols]; off = steps[kTS_Words * (ns_all - 1) + kTS_OffBwd]; }
-    int4 rec = make_int4(0, 0, 0, 0);
-    if (warp < nc) rec = *reinterpret_cast<const int4 *>(prog + off + 4 * warp);
+    // (measured, not kept: fetching a step's descriptors - with or without the first item's column of Y_ij - ahead of
+    // the barrier that makes its sources final: 49.7 -> 51.6 us per solve at cfg3)
+    auto bwd_rounds = [&](int n_rounds, int off) {
+      const int *items = prog + off;
+#pragma unroll 1
+      for (int rd = warp; rd < n_rounds; rd += kTreeWarps) {
+        if (g < 5) {
+          const int2 it = *reinterpret_cast<const int2 *>(items + kTreeRoundWords * rd + kTreeItemWords * g);
+          const int n = (int)((unsigned)it.x >> 16);
+          if (n > 0) {
+            double acc = 0.0;
+            unsigned pw = (unsigned)prog[it.y];
+            for (int p = 0; p < n; ++p) {
+              const double *B = pool + (pw & 0xffffu);
+              const double2 *x2 = reinterpret_cast<const double2 *>(pool + (pw >> 16));
+              if (p + 1 < n) pw = (unsigned)prog[it.y + p + 1];
+              const double2 x0 = x2[0], x1 = x2[1], xx2 = x2[2];
+              acc += B[r] * x0.x + B[6 + r] * x0.y + B[12 + r] * x1.x + B[18 + r] * x1.y + B[24 + r] * xx2.x + B[30 + r] * xx2.y;
+            }
+            pool[(it.x & 0xffff) + r] -= acc;
+          }
+        }
+      }
+    };
 #pragma unroll 1
     for (int s = ns_all - 1;; --s) {
       if (s == nsa - 1) {
@@ -411,37 +433,16 @@ __global__ void __launch_bounds__(kTreeThreads, 1) k_tree_solve(const DeviceProb
               const int m = i - 6 * (i / 6);
               pool[(wd & 0xffffu) + m] = __ldcg(P.xp + 6 * (size_t)(wd >> 16) + m);
             }
+            __syncthreads();
+            bwd_rounds(prog[kTH_NTopBwd], prog[kTH_OffTopBwd]);
           }
           __syncthreads();
         }
         TS_TRACE_G(7);
       }
-      if (s < 0) break;
-      int nnc = 0, noff = 0;
-      if (s > 0) { nnc = steps[kTS_Words * (s - 1) + kTS_Cols]; noff = steps[kTS_Words * (s - 1) + kTS_OffBwd]; }
-#pragma unroll 1
-      for (int t = warp; t < nc; t += kTreeWarps) {
-        const int4 rc = t == warp ? rec : *reinterpret_cast<const int4 *>(prog + off + 4 * t);
-        const int dg = rc.x, vo = rc.y, nb = rc.z;
-        const int *rows = prog + rc.w;
-        double acc = 0.0;
-        if (g < 5) {
-          for (int k = g; k < nb; k += 5) {
-            const double *B = pool + dg + 36 * (1 + k);
-            const double2 *x2 = reinterpret_cast<const double2 *>(pool + rows[k]);
-            const double2 x0 = x2[0], x1 = x2[1], xx2 = x2[2];
-            acc += B[r] * x0.x + B[6 + r] * x0.y + B[12 + r] * x1.x + B[18 + r] * x1.y + B[24 + r] * xx2.x + B[30 + r] * xx2.y;
-          }
-        }
-        acc = ts_group_reduce(acc, lane);  // totals on lanes 0..5
-        if (lane < 6) pool[vo + r] -= acc;
-      }
-      int4 nrec = make_int4(0, 0, 0, 0);
-      if (warp < nnc) nrec = *reinterpret_cast<const int4 *>(prog + noff + 4 * warp);
-      // a chain of single-column steps runs on warp 0 alone: its own stores and loads only need the warp in step
-      const bool chain = nc == 1 && nnc == 1 && s != nsa;
-      nc = nnc; off = noff; rec = nrec;
-      if (chain) __syncwarp(); else __syncthreads();
+      if (s < 1) break;  // the columns of step 0 reach nothing
+      bwd_rounds((int)((unsigned)steps[kTS_Words * s + kTS_Cols] >> 16), steps[kTS_Words * s + kTS_OffBwd]);
+      __syncthreads();
 #ifdef SSBA_SOLVER_TRACE
       TS_TRACE_C(trc); ++trc;
 #endif

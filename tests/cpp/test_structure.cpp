@@ -228,11 +228,11 @@ static void tree_forward_steps(TreeCta &c, int s0, int s1, bool *fail) {
   const int32_t *prev = nullptr;  // the previous step's table entry
   for (int s = s0; s <= s1; ++s) {
     const int32_t *st = s < s1 ? w + w[kTH_OffSteps] + kTS_Words * s : nullptr;
-    if (st) CHECK(st[kTS_OffDiag] % 2 == 0 && st[kTS_OffLook] % 2 == 0 && st[kTS_OffPanel] % 2 == 0 && st[kTS_OffBwd] % 4 == 0 && st[kTS_OffPre] % 2 == 0, "tree program: item arrays misaligned");
+    if (st) CHECK(st[kTS_OffDiag] % 2 == 0 && st[kTS_OffLook] % 2 == 0 && st[kTS_OffPanel] % 2 == 0 && st[kTS_OffBwd] % 2 == 0 && st[kTS_OffPre] % 2 == 0, "tree program: item arrays misaligned");
     ++c.T;  // interval A (after the last step: the drain of its panel items)
     ++c.dg_stamp;
     if (st)
-      for (int t = 0; t < st[kTS_Cols]; ++t) {
+      for (int t = 0; t < (st[kTS_Cols] & 0xffff); ++t) {
         ++c.item;
         const int32_t *pre = w + st[kTS_OffPre] + 2 * t;
         for (int i = 0; i < pre[0]; ++i) tree_panel_item(c, w + pre[1] + kTreeItemWords * i);
@@ -287,21 +287,32 @@ static void tree_forward_steps(TreeCta &c, int s0, int s1, bool *fail) {
     prev = st;
   }
 }
+// the backward rounds of one source step (or of the top columns for a CTA != 0): every item is one work item of the
+// interval; it reads final x_i, blocks Y_ij and rewrites its own destination w_j
+static void tree_backward_rounds(TreeCta &c, int n_rounds, int off) {
+  const int32_t *w = c.w;
+  CHECK(off % 2 == 0, "tree program: backward items misaligned");
+  ++c.T;
+  for (int i = 0; i < 5 * n_rounds; ++i) {
+    ++c.item;
+    const int32_t *it = w + off + kTreeItemWords * i;
+    const int dest = it[0] & 0xffff, n = (int)((unsigned)it[0] >> 16);
+    if (n == 0) continue;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int p = 0; p < n; ++p) {
+      const unsigned pw = (unsigned)w[it[1] + p];
+      const int B = (int)(pw & 0xffff), xo = (int)(pw >> 16);
+      c.rd2(xo);
+      for (int m = 0; m < 6; ++m) { double t = 0; for (int nn = 0; nn < 6; ++nn) t += c.rd(B + 6 * nn + m) * c.rd(xo + nn); acc[m] += t; }
+    }
+    for (int m = 0; m < 6; ++m) c.wrt(dest + m, c.rd(dest + m) - acc[m]);  // w_j -= sum_i Y_ij^T x_i
+  }
+}
 static void tree_backward_steps(TreeCta &c, int s0, int s1) {
   const int32_t *w = c.w;
-  for (int s = s1 - 1; s >= s0; --s) {
+  for (int s = s1 - 1; s >= std::max(s0, 1); --s) {
     const int32_t *st = w + w[kTH_OffSteps] + kTS_Words * s;
-    ++c.T;
-    for (int t = 0; t < st[kTS_Cols]; ++t) {
-      ++c.item;
-      const int32_t *rec = w + st[kTS_OffBwd] + 4 * t;
-      const int dg = rec[0], v = rec[1], nb = rec[2];
-      const int32_t *rows = w + rec[3];
-      double sv[6];
-      for (int m = 0; m < 6; ++m) sv[m] = c.rd(v + m);
-      for (int k = 0; k < nb; ++k) { const int B = dg + 36 * (1 + k); for (int m = 0; m < 6; ++m) for (int nn = 0; nn < 6; ++nn) sv[m] -= c.rd(B + 6 * nn + m) * c.rd(rows[k] + nn); }
-      for (int m = 0; m < 6; ++m) c.wrt(v + m, sv[m]);  // x_j = w_j - sum_i Y_ij^T x_i
-    }
+    tree_backward_rounds(c, (int)((unsigned)st[kTS_Cols] >> 16), st[kTS_OffBwd]);
   }
 }
 static std::vector<double> interpret_tree_program(const Structure &s, const std::vector<double> &L0, const std::vector<double> &b) {
@@ -358,6 +369,7 @@ static std::vector<double> interpret_tree_program(const Structure &s, const std:
       const unsigned wd = (unsigned)t.w[t.w[kTH_OffXload] + i];
       for (int m = 0; m < 6; ++m) t.wrt((int)(wd & 0xffff) + m, x[6 * (size_t)(wd >> 16) + m]);
     }
+    tree_backward_rounds(t, t.w[kTH_NTopBwd], t.w[kTH_OffTopBwd]);
   }
   for (int c = 0; c < C; ++c) {
     tree_backward_steps(cta[c], 0, cta[c].w[kTH_StepsA]);
