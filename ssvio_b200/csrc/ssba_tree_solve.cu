@@ -314,7 +314,9 @@ __global__ void __launch_bounds__(kTreeThreads, 1) k_tree_solve(const DeviceProb
         // (measured, not kept: arriving only after the critical products, so that the look-ahead warps' loads do not
         // queue in front of the diagonal blocks' operands: 56.0 -> 59.9 us per solve - the look-ahead is on the path too;
         // requesting the first critical pair's operands (21 x 16 bytes per lane) before the arrive: 68 us - the kernel
-        // sits at its 128-register cap and the 42 extra live doubles spill)
+        // sat at its 128-register cap and the 42 extra live doubles spilled; a second code path for warps with a
+        // single column, in which the four idle lane groups share the critical panel item and product - one entry of
+        // the 6x6 result per lane: 50.6 -> 54.3 us, the step body no longer fits the instruction cache next to it)
         if (!all_diag) asm volatile("bar.arrive 1, %0;" ::"n"(kTreeThreads) : "memory");
       }
       if (w0 >= 0 && g < 5) {
