@@ -18,4 +18,8 @@ except Exception as e:
     print("$w N=$N: no line", e)
 PY
 done
-if [ "$N" != "1" ]; then python -m pytest tests/test_gpu_multi.py -q 2>&1 | tail -2 | tee gpurun_out/r2_mgpu_test_n$N.log; fi
+if [ "$N" != "1" ]; then
+  python -m pytest tests/test_gpu_multi.py -q 2>&1 | tail -2 | tee gpurun_out/r2_mgpu_test_n$N.log
+  # the worker's own report (rank agreement bit for bit, golden chi2, pre-sharded input), kept as evidence
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2953$N tests/mgpu_worker.py 2>/dev/null | grep -v "^\[W\|^W[0-9]" | tee gpurun_out/r2_mgpu_worker_n$N.log | tail -12
+fi
