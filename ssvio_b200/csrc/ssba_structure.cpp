@@ -1200,19 +1200,36 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
         if (s.pair_q[s.slot_pair_ptr[x] + i] != s.pair_q[s.slot_pair_ptr[y] + i]) return false;
       return true;
     };
-    int sl = 0;
-    while (sl < s.n_slots) {
-      const int k = wcount(sl);
-      if (k == 0) { ++sl; continue; }
-      int e = sl + 1;
-      // the run's W blocks are staged in shared memory by k_schur: at most kSchurRunPairs of them
-      const int max_run = std::max(1, std::min(kSchurRun, kSchurRunPairs / k));
-      while (e < s.n_slots && e - sl < max_run && wcount(e) == k && same_list(sl, e, k)) ++e;
-      const int npairs = k * (k + 1) / 2;
-      for (int c0 = 0; c0 < npairs; c0 += 32) {
-        s.unit_slot.push_back(sl); s.unit_n.push_back(e - sl); s.unit_k.push_back(k); s.unit_c0.push_back(c0);
+    // runs never cross the boundaries of fixed blocks of slots (independent of the thread count, so the units -
+    // and with them the summation order of the reduced system - only depend on the graph): the blocks are scanned
+    // in parallel and their unit lists concatenated in block order
+    constexpr int kUnitBlock = 1024;
+    const int n_ublocks = (s.n_slots + kUnitBlock - 1) / kUnitBlock;
+    struct UnitList { std::vector<int32_t> slot, n, k, c0; };
+    std::vector<UnitList> ul(n_ublocks);
+    pool.run(std::min(T, std::max(1, n_ublocks)), [&](int t, int TT) {
+      for (int ub = t; ub < n_ublocks; ub += TT) {
+        UnitList &u = ul[ub];
+        const int end = std::min(s.n_slots, (ub + 1) * kUnitBlock);
+        int sl = ub * kUnitBlock;
+        while (sl < end) {
+          const int k = wcount(sl);
+          if (k == 0) { ++sl; continue; }
+          int e = sl + 1;
+          // the run's W blocks are staged in shared memory by k_schur: at most kSchurRunPairs of them
+          const int max_run = std::max(1, std::min(kSchurRun, kSchurRunPairs / k));
+          while (e < end && e - sl < max_run && wcount(e) == k && same_list(sl, e, k)) ++e;
+          const int npairs = k * (k + 1) / 2;
+          for (int c0 = 0; c0 < npairs; c0 += 32) { u.slot.push_back(sl); u.n.push_back(e - sl); u.k.push_back(k); u.c0.push_back(c0); }
+          sl = e;
+        }
       }
-      sl = e;
+    });
+    for (const UnitList &u : ul) {
+      s.unit_slot.insert(s.unit_slot.end(), u.slot.begin(), u.slot.end());
+      s.unit_n.insert(s.unit_n.end(), u.n.begin(), u.n.end());
+      s.unit_k.insert(s.unit_k.end(), u.k.begin(), u.k.end());
+      s.unit_c0.insert(s.unit_c0.end(), u.c0.begin(), u.c0.end());
     }
     s.n_units = (int)s.unit_slot.size();
     tm.mark("  unit runs");
