@@ -740,9 +740,9 @@ class HostPool {
     }
   }
   HostPool() {
-    // measured on the B200 hosts (16 cores) with the polling pool: initialize 1.84 ms with 4 threads, 1.59 with 6,
-    // 1.74 with 8 - the passes are short and memory-bound
-    int n = std::min((int)std::thread::hardware_concurrency(), 6);
+    // measured on the B200 hosts (16 cores) with the polling pool, cfg3: initialize 1.69 ms with 4 threads, 1.44 with 6,
+    // 1.33 with 8, 1.44 with 10, 1.58 with 12, 2.1 with 16 - the passes are short and memory-bound
+    int n = std::min((int)std::thread::hardware_concurrency(), 8);
     // several ranks on one host (one process per GPU) share its cores: polling workers must not oversubscribe them
     n = std::max(1, std::min(n, (int)std::thread::hardware_concurrency() / std::max(1, g_ranks_on_host.load())));
     if (const char *e = std::getenv("SSBA_HOST_THREADS")) n = std::atoi(e);
