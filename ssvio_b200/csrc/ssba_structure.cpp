@@ -1052,16 +1052,30 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   // by edge count
   std::vector<int32_t> slots;
   {
+    // counting sort by first pose, stable in the landmark index: per-thread histograms over contiguous landmark
+    // ranges, offsets in (bucket, thread) order, parallel fill - the same array a serial pass would produce
     std::vector<int32_t> bucket_cnt(n + 2, 0);
     int n_act_pts = 0;
-    for (int j = 0; j < NP; ++j) if (point_active[j]) { ++bucket_cnt[lm_minq[j] + 1]; ++n_act_pts; }
-    for (int q = 0; q <= n; ++q) bucket_cnt[q + 1] += bucket_cnt[q];
+    const int TB = NP >= 8192 ? T : 1;
+    std::vector<std::vector<int32_t>> t_hist(TB);
+    pool.run(TB, [&](int t, int TT) {
+      int j0, j1; split_range(t, TT, NP, j0, j1);
+      std::vector<int32_t> &hst = t_hist[t];
+      hst.assign(n + 1, 0);
+      for (int j = j0; j < j1; ++j) if (point_active[j]) ++hst[lm_minq[j]];
+    });
+    for (int q = 0; q <= n; ++q) {
+      bucket_cnt[q] = n_act_pts;
+      for (int t = 0; t < TB; ++t) { if (t_hist[t].empty()) continue; const int c = t_hist[t][q]; t_hist[t][q] = n_act_pts; n_act_pts += c; }
+    }
+    bucket_cnt[n + 1] = n_act_pts;
     // (hash, landmark) keys side by side: the comparisons of the sort stay inside the array
     std::vector<std::pair<uint64_t, int32_t>> sorted(n_act_pts);
-    {
-      std::vector<int32_t> fill(bucket_cnt.begin(), bucket_cnt.end() - 1);
-      for (int j = 0; j < NP; ++j) if (point_active[j]) sorted[fill[lm_minq[j]]++] = {lm_hash[j], j};
-    }
+    pool.run(TB, [&](int t, int TT) {
+      int j0, j1; split_range(t, TT, NP, j0, j1);
+      std::vector<int32_t> &fill = t_hist[t];  // now: where this thread's next landmark of bucket q goes
+      for (int j = j0; j < j1; ++j) if (point_active[j]) sorted[fill[lm_minq[j]]++] = {lm_hash[j], j};
+    });
     // Inside a bucket the landmarks only have to be GROUPED by pose list (they arrive in
     // landmark order, which every group keeps): a stable counting sort over the few distinct
     // hashes, in order of first appearance; a comparison sort only if a bucket has many lists.
@@ -1094,7 +1108,13 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     });
     const long long total = n_active;
     long long seen = 0;
-    slots.reserve(world > 1 ? n_act_pts / world + 64 : n_act_pts);
+    if (world == 1) {  // one rank owns everything: the order itself
+      slots.resize(n_act_pts);
+      pool.run(TB, [&](int t, int TT) {
+        int i0, i1; split_range(t, TT, n_act_pts, i0, i1);
+        for (int i = i0; i < i1; ++i) slots[i] = sorted[i].second;
+      });
+    } else
     for (const auto &hj : sorted) {
       const int j = hj.second;
       // owner = the rank whose edge-quantile holds the first edge of this landmark
@@ -1112,12 +1132,30 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   const bool have_info = host_values && !g.e_info.empty(), have_delta = host_values && !g.e_delta.empty();
   // offsets of every slot's edges, pairs and Schur targets (prefix sums), then a parallel fill
   std::vector<int32_t> slot_edge_ptr(s.n_slots + 1, 0);
-  for (int sl = 0; sl < s.n_slots; ++sl) {
-    const int j = slots[sl];
-    slot_edge_ptr[sl + 1] = slot_edge_ptr[sl] + point_deg[j];
-    s.slot_pair_ptr[sl + 1] = s.slot_pair_ptr[sl] + lm_npairs[j];
-    s.slot_free[sl] = !lfix[j];
-    if (!lfix[j]) ++s.n_fl;
+  {
+    // two parallel passes: the counts of every slot (random reads by landmark) and the totals of every thread's
+    // range, then the prefix sums of the range on top of the totals before it
+    const int TS = s.n_slots >= 8192 ? T : 1;
+    std::vector<long long> t_edges(TS + 1, 0), t_pairs(TS + 1, 0), t_free(TS + 1, 0);
+    int32_t *sep = slot_edge_ptr.data(), *spp = s.slot_pair_ptr.data();
+    pool.run(TS, [&](int t, int TT) {
+      int a, b; split_range(t, TT, s.n_slots, a, b);
+      long long ne = 0, npr = 0, nf = 0;
+      for (int sl = a; sl < b; ++sl) {
+        const int j = slots[sl];
+        sep[sl + 1] = point_deg[j]; spp[sl + 1] = lm_npairs[j];
+        ne += point_deg[j]; npr += lm_npairs[j];
+        s.slot_free[sl] = !lfix[j];
+        nf += !lfix[j];
+      }
+      t_edges[t + 1] = ne; t_pairs[t + 1] = npr; t_free[t + 1] = nf;
+    });
+    for (int t = 0; t < TS; ++t) { t_edges[t + 1] += t_edges[t]; t_pairs[t + 1] += t_pairs[t]; s.n_fl += (int)t_free[t + 1]; }
+    pool.run(TS, [&](int t, int TT) {
+      int a, b; split_range(t, TT, s.n_slots, a, b);
+      int32_t ce = (int32_t)t_edges[t], cp = (int32_t)t_pairs[t];
+      for (int sl = a; sl < b; ++sl) { ce += sep[sl + 1]; cp += spp[sl + 1]; sep[sl + 1] = ce; spp[sl + 1] = cp; }
+    });
   }
   {
     const size_t ne_local = (size_t)slot_edge_ptr[s.n_slots], np_local = (size_t)s.slot_pair_ptr[s.n_slots];
