@@ -918,27 +918,42 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   // (block_solver.hpp:224-249): per-thread bitmaps when small enough, else key lists
   const bool use_bitmap = n <= 4096;
   const size_t bm_words = use_bitmap ? ((size_t)n * n + 63) / 64 : 0;
+  // The same pass collects what the landmark ORDER needs, none of which depends on the elimination order that is
+  // computed from this pattern: per landmark a hash of its free-pose set (over the free-pose indices), its first
+  // free pose, its number of (pose, landmark) pairs and of W pairs.  For every active landmark, because the
+  // landmark order is global across ranks.
+  std::vector<uint64_t> lm_hash(NP, 0);
+  std::vector<int32_t> lm_minq(NP, n), lm_npairs(NP, 0), lm_k(NP, 0);  // lm_minq: first free pose (free-pose index)
   std::vector<std::vector<uint64_t>> t_bitmap(T), t_keys(T);
   pool.run(T, [&](int t, int TT) {
     int j0, j1; split_range(t, TT, NP, j0, j1);
     std::vector<uint64_t> &bm = t_bitmap[t], &keys = t_keys[t];
     if (use_bitmap) bm.assign(bm_words, 0);
-    int ql[64];
-    std::vector<int32_t> big;
+    int ql[64], fl[64];
+    std::vector<int32_t> big, bigf;
+    auto insert_unique = [](int *lst, int &cnt, int f) {  // sorted insert, duplicates dropped
+      int i = cnt;
+      while (i > 0 && lst[i - 1] > f) --i;
+      if (i > 0 && lst[i - 1] == f) return;
+      for (int u = cnt; u > i; --u) lst[u] = lst[u - 1];
+      lst[i] = f; ++cnt;
+    };
     for (int j = j0; j < j1; ++j) {
-      if (!point_active[j] || lfix[j]) continue;
+      if (!point_active[j]) continue;
       const int m = pt_ptr[j + 1] - pt_ptr[j];
-      int *lst = ql, cnt = 0;
-      if (m > 64) { big.resize(m); lst = big.data(); }
+      int *lst = ql, *fst = fl, cnt = 0, fcnt = 0;  // distinct free poses (free-pose index) / fixed poses (row)
+      if (m > 64) { big.resize(m); bigf.resize(m); lst = big.data(); fst = bigf.data(); }
       for (int k = pt_ptr[j]; k < pt_ptr[j + 1]; ++k) {
-        const int f = fp_of_pose[ge_pose[pt_edges[k]]];
-        if (f < 0) continue;
-        int i = cnt;  // sorted insert, duplicates dropped
-        while (i > 0 && lst[i - 1] > f) --i;
-        if (i > 0 && lst[i - 1] == f) continue;
-        for (int u = cnt; u > i; --u) lst[u] = lst[u - 1];
-        lst[i] = f; ++cnt;
+        const int pose = ge_pose[pt_edges[k]];
+        const int f = fp_of_pose[pose];
+        if (f >= 0) insert_unique(lst, cnt, f); else insert_unique(fst, fcnt, pose);
       }
+      lm_npairs[j] = cnt + fcnt;
+      if (lfix[j]) continue;  // a fixed landmark: pairs, but no W blocks and no part in the pattern
+      uint64_t h = 1469598103934665603ull;
+      for (int i = 0; i < cnt; ++i) h = (h ^ (uint64_t)(lst[i] + 1)) * 1099511628211ull;
+      lm_hash[j] = h; lm_k[j] = cnt;
+      if (cnt) lm_minq[j] = lst[0];
       for (int a2 = 0; a2 < cnt; ++a2)
         for (int b2 = a2 + 1; b2 < cnt; ++b2) {
           const size_t bit = (size_t)lst[a2] * n + lst[b2];  // column a2 < row b2
@@ -976,76 +991,31 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   }
 
   tm.mark("co-visibility");
-  // ---- elimination order and symbolic factorisation over q (the solver program follows on its own thread)
+  // ---- elimination order and symbolic factorisation over q, then the solver program: all serial and all a
+  // function of the pattern only - on a thread of its own, while this one goes on with the landmark order (which
+  // does not depend on q) on the pool.  `plan_state` is raised when the order and the factor pattern are in place
+  // (the pair / unit lists below need them), the program follows.
   SolverPlan solver_plan;
-  {
-    if (!plan_reduced_solver(n, adj, s, solver_plan, err)) return false;
-    const std::vector<int> &perm = solver_plan.perm;  // q -> free pose index
-    s.q_of_pose.assign(NK, -1);
-    s.pose_of_q.resize(n);
-    for (int q = 0; q < n; ++q) { s.q_of_pose[free_pose_rows[perm[q]]] = q; s.pose_of_q[q] = free_pose_rows[perm[q]]; }
-  }
-  // The solver program (serial, the longest single piece of host work left) is built on a thread
-  // of its own while this one goes on with the landmark / pair / chunk / unit lists: it reads the factor
-  // pattern only and writes tree / prog / prog_ptr / task lists / solver_* only.
-  std::thread program_thread([&] { finish_solver_program(n, adj, s, solver_plan); });
+  std::atomic<int> plan_state{0};  // 1: order + symbolic done, -1: failed (plan_err)
+  std::string plan_err;
+  std::thread program_thread([&] {
+    const bool ok = plan_reduced_solver(n, adj, s, solver_plan, plan_err);
+    if (ok) {
+      const std::vector<int> &perm = solver_plan.perm;  // q -> free pose index
+      s.q_of_pose.assign(NK, -1);
+      s.pose_of_q.resize(n);
+      for (int q = 0; q < n; ++q) { s.q_of_pose[free_pose_rows[perm[q]]] = q; s.pose_of_q[q] = free_pose_rows[perm[q]]; }
+    }
+    plan_state.store(ok ? 1 : -1, std::memory_order_release);
+    if (ok) finish_solver_program(n, adj, s, solver_plan);
+  });
   struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{program_thread};
   auto find_block = [&](int row, int col) -> int {  // row >= col
     const int *b0 = s.blk_row.data() + s.col_ptr[col], *b1 = s.blk_row.data() + s.col_ptr[col + 1];
     const int *it = std::lower_bound(b0, b1, row);
     return (it != b1 && *it == row) ? (int)(it - s.blk_row.data()) : -1;
   };
-  const int32_t *__restrict__ qmap = s.q_of_pose.data();
 
-  tm.mark("order + symbolic");
-  // ---- per landmark: its edges sorted by pose (free poses first by q, then fixed poses by row;
-  // addEdge order inside a pose), in place in pt_edges; a hash of its free-pose list, its first
-  // pose, its number of (pose, landmark) pairs and of W pairs.  For every active landmark,
-  // because the landmark ORDER below is global across ranks.
-  std::vector<uint64_t> lm_hash(NP, 0);
-  std::vector<int32_t> lm_minq(NP, n), lm_npairs(NP, 0), lm_k(NP, 0);
-  pool.run(T, [&](int t, int TT) {
-    int j0, j1; split_range(t, TT, NP, j0, j1);
-    std::vector<std::pair<long long, int32_t>> big;
-    for (int j = j0; j < j1; ++j) {
-      if (!point_active[j]) continue;
-      int32_t *seg = pt_edges.data() + pt_ptr[j];
-      const int m = pt_ptr[j + 1] - pt_ptr[j];
-      auto pose_key = [&](int e) -> long long { const int q = qmap[ge_pose[e]]; return q >= 0 ? q : (long long)n + ge_pose[e]; };
-      if (m <= 48) {  // insertion sort, stable
-        long long keys[48];
-        for (int i = 0; i < m; ++i) {
-          const int e = seg[i];
-          const long long k = pose_key(e);
-          int u = i;
-          while (u > 0 && keys[u - 1] > k) { keys[u] = keys[u - 1]; seg[u] = seg[u - 1]; --u; }
-          keys[u] = k; seg[u] = e;
-        }
-      } else {
-        big.clear();
-        for (int i = 0; i < m; ++i) big.emplace_back(pose_key(seg[i]), seg[i]);
-        std::sort(big.begin(), big.end());
-        for (int i = 0; i < m; ++i) seg[i] = big[i].second;
-      }
-      const bool lfree = !lfix[j];
-      uint64_t h = 1469598103934665603ull;
-      int prev_pose = -1, np_ = 0, k_ = 0;
-      for (int i = 0; i < m; ++i) {
-        const int pose = ge_pose[seg[i]];
-        if (pose == prev_pose) continue;
-        prev_pose = pose; ++np_;
-        const int q = qmap[pose];
-        if (q >= 0 && lfree) {
-          if (k_ == 0) lm_minq[j] = q;
-          ++k_;
-          h = (h ^ (uint64_t)(q + 1)) * 1099511628211ull;
-        }
-      }
-      lm_hash[j] = lfree ? h : 0; lm_npairs[j] = np_; lm_k[j] = k_;
-    }
-  });
-
-  tm.mark("per-landmark sort + hash");
   // ---- landmark order: landmarks seen by the same set of free poses are made adjacent (bucket
   // by first pose, then by the hash of the pose list), so that runs of landmarks accumulate into
   // the same Schur blocks; the shard of this rank = a contiguous range of that order, balanced
@@ -1157,6 +1127,21 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
       for (int sl = a; sl < b; ++sl) { ce += sep[sl + 1]; cp += spp[sl + 1]; sep[sl + 1] = ce; spp[sl + 1] = cp; }
     });
   }
+  tm.mark("slot offsets");
+  // ---- from here on the elimination order is needed (pairs are sorted by q inside a landmark, the Schur targets are
+  // blocks of the factor pattern): wait for the planning thread - normally long done
+  for (int spin = 0; plan_state.load(std::memory_order_acquire) == 0; ++spin) {
+    if (spin < 4096) {
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#endif
+    } else {
+      std::this_thread::yield();
+    }
+  }
+  if (plan_state.load(std::memory_order_acquire) < 0) { err = plan_err; return false; }
+  const int32_t *__restrict__ qmap = s.q_of_pose.data();
+  tm.mark("wait for order + symbolic");
   {
     const size_t ne_local = (size_t)slot_edge_ptr[s.n_slots], np_local = (size_t)s.slot_pair_ptr[s.n_slots];
     s.n_edges = (int)ne_local; s.n_pairs = (int)np_local;
@@ -1169,8 +1154,9 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     pool.run(T, [&](int t, int TT) {
       int s0, s1; split_range(t, TT, s.n_slots, s0, s1);
       const double *__restrict__ ge_uv = g.e_uv.data();
-      const int32_t *__restrict__ pe = pt_edges.data();
+      int32_t *__restrict__ pe = pt_edges.data();
       int32_t *__restrict__ o_orig = s.e_orig.data();
+      std::vector<std::pair<long long, int32_t>> big;
       double *__restrict__ o_uv = s.e_uv.data();
       uint8_t *__restrict__ o_cam = s.e_cam.data();
       int32_t *__restrict__ o_pv = s.pair_vertex.data(), *__restrict__ o_pq = s.pair_q.data(),
@@ -1192,6 +1178,28 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
         size_t ne = (size_t)slot_edge_ptr[sl], npair = (size_t)s.slot_pair_ptr[sl];
         int last_pose = -1;
         const int k1 = pt_ptr[j + 1];
+        {
+          // the landmark's edges sorted by pose, in place: free poses first by q, then fixed poses by row; addEdge
+          // order inside a pose (stable)
+          int32_t *seg = pe + pt_ptr[j];
+          const int m = k1 - pt_ptr[j];
+          auto pose_key = [&](int e) -> long long { const int q = qmap[ge_pose[e]]; return q >= 0 ? q : (long long)n + ge_pose[e]; };
+          if (m <= 48) {  // insertion sort, stable
+            long long keys[48];
+            for (int i = 0; i < m; ++i) {
+              const int e = seg[i];
+              const long long k = pose_key(e);
+              int u = i;
+              while (u > 0 && keys[u - 1] > k) { keys[u] = keys[u - 1]; seg[u] = seg[u - 1]; --u; }
+              keys[u] = k; seg[u] = e;
+            }
+          } else {
+            big.clear();
+            for (int i = 0; i < m; ++i) big.emplace_back(pose_key(seg[i]), seg[i]);
+            std::sort(big.begin(), big.end());
+            for (int i = 0; i < m; ++i) seg[i] = big[i].second;
+          }
+        }
         for (int k = pt_ptr[j]; k < k1; ++k) {
           const int e = pe[k];
           const int pose = ge_pose[e];
