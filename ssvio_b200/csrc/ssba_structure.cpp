@@ -744,7 +744,9 @@ class HostPool {
     // 1.33 with 8, 1.44 with 10, 1.58 with 12, 2.1 with 16 - the passes are short and memory-bound
     int n = std::min((int)std::thread::hardware_concurrency(), 8);
     // several ranks on one host (one process per GPU) share its cores: polling workers must not oversubscribe them
-    n = std::max(1, std::min(n, (int)std::thread::hardware_concurrency() / std::max(1, g_ranks_on_host.load())));
+    // (one core of a rank's share stays free for the planning thread of build_structure, which runs beside the pool)
+    const int ranks = std::max(1, g_ranks_on_host.load());
+    if (ranks > 1) n = std::max(1, std::min(n, (int)std::thread::hardware_concurrency() / ranks - 1));
     if (const char *e = std::getenv("SSBA_HOST_THREADS")) n = std::atoi(e);
     n_ = std::max(1, std::min(n, 64));
     for (int t = 1; t < n_; ++t) std::thread([this, t] { worker(t); }).detach();
