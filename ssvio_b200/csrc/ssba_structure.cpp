@@ -822,7 +822,11 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   s.n_edges_total = NE;
   if (!g.have_cams) { err = "ssba_set_cameras was not called"; return false; }
   HostPool &pool = HostPool::get();
-  const int T = NE >= 20000 ? pool.size() : 1;  // small graphs: threads cost more than they save
+  // small graphs: threads cost more than they save (SSBA_HOST_PAR_MIN lowers the thresholds: the CPU tests run the
+  // parallel passes on their small graphs and compare with the single-thread build)
+  static const int par_min = [] { const char *e = std::getenv("SSBA_HOST_PAR_MIN"); return e ? std::max(1, std::atoi(e)) : 0; }();
+  const int kParEdges = par_min ? par_min : 20000, kParItems = par_min ? par_min : 8192;
+  const int T = NE >= kParEdges ? pool.size() : 1;
   const int32_t *__restrict__ ge_pose = g.e_pose.data();
   const int32_t *__restrict__ ge_point = g.e_point.data();
   const uint8_t *__restrict__ ge_cam = g.e_cam.data();
@@ -1028,7 +1032,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
     // ranges, offsets in (bucket, thread) order, parallel fill - the same array a serial pass would produce
     std::vector<int32_t> bucket_cnt(n + 2, 0);
     int n_act_pts = 0;
-    const int TB = NP >= 8192 ? T : 1;
+    const int TB = NP >= kParItems ? T : 1;
     std::vector<std::vector<int32_t>> t_hist(TB);
     pool.run(TB, [&](int t, int TT) {
       int j0, j1; split_range(t, TT, NP, j0, j1);
@@ -1107,7 +1111,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   {
     // two parallel passes: the counts of every slot (random reads by landmark) and the totals of every thread's
     // range, then the prefix sums of the range on top of the totals before it
-    const int TS = s.n_slots >= 8192 ? T : 1;
+    const int TS = s.n_slots >= kParItems ? T : 1;
     std::vector<long long> t_edges(TS + 1, 0), t_pairs(TS + 1, 0), t_free(TS + 1, 0);
     int32_t *sep = slot_edge_ptr.data(), *spp = s.slot_pair_ptr.data();
     pool.run(TS, [&](int t, int TT) {

@@ -315,14 +315,33 @@ bool build_tree_program(int n, const std::vector<int32_t> &col_ptr, const std::v
       default: return CV0[p.owner] + 6 * p.dkey;
     }
   };
-  std::sort(prods.begin(), prods.end(), [](const Prod &x, const Prod &y) {
-    if (x.owner != y.owner) return x.owner < y.owner;
-    if (x.step != y.step) return x.step < y.step;
-    if (x.critical != y.critical) return x.critical > y.critical;
-    if (x.dkind != y.dkind) return x.dkind < y.dkind;
-    if (x.dkey != y.dkey) return x.dkey < y.dkey;
-    return x.k < y.k;  // summation order of a destination: by source column
-  });
+  {
+    // order: owner, step, critical first, destination kind, destination, source column (= the summation order of a
+    // destination) - packed into one 64-bit key per product, sorted with its index, then applied
+    std::vector<std::pair<uint64_t, uint32_t>> keys(prods.size());
+    bool packable = true;
+    for (size_t i = 0; i < prods.size(); ++i) {
+      const Prod &x = prods[i];
+      if (x.owner >= 32 || x.step >= 4096 || x.dkey >= (1 << 24) || x.k >= (1 << 20) || x.step < 0 || x.dkey < 0) { packable = false; break; }
+      keys[i] = {((uint64_t)x.owner << 59) | ((uint64_t)x.step << 47) | ((uint64_t)(x.critical ? 0 : 1) << 46) | ((uint64_t)x.dkind << 44) |
+                 ((uint64_t)x.dkey << 20) | (uint64_t)x.k, (uint32_t)i};
+    }
+    if (packable) {
+      std::sort(keys.begin(), keys.end());
+      std::vector<Prod> sorted(prods.size());
+      for (size_t i = 0; i < keys.size(); ++i) sorted[i] = prods[keys[i].second];
+      prods.swap(sorted);
+    } else {
+      std::sort(prods.begin(), prods.end(), [](const Prod &x, const Prod &y) {
+        if (x.owner != y.owner) return x.owner < y.owner;
+        if (x.step != y.step) return x.step < y.step;
+        if (x.critical != y.critical) return x.critical > y.critical;
+        if (x.dkind != y.dkind) return x.dkind < y.dkind;
+        if (x.dkey != y.dkey) return x.dkey < y.dkey;
+        return x.k < y.k;  // summation order of a destination: by source column
+      });
+    }
+  }
   // ---- emit the program of every CTA
   size_t pi = 0;
   tp.words.clear();

@@ -31,3 +31,21 @@ def test_structure_builder_cpp():
             r = subprocess.run([exe], capture_output=True, text=True, env=env)
             assert r.returncode == 0, f"solver={solver or 'tree'} cap={cap} cluster={cluster or 'default'}\n" + r.stdout + r.stderr
             assert r.stdout.strip().endswith("OK")
+
+
+def test_structure_build_is_independent_of_the_thread_count():
+    """The parallel passes of build_structure (forced on for the small test graphs with SSBA_HOST_PAR_MIN) give the
+    same structures, programs and statistics as the single-thread build: the report of the C++ test is identical."""
+    exe = "/tmp/ssba_test_structure"
+    if not os.path.exists(exe):
+        test_structure_builder_cpp()
+    outs = []
+    for threads, par_min in (("1", ""), ("4", "64"), ("7", "64")):
+        env = dict(os.environ)
+        env["SSBA_HOST_THREADS"] = threads
+        if par_min:
+            env["SSBA_HOST_PAR_MIN"] = par_min
+        r = subprocess.run([exe], capture_output=True, text=True, env=env)
+        assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout[-2000:] + r.stderr[-2000:]
+        outs.append(r.stdout)
+    assert outs[0] == outs[1] == outs[2]
