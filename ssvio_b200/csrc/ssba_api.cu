@@ -949,6 +949,22 @@ ssba_status ssba_step(ssba_handle *h, int32_t iteration, int32_t *solver_result,
   return SSBA_OK;
 }
 
+// Device -> caller's (pageable) buffer through the handle's pinned staging buffer: one DMA at PCIe speed, then a host
+// copy (threaded when large), instead of the driver's chunked staging of a pageable destination.  The staging buffer
+// is idle whenever a read-out can run (ssba_initialize waits for its upload).
+static ssba_status d2h(ssba_handle *h, void *out, const void *src, size_t bytes) {
+  if (bytes == 0) return SSBA_OK;
+  if (h->h_stage && bytes <= h->h_stage_bytes) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_stage, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (bytes >= (1u << 20)) parallel_copy({{out, h->h_stage, bytes}}); else std::memcpy(out, h->h_stage, bytes);
+    return SSBA_OK;
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return SSBA_OK;
+}
+
 ssba_status ssba_get_poses(ssba_handle *h, double *out) {
   if (!h || !out) return SSBA_ERR_INVALID_ARG;
   if (!h->initialized || h->dirty) {  // nothing ran on the graph as it is now: the estimates are the ones that were set
@@ -957,9 +973,7 @@ ssba_status ssba_get_poses(ssba_handle *h, double *out) {
     return SSBA_OK;
   }
   CUDA_TRY(h, cudaSetDevice(h->device));
-  CUDA_TRY(h, cudaMemcpyAsync(out, h->P.pose[h->cur], 7 * sizeof(double) * (size_t)h->P.n_poses, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  return SSBA_OK;
+  return d2h(h, out, h->P.pose[h->cur], 7 * sizeof(double) * (size_t)h->P.n_poses);
 }
 
 ssba_status ssba_get_points(ssba_handle *h, double *out) {
@@ -977,13 +991,9 @@ ssba_status ssba_get_points(ssba_handle *h, double *out) {
     h->prof.kernel_launches += 1;
     ssba_status rc = nccl_allreduce(h, h->P.gather, 3 * (size_t)h->P.n_points, kNcclSum);
     if (rc) return rc;
-    CUDA_TRY(h, cudaMemcpyAsync(out, h->P.gather, 3 * sizeof(double) * (size_t)h->P.n_points, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    return SSBA_OK;
+    return d2h(h, out, h->P.gather, 3 * sizeof(double) * (size_t)h->P.n_points);
   }
-  CUDA_TRY(h, cudaMemcpyAsync(out, h->P.point[h->cur], 3 * sizeof(double) * (size_t)h->P.n_points, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  return SSBA_OK;
+  return d2h(h, out, h->P.point[h->cur], 3 * sizeof(double) * (size_t)h->P.n_points);
 }
 
 ssba_status ssba_get_edge_errors(ssba_handle *h, double *out) {
@@ -996,9 +1006,7 @@ ssba_status ssba_get_edge_errors(ssba_handle *h, double *out) {
   h->prof.kernel_launches += 1;
   // replicated input: every edge lives on exactly one rank, the sum is the union; pre-sharded input: the edges are this rank's own
   if (h->opt.world_size > 1 && !h->opt.presharded) { rc = nccl_allreduce(h, h->P.err_out, 2 * (size_t)h->P.n_edges_total, kNcclSum); if (rc) return rc; }
-  CUDA_TRY(h, cudaMemcpyAsync(out, h->P.err_out, bytes, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  return SSBA_OK;
+  return d2h(h, out, h->P.err_out, bytes);
 }
 
 ssba_status ssba_chi2(ssba_handle *h, double *plain, double *robust) {
