@@ -899,21 +899,22 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
   for (int i = 0; i < NK; ++i)
     if (pose_active[i] && !pfix[i]) { fp_of_pose[i] = (int)free_pose_rows.size(); free_pose_rows.push_back(i); }
   s.n_fp = (int)free_pose_rows.size();
-  s.n_fl_global = 0;
-  for (int j = 0; j < NP; ++j)
-    if ((across_ranks ? s.point_active[j] : point_active[j]) && !lfix[j]) ++s.n_fl_global;
   const int n = s.n_fp;
 
-  // ---- edges by landmark (CSR over point rows, stable = addEdge order inside a landmark)
+  // ---- edges by landmark (CSR over point rows, stable = addEdge order inside a landmark), and the number of free
+  // landmarks, in one sweep over the landmarks
   std::vector<int32_t> pt_ptr(NP + 1, 0);
-  for (int j = 0; j < NP; ++j) pt_ptr[j + 1] = pt_ptr[j] + point_deg[j];
+  {
+    const uint8_t *act = across_ranks ? s.point_active.data() : point_active.data();
+    int nfl = 0;
+    for (int j = 0; j < NP; ++j) { pt_ptr[j + 1] = pt_ptr[j] + point_deg[j]; nfl += act[j] && !lfix[j]; }
+    s.n_fl_global = nfl;
+  }
   uvec<int32_t> pt_edges(n_active);
-  if (edges_by_landmark && n_active == NE) {  // the order ssvio's back-end adds them in: nothing to sort
-    pool.run(T, [&](int t, int TT) {
-      int e0, e1; split_range(t, TT, NE, e0, e1);
-      for (int e = e0; e < e1; ++e) pt_edges[e] = e;
-    });
-  } else {
+  // the order ssvio's back-end adds them in (grouped by landmark, all active): the list is the identity, written by
+  // the co-visibility pass below on its way through the landmarks
+  const bool identity_edges = edges_by_landmark && n_active == NE;
+  if (!identity_edges) {
     std::vector<int32_t> fill(pt_ptr.begin(), pt_ptr.end() - 1);
     for (int e = 0; e < NE; ++e)
       if (edge_active[e]) pt_edges[fill[ge_point[e]]++] = e;
@@ -950,6 +951,7 @@ bool build_structure(const HostGraph &g, int rank, int world, Structure &s, std:
       int *lst = ql, *fst = fl, cnt = 0, fcnt = 0;  // distinct free poses (free-pose index) / fixed poses (row)
       if (m > 64) { big.resize(m); bigf.resize(m); lst = big.data(); fst = bigf.data(); }
       for (int k = pt_ptr[j]; k < pt_ptr[j + 1]; ++k) {
+        if (identity_edges) pt_edges[k] = k;
         const int pose = ge_pose[pt_edges[k]];
         const int f = fp_of_pose[pose];
         if (f >= 0) insert_unique(lst, cnt, f); else insert_unique(fst, fcnt, pose);
