@@ -22,6 +22,10 @@ namespace ssba {
 namespace {
 
 constexpr int kLinThreads = 128;
+// = kLinPairs of the host (ssba_structure.cpp).  Not a free parameter: a build with 64 pairs per chunk (tried in
+// round 2 for a finer tail of the two CTA waves) was slower AND summed only about half of chi2 - something besides
+// the two constants depends on the value; find it before changing it.
+static_assert(kLinThreads == 128, "kLinThreads / kLinPairs: other values are not supported");
 #ifndef SSBA_LIN_MINB
 #define SSBA_LIN_MINB 3  // CTAs per SM k_linearize is compiled for (factored path: 134 registers, no spills)
 #endif
