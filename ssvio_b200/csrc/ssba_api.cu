@@ -778,7 +778,7 @@ ssba_status ssba_initialize(ssba_handle *h) {
   const int32_t *d_tree_prog = nullptr;
   stat(items_b, s.tree.words.data(), s.tree.words.size() * sizeof(int32_t), (const void **)&d_tree_prog);
   const size_t bytes_b = align_up(top) - off_b;
-  P.n_fin_blocks = (s.n_slots + 127) / 128 > 0 ? (s.n_slots + 127) / 128 : 1;
+  P.n_fin_blocks = std::max(1, (s.n_slots + kReadoutThreads - 1) / kReadoutThreads);
   P.n_lin_blocks = P.n_upd_blocks = s.n_lchunks;
   const int nblk = std::max(P.n_fin_blocks, s.n_lchunks);
   P.sys_doubles = 36 * (size_t)s.n_blocks + 12 * (size_t)s.n_fp;

@@ -79,6 +79,8 @@ struct __align__(16) PairRec {
   int32_t n_edges, point_row, lfree, pad;  // lfree: the landmark is free
 };
 
+constexpr int kReadoutThreads = 128;  // k_final_chi2: one thread per landmark (grid planned by ssba_initialize)
+
 struct DeviceProblem {
   Cameras cams;
   double ext_R[8][9];  // rotation matrices of the extrinsics
@@ -87,7 +89,7 @@ struct DeviceProblem {
   // sizes
   int n_poses, n_points, n_fp, n_slots, n_pairs, n_edges, n_blocks, n_hpp_parts, n_levels;
   int n_lin_blocks, n_upd_blocks;  // grids of k_linearize / k_update = lengths of their partial-sum arrays
-  int n_fin_blocks;                // grid of the thread-per-landmark read-out kernel
+  int n_fin_blocks;                // grid of the thread-per-landmark read-out kernel (kReadoutThreads landmarks per CTA)
   // estimates: two buffers each (current / trial), selected by Control::cur
   double *pose[2];    // n_poses x 7
   double *point[2];   // n_points x 3

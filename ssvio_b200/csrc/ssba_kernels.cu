@@ -22,10 +22,9 @@ namespace ssba {
 namespace {
 
 constexpr int kLinThreads = 128;
-// = kLinPairs of the host (ssba_structure.cpp).  Not a free parameter: a build with 64 pairs per chunk (tried in
-// round 2 for a finer tail of the two CTA waves) was slower AND summed only about half of chi2 - something besides
-// the two constants depends on the value; find it before changing it.
-static_assert(kLinThreads == 128, "kLinThreads / kLinPairs: other values are not supported");
+// = kLinPairs of the host (ssba_structure.cpp): the two must be changed together.  (64 pairs per chunk, tried in
+// round 2 for a finer tail of the two CTA waves: update 32.4 -> 33.0 us, schur + fold 28.5 -> 33.9 us - not kept.)
+static_assert(kLinThreads == 128, "kLinThreads must equal kLinPairs of ssba_structure.cpp");
 #ifndef SSBA_LIN_MINB
 #define SSBA_LIN_MINB 3  // CTAs per SM k_linearize is compiled for (factored path: 134 registers, no spills)
 #endif
@@ -1694,9 +1693,9 @@ __global__ void __launch_bounds__(256) k_control_p2p(const DeviceProblem P, int 
 // ---------------------------------------------------------------------------------------------
 // final read-outs at the current estimate: activeChi2 / activeRobustChi2
 // (sparse_optimizer.cpp:92-116), the outlier count of backend.cpp:180-197, per-edge errors.
-__global__ void __launch_bounds__(kLinThreads) k_final_chi2(const DeviceProblem P, double threshold,
-                                                            int write_errors) {
-  __shared__ double red[kLinThreads / 32];
+__global__ void __launch_bounds__(kReadoutThreads) k_final_chi2(const DeviceProblem P, double threshold,
+                                                                int write_errors) {
+  __shared__ double red[kReadoutThreads / 32];
   const int cur = P.ctl->cur;
   const double *__restrict__ pose = P.pose[cur];
   const double *__restrict__ point = P.point[cur];
@@ -1725,10 +1724,10 @@ __global__ void __launch_bounds__(kLinThreads) k_final_chi2(const DeviceProblem 
       }
     }
   }
-  const double a = block_sum<kLinThreads>(plain, red);
-  const double b = block_sum<kLinThreads>(robust, red);
-  const double c = block_sum<kLinThreads>(nout, red);
-  const double d = block_sum<kLinThreads>(nin, red);
+  const double a = block_sum<kReadoutThreads>(plain, red);
+  const double b = block_sum<kReadoutThreads>(robust, red);
+  const double c = block_sum<kReadoutThreads>(nout, red);
+  const double d = block_sum<kReadoutThreads>(nin, red);
   if (threadIdx.x == 0) {
     // the partial arrays of the LM loop are free at this point
     P.chi_cur_part[blockIdx.x] = a; P.maxdiag_part[blockIdx.x] = b;
@@ -2089,7 +2088,7 @@ void launch_exchange_sys(const DeviceProblem &P, cudaStream_t st) {
 void launch_control_p2p(const DeviceProblem &P, cudaStream_t st) { k_control_p2p<<<1, 256, 0, st>>>(P, update_linearizes(P) ? 1 : 0); }
 
 void launch_final_chi2(const DeviceProblem &P, double threshold, cudaStream_t st) {
-  k_final_chi2<<<P.n_fin_blocks, kLinThreads, 0, st>>>(P, threshold, 0);
+  k_final_chi2<<<P.n_fin_blocks, kReadoutThreads, 0, st>>>(P, threshold, 0);
   k_final_reduce<<<1, 256, 0, st>>>(P);
 }
 
@@ -2108,11 +2107,11 @@ void launch_gather_points(const DeviceProblem &P, cudaStream_t st) {
 }
 
 void launch_edge_errors(const DeviceProblem &P, cudaStream_t st) {
-  k_final_chi2<<<P.n_fin_blocks, kLinThreads, 0, st>>>(P, 0.0, 1);
+  k_final_chi2<<<P.n_fin_blocks, kReadoutThreads, 0, st>>>(P, 0.0, 1);
 }
 
 void launch_outlier_mask(const DeviceProblem &P, double threshold, cudaStream_t st) {
-  k_final_chi2<<<P.n_fin_blocks, kLinThreads, 0, st>>>(P, threshold, 2);
+  k_final_chi2<<<P.n_fin_blocks, kReadoutThreads, 0, st>>>(P, threshold, 2);
   k_final_reduce<<<1, 256, 0, st>>>(P);
 }
 
