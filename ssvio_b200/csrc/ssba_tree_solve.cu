@@ -9,7 +9,7 @@
 // Data movement: the CTA's slice of the reduced system (its factor blocks, right-hand sides, b_p) and its
 // whole program arrive with four bulk asynchronous copies (TMA, cp.async.bulk) on one mbarrier; from then
 // on every operand is a shared-memory load.  Two cluster barriers per solve (contributions up, top solution
-// down); two __syncthreads per elimination step.
+// down); one block barrier per forward step (plus a named barrier of the look-ahead warps), one per backward step.
 #include <atomic>
 
 #include "ssba_device.hpp"
