@@ -327,9 +327,22 @@ bool build_tree_program(int n, const std::vector<int32_t> &col_ptr, const std::v
                  ((uint64_t)x.dkey << 20) | (uint64_t)x.k, (uint32_t)i};
     }
     if (packable) {
-      std::sort(keys.begin(), keys.end());
+      // bucket by (owner, step) - the top 17 bits of the key - with a counting sort, then sort the (small) buckets
+      int max_step = 0;
+      for (const Prod &x : prods) max_step = std::max(max_step, x.step);
+      const int n_steps = max_step + 1;
+      std::vector<uint32_t> bucket_ptr((size_t)C * n_steps + 1, 0);
+      for (const Prod &x : prods) ++bucket_ptr[(size_t)x.owner * n_steps + x.step + 1];
+      for (size_t b = 0; b + 1 < bucket_ptr.size(); ++b) bucket_ptr[b + 1] += bucket_ptr[b];
+      std::vector<std::pair<uint64_t, uint32_t>> scattered(keys.size());
+      {
+        std::vector<uint32_t> fill(bucket_ptr.begin(), bucket_ptr.end() - 1);
+        for (size_t i = 0; i < prods.size(); ++i) scattered[fill[(size_t)prods[i].owner * n_steps + prods[i].step]++] = keys[i];
+      }
+      for (size_t b = 0; b + 1 < bucket_ptr.size(); ++b)
+        if (bucket_ptr[b + 1] - bucket_ptr[b] > 1) std::sort(scattered.begin() + bucket_ptr[b], scattered.begin() + bucket_ptr[b + 1]);
       std::vector<Prod> sorted(prods.size());
-      for (size_t i = 0; i < keys.size(); ++i) sorted[i] = prods[keys[i].second];
+      for (size_t i = 0; i < scattered.size(); ++i) sorted[i] = prods[scattered[i].second];
       prods.swap(sorted);
     } else {
       std::sort(prods.begin(), prods.end(), [](const Prod &x, const Prod &y) {
